@@ -1,0 +1,15 @@
+"""Hot ops: native sm_100a kernels on CUDA tensors, torch reference on CPU tensors."""
+
+from . import reference  # noqa: F401
+from .functional import (  # noqa: F401
+    add_rmsnorm,
+    attention,
+    cross_entropy,
+    gemm,
+    launch_count,
+    linear,
+    reset_launch_count,
+    rmsnorm,
+    rope_qkv,
+    swiglu,
+)

@@ -1,0 +1,366 @@
+"""Public op surface.  CUDA tensors → hand-written sm_100a kernels (required, loud failure);
+CPU tensors → the torch reference in :mod:`prime_b200.ops.reference`.
+
+Every CUDA op is a ``torch.autograd.Function`` whose forward/backward launch kernels from the
+native library on the *current* torch stream (so they compose with streams and CUDA graphs).
+``launch_count()`` reports how many native kernels were launched — bench.py's ``gpu_launches``.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib, reference
+
+_LAUNCHES = 0
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def reset_launch_count() -> None:
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+def _count(n: int = 1) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------- GEMM
+
+
+def gemm(
+    a: torch.Tensor,
+    b: torch.Tensor,
+    *,
+    a_mn_major: bool = False,
+    b_mn_major: bool = False,
+    out: torch.Tensor | None = None,
+    out_dtype: torch.dtype = torch.bfloat16,
+    accumulate: bool = False,
+    max_ctas: int = 0,
+) -> torch.Tensor:
+    """C[M,N] (+)= A·Bᵀ on the tcgen05 kernel.
+
+    ``a``: [M,K] (K-major) or, if ``a_mn_major``, stored [K,M].
+    ``b``: [N,K] (K-major) or, if ``b_mn_major``, stored [K,N].
+    Both must be 2-D bf16 with unit inner stride.
+    """
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    if a_mn_major:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn_major:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    assert K == Kb, f"contraction mismatch {K} vs {Kb}"
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    else:
+        assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    lib = _lib.load()
+    rc = lib.pb_gemm_bf16(
+        a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0), out.stride(0),
+        int(a_mn_major), int(b_mn_major), int(out.dtype == torch.float32), int(accumulate), max_ctas, _stream(),
+    )  # fmt: skip
+    _lib.check(rc, "pb_gemm_bf16")
+    _count()
+    return out
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x Wᵀ.  Weight gradient accumulates straight into ``weight.main_grad`` (fp32, fused in the GEMM
+    epilogue) when the FSDP engine has attached one; otherwise a bf16 gradient is returned."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        ctx.save_for_backward(x2, weight)
+        ctx.x_shape = x.shape
+        y = gemm(x2, weight)
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        x2, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy2, weight, b_mn_major=True).view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            main_grad = getattr(weight, "main_grad", None)
+            if main_grad is not None:
+                gemm(dy2, x2, a_mn_major=True, b_mn_major=True, out=main_grad, accumulate=True)
+                dw = None
+            else:
+                dw = gemm(dy2, x2, a_mn_major=True, b_mn_major=True)
+        return dx, dw
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    if x.is_cuda:
+        return _LinearFn.apply(x, weight)
+    return reference.linear(x, weight)
+
+
+# --------------------------------------------------------------------------- RMSNorm
+
+
+def _accumulate_param_grad(param: torch.Tensor, grad_fp32: torch.Tensor | None):
+    """Helper for ops that produce fp32 weight grads."""
+    return None if grad_fp32 is None else grad_fp32.to(param.dtype)
+
+
+class _RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, eps):
+        lib = _lib.load()
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        R = x2.shape[0]
+        y = torch.empty_like(x2)
+        rstd = torch.empty(R, dtype=torch.float32, device=x.device)
+        if residual is not None:
+            r2 = residual.reshape(-1, D)
+            r2 = r2 if r2.is_contiguous() else r2.contiguous()
+            h = torch.empty_like(x2)
+        else:
+            r2, h = None, x2
+        rc = lib.pb_rmsnorm_fwd(_ptr(x2), _ptr(r2), _ptr(weight), _ptr(y), _ptr(h) if residual is not None else None,
+                                _ptr(rstd), R, D, float(eps), _stream())  # fmt: skip
+        _lib.check(rc, "pb_rmsnorm_fwd")
+        _count()
+        ctx.save_for_backward(h, weight, rstd)
+        ctx.has_res = residual is not None
+        ctx.shape = x.shape
+        if residual is not None:
+            return y.view(x.shape), h.view(x.shape)
+        return y.view(x.shape), None
+
+    @staticmethod
+    def backward(ctx, dy, dh):
+        lib = _lib.load()
+        h, weight, rstd = ctx.saved_tensors
+        R, D = h.shape
+        dy2 = dy.reshape(R, D)
+        dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
+        dres = None
+        if dh is not None:
+            dres = dh.reshape(R, D)
+            dres = dres if dres.is_contiguous() else dres.contiguous()
+        dx = torch.empty_like(h)
+        grid = lib.pb_rmsnorm_bwd_grid(R)
+        partial = torch.empty((grid, D), dtype=torch.float32, device=h.device)
+        main_grad = getattr(weight, "main_grad", None)
+        if main_grad is not None:
+            dw32, acc = main_grad, 1
+        else:
+            dw32, acc = torch.empty(D, dtype=torch.float32, device=h.device), 0
+        rc = lib.pb_rmsnorm_bwd(_ptr(dy2), _ptr(h), _ptr(weight), _ptr(rstd), _ptr(dres), _ptr(dx), _ptr(partial),
+                                _ptr(dw32), acc, R, D, _stream())  # fmt: skip
+        _lib.check(rc, "pb_rmsnorm_bwd")
+        _count(2)
+        dxv = dx.view(ctx.shape)
+        dw = None if main_grad is not None else dw32.to(weight.dtype)
+        # residual-add backward: gradient flows identically to x and residual
+        return dxv, (dxv if ctx.has_res else None), dw, None
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    if x.is_cuda:
+        return _RMSNormFn.apply(x, None, weight, eps)[0]
+    return reference.rmsnorm(x, weight, eps)
+
+
+def add_rmsnorm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, eps: float = 1e-5):
+    """(rmsnorm(x + residual), x + residual) in one pass over HBM."""
+    if x.is_cuda:
+        return _RMSNormFn.apply(x, residual, weight, eps)
+    return reference.add_rmsnorm(x, residual, weight, eps)
+
+
+# --------------------------------------------------------------------------- RoPE (in place on fused QKV)
+
+
+class _RopeQKVFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, cos, sin, n_heads, n_kv_heads, seq_len):
+        # qkv: [B, S, (H + 2*Hkv) * D] contiguous, produced by the QKV GEMM → rotate in place
+        lib = _lib.load()
+        total_heads = n_heads + 2 * n_kv_heads
+        D = qkv.shape[-1] // total_heads
+        tokens = qkv.numel() // qkv.shape[-1]
+        assert qkv.is_contiguous()
+        rc = lib.pb_rope_inplace(_ptr(qkv), _ptr(cos), _ptr(sin), tokens, seq_len, n_heads + n_kv_heads, total_heads, D,
+                                 1.0, _stream())  # fmt: skip
+        _lib.check(rc, "pb_rope_inplace")
+        _count()
+        ctx.mark_dirty(qkv)
+        ctx.save_for_backward(cos, sin)
+        ctx.meta = (n_heads, n_kv_heads, seq_len, D, total_heads)
+        return qkv
+
+    @staticmethod
+    def backward(ctx, dqkv):
+        lib = _lib.load()
+        cos, sin = ctx.saved_tensors
+        n_heads, n_kv_heads, seq_len, D, total_heads = ctx.meta
+        dqkv = dqkv if dqkv.is_contiguous() else dqkv.contiguous()
+        tokens = dqkv.numel() // dqkv.shape[-1]
+        # rotation is orthogonal: the backward is the inverse rotation, applied in place on the incoming grad
+        rc = lib.pb_rope_inplace(_ptr(dqkv), _ptr(cos), _ptr(sin), tokens, seq_len, n_heads + n_kv_heads, total_heads, D,
+                                 -1.0, _stream())  # fmt: skip
+        _lib.check(rc, "pb_rope_inplace(bwd)")
+        _count()
+        return dqkv, None, None, None, None, None
+
+
+def rope_qkv(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, n_kv_heads: int) -> torch.Tensor:
+    """Rotate the Q and K heads of a fused [B,S,(H+2Hkv)·D] activation."""
+    B, S, W = qkv.shape
+    if qkv.is_cuda:
+        return _RopeQKVFn.apply(qkv, cos, sin, n_heads, n_kv_heads, S)
+    D = W // (n_heads + 2 * n_kv_heads)
+    x = qkv.view(B, S, n_heads + 2 * n_kv_heads, D)
+    rot = reference.rope(x[:, :, : n_heads + n_kv_heads], cos, sin)
+    return torch.cat((rot, x[:, :, n_heads + n_kv_heads :]), dim=2).view(B, S, W)
+
+
+# --------------------------------------------------------------------------- SwiGLU
+
+
+class _SwiGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate_up):
+        lib = _lib.load()
+        F2 = gate_up.shape[-1]
+        gu = gate_up.reshape(-1, F2)
+        gu = gu if gu.is_contiguous() else gu.contiguous()
+        out = torch.empty((gu.shape[0], F2 // 2), dtype=gu.dtype, device=gu.device)
+        rc = lib.pb_swiglu_fwd(_ptr(gu), _ptr(out), gu.shape[0], F2 // 2, _stream())
+        _lib.check(rc, "pb_swiglu_fwd")
+        _count()
+        ctx.save_for_backward(gu)
+        ctx.shape = gate_up.shape
+        return out.view(*gate_up.shape[:-1], F2 // 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        (gu,) = ctx.saved_tensors
+        d2 = dout.reshape(gu.shape[0], -1)
+        d2 = d2 if d2.is_contiguous() else d2.contiguous()
+        dgu = torch.empty_like(gu)
+        rc = lib.pb_swiglu_bwd(_ptr(gu), _ptr(d2), _ptr(dgu), gu.shape[0], gu.shape[1] // 2, _stream())
+        _lib.check(rc, "pb_swiglu_bwd")
+        _count()
+        return dgu.view(ctx.shape)
+
+
+def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
+    if gate_up.is_cuda:
+        return _SwiGLUFn.apply(gate_up)
+    return reference.swiglu(gate_up)
+
+
+# --------------------------------------------------------------------------- cross entropy
+
+
+class _CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, ignore_index, grad_scale, unit_upstream):
+        lib = _lib.load()
+        V = logits.shape[-1]
+        z = logits.reshape(-1, V)
+        assert z.is_contiguous()
+        t = targets.reshape(-1)
+        R = z.shape[0]
+        n_valid = (t != ignore_index).sum().clamp_(min=1).to(torch.float32)
+        scale = (1.0 / n_valid).reshape(1)
+        kscale = scale * grad_scale if grad_scale != 1.0 else scale
+        losses = torch.empty(R, dtype=torch.float32, device=z.device)
+        # logits are overwritten with d(mean loss)/d(logits): nothing else needs them afterwards
+        rc = lib.pb_cross_entropy_fwd_bwd(_ptr(z), _ptr(t), _ptr(losses), _ptr(kscale), R, V, ignore_index, _stream())
+        _lib.check(rc, "pb_cross_entropy_fwd_bwd")
+        _count()
+        ctx.mark_dirty(logits)
+        ctx.save_for_backward(z)
+        ctx.shape = logits.shape
+        ctx.unit_upstream = unit_upstream
+        return (losses.sum() * scale).reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dz,) = ctx.saved_tensors
+        # dz already holds the gradient for dloss == 1; rescale for loss scaling / grad accumulation
+        if not ctx.unit_upstream:
+            dz = dz * dloss.to(dz.dtype)
+        return dz.view(ctx.shape), None, None, None, None
+
+
+def cross_entropy(
+    logits: torch.Tensor,
+    targets: torch.Tensor,
+    ignore_index: int = -100,
+    *,
+    grad_scale: float = 1.0,
+    unit_upstream: bool = False,
+) -> torch.Tensor:
+    """Mean token cross-entropy.  On CUDA the logits buffer is consumed (overwritten with its gradient).
+
+    ``grad_scale`` folds a gradient multiplier (e.g. 1/grad-accumulation-steps) into the fused kernel; the
+    returned loss value is NOT scaled.  ``unit_upstream=True`` promises the loss is back-propagated with a
+    unit upstream gradient, which removes one full pass over the logits gradient.
+    """
+    if logits.is_cuda:
+        return _CrossEntropyFn.apply(logits, targets, ignore_index, float(grad_scale), bool(unit_upstream))
+    loss = reference.cross_entropy(logits, targets, ignore_index)
+    if grad_scale != 1.0:
+        # same contract on CPU: value unscaled, gradient scaled
+        loss = loss.detach() + (loss - loss.detach()) * grad_scale
+    return loss
+
+
+# --------------------------------------------------------------------------- attention
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True, impl: str = "auto") -> torch.Tensor:
+    """q [B,S,H,D], k/v [B,S,Hkv,D] (may be strided views of the fused QKV buffer) → [B,S,H,D]."""
+    if not q.is_cuda:
+        return reference.attention(q, k, v, causal)
+    if impl in ("auto", "native"):
+        from . import attention as native_attn
+
+        if native_attn.supported(q, k, v):
+            return native_attn.flash_attention(q, k, v, causal)
+        if impl == "native":
+            raise RuntimeError("native flash-attention kernel does not support this shape")
+    import torch.nn.functional as F
+
+    H, Hkv = q.shape[2], k.shape[2]
+    out = F.scaled_dot_product_attention(
+        q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=causal, enable_gqa=(H != Hkv)
+    )
+    return out.transpose(1, 2)

@@ -1,0 +1,142 @@
+"""Plain-PyTorch reference implementations of every hot op.
+
+These are (a) the CPU/gloo execution path (BASELINE.json config 1) and (b) the
+fp32 numerical oracle every sm_100a kernel is tested against
+(``tests/test_kernels_gpu.py``).  Nothing here is ever selected on a CUDA
+tensor by :mod:`prime_b200.ops.functional` — on the GPU the native kernels run
+or the call fails loudly.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    xf = x.float()
+    rstd = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return (xf * rstd * weight.float()).to(x.dtype)
+
+
+def add_rmsnorm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, eps: float = 1e-5):
+    """h = x + residual ; y = rmsnorm(h).  Returns (y, h)."""
+    h = (x.float() + residual.float()).to(x.dtype)
+    return rmsnorm(h, weight, eps), h
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    return F.linear(x, weight)
+
+
+def rope_tables(seq_len: int, head_dim: int, theta: float = 10000.0, device=None) -> tuple[torch.Tensor, torch.Tensor]:
+    """cos/sin tables [seq, head_dim/2] (fp32), interleaved-pair convention (Llama reference)."""
+    freqs = 1.0 / (theta ** (torch.arange(0, head_dim, 2, device=device, dtype=torch.float32) / head_dim))
+    t = torch.arange(seq_len, device=device, dtype=torch.float32)
+    ang = torch.outer(t, freqs)
+    return ang.cos(), ang.sin()
+
+
+def rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """x: [B, S, H, D]; rotates interleaved pairs (x[2i], x[2i+1])."""
+    B, S, H, D = x.shape
+    xf = x.float().reshape(B, S, H, D // 2, 2)
+    c = cos[:S].view(1, S, 1, D // 2)
+    s = sin[:S].view(1, S, 1, D // 2)
+    x0, x1 = xf[..., 0], xf[..., 1]
+    out = torch.stack((x0 * c - x1 * s, x0 * s + x1 * c), dim=-1)
+    return out.reshape(B, S, H, D).to(x.dtype)
+
+
+def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
+    """gate_up: [..., 2*F] = concat(gate, up) → silu(gate) * up."""
+    g, u = gate_up.float().chunk(2, dim=-1)
+    return (F.silu(g) * u).to(gate_up.dtype)
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True) -> torch.Tensor:
+    """q: [B, S, H, D]; k/v: [B, S, Hkv, D] → [B, S, H, D]."""
+    B, S, H, D = q.shape
+    Hkv = k.shape[2]
+    qf, kf, vf = (t.float().transpose(1, 2) for t in (q, k, v))
+    if Hkv != H:
+        kf = kf.repeat_interleave(H // Hkv, dim=1)
+        vf = vf.repeat_interleave(H // Hkv, dim=1)
+    scores = qf @ kf.transpose(-1, -2) / math.sqrt(D)
+    if causal:
+        mask = torch.ones(S, S, dtype=torch.bool, device=q.device).tril()
+        scores = scores.masked_fill(~mask, float("-inf"))
+    out = scores.softmax(-1) @ vf
+    return out.transpose(1, 2).to(q.dtype)
+
+
+def cross_entropy(logits: torch.Tensor, targets: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    return F.cross_entropy(logits.float().view(-1, logits.shape[-1]), targets.view(-1), ignore_index=ignore_index)
+
+
+def adamw_step(
+    p: torch.Tensor,
+    g: torch.Tensor,
+    m: torch.Tensor,
+    v: torch.Tensor,
+    *,
+    lr: float,
+    beta1: float,
+    beta2: float,
+    eps: float,
+    weight_decay: float,
+    step: int,
+    grad_scale: float = 1.0,
+) -> None:
+    """In-place decoupled AdamW on fp32 master tensors (torch.optim.AdamW semantics)."""
+    g = g.float() * grad_scale
+    p.mul_(1.0 - lr * weight_decay)
+    m.mul_(beta1).add_(g, alpha=1.0 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+    bc1 = 1.0 - beta1**step
+    bc2 = 1.0 - beta2**step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+def quantize_int8_blockwise(x: torch.Tensor, block: int = 1024) -> tuple[torch.Tensor, torch.Tensor]:
+    """Symmetric per-block int8: returns (q int8 [n], scales fp32 [ceil(n/block)])."""
+    n = x.numel()
+    nb = (n + block - 1) // block
+    pad = nb * block - n
+    xf = x.float().reshape(-1)
+    if pad:
+        xf = F.pad(xf, (0, pad))
+    xb = xf.view(nb, block)
+    amax = xb.abs().amax(dim=1)
+    scale = amax / 127.0
+    inv = torch.where(scale > 0, 1.0 / scale, torch.zeros_like(scale))
+    q = torch.clamp(torch.round(xb * inv[:, None]), -127, 127).to(torch.int8)
+    return q.view(-1)[:n].contiguous(), scale
+
+
+def dequantize_int8_blockwise(q: torch.Tensor, scale: torch.Tensor, block: int = 1024) -> torch.Tensor:
+    n = q.numel()
+    nb = scale.numel()
+    pad = nb * block - n
+    qf = q.float()
+    if pad:
+        qf = F.pad(qf, (0, pad))
+    return (qf.view(nb, block) * scale[:, None]).view(-1)[:n]
+
+
+def nesterov_outer_step(
+    theta0: torch.Tensor,
+    avg_pseudo_grad: torch.Tensor,
+    momentum_buf: torch.Tensor,
+    *,
+    lr: float,
+    momentum: float,
+    nesterov: bool = True,
+) -> None:
+    """torch.optim.SGD(nesterov=True) semantics, in place on fp32 theta0 / momentum."""
+    momentum_buf.mul_(momentum).add_(avg_pseudo_grad)
+    step = avg_pseudo_grad + momentum * momentum_buf if nesterov else momentum_buf
+    theta0.add_(step, alpha=-lr)

@@ -1,0 +1,129 @@
+"""Trainer: the public training API (``Trainer(cfg).step()``) behind ``diloco.train`` and ``bench.py``.
+
+One *inner step* = ``accum`` micro-batches of forward/backward (gradients accumulate in fp32 in the
+GEMM epilogues) → bucketed gradient reduce-scatter → clip → partitioned AdamW → parameter all-gather.
+Every ``diloco.inner_steps`` inner steps the outer optimizer runs (int8 pseudo-gradient all-reduce
+across workers ⊕ Nesterov).
+"""
+
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+from .config import Config
+from .data import Batch, PinnedPrefetcher, build_dataset
+from .models.llama import Transformer, build_model
+from .optim.schedule import lr_at
+from .parallel.diloco import DilocoOuter, OuterHyper
+from .parallel.fsdp import AdamHyper, ShardedEngine
+from .parallel.mesh import Mesh, WorldInfo, build_mesh, init_distributed
+
+
+@dataclass
+class StepResult:
+    loss: torch.Tensor  # device scalar, mean over micro-batches of this rank
+    lr: float
+    grad_norm: torch.Tensor | None
+    tokens: int  # tokens consumed by the WHOLE job in this step
+    did_outer: bool
+
+
+class Trainer:
+    def __init__(self, cfg: Config, *, mesh: Mesh | None = None, model_overrides: dict | None = None):
+        self.cfg = cfg
+        if mesh is None:
+            world = init_distributed(cfg.mesh.backend) if (_env_world() > 1 or dist.is_initialized()) else WorldInfo.from_env()
+            if torch.cuda.is_available():
+                torch.cuda.set_device(world.local_rank)
+            mesh = build_mesh(world, cfg.mesh.num_workers, cfg.mesh.fsdp_size)
+        self.mesh = mesh
+        self.device = mesh.device
+        cuda = self.device.type == "cuda"
+        torch.manual_seed(cfg.seed)
+        dtype = torch.bfloat16 if cuda else torch.float32
+        overrides = dict(model_overrides or {})
+        overrides.setdefault("max_seq_len", max(cfg.data.seq_length, 128))
+        # identical init on every rank (same seed) — workers start from the same θ₀
+        self.model: Transformer = build_model(cfg.name_model, cfg.type_model, device=self.device, dtype=dtype, seed=cfg.seed, **overrides)
+        self.model.attn_impl = cfg.train.attn_impl
+
+        self.heap = None
+        use_fused = cuda and cfg.train.fused_comm
+        if use_fused:
+            from .parallel.symm import SymmetricHeap, dist_exchange
+
+            n = sum(p.numel() for p in self.model.parameters())
+            pad = (len(list(self.model.parameters())) + 64) * 8 + (self.model.args.n_layers + 3) * mesh.fsdp_size * 1024
+            total = n + pad
+            nbytes = total * 6 + (total // mesh.fsdp_size) * 2 + (64 << 20)
+            self.heap = SymmetricHeap(nbytes, mesh.world.rank, mesh.world.world_size, dist_exchange(), self.device)
+
+        o = cfg.optim
+        hyper = AdamHyper(o.optim.lr, o.optim.betas1, o.optim.betas2, o.optim.eps, o.optim.weight_decay,
+                          o.max_norm if o.clip_mode != "none" else 0.0)  # fmt: skip
+        self.engine = ShardedEngine(self.model, mesh, hyper, backend="fused" if use_fused else "collective", heap=self.heap)
+        self.outer: DilocoOuter | None = None
+        if cfg.diloco is not None:
+            d = cfg.diloco
+            comp = "int8" if d.compression in ("int8", "uint8") else "no"
+            self.outer = DilocoOuter(self.engine, OuterHyper(d.outer_lr, d.outer_momentum, d.nesterov, comp))
+
+        # batch plan: optim.batch_size sequences per worker per step
+        per_rank = max(1, o.batch_size // mesh.fsdp_size)
+        self.micro_bs = min(cfg.train.micro_bs, per_rank)
+        self.accum = max(1, per_rank // self.micro_bs)
+        self.tokens_per_step = self.micro_bs * self.accum * cfg.data.seq_length * mesh.world.world_size
+        self.dataset = build_dataset(cfg.data, self.model.args.vocab_size, mesh.world.rank, mesh.world.world_size)
+        self.loader = PinnedPrefetcher(self.dataset, self.micro_bs, self.device)
+        self.step_count = 0
+        self._loss_acc = torch.zeros((), dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ one optimizer step
+    def current_lr(self) -> float:
+        o = self.cfg.optim
+        return lr_at(self.step_count, base_lr=o.optim.lr, sched_type=o.sched_type, warmup_steps=o.warmup_steps,
+                     total_steps=o.total_steps, stable_steps=o.stable_steps)  # fmt: skip
+
+    def inner_step(self, batches: list[Batch] | None = None) -> StepResult:
+        eng = self.engine
+        eng.zero_grad()
+        self._loss_acc.zero_()
+        for i in range(self.accum):
+            batch = batches[i] if batches is not None else self.loader.next()
+            last = i == self.accum - 1
+            eng.set_micro_step(last)
+            loss = self.model.loss(batch.input_ids, batch.labels, grad_scale=1.0 / self.accum)
+            loss.backward()
+            if last:
+                eng.finish_backward()
+            else:
+                eng.fold_micro_grads()
+            self._loss_acc += loss.detach().float()
+        lr = self.current_lr()
+        eng.step(lr)
+        self.step_count += 1
+        did_outer = False
+        if self.outer is not None and self.step_count % self.cfg.diloco.inner_steps == 0:
+            self.outer.step()
+            did_outer = True
+        return StepResult(self._loss_acc / self.accum, lr, eng.last_grad_norm, self.tokens_per_step, did_outer)
+
+    # ------------------------------------------------------------------ helpers
+    def flops_per_step(self) -> float:
+        return self.model.flops_per_token(self.cfg.data.seq_length) * self.tokens_per_step
+
+    def close(self) -> None:
+        if self.heap is not None:
+            torch.cuda.synchronize()
+            self.heap.close()
+            self.heap = None
+
+
+def _env_world() -> int:
+    import os
+
+    return int(os.environ.get("WORLD_SIZE", "1"))

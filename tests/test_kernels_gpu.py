@@ -1,0 +1,286 @@
+"""Numerics of every native sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
+
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib_loaded():
+    from prime_b200.ops import _lib
+
+    _lib.load()  # a GPU box without the native library is a hard failure, never a silent fallback
+    yield
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (384, 1000 // 8 * 8, 136), (2048, 2048, 2048), (130, 264, 72)])
+def test_gemm_layouts(M, N, K, a_mn, b_mn):
+    from prime_b200 import ops
+
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=_dev(), dtype=torch.bfloat16)
+    B = torch.randn(N, K, device=_dev(), dtype=torch.bfloat16)
+    ref = A.float() @ B.float().t()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    out = ops.gemm(a, b, a_mn_major=a_mn, b_mn_major=b_mn)
+    torch.cuda.synchronize()
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16
+    assert _rel_err(out, ref) < 1e-2, f"rel err {_rel_err(out, ref)}"
+
+
+def test_gemm_fp32_accumulate():
+    from prime_b200 import ops
+
+    torch.manual_seed(0)
+    M, N, K = 512, 768, 1024
+    A = torch.randn(K, M, device=_dev(), dtype=torch.bfloat16)  # stored [K, M]  (dW = dyᵀ x pattern)
+    B = torch.randn(K, N, device=_dev(), dtype=torch.bfloat16)
+    C = torch.randn(M, N, device=_dev(), dtype=torch.float32)
+    ref = C + A.float().t() @ B.float()
+    ops.gemm(A, B, a_mn_major=True, b_mn_major=True, out=C, accumulate=True)
+    torch.cuda.synchronize()
+    assert _rel_err(C, ref) < 2e-3
+
+
+def test_gemm_many_tiles_persistent():
+    """More tiles than SMs, K long enough to wrap the smem ring many times, both accumulator stages in use."""
+    from prime_b200 import ops
+
+    torch.manual_seed(1)
+    M, N, K = 4096, 4096, 1024
+    A = torch.randn(M, K, device=_dev(), dtype=torch.bfloat16) * 0.1
+    B = torch.randn(N, K, device=_dev(), dtype=torch.bfloat16) * 0.1
+    out = ops.gemm(A, B)
+    ref = A.float() @ B.float().t()
+    assert _rel_err(out, ref) < 1e-2
+
+
+def test_linear_autograd_matches_torch():
+    from prime_b200 import ops
+
+    torch.manual_seed(2)
+    x = torch.randn(4, 96, 512, device=_dev(), dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.randn(1536, 512, device=_dev(), dtype=torch.bfloat16) * 0.05).requires_grad_(True)
+    y = ops.linear(x, w)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    wr = w.detach().float().requires_grad_(True)
+    yr = torch.nn.functional.linear(xr, wr)
+    yr.backward(dy.float())
+    assert _rel_err(y, yr) < 1e-2
+    assert _rel_err(x.grad, xr.grad) < 1e-2
+    assert _rel_err(w.grad, wr.grad) < 1e-2
+
+
+def test_linear_main_grad_fusion():
+    from prime_b200 import ops
+
+    torch.manual_seed(3)
+    x = torch.randn(256, 256, device=_dev(), dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.randn(512, 256, device=_dev(), dtype=torch.bfloat16) * 0.05).requires_grad_(True)
+    w.main_grad = torch.zeros(512, 256, device=_dev(), dtype=torch.float32)
+    for _ in range(2):
+        ops.linear(x, w).sum().backward()
+    assert w.grad is None
+    ref = 2 * torch.ones(256, 512, device=_dev()).t() @ x.detach().float()
+    assert _rel_err(w.main_grad, ref) < 5e-3
+
+
+# ------------------------------------------------------------------ norm / rope / swiglu / loss
+@pytest.mark.parametrize("D", [1024, 2048, 4096, 5120])
+def test_rmsnorm_fwd_bwd(D):
+    from prime_b200 import ops
+    from prime_b200.ops import reference as R
+
+    torch.manual_seed(D)
+    x = torch.randn(300, D, device=_dev(), dtype=torch.bfloat16, requires_grad=True)
+    w = (1 + 0.1 * torch.randn(D, device=_dev())).to(torch.bfloat16).requires_grad_(True)
+    y = ops.rmsnorm(x, w, 1e-5)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    yr = R.rmsnorm(xr, wr, 1e-5)
+    yr.backward(dy.float())
+    assert _rel_err(y, yr) < 1e-2
+    assert _rel_err(x.grad, xr.grad) < 1e-2
+    assert _rel_err(w.grad, wr.grad) < 2e-2
+
+
+def test_add_rmsnorm_fwd_bwd():
+    from prime_b200 import ops
+    from prime_b200.ops import reference as R
+
+    torch.manual_seed(7)
+    D = 2048
+    x = torch.randn(4, 64, D, device=_dev(), dtype=torch.bfloat16, requires_grad=True)
+    r = torch.randn(4, 64, D, device=_dev(), dtype=torch.bfloat16, requires_grad=True)
+    w = torch.ones(D, device=_dev(), dtype=torch.bfloat16, requires_grad=True)
+    y, h = ops.add_rmsnorm(x, r, w)
+    dy, dh = torch.randn_like(y), torch.randn_like(h)
+    torch.autograd.backward([y, h], [dy, dh])
+    xr, rr, wr = (t.detach().float().requires_grad_(True) for t in (x, r, w))
+    yr, hr = R.add_rmsnorm(xr, rr, wr)
+    torch.autograd.backward([yr, hr], [dy.float(), dh.float()])
+    assert _rel_err(h, hr) < 1e-2 and _rel_err(y, yr) < 1e-2
+    assert _rel_err(x.grad, xr.grad) < 1e-2 and _rel_err(r.grad, rr.grad) < 1e-2
+    assert _rel_err(w.grad, wr.grad) < 2e-2
+
+
+@pytest.mark.parametrize("H,Hkv,D", [(16, 16, 128), (8, 2, 64)])
+def test_rope_qkv(H, Hkv, D):
+    from prime_b200 import ops
+    from prime_b200.ops import reference as R
+
+    torch.manual_seed(11)
+    B, S = 2, 96
+    W = (H + 2 * Hkv) * D
+    qkv = torch.randn(B, S, W, device=_dev(), dtype=torch.bfloat16)
+    cos, sin = R.rope_tables(S, D, device=_dev())
+    base = qkv.clone().requires_grad_(True)
+    out = ops.rope_qkv(base * 1.0, cos, sin, H, Hkv)  # *1.0: non-leaf so the in-place rotate is legal
+    ref4 = qkv.float().view(B, S, H + 2 * Hkv, D)
+    ref = torch.cat((R.rope(ref4[:, :, : H + Hkv], cos, sin), ref4[:, :, H + Hkv :]), dim=2).view(B, S, W)
+    assert _rel_err(out, ref) < 1e-2
+    g = torch.randn_like(out)
+    out.backward(g)
+    g4 = g.float().view(B, S, H + 2 * Hkv, D)
+    gref = torch.cat((R.rope(g4[:, :, : H + Hkv], cos, -sin), g4[:, :, H + Hkv :]), dim=2).view(B, S, W)
+    assert _rel_err(base.grad, gref) < 1e-2
+
+
+def test_swiglu_fwd_bwd():
+    from prime_b200 import ops
+    from prime_b200.ops import reference as R
+
+    torch.manual_seed(13)
+    gu = torch.randn(200, 2 * 5632, device=_dev(), dtype=torch.bfloat16, requires_grad=True)
+    out = ops.swiglu(gu)
+    d = torch.randn_like(out)
+    out.backward(d)
+    gr = gu.detach().float().requires_grad_(True)
+    outr = R.swiglu(gr)
+    outr.backward(d.float())
+    assert _rel_err(out, outr) < 1e-2 and _rel_err(gu.grad, gr.grad) < 1e-2
+
+
+@pytest.mark.parametrize("V", [32000, 2048])
+def test_cross_entropy_fused(V):
+    from prime_b200 import ops
+
+    torch.manual_seed(17)
+    R_ = 257
+    logits = (torch.randn(R_, V, device=_dev()) * 2).to(torch.bfloat16)
+    tgt = torch.randint(0, V, (R_,), device=_dev())
+    tgt[5] = -100
+    zr = logits.float().requires_grad_(True)
+    lr = torch.nn.functional.cross_entropy(zr, tgt, ignore_index=-100)
+    lr.backward()
+    z = (logits.clone() * 1.0).requires_grad_(True)
+    zz = z * 1.0
+    loss = ops.cross_entropy(zz, tgt, grad_scale=0.5, unit_upstream=True)
+    loss.backward()
+    assert abs(float(loss) - float(lr)) < 2e-3 * max(1.0, abs(float(lr)))
+    assert _rel_err(z.grad, 0.5 * zr.grad) < 2e-2
+
+
+# ------------------------------------------------------------------ optimizer / outer kernels (single GPU, 1 "peer")
+def test_fused_engine_matches_collective_single_gpu():
+    """fused (P2P kernels with F=1) vs collective (torch ops) engines must produce the same parameters."""
+    import copy
+
+    from prime_b200.models.llama import build_model
+    from prime_b200.parallel.fsdp import AdamHyper, ShardedEngine
+    from prime_b200.parallel.mesh import WorldInfo, build_mesh
+    from prime_b200.parallel.symm import SymmetricHeap
+
+    dev = _dev()
+    torch.manual_seed(0)
+    m1 = build_model("debugmodel", device=dev, dtype=torch.bfloat16, seed=3)
+    m2 = copy.deepcopy(m1)
+    mesh = build_mesh(WorldInfo(), device=dev)
+    heap = SymmetricHeap(256 << 20, 0, 1, lambda h: [h], dev)
+    hyper = AdamHyper(lr=1e-3, max_norm=1.0)
+    e1 = ShardedEngine(m1, mesh, hyper, backend="fused", heap=heap)
+    e2 = ShardedEngine(m2, mesh, hyper, backend="collective")
+    V = m1.args.vocab_size
+    for _ in range(3):
+        tok = torch.randint(0, V, (2, 64), device=dev)
+        for m, e in ((m1, e1), (m2, e2)):
+            e.zero_grad()
+            e.set_micro_step(True)
+            m.loss(tok, tok).backward()
+            e.finish_backward()
+            e.step()
+    torch.cuda.synchronize()
+    heap.check_errors()
+    assert _rel_err(e1.master, e2.master) < 1e-4
+    assert abs(float(e1.last_grad_norm) - float(e2.last_grad_norm)) < 1e-2 * float(e2.last_grad_norm)
+    assert torch.equal(e1.param_flat.float() == 0, e2.param_flat.float() == 0)
+    assert _rel_err(e1.param_flat, e2.param_flat) < 1e-3
+    heap.close()
+
+
+def test_outer_step_fused_matches_reference():
+    from prime_b200.models.llama import build_model
+    from prime_b200.ops import reference as R
+    from prime_b200.parallel.diloco import DilocoOuter, OuterHyper
+    from prime_b200.parallel.fsdp import AdamHyper, ShardedEngine
+    from prime_b200.parallel.mesh import WorldInfo, build_mesh
+    from prime_b200.parallel.symm import SymmetricHeap
+
+    dev = _dev()
+    m = build_model("debugmodel", device=dev, dtype=torch.bfloat16, seed=4)
+    mesh = build_mesh(WorldInfo(), device=dev)
+    heap = SymmetricHeap(256 << 20, 0, 1, lambda h: [h], dev)
+    eng = ShardedEngine(m, mesh, AdamHyper(), backend="fused", heap=heap)
+    outer = DilocoOuter(eng, OuterHyper(lr=0.7, momentum=0.9, nesterov=True, compression="int8"))
+    theta0 = outer.theta0.clone()
+    eng.master.add_(torch.randn_like(eng.master) * 1e-3)  # pretend H inner steps moved the weights
+    pseudo = theta0 - eng.master
+    q, s = R.quantize_int8_blockwise(pseudo, 1024)
+    avg = R.dequantize_int8_blockwise(q, s, 1024)
+    mom = torch.zeros_like(theta0)
+    R.nesterov_outer_step(theta0, avg, mom, lr=0.7, momentum=0.9, nesterov=True)
+    outer.step()
+    torch.cuda.synchronize()
+    heap.check_errors()
+    torch.testing.assert_close(outer.theta0, theta0, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(eng.master, theta0, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(outer.momentum, mom, rtol=1e-5, atol=1e-7)
+    # bf16 parameters were refreshed from the new θ
+    b = eng.buckets[1]
+    got = eng.param_flat[b.start : b.start + b.shard_size].float()
+    want = theta0[b.shard_start : b.shard_start + b.shard_size].to(torch.bfloat16).float()
+    torch.testing.assert_close(got, want)
+    heap.close()
+
+
+def test_trainer_loss_decreases_on_gpu():
+    from prime_b200.config import Config
+    from prime_b200.trainer import Trainer
+
+    cfg = Config.model_validate(
+        {"name_model": "debugmodel", "data": {"seq_length": 128}, "optim": {"batch_size": 8, "warmup_steps": 2, "optim": {"lr": 3e-3}},
+         "train": {"micro_bs": 4}, "diloco": {"inner_steps": 5}}
+    )  # fmt: skip
+    t = Trainer(cfg)
+    losses = [float(t.inner_step().loss.item()) for _ in range(15)]
+    assert all(math.isfinite(x) for x in losses)
+    assert losses[-1] < losses[0] - 0.5, losses
+    assert t.outer.outer_step_count == 3
+    t.close()
