@@ -29,7 +29,8 @@ constexpr int kThreads = 256;
 constexpr uint32_t kABytes = BM * BK * 2;  // 16 KB
 constexpr uint32_t kBBytes = BN * BK * 2;  // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t kStagingBytes = 4 /*epilogue warps*/ * 2 /*buffers*/ * 4096;  // 32 rows x 128 B per buffer
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kGroupM = 16;  // raster: super-rows of 16 M-tiles keep the A slab L2-resident
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -83,6 +84,30 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// smem → global tensor store / reduce-add (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(uint32_t lo_f32_bits, uint32_t hi_f32_bits) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(lo_f32_bits), __uint_as_float(hi_f32_bits));
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -166,10 +191,11 @@ struct GemmParams {
 template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* staging = smem + kStages * kStageBytes;  // 1024-aligned: 4 warps x 2 buffers x 4 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + kAccStages;
@@ -183,6 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -266,63 +293,83 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (TMEM → regs → global)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------------ epilogue
+    // TMEM → registers → 128B-swizzled smem slab (32 rows x 128 B per warp) → TMA store / reduce-add.
+    // Each warp owns its TMEM lane quadrant, its own staging double-buffer and its own bulk groups,
+    // so the four epilogue warps never synchronise with each other.
+    const int q = warp & 3;
+    uint8_t* my_stage = staging + q * 8192;
+    const uint32_t row_sw = (uint32_t)(lane & 7);
     int acc = 0;
     uint32_t acc_phase = 0;
+    int buf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int tm, tn;
       tile_coords(tile, tiles_m, tiles_n, tm, tn);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = tm * BM + q * 32 + lane;
+      const int row0 = tm * BM + q * 32;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      if (p.c_fp32) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = tn * BN + c * 32;
-        if (row < p.M && col0 < p.N) {
-          if (p.c_fp32) {
-            float* dst = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
+        for (int c = 0; c < BN / 32; ++c) {  // 32 fp32 columns = one 128 B row
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          if (lane == 0) bulk_wait_read<1>();  // the store that last read this buffer has drained
+          __syncwarp();
+          tmem_ld_wait();
+          const uint32_t sbase = smem_u32(my_stage + buf * 4096) + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (col0 + j * 4 < p.N) {
-                float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                if (p.accumulate) {
-                  const float4 o = *reinterpret_cast<const float4*>(dst + j * 4);
-                  v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
-                }
-                *reinterpret_cast<float4*>(dst + j * 4) = v;
-              }
-            }
-          } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (col0 + j * 8 < p.N) {
-                float f[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(r[8 * j + t]);
-                if (p.accumulate) {
-                  float o[8];
-                  pb::unpack8(*reinterpret_cast<const pb::bf16x8*>(dst + j * 8), o);
-#pragma unroll
-                  for (int t = 0; t < 8; ++t) f[t] += o[t];
-                }
-                *reinterpret_cast<pb::bf16x8*>(dst + j * 8) = pb::pack8(f);
-              }
-            }
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(sbase + ((j ^ row_sw) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          const int col0 = tn * BN + c * 32;
+          if (lane == 0 && row0 < p.M && col0 < p.N) {
+            if (p.accumulate) tma_reduce_add_2d(&tmap_c, my_stage + buf * 4096, col0, row0);
+            else tma_store_2d(&tmap_c, my_stage + buf * 4096, col0, row0);
           }
+          if (lane == 0) bulk_commit();
+          buf ^= 1;
+        }
+      } else {
+#pragma unroll 1
+        for (int g = 0; g < BN / 64; ++g) {  // 64 bf16 columns = one 128 B row
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(taddr + g * 64, r0);
+          tmem_ld_32x32b_x32(taddr + g * 64 + 32, r1);
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          tmem_ld_wait();
+          const uint32_t sbase = smem_u32(my_stage + buf * 4096) + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(sbase + ((j ^ row_sw) << 4), pack_bf16x2(r0[8 * j], r0[8 * j + 1]),
+                         pack_bf16x2(r0[8 * j + 2], r0[8 * j + 3]), pack_bf16x2(r0[8 * j + 4], r0[8 * j + 5]),
+                         pack_bf16x2(r0[8 * j + 6], r0[8 * j + 7]));
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(sbase + (((j + 4) ^ row_sw) << 4), pack_bf16x2(r1[8 * j], r1[8 * j + 1]),
+                         pack_bf16x2(r1[8 * j + 2], r1[8 * j + 3]), pack_bf16x2(r1[8 * j + 4], r1[8 * j + 5]),
+                         pack_bf16x2(r1[8 * j + 6], r1[8 * j + 7]));
+          fence_proxy_async();
+          __syncwarp();
+          const int col0 = tn * BN + g * 64;
+          if (lane == 0 && row0 < p.M && col0 < p.N) {
+            if (p.accumulate) tma_reduce_add_2d(&tmap_c, my_stage + buf * 4096, col0, row0);
+            else tma_store_2d(&tmap_c, my_stage + buf * 4096, col0, row0);
+          }
+          if (lane == 0) bulk_commit();
+          buf ^= 1;
         }
       }
+      // every TMEM read of this accumulator has completed (wait::ld above) → hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == kAccStages) acc = 0, acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait_read<0>();  // staging smem must outlive the last store's reads
   }
 
   tc_fence_before();
@@ -351,16 +398,20 @@ EncodeFn get_encode() {
   return fn;
 }
 
-// rows x cols (cols contiguous) bf16 matrix with row stride ld (elements); box = box_cols x box_rows
+// rows x cols (cols contiguous) matrix with row stride ld (elements); box = box_cols x box_rows; esize 2 (bf16) | 4 (f32)
 int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
-              uint32_t box_rows) {
+              uint32_t box_rows, int esize = 2) {
   EncodeFn enc = get_encode();
   if (!enc) return -10;
+  // Driver entry points need a current context on THIS thread; autograd's backward threads may not have
+  // bound the primary context yet (seen as CUDA_ERROR_INVALID_CONTEXT). A no-op runtime call binds it.
+  cudaFree(nullptr);
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (uint64_t)esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -11 - (int)r;
@@ -370,28 +421,30 @@ struct MapKey {
   const void* ptr;
   uint64_t rows, cols, ld;
   uint32_t bc, br;
+  int esize;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && bc == o.bc && br == o.br;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && bc == o.bc && br == o.br && esize == o.esize;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = std::hash<const void*>()(k.ptr);
     auto mix = [&](uint64_t v) { h ^= std::hash<uint64_t>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-    mix(k.rows), mix(k.cols), mix(k.ld), mix(k.bc), mix(k.br);
+    mix(k.rows), mix(k.cols), mix(k.ld), mix(k.bc), mix(k.br), mix((uint64_t)k.esize);
     return h;
   }
 };
 
-int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t bc, uint32_t br) {
+int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t bc, uint32_t br,
+                int esize = 2) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
-  MapKey key{ptr, rows, cols, ld, bc, br};
+  MapKey key{ptr, rows, cols, ld, bc, br, esize};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it == cache.end()) {
     CUtensorMap m;
-    int rc = make_tmap(&m, ptr, rows, cols, ld, bc, br);
+    int rc = make_tmap(&m, ptr, rows, cols, ld, bc, br, esize);
     if (rc) return rc;
     if (cache.size() > 8192) cache.clear();
     it = cache.emplace(key, m).first;
@@ -403,7 +456,8 @@ int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
 int g_num_sms = 0;
 
 template <int A_MN, int B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int max_ctas, cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int max_ctas,
+           cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -420,7 +474,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, in
   int grid = g_num_sms;
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (tiles < grid) grid = tiles;
-  gemm_bf16_kernel<A_MN, B_MN><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);
+  gemm_bf16_kernel<A_MN, B_MN><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, tc, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -432,7 +486,7 @@ PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, 
                            int a_mn_major, int b_mn_major, int c_fp32, int accumulate, int max_ctas,
                            cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if ((lda % 8) || (ldb % 8) || (N % 8) || (ldc % 8)) return -1;
+  if ((lda % 8) || (ldb % 8) || (ldc % (c_fp32 ? 4 : 8))) return -1;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) return -2;
   CUtensorMap ta, tb;
   int rc;
@@ -446,9 +500,13 @@ PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, 
   else
     rc = cached_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK);
   if (rc) return rc;
+  CUtensorMap tc;  // epilogue store: 32-row x 128-byte boxes
+  rc = c_fp32 ? cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 32, 4)
+              : cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 64, 32, 2);
+  if (rc) return rc;
   GemmParams p{M, N, K, ldc, a_mn_major, b_mn_major, c_fp32, accumulate, C};
-  if (!a_mn_major && !b_mn_major) return launch<0, 0>(ta, tb, p, max_ctas, stream);
-  if (!a_mn_major && b_mn_major) return launch<0, 1>(ta, tb, p, max_ctas, stream);
-  if (a_mn_major && !b_mn_major) return launch<1, 0>(ta, tb, p, max_ctas, stream);
-  return launch<1, 1>(ta, tb, p, max_ctas, stream);
+  if (!a_mn_major && !b_mn_major) return launch<0, 0>(ta, tb, tc, p, max_ctas, stream);
+  if (!a_mn_major && b_mn_major) return launch<0, 1>(ta, tb, tc, p, max_ctas, stream);
+  if (a_mn_major && !b_mn_major) return launch<1, 0>(ta, tb, tc, p, max_ctas, stream);
+  return launch<1, 1>(ta, tb, tc, p, max_ctas, stream);
 }

@@ -96,8 +96,10 @@ class _LinearFn(torch.autograd.Function):
             x2 = x2.contiguous()
         ctx.save_for_backward(x2, weight)
         ctx.x_shape = x.shape
-        y = gemm(x2, weight)
-        return y.view(*x.shape[:-1], weight.shape[0])
+        # allocate with the final shape: a Function output must not be a view (RoPE / the loss rotate / overwrite it in place)
+        y = torch.empty((*x.shape[:-1], weight.shape[0]), dtype=x.dtype, device=x.device)
+        gemm(x2, weight, out=y.view(-1, weight.shape[0]))
+        return y
 
     @staticmethod
     def backward(ctx, dy: torch.Tensor):
@@ -107,7 +109,8 @@ class _LinearFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(dy2, weight, b_mn_major=True).view(ctx.x_shape)
+            dx = torch.empty(ctx.x_shape, dtype=dy.dtype, device=dy.device)
+            gemm(dy2, weight, b_mn_major=True, out=dx.view(-1, ctx.x_shape[-1]))
         if ctx.needs_input_grad[1]:
             main_grad = getattr(weight, "main_grad", None)
             if main_grad is not None:
@@ -140,12 +143,12 @@ class _RMSNormFn(torch.autograd.Function):
         x2 = x.reshape(-1, D)
         x2 = x2 if x2.is_contiguous() else x2.contiguous()
         R = x2.shape[0]
-        y = torch.empty_like(x2)
+        y = torch.empty(x.shape, dtype=x.dtype, device=x.device)
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
         if residual is not None:
             r2 = residual.reshape(-1, D)
             r2 = r2 if r2.is_contiguous() else r2.contiguous()
-            h = torch.empty_like(x2)
+            h = torch.empty(x.shape, dtype=x.dtype, device=x.device)
         else:
             r2, h = None, x2
         rc = lib.pb_rmsnorm_fwd(_ptr(x2), _ptr(r2), _ptr(weight), _ptr(y), _ptr(h) if residual is not None else None,
@@ -155,22 +158,21 @@ class _RMSNormFn(torch.autograd.Function):
         ctx.save_for_backward(h, weight, rstd)
         ctx.has_res = residual is not None
         ctx.shape = x.shape
-        if residual is not None:
-            return y.view(x.shape), h.view(x.shape)
-        return y.view(x.shape), None
+        return y, (h if residual is not None else None)
 
     @staticmethod
     def backward(ctx, dy, dh):
         lib = _lib.load()
         h, weight, rstd = ctx.saved_tensors
-        R, D = h.shape
+        D = h.shape[-1]
+        R = h.numel() // D
         dy2 = dy.reshape(R, D)
         dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
         dres = None
         if dh is not None:
             dres = dh.reshape(R, D)
             dres = dres if dres.is_contiguous() else dres.contiguous()
-        dx = torch.empty_like(h)
+        dx = torch.empty(ctx.shape, dtype=h.dtype, device=h.device)
         grid = lib.pb_rmsnorm_bwd_grid(R)
         partial = torch.empty((grid, D), dtype=torch.float32, device=h.device)
         main_grad = getattr(weight, "main_grad", None)
@@ -182,7 +184,7 @@ class _RMSNormFn(torch.autograd.Function):
                                 _ptr(dw32), acc, R, D, _stream())  # fmt: skip
         _lib.check(rc, "pb_rmsnorm_bwd")
         _count(2)
-        dxv = dx.view(ctx.shape)
+        dxv = dx
         dw = None if main_grad is not None else dw32.to(weight.dtype)
         # residual-add backward: gradient flows identically to x and residual
         return dxv, (dxv if ctx.has_res else None), dw, None
@@ -227,7 +229,8 @@ class _RopeQKVFn(torch.autograd.Function):
         lib = _lib.load()
         cos, sin = ctx.saved_tensors
         n_heads, n_kv_heads, seq_len, D, total_heads = ctx.meta
-        dqkv = dqkv if dqkv.is_contiguous() else dqkv.contiguous()
+        # never rotate the incoming gradient in place: autograd may share that tensor with other consumers
+        dqkv = dqkv.clone(memory_format=torch.contiguous_format)
         tokens = dqkv.numel() // dqkv.shape[-1]
         # rotation is orthogonal: the backward is the inverse rotation, applied in place on the incoming grad
         rc = lib.pb_rope_inplace(_ptr(dqkv), _ptr(cos), _ptr(sin), tokens, seq_len, n_heads + n_kv_heads, total_heads, D,
@@ -258,13 +261,13 @@ class _SwiGLUFn(torch.autograd.Function):
         F2 = gate_up.shape[-1]
         gu = gate_up.reshape(-1, F2)
         gu = gu if gu.is_contiguous() else gu.contiguous()
-        out = torch.empty((gu.shape[0], F2 // 2), dtype=gu.dtype, device=gu.device)
+        out = torch.empty((*gate_up.shape[:-1], F2 // 2), dtype=gu.dtype, device=gu.device)
         rc = lib.pb_swiglu_fwd(_ptr(gu), _ptr(out), gu.shape[0], F2 // 2, _stream())
         _lib.check(rc, "pb_swiglu_fwd")
         _count()
         ctx.save_for_backward(gu)
         ctx.shape = gate_up.shape
-        return out.view(*gate_up.shape[:-1], F2 // 2)
+        return out
 
     @staticmethod
     def backward(ctx, dout):
@@ -272,11 +275,11 @@ class _SwiGLUFn(torch.autograd.Function):
         (gu,) = ctx.saved_tensors
         d2 = dout.reshape(gu.shape[0], -1)
         d2 = d2 if d2.is_contiguous() else d2.contiguous()
-        dgu = torch.empty_like(gu)
+        dgu = torch.empty(ctx.shape, dtype=gu.dtype, device=gu.device)
         rc = lib.pb_swiglu_bwd(_ptr(gu), _ptr(d2), _ptr(dgu), gu.shape[0], gu.shape[1] // 2, _stream())
         _lib.check(rc, "pb_swiglu_bwd")
         _count()
-        return dgu.view(ctx.shape)
+        return dgu
 
 
 def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
@@ -305,7 +308,7 @@ class _CrossEntropyFn(torch.autograd.Function):
         rc = lib.pb_cross_entropy_fwd_bwd(_ptr(z), _ptr(t), _ptr(losses), _ptr(kscale), R, V, ignore_index, _stream())
         _lib.check(rc, "pb_cross_entropy_fwd_bwd")
         _count()
-        ctx.mark_dirty(logits)
+        # NOTE: deliberately not mark_dirty(): the logits are consumed, not returned; their storage now holds the gradient
         ctx.save_for_backward(z)
         ctx.shape = logits.shape
         ctx.unit_upstream = unit_upstream
@@ -351,7 +354,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = 
     if not q.is_cuda:
         return reference.attention(q, k, v, causal)
     if impl in ("auto", "native"):
-        from . import attention as native_attn
+        from . import attention_native as native_attn
 
         if native_attn.supported(q, k, v):
             return native_attn.flash_attention(q, k, v, causal)

@@ -1,0 +1,16 @@
+"""Evaluation results SDK: create → push samples (size-adaptive batches, concurrent, retried) → finalize."""
+
+from .evals import AsyncEvalsClient, EvalsClient, build_batches  # noqa: F401
+from .exceptions import EvalsAPIError, EvaluationNotFoundError, InvalidEvaluationError, InvalidSampleError  # noqa: F401
+from .models import (  # noqa: F401
+    CreateEvaluationRequest,
+    Environment,
+    EnvironmentReference,
+    Evaluation,
+    EvaluationListResponse,
+    EvaluationStatus,
+    Sample,
+    SamplesResponse,
+)
+
+__version__ = "0.1.0"

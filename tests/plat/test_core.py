@@ -1,0 +1,149 @@
+import json
+
+import httpx
+import pytest
+
+from prime_b200.platform.core import (
+    APIClient,
+    APIError,
+    APITimeoutError,
+    AsyncAPIClient,
+    Config,
+    PaymentRequiredError,
+    RetryPolicy,
+    UnauthorizedError,
+    ValidationError,
+)
+from prime_b200.platform.core.client import IDEMPOTENT_RETRY, TRANSPORT_RETRY
+
+
+def test_config_env_over_file(isolated_home, monkeypatch):
+    c = Config()
+    c.set_api_key("file-key")
+    assert Config().api_key == "file-key"
+    monkeypatch.setenv("PRIME_API_KEY", "env-key")
+    assert Config().api_key == "env-key"
+    monkeypatch.setenv("PRIME_API_BASE_URL", "https://x.example/api/v1/")
+    assert Config().base_url == "https://x.example"
+
+
+def test_config_contexts(isolated_home, monkeypatch):
+    c = Config()
+    c.set_api_key("k1")
+    c.set_base_url("https://staging.example")
+    assert c.save_environment("my staging!") == "my_staging_"
+    c.set_base_url("https://other.example")
+    assert "my_staging_" in c.list_environments() and "production" in c.list_environments()
+    assert c.load_environment("my staging!")
+    assert Config().base_url == "https://staging.example" and Config().current_environment == "my_staging_"
+    # PRIME_CONTEXT selects without persisting
+    c.load_environment("production")
+    monkeypatch.setenv("PRIME_CONTEXT", "my_staging_")
+    assert Config().base_url == "https://staging.example"
+    monkeypatch.delenv("PRIME_CONTEXT")
+    assert Config().base_url == "https://api.primeintellect.ai"
+    with pytest.raises(ValueError):
+        c.save_environment("production")
+
+
+def test_sdk_config_is_read_only(isolated_home):
+    c = Config(writable=False)
+    assert not (isolated_home / ".prime").exists()
+    with pytest.raises(PermissionError):
+        c.set_api_key("x")
+
+
+def _client(handler, **kw):
+    return APIClient(api_key="k", transport=httpx.MockTransport(handler), **kw)
+
+
+def test_prefix_auth_and_204():
+    seen = {}
+
+    def h(req):
+        seen["url"], seen["auth"] = str(req.url), req.headers["authorization"]
+        return httpx.Response(204)
+
+    assert _client(h).delete("/pods/1") == {}
+    assert seen["url"].endswith("/api/v1/pods/1") and seen["auth"] == "Bearer k"
+    assert _client(h).get("pods") == {} and seen["url"].endswith("/api/v1/pods")
+
+
+@pytest.mark.parametrize("code,exc", [(401, UnauthorizedError), (402, PaymentRequiredError)])
+def test_status_mapping(code, exc):
+    with pytest.raises(exc):
+        _client(lambda r: httpx.Response(code, json={"detail": "no"})).get("/x")
+
+
+def test_422_and_generic():
+    detail = [{"loc": ["body", "model", "name"], "msg": "field required"}]
+    with pytest.raises(ValidationError) as e:
+        _client(lambda r: httpx.Response(422, json={"detail": detail})).post("/x", json={})
+    assert "model.name: field required" in str(e.value)
+    with pytest.raises(APIError, match="HTTP 500: boom"):
+        _client(lambda r: httpx.Response(500, json={"detail": "boom"})).get("/x")
+    with pytest.raises(APIError, match="not a dictionary"):
+        _client(lambda r: httpx.Response(200, json=[1])).get("/x")
+
+
+def test_timeout_and_no_key(isolated_home):
+    def h(req):
+        raise httpx.ReadTimeout("slow", request=req)
+
+    with pytest.raises(APITimeoutError):
+        _client(h).get("/x")
+    with pytest.raises(APIError, match="No API key"):
+        APIClient(transport=httpx.MockTransport(lambda r: httpx.Response(200, json={}))).get("/x")
+
+
+class FlakyTransport(httpx.BaseTransport):
+    """Fails N times with a connection error, then succeeds (reference idea: prime-sandboxes/tests/test_client_retry.py:9-57)."""
+
+    def __init__(self, failures, exc=httpx.ConnectError):
+        self.failures, self.calls, self.exc = failures, 0, exc
+
+    def handle_request(self, request):
+        self.calls += 1
+        if self.calls <= self.failures:
+            raise self.exc("nope", request=request)
+        return httpx.Response(200, json={"ok": True})
+
+
+def test_transport_retry_counts(monkeypatch):
+    monkeypatch.setattr("time.sleep", lambda s: None)
+    t = FlakyTransport(2)
+    assert APIClient(api_key="k", transport=t, retry=TRANSPORT_RETRY).get("/x") == {"ok": True}
+    assert t.calls == 3
+    t = FlakyTransport(5)
+    with pytest.raises(APIError):
+        APIClient(api_key="k", transport=t, retry=TRANSPORT_RETRY).get("/x")
+    assert t.calls == 3
+    t = FlakyTransport(1)
+    with pytest.raises(APIError):
+        APIClient(api_key="k", transport=t).get("/x")  # default: no retry
+    assert t.calls == 1
+
+
+def test_timeouts_retry_only_for_idempotent_verbs(monkeypatch):
+    monkeypatch.setattr("time.sleep", lambda s: None)
+    t = FlakyTransport(1, exc=httpx.ReadTimeout)
+    assert APIClient(api_key="k", transport=t, retry=IDEMPOTENT_RETRY).get("/x") == {"ok": True}
+    t = FlakyTransport(1, exc=httpx.ReadTimeout)
+    with pytest.raises(APITimeoutError):
+        APIClient(api_key="k", transport=t, retry=IDEMPOTENT_RETRY).post("/x", json={})
+    assert t.calls == 1
+
+
+def test_retry_policy_delay_bounds():
+    p = RetryPolicy(attempts=3, base_delay=0.1, max_delay=2.0)
+    assert all(0 < p.delay(i) <= 2.0 for i in range(10))
+
+
+@pytest.mark.anyio
+async def test_async_client_roundtrip():
+    async def h(req):
+        return httpx.Response(200, json={"path": req.url.path, "body": json.loads(req.content or b"{}")})
+
+    async with AsyncAPIClient(api_key="k", transport=httpx.MockTransport(h)) as c:
+        r = await c.post("/sandbox", json={"a": 1})
+    assert r == {"path": "/api/v1/sandbox", "body": {"a": 1}}
