@@ -132,6 +132,7 @@ def main() -> None:
     ap.add_argument("--seq", type=int, default=SEQ)
     ap.add_argument("--no-fused-comm", action="store_true", help="baseline B0: NCCL collectives instead of fused P2P kernels")
     ap.add_argument("--attn", default="auto")
+    ap.add_argument("--graphs", type=int, default=1, help="capture each micro-step (fwd+bwd) in a CUDA graph")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -161,7 +162,8 @@ def main() -> None:
             "data": {"seq_length": args.seq, "fake": True},
             "optim": {"batch_size": args.micro_bs * args.accum * fsdp, "warmup_steps": 10, "total_steps": 100000,
                       "optim": {"lr": 4e-4}},
-            "train": {"micro_bs": args.micro_bs, "fused_comm": not args.no_fused_comm, "attn_impl": args.attn},
+            "train": {"micro_bs": args.micro_bs, "fused_comm": not args.no_fused_comm, "attn_impl": args.attn,
+                      "cuda_graphs": bool(args.graphs)},
             "diloco": {"inner_steps": H, "compression": "int8", "outer_lr": 0.7},
             "mesh": {"num_workers": workers, "fsdp_size": fsdp},
         }
@@ -246,6 +248,7 @@ def main() -> None:
                 "diloco_H": H,
                 "outer": "int8 all-gather + Nesterov, forced >=1 per timed region",
                 "comm": "fused P2P kernels" if not args.no_fused_comm else "NCCL collectives (B0)",
+                "cuda_graphs": bool(args.graphs),
                 "l2": "working set (params+activations, >20 GB/step) far larger than the 126 MB L2; no flush needed",
             },
             "clocks": clocks,

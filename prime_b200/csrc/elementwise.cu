@@ -147,18 +147,28 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16x8* __restri
   }
 }
 
-__global__ void colsum_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int nparts, int D,
-                                       int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
+// 32 columns x 8 row-lanes per CTA: coalesced 128 B row segments, 8-way parallel over the partial rows.
+__global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                              int nparts, int D, int accumulate) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * D + c];
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < D)
+    for (int p = ty; p < nparts; p += 8) s += partial[(int64_t)p * D + c];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][tx];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 // dw_partial must hold grid*D floats; `grid_out` reports the grid used (query with R<0).
 PB_EXPORT int pb_rmsnorm_bwd_grid(int64_t R) {
-  int64_t g = 148 * 4;
+  int64_t g = 148 * 2;
   return (int)(R < g ? R : g);
 }
 
@@ -182,7 +192,7 @@ PB_EXPORT int pb_rmsnorm_bwd(const void* dy, const void* h, const void* w, const
   if (vpt <= 1) { LAUNCH(1) } else if (vpt <= 2) { LAUNCH(2) } else if (vpt <= 4) { LAUNCH(4) } else { LAUNCH(8) }
 #undef LAUNCH
   PB_CHECK_LAUNCH();
-  colsum_partials_kernel<<<(D + 255) / 256, 256, 0, stream>>>(dw_partial, dw, grid, D, dw_accumulate);
+  colsum_partials_kernel<<<(D + 31) / 32, 256, 0, stream>>>(dw_partial, dw, grid, D, dw_accumulate);
   PB_CHECK_LAUNCH();
   return 0;
 }

@@ -405,7 +405,11 @@ int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, u
   if (!enc) return -10;
   // Driver entry points need a current context on THIS thread; autograd's backward threads may not have
   // bound the primary context yet (seen as CUDA_ERROR_INVALID_CONTEXT). A no-op runtime call binds it.
-  cudaFree(nullptr);
+  static thread_local bool ctx_bound = false;  // once per thread: cudaFree is illegal during graph capture
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * (uint64_t)esize};
   cuuint32_t box[2] = {box_cols, box_rows};

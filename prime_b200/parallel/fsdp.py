@@ -99,6 +99,7 @@ class ShardedEngine:
         self.last_grad_norm: torch.Tensor | None = None
         self._last_micro = True
         self._epoch = 0
+        self.capture_mode = False  # True while a CUDA graph of the micro-step is captured/replayed: no comm in backward
         self._build_buckets()
         self._allocate()
         self._install_hooks()
@@ -248,7 +249,7 @@ class ShardedEngine:
 
     def _on_bucket_ready(self, bucket_id: int) -> None:
         b = self.buckets[bucket_id]
-        if not self._last_micro or b.ready:
+        if self.capture_mode or not self._last_micro or b.ready:
             return
         b.ready = True
         self._fold_autograd_grads(b)

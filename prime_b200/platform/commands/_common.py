@@ -1,0 +1,70 @@
+"""Shared plumbing for command modules: client construction, uniform API-error handling, table/JSON output."""
+
+from __future__ import annotations
+
+import functools
+from typing import Any, Callable, Iterable, Sequence
+
+import typer
+
+from ..core import APIClient, APIError, Config, ValidationError
+from ..utils.display import build_table, output_data_as_json, validate_output_format
+from ..utils.plain import PlainTyper, default_group, get_console
+
+console = get_console()
+OUTPUT_OPT = typer.Option("table", "--output", "-o", help="Output format: table or json")
+
+
+def make_app(help: str, default_cmd: str | None = None, **kw: Any) -> PlainTyper:
+    if default_cmd:
+        kw["cls"] = default_group(default_cmd)
+    return PlainTyper(help=help, no_args_is_help=default_cmd is None, **kw)
+
+
+def api() -> APIClient:
+    return APIClient(config=Config(writable=False))
+
+
+def fail(message: str, code: int = 1) -> "typer.Exit":
+    console.print(f"[red]Error:[/red] {message}")
+    return typer.Exit(code)
+
+
+def handle_errors(fn: Callable) -> Callable:
+    """Render API failures as one red line (422s field by field) and exit 1 instead of a traceback."""
+
+    @functools.wraps(fn)
+    def wrapper(*a: Any, **kw: Any):
+        try:
+            return fn(*a, **kw)
+        except ValidationError as e:
+            console.print("[red]Validation error:[/red]")
+            for err in e.errors:
+                loc = ".".join(str(p) for p in err.get("loc", []) if p != "body")
+                console.print(f"  [yellow]{loc}[/yellow]: {err.get('msg', 'invalid')}")
+            raise typer.Exit(1)
+        except APIError as e:
+            raise fail(str(e))
+        except (KeyboardInterrupt, typer.Abort):
+            console.print("\n[dim]Cancelled.[/dim]")
+            raise typer.Exit(130)
+
+    return wrapper
+
+
+def emit(output: str, payload: Any, title: str | None, columns: Sequence[str | tuple[str, str]],
+         rows: Iterable[Sequence[Any]], footer: str | None = None) -> None:  # fmt: skip
+    """One call for the list-style commands: JSON document or rich table."""
+    if validate_output_format(output, console) == "json":
+        output_data_as_json(payload, console)
+        return
+    console.print(build_table(title, columns, rows))
+    if footer:
+        console.print(footer)
+
+
+def paginate_hint(total: int, offset: int, limit: int, noun: str) -> str | None:
+    shown_to = min(offset + limit, total)
+    if total > shown_to:
+        return f"[dim]Showing {offset + 1}-{shown_to} of {total} {noun}. Use --offset {shown_to} for the next page.[/dim]"
+    return None

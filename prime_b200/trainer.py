@@ -81,6 +81,46 @@ class Trainer:
         self.loader = PinnedPrefetcher(self.dataset, self.micro_bs, self.device)
         self.step_count = 0
         self._loss_acc = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._graph = None
+        self._graph_launches = 0
+        if cfg.train.cuda_graphs and cuda:
+            self._capture_micro_step()
+
+    # ------------------------------------------------------------------ CUDA graph of one micro-step
+    def _capture_micro_step(self) -> None:
+        """Capture fwd + bwd (+ stray-grad fold) of one micro-batch into a CUDA graph.
+
+        ~2.3k kernel launches per optimizer step become `accum` graph launches; gradients accumulate into the
+        static fp32 main_grad buffers from inside the graph; bucket reduction then runs after the replay.
+        """
+        from . import ops
+
+        eng, S = self.engine, self.cfg.data.seq_length
+        self._g_tokens = torch.zeros((self.micro_bs, S), dtype=torch.int64, device=self.device)
+        self._g_labels = torch.zeros((self.micro_bs, S), dtype=torch.int64, device=self.device)
+        eng.capture_mode = True
+        scale = 1.0 / self.accum
+
+        def micro() -> torch.Tensor:
+            loss = self.model.loss(self._g_tokens, self._g_labels, grad_scale=scale)
+            loss.backward()
+            eng.fold_micro_grads()
+            return loss.detach()
+
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture: binds contexts, fills the tensor-map cache, sizes pools
+            for _ in range(2):
+                micro()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        eng.zero_grad()
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(self._graph):
+            self._g_loss = micro()
+        self._graph_launches = ops.launch_count() - n0
+        eng.zero_grad()
 
     # ------------------------------------------------------------------ one optimizer step
     def current_lr(self) -> float:
@@ -96,12 +136,21 @@ class Trainer:
             batch = batches[i] if batches is not None else self.loader.next()
             last = i == self.accum - 1
             eng.set_micro_step(last)
-            loss = self.model.loss(batch.input_ids, batch.labels, grad_scale=1.0 / self.accum)
-            loss.backward()
-            if last:
-                eng.finish_backward()
+            if self._graph is not None:
+                self._g_tokens.copy_(batch.input_ids, non_blocking=True)
+                self._g_labels.copy_(batch.labels, non_blocking=True)
+                self._graph.replay()
+                _count_launches(self._graph_launches)
+                loss = self._g_loss
+                if last:
+                    eng.finish_backward()
             else:
-                eng.fold_micro_grads()
+                loss = self.model.loss(batch.input_ids, batch.labels, grad_scale=1.0 / self.accum)
+                loss.backward()
+                if last:
+                    eng.finish_backward()
+                else:
+                    eng.fold_micro_grads()
             self._loss_acc += loss.detach().float()
         lr = self.current_lr()
         eng.step(lr)
@@ -121,6 +170,12 @@ class Trainer:
             torch.cuda.synchronize()
             self.heap.close()
             self.heap = None
+
+
+def _count_launches(n: int) -> None:
+    from .ops.functional import _count
+
+    _count(n)
 
 
 def _env_world() -> int:
