@@ -1,0 +1,560 @@
+// Flash-attention backward for sm_100a (tcgen05 / TMEM / TMA), fused-QKV layout, deterministic (no atomics).
+//
+//   delta[b,h,s]   = Σ_d dO·O                                                   (bwd_delta_kernel, memory bound)
+//   dK, dV         : one CTA per 128-row KV block; loops over 64-row query tiles (bwd_dkdv_kernel)
+//                    computes the TRANSPOSED scores Sᵀ = K Qᵀ, dPᵀ = V dOᵀ so that each softmax thread owns a KV row
+//                    and writes Pᵀ / dSᵀ as K-major A operands:  dV += Pᵀ dO ,  dK += dSᵀ Q
+//   dQ             : one CTA per 128-row query block; loops over 64-row KV tiles   (bwd_dq_kernel)
+//                    S = Q Kᵀ, dP = dO Vᵀ, dS row-wise,  dQ += dS K
+//
+// A [rows x 64-column] 128B-swizzled box is simultaneously a K-major operand (rows = M/N) and an MN-major operand
+// (rows = K), so each Q / dO / K tile is loaded ONCE by TMA and fed to both kinds of GEMM.
+// With dS = P ∘ (dP − delta) · scale the results need no further scaling.  P is recomputed from the forward's
+// log2-domain LSE: P = exp2(s·scale·log2e − lse2).
+//
+// TMEM budget (512 columns):  dK/dV kernel: Sᵀ 2×64 | dPᵀ 2×64 | dV D | dK D      dQ kernel: S 2×64 | dP 2×64 | dQ D
+#include "tc_common.cuh"
+#include "tmap.h"
+
+using namespace tc;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(256) bwd_delta_kernel(const pb::bf16x8* __restrict__ dout, const pb::bf16x8* __restrict__ out,
+                                                        float* __restrict__ delta, int64_t tokens, int S, int H, int vec_per_head) {
+  // one warp per (token, head)
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= tokens * H) return;
+  const int64_t tok = w / H;
+  const int h = (int)(w - tok * H);
+  const int64_t base = (tok * H + h) * vec_per_head;
+  float acc = 0.f;
+  for (int i = lane; i < vec_per_head; i += 32) {
+    float a[8], b[8];
+    pb::unpack8(pb::ldg_stream(dout + base + i), a);
+    pb::unpack8(pb::ldg_stream(out + base + i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += a[j] * b[j];
+  }
+  acc = pb::warp_sum(acc);
+  if (lane == 0) {
+    const int64_t bidx = tok / S;
+    const int s = (int)(tok - bidx * S);
+    delta[(bidx * H + h) * S + s] = acc;
+  }
+}
+
+struct BwdParams {
+  const float* lse2;
+  const float* delta;
+  int B, S, H, Hkv;
+  float scale, scale_log2;
+  int causal;
+};
+
+// write one 32-value fp32 chunk of a row as bf16 into a [rows x 64] swizzled block (half: which 32 columns)
+__device__ __forceinline__ void store_row_chunk_bf16(uint32_t block_base, int r, int half, const float (&x)[32]) {
+  const uint32_t sbase = block_base + r * 128;
+  const uint32_t sw = (uint32_t)(r & 7);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t chunk = (uint32_t)(half * 4 + i);
+    st_shared_v4(sbase + ((chunk ^ sw) << 4), pack_bf16x2(__float_as_uint(x[8 * i]), __float_as_uint(x[8 * i + 1])),
+                 pack_bf16x2(__float_as_uint(x[8 * i + 2]), __float_as_uint(x[8 * i + 3])),
+                 pack_bf16x2(__float_as_uint(x[8 * i + 4]), __float_as_uint(x[8 * i + 5])),
+                 pack_bf16x2(__float_as_uint(x[8 * i + 6]), __float_as_uint(x[8 * i + 7])));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------- dK / dV
+template <int D>
+struct DkvCfg {
+  static constexpr int kChunks = D / 64;
+  static constexpr uint32_t kKVBytes = 128 * D * 2;           // resident K or V (128 rows)
+  static constexpr uint32_t kQBytes = 64 * D * 2;             // one Q or dO tile (64 rows)
+  static constexpr uint32_t kPBytes = 128 * 128;              // Pᵀ or dSᵀ : [128 kv rows x 64 q]
+  static constexpr uint32_t kOffV = kKVBytes;
+  static constexpr uint32_t kOffQ = 2 * kKVBytes;             // 2 stages
+  static constexpr uint32_t kOffdO = kOffQ + 2 * kQBytes;     // 2 stages
+  static constexpr uint32_t kOffP = kOffdO + 2 * kQBytes;     // 2 stages
+  static constexpr uint32_t kOffdS = kOffP + 2 * kPBytes;     // 2 stages
+  static constexpr uint32_t kOffBar = kOffdS + 2 * kPBytes;
+  static constexpr uint32_t kSmem = kOffBar + 256 + 1024;
+  static constexpr uint32_t tS = 0, tdP = 128, tdV = 256, tdK = 256 + D;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+    bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __grid_constant__ CUtensorMap tmap_qkv64,
+                    const __grid_constant__ CUtensorMap tmap_do64, const __grid_constant__ CUtensorMap tmap_dqkv,
+                    const BwdParams p) {
+  using C = DkvCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + C::kOffV;
+  uint8_t* sQ = smem + C::kOffQ;
+  uint8_t* sdO = smem + C::kOffdO;
+  uint8_t* sP = smem + C::kOffP;
+  uint8_t* sdS = smem + C::kOffdS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint64_t* kv_full = bars;        // 1
+  uint64_t* q_full = bars + 1;     // 2
+  uint64_t* q_empty = bars + 3;    // 2
+  uint64_t* s_full = bars + 5;     // 2
+  uint64_t* s_empty = bars + 7;    // 2 (4 warps)
+  uint64_t* p_full = bars + 9;     // 2 (4 warps)
+  uint64_t* acc_done = bars + 11;  // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jb = blockIdx.x;  // KV block (128 rows)
+  const int b = blockIdx.y / p.Hkv, hk = blockIdx.y % p.Hkv;
+  const int group = p.H / p.Hkv;
+  const int nq64 = p.S / 64;
+  const int it0 = p.causal ? (jb * 128) / 64 : 0;  // first query tile that can see this KV block
+  const int tiles_per_head = nq64 - it0;
+  const int n_it = tiles_per_head * group;
+  const int kvrow0 = b * p.S + jb * 128;
+  const int col_k = (p.H + hk) * D, col_v = (p.H + p.Hkv + hk) * D;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_qkv128);
+    prefetch_tmap(&tmap_qkv64);
+    prefetch_tmap(&tmap_do64);
+    prefetch_tmap(&tmap_dqkv);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&acc_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA loader
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * C::kKVBytes);
+#pragma unroll
+      for (int c = 0; c < C::kChunks; ++c) {
+        tma_load_2d(&tmap_qkv128, kv_full, sK + c * (128 * 128), col_k + c * 64, kvrow0);
+        tma_load_2d(&tmap_qkv128, kv_full, sV + c * (128 * 128), col_v + c * 64, kvrow0);
+      }
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int h = hk * group + it / tiles_per_head;
+        const int qrow = b * p.S + (it0 + it % tiles_per_head) * 64;
+        mbar_wait(&q_empty[st], ph ^ 1);
+        mbar_expect_tx(&q_full[st], 2 * C::kQBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+          tma_load_2d(&tmap_qkv64, &q_full[st], sQ + st * C::kQBytes + c * (64 * 128), h * D + c * 64, qrow);
+          tma_load_2d(&tmap_do64, &q_full[st], sdO + st * C::kQBytes + c * (64 * 128), h * D + c * 64, qrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);  // Sᵀ[128 kv x 64 q] = K Qᵀ   (both K-major)
+      constexpr uint32_t idesc_a = idesc_bf16(128, D, 0, 1);   // dV/dK[128 kv x D] += Pᵀ·dO  (A K-major, B MN-major)
+      mbar_wait(kv_full, 0);
+      auto issue_sd = [&](int it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&q_full[st], ph);
+        mbar_wait(&s_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t k0 = smem_u32(sK), v0 = smem_u32(sV);
+        const uint32_t q0 = smem_u32(sQ + st * C::kQBytes), d0 = smem_u32(sdO + st * C::kQBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + C::tS + st * 64, make_smem_desc(k0 + c * (128 * 128) + k * 32, 16, 1024),
+                      make_smem_desc(q0 + c * (64 * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + C::tdP + st * 64, make_smem_desc(v0 + c * (128 * 128) + k * 32, 16, 1024),
+                      make_smem_desc(d0 + c * (64 * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
+        umma_commit(&s_full[st]);
+      };
+      issue_sd(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_sd(it + 1);  // overlaps the softmax math of tile `it`
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&p_full[st], ph);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP + st * C::kPBytes), da = smem_u32(sdS + st * C::kPBytes);
+        const uint32_t q0 = smem_u32(sQ + st * C::kQBytes), d0 = smem_u32(sdO + st * C::kQBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // K = 64 query rows
+          umma_bf16(tmem_base + C::tdV, make_smem_desc(pa + kk * 32, 16, 1024), make_smem_desc(d0 + kk * 2048, 64 * 128, 1024),
+                    idesc_a, (it | kk) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + C::tdK, make_smem_desc(da + kk * 32, 16, 1024), make_smem_desc(q0 + kk * 2048, 64 * 128, 1024),
+                    idesc_a, (it | kk) != 0 ? 1u : 0u);
+        umma_commit(&q_empty[st]);
+        umma_commit(&acc_done[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax-backward math + epilogue
+    const int q = warp & 3;
+    const int r = q * 32 + lane;      // KV row in the block == TMEM lane
+    const int kv_idx = jb * 128 + r;  // position in the sequence
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int h = hk * group + it / tiles_per_head;
+      const int qpos0 = (it0 + it % tiles_per_head) * 64;
+      const float* lse_row = p.lse2 + ((int64_t)(b * p.H + h)) * p.S + qpos0;
+      const float* del_row = p.delta + ((int64_t)(b * p.H + h)) * p.S + qpos0;
+      mbar_wait(&s_full[st], ph);
+      tc_fence_after();
+      if (it >= 2) mbar_wait(&acc_done[st], ph ^ 1);  // Pᵀ/dSᵀ buffers of this stage are free again
+      const bool need_mask = p.causal && (qpos0 < jb * 128 + 128);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, sv);
+        tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, dv);
+        tmem_ld_wait();
+        float pr[32], ds[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int qc = half * 32 + j;
+          const float lse = __ldg(lse_row + qc), del = __ldg(del_row + qc);
+          float pv = fast_exp2(__uint_as_float(sv[j]) * p.scale_log2 - lse);
+          if (need_mask && kv_idx > qpos0 + qc) pv = 0.f;
+          pr[j] = pv;
+          ds[j] = pv * (__uint_as_float(dv[j]) - del) * p.scale;
+        }
+        store_row_chunk_bf16(smem_u32(sP + st * C::kPBytes), r, half, pr);
+        store_row_chunk_bf16(smem_u32(sdS + st * C::kPBytes), r, half, ds);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[st]);
+        mbar_arrive(&p_full[st]);
+      }
+    }
+    // epilogue: dV, dK → bf16 → staging (the Pᵀ/dSᵀ region, 64 KB) → TMA stores into dqkv
+    const int tl = n_it - 1;
+    mbar_wait(&acc_done[tl & 1], (tl >> 1) & 1);
+    if (n_it >= 2) mbar_wait(&acc_done[(tl - 1) & 1], ((tl - 1) >> 1) & 1);
+    tc_fence_after();
+    uint8_t* stage = sP;  // [which(dV,dK)][chunk c] blocks of [128 rows x 128 B]
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+#pragma unroll 1
+      for (int c32 = 0; c32 < D / 32; ++c32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (which ? C::tdK : C::tdV) + lane_addr + c32 * 32, v);
+        tmem_ld_wait();
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        store_row_chunk_bf16(smem_u32(stage + (which * C::kChunks + (c32 >> 1)) * (128 * 128)), r, c32 & 1, x);
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < C::kChunks; ++c) {
+        tma_store_2d(&tmap_dqkv, stage + (0 * C::kChunks + c) * (128 * 128) + q * 32 * 128, col_v + c * 64, kvrow0 + q * 32);
+        tma_store_2d(&tmap_dqkv, stage + (1 * C::kChunks + c) * (128 * 128) + q * 32 * 128, col_k + c * 64, kvrow0 + q * 32);
+      }
+      bulk_commit();
+      bulk_wait_read<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------- dQ
+template <int D>
+struct DqCfg {
+  static constexpr int kChunks = D / 64;
+  static constexpr uint32_t kQBytes = 128 * D * 2;   // resident Q or dO (128 rows)
+  static constexpr uint32_t kKVBytes = 64 * D * 2;   // one K or V tile (64 rows)
+  static constexpr uint32_t kdSBytes = 128 * 128;    // dS : [128 q rows x 64 kv]
+  static constexpr uint32_t kOffdO = kQBytes;
+  static constexpr uint32_t kOffK = 2 * kQBytes;
+  static constexpr uint32_t kOffV = kOffK + 2 * kKVBytes;
+  static constexpr uint32_t kOffdS = kOffV + 2 * kKVBytes;
+  static constexpr uint32_t kOffBar = kOffdS + 2 * kdSBytes;
+  static constexpr uint32_t kSmem = kOffBar + 256 + 1024;
+  static constexpr uint32_t tS = 0, tdP = 128, tdQ = 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+    bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __grid_constant__ CUtensorMap tmap_qkv64,
+                  const __grid_constant__ CUtensorMap tmap_do128, const __grid_constant__ CUtensorMap tmap_dqkv,
+                  const BwdParams p) {
+  using C = DqCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = smem + C::kOffdO;
+  uint8_t* sK = smem + C::kOffK;
+  uint8_t* sV = smem + C::kOffV;
+  uint8_t* sdS = smem + C::kOffdS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint64_t* q_full = bars;         // 1
+  uint64_t* kv_full = bars + 1;    // 2
+  uint64_t* kv_empty = bars + 3;   // 2
+  uint64_t* s_full = bars + 5;     // 2
+  uint64_t* s_empty = bars + 7;    // 2 (4 warps)
+  uint64_t* p_full = bars + 9;     // 2 (4 warps)
+  uint64_t* acc_done = bars + 11;  // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqb = p.S / 128;
+  const int qb = nqb - 1 - (int)blockIdx.x;  // heavy blocks first
+  const int bh = blockIdx.y;
+  const int b = bh / p.H, h = bh % p.H;
+  const int hk = h / (p.H / p.Hkv);
+  const int n_kv = p.causal ? (qb * 128 + 128) / 64 : p.S / 64;
+  const int row0 = b * p.S + qb * 128;
+  const int col_q = h * D, col_k = (p.H + hk) * D, col_v = (p.H + p.Hkv + hk) * D;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_qkv128);
+    prefetch_tmap(&tmap_qkv64);
+    prefetch_tmap(&tmap_do128);
+    prefetch_tmap(&tmap_dqkv);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&acc_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * C::kQBytes);
+#pragma unroll
+      for (int c = 0; c < C::kChunks; ++c) {
+        tma_load_2d(&tmap_qkv128, q_full, sQ + c * (128 * 128), col_q + c * 64, row0);
+        tma_load_2d(&tmap_do128, q_full, sdO + c * (128 * 128), col_q + c * 64, row0);
+      }
+      for (int t = 0; t < n_kv; ++t) {
+        const int st = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        const int krow = b * p.S + t * 64;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * C::kKVBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+          tma_load_2d(&tmap_qkv64, &kv_full[st], sK + st * C::kKVBytes + c * (64 * 128), col_k + c * 64, krow);
+          tma_load_2d(&tmap_qkv64, &kv_full[st], sV + st * C::kKVBytes + c * (64 * 128), col_v + c * 64, krow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);  // S[128 q x 64 kv] = Q Kᵀ
+      constexpr uint32_t idesc_a = idesc_bf16(128, D, 0, 1);   // dQ[128 q x D] += dS · K   (K tile as MN-major B)
+      mbar_wait(q_full, 0);
+      auto issue_sd = [&](int t) {
+        const int st = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        mbar_wait(&kv_full[st], ph);
+        mbar_wait(&s_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t q0 = smem_u32(sQ), d0 = smem_u32(sdO);
+        const uint32_t k0 = smem_u32(sK + st * C::kKVBytes), v0 = smem_u32(sV + st * C::kKVBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + C::tS + st * 64, make_smem_desc(q0 + c * (128 * 128) + k * 32, 16, 1024),
+                      make_smem_desc(k0 + c * (64 * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + C::tdP + st * 64, make_smem_desc(d0 + c * (128 * 128) + k * 32, 16, 1024),
+                      make_smem_desc(v0 + c * (64 * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
+        umma_commit(&s_full[st]);
+      };
+      issue_sd(0);
+      for (int t = 0; t < n_kv; ++t) {
+        if (t + 1 < n_kv) issue_sd(t + 1);
+        const int st = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        mbar_wait(&p_full[st], ph);
+        tc_fence_after();
+        const uint32_t da = smem_u32(sdS + st * C::kdSBytes), k0 = smem_u32(sK + st * C::kKVBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)  // K = 64 kv rows
+          umma_bf16(tmem_base + C::tdQ, make_smem_desc(da + kk * 32, 16, 1024), make_smem_desc(k0 + kk * 2048, 64 * 128, 1024),
+                    idesc_a, (t | kk) != 0 ? 1u : 0u);
+        umma_commit(&kv_empty[st]);
+        umma_commit(&acc_done[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int q_idx = qb * 128 + r;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const float lse = p.lse2[((int64_t)bh) * p.S + q_idx];
+    const float del = p.delta[((int64_t)bh) * p.S + q_idx];
+    for (int t = 0; t < n_kv; ++t) {
+      const int st = t & 1;
+      const uint32_t ph = (t >> 1) & 1;
+      mbar_wait(&s_full[st], ph);
+      tc_fence_after();
+      if (t >= 2) mbar_wait(&acc_done[st], ph ^ 1);
+      const int kv0 = t * 64;
+      const bool need_mask = p.causal && (kv0 + 64 > qb * 128);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, sv);
+        tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, dv);
+        tmem_ld_wait();
+        float ds[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float pv = fast_exp2(__uint_as_float(sv[j]) * p.scale_log2 - lse);
+          if (need_mask && (kv0 + half * 32 + j) > q_idx) pv = 0.f;
+          ds[j] = pv * (__uint_as_float(dv[j]) - del) * p.scale;
+        }
+        store_row_chunk_bf16(smem_u32(sdS + st * C::kdSBytes), r, half, ds);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[st]);
+        mbar_arrive(&p_full[st]);
+      }
+    }
+    const int tl = n_kv - 1;
+    mbar_wait(&acc_done[tl & 1], (tl >> 1) & 1);
+    if (n_kv >= 2) mbar_wait(&acc_done[(tl - 1) & 1], ((tl - 1) >> 1) & 1);
+    tc_fence_after();
+    uint8_t* stage = sK;  // the K/V rings (4 x kKVBytes = 64 KB at D = 128) are idle now
+#pragma unroll 1
+    for (int c32 = 0; c32 < D / 32; ++c32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + C::tdQ + lane_addr + c32 * 32, v);
+      tmem_ld_wait();
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+      store_row_chunk_bf16(smem_u32(stage + (c32 >> 1) * (128 * 128)), r, c32 & 1, x);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < C::kChunks; ++c)
+        tma_store_2d(&tmap_dqkv, stage + c * (128 * 128) + q * 32 * 128, col_q + c * 64, row0 + q * 32);
+      bulk_commit();
+      bulk_wait_read<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D>
+int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv, int B, int S,
+               int H, int Hkv, float scale, int causal, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(bwd_dkdv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DkvCfg<D>::kSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DqCfg<D>::kSmem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const uint64_t rows = (uint64_t)B * S, wqkv = (uint64_t)(H + 2 * Hkv) * D, wo = (uint64_t)H * D;
+  {
+    const int64_t warps = (int64_t)rows * H;
+    const int64_t blocks = (warps * 32 + 255) / 256;
+    bwd_delta_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const pb::bf16x8*)dout, (const pb::bf16x8*)out, delta, (int64_t)rows, S,
+                                                          H, D / 8);
+  }
+  CUtensorMap tq128, tq64, tdo64, tdo128, tdq;
+  int rc;
+  if ((rc = pbhost::cached_tmap(&tq128, qkv, rows, wqkv, wqkv, 64, 128, 2))) return rc;
+  if ((rc = pbhost::cached_tmap(&tq64, qkv, rows, wqkv, wqkv, 64, 64, 2))) return rc;
+  if ((rc = pbhost::cached_tmap(&tdo64, dout, rows, wo, wo, 64, 64, 2))) return rc;
+  if ((rc = pbhost::cached_tmap(&tdo128, dout, rows, wo, wo, 64, 128, 2))) return rc;
+  if ((rc = pbhost::cached_tmap(&tdq, dqkv, rows, wqkv, wqkv, 64, 32, 2))) return rc;
+  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal};
+  bwd_dkdv_kernel<D><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
+  bwd_dq_kernel<D><<<dim3(S / 128, B * H), kThreads, DqCfg<D>::kSmem, stream>>>(tq128, tq64, tdo128, tdq, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace
+
+// delta: [B, H, S] fp32 scratch.  dqkv: [B, S, (H+2Hkv)·D] bf16, fully overwritten.
+PB_EXPORT int pb_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,
+                                int B, int S, int H, int Hkv, int D, float scale, int causal, cudaStream_t stream) {
+  if (S % 128 != 0 || H % Hkv != 0) return -1;
+  if (D == 128) return launch_bwd<128>(qkv, out, dout, lse2, delta, dqkv, B, S, H, Hkv, scale, causal, stream);
+  if (D == 64) return launch_bwd<64>(qkv, out, dout, lse2, delta, dqkv, B, S, H, Hkv, scale, causal, stream);
+  return -2;
+}

@@ -1,0 +1,332 @@
+// Flash attention for sm_100a on the fused QKV activation — tcgen05 S = QKᵀ and O += P·V with TMEM accumulators.
+//
+// Input : qkv [B, S, (H + 2·Hkv)·D] bf16 (RoPE already applied in place), heads laid out [Q heads | K heads | V heads]
+// Output: out [B, S, H·D] bf16 (the layout the output-projection GEMM consumes — no transposes, no copies)
+//         lse2 [B, H, S] fp32 = log2-domain log-sum-exp of (scale·log2e·s), consumed by the backward kernels
+//
+// One CTA per (128-row query block, batch, head); heavy (late) causal blocks are scheduled first.
+// Warp roles: w0 TMA loader · w1 MMA issuer · w2 TMEM allocator · w4..7 softmax (one query row per thread = one TMEM lane).
+//   S is double-buffered in TMEM (2 × 128 cols) so QKᵀ of tile t+1 overlaps the softmax of tile t;
+//   P is written bf16 into 128B-swizzled smem (double-buffered) as the K-major A operand of P·V;
+//   O lives in TMEM (D cols); it is only rescaled when a row max grows by more than 2^8 (lazy rescale),
+//   the final 1/l normalisation uses the same stale max, so the result is exact.
+#include "tc_common.cuh"
+#include "tmap.h"
+
+using namespace tc;
+
+namespace {
+
+constexpr int BQ = 128, BKV = 128;
+constexpr int kThreads = 256;
+constexpr float kRescaleThreshold = 8.f;  // log2 units
+
+template <int D>
+struct FwdCfg {
+  static constexpr int kChunks = D / 64;                 // 64-element (128 B) column chunks per row
+  static constexpr uint32_t kQBytes = BQ * D * 2;
+  static constexpr uint32_t kKVBytes = BKV * D * 2;
+  static constexpr uint32_t kPBytes = BQ * BKV * 2;      // 32 KB (two [128 x 64] swizzled blocks)
+  static constexpr uint32_t kOffK = kQBytes;
+  static constexpr uint32_t kOffV = kOffK + 2 * kKVBytes;
+  static constexpr uint32_t kOffP = kOffV + 2 * kKVBytes;
+  static constexpr uint32_t kOffBar = kOffP + 2 * kPBytes;
+  static constexpr uint32_t kSmem = kOffBar + 256 + 1024;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct FwdParams {
+  float* lse2;
+  int B, S, H, Hkv;
+  float scale_log2;  // softmax scale * log2(e)
+  int causal;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1)
+    flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_o,
+                     const FwdParams p) {
+  using C = FwdCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + C::kOffK;
+  uint8_t* sV = smem + C::kOffV;
+  uint8_t* sP = smem + C::kOffP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* v_full = bars + 5;        // 2
+  uint64_t* v_empty = bars + 7;       // 2
+  uint64_t* s_full = bars + 9;        // 2
+  uint64_t* s_empty = bars + 11;      // 2 (4 warp arrivals)
+  uint64_t* p_full = bars + 13;       // 2 (4 warp arrivals)
+  uint64_t* pv_done = bars + 15;      // 2 (commit of P·V for tile t → P buffer free, O stable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqb = p.S / BQ;
+  const int qb = nqb - 1 - (int)blockIdx.x;  // heavy causal blocks first
+  const int bh = blockIdx.y;
+  const int b = bh / p.H, h = bh % p.H;
+  const int hk = h / (p.H / p.Hkv);
+  const int n_kv = p.causal ? qb + 1 : p.S / BKV;
+  const int row0 = b * p.S + qb * BQ;
+  const int col_q = h * D, col_k = (p.H + hk) * D, col_v = (p.H + p.Hkv + hk) * D;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_qkv);
+    prefetch_tmap(&tmap_o);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_O = tmem_base + 256;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA loader
+    if (lane == 0) {
+      mbar_expect_tx(q_full, C::kQBytes);
+#pragma unroll
+      for (int c = 0; c < C::kChunks; ++c) tma_load_2d(&tmap_qkv, q_full, sQ + c * (BQ * 128), col_q + c * 64, row0);
+      for (int t = 0; t < n_kv; ++t) {
+        const int st = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        const int krow = b * p.S + t * BKV;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], C::kKVBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c)
+          tma_load_2d(&tmap_qkv, &k_full[st], sK + st * C::kKVBytes + c * (BKV * 128), col_k + c * 64, krow);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], C::kKVBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c)
+          tma_load_2d(&tmap_qkv, &v_full[st], sV + st * C::kKVBytes + c * (BKV * 128), col_v + c * 64, krow);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = idesc_bf16(BQ, BKV, 0, 0);  // S = Q Kᵀ : both K-major
+      constexpr uint32_t idesc_o = idesc_bf16(BQ, D, 0, 1);    // O += P V : P K-major, V MN-major
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int t) {
+        const int st = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        mbar_wait(&k_full[st], ph);
+        mbar_wait(&s_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sQ), b0 = smem_u32(sK + st * C::kKVBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + st * BKV, make_smem_desc(a0 + c * (BQ * 128) + k * 32, 16, 1024),
+                      make_smem_desc(b0 + c * (BKV * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[st]);
+      };
+      issue_s(0);
+      for (int t = 0; t < n_kv; ++t) {
+        if (t + 1 < n_kv) issue_s(t + 1);  // overlaps the softmax of tile t
+        const int st = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        mbar_wait(&v_full[st], ph);
+        mbar_wait(&p_full[st], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sP + st * C::kPBytes), b0 = smem_u32(sV + st * C::kKVBytes);
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk)
+          umma_bf16(tmem_O, make_smem_desc(a0 + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024),
+                    make_smem_desc(b0 + kk * 2048, BKV * 128, 1024), idesc_o, (t | kk) != 0 ? 1u : 0u);
+        umma_commit(&v_empty[st]);
+        umma_commit(&pv_done[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax + epilogue
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // query row inside the block == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t row_sw = (uint32_t)(r & 7);
+    float m = -INFINITY, l = 0.f;
+    for (int t = 0; t < n_kv; ++t) {
+      const int st = t & 1;
+      const uint32_t ph = (t >> 1) & 1;
+      mbar_wait(&s_full[st], ph);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + st * BKV + lane_addr;
+      const bool diag = p.causal && (t == qb);
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tS + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = __uint_as_float(v[j]);
+          if (!diag || (c * 32 + j) <= r) mx = fmaxf(mx, s);
+        }
+      }
+      mx *= p.scale_log2;
+      // lazy rescale decision (warp-uniform: tcgen05.ld/st below are warp-collective)
+      const bool grow = (mx - m) > kRescaleThreshold;
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      float alpha = 1.f;
+      if (any_grow) {
+        const float m_new = fmaxf(m, mx);
+        alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_new);
+        l *= alpha;
+        m = m_new;
+      }
+      // the P buffer of this stage was last read by P·V of tile t-2
+      if (t >= 2) mbar_wait(&pv_done[st], ph ^ 1);
+      // pass 2: p = exp2(x - m) → bf16 → swizzled smem (K-major A operand), row sum
+      uint8_t* pbuf = sP + st * C::kPBytes;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tS + c * 32, v);
+        tmem_ld_wait();
+        float pr[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = __uint_as_float(v[j]) * p.scale_log2 - m;
+          pr[j] = (!diag || (c * 32 + j) <= r) ? fast_exp2(x) : 0.f;
+          l += pr[j];
+        }
+        const uint32_t sbase = smem_u32(pbuf + (c >> 1) * (BQ * 128)) + r * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t chunk = (uint32_t)((c & 1) * 4 + i);
+          st_shared_v4(sbase + ((chunk ^ row_sw) << 4), pack_bf16x2(__float_as_uint(pr[8 * i]), __float_as_uint(pr[8 * i + 1])),
+                       pack_bf16x2(__float_as_uint(pr[8 * i + 2]), __float_as_uint(pr[8 * i + 3])),
+                       pack_bf16x2(__float_as_uint(pr[8 * i + 4]), __float_as_uint(pr[8 * i + 5])),
+                       pack_bf16x2(__float_as_uint(pr[8 * i + 6]), __float_as_uint(pr[8 * i + 7])));
+        }
+      }
+      // S buffer fully consumed → QKᵀ of tile t+2 may overwrite it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      // rescale O if some row's max moved (needs P·V of tile t-1 finished: O stable)
+      if (any_grow && t > 0) {
+        mbar_wait(&pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+          tmem_st_32x32b_x32(tmem_O + lane_addr + c * 32, v);
+        }
+        tmem_st_wait();
+      }
+      fence_proxy_async();  // P (generic-proxy smem writes) → visible to the tensor core's async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[st]);
+    }
+    // ---- epilogue: O / l → bf16 → swizzled staging (P buffer 0) → TMA store; lse2 = m + log2(l)
+    const int tl = n_kv - 1;
+    mbar_wait(&pv_done[tl & 1], (tl >> 1) & 1);
+    if (n_kv >= 2) mbar_wait(&pv_done[(tl - 1) & 1], ((tl - 1) >> 1) & 1);  // staging aliases P buffer 0/1
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    uint8_t* stage = sP;
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, v);
+      tmem_ld_wait();
+      const uint32_t sbase = smem_u32(stage + (c >> 1) * (BQ * 128)) + r * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t chunk = (uint32_t)((c & 1) * 4 + i);
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          w[e] = pack_bf16x2(__float_as_uint(__uint_as_float(v[8 * i + 2 * e]) * inv_l),
+                             __float_as_uint(__uint_as_float(v[8 * i + 2 * e + 1]) * inv_l));
+        st_shared_v4(sbase + ((chunk ^ row_sw) << 4), w[0], w[1], w[2], w[3]);
+      }
+    }
+    p.lse2[((int64_t)bh) * p.S + qb * BQ + r] = m + log2f(l);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < C::kChunks; ++c)
+        tma_store_2d(&tmap_o, stage + c * (BQ * 128) + q * 32 * 128, col_q + c * 64, row0 + q * 32);
+      bulk_commit();
+      bulk_wait_read<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D>
+int launch_fwd(const void* qkv, void* out, float* lse2, int B, int S, int H, int Hkv, float scale, int causal,
+               cudaStream_t stream) {
+  using C = FwdCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const uint64_t rows = (uint64_t)B * S, wqkv = (uint64_t)(H + 2 * Hkv) * D, wo = (uint64_t)H * D;
+  CUtensorMap tq, to;
+  int rc = pbhost::cached_tmap(&tq, qkv, rows, wqkv, wqkv, 64, 128, 2);
+  if (rc) return rc;
+  rc = pbhost::cached_tmap(&to, out, rows, wo, wo, 64, 32, 2);
+  if (rc) return rc;
+  FwdParams p{lse2, B, S, H, Hkv, scale * 1.4426950408889634f, causal};
+  dim3 grid(S / BQ, B * H);
+  flash_fwd_kernel<D><<<grid, kThreads, C::kSmem, stream>>>(tq, to, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace
+
+PB_EXPORT int pb_flash_attn_fwd(const void* qkv, void* out, float* lse2, int B, int S, int H, int Hkv, int D, float scale,
+                                int causal, cudaStream_t stream) {
+  if (S % BQ != 0 || H % Hkv != 0) return -1;
+  if (D == 128) return launch_fwd<128>(qkv, out, lse2, B, S, H, Hkv, scale, causal, stream);
+  if (D == 64) return launch_fwd<64>(qkv, out, lse2, B, S, H, Hkv, scale, causal, stream);
+  return -2;
+}

@@ -1,0 +1,13 @@
+// Host-side TMA tensor-map construction (cuTensorMapEncodeTiled through the runtime's driver entry point) with a
+// process-wide cache keyed by (pointer, shape, stride, box, element size).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace pbhost {
+// rows x cols matrix (cols contiguous), row stride `ld` elements, 128B-swizzled boxes of box_cols x box_rows.
+// esize: 2 = bf16, 4 = fp32.  Returns 0 on success.
+int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                uint32_t box_rows, int esize = 2);
+int num_sms();
+}  // namespace pbhost

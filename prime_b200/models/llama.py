@@ -106,10 +106,8 @@ class Attention(nn.Module):
         H, Hkv, D = self.n_heads, self.n_kv_heads, self.head_dim
         qkv = ops.linear(x, self.wqkv)  # [B, S, (H+2Hkv)·D]
         qkv = ops.rope_qkv(qkv, cos, sin, H, Hkv)
-        qkv4 = qkv.view(B, S, H + 2 * Hkv, D)
-        q, k, v = qkv4[:, :, :H], qkv4[:, :, H : H + Hkv], qkv4[:, :, H + Hkv :]
-        out = ops.attention(q, k, v, causal=True, impl=attn_impl)  # [B, S, H, D]
-        return ops.linear(out.reshape(B, S, H * D), self.wo)
+        out = ops.attention_qkv(qkv, H, Hkv, causal=True, impl=attn_impl)  # [B, S, H·D], no layout shuffles
+        return ops.linear(out, self.wo)
 
 
 class FeedForward(nn.Module):

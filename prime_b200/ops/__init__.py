@@ -4,6 +4,7 @@ from . import reference  # noqa: F401
 from .functional import (  # noqa: F401
     add_rmsnorm,
     attention,
+    attention_qkv,
     cross_entropy,
     gemm,
     launch_count,

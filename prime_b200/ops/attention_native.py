@@ -1,26 +1,68 @@
-"""Flash-attention on sm_100a (tcgen05 QKᵀ / PV with TMEM accumulators).
+"""Flash attention on sm_100a over the fused QKV activation (tcgen05 QKᵀ / P·V, TMEM accumulators, TMA).
 
-``supported`` gates which shapes the native kernel covers; everything else is routed to the SDPA
-fallback by :func:`prime_b200.ops.functional.attention` (outside the named hot path).
+Forward : ``csrc/attention_sm100.cu``      qkv [B,S,(H+2Hkv)·D] → out [B,S,H·D], lse2 [B,H,S]
+Backward: ``csrc/attention_bwd_sm100.cu``  → dqkv [B,S,(H+2Hkv)·D]  (dK/dV kernel + dQ kernel + delta preprocess)
+
+No transposes, slices or concatenations ever touch HBM: the kernels address Q/K/V heads inside the fused buffer
+through one TMA tensor map and write gradients straight back in the same layout.
 """
 
 from __future__ import annotations
 
+import math
+
 import torch
 
 from . import _lib
+from .functional import _count, _ptr, _stream
 
 
-def supported(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> bool:
+def supported_shape(S: int, D: int, H: int, Hkv: int) -> bool:
+    return D in (64, 128) and S % 128 == 0 and H % Hkv == 0
+
+
+def supported(qkv: torch.Tensor, n_heads: int, n_kv_heads: int) -> bool:
     try:
         lib = _lib.load()
     except Exception:
         return False
     if getattr(lib, "pb_flash_attn_fwd", None) is None:
         return False
-    D = q.shape[-1]
-    return q.dtype == torch.bfloat16 and D in (64, 128) and q.shape[1] % 128 == 0 and q.shape[2] % k.shape[2] == 0
+    D = qkv.shape[-1] // (n_heads + 2 * n_kv_heads)
+    return qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and supported_shape(qkv.shape[1], D, n_heads, n_kv_heads)
 
 
-def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True) -> torch.Tensor:
-    raise NotImplementedError("native flash attention lands in a later milestone")
+class _FlashAttnQKVFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool):
+        lib = _lib.load()
+        B, S, W = qkv.shape
+        D = W // (n_heads + 2 * n_kv_heads)
+        out = torch.empty((B, S, n_heads * D), dtype=qkv.dtype, device=qkv.device)
+        lse2 = torch.empty((B, n_heads, S), dtype=torch.float32, device=qkv.device)
+        scale = 1.0 / math.sqrt(D)
+        rc = lib.pb_flash_attn_fwd(_ptr(qkv), _ptr(out), _ptr(lse2), B, S, n_heads, n_kv_heads, D, scale, int(causal), _stream())
+        _lib.check(rc, "pb_flash_attn_fwd")
+        _count()
+        ctx.save_for_backward(qkv, out, lse2)
+        ctx.meta = (n_heads, n_kv_heads, D, scale, causal)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: torch.Tensor):
+        lib = _lib.load()
+        qkv, out, lse2 = ctx.saved_tensors
+        n_heads, n_kv_heads, D, scale, causal = ctx.meta
+        B, S, _ = qkv.shape
+        dout = dout if dout.is_contiguous() else dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty_like(lse2)
+        rc = lib.pb_flash_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse2), _ptr(delta), _ptr(dqkv), B, S, n_heads,
+                                   n_kv_heads, D, scale, int(causal), _stream())  # fmt: skip
+        _lib.check(rc, "pb_flash_attn_bwd")
+        _count(3)
+        return dqkv, None, None, None
+
+
+def flash_attention_qkv(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool = True) -> torch.Tensor:
+    return _FlashAttnQKVFn.apply(qkv, n_heads, n_kv_heads, causal)

@@ -349,17 +349,11 @@ def cross_entropy(
 # --------------------------------------------------------------------------- attention
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True, impl: str = "auto") -> torch.Tensor:
-    """q [B,S,H,D], k/v [B,S,Hkv,D] (may be strided views of the fused QKV buffer) → [B,S,H,D]."""
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True) -> torch.Tensor:
+    """Unfused-layout attention, q [B,S,H,D], k/v [B,S,Hkv,D] → [B,S,H,D].  SDPA on CUDA (not a hot path: the models
+    call :func:`attention_qkv`), torch reference on CPU."""
     if not q.is_cuda:
         return reference.attention(q, k, v, causal)
-    if impl in ("auto", "native"):
-        from . import attention_native as native_attn
-
-        if native_attn.supported(q, k, v):
-            return native_attn.flash_attention(q, k, v, causal)
-        if impl == "native":
-            raise RuntimeError("native flash-attention kernel does not support this shape")
     import torch.nn.functional as F
 
     H, Hkv = q.shape[2], k.shape[2]
@@ -367,3 +361,23 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = 
         q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=causal, enable_gqa=(H != Hkv)
     )
     return out.transpose(1, 2)
+
+
+def attention_qkv(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool = True, impl: str = "auto") -> torch.Tensor:
+    """Attention over the fused, RoPE-rotated QKV activation [B,S,(H+2Hkv)·D] → [B,S,H·D].
+
+    ``impl``: "native" = tcgen05 flash-attention kernels (error if the shape is unsupported); "sdpa" = library
+    fallback; "auto" = native whenever supported.
+    """
+    B, S, W = qkv.shape
+    D = W // (n_heads + 2 * n_kv_heads)
+    if qkv.is_cuda and impl in ("auto", "native"):
+        from . import attention_native as native
+
+        if native.supported(qkv, n_heads, n_kv_heads):
+            return native.flash_attention_qkv(qkv, n_heads, n_kv_heads, causal)
+        if impl == "native":
+            raise RuntimeError(f"native flash attention does not support S={S}, D={D}, H={n_heads}, Hkv={n_kv_heads}")
+    x = qkv.view(B, S, n_heads + 2 * n_kv_heads, D)
+    q, k, v = x[:, :, :n_heads], x[:, :, n_heads : n_heads + n_kv_heads], x[:, :, n_heads + n_kv_heads :]
+    return attention(q, k, v, causal).reshape(B, S, n_heads * D)

@@ -237,6 +237,13 @@ class Config:
         self._context_path(clean).write_text(json.dumps(snapshot, indent=2))
         return clean
 
+    def update_current_environment_file(self) -> None:
+        """Keep the active named context in sync with edits made while it is selected."""
+        cur = self.current_environment
+        if cur != BUILTIN_CONTEXT and self._context_path(cur).exists():
+            snapshot = {k: self.data.get(k) for k in self.CONTEXT_FIELDS}
+            self._context_path(cur).write_text(json.dumps(snapshot, indent=2))
+
     def list_environments(self) -> list[str]:
         names = {BUILTIN_CONTEXT}
         if self.environments_dir.exists():

@@ -284,3 +284,29 @@ def test_trainer_loss_decreases_on_gpu():
     assert losses[-1] < losses[0] - 0.5, losses
     assert t.outer.outer_step_count == 3
     t.close()
+
+
+# ------------------------------------------------------------------ native flash attention (tcgen05)
+@pytest.mark.parametrize("B,S,H,Hkv,D", [(2, 256, 4, 4, 128), (1, 512, 4, 2, 128), (2, 384, 8, 8, 64), (1, 128, 2, 1, 64), (1, 1024, 2, 2, 128)])
+@pytest.mark.parametrize("causal", [True, False])
+def test_flash_attention_fwd_bwd(B, S, H, Hkv, D, causal):
+    from prime_b200.ops import attention_native as A
+    from prime_b200.ops import reference as R
+
+    torch.manual_seed(S + H + D)
+    W = (H + 2 * Hkv) * D
+    qkv = (torch.randn(B, S, W, device=_dev()) * 0.7).to(torch.bfloat16).requires_grad_(True)
+    assert A.supported(qkv, H, Hkv)
+    out = A.flash_attention_qkv(qkv, H, Hkv, causal)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    torch.cuda.synchronize()
+    ref_in = qkv.detach().float().requires_grad_(True)
+    x = ref_in.view(B, S, H + 2 * Hkv, D)
+    ref = R.attention(x[:, :, :H], x[:, :, H : H + Hkv], x[:, :, H + Hkv :], causal).reshape(B, S, H * D)
+    ref.backward(dout.float())
+    assert _rel_err(out, ref) < 2e-2, f"fwd rel err {_rel_err(out, ref)}"
+    g, gr = qkv.grad.view(B, S, H + 2 * Hkv, D), ref_in.grad.view(B, S, H + 2 * Hkv, D)
+    assert _rel_err(g[:, :, :H], gr[:, :, :H]) < 3e-2, f"dQ rel err {_rel_err(g[:, :, :H], gr[:, :, :H])}"
+    assert _rel_err(g[:, :, H : H + Hkv], gr[:, :, H : H + Hkv]) < 3e-2, "dK"
+    assert _rel_err(g[:, :, H + Hkv :], gr[:, :, H + Hkv :]) < 3e-2, "dV"
