@@ -132,7 +132,7 @@ def main() -> None:
     ap.add_argument("--seq", type=int, default=SEQ)
     ap.add_argument("--no-fused-comm", action="store_true", help="baseline B0: NCCL collectives instead of fused P2P kernels")
     ap.add_argument("--attn", default="auto")
-    ap.add_argument("--graphs", type=int, default=1, help="capture each micro-step (fwd+bwd) in a CUDA graph")
+    ap.add_argument("--graphs", type=int, default=0, help="capture each micro-step (fwd+bwd) in a CUDA graph")
     args = ap.parse_args()
 
     if args.impl == "reference":
