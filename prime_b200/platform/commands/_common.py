@@ -21,8 +21,8 @@ def make_app(help: str, default_cmd: str | None = None, **kw: Any) -> PlainTyper
     return PlainTyper(help=help, no_args_is_help=default_cmd is None, **kw)
 
 
-def api() -> APIClient:
-    return APIClient(config=Config(writable=False))
+def api(require_auth: bool = True) -> APIClient:
+    return APIClient(config=Config(writable=False), require_auth=require_auth)
 
 
 def fail(message: str, code: int = 1) -> "typer.Exit":
