@@ -1,0 +1,294 @@
+"""Sharded checkpointing: every rank writes ONLY its 1/F optimizer shard, asynchronously, with an atomic publish.
+
+Layout::
+
+    <ckpt.path>/step_000200/            ← appears atomically (rename of ``.tmp-step_000200``)
+        meta.json                       ← written last by rank 0: config, mesh, step counters, shard table
+        rank_00003.pbck                 ← JSON header + raw little-endian tensor bytes (no pickle → safe to load)
+    <ckpt.path>/latest                  ← text file naming the newest complete step (written after the rename)
+
+Write path (``save``): the shard (master + m + v + θ₀ + momentum = 20 B/param/F) is first cloned on the device at HBM
+speed (≈7 ms for a whole 1B model; 180 GB parts have the room), so training resumes immediately; the clone drains to
+reusable pinned host buffers on a side stream (PCIe 5, ≈0.4 s for 22 GB, overlapped with the next steps), a writer thread
+streams the pinned buffers to disk and fsyncs, then ranks meet on a barrier and rank 0 publishes by rename.
+
+Resume (``load``): ``ckpt.resume = <dir> | "latest"``; the shard table is validated against the live engine
+(bucket layout, fsdp size) before any tensor is copied; the data loader position and RNG state come back too.
+
+This is the training-side analogue of the reference's only "checkpoint-like" pipelines — the resumable chunked upload of
+``prime env push`` (reference: packages/prime/src/prime_cli/commands/env.py:1150-1340) and hosted-RL checkpoint listing
+(reference: packages/prime/src/prime_cli/api/rl.py:316-340); BASELINE.json's DiLoCo contract requires the real thing.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import shutil
+import struct
+import threading
+import time
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+MAGIC = b"PBCK0001"
+_NP = {torch.float32: np.float32, torch.int8: np.int8, torch.int64: np.int64, torch.uint8: np.uint8, torch.float16: np.float16,
+       torch.int32: np.int32, torch.bfloat16: np.uint16}  # fmt: skip
+_DT = {str(k).replace("torch.", ""): k for k in _NP}
+
+
+def step_dir(root: Path, step: int) -> Path:
+    return Path(root) / f"step_{step:06d}"
+
+
+def list_steps(root: Path) -> list[int]:
+    out = []
+    for p in Path(root).glob("step_*"):
+        if p.is_dir() and (p / "meta.json").exists():
+            try:
+                out.append(int(p.name.split("_", 1)[1]))
+            except ValueError:
+                pass
+    return sorted(out)
+
+
+def resolve_resume(spec: str, root: str | None) -> Path | None:
+    """``"latest"`` → newest complete step under ``root``; otherwise a path to a step directory (or a root holding steps)."""
+    if spec == "latest":
+        if root is None:
+            return None
+        steps = list_steps(Path(root))
+        return step_dir(Path(root), steps[-1]) if steps else None
+    p = Path(spec)
+    if (p / "meta.json").exists():
+        return p
+    steps = list_steps(p)
+    if steps:
+        return step_dir(p, steps[-1])
+    raise FileNotFoundError(f"no complete checkpoint at {spec}")
+
+
+# ------------------------------------------------------------------------------------------------- shard file format
+def write_shard(path: Path, tensors: dict[str, torch.Tensor], extra: dict[str, Any]) -> int:
+    """Header (JSON: name → dtype/shape/offset/nbytes, plus ``extra``) then 64-byte-aligned raw tensor bytes. Returns bytes written."""
+    table, off = {}, 0
+    for name, t in tensors.items():
+        nbytes = t.numel() * t.element_size()
+        table[name] = {"dtype": str(t.dtype).replace("torch.", ""), "shape": list(t.shape), "offset": off, "nbytes": nbytes}
+        off += (nbytes + 63) & ~63
+    header = json.dumps({"tensors": table, "extra": extra}).encode()
+    pad = (-(len(MAGIC) + 8 + len(header))) % 64
+    with open(path, "wb") as f:
+        f.write(MAGIC)
+        f.write(struct.pack("<Q", len(header) + pad))
+        f.write(header + b" " * pad)
+        base = f.tell()
+        for name, t in tensors.items():
+            f.seek(base + table[name]["offset"])
+            if t.numel():
+                f.write(memoryview(t.contiguous().view(-1).view(torch.uint8).numpy()))
+        f.truncate(base + off)
+        f.flush()
+        os.fsync(f.fileno())
+        return base + off
+
+
+def read_shard(path: Path, device: torch.device | str = "cpu") -> tuple[dict[str, torch.Tensor], dict[str, Any]]:
+    with open(path, "rb") as f:
+        if f.read(8) != MAGIC:
+            raise ValueError(f"{path} is not a prime_b200 checkpoint shard")
+        (hlen,) = struct.unpack("<Q", f.read(8))
+        header = json.loads(f.read(hlen))
+        base = f.tell()
+    mm = np.memmap(path, dtype=np.uint8, mode="r", offset=base) if any(d["nbytes"] for d in header["tensors"].values()) else None
+    out = {}
+    for name, d in header["tensors"].items():
+        dt = _DT[d["dtype"]]
+        if d["nbytes"] == 0:
+            out[name] = torch.empty(d["shape"], dtype=dt, device=device)
+            continue
+        raw = torch.from_numpy(np.array(mm[d["offset"] : d["offset"] + d["nbytes"]]))  # copy out of the mapping
+        out[name] = raw.view(dt).reshape(d["shape"]).to(device)
+    return out, header["extra"]
+
+
+# ------------------------------------------------------------------------------------------------- manager
+@dataclass
+class SaveHandle:
+    step: int
+    thread: threading.Thread | None
+    error: list[BaseException]
+
+    def wait(self) -> None:
+        if self.thread is not None:
+            self.thread.join()
+        if self.error:
+            raise RuntimeError(f"checkpoint step {self.step} failed") from self.error[0]
+
+
+class CheckpointManager:
+    def __init__(self, root: str | Path, *, rank: int, world_size: int, topk: int | None = None, async_write: bool = True,
+                 device: torch.device | None = None):  # fmt: skip
+        self.root = Path(root)
+        self.rank, self.world = rank, world_size
+        self.topk, self.async_write = topk, async_write
+        self.device = device or torch.device("cpu")
+        self.cuda = self.device.type == "cuda"
+        self._pending: SaveHandle | None = None
+        self._pinned: dict[str, torch.Tensor] = {}
+        self._stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self._snap_done = torch.cuda.Event() if self.cuda else None
+        self.last_snapshot_s = 0.0
+        self.last_write_s = 0.0
+        self.last_bytes = 0
+        if rank == 0:
+            self.root.mkdir(parents=True, exist_ok=True)
+
+    # -- snapshot: device clone at HBM speed on the training stream, then clone → pinned host on a side stream
+    def _snapshot(self, tensors: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        t0 = time.perf_counter()
+        host: dict[str, torch.Tensor] = {}
+        if not self.cuda:
+            host = {k: v.detach().clone() for k, v in tensors.items()}
+        else:
+            staged = {k: v.detach().clone() for k, v in tensors.items()}  # training may now overwrite the originals
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                for k, v in staged.items():
+                    buf = self._pinned.get(k)
+                    if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                        buf = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                        self._pinned[k] = buf
+                    buf.copy_(v, non_blocking=True)
+                    v.record_stream(self._stream)  # the caching allocator may reuse the clone only after the D2H
+                    host[k] = buf
+                self._snap_done.record(self._stream)
+        self.last_snapshot_s = time.perf_counter() - t0
+        return host
+
+    def _barrier(self) -> None:
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier()
+
+    def _publish(self, step: int, meta: dict[str, Any]) -> None:
+        tmp, final = self.root / f".tmp-step_{step:06d}", step_dir(self.root, step)
+        (tmp / "meta.json").write_text(json.dumps(meta, indent=1))
+        if final.exists():
+            shutil.rmtree(final)
+        os.replace(tmp, final)
+        latest = self.root / ".latest.tmp"
+        latest.write_text(final.name)
+        os.replace(latest, self.root / "latest")
+        if self.topk:
+            for old in list_steps(self.root)[: -self.topk]:
+                shutil.rmtree(step_dir(self.root, old), ignore_errors=True)
+
+    def save(self, step: int, tensors: dict[str, torch.Tensor], extra: dict[str, Any], meta: dict[str, Any]) -> SaveHandle:
+        """Snapshot now, write in the background. ``tensors`` = this rank's shard; ``meta`` = job-level description (rank 0)."""
+        self.wait()  # one checkpoint in flight: the pinned buffers are reused
+        tmp = self.root / f".tmp-step_{step:06d}"
+        if self.rank == 0:
+            if tmp.exists():
+                shutil.rmtree(tmp)
+            tmp.mkdir(parents=True)
+        self._barrier()
+        host = self._snapshot(tensors)
+        handle = SaveHandle(step, None, [])
+
+        def work() -> None:
+            try:
+                t0 = time.perf_counter()
+                if self.cuda:
+                    self._snap_done.synchronize()
+                self.last_bytes = write_shard(tmp / f"rank_{self.rank:05d}.pbck", host, extra)
+                self.last_write_s = time.perf_counter() - t0
+            except BaseException as e:  # surfaced by wait()
+                handle.error.append(e)
+
+        if self.async_write and self.world == 1:
+            # single-rank jobs can publish from the writer thread; multi-rank publish needs a collective → done in wait()
+            def work_and_publish() -> None:
+                work()
+                if not handle.error:
+                    try:
+                        self._publish(step, {**meta, "step": step, "world_size": self.world})
+                    except BaseException as e:
+                        handle.error.append(e)
+
+            handle.thread = threading.Thread(target=work_and_publish, name=f"ckpt-{step}", daemon=True)
+            handle.thread.start()
+            self._pending = handle
+            return handle
+        if self.async_write:
+            handle.thread = threading.Thread(target=work, name=f"ckpt-{step}", daemon=True)
+            handle.thread.start()
+            self._pending = handle
+            self._pending_meta = {**meta, "step": step, "world_size": self.world}
+            return handle
+        work()
+        handle.wait()
+        self._barrier()
+        if self.rank == 0:
+            self._publish(step, {**meta, "step": step, "world_size": self.world})
+        self._barrier()
+        return handle
+
+    def wait(self) -> None:
+        """Finish the in-flight checkpoint (called before the next save, before exit, and by tests)."""
+        h, self._pending = self._pending, None
+        if h is None:
+            return
+        h.wait()
+        if self.world > 1:
+            self._barrier()  # every shard is on disk
+            if self.rank == 0:
+                self._publish(h.step, self._pending_meta)
+            self._barrier()
+
+    def load(self, path: Path) -> tuple[dict[str, torch.Tensor], dict[str, Any], dict[str, Any]]:
+        meta = json.loads((Path(path) / "meta.json").read_text())
+        if meta.get("world_size") != self.world:
+            raise ValueError(f"checkpoint {path} was written by {meta.get('world_size')} ranks; this job has {self.world} "
+                             "(resharding a checkpoint is not supported — restart with the same mesh)")  # fmt: skip
+        tensors, extra = read_shard(Path(path) / f"rank_{self.rank:05d}.pbck", self.device)
+        return tensors, extra, meta
+
+
+# ------------------------------------------------------------------------------------------------- trainer glue
+def trainer_state(trainer) -> tuple[dict[str, torch.Tensor], dict[str, Any]]:
+    eng, outer = trainer.engine, trainer.outer
+    tensors = {"master": eng.master, "exp_avg": eng.exp_avg, "exp_avg_sq": eng.exp_avg_sq}
+    extra: dict[str, Any] = {
+        "trainer_step": trainer.step_count, "engine_step": eng.step_count, "fsdp_size": eng.F, "fsdp_rank": eng.mesh.fsdp_rank,
+        "layout": [[b.name, b.start, b.size, b.shard_start, b.shard_size] for b in eng.buckets],
+        "data": trainer.loader.state_dict(),
+    }  # fmt: skip
+    if outer is not None:
+        tensors.update(theta0=outer.theta0, momentum=outer.momentum)
+        extra["outer_step"] = outer.outer_step_count
+    return tensors, extra
+
+
+def restore_trainer(trainer, tensors: dict[str, torch.Tensor], extra: dict[str, Any], *, skip_dataloader: bool = False) -> None:
+    eng, outer = trainer.engine, trainer.outer
+    layout = [[b.name, b.start, b.size, b.shard_start, b.shard_size] for b in eng.buckets]
+    if extra["layout"] != layout or extra["fsdp_size"] != eng.F:
+        raise ValueError("checkpoint shard layout does not match this model/mesh")
+    with torch.no_grad():
+        eng.master.copy_(tensors["master"])
+        eng.exp_avg.copy_(tensors["exp_avg"])
+        eng.exp_avg_sq.copy_(tensors["exp_avg_sq"])
+        eng.step_count = int(extra["engine_step"])
+        if outer is not None and "theta0" in tensors:
+            outer.theta0.copy_(tensors["theta0"])
+            outer.momentum.copy_(tensors["momentum"])
+            outer.outer_step_count = int(extra.get("outer_step", 0))
+        eng.publish_params()
+    trainer.step_count = int(extra["trainer_step"])
+    if not skip_dataloader:
+        trainer.loader.load_state_dict(extra["data"])

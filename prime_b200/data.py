@@ -100,11 +100,25 @@ class PinnedPrefetcher:
         self.slot = 0
         self.h2d_bytes_per_batch = 2 * batch_size * S * 8
         self._inflight: list[int] = []
+        self._states: list[dict] = []  # dataset state BEFORE each in-flight batch was drawn (checkpoint = oldest one)
         for _ in range(depth - 1):
             self._issue()
 
+    def state_dict(self) -> dict:
+        """Position of the next batch the *consumer* will see (prefetched-but-unconsumed batches are replayed on resume)."""
+        import copy
+
+        return copy.deepcopy(self._states[0]) if self._states else self.ds.state_dict()
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.ds.load_state_dict(sd)
+        self.reset()
+
     def _issue(self) -> None:
         i = self.slot
+        import copy
+
+        self._states.append(copy.deepcopy(self.ds.state_dict()))
         x, y = self.ds.next_batch(self.bs)
         self.host[i][0].copy_(torch.from_numpy(np.ascontiguousarray(x)))
         self.host[i][1].copy_(torch.from_numpy(np.ascontiguousarray(y)))
@@ -117,9 +131,20 @@ class PinnedPrefetcher:
         self._inflight.append(i)
         self.slot = (self.slot + 1) % self.depth
 
+    def reset(self) -> None:
+        """Drop prefetched batches (they were drawn before a dataset ``load_state_dict``) and refill the pipeline."""
+        if self.cuda:
+            self.stream.synchronize()
+        self._inflight.clear()
+        self._states.clear()
+        self.slot = 0
+        for _ in range(self.depth - 1):
+            self._issue()
+
     def next(self) -> Batch:
         self._issue()
         i = self._inflight.pop(0)
+        self._states.pop(0)
         if self.cuda:
             torch.cuda.current_stream().wait_event(self.events[i])
             t = self.dev[i]

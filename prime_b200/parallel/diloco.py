@@ -36,8 +36,23 @@ class OuterHyper:
     compression: str = "int8"  # "int8" | "no"
 
 
+def _all_gather(group, outs: list[torch.Tensor], t: torch.Tensor) -> None:
+    """Works for registered groups and for the standalone per-epoch groups the elastic coordinator builds."""
+    if group is None:
+        dist.all_gather(outs, t)
+    else:
+        group.allgather([outs], [t]).wait()
+
+
+def _all_reduce(group, t: torch.Tensor) -> None:
+    if group is None:
+        dist.all_reduce(t)
+    else:
+        group.allreduce([t]).wait()
+
+
 class DilocoOuter:
-    def __init__(self, engine: ShardedEngine, hyper: OuterHyper, *, diloco_group=None, diloco_ranks=None):
+    def __init__(self, engine: ShardedEngine, hyper: OuterHyper, *, diloco_group=None, diloco_ranks=None, collective: bool = False):
         self.engine, self.hyper = engine, hyper
         self.mesh = engine.mesh
         self.group = diloco_group if diloco_group is not None else self.mesh.diloco_group
@@ -49,7 +64,9 @@ class DilocoOuter:
         self.outer_step_count = 0
         self.last_bytes_on_wire = 0
         self.last_seconds = 0.0
-        self.fused = engine.backend == "fused"
+        # ``collective=True``: elastic jobs — workers are separate process worlds, so the exchange goes through a
+        # (re-creatable) process group instead of the symmetric heap, which cannot span independently launched workers
+        self.fused = engine.backend == "fused" and not collective
         if self.fused:
             heap = engine.heap
             self.q = heap.alloc(n, torch.int8)
@@ -121,8 +138,8 @@ class DilocoOuter:
                 q, sc = reference.quantize_int8_blockwise(pseudo, SHARD_ALIGN)
                 qs = [torch.empty_like(q) for _ in range(W)]
                 scs = [torch.empty_like(sc) for _ in range(W)]
-                dist.all_gather(qs, q, group=self.group)
-                dist.all_gather(scs, sc, group=self.group)
+                _all_gather(self.group, qs, q)
+                _all_gather(self.group, scs, sc)
                 avg = torch.zeros_like(pseudo)
                 for qw, sw in zip(qs, scs):  # fixed worker order → identical result on every worker
                     avg += reference.dequantize_int8_blockwise(qw, sw, SHARD_ALIGN)
@@ -130,7 +147,7 @@ class DilocoOuter:
                 self.last_bytes_on_wire = (W - 1) * (q.numel() + 4 * sc.numel())
             else:
                 avg = pseudo
-                dist.all_reduce(avg, group=self.group)
+                _all_reduce(self.group, avg)
                 avg /= W
                 self.last_bytes_on_wire = 2 * (W - 1) * 4 * avg.numel() // W
         else:

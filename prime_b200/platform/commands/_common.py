@@ -18,7 +18,7 @@ OUTPUT_OPT = typer.Option("table", "--output", "-o", help="Output format: table 
 def make_app(help: str, default_cmd: str | None = None, **kw: Any) -> PlainTyper:
     if default_cmd:
         kw["cls"] = default_group(default_cmd)
-    return PlainTyper(help=help, no_args_is_help=default_cmd is None, **kw)
+    return PlainTyper(help=help, no_args_is_help=default_cmd is None and not kw.get("invoke_without_command"), **kw)
 
 
 def api(require_auth: bool = True) -> APIClient:

@@ -39,7 +39,10 @@ class Trainer:
             world = init_distributed(cfg.mesh.backend) if (_env_world() > 1 or dist.is_initialized()) else WorldInfo.from_env()
             if torch.cuda.is_available():
                 torch.cuda.set_device(world.local_rank)
-            mesh = build_mesh(world, cfg.mesh.num_workers, cfg.mesh.fsdp_size)
+            if cfg.mesh.elastic:  # this process world IS one worker; other workers are reached through the elastic coordinator
+                mesh = build_mesh(world, 1, world.world_size)
+            else:
+                mesh = build_mesh(world, cfg.mesh.num_workers, cfg.mesh.fsdp_size)
         self.mesh = mesh
         self.device = mesh.device
         cuda = self.device.type == "cuda"
@@ -70,14 +73,24 @@ class Trainer:
         if cfg.diloco is not None:
             d = cfg.diloco
             comp = "int8" if d.compression in ("int8", "uint8") else "no"
-            self.outer = DilocoOuter(self.engine, OuterHyper(d.outer_lr, d.outer_momentum, d.nesterov, comp))
+            self.outer = DilocoOuter(self.engine, OuterHyper(d.outer_lr, d.outer_momentum, d.nesterov, comp), collective=cfg.mesh.elastic)
+        self.on_outer_boundary = None  # callable run right before every outer step (elastic rendezvous lives here)
+        self.global_workers = mesh.num_workers  # elastic: updated by the coordinator at every boundary
+        self.data_rank, self.data_world = mesh.world.rank, mesh.world.world_size
 
         # batch plan: optim.batch_size sequences per worker per step
         per_rank = max(1, o.batch_size // mesh.fsdp_size)
         self.micro_bs = min(cfg.train.micro_bs, per_rank)
         self.accum = max(1, per_rank // self.micro_bs)
         self.tokens_per_step = self.micro_bs * self.accum * cfg.data.seq_length * mesh.world.world_size
-        self.dataset = build_dataset(cfg.data, self.model.args.vocab_size, mesh.world.rank, mesh.world.world_size)
+        if cfg.mesh.elastic:  # no global rank exists: derive a stable, distinct data stream from the worker's name
+            import os
+            import zlib
+
+            name = os.environ.get("GLOBAL_UNIQUE_ID") or os.environ.get("GLOBAL_RANK") or "w0"
+            self.data_rank = (zlib.crc32(name.encode()) % 65536) * mesh.fsdp_size + mesh.fsdp_rank
+            self.data_world = 65536 * mesh.fsdp_size
+        self.dataset = build_dataset(cfg.data, self.model.args.vocab_size, self.data_rank, self.data_world)
         self.loader = PinnedPrefetcher(self.dataset, self.micro_bs, self.device)
         self.step_count = 0
         self._loss_acc = torch.zeros((), dtype=torch.float32, device=self.device)
@@ -157,9 +170,12 @@ class Trainer:
         self.step_count += 1
         did_outer = False
         if self.outer is not None and self.step_count % self.cfg.diloco.inner_steps == 0:
+            if self.on_outer_boundary is not None:
+                self.on_outer_boundary()
             self.outer.step()
             did_outer = True
-        return StepResult(self._loss_acc / self.accum, lr, eng.last_grad_norm, self.tokens_per_step, did_outer)
+        tokens = self.tokens_per_step * (self.global_workers if self.cfg.mesh.elastic else 1)
+        return StepResult(self._loss_acc / self.accum, lr, eng.last_grad_norm, tokens, did_outer)
 
     # ------------------------------------------------------------------ helpers
     def flops_per_step(self) -> float:

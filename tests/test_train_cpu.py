@@ -1,0 +1,177 @@
+"""Training entrypoint on CPU: checkpoint shard format, atomic publish + top-k, bit-exact resume, and a real elastic run
+(three independently launched workers over gloo; one is SIGKILLed, a fourth joins and receives the live checkpoint)."""
+
+import json
+import os
+import signal
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import pytest
+import torch
+
+from prime_b200 import checkpoint as ck
+from prime_b200.config import load_config
+from prime_b200.train import train
+
+ROOT = Path(__file__).resolve().parents[1]
+BASE = ["--name_model", "debugmodel", "--data.seq_length", "32", "--optim.batch_size", "4", "--train.micro_bs", "2",
+        "--optim.warmup_steps", "2", "--optim.total_steps", "8", "--diloco.inner_steps", "4"]  # fmt: skip
+
+
+def test_shard_roundtrip_all_dtypes(tmp_path):
+    t = {"f32": torch.randn(1000), "bf16": torch.randn(7, 9).bfloat16(), "i8": torch.randint(-128, 127, (333,), dtype=torch.int8),
+         "i64": torch.arange(5), "empty": torch.zeros(0)}  # fmt: skip
+    n = ck.write_shard(tmp_path / "s.pbck", t, {"k": [1, 2], "nested": {"a": "b"}})
+    assert n == (tmp_path / "s.pbck").stat().st_size
+    back, extra = ck.read_shard(tmp_path / "s.pbck")
+    assert extra == {"k": [1, 2], "nested": {"a": "b"}} and set(back) == set(t)
+    for k in t:
+        assert back[k].dtype == t[k].dtype and back[k].shape == t[k].shape and torch.equal(back[k], t[k])
+    (tmp_path / "junk").write_bytes(b"not a checkpoint")
+    with pytest.raises(ValueError):
+        ck.read_shard(tmp_path / "junk")
+
+
+def test_publish_is_atomic_and_topk_prunes(tmp_path):
+    m = ck.CheckpointManager(tmp_path, rank=0, world_size=1, topk=2, async_write=True)
+    for step in (4, 8, 12):
+        h = m.save(step, {"x": torch.full((10,), float(step))}, {"s": step}, {"note": "t"})
+        h.wait()
+    assert ck.list_steps(tmp_path) == [8, 12] and (tmp_path / "latest").read_text() == "step_000012"
+    assert not list(tmp_path.glob(".tmp-*"))
+    # a crashed writer leaves only a .tmp dir, which is never mistaken for a checkpoint
+    (tmp_path / ".tmp-step_000016").mkdir()
+    (tmp_path / "step_000020").mkdir()  # no meta.json → incomplete
+    assert ck.resolve_resume("latest", str(tmp_path)) == tmp_path / "step_000012"
+    t, extra, meta = m.load(tmp_path / "step_000012")
+    assert t["x"][0] == 12 and extra == {"s": 12} and meta["step"] == 12 and meta["note"] == "t"
+    with pytest.raises(ValueError):
+        ck.CheckpointManager(tmp_path, rank=0, world_size=2).load(tmp_path / "step_000012")
+    assert ck.resolve_resume("latest", str(tmp_path / "nothing")) is None
+    with pytest.raises(FileNotFoundError):
+        ck.resolve_resume(str(tmp_path / "nothing"), None)
+
+
+def _losses(jsonl: Path) -> dict[int, float]:
+    return {r["step"]: r["loss"] for r in map(json.loads, jsonl.read_text().splitlines())}
+
+
+def test_resume_is_bit_exact(tmp_path):
+    a, b = tmp_path / "a", tmp_path / "b"
+    train(load_config(BASE + ["--monitor.jsonl_path", str(a / "log.jsonl")]))
+    straight = _losses(a / "log.jsonl")
+    train(load_config(BASE + ["--ckpt.path", str(b), "--ckpt.interval", "4", "--monitor.jsonl_path", str(b / "log1.jsonl")]), max_steps=4)
+    assert ck.list_steps(b) == [4]
+    out = train(load_config(BASE + ["--ckpt.path", str(b), "--ckpt.interval", "4", "--ckpt.resume", "latest", "--monitor.jsonl_path", str(b / "log2.jsonl")]))
+    resumed = {**_losses(b / "log1.jsonl"), **_losses(b / "log2.jsonl")}
+    assert out["step"] == 8 and sorted(resumed) == list(range(1, 9))
+    assert resumed == straight  # optimizer shards, outer state, LR schedule position and data stream all came back
+    assert ck.list_steps(b) == [4, 8]
+
+
+def test_sigterm_writes_a_final_checkpoint(tmp_path):
+    cmd = [sys.executable, "-m", "prime_b200.train", *BASE, "--optim.total_steps", "100000", "--ckpt.path", str(tmp_path / "c"), "--ckpt.interval", "1000"]
+    logf = tmp_path / "train.log"
+    with open(logf, "w") as lf:
+        p = subprocess.Popen(cmd, cwd=ROOT, env={**os.environ, "PYTHONPATH": str(ROOT)}, stdout=lf, stderr=subprocess.STDOUT)
+        deadline = time.time() + 120
+        while time.time() < deadline and "step 3 " not in logf.read_text():
+            time.sleep(0.1)
+        p.send_signal(signal.SIGTERM)
+        assert p.wait(timeout=60) == 0, logf.read_text()
+    log, err = logf.read_text(), ""
+    steps = ck.list_steps(tmp_path / "c")
+    assert len(steps) == 1 and steps[0] >= 3 and "SIGTERM received" in log + err
+
+
+WORKER = """
+import os, sys
+sys.path.insert(0, {root!r})
+from prime_b200.config import load_config
+from prime_b200.train import train
+cfg = load_config({argv!r})
+print("FINAL", train(cfg), flush=True)
+"""
+
+
+@pytest.mark.slow
+def test_elastic_drop_and_join_end_to_end(tmp_path):
+    from prime_b200.parallel import elastic as el
+
+    served = el.serve(0)
+    argv = ["--name_model", "debugmodel", "--data.seq_length", "32", "--optim.batch_size", "2", "--train.micro_bs", "2", "--optim.warmup_steps", "2",
+            "--optim.total_steps", "60", "--diloco.inner_steps", "4", "--mesh.elastic", "true", "--mesh.num_workers", "3",
+            "--mesh.heartbeat_interval_s", "0.1", "--mesh.heartbeat_timeout_s", "1.5", "--train.log_model_hash", "true"]  # fmt: skip
+
+    def launch(name, extra=()):
+        env = {**os.environ, "PYTHONPATH": str(ROOT), "GLOBAL_ADDR": "127.0.0.1", "GLOBAL_PORT": str(served.port), "GLOBAL_UNIQUE_ID": name,
+               "PRIME_B200_STEP_DELAY_S": "0.3"}  # fmt: skip
+        log = open(tmp_path / f"{name}.log", "w")
+        return subprocess.Popen([sys.executable, "-c", WORKER.format(root=str(ROOT), argv=argv + ["--monitor.jsonl_path", str(tmp_path / f"{name}.jsonl"), *extra])],
+                                cwd=ROOT, env=env, stdout=log, stderr=subprocess.STDOUT)  # fmt: skip
+
+    def wait_for(path, needle, timeout=120):
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            if path.exists() and needle in path.read_text():
+                return
+            time.sleep(0.1)
+        raise AssertionError(f"{needle!r} never appeared in {path.name}:\n{path.read_text() if path.exists() else ''}")
+
+    procs = {n: launch(n) for n in ("w0", "w1", "w2")}
+    try:
+        wait_for(tmp_path / "w0.log", "members=['w0', 'w1', 'w2']")
+        wait_for(tmp_path / "w0.log", "step 5 ")  # past the first outer step with 3 workers
+        procs["w2"].kill()  # no goodbye: must be detected by heartbeat timeout
+        wait_for(tmp_path / "w0.log", "members=['w0', 'w1']")
+        procs["w3"] = launch("w3")
+        wait_for(tmp_path / "w3.log", "received live checkpoint from w0")
+        wait_for(tmp_path / "w0.log", "members=['w0', 'w1', 'w3']")
+        for n in ("w0", "w1", "w3"):
+            assert procs[n].wait(timeout=180) == 0, (tmp_path / f"{n}.log").read_text()
+    finally:
+        for p in procs.values():
+            if p.poll() is None:
+                p.kill()
+    rows = {n: [json.loads(x) for x in (tmp_path / f"{n}.jsonl").read_text().splitlines()] for n in ("w0", "w1", "w3")}
+    assert {r["workers"] for r in rows["w0"]} >= {3, 2}
+    # after every outer step the replicas hold the same parameters, including the worker that joined mid-run
+    final = {n: [r for r in rows[n] if r.get("outer")][-1] for n in rows}
+    assert final["w0"]["step"] == final["w1"]["step"] == final["w3"]["step"] == 60
+    assert final["w0"]["param_hash"] == final["w1"]["param_hash"] == final["w3"]["param_hash"]
+    del served.store
+
+
+def test_every_shipped_config_validates():
+    seen = {}
+    for f in sorted((ROOT / "configs").glob("*/*.toml")):
+        cfg = load_config([f"@{f}"])
+        seen[f"{f.parent.name}/{f.name}"] = cfg
+    # the five BASELINE.json configurations
+    assert seen["150M/gloo_2x1.toml"].diloco.inner_steps == 10 and seen["150M/gloo_2x1.toml"].mesh.backend == "gloo"
+    c = seen["1B/diloco_4x2.toml"]
+    assert (c.name_model, c.diloco.inner_steps, c.mesh.num_workers, c.mesh.fsdp_size, c.diloco.compression) == ("1B", 100, 4, 2, "int8")
+    c = seen["7B/diloco_2x4.toml"]
+    assert (c.name_model, c.diloco.inner_steps, c.mesh.num_workers, c.mesh.fsdp_size) == ("7B", 500, 2, 4)
+    assert seen["7B/fsdp_8.toml"].diloco is None and seen["7B/fsdp_8.toml"].mesh.fsdp_size == 8
+    assert seen["1B/elastic.toml"].mesh.elastic and seen["1B/elastic.toml"].mesh.num_workers == 4
+
+
+@pytest.mark.slow
+def test_entrypoint_under_torchrun_gloo_2_workers(tmp_path):
+    """BASELINE config 1 shape (2 workers × 1 rank, gloo, int8 outer exchange) through ``python -m diloco.train`` — shrunk to the debug model."""
+    port = 29650 + os.getpid() % 200
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           "-m", "diloco.train", f"@{ROOT / 'configs/150M/gloo_2x1.toml'}", "--name_model", "debugmodel", "--data.seq_length", "32",
+           "--optim.total_steps", "6", "--diloco.inner_steps", "3", "--optim.warmup_steps", "1", "--train.log_model_hash", "true",
+           "--ckpt.path", str(tmp_path / "ck"), "--ckpt.interval", "3", "--monitor.jsonl_path", str(tmp_path / "log.jsonl")]  # fmt: skip
+    r = subprocess.run(cmd, cwd=ROOT, env={**os.environ, "PYTHONPATH": str(ROOT)}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rows = [json.loads(x) for x in (tmp_path / "log.jsonl").read_text().splitlines()]
+    outers = [x for x in rows if x["outer"]]
+    assert [x["step"] for x in outers] == [3, 6] and all(x["outer_bytes"] > 0 for x in outers)
+    assert ck.list_steps(tmp_path / "ck") == [3, 6]
+    assert sorted(p.name for p in (tmp_path / "ck" / "step_000006").iterdir()) == ["meta.json", "rank_00000.pbck", "rank_00001.pbck"]
