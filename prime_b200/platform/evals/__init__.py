@@ -1,5 +1,6 @@
 """Evaluation results SDK: create → push samples (size-adaptive batches, concurrent, retried) → finalize."""
 
+from ..core.client import APIClient, AsyncAPIClient  # noqa: F401
 from .evals import AsyncEvalsClient, EvalsClient, build_batches  # noqa: F401
 from .exceptions import EvalsAPIError, EvaluationNotFoundError, InvalidEvaluationError, InvalidSampleError  # noqa: F401
 from .models import (  # noqa: F401
