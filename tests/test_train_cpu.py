@@ -77,11 +77,15 @@ def test_sigterm_writes_a_final_checkpoint(tmp_path):
     logf = tmp_path / "train.log"
     with open(logf, "w") as lf:
         p = subprocess.Popen(cmd, cwd=ROOT, env={**os.environ, "PYTHONPATH": str(ROOT)}, stdout=lf, stderr=subprocess.STDOUT)
-        deadline = time.time() + 120
-        while time.time() < deadline and "step 3 " not in logf.read_text():
-            time.sleep(0.1)
-        p.send_signal(signal.SIGTERM)
-        assert p.wait(timeout=60) == 0, logf.read_text()
+        try:
+            deadline = time.time() + 120
+            while time.time() < deadline and "step 3 " not in logf.read_text():
+                time.sleep(0.1)
+            p.send_signal(signal.SIGTERM)
+            assert p.wait(timeout=60) == 0, logf.read_text()
+        finally:
+            if p.poll() is None:  # never leave a 100000-step job behind
+                p.kill()
     log, err = logf.read_text(), ""
     steps = ck.list_steps(tmp_path / "c")
     assert len(steps) == 1 and steps[0] >= 3 and "SIGTERM received" in log + err
