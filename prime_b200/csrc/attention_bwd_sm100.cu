@@ -240,21 +240,31 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_after();
       if (it >= 2) mbar_wait(&acc_done[st], ph ^ 1);  // Pᵀ/dSᵀ buffers of this stage are free again
       const bool need_mask = p.causal && (qpos0 < jb * 128 + 128);
-#pragma unroll 1
+      // all four TMEM loads in flight, one wait; the per-query lse/delta rows are warp-uniform 128-bit loads
+      uint32_t sv[64], dv[64];
+#pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, sv);
-        tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, dv);
-        tmem_ld_wait();
+        tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[half * 32]));
+        tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[half * 32]));
+      }
+      const float4* lse4 = reinterpret_cast<const float4*>(lse_row);
+      const float4* del4 = reinterpret_cast<const float4*>(del_row);
+      tmem_ld_wait();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
         float pr[32], ds[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int qc = half * 32 + j;
-          const float lse = __ldg(lse_row + qc), del = __ldg(del_row + qc);
-          float pv = fast_exp2(__uint_as_float(sv[j]) * p.scale_log2 - lse);
-          if (need_mask && kv_idx > qpos0 + qc) pv = 0.f;
-          pr[j] = pv;
-          ds[j] = pv * (__uint_as_float(dv[j]) - del) * p.scale;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 L = __ldg(lse4 + half * 8 + j4), Dl = __ldg(del4 + half * 8 + j4);
+          const float ls[4] = {L.x, L.y, L.z, L.w}, dl[4] = {Dl.x, Dl.y, Dl.z, Dl.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e, qc = half * 32 + j;
+            float pv = fast_exp2(fmaf(__uint_as_float(sv[qc]), p.scale_log2, -ls[e]));
+            if (need_mask && kv_idx > qpos0 + qc) pv = 0.f;
+            pr[j] = pv;
+            ds[j] = pv * (__uint_as_float(dv[qc]) - dl[e]) * p.scale;
+          }
         }
         store_row_chunk_bf16(smem_u32(sP + st * C::kPBytes), r, half, pr);
         store_row_chunk_bf16(smem_u32(sdS + st * C::kPBytes), r, half, ds);
@@ -459,18 +469,21 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (t >= 2) mbar_wait(&acc_done[st], ph ^ 1);
       const int kv0 = t * 64;
       const bool need_mask = p.causal && (kv0 + 64 > qb * 128);
-#pragma unroll 1
+      uint32_t sv[64], dv[64];
+#pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, sv);
-        tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, dv);
-        tmem_ld_wait();
+        tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[half * 32]));
+        tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[half * 32]));
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
         float ds[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float pv = fast_exp2(__uint_as_float(sv[j]) * p.scale_log2 - lse);
+          float pv = fast_exp2(fmaf(__uint_as_float(sv[half * 32 + j]), p.scale_log2, -lse));
           if (need_mask && (kv0 + half * 32 + j) > q_idx) pv = 0.f;
-          ds[j] = pv * (__uint_as_float(dv[j]) - del) * p.scale;
+          ds[j] = pv * (__uint_as_float(dv[half * 32 + j]) - del) * p.scale;
         }
         store_row_chunk_bf16(smem_u32(sdS + st * C::kdSBytes), r, half, ds);
       }

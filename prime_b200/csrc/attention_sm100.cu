@@ -180,18 +180,30 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_after();
       const uint32_t tS = tmem_base + st * BKV + lane_addr;
       const bool diag = p.causal && (t == qb);
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tS + c * 32, v);
-        tmem_ld_wait();
+      // one TMEM read per tile: the whole 128-column score row lives in registers (4 loads in flight, one wait)
+      uint32_t v[BKV];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = __uint_as_float(v[j]);
-          if (!diag || (c * 32 + j) <= r) mx = fmaxf(mx, s);
+      for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      tmem_ld_wait();
+      // S buffer consumed → QKᵀ of tile t+2 may overwrite it while we do the math
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      float mx = -INFINITY;
+      if (diag) {
+#pragma unroll
+        for (int j = 0; j < BKV; ++j)
+          if (j <= r) mx = fmaxf(mx, __uint_as_float(v[j]));
+      } else {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains: FMNMX latency, not throughput
+#pragma unroll
+        for (int j = 0; j < BKV; j += 4) {
+          m4[0] = fmaxf(m4[0], __uint_as_float(v[j]));
+          m4[1] = fmaxf(m4[1], __uint_as_float(v[j + 1]));
+          m4[2] = fmaxf(m4[2], __uint_as_float(v[j + 2]));
+          m4[3] = fmaxf(m4[3], __uint_as_float(v[j + 3]));
         }
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
       mx *= p.scale_log2;
       // lazy rescale decision (warp-uniform: tcgen05.ld/st below are warp-collective)
@@ -204,36 +216,31 @@ __global__ void __launch_bounds__(kThreads, 1)
         l *= alpha;
         m = m_new;
       }
+      // p = exp2(s·scale − m), in place; four partial sums keep the FADD chain short
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < BKV; ++j) {
+        float e = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -m));
+        if (diag && j > r) e = 0.f;
+        l4[j & 3] += e;
+        v[j] = __float_as_uint(e);
+      }
+      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       // the P buffer of this stage was last read by P·V of tile t-2
       if (t >= 2) mbar_wait(&pv_done[st], ph ^ 1);
-      // pass 2: p = exp2(x - m) → bf16 → swizzled smem (K-major A operand), row sum
+      // bf16 → 128B-swizzled smem: the K-major A operand of P·V
       uint8_t* pbuf = sP + st * C::kPBytes;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tS + c * 32, v);
-        tmem_ld_wait();
-        float pr[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = __uint_as_float(v[j]) * p.scale_log2 - m;
-          pr[j] = (!diag || (c * 32 + j) <= r) ? fast_exp2(x) : 0.f;
-          l += pr[j];
-        }
+      for (int c = 0; c < BKV / 32; ++c) {
         const uint32_t sbase = smem_u32(pbuf + (c >> 1) * (BQ * 128)) + r * 128;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t chunk = (uint32_t)((c & 1) * 4 + i);
-          st_shared_v4(sbase + ((chunk ^ row_sw) << 4), pack_bf16x2(__float_as_uint(pr[8 * i]), __float_as_uint(pr[8 * i + 1])),
-                       pack_bf16x2(__float_as_uint(pr[8 * i + 2]), __float_as_uint(pr[8 * i + 3])),
-                       pack_bf16x2(__float_as_uint(pr[8 * i + 4]), __float_as_uint(pr[8 * i + 5])),
-                       pack_bf16x2(__float_as_uint(pr[8 * i + 6]), __float_as_uint(pr[8 * i + 7])));
+          const int o = c * 32 + 8 * i;
+          st_shared_v4(sbase + ((chunk ^ row_sw) << 4), pack_bf16x2(v[o], v[o + 1]), pack_bf16x2(v[o + 2], v[o + 3]),
+                       pack_bf16x2(v[o + 4], v[o + 5]), pack_bf16x2(v[o + 6], v[o + 7]));
         }
       }
-      // S buffer fully consumed → QKᵀ of tile t+2 may overwrite it
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
       // rescale O if some row's max moved (needs P·V of tile t-1 finished: O stable)
       if (any_grow && t > 0) {
         mbar_wait(&pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);

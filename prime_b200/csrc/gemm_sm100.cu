@@ -13,6 +13,12 @@
 // Tile 128 x 256 x 64, 4-stage TMA ring (48 KB / stage), 2 TMEM accumulator stages (2 x 256 cols =
 // the whole 512-column TMEM) so the epilogue of tile i overlaps the main loop of tile i+1.
 // Warp roles: w0 = TMA producer (1 lane), w1 = MMA issuer (1 lane), w2 = TMEM alloc, w4..7 = epilogue.
+//
+// PAIR = 1 is the cta_group::2 variant: a 2-CTA cluster (the two SMs of a TPC) computes a 256 x 256 tile. Each CTA stages its
+// own 128 A rows and HALF of B (128 of the 256 N rows), so per-SM shared-memory traffic per FLOP halves (and the 32 KB stages
+// allow a 6-deep ring); the leader CTA issues M=256 tcgen05.mma.cta_group::2 instructions that read both CTAs' operands and
+// write each CTA's TMEM with its own 128 accumulator rows; both CTAs run the epilogue on their half. Completion is
+// multicast to both CTAs' barriers; the peer's TMA transactions and epilogue arrivals land on the leader's barriers.
 #include <cuda.h>
 
 #include <mutex>
@@ -25,22 +31,29 @@
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kThreads = 256;
 constexpr uint32_t kABytes = BM * BK * 2;  // 16 KB
-constexpr uint32_t kBBytes = BN * BK * 2;  // 32 KB
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kStagingBytes = 4 /*epilogue warps*/ * 2 /*buffers*/ * 4096;  // 32 rows x 128 B per buffer
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kGroupM = 16;  // raster: super-rows of 16 M-tiles keep the A slab L2-resident
+
+// per-variant geometry: PAIR=0 one CTA owns 128 x 256; PAIR=1 a CTA pair owns 256 x 256 and each CTA stages half of B
+template <int PAIR>
+struct Geo {
+  static constexpr int kTileM = PAIR ? 2 * BM : BM;        // rows of C per scheduled tile
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;        // B rows staged by one CTA
+  static constexpr uint32_t kBBytes = kBRows * BK * 2;     // 16 KB | 32 KB
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = PAIR ? 6 : 4;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 using namespace tc;
 
-__host__ __device__ constexpr uint32_t make_idesc(int a_mn, int b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(int a_mn, int b_mn, int m) {
   // c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10), majors (15,16), N>>3 at 17, M>>4 at 24
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
@@ -61,10 +74,18 @@ struct GemmParams {
   void* C;
 };
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+  using G = Geo<PAIR>;
+  constexpr int kStages = G::kStages;
+  constexpr uint32_t kStageBytes = G::kStageBytes;
+  constexpr int kBRows = G::kBRows;
+  constexpr int kTileM = G::kTileM;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+  const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + kStages * kStageBytes;  // 1024-aligned: 4 warps x 2 buffers x 4 KB
@@ -75,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + kTileM - 1) / kTileM, tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
 
@@ -91,13 +112,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs in a pair)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must exist before any remote arrive / TMA completion targets them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -106,27 +131,34 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         int tm, tn;
         tile_coords(tile, tiles_m, tiles_n, tm, tn);
+        const int m0 = tm * kTileM + (int)crank * BM;      // this CTA's A rows
+        const int n0 = tn * BN + (int)crank * kBRows;      // this CTA's share of the B rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          // PAIR: the leader's barrier collects the bytes of BOTH CTAs' loads (complete_tx may precede expect_tx in a phase)
+          if (!PAIR || crank == 0) mbar_expect_tx(&full_bar[stage], (PAIR ? 2u : 1u) * kStageBytes);
+          auto load = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+            if (PAIR) tma_load_2d_pair(m, &full_bar[stage], dst, c0, c1);
+            else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
+          };
           if (A_MN == 0) {
-            tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BK, tm * BM);  // box {64 k, 128 m}
+            load(&tmap_a, sa, kb * BK, m0);  // box {64 k, 128 m}
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)  // box {64 m, 64 k} → 8 KB each
-              tma_load_2d(&tmap_a, &full_bar[stage], sa + j * (BK * 128), tm * BM + j * 64, kb * BK);
+              load(&tmap_a, sa + j * (BK * 128), m0 + j * 64, kb * BK);
           }
           if (B_MN == 0) {
-            tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BK, tn * BN);  // box {64 k, 256 n}
+            load(&tmap_b, sb, kb * BK, n0);  // box {64 k, kBRows n}
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(&tmap_b, &full_bar[stage], sb + j * (BK * 128), tn * BN + j * 64, kb * BK);
+            for (int j = 0; j < kBRows / 64; ++j)
+              load(&tmap_b, sb + j * (BK * 128), n0 + j * 64, kb * BK);
           }
           if (++stage == kStages) stage = 0, phase ^= 1;
         }
@@ -134,13 +166,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN, kTileM);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -156,12 +188,17 @@ __global__ void __launch_bounds__(kThreads, 1)
                                              : make_smem_desc(sa + k * 2048, BK * 128, 1024);
             const uint64_t bdesc = B_MN == 0 ? make_smem_desc(sb + k * 32, 16, 1024)
                                              : make_smem_desc(sb + k * 2048, BK * 128, 1024);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (PAIR: in both CTAs)
+          if (PAIR) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) stage = 0, phase ^= 1;
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete → epilogue
+        // accumulator complete → epilogue (PAIR: of both CTAs)
+        if (PAIR) umma_commit_pair(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == kAccStages) acc = 0, acc_phase ^= 1;
       }
     }
@@ -176,12 +213,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
       int tm, tn;
       tile_coords(tile, tiles_m, tiles_n, tm, tn);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row0 = tm * BM + q * 32;
+      const int row0 = tm * kTileM + (int)crank * BM + q * 32;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
       if (p.c_fp32) {
 #pragma unroll 1
@@ -239,30 +276,36 @@ __global__ void __launch_bounds__(kThreads, 1)
       // every TMEM read of this accumulator has completed (wait::ld above) → hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tempty_bar[acc]);  // the leader's MMA warp waits for both CTAs' epilogues
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == kAccStages) acc = 0, acc_phase ^= 1;
     }
     if (lane == 0) bulk_wait_read<0>();  // staging smem must outlive the last store's reads
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA may exit (or free TMEM) while its partner can still signal it / be read by the MMAs
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
 // ---------------------------------------------------------------- host side
 int g_num_sms = 0;
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int PAIR>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int max_ctas,
            cudaStream_t stream) {
+  using G = Geo<PAIR>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)G::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -271,16 +314,53 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int tiles = ((p.M + G::kTileM - 1) / G::kTileM) * ((p.N + BN - 1) / BN);
   int grid = g_num_sms;
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  if (tiles < grid) grid = tiles;
-  gemm_bf16_kernel<A_MN, B_MN><<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, tc, p);
+  if (!PAIR) {
+    if (tiles < grid) grid = tiles;
+    gemm_bf16_kernel<A_MN, B_MN, 0><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, p);
+  } else {
+    grid &= ~1;
+    if (2 * tiles < grid) grid = 2 * tiles;
+    if (grid < 2) grid = 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = G::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1>, ta, tb, tc, p);
+    if (e != cudaSuccess) return (int)e;
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
 
+// 0 = one CTA per 128x256 tile, 1 = CTA pair per 256x256 tile. PB_GEMM_PAIR overrides (A/B testing); default set below.
+int g_pair_mode = -1;
+int pair_mode() {
+  if (g_pair_mode < 0) {
+    const char* e = getenv("PB_GEMM_PAIR");
+    g_pair_mode = e ? (atoi(e) != 0) : 0;
+  }
+  return g_pair_mode;
+}
+
 }  // namespace
+
+// Select the tile scheduler: 0 = single-CTA 128x256 tiles, 1 = CTA-pair 256x256 tiles (cta_group::2), -1 = from PB_GEMM_PAIR.
+PB_EXPORT int pb_gemm_set_pair_mode(int mode) {
+  const int old = pair_mode();
+  g_pair_mode = mode;
+  return old;
+}
 
 // lda/ldb: row stride (elements) of the matrix AS STORED (see header comment).
 PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
@@ -296,8 +376,9 @@ PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, 
   else
     rc = pbhost::cached_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BK);
   if (rc) return rc;
+  const int pair = pair_mode() && M > BM;  // a pair needs two M blocks to be worth it
   if (!b_mn_major)
-    rc = pbhost::cached_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BN);
+    rc = pbhost::cached_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, pair ? BN / 2 : BN);
   else
     rc = pbhost::cached_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK);
   if (rc) return rc;
@@ -306,8 +387,14 @@ PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, 
               : pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 64, 32, 2);
   if (rc) return rc;
   GemmParams p{M, N, K, ldc, a_mn_major, b_mn_major, c_fp32, accumulate, C};
-  if (!a_mn_major && !b_mn_major) return launch<0, 0>(ta, tb, tc, p, max_ctas, stream);
-  if (!a_mn_major && b_mn_major) return launch<0, 1>(ta, tb, tc, p, max_ctas, stream);
-  if (a_mn_major && !b_mn_major) return launch<1, 0>(ta, tb, tc, p, max_ctas, stream);
-  return launch<1, 1>(ta, tb, tc, p, max_ctas, stream);
+  if (pair) {
+    if (!a_mn_major && !b_mn_major) return launch<0, 0, 1>(ta, tb, tc, p, max_ctas, stream);
+    if (!a_mn_major && b_mn_major) return launch<0, 1, 1>(ta, tb, tc, p, max_ctas, stream);
+    if (a_mn_major && !b_mn_major) return launch<1, 0, 1>(ta, tb, tc, p, max_ctas, stream);
+    return launch<1, 1, 1>(ta, tb, tc, p, max_ctas, stream);
+  }
+  if (!a_mn_major && !b_mn_major) return launch<0, 0, 0>(ta, tb, tc, p, max_ctas, stream);
+  if (!a_mn_major && b_mn_major) return launch<0, 1, 0>(ta, tb, tc, p, max_ctas, stream);
+  if (a_mn_major && !b_mn_major) return launch<1, 0, 0>(ta, tb, tc, p, max_ctas, stream);
+  return launch<1, 1, 0>(ta, tb, tc, p, max_ctas, stream);
 }

@@ -105,8 +105,7 @@ class Attention(nn.Module):
         B, S, _ = x.shape
         H, Hkv, D = self.n_heads, self.n_kv_heads, self.head_dim
         qkv = ops.linear(x, self.wqkv)  # [B, S, (H+2Hkv)·D]
-        qkv = ops.rope_qkv(qkv, cos, sin, H, Hkv)
-        out = ops.attention_qkv(qkv, H, Hkv, causal=True, impl=attn_impl)  # [B, S, H·D], no layout shuffles
+        out = ops.rope_attention_qkv(qkv, cos, sin, H, Hkv, causal=True, impl=attn_impl)  # [B, S, H·D], no layout shuffles
         return ops.linear(out, self.wo)
 
 

@@ -11,6 +11,8 @@ from .functional import (  # noqa: F401
     linear,
     reset_launch_count,
     rmsnorm,
+    rope_attention_qkv,
     rope_qkv,
+    set_gemm_pair_mode,
     swiglu,
 )

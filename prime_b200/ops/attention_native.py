@@ -66,3 +66,54 @@ class _FlashAttnQKVFn(torch.autograd.Function):
 
 def flash_attention_qkv(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool = True) -> torch.Tensor:
     return _FlashAttnQKVFn.apply(qkv, n_heads, n_kv_heads, causal)
+
+
+def _rope_inplace(lib, t: torch.Tensor, cos, sin, n_heads: int, n_kv_heads: int, D: int, sign: float) -> None:
+    tokens = t.numel() // t.shape[-1]
+    rc = lib.pb_rope_inplace(_ptr(t), _ptr(cos), _ptr(sin), tokens, t.shape[1], n_heads + n_kv_heads, n_heads + 2 * n_kv_heads, D,
+                             sign, _stream())  # fmt: skip
+    _lib.check(rc, "pb_rope_inplace")
+    _count()
+
+
+class _RopeFlashAttnFn(torch.autograd.Function):
+    """RoPE ⊕ attention as ONE autograd node: the rotation is applied in place on the QKV GEMM output (nobody else reads the
+    un-rotated activation) and the inverse rotation is applied in place on the dQKV this node itself allocates — no copy of
+    the 200 MB gradient, which a stand-alone RoPE node needs because it may not mutate a gradient it does not own."""
+
+    @staticmethod
+    def forward(ctx, qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool):
+        lib = _lib.load()
+        B, S, W = qkv.shape
+        D = W // (n_heads + 2 * n_kv_heads)
+        _rope_inplace(lib, qkv, cos, sin, n_heads, n_kv_heads, D, 1.0)
+        out = torch.empty((B, S, n_heads * D), dtype=qkv.dtype, device=qkv.device)
+        lse2 = torch.empty((B, n_heads, S), dtype=torch.float32, device=qkv.device)
+        scale = 1.0 / math.sqrt(D)
+        rc = lib.pb_flash_attn_fwd(_ptr(qkv), _ptr(out), _ptr(lse2), B, S, n_heads, n_kv_heads, D, scale, int(causal), _stream())
+        _lib.check(rc, "pb_flash_attn_fwd")
+        _count()
+        ctx.save_for_backward(qkv, out, lse2, cos, sin)
+        ctx.meta = (n_heads, n_kv_heads, D, scale, causal)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: torch.Tensor):
+        lib = _lib.load()
+        qkv, out, lse2, cos, sin = ctx.saved_tensors
+        n_heads, n_kv_heads, D, scale, causal = ctx.meta
+        B, S, _ = qkv.shape
+        dout = dout if dout.is_contiguous() else dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty_like(lse2)
+        rc = lib.pb_flash_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse2), _ptr(delta), _ptr(dqkv), B, S, n_heads,
+                                   n_kv_heads, D, scale, int(causal), _stream())  # fmt: skip
+        _lib.check(rc, "pb_flash_attn_bwd")
+        _count(3)
+        _rope_inplace(lib, dqkv, cos, sin, n_heads, n_kv_heads, D, -1.0)  # rotation is orthogonal: backward = inverse rotation
+        return dqkv, None, None, None, None, None
+
+
+def rope_flash_attention_qkv(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, n_kv_heads: int,
+                             causal: bool = True) -> torch.Tensor:  # fmt: skip
+    return _RopeFlashAttnFn.apply(qkv, cos, sin, n_heads, n_kv_heads, causal)

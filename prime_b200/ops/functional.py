@@ -85,6 +85,12 @@ def gemm(
     return out
 
 
+def set_gemm_pair_mode(on: bool | None) -> int:
+    """Tile scheduler of the tcgen05 GEMM: ``False`` = one CTA per 128×256 tile, ``True`` = a CTA pair (``cta_group::2``,
+    the two SMs of a TPC) per 256×256 tile, ``None`` = re-read ``PB_GEMM_PAIR``. Returns the previous mode."""
+    return int(_lib.load().pb_gemm_set_pair_mode(-1 if on is None else int(bool(on))))
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x Wᵀ.  Weight gradient accumulates straight into ``weight.main_grad`` (fp32, fused in the GEMM
     epilogue) when the FSDP engine has attached one; otherwise a bf16 gradient is returned."""
@@ -381,3 +387,15 @@ def attention_qkv(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool
     x = qkv.view(B, S, n_heads + 2 * n_kv_heads, D)
     q, k, v = x[:, :, :n_heads], x[:, :, n_heads : n_heads + n_kv_heads], x[:, :, n_heads + n_kv_heads :]
     return attention(q, k, v, causal).reshape(B, S, n_heads * D)
+
+
+def rope_attention_qkv(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool = True,
+                       impl: str = "auto") -> torch.Tensor:  # fmt: skip
+    """RoPE on the Q/K heads of the fused QKV activation followed by attention → [B,S,H·D]. On the native path both run as
+    one autograd node (in-place rotation forward, in-place inverse rotation of the node's own dQKV backward)."""
+    if qkv.is_cuda and impl in ("auto", "native"):
+        from . import attention_native as native
+
+        if native.supported(qkv, n_heads, n_kv_heads):
+            return native.rope_flash_attention_qkv(qkv, cos, sin, n_heads, n_kv_heads, causal)
+    return attention_qkv(rope_qkv(qkv, cos, sin, n_heads, n_kv_heads), n_heads, n_kv_heads, causal, impl)

@@ -10,7 +10,16 @@ from ..api.availability import AvailabilityClient, GPUAvailability
 from ..helper.short_id import generate_short_id, generate_short_id_disk
 from ..utils.display import status_color
 from ..utils.json_help import list_json_help
+from ..utils.plain import get_console
 from ._common import OUTPUT_OPT, api, console, emit, handle_errors, make_app
+
+_err = get_console(stderr=True)
+
+
+def _warn(message: str) -> None:
+    """Partial-failure notes (one endpoint of several down) go to stderr so that ``--output json`` stays parseable."""
+    _err.print(message)
+
 
 app = make_app("Check GPU and disk availability")
 STOCK_COLORS = {"AVAILABLE": "green", "HIGH": "green", "MEDIUM": "yellow", "LOW": "yellow", "UNAVAILABLE": "red"}
@@ -83,7 +92,7 @@ def list_(
     output: str = OUTPUT_OPT,
 ) -> None:
     """List available GPU offers, cheapest first."""
-    data = AvailabilityClient(api(), on_error=console.print).get(gpu_type=gpu_type, gpu_count=gpu_count, regions=regions, disks=disks)
+    data = AvailabilityClient(api(), on_error=_warn).get(gpu_type=gpu_type, gpu_count=gpu_count, regions=regions, disks=disks)
     rows = [offer_row(g, t) for t, gs in data.items() for g in gs
             if (not provider or g.provider == provider) and (not socket or g.socket == socket)]  # fmt: skip
     rows = group_similar_rows(rows) if group_similar else dedupe(rows)
@@ -107,7 +116,7 @@ def disks(
     output: str = OUTPUT_OPT,
 ) -> None:
     """List persistent-disk offers."""
-    offers = AvailabilityClient(api(), on_error=console.print).get_disks(regions=regions, data_center_id=data_center_id)
+    offers = AvailabilityClient(api(), on_error=_warn).get_disks(regions=regions, data_center_id=data_center_id)
     rows = [{"id": generate_short_id_disk(d), "cloud_id": d.cloud_id, "provider": d.provider or "N/A", "data_center": d.data_center or "N/A",
              "location": d.country or d.region or "N/A", "stock_status": d.stock_status or "N/A",
              "price_per_gb_month": f"${d.spec.price_per_unit:.4f}" if d.spec.price_per_unit is not None else "N/A",

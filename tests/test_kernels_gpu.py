@@ -310,3 +310,27 @@ def test_flash_attention_fwd_bwd(B, S, H, Hkv, D, causal):
     assert _rel_err(g[:, :, :H], gr[:, :, :H]) < 3e-2, f"dQ rel err {_rel_err(g[:, :, :H], gr[:, :, :H])}"
     assert _rel_err(g[:, :, H : H + Hkv], gr[:, :, H : H + Hkv]) < 3e-2, "dK"
     assert _rel_err(g[:, :, H + Hkv :], gr[:, :, H + Hkv :]) < 3e-2, "dV"
+
+
+@pytest.mark.parametrize("H,Hkv,D", [(4, 4, 128), (8, 2, 64)])
+def test_rope_attention_fused_node_matches_reference(H, Hkv, D):
+    """RoPE ⊕ flash attention as one autograd node (in-place rotation, in-place inverse rotation of its own dQKV)."""
+    from prime_b200 import ops
+    from prime_b200.ops import reference as R
+
+    torch.manual_seed(5)
+    B, S = 2, 256
+    W = (H + 2 * Hkv) * D
+    base = (torch.randn(B, S, W, device=_dev()) * 0.7).to(torch.bfloat16).requires_grad_(True)
+    cos, sin = R.rope_tables(S, D, device=_dev())
+    out = ops.rope_attention_qkv(base * 1.0, cos, sin, H, Hkv, causal=True, impl="native")
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    torch.cuda.synchronize()
+    ref_in = base.detach().float().requires_grad_(True)
+    x = ref_in.view(B, S, H + 2 * Hkv, D)
+    rot = R.rope(x[:, :, : H + Hkv], cos, sin)
+    ref = R.attention(rot[:, :, :H], rot[:, :, H:], x[:, :, H + Hkv :], True).reshape(B, S, H * D)
+    ref.backward(dout.float())
+    assert _rel_err(out, ref) < 2e-2
+    assert _rel_err(base.grad, ref_in.grad) < 3e-2

@@ -1,13 +1,18 @@
 #!/bin/bash
 # Run ON the GPU box (via gpurun): ncu --set full captures of every hand-written kernel + launch breakdown of one step.
-# Outputs land in gpurun_out/ncu/*.ncu-rep (read back with `ncu -i … --page raw --csv`).
+# gpurun copies back at most 64 MiB, so every report is exported to CSV here and oversized .ncu-rep files are dropped.
 set -u
 mkdir -p gpurun_out/ncu
-NCU="ncu --set full --clock-control none --import-source on"
-$NCU -k regex:gemm_bf16_kernel -s 30 -c 2 -o gpurun_out/ncu/gemm -f python tools/gemm_bench.py > gpurun_out/ncu/gemm.log 2>&1
-$NCU -k regex:'flash_fwd_kernel|bwd_dkdv_kernel|bwd_dq_kernel|bwd_delta_kernel' -s 16 -c 4 -o gpurun_out/ncu/attn -f python tools/attn_bench.py > gpurun_out/ncu/attn.log 2>&1
-$NCU -k regex:'rmsnorm|rope|swiglu|cross_entropy|colsum|grad_reduce|norm_publish|adamw_push|pseudograd|outer_nesterov|cast_push' -c 60 -o gpurun_out/ncu/ops -f \
+NCU="ncu --set full --clock-control none"
+$NCU --import-source on -k regex:gemm_bf16_kernel -s 30 -c 2 -o gpurun_out/ncu/gemm -f python tools/gemm_bench.py > gpurun_out/ncu/gemm.log 2>&1
+$NCU --import-source on -k regex:'flash_fwd_kernel|bwd_dkdv_kernel|bwd_dq_kernel|bwd_delta_kernel' -s 16 -c 4 -o gpurun_out/ncu/attn -f python tools/attn_bench.py > gpurun_out/ncu/attn.log 2>&1
+$NCU -k regex:'rmsnorm|rope|swiglu|cross_entropy|colsum|grad_reduce|norm_publish|adamw_push|pseudograd|outer_nesterov|cast_push' -c 40 -o gpurun_out/ncu/ops -f \
     python tools/op_bench.py --once > gpurun_out/ncu/ops.log 2>&1
+for r in gemm attn ops; do
+  ncu -i gpurun_out/ncu/$r.ncu-rep --page raw --csv > gpurun_out/ncu/$r.raw.csv 2>/dev/null
+  sz=$(stat -c %s gpurun_out/ncu/$r.ncu-rep 2>/dev/null || echo 0)
+  if [ "$sz" -gt 12000000 ]; then rm -f gpurun_out/ncu/$r.ncu-rep; echo "dropped $r.ncu-rep ($sz bytes), kept CSV"; fi
+done
 ncu --metrics gpu__time_duration.sum --clock-control none -s 2600 -c 2600 --csv --log-file gpurun_out/launches_native.csv \
     python bench.py --steps 1 --warmup 1 --attn native > gpurun_out/launches_native.log 2>&1
-ls -la gpurun_out/ncu
+du -sh gpurun_out; ls -la gpurun_out/ncu
