@@ -20,7 +20,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // w0 TMA · w1 MMA · w2 TMEM alloc · w3 idle · w4..11 math (two warps per TMEM lane quadrant)
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_empty[i], 8);  // one arrive per math warp
+      mbar_init(&p_full[i], 8);
       mbar_init(&acc_done[i], 1);
     }
     fence_barrier_init();
@@ -226,8 +226,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax-backward math + epilogue
     const int q = warp & 3;
-    const int r = q * 32 + lane;      // KV row in the block == TMEM lane
-    const int kv_idx = jb * 128 + r;  // position in the sequence
+    const int half = (warp - 4) >> 2;  // which 32 of the 64 query columns (and, in the epilogue, dV or dK) this warp owns
+    const int r = q * 32 + lane;       // KV row in the block == TMEM lane
+    const int kv_idx = jb * 128 + r;   // position in the sequence
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
@@ -240,30 +241,27 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_after();
       if (it >= 2) mbar_wait(&acc_done[st], ph ^ 1);  // Pᵀ/dSᵀ buffers of this stage are free again
       const bool need_mask = p.causal && (qpos0 < jb * 128 + 128);
-      // all four TMEM loads in flight, one wait; the per-query lse/delta rows are warp-uniform 128-bit loads
-      uint32_t sv[64], dv[64];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[half * 32]));
-        tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[half * 32]));
-      }
-      const float4* lse4 = reinterpret_cast<const float4*>(lse_row);
-      const float4* del4 = reinterpret_cast<const float4*>(del_row);
+      // the two warps of a quadrant split the 64 query columns (P and dS are elementwise: no cross-warp reduction);
+      // both TMEM loads in flight, one wait; the per-query lse/delta values are warp-uniform 128-bit loads
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, sv);
+      tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, dv);
+      const float4* lse4 = reinterpret_cast<const float4*>(lse_row) + half * 8;
+      const float4* del4 = reinterpret_cast<const float4*>(del_row) + half * 8;
       tmem_ld_wait();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      {
         float pr[32], ds[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 L = __ldg(lse4 + half * 8 + j4), Dl = __ldg(del4 + half * 8 + j4);
+          const float4 L = __ldg(lse4 + j4), Dl = __ldg(del4 + j4);
           const float ls[4] = {L.x, L.y, L.z, L.w}, dl[4] = {Dl.x, Dl.y, Dl.z, Dl.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = j4 * 4 + e, qc = half * 32 + j;
-            float pv = fast_exp2(fmaf(__uint_as_float(sv[qc]), p.scale_log2, -ls[e]));
+            float pv = fast_exp2(fmaf(__uint_as_float(sv[j]), p.scale_log2, -ls[e]));
             if (need_mask && kv_idx > qpos0 + qc) pv = 0.f;
             pr[j] = pv;
-            ds[j] = pv * (__uint_as_float(dv[qc]) - dl[e]) * p.scale;
+            ds[j] = pv * (__uint_as_float(dv[j]) - dl[e]) * p.scale;
           }
         }
         store_row_chunk_bf16(smem_u32(sP + st * C::kPBytes), r, half, pr);
@@ -283,8 +281,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (n_it >= 2) mbar_wait(&acc_done[(tl - 1) & 1], ((tl - 1) >> 1) & 1);
     tc_fence_after();
     uint8_t* stage = sP;  // [which(dV,dK)][chunk c] blocks of [128 rows x 128 B]
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
+    {
+      const int which = half;  // warps 4..7 drain dV, warps 8..11 drain dK
 #pragma unroll 1
       for (int c32 = 0; c32 < D / 32; ++c32) {
         uint32_t v[32];
@@ -295,17 +293,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
         store_row_chunk_bf16(smem_u32(stage + (which * C::kChunks + (c32 >> 1)) * (128 * 128)), r, c32 & 1, x);
       }
-    }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
 #pragma unroll
-      for (int c = 0; c < C::kChunks; ++c) {
-        tma_store_2d(&tmap_dqkv, stage + (0 * C::kChunks + c) * (128 * 128) + q * 32 * 128, col_v + c * 64, kvrow0 + q * 32);
-        tma_store_2d(&tmap_dqkv, stage + (1 * C::kChunks + c) * (128 * 128) + q * 32 * 128, col_k + c * 64, kvrow0 + q * 32);
+        for (int c = 0; c < C::kChunks; ++c)
+          tma_store_2d(&tmap_dqkv, stage + (which * C::kChunks + c) * (128 * 128) + q * 32 * 128, (which ? col_k : col_v) + c * 64,
+                       kvrow0 + q * 32);
+        bulk_commit();
+        bulk_wait_read<0>();
       }
-      bulk_commit();
-      bulk_wait_read<0>();
     }
   }
 
@@ -378,8 +375,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_empty[i], 8);  // one arrive per math warp
+      mbar_init(&p_full[i], 8);
       mbar_init(&acc_done[i], 1);
     }
     fence_barrier_init();
@@ -456,6 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;  // which 32 of the 64 kv columns (and which half of the dQ columns in the epilogue)
     const int r = q * 32 + lane;
     const int q_idx = qb * 128 + r;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -469,21 +467,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (t >= 2) mbar_wait(&acc_done[st], ph ^ 1);
       const int kv0 = t * 64;
       const bool need_mask = p.causal && (kv0 + 64 > qb * 128);
-      uint32_t sv[64], dv[64];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[half * 32]));
-        tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[half * 32]));
-      }
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, sv);
+      tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, dv);
       tmem_ld_wait();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      {
         float ds[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float pv = fast_exp2(fmaf(__uint_as_float(sv[half * 32 + j]), p.scale_log2, -lse));
+          float pv = fast_exp2(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse));
           if (need_mask && (kv0 + half * 32 + j) > q_idx) pv = 0.f;
-          ds[j] = pv * (__uint_as_float(dv[half * 32 + j]) - del) * p.scale;
+          ds[j] = pv * (__uint_as_float(dv[j]) - del) * p.scale;
         }
         store_row_chunk_bf16(smem_u32(sdS + st * C::kdSBytes), r, half, ds);
       }
@@ -500,8 +494,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (n_kv >= 2) mbar_wait(&acc_done[(tl - 1) & 1], ((tl - 1) >> 1) & 1);
     tc_fence_after();
     uint8_t* stage = sK;  // the K/V rings (4 x kKVBytes = 64 KB at D = 128) are idle now
+    constexpr int kC32PerWarp = D / 64;  // each warp of a quadrant drains half of the D accumulator columns
 #pragma unroll 1
-    for (int c32 = 0; c32 < D / 32; ++c32) {
+    for (int i = 0; i < kC32PerWarp; ++i) {
+      const int c32 = half * kC32PerWarp + i;
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_base + C::tdQ + lane_addr + c32 * 32, v);
       tmem_ld_wait();
@@ -512,10 +508,19 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     fence_proxy_async();
     __syncwarp();
-    if (lane == 0) {
+    // a 64-column chunk is stored once both 32-column halves are in smem: D=128 → each warp owns one whole chunk;
+    // D=64 → the two warps share chunk 0, so pair up through a named barrier and let the first warp issue the store
+    if (D == 64) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    if (lane == 0 && (D != 64 || half == 0)) {
+      if (D == 64) {
+        tma_store_2d(&tmap_dqkv, stage + q * 32 * 128, col_q, row0 + q * 32);
+      } else {
 #pragma unroll
-      for (int c = 0; c < C::kChunks; ++c)
-        tma_store_2d(&tmap_dqkv, stage + c * (128 * 128) + q * 32 * 128, col_q + c * 64, row0 + q * 32);
+        for (int i = 0; i < kC32PerWarp / 2; ++i) {
+          const int c = half * (kC32PerWarp / 2) + i;
+          tma_store_2d(&tmap_dqkv, stage + c * (128 * 128) + q * 32 * 128, col_q + c * 64, row0 + q * 32);
+        }
+      }
       bulk_commit();
       bulk_wait_read<0>();
     }

@@ -5,7 +5,10 @@
 //         lse2 [B, H, S] fp32 = log2-domain log-sum-exp of (scale·log2e·s), consumed by the backward kernels
 //
 // One CTA per (128-row query block, batch, head); heavy (late) causal blocks are scheduled first.
-// Warp roles: w0 TMA loader · w1 MMA issuer · w2 TMEM allocator · w4..7 softmax (one query row per thread = one TMEM lane).
+// Warp roles: w0 TMA loader · w1 MMA issuer · w2 TMEM allocator · w4..11 softmax: TMEM lane quadrant q is served by the warp
+//   pair (4+q, 8+q); each warp owns 64 of the 128 score columns of its 32 rows and the pair exchanges the partial row
+//   maximum through 2 KB of smem + a 64-thread named barrier (the softmax phase is issue/latency-bound, not MUFU-bound,
+//   so doubling the warps that work on a tile nearly halves it).
 //   S is double-buffered in TMEM (2 × 128 cols) so QKᵀ of tile t+1 overlaps the softmax of tile t;
 //   P is written bf16 into 128B-swizzled smem (double-buffered) as the K-major A operand of P·V;
 //   O lives in TMEM (D cols); it is only rescaled when a row max grows by more than 2^8 (lazy rescale),
@@ -18,7 +21,7 @@ using namespace tc;
 namespace {
 
 constexpr int BQ = 128, BKV = 128;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // w0 TMA · w1 MMA · w2 TMEM alloc · w3 idle · w4..11 softmax (two warps per TMEM lane quadrant)
 constexpr float kRescaleThreshold = 8.f;  // log2 units
 
 template <int D>
@@ -31,7 +34,9 @@ struct FwdCfg {
   static constexpr uint32_t kOffV = kOffK + 2 * kKVBytes;
   static constexpr uint32_t kOffP = kOffV + 2 * kKVBytes;
   static constexpr uint32_t kOffBar = kOffP + 2 * kPBytes;
-  static constexpr uint32_t kSmem = kOffBar + 256 + 1024;
+  static constexpr uint32_t kOffXchg = kOffBar + 256;          // [parity][half][128 rows] fp32 partial row maxima (2 KB)
+  static constexpr uint32_t kSmem = kOffXchg + 2048;           // 226.25 KB at D=128: no room for alignment slack, so the
+                                                               // dynamic smem base itself is declared 1024-aligned
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -52,8 +57,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     flash_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_o,
                      const FwdParams p) {
   using C = FwdCfg<D>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operands need 1024-byte aligned tiles
   uint8_t* sQ = smem;
   uint8_t* sK = smem + C::kOffK;
   uint8_t* sV = smem + C::kOffV;
@@ -69,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* p_full = bars + 13;       // 2 (4 warp arrivals)
   uint64_t* pv_done = bars + 15;      // 2 (commit of P·V for tile t → P buffer free, O stable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  float* xchg = reinterpret_cast<float*>(smem + C::kOffXchg);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqb = p.S / BQ;
@@ -92,8 +99,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_empty[i], 8);  // one arrive per softmax warp
+      mbar_init(&p_full[i], 8);
       mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
@@ -169,21 +176,25 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + epilogue
     const int q = warp & 3;
-    const int r = q * 32 + lane;  // query row inside the block == TMEM lane
+    const int half = (warp - 4) >> 2;  // which 64 of the 128 score columns (and which half of the O columns) this warp owns
+    const int r = q * 32 + lane;       // query row inside the block == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t row_sw = (uint32_t)(r & 7);
-    float m = -INFINITY, l = 0.f;
+    constexpr int HC = BKV / 2;        // columns per warp
+    constexpr int kOC = D / 64;        // 32-column O chunks per warp
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
+    float m = -INFINITY, l = 0.f;      // m is the pair-wide row max (identical in both warps); l is this warp's partial sum
     for (int t = 0; t < n_kv; ++t) {
       const int st = t & 1;
       const uint32_t ph = (t >> 1) & 1;
       mbar_wait(&s_full[st], ph);
       tc_fence_after();
-      const uint32_t tS = tmem_base + st * BKV + lane_addr;
+      const uint32_t tS = tmem_base + st * BKV + half * HC + lane_addr;
       const bool diag = p.causal && (t == qb);
-      // one TMEM read per tile: the whole 128-column score row lives in registers (4 loads in flight, one wait)
-      uint32_t v[BKV];
+      // one TMEM read per tile: this warp's 64 score columns live in registers (both loads in flight, one wait)
+      uint32_t v[HC];
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      for (int c = 0; c < HC / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       tmem_ld_wait();
       // S buffer consumed → QKᵀ of tile t+2 may overwrite it while we do the math
       tc_fence_before();
@@ -192,12 +203,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       float mx = -INFINITY;
       if (diag) {
 #pragma unroll
-        for (int j = 0; j < BKV; ++j)
-          if (j <= r) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 0; j < HC; ++j)
+          if (half * HC + j <= r) mx = fmaxf(mx, __uint_as_float(v[j]));
       } else {
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains: FMNMX latency, not throughput
 #pragma unroll
-        for (int j = 0; j < BKV; j += 4) {
+        for (int j = 0; j < HC; j += 4) {
           m4[0] = fmaxf(m4[0], __uint_as_float(v[j]));
           m4[1] = fmaxf(m4[1], __uint_as_float(v[j + 1]));
           m4[2] = fmaxf(m4[2], __uint_as_float(v[j + 2]));
@@ -205,8 +216,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
-      mx *= p.scale_log2;
-      // lazy rescale decision (warp-uniform: tcgen05.ld/st below are warp-collective)
+      // pair-wide row max. Slots alternate with tile parity: a warp can only overwrite parity p again after the NEXT
+      // pair barrier, which its partner reaches only after reading this tile's value.
+      float* slot = xchg + (t & 1) * 256;
+      slot[half * 128 + r] = mx;
+      pair_sync();
+      mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]) * p.scale_log2;
+      // lazy rescale decision (warp-uniform: tcgen05.ld/st below are warp-collective; identical in both warps of the pair)
       const bool grow = (mx - m) > kRescaleThreshold;
       const bool any_grow = __any_sync(0xffffffffu, grow);
       float alpha = 1.f;
@@ -219,40 +235,36 @@ __global__ void __launch_bounds__(kThreads, 1)
       // p = exp2(s·scale − m), in place; four partial sums keep the FADD chain short
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < BKV; ++j) {
+      for (int j = 0; j < HC; ++j) {
         float e = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -m));
-        if (diag && j > r) e = 0.f;
+        if (diag && half * HC + j > r) e = 0.f;
         l4[j & 3] += e;
         v[j] = __float_as_uint(e);
       }
       l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       // the P buffer of this stage was last read by P·V of tile t-2
       if (t >= 2) mbar_wait(&pv_done[st], ph ^ 1);
-      // bf16 → 128B-swizzled smem: the K-major A operand of P·V
-      uint8_t* pbuf = sP + st * C::kPBytes;
+      // bf16 → this warp's [128 x 64] 128B-swizzled block of the K-major A operand of P·V
+      const uint32_t sbase = smem_u32(sP + st * C::kPBytes + half * (BQ * 128)) + r * 128;
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        const uint32_t sbase = smem_u32(pbuf + (c >> 1) * (BQ * 128)) + r * 128;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t chunk = (uint32_t)((c & 1) * 4 + i);
-          const int o = c * 32 + 8 * i;
-          st_shared_v4(sbase + ((chunk ^ row_sw) << 4), pack_bf16x2(v[o], v[o + 1]), pack_bf16x2(v[o + 2], v[o + 3]),
-                       pack_bf16x2(v[o + 4], v[o + 5]), pack_bf16x2(v[o + 6], v[o + 7]));
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int o = 8 * i;
+        st_shared_v4(sbase + (((uint32_t)i ^ row_sw) << 4), pack_bf16x2(v[o], v[o + 1]), pack_bf16x2(v[o + 2], v[o + 3]),
+                     pack_bf16x2(v[o + 4], v[o + 5]), pack_bf16x2(v[o + 6], v[o + 7]));
       }
-      // rescale O if some row's max moved (needs P·V of tile t-1 finished: O stable)
+      // rescale this warp's half of the O columns if some row's max moved (needs P·V of tile t-1 finished: O stable)
       if (any_grow && t > 0) {
         mbar_wait(&pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < D / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, v);
+        for (int i = 0; i < kOC; ++i) {
+          const uint32_t a = tmem_O + lane_addr + (half * kOC + i) * 32;
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(a, o);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-          tmem_st_32x32b_x32(tmem_O + lane_addr + c * 32, v);
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+          tmem_st_32x32b_x32(a, o);
         }
         tmem_st_wait();
       }
@@ -266,32 +278,40 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_wait(&pv_done[tl & 1], (tl >> 1) & 1);
     if (n_kv >= 2) mbar_wait(&pv_done[(tl - 1) & 1], ((tl - 1) >> 1) & 1);  // staging aliases P buffer 0/1
     tc_fence_after();
+    {  // total row sum = the two warps' partials (the slot of parity n_kv&1 is not in flight any more)
+      float* slot = xchg + (n_kv & 1) * 256;
+      slot[half * 128 + r] = l;
+      pair_sync();
+      l += slot[(half ^ 1) * 128 + r];
+    }
     const float inv_l = 1.f / l;
     uint8_t* stage = sP;
 #pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
+    for (int i = 0; i < kOC; ++i) {
+      const int c = half * kOC + i;  // 32-column chunk of O
       uint32_t v[32];
       tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, v);
       tmem_ld_wait();
       const uint32_t sbase = smem_u32(stage + (c >> 1) * (BQ * 128)) + r * 128;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t chunk = (uint32_t)((c & 1) * 4 + i);
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t chunk = (uint32_t)((c & 1) * 4 + k);
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          w[e] = pack_bf16x2(__float_as_uint(__uint_as_float(v[8 * i + 2 * e]) * inv_l),
-                             __float_as_uint(__uint_as_float(v[8 * i + 2 * e + 1]) * inv_l));
+          w[e] = pack_bf16x2(__float_as_uint(__uint_as_float(v[8 * k + 2 * e]) * inv_l),
+                             __float_as_uint(__uint_as_float(v[8 * k + 2 * e + 1]) * inv_l));
         st_shared_v4(sbase + ((chunk ^ row_sw) << 4), w[0], w[1], w[2], w[3]);
       }
     }
-    p.lse2[((int64_t)bh) * p.S + qb * BQ + r] = m + log2f(l);
+    if (half == 0) p.lse2[((int64_t)bh) * p.S + qb * BQ + r] = m + log2f(l);
     fence_proxy_async();
     __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < C::kChunks; ++c)
-        tma_store_2d(&tmap_o, stage + c * (BQ * 128) + q * 32 * 128, col_q + c * 64, row0 + q * 32);
+    // D=128: each warp filled one whole 64-column chunk and stores it; D=64: the pair shares chunk 0 → meet, then one store
+    if (D == 64) pair_sync();
+    if (lane == 0 && (D != 64 || half == 0)) {
+      const int c = D == 64 ? 0 : half;
+      tma_store_2d(&tmap_o, stage + c * (BQ * 128) + q * 32 * 128, col_q + c * 64, row0 + q * 32);
       bulk_commit();
       bulk_wait_read<0>();
     }
