@@ -71,6 +71,7 @@ struct GemmParams {
   int ldc;
   int a_mn, b_mn;
   int c_fp32, accumulate;
+  int split_k;  // >1 only with c_fp32 && accumulate: every K slice reduce-adds its partial tile (weight-gradient GEMMs)
   void* C;
 };
 
@@ -97,8 +98,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + kTileM - 1) / kTileM, tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
+  // split-K: work item w = tile * split_k + slice; slice s covers k-blocks [s*kb_per, min(num_kb, (s+1)*kb_per))
+  const int split_k = p.split_k;
+  const int kb_per = (num_kb + split_k - 1) / split_k;
+  const int num_tiles = tiles_m * tiles_n * split_k;  // = number of work items
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -133,10 +137,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t phase = 0;
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         int tm, tn;
-        tile_coords(tile, tiles_m, tiles_n, tm, tn);
+        tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn);
+        const int kb0 = (tile % split_k) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        if (kb0 >= kb1) continue;  // empty K slice (split does not divide K): every role skips it identically
         const int m0 = tm * kTileM + (int)crank * BM;      // this CTA's A rows
         const int n0 = tn * BN + (int)crank * kBRows;      // this CTA's share of the B rows
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
@@ -173,10 +179,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
+        const int kb0 = (tile % split_k) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        if (kb0 >= kb1) continue;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
@@ -188,8 +196,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                                              : make_smem_desc(sa + k * 2048, BK * 128, 1024);
             const uint64_t bdesc = B_MN == 0 ? make_smem_desc(sb + k * 32, 16, 1024)
                                              : make_smem_desc(sb + k * 2048, BK * 128, 1024);
-            if (PAIR) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           // smem slot reusable once these MMAs retire (PAIR: in both CTAs)
           if (PAIR) umma_commit_pair(&empty_bar[stage]);
@@ -215,7 +223,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     int buf = 0;
     for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
       int tm, tn;
-      tile_coords(tile, tiles_m, tiles_n, tm, tn);
+      tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn);
+      if ((tile % split_k) * kb_per >= num_kb) continue;  // empty K slice
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row0 = tm * kTileM + (int)crank * BM + q * 32;
@@ -298,6 +307,20 @@ __global__ void __launch_bounds__(kThreads, 1)
 // ---------------------------------------------------------------- host side
 int g_num_sms = 0;
 
+// Split-K for reduce-add outputs. Measured on B200 (profiles/gemm_splitk_r1.json): for grids that already fill the machine,
+// splitting K to smooth wave quantisation LOSES 3-25 % — the extra fp32 tile reductions cost more than the idle tail — so the
+// automatic policy only splits when the output has fewer than half as many tiles as there are schedulable CTAs (pairs), i.e.
+// when most SMs would otherwise sit idle for the whole kernel; slices keep >= 16 k-blocks (K >= 1024) each.
+int choose_split_k(int tiles, int units, int num_kb) {
+  if (tiles * 2 > units) return 1;
+  int s = units / tiles;
+  if (s > 8) s = 8;
+  while (s > 1 && num_kb / s < 16) --s;
+  return s < 1 ? 1 : s;
+}
+
+int g_split_k_mode = -1;  // -1 auto, 0/1 off, n>1 forced
+
 template <int A_MN, int B_MN, int PAIR>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int max_ctas,
            cudaStream_t stream) {
@@ -314,9 +337,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int tiles = ((p.M + G::kTileM - 1) / G::kTileM) * ((p.N + BN - 1) / BN);
   int grid = g_num_sms;
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  const int tiles = ((p.M + G::kTileM - 1) / G::kTileM) * ((p.N + BN - 1) / BN) * p.split_k;
   if (!PAIR) {
     if (tiles < grid) grid = tiles;
     gemm_bf16_kernel<A_MN, B_MN, 0><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, p);
@@ -362,6 +385,13 @@ PB_EXPORT int pb_gemm_set_pair_mode(int mode) {
   return old;
 }
 
+// Split-K policy for fp32 reduce-add outputs: -1 = automatic (default), 0 = never, n > 1 = always n slices (testing).
+PB_EXPORT int pb_gemm_set_split_k(int mode) {
+  const int old = g_split_k_mode;
+  g_split_k_mode = mode;
+  return old;
+}
+
 // lda/ldb: row stride (elements) of the matrix AS STORED (see header comment).
 PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                            int a_mn_major, int b_mn_major, int c_fp32, int accumulate, int max_ctas,
@@ -386,7 +416,20 @@ PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, 
   rc = c_fp32 ? pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 32, 4)
               : pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 64, 32, 2);
   if (rc) return rc;
-  GemmParams p{M, N, K, ldc, a_mn_major, b_mn_major, c_fp32, accumulate, C};
+  GemmParams p{M, N, K, ldc, a_mn_major, b_mn_major, c_fp32, accumulate, 1, C};
+  if (c_fp32 && accumulate && g_split_k_mode != 0 && g_split_k_mode != 1) {
+    if (g_num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int units = (max_ctas > 0 && max_ctas < g_num_sms) ? max_ctas : g_num_sms;
+    if (pair) units /= 2;
+    const int tile_m = pair ? 2 * BM : BM;
+    const int tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
+    const int num_kb = (K + BK - 1) / BK;
+    p.split_k = g_split_k_mode > 1 ? (num_kb / g_split_k_mode >= 1 ? g_split_k_mode : 1) : choose_split_k(tiles, units > 0 ? units : 1, num_kb);
+  }
   if (pair) {
     if (!a_mn_major && !b_mn_major) return launch<0, 0, 1>(ta, tb, tc, p, max_ctas, stream);
     if (!a_mn_major && b_mn_major) return launch<0, 1, 1>(ta, tb, tc, p, max_ctas, stream);

@@ -14,5 +14,6 @@ from .functional import (  # noqa: F401
     rope_attention_qkv,
     rope_qkv,
     set_gemm_pair_mode,
+    set_gemm_split_k,
     swiglu,
 )

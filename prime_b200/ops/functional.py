@@ -91,6 +91,11 @@ def set_gemm_pair_mode(on: bool | None) -> int:
     return int(_lib.load().pb_gemm_set_pair_mode(-1 if on is None else int(bool(on))))
 
 
+def set_gemm_split_k(mode: int) -> int:
+    """Split-K policy of fp32 reduce-add GEMMs (weight gradients): -1 automatic, 0 off, n>1 force n slices. Returns the old mode."""
+    return int(_lib.load().pb_gemm_set_split_k(int(mode)))
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x Wᵀ.  Weight gradient accumulates straight into ``weight.main_grad`` (fp32, fused in the GEMM
     epilogue) when the FSDP engine has attached one; otherwise a bf16 gradient is returned."""

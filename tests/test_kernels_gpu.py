@@ -334,3 +334,46 @@ def test_rope_attention_fused_node_matches_reference(H, Hkv, D):
     ref.backward(dout.float())
     assert _rel_err(out, ref) < 2e-2
     assert _rel_err(base.grad, ref_in.grad) < 3e-2
+
+
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(256, 256, 64, False, False), (384, 1000, 136, False, True), (640, 264, 4096, True, True), (4096, 4096, 1024, True, False)])
+def test_gemm_pair_and_single_schedulers_agree(pair, M, N, K, a_mn, b_mn):
+    """cta_group::2 (a CTA pair per 256x256 tile, B split across the two CTAs' smem) vs one CTA per 128x256 tile."""
+    from prime_b200 import ops
+
+    old = ops.set_gemm_pair_mode(pair)
+    try:
+        torch.manual_seed(M + N)
+        A = torch.randn(M, K, device=_dev(), dtype=torch.bfloat16) * 0.1
+        B = torch.randn(N, K, device=_dev(), dtype=torch.bfloat16) * 0.1
+        a = A.t().contiguous() if a_mn else A
+        b = B.t().contiguous() if b_mn else B
+        out = ops.gemm(a, b, a_mn_major=a_mn, b_mn_major=b_mn)
+        torch.cuda.synchronize()
+        assert _rel_err(out, A.float() @ B.float().t()) < 1e-2
+    finally:
+        ops.set_gemm_pair_mode(bool(old))
+
+
+@pytest.mark.parametrize("split", [-1, 2, 3, 8])
+@pytest.mark.parametrize("pair", [False, True])
+def test_gemm_split_k_reduce_add(split, pair):
+    """Weight-gradient pattern: fp32 C += AᵀB with K sliced across work items, every slice TMA-reduce-adding its partial tile.
+    K = 17·64 + 8 is not divisible by any split (ragged last slice, and with split 8 an empty one)."""
+    from prime_b200 import ops
+
+    old_p, old_s = ops.set_gemm_pair_mode(pair), ops.set_gemm_split_k(split)
+    try:
+        torch.manual_seed(3)
+        M, N, K = 512, 768, 17 * 64 + 8
+        A = torch.randn(K, M, device=_dev(), dtype=torch.bfloat16)
+        B = torch.randn(K, N, device=_dev(), dtype=torch.bfloat16)
+        C = torch.randn(M, N, device=_dev(), dtype=torch.float32)
+        ref = C + A.float().t() @ B.float()
+        ops.gemm(A, B, a_mn_major=True, b_mn_major=True, out=C, accumulate=True)
+        torch.cuda.synchronize()
+        assert _rel_err(C, ref) < 2e-3
+    finally:
+        ops.set_gemm_pair_mode(bool(old_p))
+        ops.set_gemm_split_k(old_s)
