@@ -4,7 +4,10 @@
 // Output: out [B, S, H·D] bf16 (the layout the output-projection GEMM consumes — no transposes, no copies)
 //         lse2 [B, H, S] fp32 = log2-domain log-sum-exp of (scale·log2e·s), consumed by the backward kernels
 //
-// One CTA per (128-row query block, batch, head); heavy (late) causal blocks are scheduled first.
+// Persistent: one CTA per SM walks a static work list of (128-row query block, batch, head) items, heavy (late) causal blocks
+// first. All rings (K/V smem, S in TMEM, P in smem) run on one global tile counter, so the TMA loader and the MMA issuer flow
+// straight into the next item while the softmax warps are still normalising/storing the previous one: the per-item pipeline
+// fill/drain (≈7 µs measured with one CTA per item — more than the math of a short causal item) is paid once per CTA.
 // Warp roles: w0 TMA loader · w1 MMA issuer · w2 TMEM allocator · w4..11 softmax: TMEM lane quadrant q is served by the warp
 //   pair (4+q, 8+q); each warp owns 64 of the 128 score columns of its 32 rows and the pair exchanges the partial row
 //   maximum through 2 KB of smem + a 64-thread named barrier (the softmax phase is issue/latency-bound, not MUFU-bound,
@@ -65,27 +68,29 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* sV = smem + C::kOffV;
   uint8_t* sP = smem + C::kOffP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // 2
-  uint64_t* k_empty = bars + 3;       // 2
-  uint64_t* v_full = bars + 5;        // 2
-  uint64_t* v_empty = bars + 7;       // 2
-  uint64_t* s_full = bars + 9;        // 2
-  uint64_t* s_empty = bars + 11;      // 2 (4 warp arrivals)
-  uint64_t* p_full = bars + 13;       // 2 (4 warp arrivals)
-  uint64_t* pv_done = bars + 15;      // 2 (commit of P·V for tile t → P buffer free, O stable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* q_full = bars;            // 1   producer → MMA, one phase per work item
+  uint64_t* q_empty = bars + 1;       // 1   MMA → producer: every QKᵀ of the item has retired, Q smem reusable
+  uint64_t* k_full = bars + 2;        // 2   K/V rings, S and P buffers run on ONE global tile counter across work items
+  uint64_t* k_empty = bars + 4;       // 2
+  uint64_t* v_full = bars + 6;        // 2
+  uint64_t* v_empty = bars + 8;       // 2
+  uint64_t* s_full = bars + 10;       // 2
+  uint64_t* s_empty = bars + 12;      // 2 (8 warp arrivals)
+  uint64_t* p_full = bars + 14;       // 2 (8 warp arrivals)
+  uint64_t* pv_done = bars + 16;      // 2 (commit of P·V for a tile → P buffer free, O stable)
+  uint64_t* o_free = bars + 18;       // 1 (8 warp arrivals): the epilogue has read O out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   float* xchg = reinterpret_cast<float*>(smem + C::kOffXchg);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqb = p.S / BQ;
-  const int qb = nqb - 1 - (int)blockIdx.x;  // heavy causal blocks first
-  const int bh = blockIdx.y;
-  const int b = bh / p.H, h = bh % p.H;
-  const int hk = h / (p.H / p.Hkv);
-  const int n_kv = p.causal ? qb + 1 : p.S / BKV;
-  const int row0 = b * p.S + qb * BQ;
-  const int col_q = h * D, col_k = (p.H + hk) * D, col_v = (p.H + p.Hkv + hk) * D;
+  const int BH = p.B * p.H;
+  const int n_items = nqb * BH;
+  // work item w → (query block, batch·head); heavy (late) causal blocks first, round-robin over the persistent CTAs
+  auto item = [&](int w, int& qb, int& bh) {
+    qb = nqb - 1 - w / BH;
+    bh = w % BH;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_qkv);
@@ -93,6 +98,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, 8);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -113,25 +120,36 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_O = tmem_base + 256;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA loader
+    // ------------------------------------------------------------------ TMA loader (runs ahead across work items)
     if (lane == 0) {
-      mbar_expect_tx(q_full, C::kQBytes);
+      int g = 0;  // global kv-tile counter
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        int qb, bh;
+        item(w, qb, bh);
+        const int b = bh / p.H, h = bh % p.H, hk = h / (p.H / p.Hkv);
+        const int n_kv = p.causal ? qb + 1 : p.S / BKV;
+        const int row0 = b * p.S + qb * BQ;
+        const int col_q = h * D, col_k = (p.H + hk) * D, col_v = (p.H + p.Hkv + hk) * D;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, C::kQBytes);
 #pragma unroll
-      for (int c = 0; c < C::kChunks; ++c) tma_load_2d(&tmap_qkv, q_full, sQ + c * (BQ * 128), col_q + c * 64, row0);
-      for (int t = 0; t < n_kv; ++t) {
-        const int st = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
-        const int krow = b * p.S + t * BKV;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], C::kKVBytes);
+        for (int c = 0; c < C::kChunks; ++c) tma_load_2d(&tmap_qkv, q_full, sQ + c * (BQ * 128), col_q + c * 64, row0);
+        for (int t = 0; t < n_kv; ++t, ++g) {
+          const int st = g & 1;
+          const uint32_t ph = (g >> 1) & 1;
+          const int krow = b * p.S + t * BKV;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], C::kKVBytes);
 #pragma unroll
-        for (int c = 0; c < C::kChunks; ++c)
-          tma_load_2d(&tmap_qkv, &k_full[st], sK + st * C::kKVBytes + c * (BKV * 128), col_k + c * 64, krow);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], C::kKVBytes);
+          for (int c = 0; c < C::kChunks; ++c)
+            tma_load_2d(&tmap_qkv, &k_full[st], sK + st * C::kKVBytes + c * (BKV * 128), col_k + c * 64, krow);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], C::kKVBytes);
 #pragma unroll
-        for (int c = 0; c < C::kChunks; ++c)
-          tma_load_2d(&tmap_qkv, &v_full[st], sV + st * C::kKVBytes + c * (BKV * 128), col_v + c * 64, krow);
+          for (int c = 0; c < C::kChunks; ++c)
+            tma_load_2d(&tmap_qkv, &v_full[st], sV + st * C::kKVBytes + c * (BKV * 128), col_v + c * 64, krow);
+        }
       }
     }
   } else if (warp == 1) {
@@ -139,10 +157,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc_bf16(BQ, BKV, 0, 0);  // S = Q Kᵀ : both K-major
       constexpr uint32_t idesc_o = idesc_bf16(BQ, D, 0, 1);    // O += P V : P K-major, V MN-major
-      mbar_wait(q_full, 0);
-      auto issue_s = [&](int t) {
-        const int st = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
+      int g = 0;
+      int it = 0;
+      auto issue_s = [&](int gg, bool last_of_item) {
+        const int st = gg & 1;
+        const uint32_t ph = (gg >> 1) & 1;
         mbar_wait(&k_full[st], ph);
         mbar_wait(&s_empty[st], ph ^ 1);
         tc_fence_after();
@@ -155,22 +174,30 @@ __global__ void __launch_bounds__(kThreads, 1)
                       make_smem_desc(b0 + c * (BKV * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[st]);
+        if (last_of_item) umma_commit(q_empty);  // the producer may now overwrite Q with the next item's block
       };
-      issue_s(0);
-      for (int t = 0; t < n_kv; ++t) {
-        if (t + 1 < n_kv) issue_s(t + 1);  // overlaps the softmax of tile t
-        const int st = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
-        mbar_wait(&v_full[st], ph);
-        mbar_wait(&p_full[st], ph);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(sP + st * C::kPBytes), b0 = smem_u32(sV + st * C::kKVBytes);
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        int qb, bh;
+        item(w, qb, bh);
+        const int n_kv = p.causal ? qb + 1 : p.S / BKV;
+        mbar_wait(q_full, it & 1);
+        issue_s(g, n_kv == 1);
+        for (int t = 0; t < n_kv; ++t, ++g) {
+          if (t + 1 < n_kv) issue_s(g + 1, t + 2 == n_kv);  // overlaps the softmax of tile t
+          const int st = g & 1;
+          const uint32_t ph = (g >> 1) & 1;
+          mbar_wait(&v_full[st], ph);
+          mbar_wait(&p_full[st], ph);
+          if (t == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);  // previous item's epilogue has drained O
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sP + st * C::kPBytes), b0 = smem_u32(sV + st * C::kKVBytes);
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk)
-          umma_bf16(tmem_O, make_smem_desc(a0 + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024),
-                    make_smem_desc(b0 + kk * 2048, BKV * 128, 1024), idesc_o, (t | kk) != 0 ? 1u : 0u);
-        umma_commit(&v_empty[st]);
-        umma_commit(&pv_done[st]);
+          for (int kk = 0; kk < BKV / 16; ++kk)
+            umma_bf16(tmem_O, make_smem_desc(a0 + (kk >> 2) * (BQ * 128) + (kk & 3) * 32, 16, 1024),
+                      make_smem_desc(b0 + kk * 2048, BKV * 128, 1024), idesc_o, (t | kk) != 0 ? 1u : 0u);
+          umma_commit(&v_empty[st]);
+          umma_commit(&pv_done[st]);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -183,137 +210,154 @@ __global__ void __launch_bounds__(kThreads, 1)
     constexpr int HC = BKV / 2;        // columns per warp
     constexpr int kOC = D / 64;        // 32-column O chunks per warp
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
-    float m = -INFINITY, l = 0.f;      // m is the pair-wide row max (identical in both warps); l is this warp's partial sum
-    for (int t = 0; t < n_kv; ++t) {
-      const int st = t & 1;
-      const uint32_t ph = (t >> 1) & 1;
-      mbar_wait(&s_full[st], ph);
-      tc_fence_after();
-      const uint32_t tS = tmem_base + st * BKV + half * HC + lane_addr;
-      const bool diag = p.causal && (t == qb);
-      // one TMEM read per tile: this warp's 64 score columns live in registers (both loads in flight, one wait)
-      uint32_t v[HC];
-#pragma unroll
-      for (int c = 0; c < HC / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
-      tmem_ld_wait();
-      // S buffer consumed → QKᵀ of tile t+2 may overwrite it while we do the math
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
-      float mx = -INFINITY;
-      if (diag) {
-#pragma unroll
-        for (int j = 0; j < HC; ++j)
-          if (half * HC + j <= r) mx = fmaxf(mx, __uint_as_float(v[j]));
-      } else {
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains: FMNMX latency, not throughput
-#pragma unroll
-        for (int j = 0; j < HC; j += 4) {
-          m4[0] = fmaxf(m4[0], __uint_as_float(v[j]));
-          m4[1] = fmaxf(m4[1], __uint_as_float(v[j + 1]));
-          m4[2] = fmaxf(m4[2], __uint_as_float(v[j + 2]));
-          m4[3] = fmaxf(m4[3], __uint_as_float(v[j + 3]));
-        }
-        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      }
-      // pair-wide row max. Slots alternate with tile parity: a warp can only overwrite parity p again after the NEXT
-      // pair barrier, which its partner reaches only after reading this tile's value.
-      float* slot = xchg + (t & 1) * 256;
-      slot[half * 128 + r] = mx;
-      pair_sync();
-      mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]) * p.scale_log2;
-      // lazy rescale decision (warp-uniform: tcgen05.ld/st below are warp-collective; identical in both warps of the pair)
-      const bool grow = (mx - m) > kRescaleThreshold;
-      const bool any_grow = __any_sync(0xffffffffu, grow);
-      float alpha = 1.f;
-      if (any_grow) {
-        const float m_new = fmaxf(m, mx);
-        alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_new);
-        l *= alpha;
-        m = m_new;
-      }
-      // p = exp2(s·scale − m), in place; four partial sums keep the FADD chain short
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < HC; ++j) {
-        float e = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -m));
-        if (diag && half * HC + j > r) e = 0.f;
-        l4[j & 3] += e;
-        v[j] = __float_as_uint(e);
-      }
-      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-      // the P buffer of this stage was last read by P·V of tile t-2
-      if (t >= 2) mbar_wait(&pv_done[st], ph ^ 1);
-      // bf16 → this warp's [128 x 64] 128B-swizzled block of the K-major A operand of P·V
-      const uint32_t sbase = smem_u32(sP + st * C::kPBytes + half * (BQ * 128)) + r * 128;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int o = 8 * i;
-        st_shared_v4(sbase + (((uint32_t)i ^ row_sw) << 4), pack_bf16x2(v[o], v[o + 1]), pack_bf16x2(v[o + 2], v[o + 3]),
-                     pack_bf16x2(v[o + 4], v[o + 5]), pack_bf16x2(v[o + 6], v[o + 7]));
-      }
-      // rescale this warp's half of the O columns if some row's max moved (needs P·V of tile t-1 finished: O stable)
-      if (any_grow && t > 0) {
-        mbar_wait(&pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);
+    int g = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      int qb, bh;
+      item(w, qb, bh);
+      const int b = bh / p.H, h = bh % p.H;
+      const int n_kv = p.causal ? qb + 1 : p.S / BKV;
+      const int row0 = b * p.S + qb * BQ;
+      const int col_q = h * D;
+      float m = -INFINITY, l = 0.f;  // m is the pair-wide row max (identical in both warps); l is this warp's partial sum
+      for (int t = 0; t < n_kv; ++t, ++g) {
+        const int st = g & 1;
+        const uint32_t ph = (g >> 1) & 1;
+        mbar_wait(&s_full[st], ph);
         tc_fence_after();
-#pragma unroll 1
-        for (int i = 0; i < kOC; ++i) {
-          const uint32_t a = tmem_O + lane_addr + (half * kOC + i) * 32;
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(a, o);
-          tmem_ld_wait();
+        const uint32_t tS = tmem_base + st * BKV + half * HC + lane_addr;
+        const bool diag = p.causal && (t == qb);
+        // one TMEM read per tile: this warp's 64 score columns live in registers (both loads in flight, one wait)
+        uint32_t v[HC];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-          tmem_st_32x32b_x32(a, o);
+        for (int c = 0; c < HC / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+        tmem_ld_wait();
+        // S buffer consumed → QKᵀ two tiles ahead may overwrite it while we do the math
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);
+        float mx = -INFINITY;
+        if (diag) {
+#pragma unroll
+          for (int j = 0; j < HC; ++j)
+            if (half * HC + j <= r) mx = fmaxf(mx, __uint_as_float(v[j]));
+        } else {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains: FMNMX latency, not throughput
+#pragma unroll
+          for (int j = 0; j < HC; j += 4) {
+            m4[0] = fmaxf(m4[0], __uint_as_float(v[j]));
+            m4[1] = fmaxf(m4[1], __uint_as_float(v[j + 1]));
+            m4[2] = fmaxf(m4[2], __uint_as_float(v[j + 2]));
+            m4[3] = fmaxf(m4[3], __uint_as_float(v[j + 3]));
+          }
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         }
-        tmem_st_wait();
+        // pair-wide row max. Slots alternate with tile parity: a warp can only overwrite parity p again after the NEXT
+        // pair barrier, which its partner reaches only after reading this tile's value.
+        float* slot = xchg + (g & 1) * 256;
+        slot[half * 128 + r] = mx;
+        pair_sync();
+        mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]) * p.scale_log2;
+        // lazy rescale decision (warp-uniform: tcgen05.ld/st below are warp-collective; identical in both warps of the pair)
+        const bool grow = (mx - m) > kRescaleThreshold;
+        const bool any_grow = __any_sync(0xffffffffu, grow);
+        float alpha = 1.f;
+        if (any_grow) {
+          const float m_new = fmaxf(m, mx);
+          alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_new);
+          l *= alpha;
+          m = m_new;
+        }
+        // p = exp2(s·scale − m), in place; four partial sums keep the FADD chain short
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < HC; ++j) {
+          float e = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -m));
+          if (diag && half * HC + j > r) e = 0.f;
+          l4[j & 3] += e;
+          v[j] = __float_as_uint(e);
+        }
+        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        // the P buffer of this stage was last read by P·V two tiles ago (possibly of the previous work item)
+        if (g >= 2) mbar_wait(&pv_done[st], ph ^ 1);
+        // bf16 → this warp's [128 x 64] 128B-swizzled block of the K-major A operand of P·V
+        const uint32_t sbase = smem_u32(sP + st * C::kPBytes + half * (BQ * 128)) + r * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int o = 8 * i;
+          st_shared_v4(sbase + (((uint32_t)i ^ row_sw) << 4), pack_bf16x2(v[o], v[o + 1]), pack_bf16x2(v[o + 2], v[o + 3]),
+                       pack_bf16x2(v[o + 4], v[o + 5]), pack_bf16x2(v[o + 6], v[o + 7]));
+        }
+        // rescale this warp's half of the O columns if some row's max moved (needs P·V of the previous tile finished)
+        if (any_grow && t > 0) {
+          mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int i = 0; i < kOC; ++i) {
+            const uint32_t a = tmem_O + lane_addr + (half * kOC + i) * 32;
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(a, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st_32x32b_x32(a, o);
+          }
+          tmem_st_wait();
+        }
+        fence_proxy_async();  // P (generic-proxy smem writes) → visible to the tensor core's async proxy
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[st]);
       }
-      fence_proxy_async();  // P (generic-proxy smem writes) → visible to the tensor core's async proxy
+      // ---- epilogue of this work item: O / l → bf16 → swizzled staging (P buffer 0) → TMA store; lse2 = m + log2(l).
+      // Meanwhile the MMA warp is already computing S of the next item's first tile and the loader is 1-2 tiles ahead.
+      const int gl = g - 1;
+      mbar_wait(&pv_done[gl & 1], (gl >> 1) & 1);
+      if (gl >= 1) mbar_wait(&pv_done[(gl - 1) & 1], ((gl - 1) >> 1) & 1);  // staging aliases P buffer 0: both P·V readers retired
+      tc_fence_after();
+      {  // total row sum = the two warps' partials; the extra barrier keeps the slot stable until both have read it
+        float* slot = xchg + (g & 1) * 256;
+        slot[half * 128 + r] = l;
+        pair_sync();
+        l += slot[(half ^ 1) * 128 + r];
+        pair_sync();
+      }
+      const float inv_l = 1.f / l;
+      uint8_t* stage = sP;
+#pragma unroll 1
+      for (int i = 0; i < kOC; ++i) {
+        const int c = half * kOC + i;  // 32-column chunk of O
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        const uint32_t sbase = smem_u32(stage + (c >> 1) * (BQ * 128)) + r * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t chunk = (uint32_t)((c & 1) * 4 + k);
+          uint32_t wv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            wv[e] = pack_bf16x2(__float_as_uint(__uint_as_float(v[8 * k + 2 * e]) * inv_l),
+                                __float_as_uint(__uint_as_float(v[8 * k + 2 * e + 1]) * inv_l));
+          st_shared_v4(sbase + ((chunk ^ row_sw) << 4), wv[0], wv[1], wv[2], wv[3]);
+        }
+      }
+      // O has left TMEM → the first P·V of the next item may overwrite it
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[st]);
-    }
-    // ---- epilogue: O / l → bf16 → swizzled staging (P buffer 0) → TMA store; lse2 = m + log2(l)
-    const int tl = n_kv - 1;
-    mbar_wait(&pv_done[tl & 1], (tl >> 1) & 1);
-    if (n_kv >= 2) mbar_wait(&pv_done[(tl - 1) & 1], ((tl - 1) >> 1) & 1);  // staging aliases P buffer 0/1
-    tc_fence_after();
-    {  // total row sum = the two warps' partials (the slot of parity n_kv&1 is not in flight any more)
-      float* slot = xchg + (n_kv & 1) * 256;
-      slot[half * 128 + r] = l;
-      pair_sync();
-      l += slot[(half ^ 1) * 128 + r];
-    }
-    const float inv_l = 1.f / l;
-    uint8_t* stage = sP;
-#pragma unroll 1
-    for (int i = 0; i < kOC; ++i) {
-      const int c = half * kOC + i;  // 32-column chunk of O
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, v);
-      tmem_ld_wait();
-      const uint32_t sbase = smem_u32(stage + (c >> 1) * (BQ * 128)) + r * 128;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t chunk = (uint32_t)((c & 1) * 4 + k);
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          w[e] = pack_bf16x2(__float_as_uint(__uint_as_float(v[8 * k + 2 * e]) * inv_l),
-                             __float_as_uint(__uint_as_float(v[8 * k + 2 * e + 1]) * inv_l));
-        st_shared_v4(sbase + ((chunk ^ row_sw) << 4), w[0], w[1], w[2], w[3]);
+      if (lane == 0) mbar_arrive(o_free);
+      if (half == 0) p.lse2[((int64_t)bh) * p.S + qb * BQ + r] = m + log2f(l);
+      fence_proxy_async();
+      __syncwarp();
+      // D=128: each warp filled one whole 64-column chunk and stores it; D=64: the pair shares chunk 0 → meet, then one store
+      if (D == 64) pair_sync();
+      if (lane == 0 && (D != 64 || half == 0)) {
+        const int c = D == 64 ? 0 : half;
+        tma_store_2d(&tmap_o, stage + c * (BQ * 128) + q * 32 * 128, col_q + c * 64, row0 + q * 32);
+        bulk_commit();
+        bulk_wait_read<0>();  // this warp's staging rows are the rows it writes P into next: keep them until the store has read them
       }
-    }
-    if (half == 0) p.lse2[((int64_t)bh) * p.S + qb * BQ + r] = m + log2f(l);
-    fence_proxy_async();
-    __syncwarp();
-    // D=128: each warp filled one whole 64-column chunk and stores it; D=64: the pair shares chunk 0 → meet, then one store
-    if (D == 64) pair_sync();
-    if (lane == 0 && (D != 64 || half == 0)) {
-      const int c = D == 64 ? 0 : half;
-      tma_store_2d(&tmap_o, stage + c * (BQ * 128) + q * 32 * 128, col_q + c * 64, row0 + q * 32);
-      bulk_commit();
-      bulk_wait_read<0>();
+      if (D == 64) pair_sync();  // the partner's rows of the shared chunk were read by the same store
+      __syncwarp();
     }
   }
 
@@ -342,7 +386,8 @@ int launch_fwd(const void* qkv, void* out, float* lse2, int B, int S, int H, int
   rc = pbhost::cached_tmap(&to, out, rows, wo, wo, 64, 32, 2);
   if (rc) return rc;
   FwdParams p{lse2, B, S, H, Hkv, scale * 1.4426950408889634f, causal};
-  dim3 grid(S / BQ, B * H);
+  const int items = (S / BQ) * B * H;
+  const int grid = items < pbhost::num_sms() ? items : pbhost::num_sms();  // persistent: one CTA per SM walks the work list
   flash_fwd_kernel<D><<<grid, kThreads, C::kSmem, stream>>>(tq, to, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
