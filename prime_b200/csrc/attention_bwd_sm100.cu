@@ -20,7 +20,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreads = 384;  // w0 TMA · w1 MMA · w2 TMEM alloc · w3 idle · w4..11 math (two warps per TMEM lane quadrant)
+constexpr int kThreads = 384;  // w0 TMA · w1 MMA · w2 TMEM alloc · w3 idle · w4..7 math group 0 (even tiles) · w8..11 math group 1 (odd tiles)
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -59,7 +59,19 @@ struct BwdParams {
   int B, S, H, Hkv;
   float scale, scale_log2;
   int causal;
+  unsigned long long* trace;  // optional pipeline trace (tools/attn_trace.py): CTA (0,0) stamps clock64() at role events
 };
+
+// trace record: [role 0..3][slot] = {event code, tile, clock}; role 0 loader, 1 MMA, 2 math group 0, 3 math group 1
+__device__ __forceinline__ void trace_ev(const BwdParams& p, int role, int& n, int code, int tile) {
+  if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && n < 256) {
+    unsigned long long* e = p.trace + ((size_t)role * 256 + n) * 3;
+    e[0] = (unsigned long long)code;
+    e[1] = (unsigned long long)tile;
+    e[2] = (unsigned long long)clock64();
+    ++n;
+  }
+}
 
 // write one 32-value fp32 chunk of a row as bf16 into a [rows x 64] swizzled block (half: which 32 columns)
 __device__ __forceinline__ void store_row_chunk_bf16(uint32_t block_base, int r, int half, const float (&x)[32]) {
@@ -83,9 +95,11 @@ struct DkvCfg {
   static constexpr uint32_t kQBytes = 64 * D * 2;             // one Q or dO tile (64 rows)
   static constexpr uint32_t kPBytes = 128 * 128;              // Pᵀ or dSᵀ : [128 kv rows x 64 q]
   static constexpr uint32_t kOffV = kKVBytes;
-  static constexpr uint32_t kOffQ = 2 * kKVBytes;             // 2 stages
-  static constexpr uint32_t kOffdO = kOffQ + 2 * kQBytes;     // 2 stages
-  static constexpr uint32_t kOffP = kOffdO + 2 * kQBytes;     // 2 stages
+  static constexpr int kQStages = 3;                          // Q/dO ring: a slot is held until dV/dK of its tile retire, so
+                                                              // two tiles in flight + one TMA load (≈1 µs) in the air
+  static constexpr uint32_t kOffQ = 2 * kKVBytes;
+  static constexpr uint32_t kOffdO = kOffQ + kQStages * kQBytes;
+  static constexpr uint32_t kOffP = kOffdO + kQStages * kQBytes;  // 2 stages
   static constexpr uint32_t kOffdS = kOffP + 2 * kPBytes;     // 2 stages
   static constexpr uint32_t kOffBar = kOffdS + 2 * kPBytes;
   static constexpr uint32_t kSmem = kOffBar + 256 + 1024;
@@ -108,13 +122,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* sdS = smem + C::kOffdS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* kv_full = bars;        // 1
-  uint64_t* q_full = bars + 1;     // 2
-  uint64_t* q_empty = bars + 3;    // 2
-  uint64_t* s_full = bars + 5;     // 2
-  uint64_t* s_empty = bars + 7;    // 2 (4 warps)
-  uint64_t* p_full = bars + 9;     // 2 (4 warps)
-  uint64_t* acc_done = bars + 11;  // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* q_full = bars + 1;     // 3
+  uint64_t* q_empty = bars + 4;    // 3
+  uint64_t* s_full = bars + 7;     // 2
+  uint64_t* s_empty = bars + 9;    // 2 (4 warps)
+  uint64_t* p_full = bars + 11;    // 2 (4 warps)
+  uint64_t* acc_done = bars + 13;  // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jb = blockIdx.x;  // KV block (128 rows)
@@ -135,12 +149,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < C::kQStages; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);  // one arrive per math warp
-      mbar_init(&p_full[i], 8);
+      mbar_init(&s_empty[i], 4);  // stage i is always served by math group i (4 warps)
+      mbar_init(&p_full[i], 4);
       mbar_init(&acc_done[i], 1);
     }
     fence_barrier_init();
@@ -160,12 +176,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         tma_load_2d(&tmap_qkv128, kv_full, sK + c * (128 * 128), col_k + c * 64, kvrow0);
         tma_load_2d(&tmap_qkv128, kv_full, sV + c * (128 * 128), col_v + c * 64, kvrow0);
       }
+      int tr_n = 0;
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+        const int st = it % C::kQStages;
+        const uint32_t ph = (it / C::kQStages) & 1;
         const int h = hk * group + it / tiles_per_head;
         const int qrow = b * p.S + (it0 + it % tiles_per_head) * 64;
         mbar_wait(&q_empty[st], ph ^ 1);
+        trace_ev(p, 0, tr_n, 1, it);  // slot free → issue the Q/dO loads of tile `it`
         mbar_expect_tx(&q_full[st], 2 * C::kQBytes);
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
@@ -180,14 +198,18 @@ __global__ void __launch_bounds__(kThreads, 1)
       constexpr uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);  // Sᵀ[128 kv x 64 q] = K Qᵀ   (both K-major)
       constexpr uint32_t idesc_a = idesc_bf16(128, D, 0, 1);   // dV/dK[128 kv x D] += Pᵀ·dO  (A K-major, B MN-major)
       mbar_wait(kv_full, 0);
+      int tr_n = 0;
       auto issue_sd = [&](int it) {
         const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&q_full[st], ph);
+        const int qs = it % C::kQStages;
+        mbar_wait(&q_full[qs], (it / C::kQStages) & 1);
+        trace_ev(p, 1, tr_n, 1, it);  // Q/dO landed
         mbar_wait(&s_empty[st], ph ^ 1);
+        trace_ev(p, 1, tr_n, 2, it);  // S/dP stage free → issue S, dP
         tc_fence_after();
         const uint32_t k0 = smem_u32(sK), v0 = smem_u32(sV);
-        const uint32_t q0 = smem_u32(sQ + st * C::kQBytes), d0 = smem_u32(sdO + st * C::kQBytes);
+        const uint32_t q0 = smem_u32(sQ + qs * C::kQBytes), d0 = smem_u32(sdO + qs * C::kQBytes);
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c)
 #pragma unroll
@@ -208,9 +230,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         mbar_wait(&p_full[st], ph);
+        trace_ev(p, 1, tr_n, 3, it);  // Pᵀ/dSᵀ ready → issue dV, dK
         tc_fence_after();
+        const int qs = it % C::kQStages;
         const uint32_t pa = smem_u32(sP + st * C::kPBytes), da = smem_u32(sdS + st * C::kPBytes);
-        const uint32_t q0 = smem_u32(sQ + st * C::kQBytes), d0 = smem_u32(sdO + st * C::kQBytes);
+        const uint32_t q0 = smem_u32(sQ + qs * C::kQBytes), d0 = smem_u32(sdO + qs * C::kQBytes);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)  // K = 64 query rows
           umma_bf16(tmem_base + C::tdV, make_smem_desc(pa + kk * 32, 16, 1024), make_smem_desc(d0 + kk * 2048, 64 * 128, 1024),
@@ -219,61 +243,73 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int kk = 0; kk < 4; ++kk)
           umma_bf16(tmem_base + C::tdK, make_smem_desc(da + kk * 32, 16, 1024), make_smem_desc(q0 + kk * 2048, 64 * 128, 1024),
                     idesc_a, (it | kk) != 0 ? 1u : 0u);
-        umma_commit(&q_empty[st]);
+        umma_commit(&q_empty[qs]);
         umma_commit(&acc_done[st]);
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax-backward math + epilogue
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;  // which 32 of the 64 query columns (and, in the epilogue, dV or dK) this warp owns
+    const int half = (warp - 4) >> 2;  // math group: owns the tiles of this parity and, in the epilogue, dV (0) or dK (1)
     const int r = q * 32 + lane;       // KV row in the block == TMEM lane
     const int kv_idx = jb * 128 + r;   // position in the sequence
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    for (int it = 0; it < n_it; ++it) {
+    // Two math groups leapfrog over the tiles (group g owns the tiles — and therefore the S/dP TMEM stage and the Pᵀ/dSᵀ smem
+    // stage — of parity g). TMEM can only be read at 64 B/clk per SM, so one group's 64 KB of S/dP loads overlap the other
+    // group's exp2/FMA/pack/st.shared phase instead of every warp queueing on the same resource at the same time.
+    int tr_n = 0;
+    for (int it = half; it < n_it; it += 2) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int h = hk * group + it / tiles_per_head;
       const int qpos0 = (it0 + it % tiles_per_head) * 64;
       const float* lse_row = p.lse2 + ((int64_t)(b * p.H + h)) * p.S + qpos0;
       const float* del_row = p.delta + ((int64_t)(b * p.H + h)) * p.S + qpos0;
+      if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 1, it);  // start waiting for S/dP
       mbar_wait(&s_full[st], ph);
+      if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 2, it);  // S/dP ready
       tc_fence_after();
-      if (it >= 2) mbar_wait(&acc_done[st], ph ^ 1);  // Pᵀ/dSᵀ buffers of this stage are free again
       const bool need_mask = p.causal && (qpos0 < jb * 128 + 128);
-      // the two warps of a quadrant split the 64 query columns (P and dS are elementwise: no cross-warp reduction);
-      // both TMEM loads in flight, one wait; the per-query lse/delta values are warp-uniform 128-bit loads
-      uint32_t sv[32], dv[32];
-      tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, sv);
-      tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, dv);
-      const float4* lse4 = reinterpret_cast<const float4*>(lse_row) + half * 8;
-      const float4* del4 = reinterpret_cast<const float4*>(del_row) + half * 8;
+      // all four TMEM loads in flight, one wait; the per-query lse/delta rows are warp-uniform 128-bit loads
+      uint32_t sv[64], dv[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+        tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[c * 32]));
+      }
+      const float4* lse4 = reinterpret_cast<const float4*>(lse_row);
+      const float4* del4 = reinterpret_cast<const float4*>(del_row);
       tmem_ld_wait();
-      {
+      // S/dP of this stage now live in registers → the MMA warp may overwrite the stage with tile it+2
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 3, it);  // TMEM loads done
+      if (it >= 2) mbar_wait(&acc_done[st], ph ^ 1);  // Pᵀ/dSᵀ buffers of this stage are free again
+      if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 4, it);  // P/dS smem stage free
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         float pr[32], ds[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 L = __ldg(lse4 + j4), Dl = __ldg(del4 + j4);
+          const float4 L = __ldg(lse4 + c * 8 + j4), Dl = __ldg(del4 + c * 8 + j4);
           const float ls[4] = {L.x, L.y, L.z, L.w}, dl[4] = {Dl.x, Dl.y, Dl.z, Dl.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int j = j4 * 4 + e, qc = half * 32 + j;
-            float pv = fast_exp2(fmaf(__uint_as_float(sv[j]), p.scale_log2, -ls[e]));
+            const int j = j4 * 4 + e, qc = c * 32 + j;
+            float pv = fast_exp2(fmaf(__uint_as_float(sv[qc]), p.scale_log2, -ls[e]));
             if (need_mask && kv_idx > qpos0 + qc) pv = 0.f;
             pr[j] = pv;
-            ds[j] = pv * (__uint_as_float(dv[j]) - dl[e]) * p.scale;
+            ds[j] = pv * (__uint_as_float(dv[qc]) - dl[e]) * p.scale;
           }
         }
-        store_row_chunk_bf16(smem_u32(sP + st * C::kPBytes), r, half, pr);
-        store_row_chunk_bf16(smem_u32(sdS + st * C::kPBytes), r, half, ds);
+        store_row_chunk_bf16(smem_u32(sP + st * C::kPBytes), r, c, pr);
+        store_row_chunk_bf16(smem_u32(sdS + st * C::kPBytes), r, c, ds);
       }
-      tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[st]);
-        mbar_arrive(&p_full[st]);
-      }
+      if (lane == 0) mbar_arrive(&p_full[st]);
+      if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 5, it);  // math + stores done
     }
     // epilogue: dV, dK → bf16 → staging (the Pᵀ/dSᵀ region, 64 KB) → TMA stores into dqkv
     const int tl = n_it - 1;
@@ -322,9 +358,10 @@ struct DqCfg {
   static constexpr uint32_t kKVBytes = 64 * D * 2;   // one K or V tile (64 rows)
   static constexpr uint32_t kdSBytes = 128 * 128;    // dS : [128 q rows x 64 kv]
   static constexpr uint32_t kOffdO = kQBytes;
+  static constexpr int kKVStages = 3;  // K/V ring: a slot is held until dQ += dS·K of its tile retires
   static constexpr uint32_t kOffK = 2 * kQBytes;
-  static constexpr uint32_t kOffV = kOffK + 2 * kKVBytes;
-  static constexpr uint32_t kOffdS = kOffV + 2 * kKVBytes;
+  static constexpr uint32_t kOffV = kOffK + kKVStages * kKVBytes;
+  static constexpr uint32_t kOffdS = kOffV + kKVStages * kKVBytes;
   static constexpr uint32_t kOffBar = kOffdS + 2 * kdSBytes;
   static constexpr uint32_t kSmem = kOffBar + 256 + 1024;
   static constexpr uint32_t tS = 0, tdP = 128, tdQ = 256;
@@ -345,13 +382,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* sdS = smem + C::kOffdS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* q_full = bars;         // 1
-  uint64_t* kv_full = bars + 1;    // 2
-  uint64_t* kv_empty = bars + 3;   // 2
-  uint64_t* s_full = bars + 5;     // 2
-  uint64_t* s_empty = bars + 7;    // 2 (4 warps)
-  uint64_t* p_full = bars + 9;     // 2 (4 warps)
-  uint64_t* acc_done = bars + 11;  // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* kv_full = bars + 1;    // 3
+  uint64_t* kv_empty = bars + 4;   // 3
+  uint64_t* s_full = bars + 7;     // 2
+  uint64_t* s_empty = bars + 9;    // 2 (4 warps)
+  uint64_t* p_full = bars + 11;    // 2 (4 warps)
+  uint64_t* acc_done = bars + 13;  // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqb = p.S / 128;
@@ -371,12 +408,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < C::kKVStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);  // one arrive per math warp
-      mbar_init(&p_full[i], 8);
+      mbar_init(&s_empty[i], 4);  // stage i is always served by math group i (4 warps)
+      mbar_init(&p_full[i], 4);
       mbar_init(&acc_done[i], 1);
     }
     fence_barrier_init();
@@ -396,8 +435,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         tma_load_2d(&tmap_do128, q_full, sdO + c * (128 * 128), col_q + c * 64, row0);
       }
       for (int t = 0; t < n_kv; ++t) {
-        const int st = t & 1;
-        const uint32_t ph = (t >> 1) & 1;
+        const int st = t % C::kKVStages;
+        const uint32_t ph = (t / C::kKVStages) & 1;
         const int krow = b * p.S + t * 64;
         mbar_wait(&kv_empty[st], ph ^ 1);
         mbar_expect_tx(&kv_full[st], 2 * C::kKVBytes);
@@ -416,11 +455,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto issue_sd = [&](int t) {
         const int st = t & 1;
         const uint32_t ph = (t >> 1) & 1;
-        mbar_wait(&kv_full[st], ph);
+        const int ks = t % C::kKVStages;
+        mbar_wait(&kv_full[ks], (t / C::kKVStages) & 1);
         mbar_wait(&s_empty[st], ph ^ 1);
         tc_fence_after();
         const uint32_t q0 = smem_u32(sQ), d0 = smem_u32(sdO);
-        const uint32_t k0 = smem_u32(sK + st * C::kKVBytes), v0 = smem_u32(sV + st * C::kKVBytes);
+        const uint32_t k0 = smem_u32(sK + ks * C::kKVBytes), v0 = smem_u32(sV + ks * C::kKVBytes);
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c)
 #pragma unroll
@@ -442,52 +482,56 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t ph = (t >> 1) & 1;
         mbar_wait(&p_full[st], ph);
         tc_fence_after();
-        const uint32_t da = smem_u32(sdS + st * C::kdSBytes), k0 = smem_u32(sK + st * C::kKVBytes);
+        const int ks = t % C::kKVStages;
+        const uint32_t da = smem_u32(sdS + st * C::kdSBytes), k0 = smem_u32(sK + ks * C::kKVBytes);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)  // K = 64 kv rows
           umma_bf16(tmem_base + C::tdQ, make_smem_desc(da + kk * 32, 16, 1024), make_smem_desc(k0 + kk * 2048, 64 * 128, 1024),
                     idesc_a, (t | kk) != 0 ? 1u : 0u);
-        umma_commit(&kv_empty[st]);
+        umma_commit(&kv_empty[ks]);
         umma_commit(&acc_done[st]);
       }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;  // which 32 of the 64 kv columns (and which half of the dQ columns in the epilogue)
+    const int half = (warp - 4) >> 2;  // math group: owns the kv tiles of this parity and half of the dQ columns in the epilogue
     const int r = q * 32 + lane;
     const int q_idx = qb * 128 + r;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float lse = p.lse2[((int64_t)bh) * p.S + q_idx];
     const float del = p.delta[((int64_t)bh) * p.S + q_idx];
-    for (int t = 0; t < n_kv; ++t) {
+    for (int t = half; t < n_kv; t += 2) {  // the two math groups leapfrog over the kv tiles (see the dK/dV kernel)
       const int st = t & 1;
       const uint32_t ph = (t >> 1) & 1;
       mbar_wait(&s_full[st], ph);
       tc_fence_after();
-      if (t >= 2) mbar_wait(&acc_done[st], ph ^ 1);
       const int kv0 = t * 64;
       const bool need_mask = p.causal && (kv0 + 64 > qb * 128);
-      uint32_t sv[32], dv[32];
-      tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + half * 32, sv);
-      tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + half * 32, dv);
+      uint32_t sv[64], dv[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+        tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[c * 32]));
+      }
       tmem_ld_wait();
-      {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (t >= 2) mbar_wait(&acc_done[st], ph ^ 1);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         float ds[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float pv = fast_exp2(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse));
-          if (need_mask && (kv0 + half * 32 + j) > q_idx) pv = 0.f;
-          ds[j] = pv * (__uint_as_float(dv[j]) - del) * p.scale;
+          float pv = fast_exp2(fmaf(__uint_as_float(sv[c * 32 + j]), p.scale_log2, -lse));
+          if (need_mask && (kv0 + c * 32 + j) > q_idx) pv = 0.f;
+          ds[j] = pv * (__uint_as_float(dv[c * 32 + j]) - del) * p.scale;
         }
-        store_row_chunk_bf16(smem_u32(sdS + st * C::kdSBytes), r, half, ds);
+        store_row_chunk_bf16(smem_u32(sdS + st * C::kdSBytes), r, c, ds);
       }
-      tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[st]);
-        mbar_arrive(&p_full[st]);
-      }
+      if (lane == 0) mbar_arrive(&p_full[st]);
     }
     const int tl = n_kv - 1;
     mbar_wait(&acc_done[tl & 1], (tl >> 1) & 1);
@@ -534,6 +578,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
+unsigned long long* g_bwd_trace = nullptr;
+
 template <int D>
 int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv, int B, int S,
                int H, int Hkv, float scale, int causal, cudaStream_t stream) {
@@ -559,7 +605,7 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   if ((rc = pbhost::cached_tmap(&tdo64, dout, rows, wo, wo, 64, 64, 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tdo128, dout, rows, wo, wo, 64, 128, 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tdq, dqkv, rows, wqkv, wqkv, 64, 32, 2))) return rc;
-  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal};
+  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace};
   bwd_dkdv_kernel<D><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
   bwd_dq_kernel<D><<<dim3(S / 128, B * H), kThreads, DqCfg<D>::kSmem, stream>>>(tq128, tq64, tdo128, tdq, p);
   cudaError_t e = cudaGetLastError();
@@ -567,6 +613,9 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
 }
 
 }  // namespace
+
+// Device buffer of 4 roles x 256 events x 3 u64 that CTA (0,0) of the dK/dV kernel fills (nullptr = tracing off).
+PB_EXPORT void pb_flash_attn_bwd_set_trace(unsigned long long* buf) { g_bwd_trace = buf; }
 
 // delta: [B, H, S] fp32 scratch.  dqkv: [B, S, (H+2Hkv)·D] bf16, fully overwritten.
 PB_EXPORT int pb_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,
