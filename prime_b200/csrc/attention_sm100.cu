@@ -8,10 +8,13 @@
 // first. All rings (K/V smem, S in TMEM, P in smem) run on one global tile counter, so the TMA loader and the MMA issuer flow
 // straight into the next item while the softmax warps are still normalising/storing the previous one: the per-item pipeline
 // fill/drain (≈7 µs measured with one CTA per item — more than the math of a short causal item) is paid once per CTA.
-// Warp roles: w0 TMA loader · w1 MMA issuer · w2 TMEM allocator · w4..11 softmax: TMEM lane quadrant q is served by the warp
-//   pair (4+q, 8+q); each warp owns 64 of the 128 score columns of its 32 rows and the pair exchanges the partial row
-//   maximum through 2 KB of smem + a 64-thread named barrier (the softmax phase is issue/latency-bound, not MUFU-bound,
-//   so doubling the warps that work on a tile nearly halves it).
+// Warp roles: w0 TMA loader · w1 MMA issuer · w2 TMEM allocator · w3..10 softmax in TWO GROUPS that leapfrog over the kv tiles
+//   (group = global tile parity = S/P stage). A 128×128 fp32 score tile takes 1024 clk to read out of TMEM (64 B/clk/SM), 1024 clk
+//   of MUFU.EX2 and 1024 clk of MMAs; with every softmax warp on the same tile those phases run back to back, with two groups on
+//   consecutive tiles one group's TMEM read overlaps the other's exp2/pack/st.shared. Rows are per-thread (one TMEM lane), so the
+//   only cross-group state is the running row max: the owner of tile t publishes m(t) through 1 KB of smem and a 64-thread named
+//   barrier (warp q of one group ↔ warp q of the other) BEFORE its exp phase, so the hand-off is off the critical path. Each
+//   group keeps its own partial row sum relative to the max it last saw; they are merged in the epilogue.
 //   S is double-buffered in TMEM (2 × 128 cols) so QKᵀ of tile t+1 overlaps the softmax of tile t;
 //   P is written bf16 into 128B-swizzled smem (double-buffered) as the K-major A operand of P·V;
 //   O lives in TMEM (D cols); it is only rescaled when a row max grows by more than 2^8 (lazy rescale),
@@ -24,7 +27,7 @@ using namespace tc;
 namespace {
 
 constexpr int BQ = 128, BKV = 128;
-constexpr int kThreads = 384;  // w0 TMA · w1 MMA · w2 TMEM alloc · w3 idle · w4..11 softmax (two warps per TMEM lane quadrant)
+constexpr int kThreads = 352;  // w0 TMA · w1 MMA · w2 TMEM alloc · w3..10 softmax: group (w-3)/4, TMEM lane quadrant w%4
 constexpr float kRescaleThreshold = 8.f;  // log2 units
 
 template <int D>
@@ -37,7 +40,7 @@ struct FwdCfg {
   static constexpr uint32_t kOffV = kOffK + 2 * kKVBytes;
   static constexpr uint32_t kOffP = kOffV + 2 * kKVBytes;
   static constexpr uint32_t kOffBar = kOffP + 2 * kPBytes;
-  static constexpr uint32_t kOffXchg = kOffBar + 256;          // [parity][half][128 rows] fp32 partial row maxima (2 KB)
+  static constexpr uint32_t kOffXchg = kOffBar + 256;          // mrow[2][128] running max per tile parity + lrow[2][128] partial sums
   static constexpr uint32_t kSmem = kOffXchg + 2048;           // 226.25 KB at D=128: no room for alignment slack, so the
                                                                // dynamic smem base itself is declared 1024-aligned
 };
@@ -75,8 +78,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* v_full = bars + 6;        // 2
   uint64_t* v_empty = bars + 8;       // 2
   uint64_t* s_full = bars + 10;       // 2
-  uint64_t* s_empty = bars + 12;      // 2 (8 warp arrivals)
-  uint64_t* p_full = bars + 14;       // 2 (8 warp arrivals)
+  uint64_t* s_empty = bars + 12;      // 2 (4 warp arrivals: stage i ↔ softmax group i)
+  uint64_t* p_full = bars + 14;       // 2 (4 warp arrivals)
   uint64_t* pv_done = bars + 16;      // 2 (commit of P·V for a tile → P buffer free, O stable)
   uint64_t* o_free = bars + 18;       // 1 (8 warp arrivals): the epilogue has read O out of TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
@@ -106,8 +109,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 8);  // one arrive per softmax warp
-      mbar_init(&p_full[i], 8);
+      mbar_init(&s_empty[i], 4);  // stage i is always served by softmax group i (4 warps)
+      mbar_init(&p_full[i], 4);
       mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
@@ -200,16 +203,20 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 3) {
     // ------------------------------------------------------------------ softmax + epilogue
-    const int q = warp & 3;
-    const int half = (warp - 4) >> 2;  // which 64 of the 128 score columns (and which half of the O columns) this warp owns
+    const int q = warp & 3;            // TMEM lane quadrant this warp may touch
+    const int grp = (warp - 3) >> 2;   // softmax group: owns the tiles of this global parity, and this half of the O columns
     const int r = q * 32 + lane;       // query row inside the block == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const uint32_t row_sw = (uint32_t)(r & 7);
-    constexpr int HC = BKV / 2;        // columns per warp
-    constexpr int kOC = D / 64;        // 32-column O chunks per warp
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
+    constexpr int kOC = D / 64;        // 32-column O chunks per warp in the epilogue
+    float* mrow = xchg;                // [2][128]
+    float* lrow = xchg + 256;          // [2][128]
+    // named barriers 1..8: id(from) is signalled by group `from`'s warp q and awaited by the other group's warp q; 9..12: pair sync
+    auto publish = [&]() { asm volatile("bar.arrive %0, 64;" ::"r"(1 + q + 4 * grp) : "memory"); };
+    auto consume = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q + 4 * (grp ^ 1)) : "memory"); };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(9 + q) : "memory"); };
     int g = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       int qb, bh;
@@ -218,32 +225,33 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int n_kv = p.causal ? qb + 1 : p.S / BKV;
       const int row0 = b * p.S + qb * BQ;
       const int col_q = h * D;
-      float m = -INFINITY, l = 0.f;  // m is the pair-wide row max (identical in both warps); l is this warp's partial sum
+      float m_ref = -INFINITY, l = 0.f;  // this group's partial row sum, relative to the last running max it has seen
       for (int t = 0; t < n_kv; ++t, ++g) {
+        if ((g & 1) != grp) continue;
         const int st = g & 1;
         const uint32_t ph = (g >> 1) & 1;
         mbar_wait(&s_full[st], ph);
         tc_fence_after();
-        const uint32_t tS = tmem_base + st * BKV + half * HC + lane_addr;
+        const uint32_t tS = tmem_base + st * BKV + lane_addr;
         const bool diag = p.causal && (t == qb);
-        // one TMEM read per tile: this warp's 64 score columns live in registers (both loads in flight, one wait)
-        uint32_t v[HC];
+        // one TMEM read per tile: the whole 128-column score row lives in registers (4 loads in flight, one wait)
+        uint32_t v[BKV];
 #pragma unroll
-        for (int c = 0; c < HC / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+        for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
         tmem_ld_wait();
-        // S buffer consumed → QKᵀ two tiles ahead may overwrite it while we do the math
+        // S stage consumed → QKᵀ two tiles ahead may overwrite it while we do the math
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);
         float mx = -INFINITY;
         if (diag) {
 #pragma unroll
-          for (int j = 0; j < HC; ++j)
-            if (half * HC + j <= r) mx = fmaxf(mx, __uint_as_float(v[j]));
+          for (int j = 0; j < BKV; ++j)
+            if (j <= r) mx = fmaxf(mx, __uint_as_float(v[j]));
         } else {
           float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains: FMNMX latency, not throughput
 #pragma unroll
-          for (int j = 0; j < HC; j += 4) {
+          for (int j = 0; j < BKV; j += 4) {
             m4[0] = fmaxf(m4[0], __uint_as_float(v[j]));
             m4[1] = fmaxf(m4[1], __uint_as_float(v[j + 1]));
             m4[2] = fmaxf(m4[2], __uint_as_float(v[j + 2]));
@@ -251,49 +259,56 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         }
-        // pair-wide row max. Slots alternate with tile parity: a warp can only overwrite parity p again after the NEXT
-        // pair barrier, which its partner reaches only after reading this tile's value.
-        float* slot = xchg + (g & 1) * 256;
-        slot[half * 128 + r] = mx;
-        pair_sync();
-        mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]) * p.scale_log2;
-        // lazy rescale decision (warp-uniform: tcgen05.ld/st below are warp-collective; identical in both warps of the pair)
-        const bool grow = (mx - m) > kRescaleThreshold;
-        const bool any_grow = __any_sync(0xffffffffu, grow);
-        float alpha = 1.f;
-        if (any_grow) {
-          const float m_new = fmaxf(m, mx);
-          alpha = (m == -INFINITY) ? 0.f : fast_exp2(m - m_new);
-          l *= alpha;
-          m = m_new;
+        mx *= p.scale_log2;
+        // running max after the previous tile (owned by the other group), then publish ours before the long exp phase
+        float m_prev = -INFINITY;
+        if (t > 0) {
+          consume();
+          m_prev = mrow[((g - 1) & 1) * 128 + r];
         }
-        // p = exp2(s·scale − m), in place; four partial sums keep the FADD chain short
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < HC; ++j) {
-          float e = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -m));
-          if (diag && half * HC + j > r) e = 0.f;
-          l4[j & 3] += e;
-          v[j] = __float_as_uint(e);
+        // lazy rescale (warp-uniform: the tcgen05.ld/st of the O rescale are warp-collective)
+        const bool any_grow = __any_sync(0xffffffffu, (mx - m_prev) > kRescaleThreshold);
+        const float m_new = any_grow ? fmaxf(m_prev, mx) : m_prev;
+        mrow[(g & 1) * 128 + r] = m_new;
+        publish();
+        const float alpha = (any_grow && m_prev != -INFINITY) ? fast_exp2(m_prev - m_new) : (any_grow ? 0.f : 1.f);
+        if (m_ref != m_new) {  // bring this group's partial sum to the new reference (exp2(-inf) = 0 covers the first tile)
+          l *= fast_exp2(m_ref - m_new);
+          m_ref = m_new;
         }
-        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         // the P buffer of this stage was last read by P·V two tiles ago (possibly of the previous work item)
         if (g >= 2) mbar_wait(&pv_done[st], ph ^ 1);
-        // bf16 → this warp's [128 x 64] 128B-swizzled block of the K-major A operand of P·V
-        const uint32_t sbase = smem_u32(sP + st * C::kPBytes + half * (BQ * 128)) + r * 128;
+        // p = exp2(s·scale − m) → bf16 → 128B-swizzled smem (the K-major A operand of P·V), 32 columns at a time so the score
+        // registers retire as we go; four partial sums keep the FADD chain short
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint8_t* pbuf = sP + st * C::kPBytes;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int o = 8 * i;
-          st_shared_v4(sbase + (((uint32_t)i ^ row_sw) << 4), pack_bf16x2(v[o], v[o + 1]), pack_bf16x2(v[o + 2], v[o + 3]),
-                       pack_bf16x2(v[o + 4], v[o + 5]), pack_bf16x2(v[o + 6], v[o + 7]));
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + j]), p.scale_log2, -m_new));
+            float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + j + 1]), p.scale_log2, -m_new));
+            if (diag && c * 32 + j > r) e0 = 0.f;
+            if (diag && c * 32 + j + 1 > r) e1 = 0.f;
+            l4[(j >> 1) & 3] += e0 + e1;
+            pk[j >> 1] = pack_bf16x2(__float_as_uint(e0), __float_as_uint(e1));
+          }
+          const uint32_t sbase = smem_u32(pbuf + (c >> 1) * (BQ * 128)) + r * 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t chunk = (uint32_t)((c & 1) * 4 + i);
+            st_shared_v4(sbase + ((chunk ^ row_sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
         }
-        // rescale this warp's half of the O columns if some row's max moved (needs P·V of the previous tile finished)
+        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        // rescale O if some row's max moved (needs P·V of the previous tile finished; ordered before ours by p_full below)
         if (any_grow && t > 0) {
           mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int i = 0; i < kOC; ++i) {
-            const uint32_t a = tmem_O + lane_addr + (half * kOC + i) * 32;
+          for (int c = 0; c < D / 32; ++c) {
+            const uint32_t a = tmem_O + lane_addr + c * 32;
             uint32_t o[32];
             tmem_ld_32x32b_x32(a, o);
             tmem_ld_wait();
@@ -311,21 +326,25 @@ __global__ void __launch_bounds__(kThreads, 1)
       // ---- epilogue of this work item: O / l → bf16 → swizzled staging (P buffer 0) → TMA store; lse2 = m + log2(l).
       // Meanwhile the MMA warp is already computing S of the next item's first tile and the loader is 1-2 tiles ahead.
       const int gl = g - 1;
+      float m_fin;
+      if ((gl & 1) == grp) {
+        m_fin = m_ref;  // we processed the last tile: our reference IS the final max
+      } else {
+        consume();      // the other group's publish for the last tile
+        m_fin = mrow[(gl & 1) * 128 + r];
+      }
+      l *= fast_exp2(m_ref - m_fin);  // partial sum → final reference (a group without tiles contributes exp2(-inf)·0 = 0)
+      lrow[grp * 128 + r] = l;
+      pair_sync();
+      l += lrow[(grp ^ 1) * 128 + r];
       mbar_wait(&pv_done[gl & 1], (gl >> 1) & 1);
       if (gl >= 1) mbar_wait(&pv_done[(gl - 1) & 1], ((gl - 1) >> 1) & 1);  // staging aliases P buffer 0: both P·V readers retired
       tc_fence_after();
-      {  // total row sum = the two warps' partials; the extra barrier keeps the slot stable until both have read it
-        float* slot = xchg + (g & 1) * 256;
-        slot[half * 128 + r] = l;
-        pair_sync();
-        l += slot[(half ^ 1) * 128 + r];
-        pair_sync();
-      }
       const float inv_l = 1.f / l;
       uint8_t* stage = sP;
 #pragma unroll 1
       for (int i = 0; i < kOC; ++i) {
-        const int c = half * kOC + i;  // 32-column chunk of O
+        const int c = grp * kOC + i;  // 32-column chunk of O
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, v);
         tmem_ld_wait();
@@ -345,19 +364,21 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free);
-      if (half == 0) p.lse2[((int64_t)bh) * p.S + qb * BQ + r] = m + log2f(l);
+      if (grp == 0) p.lse2[((int64_t)bh) * p.S + qb * BQ + r] = m_fin + log2f(l);
       fence_proxy_async();
       __syncwarp();
       // D=128: each warp filled one whole 64-column chunk and stores it; D=64: the pair shares chunk 0 → meet, then one store
       if (D == 64) pair_sync();
-      if (lane == 0 && (D != 64 || half == 0)) {
-        const int c = D == 64 ? 0 : half;
+      if (lane == 0 && (D != 64 || grp == 0)) {
+        const int c = D == 64 ? 0 : grp;
         tma_store_2d(&tmap_o, stage + c * (BQ * 128) + q * 32 * 128, col_q + c * 64, row0 + q * 32);
         bulk_commit();
-        bulk_wait_read<0>();  // this warp's staging rows are the rows it writes P into next: keep them until the store has read them
+        bulk_wait_read<0>();
       }
-      if (D == 64) pair_sync();  // the partner's rows of the shared chunk were read by the same store
       __syncwarp();
+      // the staging rows of BOTH warps of the pair alias rows that group 0 writes P into at its next tile, and lrow is reused by
+      // the next item: nobody moves on until both stores have been read out of smem
+      pair_sync();
     }
   }
 

@@ -84,7 +84,7 @@ PB_EXPORT int pb_rmsnorm_fwd(const void* x, const void* res, const void* w, void
 // kernel folds the [grid, D] partials (deterministic order) into the fp32 weight gradient.
 // --------------------------------------------------------------------------------------
 template <int MAXV, bool HAS_DRES>
-__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16x8* __restrict__ dy, const bf16x8* __restrict__ h,
+__global__ void __launch_bounds__(256, MAXV == 1 ? 4 : 1) rmsnorm_bwd_kernel(const bf16x8* __restrict__ dy, const bf16x8* __restrict__ h,
                                                           const bf16x8* __restrict__ w, const float* __restrict__ rstd,
                                                           const bf16x8* __restrict__ dres, bf16x8* __restrict__ dx,
                                                           float* __restrict__ dw_partial, int64_t R, int nvec,
@@ -98,8 +98,23 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16x8* __restri
     for (int j = 0; j < 8; ++j) dwacc[i][j] = 0.f;
     if (c < nvec) unpack8(w[c], wv[i]);
   }
+  // Software pipeline over rows: the raw 16-byte loads of the NEXT row are issued before the block reduction of the current one,
+  // so the ≈1 µs HBM latency hides behind reduce + normalise + store instead of being paid once per row per CTA.
+  bf16x8 nd[MAXV], nh[MAXV], nr[MAXV];
+  auto fetch = [&](int64_t row) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = threadIdx.x + i * blockDim.x;
+      if (c < nvec) {
+        nd[i] = ldg_stream(dy + row * nvec + c);
+        nh[i] = ldg_stream(h + row * nvec + c);
+        if (HAS_DRES) nr[i] = ldg_stream(dres + row * nvec + c);
+      }
+    }
+  };
+  if ((int64_t)blockIdx.x < R) fetch(blockIdx.x);
   for (int64_t row = blockIdx.x; row < R; row += gridDim.x) {
-    float g[MAXV][8], hv[MAXV][8];
+    float g[MAXV][8], hv[MAXV][8], rv[MAXV][8];
     const float rs = rstd[row];
     float dot = 0.f;
 #pragma unroll
@@ -107,8 +122,9 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16x8* __restri
       const int c = threadIdx.x + i * blockDim.x;
       if (c < nvec) {
         float d[8];
-        unpack8(ldg_stream(dy + row * nvec + c), d);
-        unpack8(ldg_stream(h + row * nvec + c), hv[i]);
+        unpack8(nd[i], d);
+        unpack8(nh[i], hv[i]);
+        if (HAS_DRES) unpack8(nr[i], rv[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           g[i][j] = d[j] * wv[i][j];
@@ -117,6 +133,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16x8* __restri
         }
       }
     }
+    if (row + gridDim.x < R) fetch(row + gridDim.x);  // in flight during the reduction and the stores below
     dot = block_sum(dot, red);
     const float coef = dot * inv_d * rs * rs * rs;
 #pragma unroll
@@ -127,10 +144,8 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const bf16x8* __restri
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = g[i][j] * rs - hv[i][j] * coef;
         if (HAS_DRES) {
-          float r[8];
-          unpack8(ldg_stream(dres + row * nvec + c), r);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
+          for (int j = 0; j < 8; ++j) o[j] += rv[i][j];
         }
         stg_stream(dx + row * nvec + c, pack8(o));
       }
@@ -168,9 +183,9 @@ __global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __res
 
 // dw_partial must hold grid*D floats; `grid_out` reports the grid used (query with R<0).
 PB_EXPORT int pb_rmsnorm_bwd_grid(int64_t R) {
-  // 6 resident CTAs per SM: each row iteration is load → block reduction → store, i.e. latency-bound per CTA, so HBM is only
+  // 4 resident CTAs per SM (register-capped by __launch_bounds__): each row iteration is load → block reduction → store, i.e. latency-bound per CTA, so HBM is only
   // saturated by many CTAs in flight (2 per SM measured 28 % of copy bandwidth). Cost: a [grid, D] fp32 partial buffer.
-  int64_t g = 148 * 6;
+  int64_t g = 148 * 4;
   return (int)(R < g ? R : g);
 }
 

@@ -47,7 +47,7 @@ def _elastic_setup(cfg: Config, trainer: Trainer, log) -> Any:
     from .parallel.elastic import ElasticConfig, ElasticContext, display_name
 
     mesh = trainer.mesh
-    backend = "nccl" if mesh.device.type == "cuda" else "gloo"
+    backend = __import__("os").environ.get("PRIME_B200_ELASTIC_BACKEND") or ("nccl" if mesh.device.type == "cuda" else "gloo")
     ecfg = ElasticConfig(heartbeat_interval_s=cfg.mesh.heartbeat_interval_s, heartbeat_timeout_s=cfg.mesh.heartbeat_timeout_s,
                          min_workers=max(1, cfg.mesh.num_workers))  # fmt: skip
     ctx = ElasticContext.from_env(fsdp_rank=mesh.fsdp_rank, backend=backend, cfg=ecfg)
