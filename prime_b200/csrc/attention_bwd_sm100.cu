@@ -13,6 +13,8 @@
 // log2-domain LSE: P = exp2(s·scale·log2e − lse2).
 //
 // TMEM budget (512 columns):  dK/dV kernel: Sᵀ 2×64 | dPᵀ 2×64 | dV D | dK D      dQ kernel: S 2×64 | dP 2×64 | dQ D
+#include <type_traits>
+
 #include "tc_common.cuh"
 #include "tmap.h"
 
@@ -182,6 +184,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t ph = (it / C::kQStages) & 1;
         const int h = hk * group + it / tiles_per_head;
         const int qrow = b * p.S + (it0 + it % tiles_per_head) * 64;
+        {  // the tile that will be loaded kQStages iterations from now: start moving it HBM → L2 (measured: a cold 32 KB
+           // Q/dO stage takes ≈3900 clk to land, and only one load can be in flight with every slot held until dV/dK retire)
+          const int nx = it + C::kQStages;
+          if (nx < n_it) {
+            const int hn = hk * group + nx / tiles_per_head;
+            const int qn = b * p.S + (it0 + nx % tiles_per_head) * 64;
+#pragma unroll
+            for (int c = 0; c < C::kChunks; ++c) {
+              tma_prefetch_l2_2d(&tmap_qkv64, hn * D + c * 64, qn);
+              tma_prefetch_l2_2d(&tmap_do64, hn * D + c * 64, qn);
+            }
+          }
+        }
         mbar_wait(&q_empty[st], ph ^ 1);
         trace_ev(p, 0, tr_n, 1, it);  // slot free → issue the Q/dO loads of tile `it`
         mbar_expect_tx(&q_full[st], 2 * C::kQBytes);
@@ -224,9 +239,11 @@ __global__ void __launch_bounds__(kThreads, 1)
                       make_smem_desc(d0 + c * (64 * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
         umma_commit(&s_full[st]);
       };
+      // (Issuing S/dP two tiles ahead was tried: with a 3-slot Q/dO ring the MMA thread then blocks on the load of tile it+2 in
+      // front of dV/dK of tile it and everything slows down — it needs a ≥5-slot ring, i.e. Pᵀ/dSᵀ moved from smem into TMEM.)
       issue_sd(0);
       for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) issue_sd(it + 1);  // overlaps the softmax math of tile `it`
+        if (it + 1 < n_it) issue_sd(it + 1);  // overlaps the math of tile `it`
         const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         mbar_wait(&p_full[st], ph);
@@ -287,25 +304,30 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 3, it);  // TMEM loads done
       if (it >= 2) mbar_wait(&acc_done[st], ph ^ 1);  // Pᵀ/dSᵀ buffers of this stage are free again
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 4, it);  // P/dS smem stage free
+      // only the (at most two) diagonal tiles need the causal mask: keep the per-element compare/select out of the common path
+      auto tile_math = [&](auto masked) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float pr[32], ds[32];
+        for (int c = 0; c < 2; ++c) {
+          float pr[32], ds[32];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 L = __ldg(lse4 + c * 8 + j4), Dl = __ldg(del4 + c * 8 + j4);
-          const float ls[4] = {L.x, L.y, L.z, L.w}, dl[4] = {Dl.x, Dl.y, Dl.z, Dl.w};
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 L = __ldg(lse4 + c * 8 + j4), Dl = __ldg(del4 + c * 8 + j4);
+            const float ls[4] = {L.x, L.y, L.z, L.w}, dl[4] = {Dl.x * p.scale, Dl.y * p.scale, Dl.z * p.scale, Dl.w * p.scale};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = j4 * 4 + e, qc = c * 32 + j;
-            float pv = fast_exp2(fmaf(__uint_as_float(sv[qc]), p.scale_log2, -ls[e]));
-            if (need_mask && kv_idx > qpos0 + qc) pv = 0.f;
-            pr[j] = pv;
-            ds[j] = pv * (__uint_as_float(dv[qc]) - dl[e]) * p.scale;
+            for (int e = 0; e < 4; ++e) {
+              const int j = j4 * 4 + e, qc = c * 32 + j;
+              float pv = fast_exp2(fmaf(__uint_as_float(sv[qc]), p.scale_log2, -ls[e]));
+              if (decltype(masked)::value && kv_idx > qpos0 + qc) pv = 0.f;
+              pr[j] = pv;
+              ds[j] = pv * fmaf(__uint_as_float(dv[qc]), p.scale, -dl[e]);
+            }
           }
+          store_row_chunk_bf16(smem_u32(sP + st * C::kPBytes), r, c, pr);
+          store_row_chunk_bf16(smem_u32(sdS + st * C::kPBytes), r, c, ds);
         }
-        store_row_chunk_bf16(smem_u32(sP + st * C::kPBytes), r, c, pr);
-        store_row_chunk_bf16(smem_u32(sdS + st * C::kPBytes), r, c, ds);
-      }
+      };
+      if (need_mask) tile_math(std::true_type{});
+      else tile_math(std::false_type{});
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);
@@ -438,6 +460,14 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int st = t % C::kKVStages;
         const uint32_t ph = (t / C::kKVStages) & 1;
         const int krow = b * p.S + t * 64;
+        if (t + C::kKVStages < n_kv) {
+          const int kn = b * p.S + (t + C::kKVStages) * 64;
+#pragma unroll
+          for (int c = 0; c < C::kChunks; ++c) {
+            tma_prefetch_l2_2d(&tmap_qkv64, col_k + c * 64, kn);
+            tma_prefetch_l2_2d(&tmap_qkv64, col_v + c * 64, kn);
+          }
+        }
         mbar_wait(&kv_empty[st], ph ^ 1);
         mbar_expect_tx(&kv_full[st], 2 * C::kKVBytes);
 #pragma unroll
@@ -499,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int q_idx = qb * 128 + r;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float lse = p.lse2[((int64_t)bh) * p.S + q_idx];
-    const float del = p.delta[((int64_t)bh) * p.S + q_idx];
+    const float del_s = p.delta[((int64_t)bh) * p.S + q_idx] * p.scale;
     for (int t = half; t < n_kv; t += 2) {  // the two math groups leapfrog over the kv tiles (see the dK/dV kernel)
       const int st = t & 1;
       const uint32_t ph = (t >> 1) & 1;
@@ -518,17 +548,21 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
       if (t >= 2) mbar_wait(&acc_done[st], ph ^ 1);
+      auto tile_math = [&](auto masked) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float ds[32];
+        for (int c = 0; c < 2; ++c) {
+          float ds[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float pv = fast_exp2(fmaf(__uint_as_float(sv[c * 32 + j]), p.scale_log2, -lse));
-          if (need_mask && (kv0 + c * 32 + j) > q_idx) pv = 0.f;
-          ds[j] = pv * (__uint_as_float(dv[c * 32 + j]) - del) * p.scale;
+          for (int j = 0; j < 32; ++j) {
+            float pv = fast_exp2(fmaf(__uint_as_float(sv[c * 32 + j]), p.scale_log2, -lse));
+            if (decltype(masked)::value && (kv0 + c * 32 + j) > q_idx) pv = 0.f;
+            ds[j] = pv * fmaf(__uint_as_float(dv[c * 32 + j]), p.scale, -del_s);
+          }
+          store_row_chunk_bf16(smem_u32(sdS + st * C::kdSBytes), r, c, ds);
         }
-        store_row_chunk_bf16(smem_u32(sdS + st * C::kdSBytes), r, c, ds);
-      }
+      };
+      if (need_mask) tile_math(std::true_type{});
+      else tile_math(std::false_type{});
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);

@@ -19,6 +19,8 @@
 //   P is written bf16 into 128B-swizzled smem (double-buffered) as the K-major A operand of P·V;
 //   O lives in TMEM (D cols); it is only rescaled when a row max grows by more than 2^8 (lazy rescale),
 //   the final 1/l normalisation uses the same stale max, so the result is exact.
+#include <type_traits>
+
 #include "tc_common.cuh"
 #include "tmap.h"
 
@@ -142,6 +144,13 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int st = g & 1;
           const uint32_t ph = (g >> 1) & 1;
           const int krow = b * p.S + t * BKV;
+          if (t + 2 < n_kv) {  // start moving the tile after next HBM → L2 while this one is still waiting for its slot
+#pragma unroll
+            for (int c = 0; c < C::kChunks; ++c) {
+              tma_prefetch_l2_2d(&tmap_qkv, col_k + c * 64, krow + 2 * BKV);
+              tma_prefetch_l2_2d(&tmap_qkv, col_v + c * 64, krow + 2 * BKV);
+            }
+          }
           mbar_wait(&k_empty[st], ph ^ 1);
           mbar_expect_tx(&k_full[st], C::kKVBytes);
 #pragma unroll
@@ -282,25 +291,32 @@ __global__ void __launch_bounds__(kThreads, 1)
         // registers retire as we go; four partial sums keep the FADD chain short
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         uint8_t* pbuf = sP + st * C::kPBytes;
+        // only the diagonal tile needs the causal mask: keep the per-element compare/select out of the common path
+        auto exp_pack_store = [&](auto masked) {
 #pragma unroll
-        for (int c = 0; c < BKV / 32; ++c) {
-          uint32_t pk[16];
+          for (int c = 0; c < BKV / 32; ++c) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + j]), p.scale_log2, -m_new));
-            float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + j + 1]), p.scale_log2, -m_new));
-            if (diag && c * 32 + j > r) e0 = 0.f;
-            if (diag && c * 32 + j + 1 > r) e1 = 0.f;
-            l4[(j >> 1) & 3] += e0 + e1;
-            pk[j >> 1] = pack_bf16x2(__float_as_uint(e0), __float_as_uint(e1));
+            for (int j = 0; j < 32; j += 2) {
+              float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + j]), p.scale_log2, -m_new));
+              float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + j + 1]), p.scale_log2, -m_new));
+              if (decltype(masked)::value) {
+                if (c * 32 + j > r) e0 = 0.f;
+                if (c * 32 + j + 1 > r) e1 = 0.f;
+              }
+              l4[(j >> 1) & 3] += e0 + e1;
+              pk[j >> 1] = pack_bf16x2(__float_as_uint(e0), __float_as_uint(e1));
+            }
+            const uint32_t sbase = smem_u32(pbuf + (c >> 1) * (BQ * 128)) + r * 128;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t chunk = (uint32_t)((c & 1) * 4 + i);
+              st_shared_v4(sbase + ((chunk ^ row_sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            }
           }
-          const uint32_t sbase = smem_u32(pbuf + (c >> 1) * (BQ * 128)) + r * 128;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t chunk = (uint32_t)((c & 1) * 4 + i);
-            st_shared_v4(sbase + ((chunk ^ row_sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-          }
-        }
+        };
+        if (diag) exp_pack_store(std::true_type{});
+        else exp_pack_store(std::false_type{});
         l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         // rescale O if some row's max moved (needs P·V of the previous tile finished; ordered before ours by p_full below)
         if (any_grow && t > 0) {
