@@ -158,6 +158,7 @@ class Transformer(nn.Module):
         self.layers = nn.ModuleList(TransformerBlock(i, args) for i in range(args.n_layers))
         self.norm = RMSNormWeight(args.dim)
         self.output = nn.Parameter(torch.empty(args.vocab_size, args.dim))
+        self.ac_ckpt: bool | int = False  # True = every block, n = every n-th block (train.ac_ckpt)
         self.attn_impl = "auto"
         self._rope: tuple[torch.Tensor, torch.Tensor] | None = None
 
@@ -188,8 +189,16 @@ class Transformer(nn.Module):
         cos, sin = self.rope_tables(S, tokens.device)
         h = self.tok_embeddings(tokens)
         delta = None
-        for layer in self.layers:
-            h, delta = layer(h, delta, cos, sin, self.attn_impl)
+        ac = self.ac_ckpt if torch.is_grad_enabled() else False
+        for i, layer in enumerate(self.layers):
+            if ac and (ac is True or i % int(ac) == 0):
+                # activation checkpointing: keep only the block's inputs, re-run its forward inside backward. The in-place ops of
+                # the block (RoPE on the QKV GEMM output) act on tensors the block itself creates, so replaying it is safe.
+                from torch.utils.checkpoint import checkpoint
+
+                h, delta = checkpoint(layer, h, delta, cos, sin, self.attn_impl, use_reentrant=False)
+            else:
+                h, delta = layer(h, delta, cos, sin, self.attn_impl)
         x, _ = ops.add_rmsnorm(delta, h, self.norm.weight, self.args.norm_eps)
         return x
 

@@ -53,6 +53,7 @@ class Trainer:
         # identical init on every rank (same seed) — workers start from the same θ₀
         self.model: Transformer = build_model(cfg.name_model, cfg.type_model, device=self.device, dtype=dtype, seed=cfg.seed, **overrides)
         self.model.attn_impl = cfg.train.attn_impl
+        self.model.ac_ckpt = cfg.train.ac_ckpt
 
         self.heap = None
         use_fused = cuda and cfg.train.fused_comm

@@ -2,6 +2,7 @@
 
 import copy
 
+import pytest
 import torch
 
 from prime_b200.models.llama import build_model
@@ -69,3 +70,23 @@ def test_boundary_hooks_fire_per_layer():
     m.loss(tok, tok).backward()
     # backward order: head first, then layers from last to first
     assert fired == ["head", "layer1", "layer0"]
+
+
+@pytest.mark.parametrize("ac", [True, 2])
+def test_activation_checkpointing_is_exact(ac):
+    """Re-running a block's forward inside backward must not change the loss, the gradients or how often a bucket is reduced."""
+    import torch
+
+    from prime_b200.config import Config
+    from prime_b200.trainer import Trainer
+
+    def run(ac_ckpt):
+        cfg = Config.model_validate({"name_model": "debugmodel", "data": {"seq_length": 32}, "optim": {"batch_size": 4, "warmup_steps": 1},
+                                     "train": {"micro_bs": 2, "ac_ckpt": ac_ckpt}})  # fmt: skip
+        t = Trainer(cfg)
+        losses = [float(t.inner_step().loss) for _ in range(3)]
+        return losses, t.engine.master.clone(), float(t.engine.last_grad_norm)
+
+    l0, m0, g0 = run(False)
+    l1, m1, g1 = run(ac)
+    assert l0 == l1 and g0 == g1 and torch.equal(m0, m1)
