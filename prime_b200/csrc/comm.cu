@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(512) adamw_push_kernel(float* __restrict__ p32
     const bf16x8 packed = pack8(out);
 #pragma unroll
     for (int q = 0; q < kMaxPeers; ++q)
-      if (q < dst.n) reinterpret_cast<bf16x8*>(reinterpret_cast<__nv_bfloat16*>(dst.p[q]) + dst_off)[i] = packed;
+      if (q < dst.n) stg_v4(reinterpret_cast<bf16x8*>(reinterpret_cast<__nv_bfloat16*>(dst.p[q]) + dst_off) + i, packed);
   }
 }
 
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(512) cast_push_kernel(const float* __restrict_
     const bf16x8 pk = pack8(f);
 #pragma unroll
     for (int q = 0; q < kMaxPeers; ++q)
-      if (q < dst.n) reinterpret_cast<bf16x8*>(reinterpret_cast<__nv_bfloat16*>(dst.p[q]) + dst_off)[i] = pk;
+      if (q < dst.n) stg_v4(reinterpret_cast<bf16x8*>(reinterpret_cast<__nv_bfloat16*>(dst.p[q]) + dst_off) + i, pk);
   }
 }
 PB_EXPORT int pb_cast_push(const float* src, int64_t n, const PeerPtrs* dst, int64_t dst_off, cudaStream_t stream) {

@@ -83,6 +83,12 @@ __device__ __forceinline__ void stg_stream(bf16x8* p, const bf16x8& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r.x), "r"(r.y), "r"(r.z),
                "r"(r.w));
 }
+// one 16-byte store (plain `*dst = v` on the struct is split into four 32-bit stores by the compiler: 4x the instructions and,
+// on peer pointers, 4x the NVLink write packets)
+__device__ __forceinline__ void stg_v4(bf16x8* p, const bf16x8& v) {
+  const uint4& r = *reinterpret_cast<const uint4*>(&v);
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
+}
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
