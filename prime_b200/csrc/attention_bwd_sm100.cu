@@ -89,6 +89,14 @@ __device__ __forceinline__ void store_row_chunk_bf16(uint32_t block_base, int r,
   }
 }
 
+// same, for 32 values already packed as 16 bf16x2 words
+__device__ __forceinline__ void store_row_chunk_packed(uint32_t block_base, int r, int half, const uint32_t (&x)[16]) {
+  const uint32_t sbase = block_base + r * 128;
+  const uint32_t sw = (uint32_t)(r & 7);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) st_shared_v4(sbase + (((uint32_t)(half * 4 + i) ^ sw) << 4), x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+}
+
 // ----------------------------------------------------------------------------------------------------- dK / dV
 template <int D>
 struct DkvCfg {
@@ -97,13 +105,16 @@ struct DkvCfg {
   static constexpr uint32_t kQBytes = 64 * D * 2;             // one Q or dO tile (64 rows)
   static constexpr uint32_t kPBytes = 128 * 128;              // Pᵀ or dSᵀ : [128 kv rows x 64 q]
   static constexpr uint32_t kOffV = kKVBytes;
-  static constexpr int kQStages = 3;                          // Q/dO ring: a slot is held until dV/dK of its tile retire, so
-                                                              // two tiles in flight + one TMA load (≈1 µs) in the air
+  // Q/dO ring of 4: a slot is held from its TMA load (≈2600 clk to land, measured) until dV/dK of its tile retire, and S/dP are
+  // issued TWO tiles ahead, so tiles it, it+1 (in the math groups), it+2 (S/dP issued) and it+3 (loading) are all resident. The
+  // 32 KB for the 4th slot come from single-buffering Pᵀ/dSᵀ: a math group packs its tile in registers and only waits for the
+  // previous tile's dV/dK MMAs right before storing (they retired long ago unless the groups have drifted together).
+  static constexpr int kQStages = 4;
   static constexpr uint32_t kOffQ = 2 * kKVBytes;
   static constexpr uint32_t kOffdO = kOffQ + kQStages * kQBytes;
-  static constexpr uint32_t kOffP = kOffdO + kQStages * kQBytes;  // 2 stages
-  static constexpr uint32_t kOffdS = kOffP + 2 * kPBytes;     // 2 stages
-  static constexpr uint32_t kOffBar = kOffdS + 2 * kPBytes;
+  static constexpr uint32_t kOffP = kOffdO + kQStages * kQBytes;
+  static constexpr uint32_t kOffdS = kOffP + kPBytes;
+  static constexpr uint32_t kOffBar = kOffdS + kPBytes;
   static constexpr uint32_t kSmem = kOffBar + 256 + 1024;
   static constexpr uint32_t tS = 0, tdP = 128, tdV = 256, tdK = 256 + D;
 };
@@ -124,13 +135,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* sdS = smem + C::kOffdS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* kv_full = bars;        // 1
-  uint64_t* q_full = bars + 1;     // 3
-  uint64_t* q_empty = bars + 4;    // 3
-  uint64_t* s_full = bars + 7;     // 2
-  uint64_t* s_empty = bars + 9;    // 2 (4 warps)
-  uint64_t* p_full = bars + 11;    // 2 (4 warps)
-  uint64_t* acc_done = bars + 13;  // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* q_full = bars + 1;     // 4
+  uint64_t* q_empty = bars + 5;    // 4
+  uint64_t* s_full = bars + 9;     // 2
+  uint64_t* s_empty = bars + 11;   // 2 (4 warps)
+  uint64_t* p_full = bars + 13;    // 2 (4 warps)
+  uint64_t* acc_done = bars + 15;  // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jb = blockIdx.x;  // KV block (128 rows)
@@ -239,18 +250,30 @@ __global__ void __launch_bounds__(kThreads, 1)
                       make_smem_desc(d0 + c * (64 * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
         umma_commit(&s_full[st]);
       };
-      // (Issuing S/dP two tiles ahead was tried: with a 3-slot Q/dO ring the MMA thread then blocks on the load of tile it+2 in
-      // front of dV/dK of tile it and everything slows down — it needs a ≥5-slot ring, i.e. Pᵀ/dSᵀ moved from smem into TMEM.)
+      // S/dP run up to TWO tiles ahead: TMEM stage it&1 is free as soon as its math group has pulled tile `it` into registers (long
+      // before it finishes the math), so tile it+2 can already be waiting in TMEM when that group comes back. The second tile is
+      // issued opportunistically from the P-wait polling loop: a blocking wait for its Q/dO load in front of dV/dK of tile `it`
+      // stalls the whole pipeline (measured with a 3-slot ring: slower than one-ahead; the trace shows the MMA thread parked there).
+      auto sd_ready = [&](int it) {  // can S/dP of tile `it` be issued without blocking?
+        return mbar_try_wait(&q_full[it % C::kQStages], (it / C::kQStages) & 1) && mbar_try_wait(&s_empty[it & 1], ((it >> 1) & 1) ^ 1);
+      };
       issue_sd(0);
+      int sd_next = 1;  // next tile whose S/dP has not been issued
       for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) issue_sd(it + 1);  // overlaps the math of tile `it`
+        if (sd_next <= it + 1 && sd_next < n_it) issue_sd(sd_next++);  // one tile ahead is mandatory
         const int st = it & 1;
         const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&p_full[st], ph);
+        {  // two tiles ahead whenever it costs nothing; never block in front of dV/dK of tile `it`
+          SpinGuard guard;
+          while (!mbar_try_wait(&p_full[st], ph)) {
+            guard.tick();
+            if (sd_next == it + 2 && sd_next < n_it && sd_ready(sd_next)) issue_sd(sd_next++);
+          }
+        }
         trace_ev(p, 1, tr_n, 3, it);  // Pᵀ/dSᵀ ready → issue dV, dK
         tc_fence_after();
         const int qs = it % C::kQStages;
-        const uint32_t pa = smem_u32(sP + st * C::kPBytes), da = smem_u32(sdS + st * C::kPBytes);
+        const uint32_t pa = smem_u32(sP), da = smem_u32(sdS);  // single-buffered: see DkvCfg
         const uint32_t q0 = smem_u32(sQ + qs * C::kQBytes), d0 = smem_u32(sdO + qs * C::kQBytes);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)  // K = 64 query rows
@@ -302,32 +325,37 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 3, it);  // TMEM loads done
-      if (it >= 2) mbar_wait(&acc_done[st], ph ^ 1);  // Pᵀ/dSᵀ buffers of this stage are free again
-      if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 4, it);  // P/dS smem stage free
       // only the (at most two) diagonal tiles need the causal mask: keep the per-element compare/select out of the common path
+      uint32_t pk[32], dk[32];  // Pᵀ and dSᵀ rows of this thread, packed bf16x2
       auto tile_math = [&](auto masked) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float pr[32], ds[32];
+        for (int j4 = 0; j4 < 16; ++j4) {
+          const float4 L = __ldg(lse4 + j4), Dl = __ldg(del4 + j4);
+          const float ls[4] = {L.x, L.y, L.z, L.w}, dl[4] = {Dl.x * p.scale, Dl.y * p.scale, Dl.z * p.scale, Dl.w * p.scale};
+          float pv[4], dsv[4];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 L = __ldg(lse4 + c * 8 + j4), Dl = __ldg(del4 + c * 8 + j4);
-            const float ls[4] = {L.x, L.y, L.z, L.w}, dl[4] = {Dl.x * p.scale, Dl.y * p.scale, Dl.z * p.scale, Dl.w * p.scale};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j4 * 4 + e, qc = c * 32 + j;
-              float pv = fast_exp2(fmaf(__uint_as_float(sv[qc]), p.scale_log2, -ls[e]));
-              if (decltype(masked)::value && kv_idx > qpos0 + qc) pv = 0.f;
-              pr[j] = pv;
-              ds[j] = pv * fmaf(__uint_as_float(dv[qc]), p.scale, -dl[e]);
-            }
+          for (int e = 0; e < 4; ++e) {
+            const int qc = j4 * 4 + e;
+            pv[e] = fast_exp2(fmaf(__uint_as_float(sv[qc]), p.scale_log2, -ls[e]));
+            if (decltype(masked)::value && kv_idx > qpos0 + qc) pv[e] = 0.f;
+            dsv[e] = pv[e] * fmaf(__uint_as_float(dv[qc]), p.scale, -dl[e]);
           }
-          store_row_chunk_bf16(smem_u32(sP + st * C::kPBytes), r, c, pr);
-          store_row_chunk_bf16(smem_u32(sdS + st * C::kPBytes), r, c, ds);
+          pk[2 * j4] = pack_bf16x2(__float_as_uint(pv[0]), __float_as_uint(pv[1]));
+          pk[2 * j4 + 1] = pack_bf16x2(__float_as_uint(pv[2]), __float_as_uint(pv[3]));
+          dk[2 * j4] = pack_bf16x2(__float_as_uint(dsv[0]), __float_as_uint(dsv[1]));
+          dk[2 * j4 + 1] = pack_bf16x2(__float_as_uint(dsv[2]), __float_as_uint(dsv[3]));
         }
       };
       if (need_mask) tile_math(std::true_type{});
       else tile_math(std::false_type{});
+      // the single Pᵀ/dSᵀ buffer was last read by dV/dK of the previous tile (the other group's)
+      if (it >= 1) mbar_wait(&acc_done[(it - 1) & 1], ((it - 1) >> 1) & 1);
+      if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 4, it);  // P/dS buffer free
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        store_row_chunk_packed(smem_u32(sP), r, c, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
+        store_row_chunk_packed(smem_u32(sdS), r, c, *reinterpret_cast<uint32_t(*)[16]>(&dk[c * 16]));
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);
@@ -338,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_wait(&acc_done[tl & 1], (tl >> 1) & 1);
     if (n_it >= 2) mbar_wait(&acc_done[(tl - 1) & 1], ((tl - 1) >> 1) & 1);
     tc_fence_after();
-    uint8_t* stage = sP;  // [which(dV,dK)][chunk c] blocks of [128 rows x 128 B]
+    uint8_t* stage = sQ;  // the Q/dO rings are idle now: [which(dV,dK)][chunk c] blocks of [128 rows x 128 B]
     {
       const int which = half;  // warps 4..7 drain dV, warps 8..11 drain dK
 #pragma unroll 1
@@ -380,7 +408,7 @@ struct DqCfg {
   static constexpr uint32_t kKVBytes = 64 * D * 2;   // one K or V tile (64 rows)
   static constexpr uint32_t kdSBytes = 128 * 128;    // dS : [128 q rows x 64 kv]
   static constexpr uint32_t kOffdO = kQBytes;
-  static constexpr int kKVStages = 3;  // K/V ring: a slot is held until dQ += dS·K of its tile retires
+  static constexpr int kKVStages = 4;  // K/V ring: a slot is held until dQ += dS·K of its tile retires; S/dP run two tiles ahead
   static constexpr uint32_t kOffK = 2 * kQBytes;
   static constexpr uint32_t kOffV = kOffK + kKVStages * kKVBytes;
   static constexpr uint32_t kOffdS = kOffV + kKVStages * kKVBytes;
@@ -404,13 +432,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* sdS = smem + C::kOffdS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* q_full = bars;         // 1
-  uint64_t* kv_full = bars + 1;    // 3
-  uint64_t* kv_empty = bars + 4;   // 3
-  uint64_t* s_full = bars + 7;     // 2
-  uint64_t* s_empty = bars + 9;    // 2 (4 warps)
-  uint64_t* p_full = bars + 11;    // 2 (4 warps)
-  uint64_t* acc_done = bars + 13;  // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* kv_full = bars + 1;    // 4
+  uint64_t* kv_empty = bars + 5;   // 4
+  uint64_t* s_full = bars + 9;     // 2
+  uint64_t* s_empty = bars + 11;   // 2 (4 warps)
+  uint64_t* p_full = bars + 13;    // 2 (4 warps)
+  uint64_t* acc_done = bars + 15;  // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqb = p.S / 128;
@@ -505,12 +533,22 @@ __global__ void __launch_bounds__(kThreads, 1)
                       make_smem_desc(v0 + c * (64 * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
         umma_commit(&s_full[st]);
       };
-      issue_sd(0);
+      auto sd_ready = [&](int t) {
+        return mbar_try_wait(&kv_full[t % C::kKVStages], (t / C::kKVStages) & 1) && mbar_try_wait(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
+      };
+      issue_sd(0);  // S/dP: one tile ahead mandatory, two ahead opportunistic (see the dK/dV kernel)
+      int sd_next = 1;
       for (int t = 0; t < n_kv; ++t) {
-        if (t + 1 < n_kv) issue_sd(t + 1);
+        if (sd_next <= t + 1 && sd_next < n_kv) issue_sd(sd_next++);
         const int st = t & 1;
         const uint32_t ph = (t >> 1) & 1;
-        mbar_wait(&p_full[st], ph);
+        {
+          SpinGuard guard;
+          while (!mbar_try_wait(&p_full[st], ph)) {
+            guard.tick();
+            if (sd_next == t + 2 && sd_next < n_kv && sd_ready(sd_next)) issue_sd(sd_next++);
+          }
+        }
         tc_fence_after();
         const int ks = t % C::kKVStages;
         const uint32_t da = smem_u32(sdS + st * C::kdSBytes), k0 = smem_u32(sK + ks * C::kKVBytes);

@@ -188,18 +188,38 @@ __global__ void __launch_bounds__(kThreads, 1)
         umma_commit(&s_full[st]);
         if (last_of_item) umma_commit(q_empty);  // the producer may now overwrite Q with the next item's block
       };
+      // can QKᵀ of tile gg be issued right now without blocking? (its K tile has landed and its S stage has been drained)
+      auto s_ready = [&](int gg) {
+        const int st = gg & 1;
+        const uint32_t ph = (gg >> 1) & 1;
+        return mbar_try_wait(&k_full[st], ph) && mbar_try_wait(&s_empty[st], ph ^ 1);
+      };
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         int qb, bh;
         item(w, qb, bh);
         const int n_kv = p.causal ? qb + 1 : p.S / BKV;
         mbar_wait(q_full, it & 1);
         issue_s(g, n_kv == 1);
+        int s_next = 1;  // next tile (item-local) whose QKᵀ has not been issued yet
         for (int t = 0; t < n_kv; ++t, ++g) {
-          if (t + 1 < n_kv) issue_s(g + 1, t + 2 == n_kv);  // overlaps the softmax of tile t
+          if (s_next <= t + 1 && s_next < n_kv) {  // one tile ahead is mandatory (overlaps the softmax of tile t)
+            issue_s(g + (s_next - t), s_next + 1 == n_kv);
+            ++s_next;
+          }
           const int st = g & 1;
           const uint32_t ph = (g >> 1) & 1;
           mbar_wait(&v_full[st], ph);
-          mbar_wait(&p_full[st], ph);
+          // while P of tile t is being produced, opportunistically run QKᵀ TWO tiles ahead: S stage g&1 is free as soon as its
+          // softmax group has pulled tile g into registers, so when K(g+2) has landed too the group finds its next tile waiting.
+          // Never block on it here — a blocking wait in front of P·V(t) measurably slows the whole pipeline down.
+          SpinGuard guard;
+          while (!mbar_try_wait(&p_full[st], ph)) {
+            guard.tick();
+            if (s_next == t + 2 && s_next < n_kv && s_ready(g + 2)) {
+              issue_s(g + 2, s_next + 1 == n_kv);
+              ++s_next;
+            }
+          }
           if (t == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);  // previous item's epilogue has drained O
           tc_fence_after();
           const uint32_t a0 = smem_u32(sP + st * C::kPBytes), b0 = smem_u32(sV + st * C::kKVBytes);

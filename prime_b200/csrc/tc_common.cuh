@@ -45,6 +45,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// for hand-written polling loops: same 4 s bound as mbar_wait (call once per iteration)
+struct SpinGuard {
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  __device__ __forceinline__ void tick() {
+    if ((++spins & 0xfff) == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) __trap();
+    }
+  }
+};
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
