@@ -62,7 +62,31 @@ struct BwdParams {
   float scale, scale_log2;
   int causal;
   unsigned long long* trace;  // optional pipeline trace (tools/attn_trace.py): CTA (0,0) stamps clock64() at role events
+  // optional fused RoPE backward: fp32 tables [S, D/2]; dQ and dK leave the kernels already rotated back (inverse rotation,
+  // interleaved-pair convention) so no separate pass over the 200 MB dQKV tensor is needed. nullptr = plain attention backward.
+  const float* rope_cos;
+  const float* rope_sin;
 };
+
+// inverse RoPE on 32 consecutive head-dim columns [c32*32, c32*32+32) of one row at sequence position `pos`
+template <int D>
+__device__ __forceinline__ void rope_inverse_chunk(float (&x)[32], const float* __restrict__ cosb, const float* __restrict__ sinb, int pos,
+                                                   int c32) {
+  const float4* c4 = reinterpret_cast<const float4*>(cosb + (int64_t)pos * (D / 2) + c32 * 16);
+  const float4* s4 = reinterpret_cast<const float4*>(sinb + (int64_t)pos * (D / 2) + c32 * 16);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 c = __ldg(c4 + k), sn = __ldg(s4 + k);
+    const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = (k * 4 + e) * 2;
+      const float a = x[j], b = x[j + 1];
+      x[j] = a * cc[e] + b * ss[e];
+      x[j + 1] = b * cc[e] - a * ss[e];
+    }
+  }
+}
 
 // trace record: [role 0..3][slot] = {event code, tile, clock}; role 0 loader, 1 MMA, 2 math group 0, 3 math group 1
 __device__ __forceinline__ void trace_ev(const BwdParams& p, int role, int& n, int code, int tile) {
@@ -377,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        if (which == 1 && p.rope_cos != nullptr) rope_inverse_chunk<D>(x, p.rope_cos, p.rope_sin, kv_idx, c32);  // dK only
         store_row_chunk_bf16(smem_u32(stage + (which * C::kChunks + (c32 >> 1)) * (128 * 128)), r, c32 & 1, x);
       }
       fence_proxy_async();
@@ -620,6 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       float x[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+      if (p.rope_cos != nullptr) rope_inverse_chunk<D>(x, p.rope_cos, p.rope_sin, q_idx, c32);
       store_row_chunk_bf16(smem_u32(stage + (c32 >> 1) * (128 * 128)), r, c32 & 1, x);
     }
     fence_proxy_async();
@@ -654,7 +680,7 @@ unsigned long long* g_bwd_trace = nullptr;
 
 template <int D>
 int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv, int B, int S,
-               int H, int Hkv, float scale, int causal, cudaStream_t stream) {
+               int H, int Hkv, float scale, int causal, const float* rope_cos, const float* rope_sin, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(bwd_dkdv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DkvCfg<D>::kSmem);
@@ -677,7 +703,7 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   if ((rc = pbhost::cached_tmap(&tdo64, dout, rows, wo, wo, 64, 64, 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tdo128, dout, rows, wo, wo, 64, 128, 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tdq, dqkv, rows, wqkv, wqkv, 64, 32, 2))) return rc;
-  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace};
+  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace, rope_cos, rope_sin};
   bwd_dkdv_kernel<D><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
   bwd_dq_kernel<D><<<dim3(S / 128, B * H), kThreads, DqCfg<D>::kSmem, stream>>>(tq128, tq64, tdo128, tdq, p);
   cudaError_t e = cudaGetLastError();
@@ -693,7 +719,17 @@ PB_EXPORT void pb_flash_attn_bwd_set_trace(unsigned long long* buf) { g_bwd_trac
 PB_EXPORT int pb_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,
                                 int B, int S, int H, int Hkv, int D, float scale, int causal, cudaStream_t stream) {
   if (S % 128 != 0 || H % Hkv != 0) return -1;
-  if (D == 128) return launch_bwd<128>(qkv, out, dout, lse2, delta, dqkv, B, S, H, Hkv, scale, causal, stream);
-  if (D == 64) return launch_bwd<64>(qkv, out, dout, lse2, delta, dqkv, B, S, H, Hkv, scale, causal, stream);
+  if (D == 128) return launch_bwd<128>(qkv, out, dout, lse2, delta, dqkv, B, S, H, Hkv, scale, causal, nullptr, nullptr, stream);
+  if (D == 64) return launch_bwd<64>(qkv, out, dout, lse2, delta, dqkv, B, S, H, Hkv, scale, causal, nullptr, nullptr, stream);
+  return -2;
+}
+
+// Same, with the RoPE backward fused into the dQ / dK epilogues (cos/sin: fp32 [S, D/2] tables of the forward rotation).
+PB_EXPORT int pb_flash_attn_bwd_rope(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,
+                                     int B, int S, int H, int Hkv, int D, float scale, int causal, const float* rope_cos,
+                                     const float* rope_sin, cudaStream_t stream) {
+  if (S % 128 != 0 || H % Hkv != 0) return -1;
+  if (D == 128) return launch_bwd<128>(qkv, out, dout, lse2, delta, dqkv, B, S, H, Hkv, scale, causal, rope_cos, rope_sin, stream);
+  if (D == 64) return launch_bwd<64>(qkv, out, dout, lse2, delta, dqkv, B, S, H, Hkv, scale, causal, rope_cos, rope_sin, stream);
   return -2;
 }

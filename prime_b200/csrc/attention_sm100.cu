@@ -144,13 +144,6 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int st = g & 1;
           const uint32_t ph = (g >> 1) & 1;
           const int krow = b * p.S + t * BKV;
-          if (t + 2 < n_kv) {  // start moving the tile after next HBM → L2 while this one is still waiting for its slot
-#pragma unroll
-            for (int c = 0; c < C::kChunks; ++c) {
-              tma_prefetch_l2_2d(&tmap_qkv, col_k + c * 64, krow + 2 * BKV);
-              tma_prefetch_l2_2d(&tmap_qkv, col_v + c * 64, krow + 2 * BKV);
-            }
-          }
           mbar_wait(&k_empty[st], ph ^ 1);
           mbar_expect_tx(&k_full[st], C::kKVBytes);
 #pragma unroll

@@ -73,7 +73,31 @@ struct GemmParams {
   int c_fp32, accumulate;
   int split_k;  // >1 only with c_fp32 && accumulate: every K slice reduce-adds its partial tile (weight-gradient GEMMs)
   void* C;
+  // optional RoPE epilogue (QKV projection): output columns [0, rope_cols) are heads of width rope_D whose interleaved pairs are
+  // rotated by the position (row % rope_S) while the tile is still in registers; tables fp32 [rope_S.., rope_D/2]. bf16 outputs only.
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_S, rope_cols, rope_D;
 };
+
+// rotate the 16 interleaved pairs held in 32 consecutive fp32 accumulator registers (head-dim offset d0, sequence position pos)
+__device__ __forceinline__ void rope_regs(uint32_t (&r)[32], const float* __restrict__ cosb, const float* __restrict__ sinb, int pos, int d0,
+                                          int half_d) {
+  const float4* c4 = reinterpret_cast<const float4*>(cosb + (int64_t)pos * half_d + (d0 >> 1));
+  const float4* s4 = reinterpret_cast<const float4*>(sinb + (int64_t)pos * half_d + (d0 >> 1));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 c = __ldg(c4 + k), sn = __ldg(s4 + k);
+    const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = (k * 4 + e) * 2;
+      const float a = __uint_as_float(r[j]), b = __uint_as_float(r[j + 1]);
+      r[j] = __float_as_uint(a * cc[e] - b * ss[e]);
+      r[j + 1] = __float_as_uint(a * ss[e] + b * cc[e]);
+    }
+  }
+}
 
 template <int A_MN, int B_MN, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -260,6 +284,12 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
           tmem_ld_wait();
+          if (p.rope_cos != nullptr && tn * BN + g * 64 < p.rope_cols) {  // Q/K head columns: rotate in registers
+            const int pos = (row0 + lane) % p.rope_S;
+            const int d0 = (tn * BN + g * 64) % p.rope_D;
+            rope_regs(r0, p.rope_cos, p.rope_sin, pos, d0, p.rope_D >> 1);
+            rope_regs(r1, p.rope_cos, p.rope_sin, pos, d0 + 32, p.rope_D >> 1);
+          }
           const uint32_t sbase = smem_u32(my_stage + buf * 4096) + lane * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -393,9 +423,9 @@ PB_EXPORT int pb_gemm_set_split_k(int mode) {
 }
 
 // lda/ldb: row stride (elements) of the matrix AS STORED (see header comment).
-PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
-                           int a_mn_major, int b_mn_major, int c_fp32, int accumulate, int max_ctas,
-                           cudaStream_t stream) {
+static int gemm_impl(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn_major,
+                     int b_mn_major, int c_fp32, int accumulate, int max_ctas, const float* rope_cos, const float* rope_sin,
+                     int rope_S, int rope_cols, int rope_D, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (ldc % (c_fp32 ? 4 : 8))) return -1;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) return -2;
@@ -416,7 +446,7 @@ PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, 
   rc = c_fp32 ? pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 32, 4)
               : pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 64, 32, 2);
   if (rc) return rc;
-  GemmParams p{M, N, K, ldc, a_mn_major, b_mn_major, c_fp32, accumulate, 1, C};
+  GemmParams p{M, N, K, ldc, a_mn_major, b_mn_major, c_fp32, accumulate, 1, C, rope_cos, rope_sin, rope_S, rope_cols, rope_D};
   if (c_fp32 && accumulate && g_split_k_mode != 0 && g_split_k_mode != 1) {
     if (g_num_sms == 0) {
       int dev = 0;
@@ -440,4 +470,21 @@ PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, 
   if (!a_mn_major && b_mn_major) return launch<0, 1, 0>(ta, tb, tc, p, max_ctas, stream);
   if (a_mn_major && !b_mn_major) return launch<1, 0, 0>(ta, tb, tc, p, max_ctas, stream);
   return launch<1, 1, 0>(ta, tb, tc, p, max_ctas, stream);
+}
+
+PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                           int a_mn_major, int b_mn_major, int c_fp32, int accumulate, int max_ctas,
+                           cudaStream_t stream) {
+  return gemm_impl(A, B, C, M, N, K, lda, ldb, ldc, a_mn_major, b_mn_major, c_fp32, accumulate, max_ctas, nullptr, nullptr, 1, 0, 64,
+                   stream);
+}
+
+// y = x·Wᵀ with RoPE applied to output columns [0, rope_cols) in the epilogue (the fused QKV projection). Row r of the output is
+// token r of a [B, S] batch (position r % S); heads are rope_D wide; cos/sin are fp32 [>=S, rope_D/2]. bf16 output, K-major operands.
+PB_EXPORT int pb_gemm_bf16_rope(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int max_ctas,
+                                const float* rope_cos, const float* rope_sin, int rope_S, int rope_cols, int rope_D,
+                                cudaStream_t stream) {
+  if (rope_cos == nullptr || rope_sin == nullptr || rope_S <= 0 || M % rope_S != 0) return -3;
+  if ((rope_D != 64 && rope_D != 128) || rope_cols % rope_D != 0 || rope_cols > N) return -4;
+  return gemm_impl(A, B, C, M, N, K, lda, ldb, ldc, 0, 0, 0, 0, max_ctas, rope_cos, rope_sin, rope_S, rope_cols, rope_D, stream);
 }

@@ -104,8 +104,13 @@ class Attention(nn.Module):
     def forward(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, attn_impl: str = "auto") -> torch.Tensor:
         B, S, _ = x.shape
         H, Hkv, D = self.n_heads, self.n_kv_heads, self.head_dim
-        qkv = ops.linear(x, self.wqkv)  # [B, S, (H+2Hkv)·D]
-        out = ops.rope_attention_qkv(qkv, cos, sin, H, Hkv, causal=True, impl=attn_impl)  # [B, S, H·D], no layout shuffles
+        if attn_impl in ("auto", "native") and ops.rope_fusable(x, H, Hkv, D):
+            # RoPE rides in the QKV GEMM epilogue (forward) and in the dQ/dK epilogues of the attention backward: no rotation pass
+            qkv = ops.linear_qkv_rope(x, self.wqkv, cos, sin, H, Hkv)  # [B, S, (H+2Hkv)·D], Q/K heads rotated
+            out = ops.rope_attention_qkv(qkv, cos, sin, H, Hkv, causal=True, impl=attn_impl, pre_rotated=True)
+        else:
+            qkv = ops.linear(x, self.wqkv)  # [B, S, (H+2Hkv)·D]
+            out = ops.rope_attention_qkv(qkv, cos, sin, H, Hkv, causal=True, impl=attn_impl)  # [B, S, H·D], no layout shuffles
         return ops.linear(out, self.wo)
 
 

@@ -9,6 +9,8 @@ from .functional import (  # noqa: F401
     gemm,
     launch_count,
     linear,
+    linear_qkv_rope,
+    rope_fusable,
     reset_launch_count,
     rmsnorm,
     rope_attention_qkv,

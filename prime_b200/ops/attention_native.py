@@ -77,16 +77,19 @@ def _rope_inplace(lib, t: torch.Tensor, cos, sin, n_heads: int, n_kv_heads: int,
 
 
 class _RopeFlashAttnFn(torch.autograd.Function):
-    """RoPE ⊕ attention as ONE autograd node: the rotation is applied in place on the QKV GEMM output (nobody else reads the
-    un-rotated activation) and the inverse rotation is applied in place on the dQKV this node itself allocates — no copy of
-    the 200 MB gradient, which a stand-alone RoPE node needs because it may not mutate a gradient it does not own."""
+    """RoPE ⊕ attention as ONE autograd node: forward rotates in place on the QKV GEMM output (nobody else reads the un-rotated
+    activation); backward folds the inverse rotation into the dQ / dK epilogues of the attention-backward kernels, so there is
+    neither a copy of the 200 MB gradient (a stand-alone RoPE node may not mutate a gradient it does not own) nor a separate
+    rotation pass over it."""
 
     @staticmethod
-    def forward(ctx, qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool):
+    def forward(ctx, qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool,
+                pre_rotated: bool = False):  # fmt: skip
         lib = _lib.load()
         B, S, W = qkv.shape
         D = W // (n_heads + 2 * n_kv_heads)
-        _rope_inplace(lib, qkv, cos, sin, n_heads, n_kv_heads, D, 1.0)
+        if not pre_rotated:  # otherwise the QKV GEMM epilogue already did it
+            _rope_inplace(lib, qkv, cos, sin, n_heads, n_kv_heads, D, 1.0)
         out = torch.empty((B, S, n_heads * D), dtype=qkv.dtype, device=qkv.device)
         lse2 = torch.empty((B, n_heads, S), dtype=torch.float32, device=qkv.device)
         scale = 1.0 / math.sqrt(D)
@@ -106,14 +109,16 @@ class _RopeFlashAttnFn(torch.autograd.Function):
         dout = dout if dout.is_contiguous() else dout.contiguous()
         dqkv = torch.empty_like(qkv)
         delta = torch.empty_like(lse2)
-        rc = lib.pb_flash_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse2), _ptr(delta), _ptr(dqkv), B, S, n_heads,
-                                   n_kv_heads, D, scale, int(causal), _stream())  # fmt: skip
-        _lib.check(rc, "pb_flash_attn_bwd")
+        # rotation is orthogonal: its backward is the inverse rotation, applied to dQ / dK inside the attention-backward epilogues
+        # (registers → smem → TMA store), so dQKV is written exactly once
+        assert cos.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous() and cos.shape[1] == D // 2 and cos.shape[0] >= S
+        rc = lib.pb_flash_attn_bwd_rope(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse2), _ptr(delta), _ptr(dqkv), B, S, n_heads,
+                                        n_kv_heads, D, scale, int(causal), _ptr(cos), _ptr(sin), _stream())  # fmt: skip
+        _lib.check(rc, "pb_flash_attn_bwd_rope")
         _count(3)
-        _rope_inplace(lib, dqkv, cos, sin, n_heads, n_kv_heads, D, -1.0)  # rotation is orthogonal: backward = inverse rotation
-        return dqkv, None, None, None, None, None
+        return dqkv, None, None, None, None, None, None
 
 
 def rope_flash_attention_qkv(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, n_kv_heads: int,
-                             causal: bool = True) -> torch.Tensor:  # fmt: skip
-    return _RopeFlashAttnFn.apply(qkv, cos, sin, n_heads, n_kv_heads, causal)
+                             causal: bool = True, pre_rotated: bool = False) -> torch.Tensor:  # fmt: skip
+    return _RopeFlashAttnFn.apply(qkv, cos, sin, n_heads, n_kv_heads, causal, pre_rotated)

@@ -101,7 +101,7 @@ class _LinearFn(torch.autograd.Function):
     epilogue) when the FSDP engine has attached one; otherwise a bf16 gradient is returned."""
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, rope: tuple | None = None) -> torch.Tensor:
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
@@ -109,7 +109,19 @@ class _LinearFn(torch.autograd.Function):
         ctx.x_shape = x.shape
         # allocate with the final shape: a Function output must not be a view (RoPE / the loss rotate / overwrite it in place)
         y = torch.empty((*x.shape[:-1], weight.shape[0]), dtype=x.dtype, device=x.device)
-        gemm(x2, weight, out=y.view(-1, weight.shape[0]))
+        if rope is None:
+            gemm(x2, weight, out=y.view(-1, weight.shape[0]))
+        else:
+            # fused QKV projection: the GEMM epilogue rotates the Q/K head columns while the tile is in registers. The consumer
+            # (rope_attention_qkv(..., pre_rotated=True)) returns the gradient w.r.t. the UN-rotated activation, so backward below
+            # is the plain linear backward.
+            cos, sin, seq_len, rot_cols, head_dim = rope
+            M, N, K = x2.shape[0], weight.shape[0], x2.shape[1]
+            assert cos.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous() and cos.shape[0] >= seq_len
+            rc = _lib.load().pb_gemm_bf16_rope(x2.data_ptr(), weight.data_ptr(), y.data_ptr(), M, N, K, x2.stride(0), weight.stride(0), N, 0,
+                                               cos.data_ptr(), sin.data_ptr(), seq_len, rot_cols, head_dim, _stream())  # fmt: skip
+            _lib.check(rc, "pb_gemm_bf16_rope")
+            _count()
         return y
 
     @staticmethod
@@ -129,13 +141,29 @@ class _LinearFn(torch.autograd.Function):
                 dw = None
             else:
                 dw = gemm(dy2, x2, a_mn_major=True, b_mn_major=True)
-        return dx, dw
+        return dx, dw, None
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     if x.is_cuda:
         return _LinearFn.apply(x, weight)
     return reference.linear(x, weight)
+
+
+def rope_fusable(x: torch.Tensor, n_heads: int, n_kv_heads: int, head_dim: int) -> bool:
+    """Can the QKV projection rotate in its epilogue AND the native attention consume/undo it? (CUDA, [B,S,·] input, S%128==0)"""
+    if not (x.is_cuda and x.dim() == 3 and x.dtype == torch.bfloat16):
+        return False
+    from . import attention_native as native
+
+    return native.supported_shape(x.shape[1], head_dim, n_heads, n_kv_heads)
+
+
+def linear_qkv_rope(x: torch.Tensor, weight: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, n_kv_heads: int) -> torch.Tensor:
+    """Fused QKV projection ⊕ RoPE: [B,S,dim] → [B,S,(H+2Hkv)·D] with the Q and K heads already rotated (GEMM epilogue).
+    Must be consumed by ``rope_attention_qkv(..., pre_rotated=True)``, whose backward undoes the rotation in its own epilogues."""
+    head_dim = weight.shape[0] // (n_heads + 2 * n_kv_heads)
+    return _LinearFn.apply(x, weight, (cos, sin, x.shape[1], (n_heads + n_kv_heads) * head_dim, head_dim))
 
 
 # --------------------------------------------------------------------------- RMSNorm
@@ -395,12 +423,15 @@ def attention_qkv(qkv: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool
 
 
 def rope_attention_qkv(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, n_heads: int, n_kv_heads: int, causal: bool = True,
-                       impl: str = "auto") -> torch.Tensor:  # fmt: skip
-    """RoPE on the Q/K heads of the fused QKV activation followed by attention → [B,S,H·D]. On the native path both run as
-    one autograd node (in-place rotation forward, in-place inverse rotation of the node's own dQKV backward)."""
+                       impl: str = "auto", pre_rotated: bool = False) -> torch.Tensor:  # fmt: skip
+    """RoPE on the Q/K heads of the fused QKV activation followed by attention → [B,S,H·D]. On the native path both run as one
+    autograd node whose backward folds the inverse rotation into the dQ/dK epilogues. ``pre_rotated=True``: the producer
+    (:func:`linear_qkv_rope`) already rotated in its GEMM epilogue; only the backward un-rotation is needed (native path only)."""
     if qkv.is_cuda and impl in ("auto", "native"):
         from . import attention_native as native
 
         if native.supported(qkv, n_heads, n_kv_heads):
-            return native.rope_flash_attention_qkv(qkv, cos, sin, n_heads, n_kv_heads, causal)
+            return native.rope_flash_attention_qkv(qkv, cos, sin, n_heads, n_kv_heads, causal, pre_rotated)
+    if pre_rotated:
+        raise RuntimeError("pre_rotated=True needs the native attention path (its backward undoes the rotation)")
     return attention_qkv(rope_qkv(qkv, cos, sin, n_heads, n_kv_heads), n_heads, n_kv_heads, causal, impl)

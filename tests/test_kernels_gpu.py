@@ -377,3 +377,37 @@ def test_gemm_split_k_reduce_add(split, pair):
     finally:
         ops.set_gemm_pair_mode(bool(old_p))
         ops.set_gemm_split_k(old_s)
+
+
+@pytest.mark.parametrize("H,Hkv,D", [(4, 4, 128), (8, 2, 64)])
+def test_qkv_gemm_rope_epilogue_and_attention_unrotate(H, Hkv, D):
+    """RoPE in the QKV GEMM epilogue (forward) + inverse RoPE in the dQ/dK epilogues of the attention backward: compare
+    y = attention(rope(x Wᵀ)) and the gradients w.r.t. x and W with the fp32 reference (flash attention path end to end)."""
+    from prime_b200 import ops
+    from prime_b200.ops import reference as R
+
+    torch.manual_seed(9)
+    B, S, dim = 2, 256, 512
+    W = (H + 2 * Hkv) * D
+    x = (torch.randn(B, S, dim, device=_dev()) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(W, dim, device=_dev()) * 0.05).to(torch.bfloat16).requires_grad_(True)
+    cos, sin = R.rope_tables(S, D, device=_dev())
+    assert ops.rope_fusable(x, H, Hkv, D)
+    qkv = ops.linear_qkv_rope(x, w, cos, sin, H, Hkv)
+    # the epilogue-rotated projection itself
+    ref_qkv4 = (x.detach().float() @ w.detach().float().t()).view(B, S, H + 2 * Hkv, D)
+    ref_rot = torch.cat((R.rope(ref_qkv4[:, :, : H + Hkv], cos, sin), ref_qkv4[:, :, H + Hkv :]), dim=2).view(B, S, W)
+    assert _rel_err(qkv.detach(), ref_rot) < 1e-2
+    out = ops.rope_attention_qkv(qkv, cos, sin, H, Hkv, causal=True, impl="native", pre_rotated=True)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    torch.cuda.synchronize()
+    xr = x.detach().float().requires_grad_(True)
+    wr = w.detach().float().requires_grad_(True)
+    q4 = (xr @ wr.t()).view(B, S, H + 2 * Hkv, D)
+    rot = R.rope(q4[:, :, : H + Hkv], cos, sin)
+    ref = R.attention(rot[:, :, :H], rot[:, :, H:], q4[:, :, H + Hkv :], True).reshape(B, S, H * D)
+    ref.backward(dout.float())
+    assert _rel_err(out, ref) < 2e-2
+    assert _rel_err(x.grad, xr.grad) < 4e-2, _rel_err(x.grad, xr.grad)
+    assert _rel_err(w.grad, wr.grad) < 4e-2, _rel_err(w.grad, wr.grad)
