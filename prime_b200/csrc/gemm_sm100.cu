@@ -78,6 +78,11 @@ struct GemmParams {
   const float* rope_cos;
   const float* rope_sin;
   int rope_S, rope_cols, rope_D;
+  // optional SwiGLU epilogue (gate/up projection, CTA-pair scheduler only): B = W13 stored [2·FF, K] as [gate rows | up rows];
+  // a tile covers 128 features: the leader CTA stages the 128 GATE rows, its partner the matching 128 UP rows, so every CTA's
+  // accumulator holds gate in columns [0,128) and up in [128,256) for the same features. The epilogue stores gate and up (bf16,
+  // for the backward) into C = gate_up [M, 2·FF] and h = silu(gate)·up into the second output [M, FF].
+  int swiglu_ff;
 };
 
 // rotate the 16 interleaved pairs held in 32 consecutive fp32 accumulator registers (head-dim offset d0, sequence position pos)
@@ -102,7 +107,7 @@ __device__ __forceinline__ void rope_regs(uint32_t (&r)[32], const float* __rest
 template <int A_MN, int B_MN, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_h, const GemmParams p) {
   using G = Geo<PAIR>;
   constexpr int kStages = G::kStages;
   constexpr uint32_t kStageBytes = G::kStageBytes;
@@ -121,7 +126,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + kTileM - 1) / kTileM, tiles_n = (p.N + BN - 1) / BN;
+  const bool swiglu = PAIR && p.swiglu_ff > 0;
+  const int tiles_m = (p.M + kTileM - 1) / kTileM, tiles_n = swiglu ? (p.swiglu_ff + 127) / 128 : (p.N + BN - 1) / BN;
   const int num_kb = (p.K + BK - 1) / BK;
   // split-K: work item w = tile * split_k + slice; slice s covers k-blocks [s*kb_per, min(num_kb, (s+1)*kb_per))
   const int split_k = p.split_k;
@@ -132,6 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_c);
+    prefetch_tmap(&tmap_h);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -165,7 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int kb0 = (tile % split_k) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
         if (kb0 >= kb1) continue;  // empty K slice (split does not divide K): every role skips it identically
         const int m0 = tm * kTileM + (int)crank * BM;      // this CTA's A rows
-        const int n0 = tn * BN + (int)crank * kBRows;      // this CTA's share of the B rows
+        // this CTA's share of the B rows (SwiGLU mode: leader = gate rows, partner = the matching up rows)
+        const int n0 = swiglu ? (int)crank * p.swiglu_ff + tn * 128 : tn * BN + (int)crank * kBRows;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
@@ -275,6 +283,50 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (lane == 0) bulk_commit();
           buf ^= 1;
         }
+      } else if (swiglu) {
+        // pack 64 fp32 accumulator columns to bf16, stage them in the swizzled slab and TMA-store them at (col0, row0)
+        auto emit64 = [&](const uint32_t (&w)[32], const CUtensorMap* map, int col0, bool in_range) {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          const uint32_t sbase = smem_u32(my_stage + buf * 4096) + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) st_shared_v4(sbase + ((j ^ row_sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && in_range) tma_store_2d(map, my_stage + buf * 4096, col0, row0);
+          if (lane == 0) bulk_commit();
+          buf ^= 1;
+        };
+        auto load64_packed = [&](uint32_t col, uint32_t (&w)[32]) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(taddr + col, r0);
+          tmem_ld_32x32b_x32(taddr + col + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            w[j] = pack_bf16x2(r0[2 * j], r0[2 * j + 1]);
+            w[16 + j] = pack_bf16x2(r1[2 * j], r1[2 * j + 1]);
+          }
+        };
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {  // two 64-feature groups of the tile's 128 features
+          const int f0 = tn * 128 + g * 64;
+          const bool ok = f0 < p.swiglu_ff;
+          uint32_t wg[32], wu[32], wh[32];
+          load64_packed(g * 64, wg);
+          emit64(wg, &tmap_c, f0, ok);
+          load64_packed(128 + g * 64, wu);
+          emit64(wu, &tmap_c, p.swiglu_ff + f0, ok);
+          // h = silu(gate)·up from the bf16-ROUNDED gate/up — bit-compatible with the stand-alone kernel that reads them back
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const __nv_bfloat162 gb = *reinterpret_cast<const __nv_bfloat162*>(&wg[j]), ub = *reinterpret_cast<const __nv_bfloat162*>(&wu[j]);
+            const float2 gf = __bfloat1622float2(gb), uf = __bfloat1622float2(ub);
+            const float h0 = gf.x / (1.f + __expf(-gf.x)) * uf.x, h1 = gf.y / (1.f + __expf(-gf.y)) * uf.y;
+            wh[j] = pack_bf16x2(__float_as_uint(h0), __float_as_uint(h1));
+          }
+          emit64(wh, &tmap_h, f0, ok);
+        }
       } else {
 #pragma unroll 1
         for (int g = 0; g < BN / 64; ++g) {  // 64 bf16 columns = one 128 B row
@@ -352,8 +404,8 @@ int choose_split_k(int tiles, int units, int num_kb) {
 int g_split_k_mode = -1;  // -1 auto, 0/1 off, n>1 forced
 
 template <int A_MN, int B_MN, int PAIR>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int max_ctas,
-           cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& th, const GemmParams& p,
+           int max_ctas, cudaStream_t stream) {
   using G = Geo<PAIR>;
   static bool configured = false;
   if (!configured) {
@@ -369,10 +421,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   }
   int grid = g_num_sms;
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  const int tiles = ((p.M + G::kTileM - 1) / G::kTileM) * ((p.N + BN - 1) / BN) * p.split_k;
+  const int tiles_n = (PAIR && p.swiglu_ff > 0) ? (p.swiglu_ff + 127) / 128 : (p.N + BN - 1) / BN;
+  const int tiles = ((p.M + G::kTileM - 1) / G::kTileM) * tiles_n * p.split_k;
   if (!PAIR) {
     if (tiles < grid) grid = tiles;
-    gemm_bf16_kernel<A_MN, B_MN, 0><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, p);
+    gemm_bf16_kernel<A_MN, B_MN, 0><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, th, p);
   } else {
     grid &= ~1;
     if (2 * tiles < grid) grid = 2 * tiles;
@@ -389,7 +442,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1>, ta, tb, tc, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1>, ta, tb, tc, th, p);
     if (e != cudaSuccess) return (int)e;
   }
   cudaError_t e = cudaGetLastError();
@@ -425,7 +478,7 @@ PB_EXPORT int pb_gemm_set_split_k(int mode) {
 // lda/ldb: row stride (elements) of the matrix AS STORED (see header comment).
 static int gemm_impl(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc, int a_mn_major,
                      int b_mn_major, int c_fp32, int accumulate, int max_ctas, const float* rope_cos, const float* rope_sin,
-                     int rope_S, int rope_cols, int rope_D, cudaStream_t stream) {
+                     int rope_S, int rope_cols, int rope_D, cudaStream_t stream, void* H = nullptr, int ldh = 0, int swiglu_ff = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (ldc % (c_fp32 ? 4 : 8))) return -1;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) return -2;
@@ -436,7 +489,7 @@ static int gemm_impl(const void* A, const void* B, void* C, int M, int N, int K,
   else
     rc = pbhost::cached_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BK);
   if (rc) return rc;
-  const int pair = pair_mode() && M > BM;  // a pair needs two M blocks to be worth it
+  const int pair = (pair_mode() && M > BM) || swiglu_ff > 0;  // a pair needs two M blocks to be worth it; SwiGLU mode requires it
   if (!b_mn_major)
     rc = pbhost::cached_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, pair ? BN / 2 : BN);
   else
@@ -446,7 +499,11 @@ static int gemm_impl(const void* A, const void* B, void* C, int M, int N, int K,
   rc = c_fp32 ? pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32, 32, 4)
               : pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 64, 32, 2);
   if (rc) return rc;
-  GemmParams p{M, N, K, ldc, a_mn_major, b_mn_major, c_fp32, accumulate, 1, C, rope_cos, rope_sin, rope_S, rope_cols, rope_D};
+  CUtensorMap th = tc;  // second output (SwiGLU mode): h [M, FF]
+  if (swiglu_ff > 0) {
+    if ((rc = pbhost::cached_tmap(&th, H, (uint64_t)M, (uint64_t)swiglu_ff, (uint64_t)ldh, 64, 32, 2))) return rc;
+  }
+  GemmParams p{M, N, K, ldc, a_mn_major, b_mn_major, c_fp32, accumulate, 1, C, rope_cos, rope_sin, rope_S, rope_cols, rope_D, swiglu_ff};
   if (c_fp32 && accumulate && g_split_k_mode != 0 && g_split_k_mode != 1) {
     if (g_num_sms == 0) {
       int dev = 0;
@@ -461,15 +518,15 @@ static int gemm_impl(const void* A, const void* B, void* C, int M, int N, int K,
     p.split_k = g_split_k_mode > 1 ? (num_kb / g_split_k_mode >= 1 ? g_split_k_mode : 1) : choose_split_k(tiles, units > 0 ? units : 1, num_kb);
   }
   if (pair) {
-    if (!a_mn_major && !b_mn_major) return launch<0, 0, 1>(ta, tb, tc, p, max_ctas, stream);
-    if (!a_mn_major && b_mn_major) return launch<0, 1, 1>(ta, tb, tc, p, max_ctas, stream);
-    if (a_mn_major && !b_mn_major) return launch<1, 0, 1>(ta, tb, tc, p, max_ctas, stream);
-    return launch<1, 1, 1>(ta, tb, tc, p, max_ctas, stream);
+    if (!a_mn_major && !b_mn_major) return launch<0, 0, 1>(ta, tb, tc, th, p, max_ctas, stream);
+    if (!a_mn_major && b_mn_major) return launch<0, 1, 1>(ta, tb, tc, th, p, max_ctas, stream);
+    if (a_mn_major && !b_mn_major) return launch<1, 0, 1>(ta, tb, tc, th, p, max_ctas, stream);
+    return launch<1, 1, 1>(ta, tb, tc, th, p, max_ctas, stream);
   }
-  if (!a_mn_major && !b_mn_major) return launch<0, 0, 0>(ta, tb, tc, p, max_ctas, stream);
-  if (!a_mn_major && b_mn_major) return launch<0, 1, 0>(ta, tb, tc, p, max_ctas, stream);
-  if (a_mn_major && !b_mn_major) return launch<1, 0, 0>(ta, tb, tc, p, max_ctas, stream);
-  return launch<1, 1, 0>(ta, tb, tc, p, max_ctas, stream);
+  if (!a_mn_major && !b_mn_major) return launch<0, 0, 0>(ta, tb, tc, th, p, max_ctas, stream);
+  if (!a_mn_major && b_mn_major) return launch<0, 1, 0>(ta, tb, tc, th, p, max_ctas, stream);
+  if (a_mn_major && !b_mn_major) return launch<1, 0, 0>(ta, tb, tc, th, p, max_ctas, stream);
+  return launch<1, 1, 0>(ta, tb, tc, th, p, max_ctas, stream);
 }
 
 PB_EXPORT int pb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
@@ -487,4 +544,12 @@ PB_EXPORT int pb_gemm_bf16_rope(const void* A, const void* B, void* C, int M, in
   if (rope_cos == nullptr || rope_sin == nullptr || rope_S <= 0 || M % rope_S != 0) return -3;
   if ((rope_D != 64 && rope_D != 128) || rope_cols % rope_D != 0 || rope_cols > N) return -4;
   return gemm_impl(A, B, C, M, N, K, lda, ldb, ldc, 0, 0, 0, 0, max_ctas, rope_cos, rope_sin, rope_S, rope_cols, rope_D, stream);
+}
+
+// gate_up = x·W13ᵀ (kept for the backward) AND h = silu(gate)·up in ONE kernel: see GemmParams::swiglu_ff.
+//   x [M, K], W13 [2·FF, K] = [gate rows | up rows], gate_up [M, 2·FF], h [M, FF]; all bf16, unit inner stride.
+PB_EXPORT int pb_gemm_bf16_swiglu(const void* A, const void* W13, void* gate_up, void* H, int M, int FF, int K, int lda, int ldb,
+                                  int ld_gu, int ld_h, cudaStream_t stream) {
+  if (FF % 64 != 0 || (ld_h % 8) || (reinterpret_cast<uintptr_t>(H) & 15)) return -5;
+  return gemm_impl(A, W13, gate_up, M, 2 * FF, K, lda, ldb, ld_gu, 0, 0, 0, 0, 0, nullptr, nullptr, 1, 0, 64, stream, H, ld_h, FF);
 }

@@ -122,7 +122,7 @@ class FeedForward(nn.Module):
         self.w2 = nn.Parameter(torch.empty(args.dim, hidden))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return ops.linear(ops.swiglu(ops.linear(x, self.w13)), self.w2)
+        return ops.linear(ops.linear_swiglu(x, self.w13), self.w2)  # SwiGLU rides in the gate/up GEMM epilogue on CUDA
 
 
 class TransformerBlock(nn.Module):

@@ -10,6 +10,7 @@ from .functional import (  # noqa: F401
     launch_count,
     linear,
     linear_qkv_rope,
+    linear_swiglu,
     rope_fusable,
     reset_launch_count,
     rmsnorm,

@@ -327,6 +327,60 @@ def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
     return reference.swiglu(gate_up)
 
 
+class _LinearSwiGLUFn(torch.autograd.Function):
+    """h = silu(x W1ᵀ) · (x W3ᵀ) with W13 = [W1; W3]: ONE GEMM whose epilogue emits both the bf16 gate/up activations (kept for
+    the backward) and h — the separate SwiGLU pass over the 370 MB gate_up tensor disappears from the forward. CTA-pair GEMM:
+    the leader stages 128 gate rows of W13, its partner the matching 128 up rows."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, w13: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M, K = x2.shape
+        FF = w13.shape[0] // 2
+        gate_up = torch.empty((M, 2 * FF), dtype=x.dtype, device=x.device)
+        h = torch.empty((*x.shape[:-1], FF), dtype=x.dtype, device=x.device)
+        rc = lib.pb_gemm_bf16_swiglu(x2.data_ptr(), w13.data_ptr(), gate_up.data_ptr(), h.data_ptr(), M, FF, K, x2.stride(0), w13.stride(0),
+                                     2 * FF, FF, _stream())  # fmt: skip
+        _lib.check(rc, "pb_gemm_bf16_swiglu")
+        _count()
+        ctx.save_for_backward(x2, w13, gate_up)
+        ctx.x_shape = x.shape
+        return h
+
+    @staticmethod
+    def backward(ctx, dh: torch.Tensor):
+        lib = _lib.load()
+        x2, w13, gate_up = ctx.saved_tensors
+        M, FF = gate_up.shape[0], gate_up.shape[1] // 2
+        d2 = dh.reshape(M, FF)
+        d2 = d2 if d2.is_contiguous() else d2.contiguous()
+        dgu = torch.empty_like(gate_up)
+        rc = lib.pb_swiglu_bwd(_ptr(gate_up), _ptr(d2), _ptr(dgu), M, FF, _stream())
+        _lib.check(rc, "pb_swiglu_bwd")
+        _count()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(ctx.x_shape, dtype=dh.dtype, device=dh.device)
+            gemm(dgu, w13, b_mn_major=True, out=dx.view(-1, ctx.x_shape[-1]))
+        if ctx.needs_input_grad[1]:
+            main_grad = getattr(w13, "main_grad", None)
+            if main_grad is not None:
+                gemm(dgu, x2, a_mn_major=True, b_mn_major=True, out=main_grad, accumulate=True)
+            else:
+                dw = gemm(dgu, x2, a_mn_major=True, b_mn_major=True)
+        return dx, dw
+
+
+def linear_swiglu(x: torch.Tensor, w13: torch.Tensor) -> torch.Tensor:
+    """``swiglu(linear(x, w13))``; fused into one GEMM on CUDA when the shape allows it (M > 128, FF % 64 == 0)."""
+    if x.is_cuda and x.dtype == torch.bfloat16 and (w13.shape[0] // 2) % 64 == 0 and x.numel() // x.shape[-1] > 128:
+        return _LinearSwiGLUFn.apply(x, w13)
+    return swiglu(linear(x, w13))
+
+
 # --------------------------------------------------------------------------- cross entropy
 
 

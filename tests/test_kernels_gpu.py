@@ -411,3 +411,26 @@ def test_qkv_gemm_rope_epilogue_and_attention_unrotate(H, Hkv, D):
     assert _rel_err(out, ref) < 2e-2
     assert _rel_err(x.grad, xr.grad) < 4e-2, _rel_err(x.grad, xr.grad)
     assert _rel_err(w.grad, wr.grad) < 4e-2, _rel_err(w.grad, wr.grad)
+
+
+@pytest.mark.parametrize("M,FF,K", [(512, 1024, 256), (640, 5632, 2048), (384, 192, 136)])
+def test_gemm_swiglu_epilogue(M, FF, K):
+    """gate/up projection with SwiGLU in the epilogue (CTA pair: leader stages gate rows, partner the matching up rows) vs the
+    unfused linear → swiglu path, forward and gradients."""
+    from prime_b200 import ops
+
+    torch.manual_seed(M + FF)
+    x = (torch.randn(M, K, device=_dev()) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(2 * FF, K, device=_dev()) * 0.05).to(torch.bfloat16).requires_grad_(True)
+    h = ops.linear_swiglu(x, w)
+    dh = torch.randn_like(h)
+    h.backward(dh)
+    torch.cuda.synchronize()
+    xr = x.detach().clone().requires_grad_(True)
+    wr = w.detach().clone().requires_grad_(True)
+    hr = ops.swiglu(ops.linear(xr, wr))
+    hr.backward(dh)
+    assert _rel_err(h, hr) < 1e-3, _rel_err(h, hr)  # same bf16-rounded gate/up → near bit-identical
+    assert _rel_err(x.grad, xr.grad) < 1e-3 and _rel_err(w.grad, wr.grad) < 1e-3
+    ref = torch.nn.functional.silu(x.detach().float() @ w.detach().float()[:FF].t()) * (x.detach().float() @ w.detach().float()[FF:].t())
+    assert _rel_err(h, ref) < 2e-2
