@@ -72,10 +72,6 @@ class ElasticConfig:
     poll_s: float = 0.02
 
 
-class EvictedError(RuntimeError):
-    """Raised inside ``rendezvous`` bookkeeping when a member discovers it was dropped (handled internally)."""
-
-
 class StoreView:
     """Read-only view of the rendezvous state (also what ``elastic status`` prints)."""
 
