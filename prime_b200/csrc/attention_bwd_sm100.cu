@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       // issued opportunistically from the P-wait polling loop: a blocking wait for its Q/dO load in front of dV/dK of tile `it`
       // stalls the whole pipeline (measured with a 3-slot ring: slower than one-ahead; the trace shows the MMA thread parked there).
       auto sd_ready = [&](int it) {  // can S/dP of tile `it` be issued without blocking?
-        return mbar_try_wait(&q_full[it % C::kQStages], (it / C::kQStages) & 1) && mbar_try_wait(&s_empty[it & 1], ((it >> 1) & 1) ^ 1);
+        return mbar_test_wait(&q_full[it % C::kQStages], (it / C::kQStages) & 1) && mbar_test_wait(&s_empty[it & 1], ((it >> 1) & 1) ^ 1);
       };
       issue_sd(0);
       int sd_next = 1;  // next tile whose S/dP has not been issued
@@ -329,6 +329,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int qpos0 = (it0 + it % tiles_per_head) * 64;
       const float* lse_row = p.lse2 + ((int64_t)(b * p.H + h)) * p.S + qpos0;
       const float* del_row = p.delta + ((int64_t)(b * p.H + h)) * p.S + qpos0;
+      if (it + 2 < n_it && lane < 4) {
+        // this group's NEXT tile: pull its 64 lse and 64 delta values (4 cache lines) into L1 now, so the 32 warp-uniform
+        // 128-bit loads in the math phase hit L1 instead of exposing an L2 round trip each
+        const int nx = it + 2;
+        const int hn = hk * group + nx / tiles_per_head;
+        const int64_t off = ((int64_t)(b * p.H + hn)) * p.S + (it0 + nx % tiles_per_head) * 64 + (lane & 1) * 32;
+        const float* a = (lane & 2) ? p.delta + off : p.lse2 + off;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+      }
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 1, it);  // start waiting for S/dP
       mbar_wait(&s_full[st], ph);
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 2, it);  // S/dP ready
@@ -372,6 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       };
       if (need_mask) tile_math(std::true_type{});
       else tile_math(std::false_type{});
+      if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 6, it);  // math done (registers hold the packed tile)
       // the single Pᵀ/dSᵀ buffer was last read by dV/dK of the previous tile (the other group's)
       if (it >= 1) mbar_wait(&acc_done[(it - 1) & 1], ((it - 1) >> 1) & 1);
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 4, it);  // P/dS buffer free
@@ -559,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         umma_commit(&s_full[st]);
       };
       auto sd_ready = [&](int t) {
-        return mbar_try_wait(&kv_full[t % C::kKVStages], (t / C::kKVStages) & 1) && mbar_try_wait(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
+        return mbar_test_wait(&kv_full[t % C::kKVStages], (t / C::kKVStages) & 1) && mbar_test_wait(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
       };
       issue_sd(0);  // S/dP: one tile ahead mandatory, two ahead opportunistic (see the dK/dV kernel)
       int sd_next = 1;

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto s_ready = [&](int gg) {
         const int st = gg & 1;
         const uint32_t ph = (gg >> 1) & 1;
-        return mbar_try_wait(&k_full[st], ph) && mbar_try_wait(&s_empty[st], ph ^ 1);
+        return mbar_test_wait(&k_full[st], ph) && mbar_test_wait(&s_empty[st], ph ^ 1);
       };
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         int qb, bh;

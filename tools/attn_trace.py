@@ -18,8 +18,8 @@ from prime_b200.ops import attention_native as A  # noqa: E402
 
 ROLES = ["loader", "mma", "math0", "math1"]
 CODES = {"loader": {1: "issue_load"}, "mma": {1: "q_landed", 2: "issue_S_dP", 3: "issue_dV_dK"},
-         "math0": {1: "wait_S", 2: "S_ready", 3: "tmem_loaded", 4: "p_stage_free", 5: "done"},
-         "math1": {1: "wait_S", 2: "S_ready", 3: "tmem_loaded", 4: "p_stage_free", 5: "done"}}  # fmt: skip
+         "math0": {1: "wait_S", 2: "S_ready", 3: "tmem_loaded", 4: "p_stage_free", 5: "done", 6: "math_done"},
+         "math1": {1: "wait_S", 2: "S_ready", 3: "tmem_loaded", 4: "p_stage_free", 5: "done", 6: "math_done"}}  # fmt: skip
 
 
 def main():
@@ -61,7 +61,8 @@ def main():
         rows.append({"tile": tile, "S_issue": d.get("mma.issue_S_dP"), "S_ready": d.get(f"{g}.S_ready"),
                      "wait_for_S": (d.get(f"{g}.S_ready", 0) - d.get(f"{g}.wait_S", 0)),
                      "tmem_load": (d.get(f"{g}.tmem_loaded", 0) - d.get(f"{g}.S_ready", 0)),
-                     "wait_p_stage": (d.get(f"{g}.p_stage_free", 0) - d.get(f"{g}.tmem_loaded", 0)),
+                     "math": (d.get(f"{g}.math_done", 0) - d.get(f"{g}.tmem_loaded", 0)),
+                     "wait_p_buffer": (d.get(f"{g}.p_stage_free", 0) - d.get(f"{g}.math_done", 0)),
                      "math_store": (d.get(f"{g}.done", 0) - d.get(f"{g}.p_stage_free", 0)),
                      "S_issue_to_ready": (d.get(f"{g}.S_ready", 0) - d.get("mma.issue_S_dP", 0)),
                      "done_to_dVdK_issue": (d.get("mma.issue_dV_dK", 0) - d.get(f"{g}.done", 0)),
