@@ -104,7 +104,11 @@ __device__ __forceinline__ void rope_regs(uint32_t (&r)[32], const float* __rest
   }
 }
 
-template <int A_MN, int B_MN, int PAIR>
+// EPI: 0 = plain, 1 = RoPE on the leading output columns, 2 = SwiGLU (PAIR only). Separate instantiations on purpose: the fused
+// epilogues need 170-230 registers per thread, and a plain GEMM compiled with that footprint fills the SM's register file, so
+// the gradient-reduction / optimizer kernels of the comm stream can no longer co-reside with it during the backward pass
+// (measured: the 2-GPU step gained only a third of what the 1-GPU step gained when the epilogues were runtime branches).
+template <int A_MN, int B_MN, int PAIR, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_h, const GemmParams p) {
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool swiglu = PAIR && p.swiglu_ff > 0;
+  constexpr bool swiglu = PAIR && EPI == 2;
   const int tiles_m = (p.M + kTileM - 1) / kTileM, tiles_n = swiglu ? (p.swiglu_ff + 127) / 128 : (p.N + BN - 1) / BN;
   const int num_kb = (p.K + BK - 1) / BK;
   // split-K: work item w = tile * split_k + slice; slice s covers k-blocks [s*kb_per, min(num_kb, (s+1)*kb_per))
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (lane == 0) bulk_commit();
           buf ^= 1;
         }
-      } else if (swiglu) {
+      } else if constexpr (swiglu) {
         // pack 64 fp32 accumulator columns to bf16, stage them in the swizzled slab and TMA-store them at (col0, row0)
         auto emit64 = [&](const uint32_t (&w)[32], const CUtensorMap* map, int col0, bool in_range) {
           if (lane == 0) bulk_wait_read<1>();
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
           tmem_ld_wait();
-          if (p.rope_cos != nullptr && tn * BN + g * 64 < p.rope_cols) {  // Q/K head columns: rotate in registers
+          if (EPI == 1 && tn * BN + g * 64 < p.rope_cols) {  // Q/K head columns: rotate in registers
             const int pos = (row0 + lane) % p.rope_S;
             const int d0 = (tn * BN + g * 64) % p.rope_D;
             rope_regs(r0, p.rope_cos, p.rope_sin, pos, d0, p.rope_D >> 1);
@@ -403,13 +407,13 @@ int choose_split_k(int tiles, int units, int num_kb) {
 
 int g_split_k_mode = -1;  // -1 auto, 0/1 off, n>1 forced
 
-template <int A_MN, int B_MN, int PAIR>
+template <int A_MN, int B_MN, int PAIR, int EPI = 0>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& th, const GemmParams& p,
            int max_ctas, cudaStream_t stream) {
   using G = Geo<PAIR>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, PAIR, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)G::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     configured = true;
@@ -421,11 +425,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   }
   int grid = g_num_sms;
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  const int tiles_n = (PAIR && p.swiglu_ff > 0) ? (p.swiglu_ff + 127) / 128 : (p.N + BN - 1) / BN;
+  const int tiles_n = (PAIR && EPI == 2) ? (p.swiglu_ff + 127) / 128 : (p.N + BN - 1) / BN;
   const int tiles = ((p.M + G::kTileM - 1) / G::kTileM) * tiles_n * p.split_k;
   if (!PAIR) {
     if (tiles < grid) grid = tiles;
-    gemm_bf16_kernel<A_MN, B_MN, 0><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, th, p);
+    gemm_bf16_kernel<A_MN, B_MN, 0, EPI><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, th, p);
   } else {
     grid &= ~1;
     if (2 * tiles < grid) grid = 2 * tiles;
@@ -442,7 +446,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1>, ta, tb, tc, th, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1, EPI>, ta, tb, tc, th, p);
     if (e != cudaSuccess) return (int)e;
   }
   cudaError_t e = cudaGetLastError();
@@ -517,6 +521,8 @@ static int gemm_impl(const void* A, const void* B, void* C, int M, int N, int K,
     const int num_kb = (K + BK - 1) / BK;
     p.split_k = g_split_k_mode > 1 ? (num_kb / g_split_k_mode >= 1 ? g_split_k_mode : 1) : choose_split_k(tiles, units > 0 ? units : 1, num_kb);
   }
+  if (swiglu_ff > 0) return launch<0, 0, 1, 2>(ta, tb, tc, th, p, max_ctas, stream);
+  if (rope_cos != nullptr) return pair ? launch<0, 0, 1, 1>(ta, tb, tc, th, p, max_ctas, stream) : launch<0, 0, 0, 1>(ta, tb, tc, th, p, max_ctas, stream);
   if (pair) {
     if (!a_mn_major && !b_mn_major) return launch<0, 0, 1>(ta, tb, tc, th, p, max_ctas, stream);
     if (!a_mn_major && b_mn_major) return launch<0, 1, 1>(ta, tb, tc, th, p, max_ctas, stream);

@@ -150,9 +150,13 @@ def linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     return reference.linear(x, weight)
 
 
+# A/B switch for measurements: PB_NO_EPILOGUE_FUSION=1 runs RoPE and SwiGLU as stand-alone kernels again
+_NO_EPILOGUE_FUSION = bool(int(__import__("os").environ.get("PB_NO_EPILOGUE_FUSION", "0")))
+
+
 def rope_fusable(x: torch.Tensor, n_heads: int, n_kv_heads: int, head_dim: int) -> bool:
     """Can the QKV projection rotate in its epilogue AND the native attention consume/undo it? (CUDA, [B,S,·] input, S%128==0)"""
-    if not (x.is_cuda and x.dim() == 3 and x.dtype == torch.bfloat16):
+    if _NO_EPILOGUE_FUSION or not (x.is_cuda and x.dim() == 3 and x.dtype == torch.bfloat16):
         return False
     from . import attention_native as native
 
@@ -376,7 +380,7 @@ class _LinearSwiGLUFn(torch.autograd.Function):
 
 def linear_swiglu(x: torch.Tensor, w13: torch.Tensor) -> torch.Tensor:
     """``swiglu(linear(x, w13))``; fused into one GEMM on CUDA when the shape allows it (M > 128, FF % 64 == 0)."""
-    if x.is_cuda and x.dtype == torch.bfloat16 and (w13.shape[0] // 2) % 64 == 0 and x.numel() // x.shape[-1] > 128:
+    if not _NO_EPILOGUE_FUSION and x.is_cuda and x.dtype == torch.bfloat16 and (w13.shape[0] // 2) % 64 == 0 and x.numel() // x.shape[-1] > 128:
         return _LinearSwiGLUFn.apply(x, w13)
     return swiglu(linear(x, w13))
 
