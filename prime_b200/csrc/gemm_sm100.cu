@@ -85,6 +85,18 @@ struct GemmParams {
   int swiglu_ff;
 };
 
+// Fused collective GEMMs over the NVLink symmetric heap (IO template parameter of the kernel):
+//   IO = 1  all-gather ⊕ GEMM : row block r of A lives on rank r; the TMA producer loads every tile straight out of its owner's
+//           memory (peer tensor maps), own rows first, so the gather is hidden tile by tile behind the MMAs — no staging buffer.
+//   IO = 2  GEMM ⊕ reduce-scatter : every rank computes a full partial C; the epilogue TMA-reduce-adds each fp32 tile into the
+//           buffer of the rank that owns those rows (cp.reduce.async.bulk.tensor on a peer-mapped address).
+struct PeerMaps {
+  CUtensorMap m[8];
+  int n;              // ranks
+  int rows_per_rank;  // multiple of the tile height
+  int rot;            // tile-row rotation = my_rank * tiles_per_rank (start on local rows)
+};
+
 // rotate the 16 interleaved pairs held in 32 consecutive fp32 accumulator registers (head-dim offset d0, sequence position pos)
 __device__ __forceinline__ void rope_regs(uint32_t (&r)[32], const float* __restrict__ cosb, const float* __restrict__ sinb, int pos, int d0,
                                           int half_d) {
@@ -108,10 +120,11 @@ __device__ __forceinline__ void rope_regs(uint32_t (&r)[32], const float* __rest
 // epilogues need 170-230 registers per thread, and a plain GEMM compiled with that footprint fills the SM's register file, so
 // the gradient-reduction / optimizer kernels of the comm stream can no longer co-reside with it during the backward pass
 // (measured: the 2-GPU step gained only a third of what the 1-GPU step gained when the epilogues were runtime branches).
-template <int A_MN, int B_MN, int PAIR, int EPI>
+template <int A_MN, int B_MN, int PAIR, int EPI, int IO>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_h, const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_h, const GemmParams p,
+                     const __grid_constant__ PeerMaps pm) {
   using G = Geo<PAIR>;
   constexpr int kStages = G::kStages;
   constexpr uint32_t kStageBytes = G::kStageBytes;
@@ -143,6 +156,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_c);
     prefetch_tmap(&tmap_h);
+    if (IO != 0)
+      for (int i = 0; i < pm.n; ++i) prefetch_tmap(&pm.m[i]);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -173,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         int tm, tn;
         tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn);
+        if (IO != 0) tm = (tm + pm.rot) % tiles_m;
         const int kb0 = (tile % split_k) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
         if (kb0 >= kb1) continue;  // empty K slice (split does not divide K): every role skips it identically
         const int m0 = tm * kTileM + (int)crank * BM;      // this CTA's A rows
@@ -188,7 +204,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (PAIR) tma_load_2d_pair(m, &full_bar[stage], dst, c0, c1);
             else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
           };
-          if (A_MN == 0) {
+          if (IO == 1) {  // A row block m0 lives on rank m0 / rows_per_rank: load it from there (NVLink for remote owners)
+            const int owner = m0 / pm.rows_per_rank;
+            load(&pm.m[owner], sa, kb * BK, m0 - owner * pm.rows_per_rank);
+          } else if (A_MN == 0) {
             load(&tmap_a, sa, kb * BK, m0);  // box {64 k, 128 m}
           } else {
 #pragma unroll
@@ -260,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
       int tm, tn;
       tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn);
+      if (IO != 0) tm = (tm + pm.rot) % tiles_m;
       if ((tile % split_k) * kb_per >= num_kb) continue;  // empty K slice
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -281,7 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1)
           __syncwarp();
           const int col0 = tn * BN + c * 32;
           if (lane == 0 && row0 < p.M && col0 < p.N) {
-            if (p.accumulate) tma_reduce_add_2d(&tmap_c, my_stage + buf * 4096, col0, row0);
+            if (IO == 2) {  // reduce-scatter: add into the owner rank's buffer (peer-mapped tensor map)
+              const int owner = row0 / pm.rows_per_rank;
+              tma_reduce_add_2d(&pm.m[owner], my_stage + buf * 4096, col0, row0 - owner * pm.rows_per_rank);
+            } else if (p.accumulate) tma_reduce_add_2d(&tmap_c, my_stage + buf * 4096, col0, row0);
             else tma_store_2d(&tmap_c, my_stage + buf * 4096, col0, row0);
           }
           if (lane == 0) bulk_commit();
@@ -377,7 +400,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       if (++acc == kAccStages) acc = 0, acc_phase ^= 1;
     }
-    if (lane == 0) bulk_wait_read<0>();  // staging smem must outlive the last store's reads
+    if (lane == 0) {
+      if (IO == 2) bulk_wait_all();  // peer reductions must have been performed before this kernel retires (a barrier follows)
+      else bulk_wait_read<0>();      // staging smem must outlive the last store's reads
+    }
   }
 
   tc_fence_before();
@@ -407,13 +433,15 @@ int choose_split_k(int tiles, int units, int num_kb) {
 
 int g_split_k_mode = -1;  // -1 auto, 0/1 off, n>1 forced
 
-template <int A_MN, int B_MN, int PAIR, int EPI = 0>
+template <int A_MN, int B_MN, int PAIR, int EPI = 0, int IO = 0>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& th, const GemmParams& p,
-           int max_ctas, cudaStream_t stream) {
+           int max_ctas, cudaStream_t stream, const PeerMaps* pmp = nullptr) {
+  static const PeerMaps kNoPeers = {};
+  const PeerMaps& pm = pmp ? *pmp : kNoPeers;
   using G = Geo<PAIR>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, PAIR, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, PAIR, EPI, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)G::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     configured = true;
@@ -429,7 +457,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   const int tiles = ((p.M + G::kTileM - 1) / G::kTileM) * tiles_n * p.split_k;
   if (!PAIR) {
     if (tiles < grid) grid = tiles;
-    gemm_bf16_kernel<A_MN, B_MN, 0, EPI><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, th, p);
+    gemm_bf16_kernel<A_MN, B_MN, 0, EPI, IO><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, th, p, pm);
   } else {
     grid &= ~1;
     if (2 * tiles < grid) grid = 2 * tiles;
@@ -446,7 +474,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1, EPI>, ta, tb, tc, th, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1, EPI, IO>, ta, tb, tc, th, p, pm);
     if (e != cudaSuccess) return (int)e;
   }
   cudaError_t e = cudaGetLastError();
@@ -558,4 +586,47 @@ PB_EXPORT int pb_gemm_bf16_swiglu(const void* A, const void* W13, void* gate_up,
                                   int ld_gu, int ld_h, cudaStream_t stream) {
   if (FF % 64 != 0 || (ld_h % 8) || (reinterpret_cast<uintptr_t>(H) & 15)) return -5;
   return gemm_impl(A, W13, gate_up, M, 2 * FF, K, lda, ldb, ld_gu, 0, 0, 0, 0, 0, nullptr, nullptr, 1, 0, 64, stream, H, ld_h, FF);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// all-gather ⊕ GEMM:  C[n·M_local, N] = [A_0; A_1; …; A_{n-1}] · Bᵀ, A_r = rank r's [M_local, K] block in the symmetric heap.
+// a_peers[r] is the address of rank r's block AS MAPPED IN THIS PROCESS. The caller brackets the call with heap barriers (every
+// rank's block written before, nobody overwrites it until all ranks are done). K-major operands, bf16 output, CTA-pair tiles.
+PB_EXPORT int pb_gemm_allgather(const void* const* a_peers, int n, int rank, const void* B, void* C, int M_local, int N, int K, int lda,
+                                int ldb, int ldc, cudaStream_t stream) {
+  if (n < 1 || n > 8 || rank < 0 || rank >= n || M_local % (2 * BM) != 0) return -6;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8)) return -1;
+  PeerMaps pm = {};
+  pm.n = n;
+  pm.rows_per_rank = M_local;
+  pm.rot = rank * (M_local / (2 * BM));
+  int rc;
+  for (int r = 0; r < n; ++r)
+    if ((rc = pbhost::cached_tmap(&pm.m[r], a_peers[r], (uint64_t)M_local, (uint64_t)K, (uint64_t)lda, BK, BM))) return rc;
+  const int M = n * M_local;
+  CUtensorMap tb, tc;
+  if ((rc = pbhost::cached_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BN / 2))) return rc;
+  if ((rc = pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 64, 32, 2))) return rc;
+  GemmParams p{M, N, K, ldc, 0, 0, 0, 0, 1, C, nullptr, nullptr, 1, 0, 64, 0};
+  return launch<0, 0, 1, 0, 1>(pm.m[rank], tb, tc, tc, p, 0, stream, &pm);
+}
+
+// GEMM ⊕ reduce-scatter:  every rank holds a K-shard (A [M, K_local], B [N, K_local]); rank r ends up with rows
+// [r·M/n, (r+1)·M/n) of Σ_ranks A·Bᵀ in its fp32 buffer c_peers[r] ([M/n, N], zeroed by the caller before the opening barrier).
+PB_EXPORT int pb_gemm_reduce_scatter(const void* A, const void* B, float* const* c_peers, int n, int rank, int M, int N, int K, int lda,
+                                     int ldb, int ldc, cudaStream_t stream) {
+  if (n < 1 || n > 8 || rank < 0 || rank >= n || M % n != 0 || (M / n) % (2 * BM) != 0) return -6;
+  if ((lda % 8) || (ldb % 8) || (ldc % 4)) return -1;
+  PeerMaps pm = {};
+  pm.n = n;
+  pm.rows_per_rank = M / n;
+  pm.rot = rank * (pm.rows_per_rank / (2 * BM));
+  int rc;
+  for (int r = 0; r < n; ++r)
+    if ((rc = pbhost::cached_tmap(&pm.m[r], c_peers[r], (uint64_t)pm.rows_per_rank, (uint64_t)N, (uint64_t)ldc, 32, 32, 4))) return rc;
+  CUtensorMap ta, tb;
+  if ((rc = pbhost::cached_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, BM))) return rc;
+  if ((rc = pbhost::cached_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BN / 2))) return rc;
+  GemmParams p{M, N, K, ldc, 0, 0, 1, 1, 1, c_peers[rank], nullptr, nullptr, 1, 0, 64, 0};
+  return launch<0, 0, 1, 0, 2>(ta, tb, pm.m[rank], pm.m[rank], p, 0, stream, &pm);
 }

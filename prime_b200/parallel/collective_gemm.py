@@ -1,0 +1,73 @@
+"""Fused collective ⊕ GEMM kernels over the NVLink symmetric heap — the tensor-parallel building blocks.
+
+``all_gather_gemm``      C = [A₀; A₁; …] · Bᵀ where block r of A lives on rank r. The TMA producer of the tcgen05 GEMM loads every
+                         A tile straight out of its owner's memory (own rows first), so the gather is hidden tile by tile behind
+                         the MMAs and no gathered copy of A is ever materialised (column-parallel linear on sequence-sharded input).
+``gemm_reduce_scatter``  every rank multiplies its K-shard; the GEMM epilogue TMA-reduce-adds each fp32 tile into the buffer of the
+                         rank that owns those rows (row-parallel linear → sequence-sharded output).
+
+Both are ONE kernel each (``csrc/gemm_sm100.cu``, IO = 1 / 2); the only extra launches are two flag barriers that fence the
+symmetric buffers. The NCCL formulation of the same ops (``all_gather_into_tensor`` + GEMM, GEMM + ``reduce_scatter_tensor``) is
+the baseline they are benchmarked against in ``tools/collective_gemm_bench.py``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence
+
+import torch
+
+from ..ops import _lib
+from ..ops.functional import _count, _stream
+from .symm import SymmetricHeap
+
+
+class CollectiveGemm:
+    def __init__(self, heap: SymmetricHeap, ranks: Sequence[int]):
+        self.heap, self.ranks = heap, list(ranks)
+        self.n = len(self.ranks)
+        self.idx = self.ranks.index(heap.rank)
+        self.slot = heap.alloc_flags(self.n)
+        self.epoch = 0
+        self.lib = heap.lib
+
+    def _barrier(self) -> None:
+        self.epoch += 1
+        self.heap.barrier(self.ranks, self.slot, self.epoch, _stream())
+        _count()
+
+    def _peer_array(self, t: torch.Tensor):
+        arr = (ctypes.c_void_p * self.n)(*[self.heap.peer_ptr(r, t) for r in self.ranks])
+        return arr
+
+    def all_gather_gemm(self, a_sym: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """``a_sym``: this rank's [M_local, K] bf16 block, allocated with ``heap.alloc`` at the SAME offset on every rank
+        (M_local % 256 == 0); ``b``: [N, K] bf16 (local). Returns C [n·M_local, N] bf16."""
+        M_local, K = a_sym.shape
+        N = b.shape[0]
+        assert a_sym.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and b.shape[1] == K and M_local % 256 == 0
+        if out is None:
+            out = torch.empty((self.n * M_local, N), dtype=torch.bfloat16, device=a_sym.device)
+        self._barrier()  # every rank's block is written
+        rc = self.lib.pb_gemm_allgather(self._peer_array(a_sym), self.n, self.idx, b.data_ptr(), out.data_ptr(), M_local, N, K,
+                                        a_sym.stride(0), b.stride(0), out.stride(0), _stream())  # fmt: skip
+        _lib.check(rc, "pb_gemm_allgather")
+        _count()
+        self._barrier()  # nobody may overwrite its block while a peer is still reading it
+        return out
+
+    def gemm_reduce_scatter(self, a: torch.Tensor, b: torch.Tensor, out_sym: torch.Tensor) -> torch.Tensor:
+        """``a``: [M, K_local], ``b``: [N, K_local] (this rank's K shard, local memory); ``out_sym``: this rank's [M/n, N] fp32 buffer
+        from ``heap.alloc`` (same offset everywhere). On return it holds rows [idx·M/n, (idx+1)·M/n) of Σ_ranks a·bᵀ."""
+        M, K = a.shape
+        N = b.shape[0]
+        assert out_sym.dtype == torch.float32 and out_sym.shape == (M // self.n, N) and (M // self.n) % 256 == 0
+        out_sym.zero_()
+        self._barrier()  # all output buffers are zeroed
+        rc = self.lib.pb_gemm_reduce_scatter(a.data_ptr(), b.data_ptr(), self._peer_array(out_sym), self.n, self.idx, M, N, K,
+                                             a.stride(0), b.stride(0), out_sym.stride(0), _stream())  # fmt: skip
+        _lib.check(rc, "pb_gemm_reduce_scatter")
+        _count()
+        self._barrier()  # every rank's contributions have landed (TMA reduce completes before the kernel retires)
+        return out_sym

@@ -88,3 +88,68 @@ def test_diloco2_fused_outer_matches_collective(tmp_path):
     assert r["outer"] == 2
     assert r["rel"] < 2e-3, r
     assert r["hashes"][0] == r["hashes"][1], r  # workers identical right after an outer step
+
+
+CG_WORKER = textwrap.dedent(
+    """
+    import json, sys, torch
+    import torch.distributed as dist
+    sys.path.insert(0, {root!r})
+    from prime_b200 import ops
+    from prime_b200.parallel.mesh import init_distributed
+    from prime_b200.parallel.symm import SymmetricHeap, dist_exchange
+    from prime_b200.parallel.collective_gemm import CollectiveGemm
+
+    w = init_distributed("nccl")
+    dev = torch.device("cuda", w.local_rank)
+    n, r = w.world_size, w.rank
+    heap = SymmetricHeap(512 << 20, r, n, dist_exchange(), dev)
+    cg = CollectiveGemm(heap, list(range(n)))
+    torch.manual_seed(1234)  # same tensors on every rank, then shard
+    M_local, N, K = 512, 1024, 768
+    A_full = (torch.randn(n * M_local, K, device=dev) * 0.1).to(torch.bfloat16)
+    B = (torch.randn(N, K, device=dev) * 0.1).to(torch.bfloat16)
+    # ---- all-gather + GEMM
+    a_sym = heap.alloc(M_local * K, torch.bfloat16).view(M_local, K)
+    a_sym.copy_(A_full[r * M_local:(r + 1) * M_local])
+    C = cg.all_gather_gemm(a_sym, B)
+    ref = A_full.float() @ B.float().t()
+    e_ag = float((C.float() - ref).norm() / ref.norm())
+    # ---- GEMM + reduce-scatter (K sharded)
+    Kl = K // n
+    M = n * M_local
+    a_k = A_full[:, r * Kl:(r + 1) * Kl].contiguous()
+    b_k = B[:, r * Kl:(r + 1) * Kl].contiguous()
+    out_sym = heap.alloc((M // n) * N, torch.float32).view(M // n, N)
+    for _ in range(2):  # twice: the buffers and flags are reusable
+        cg.gemm_reduce_scatter(a_k, b_k, out_sym)
+    torch.cuda.synchronize()
+    partial = [A_full[:, i * Kl:(i + 1) * Kl].float() @ B[:, i * Kl:(i + 1) * Kl].float().t() for i in range(n)]
+    ref_rs = sum(partial)[r * (M // n):(r + 1) * (M // n)]
+    e_rs = float((out_sym - ref_rs).norm() / ref_rs.norm())
+    heap.check_errors()
+    errs = [None] * n
+    dist.all_gather_object(errs, (e_ag, e_rs))
+    if r == 0:
+        print("RESULT " + json.dumps(dict(errs=errs)))
+    dist.barrier()
+    heap.close()
+    dist.destroy_process_group()
+    """
+)
+
+
+def test_fused_allgather_gemm_and_gemm_reduce_scatter(tmp_path):
+    """ONE kernel each: A tiles pulled from the owning rank's memory by TMA inside the GEMM; fp32 tiles reduce-added into the
+    owning rank's buffer by TMA from the GEMM epilogue. Compared with the dense single-device result."""
+    script = tmp_path / "cg_worker.py"
+    script.write_text(CG_WORKER.format(root=str(ROOT)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script)]  # fmt: skip
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    errs = json.loads(line[len("RESULT "):])["errs"]
+    for e_ag, e_rs in errs:
+        assert e_ag < 1e-2, errs
+        assert e_rs < 2e-3, errs
