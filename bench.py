@@ -66,6 +66,7 @@ def main() -> None:
     ap.add_argument("--seq", type=int, default=SEQ)
     ap.add_argument("--no-fused-comm", action="store_true", help="baseline B0: NCCL collectives instead of fused P2P kernels")
     ap.add_argument("--attn", default="auto")
+    ap.add_argument("--fp8", action="store_true", help="NON-headline: MXFP8 forward/dgrad GEMMs (reported with dtype 'mxfp8+bf16')")
     ap.add_argument("--graphs", type=int, default=0, help="capture each micro-step (fwd+bwd) in a CUDA graph")
     args = ap.parse_args()
 
@@ -97,7 +98,7 @@ def main() -> None:
             "optim": {"batch_size": args.micro_bs * args.accum * fsdp, "warmup_steps": 10, "total_steps": 100000,
                       "optim": {"lr": 4e-4}},
             "train": {"micro_bs": args.micro_bs, "fused_comm": not args.no_fused_comm, "attn_impl": args.attn,
-                      "cuda_graphs": bool(args.graphs)},
+                      "cuda_graphs": bool(args.graphs), "fp8": args.fp8},
             "diloco": {"inner_steps": H, "compression": "int8", "outer_lr": 0.7},
             "mesh": {"num_workers": workers, "fsdp_size": fsdp},
         }
@@ -169,7 +170,7 @@ def main() -> None:
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "bf16",
+            "dtype": "bf16" if not args.fp8 else "mxfp8+bf16 (non-headline)",
             "data": "synthetic tokens, random-init weights",
             "impl": "ours",
             "config": {

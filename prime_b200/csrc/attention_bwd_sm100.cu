@@ -473,7 +473,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* s_empty = bars + 11;   // 2 (4 warps)
   uint64_t* p_full = bars + 13;    // 2 (4 warps)
   uint64_t* acc_done = bars + 15;  // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* all_done = bars + 17;  // 1: every dQ MMA of this block has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqb = p.S / 128;
@@ -493,6 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
+    mbar_init(all_done, 1);
     for (int i = 0; i < C::kKVStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
@@ -594,6 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         umma_commit(&kv_empty[ks]);
         umma_commit(&acc_done[st]);
       }
+      umma_commit(all_done);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -640,9 +643,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);
     }
-    const int tl = n_kv - 1;
-    mbar_wait(&acc_done[tl & 1], (tl >> 1) & 1);
-    if (n_kv >= 2) mbar_wait(&acc_done[(tl - 1) & 1], ((tl - 1) >> 1) & 1);
+    // NOT acc_done[last tile's stage]: a group only follows its OWN stage's barrier inside the loop, so it can reach this point
+    // while the other stage is still two phases behind — a parity wait would then match the phase BEFORE the previous one and
+    // fall through with the last tile's dQ += dS·K still outstanding (found by compute-sanitizer's timing perturbation)
+    mbar_wait(all_done, 0);
     tc_fence_after();
     uint8_t* stage = sK;  // the K/V rings (4 x kKVBytes = 64 KB at D = 128) are idle now
     constexpr int kC32PerWarp = D / 64;  // each warp of a quadrant drains half of the D accumulator columns

@@ -24,7 +24,7 @@ EncodeFn get_encode() {
   return fn;
 }
 
-// rows x cols (cols contiguous) matrix with row stride ld (elements); box = box_cols x box_rows; esize 2 (bf16) | 4 (f32)
+// rows x cols (cols contiguous) matrix with row stride ld (elements); box = box_cols x box_rows; esize 1 (fp8/bytes) | 2 (bf16) | 4 (f32)
 static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                      uint32_t box_rows, int esize) {
   EncodeFn enc = get_encode();
@@ -40,7 +40,8 @@ static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t 
   cuuint64_t strides[1] = {ld * (uint64_t)esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  const CUtensorMapDataType dt = esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(map, dt, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -6,7 +6,7 @@
 
 namespace pbhost {
 // rows x cols matrix (cols contiguous), row stride `ld` elements, 128B-swizzled boxes of box_cols x box_rows.
-// esize: 2 = bf16, 4 = fp32.  Returns 0 on success.
+// esize: 1 = fp8 (bytes), 2 = bf16, 4 = fp32.  Returns 0 on success.
 int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                 uint32_t box_rows, int esize = 2);
 int num_sms();

@@ -100,10 +100,15 @@ class Attention(nn.Module):
         qkv_out = (self.n_heads + 2 * self.n_kv_heads) * self.head_dim
         self.wqkv = nn.Parameter(torch.empty(qkv_out, args.dim))
         self.wo = nn.Parameter(torch.empty(args.dim, self.n_heads * self.head_dim))
+        self.fp8 = False  # train.fp8: MXFP8 forward / input-gradient GEMMs (Transformer.set_fp8)
 
     def forward(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, attn_impl: str = "auto") -> torch.Tensor:
         B, S, _ = x.shape
         H, Hkv, D = self.n_heads, self.n_kv_heads, self.head_dim
+        if self.fp8:
+            qkv = ops.linear_mxfp8(x, self.wqkv)
+            out = ops.rope_attention_qkv(qkv, cos, sin, H, Hkv, causal=True, impl=attn_impl)
+            return ops.linear_mxfp8(out, self.wo)
         if attn_impl in ("auto", "native") and ops.rope_fusable(x, H, Hkv, D):
             # RoPE rides in the QKV GEMM epilogue (forward) and in the dQ/dK epilogues of the attention backward: no rotation pass
             qkv = ops.linear_qkv_rope(x, self.wqkv, cos, sin, H, Hkv)  # [B, S, (H+2Hkv)·D], Q/K heads rotated
@@ -120,8 +125,11 @@ class FeedForward(nn.Module):
         hidden = args.ffn_hidden
         self.w13 = nn.Parameter(torch.empty(2 * hidden, args.dim))  # rows [0,hidden)=w1 (gate), [hidden,2h)=w3 (up)
         self.w2 = nn.Parameter(torch.empty(args.dim, hidden))
+        self.fp8 = False
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.fp8:
+            return ops.linear_mxfp8(ops.swiglu(ops.linear_mxfp8(x, self.w13)), self.w2)
         return ops.linear(ops.linear_swiglu(x, self.w13), self.w2)  # SwiGLU rides in the gate/up GEMM epilogue on CUDA
 
 
@@ -168,6 +176,12 @@ class Transformer(nn.Module):
         self._rope: tuple[torch.Tensor, torch.Tensor] | None = None
 
     # ------------------------------------------------------------------ init
+    def set_fp8(self, on: bool) -> None:
+        """MXFP8 (block-scaled e4m3, tcgen05 kind::mxf8f6f4) for the forward and input-gradient GEMMs of every block's four
+        projections; weight gradients, the LM head, norms and attention stay bf16 / fp32."""
+        for blk in self.layers:
+            blk.attention.fp8 = blk.feed_forward.fp8 = bool(on)
+
     def init_weights(self, seed: int | None = None) -> None:
         dev = self.output.device
         gen = None

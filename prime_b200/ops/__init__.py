@@ -7,8 +7,12 @@ from .functional import (  # noqa: F401
     attention_qkv,
     cross_entropy,
     gemm,
+    gemm_mxfp8,
     launch_count,
+    mxfp8_sf_bytes,
+    quantize_mxfp8,
     linear,
+    linear_mxfp8,
     linear_qkv_rope,
     linear_swiglu,
     rope_fusable,

@@ -129,6 +129,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "pb_gemm_bf16_swiglu": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "pb_gemm_allgather": [vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp],
         "pb_gemm_reduce_scatter": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+        "pb_quantize_mxfp8": [vp, i64, vp, vp, i32, i32, i32, vp],
+        "pb_gemm_mxfp8": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "pb_gemm_set_pair_mode": [i32],
         "pb_gemm_set_split_k": [i32],
         "pb_flash_attn_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp],
@@ -159,6 +161,9 @@ def _declare(lib: ctypes.CDLL) -> None:
             continue
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
+    if hasattr(lib, "pb_mxfp8_sf_bytes"):
+        lib.pb_mxfp8_sf_bytes.argtypes = [i32, i32]
+        lib.pb_mxfp8_sf_bytes.restype = ctypes.c_int64
 
 
 def load(build_if_missing: bool = True) -> ctypes.CDLL:

@@ -151,6 +151,110 @@ def linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
 
 
 # A/B switch for measurements: PB_NO_EPILOGUE_FUSION=1 runs RoPE and SwiGLU as stand-alone kernels again
+# --------------------------------------------------------------------------- block-scaled fp8 (MXFP8)
+
+
+def mxfp8_sf_bytes(rows: int, k: int) -> int:
+    """Size of the scale-factor buffer of a [rows, k] MXFP8 operand: [k/128][ceil(rows/128)+1] atoms of 512 bytes."""
+    return (k // 128) * ((rows + 127) // 128 + 1) * 512
+
+
+def quantize_mxfp8(x: torch.Tensor, transpose: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
+    """bf16 [R, C] → (e4m3 values as uint8, UE8M0 scales in the tensor-core layout), one power-of-two scale per 32 elements.
+
+    ``transpose=False``: values [R, C], blocks along C (operand contracted over C).
+    ``transpose=True``:  values [C, R], blocks along R (the same matrix used with R as the contraction dimension)."""
+    assert x.dim() == 2 and x.dtype == torch.bfloat16 and x.stride(1) == 1
+    R, C = x.shape
+    rows, k = (C, R) if transpose else (R, C)
+    assert k % 128 == 0, f"MXFP8 contraction dimension must be a multiple of 128, got {k}"
+    if not x.is_cuda:
+        return reference.quantize_mxfp8(x, transpose)
+    q = torch.empty((rows, k), dtype=torch.uint8, device=x.device)
+    sf = torch.empty(mxfp8_sf_bytes(rows, k), dtype=torch.uint8, device=x.device)
+    rc = _lib.load().pb_quantize_mxfp8(x.data_ptr(), x.stride(0), q.data_ptr(), sf.data_ptr(), R, C, int(transpose), _stream())
+    _lib.check(rc, "pb_quantize_mxfp8")
+    _count()
+    return q, sf
+
+
+def gemm_mxfp8(aq: torch.Tensor, asf: torch.Tensor, bq: torch.Tensor, bsf: torch.Tensor, out: torch.Tensor | None = None,
+               max_ctas: int = 0) -> torch.Tensor:  # fmt: skip
+    """C[M,N] bf16 = dequant(A)·dequant(B)ᵀ on ``tcgen05.mma.kind::mxf8f6f4.block_scale`` (scales applied by the tensor core)."""
+    M, K = aq.shape
+    N, Kb = bq.shape
+    assert K == Kb and aq.dtype == torch.uint8 and bq.dtype == torch.uint8 and aq.is_contiguous() and bq.is_contiguous()
+    if not aq.is_cuda:
+        c = reference.dequantize_mxfp8(aq, asf) @ reference.dequantize_mxfp8(bq, bsf).t()
+        if out is None:
+            return c.to(torch.bfloat16)
+        out.copy_(c)
+        return out
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=aq.device)
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16 and out.stride(1) == 1
+    rc = _lib.load().pb_gemm_mxfp8(aq.data_ptr(), asf.data_ptr(), bq.data_ptr(), bsf.data_ptr(), out.data_ptr(), M, N, K, out.stride(0),
+                                   max_ctas, _stream())  # fmt: skip
+    _lib.check(rc, "pb_gemm_mxfp8")
+    _count()
+    return out
+
+
+class _LinearMXFP8Fn(torch.autograd.Function):
+    """y = x Wᵀ with the forward and the input-gradient GEMMs in block-scaled fp8; the weight gradient stays bf16 with fp32
+    accumulation into ``main_grad`` (its contraction runs over tokens, where per-32 blocks along the token axis would need a
+    third quantisation of both operands for the least precision-tolerant of the three GEMMs)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        ctx.save_for_backward(x2, weight)
+        ctx.x_shape = x.shape
+        xq, xsf = quantize_mxfp8(x2)
+        wq, wsf = quantize_mxfp8(weight)
+        y = torch.empty((*x.shape[:-1], weight.shape[0]), dtype=x.dtype, device=x.device)
+        gemm_mxfp8(xq, xsf, wq, wsf, out=y.view(-1, weight.shape[0]))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        x2, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dyq, dysf = quantize_mxfp8(dy2)                     # [M, N], blocks along N
+            wtq, wtsf = quantize_mxfp8(weight, transpose=True)  # [K, N], blocks along N
+            dx = torch.empty(ctx.x_shape, dtype=dy.dtype, device=dy.device)
+            gemm_mxfp8(dyq, dysf, wtq, wtsf, out=dx.view(-1, ctx.x_shape[-1]))
+        if ctx.needs_input_grad[1]:
+            main_grad = getattr(weight, "main_grad", None)
+            if x2.is_cuda:
+                if main_grad is not None:
+                    gemm(dy2, x2, a_mn_major=True, b_mn_major=True, out=main_grad, accumulate=True)
+                else:
+                    dw = gemm(dy2, x2, a_mn_major=True, b_mn_major=True)
+            else:
+                dw = (dy2.float().t() @ x2.float()).to(weight.dtype)
+        return dx, dw
+
+
+def mxfp8_usable(x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Both contraction dimensions (in for the forward, out for the input gradient) must be multiples of 128."""
+    return weight.shape[0] % 128 == 0 and weight.shape[1] % 128 == 0 and x.dtype == torch.bfloat16
+
+
+def linear_mxfp8(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``linear`` with MXFP8 forward / input-gradient GEMMs (``train.precision = "mxfp8"``); falls back to bf16 for shapes the
+    block format cannot express."""
+    if not mxfp8_usable(x, weight):
+        return linear(x, weight)
+    return _LinearMXFP8Fn.apply(x, weight)
+
+
 _NO_EPILOGUE_FUSION = bool(int(__import__("os").environ.get("PB_NO_EPILOGUE_FUSION", "0")))
 
 

@@ -140,3 +140,38 @@ def nesterov_outer_step(
     momentum_buf.mul_(momentum).add_(avg_pseudo_grad)
     step = avg_pseudo_grad + momentum * momentum_buf if nesterov else momentum_buf
     theta0.add_(step, alpha=-lr)
+
+
+# ----------------------------------------------------------------------------------------------------------- MXFP8
+def _mxfp8_sf_index(rows: int, k: int, device=None) -> torch.Tensor:
+    """Byte offset of the scale of (row r, 32-block kb) in the tensor-core layout used by csrc/gemm_mxfp8_sm100.cu:
+    [k/128][ceil(rows/128)+1] atoms of 512 bytes; inside an atom (r % 32) * 16 + ((r % 128) // 32) * 4 + kb % 4."""
+    atoms = (rows + 127) // 128 + 1
+    r = torch.arange(rows, device=device).view(-1, 1)
+    kb = torch.arange(k // 32, device=device).view(1, -1)
+    return ((kb >> 2) * atoms + (r >> 7)) * 512 + (r & 31) * 16 + ((r & 127) >> 5) * 4 + (kb & 3)
+
+
+def quantize_mxfp8(x: torch.Tensor, transpose: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
+    """OCP MX e4m3: per 32 contiguous contraction elements a power-of-two scale 2^e, the smallest with amax / 2^e <= 448."""
+    xf = (x.t() if transpose else x).float().contiguous()
+    rows, k = xf.shape
+    assert k % 128 == 0
+    blocks = xf.view(rows, k // 32, 32)
+    amax = blocks.abs().amax(dim=-1)
+    v = (amax * (1.0 / 448.0)).to(torch.float32)
+    bits = v.view(torch.int32)
+    e = (bits >> 23) & 0xFF
+    e = torch.where((bits & 0x7FFFFF) != 0, e + 1, e).clamp(1, 254)
+    inv = ((254 - e) << 23).to(torch.int32).view(torch.float32)
+    q = (blocks * inv.unsqueeze(-1)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8).view(rows, k)
+    sf = torch.full(((k // 128) * ((rows + 127) // 128 + 1) * 512,), 127, dtype=torch.uint8, device=x.device)
+    sf[_mxfp8_sf_index(rows, k, x.device).reshape(-1)] = e.to(torch.uint8).reshape(-1)
+    return q, sf
+
+
+def dequantize_mxfp8(q: torch.Tensor, sf: torch.Tensor) -> torch.Tensor:
+    rows, k = q.shape
+    e = sf[_mxfp8_sf_index(rows, k, q.device).reshape(-1)].view(rows, k // 32).to(torch.int32)
+    scale = (e << 23).view(torch.float32)
+    return (q.view(torch.float8_e4m3fn).float().view(rows, k // 32, 32) * scale.unsqueeze(-1)).view(rows, k)

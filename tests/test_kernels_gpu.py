@@ -434,3 +434,80 @@ def test_gemm_swiglu_epilogue(M, FF, K):
     assert _rel_err(x.grad, xr.grad) < 1e-3 and _rel_err(w.grad, wr.grad) < 1e-3
     ref = torch.nn.functional.silu(x.detach().float() @ w.detach().float()[:FF].t()) * (x.detach().float() @ w.detach().float()[FF:].t())
     assert _rel_err(h, ref) < 2e-2
+
+
+# ------------------------------------------------------------------ MXFP8 (block-scaled fp8 on tcgen05 kind::mxf8f6f4)
+@pytest.mark.parametrize("R,C,transpose", [(256, 384, False), (200, 1024, False), (4096, 2048, False), (256, 384, True), (1024, 200, True), (2048, 5632, True)])
+def test_quantize_mxfp8_matches_reference(R, C, transpose):
+    from prime_b200 import ops
+    from prime_b200.ops import reference as Rf
+
+    torch.manual_seed(R + C)
+    x = (torch.randn(R, C, device=_dev()) * torch.rand(R, 1, device=_dev()) * 8).to(torch.bfloat16)
+    q, sf = ops.quantize_mxfp8(x, transpose)
+    q_ref, sf_ref = Rf.quantize_mxfp8(x, transpose)
+    torch.cuda.synchronize()
+    rows, k = q.shape
+    idx = Rf._mxfp8_sf_index(rows, k, _dev()).reshape(-1)
+    assert torch.equal(sf[idx], sf_ref[idx]), "UE8M0 scales differ"
+    assert torch.equal(q, q_ref), f"{int((q != q_ref).sum())} e4m3 values differ"
+    deq = Rf.dequantize_mxfp8(q, sf)
+    tgt = (x.t() if transpose else x).float()
+    assert _rel_err(deq, tgt) < 0.04
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 192, 128), (256, 384, 512), (300, 520, 256), (1024, 2112, 1024), (4096, 3072, 2048), (136, 8, 128)])
+def test_gemm_mxfp8_matches_dequantized_reference(M, N, K):
+    from prime_b200 import ops
+    from prime_b200.ops import reference as Rf
+
+    torch.manual_seed(M * 3 + N + K)
+    # per-row magnitudes spread over a few octaves so wrong scale bytes (wrong row / wrong K block) cannot cancel out
+    A = (torch.randn(M, K, device=_dev()) * torch.exp2(torch.randint(-3, 4, (M, 1), device=_dev()).float())).to(torch.bfloat16)
+    B = (torch.randn(N, K, device=_dev()) * torch.exp2(torch.randint(-3, 4, (N, 1), device=_dev()).float())).to(torch.bfloat16)
+    A[:, K // 2 :] *= 4  # and across K blocks
+    aq, asf = ops.quantize_mxfp8(A)
+    bq, bsf = ops.quantize_mxfp8(B)
+    out = ops.gemm_mxfp8(aq, asf, bq, bsf)
+    torch.cuda.synchronize()
+    ref = Rf.dequantize_mxfp8(aq, asf) @ Rf.dequantize_mxfp8(bq, bsf).t()
+    assert _rel_err(out, ref) < 6e-3, f"rel err {_rel_err(out, ref)}"
+    assert _rel_err(out, A.float() @ B.float().t()) < 0.06  # and the quantisation itself is sane
+
+
+def test_linear_mxfp8_autograd():
+    from prime_b200 import ops
+
+    torch.manual_seed(5)
+    x = torch.randn(4, 256, 1024, device=_dev(), dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.randn(1536, 1024, device=_dev()) * 0.03).to(torch.bfloat16).requires_grad_(True)
+    y = ops.linear_mxfp8(x, w)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    xr, wr = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    yr = xr @ wr.t()
+    yr.backward(dy.float())
+    assert _rel_err(y, yr) < 0.05
+    assert _rel_err(x.grad, xr.grad) < 0.05
+    assert _rel_err(w.grad, wr.grad) < 1e-2  # weight gradient stays bf16 x bf16 → fp32
+
+
+def test_model_fp8_mode_tracks_bf16_loss():
+    from prime_b200.models.llama import build_model
+
+    torch.manual_seed(0)
+    model = build_model("150M", "llama2", device=_dev(), dtype=torch.bfloat16, seed=0, n_layers=2)
+    tokens = torch.randint(0, model.args.vocab_size, (2, 256), device=_dev())
+    targets = torch.randint(0, model.args.vocab_size, (2, 256), device=_dev())
+    losses = {}
+    grads = {}
+    for fp8 in (False, True):
+        model.set_fp8(fp8)
+        model.zero_grad(set_to_none=True)
+        loss = model.loss(tokens, targets)
+        loss.backward()
+        losses[fp8] = float(loss)
+        grads[fp8] = model.layers[0].feed_forward.w2.grad.float().clone()
+    assert abs(losses[True] - losses[False]) < 0.02 * abs(losses[False]), losses
+    assert _rel_err(grads[True], grads[False]) < 0.15
