@@ -5,7 +5,7 @@
 set -u
 SAN=compute-sanitizer
 run() { # tool, pytest -k expression, tag
-  timeout 600 $SAN --tool "$1" --print-limit 5 --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -x -q -k "$2" -p no:cacheprovider \
+  timeout 600 $SAN --tool "$1" --print-limit 5 --error-exitcode 9 python -m pytest tests/test_kernels_gpu.py -q -k "$2" -p no:cacheprovider \
     > gpurun_out/sanitizer_$3.log 2>&1
   echo "$1 [$2]: exit $? — $(grep -E 'ERROR SUMMARY|passed|failed' gpurun_out/sanitizer_$3.log | tr '\n' ' ')" | tee -a gpurun_out/sanitizer_summary.txt
 }
@@ -14,5 +14,7 @@ run memcheck  "rmsnorm or swiglu or rope_qkv or cross_entropy" memcheck_elementw
 run memcheck  "gemm_layouts or gemm_fp32 or split_k" memcheck_gemm
 run memcheck  "flash_attention or rope_attention" memcheck_attention
 run racecheck "rmsnorm or cross_entropy" racecheck_elementwise
-run synccheck "gemm_pair or flash_attention" synccheck_tc
+run synccheck "gemm_pair or flash_attention or rope_attention or qkv_gemm_rope" synccheck_tc
+run memcheck  "mxfp8" memcheck_mxfp8
+run synccheck "mxfp8 or swiglu_epilogue" synccheck_mxfp8
 cat gpurun_out/sanitizer_summary.txt
