@@ -31,51 +31,69 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BN = 192, BKB = 128;  // BKB: K elements (= bytes) per stage
-constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kThreads = 256;
 constexpr uint32_t kABytes = BM * BKB;        // 16 KB
-constexpr uint32_t kBBytes = BN * BKB;        // 24 KB
 constexpr uint32_t kSfaBytes = 512;           // one atom: 128 rows x 4 K-blocks
 constexpr uint32_t kSfbBytes = 1024;          // two atoms
-constexpr uint32_t kStageBytes = kABytes + kBBytes + kSfaBytes + kSfbBytes;  // 42,496 (multiple of 1024? no: operands first)
-constexpr uint32_t kStagePitch = 43008;       // 42 KB: keeps every stage's A/B tiles 1024-aligned for SWIZZLE_128B
 constexpr uint32_t kStagingBytes = 4 * 2 * 4096;
-constexpr uint32_t kSmemBytes = kStages * kStagePitch + kStagingBytes + 1024 + 256;
 constexpr int kGroupM = 16;
 constexpr uint32_t kSfaCol = kAccStages * BN;  // 384
 constexpr uint32_t kSfbCol = kSfaCol + 4;      // 388 .. 395
 
-static_assert(kStagePitch >= kStageBytes && kStagePitch % 1024 == 0, "stage pitch");
-static_assert(kSmemBytes <= 232448, "shared memory budget");
+// PAIR = 0: one CTA per 128 x 192 tile. PAIR = 1 (cta_group::2): a CTA pair per 256 x 192 tile — each CTA stages its own 128 A rows,
+// HALF of B (96 rows), its own SFA atom and the whole SFB; the leader issues M = 256 block-scaled MMAs and the tcgen05.cp copies
+// (cta_group::2: every CTA copies from its OWN shared memory into its OWN TMEM). At fp8 rates a stage lasts only 384 clk, so the
+// single-CTA ring (4 x 40 KB in flight against ~3000 clk of TMA latency) starves the tensor core; the pair needs 28 KB per CTA per
+// stage and keeps 6 stages in flight.
+template <int PAIR>
+struct Geo {
+  static constexpr int kTileM = PAIR ? 2 * BM : BM;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;
+  static constexpr uint32_t kBBytes = kBRows * BKB;  // 12 KB | 24 KB
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes + kSfaBytes + kSfbBytes;
+  static constexpr uint32_t kStagePitch = (kStageBytes + 1023) / 1024 * 1024;  // A/B tiles stay 1024-aligned (SWIZZLE_128B)
+  static constexpr int kStages = PAIR ? 6 : 4;
+  static constexpr uint32_t kSmemBytes = kStages * kStagePitch + kStagingBytes + 1024 + 256;
+};
+static_assert(Geo<0>::kSmemBytes <= 232448 && Geo<1>::kSmemBytes <= 232448, "shared memory budget");
 
 // kind::mxf8f6f4 block-scaled instruction descriptor: a/b = e4m3 (0), K-major both, N>>3 at 17, UE8M0 scales (bit 23),
 // M>>4 at 24; scale-factor byte selectors: b_sf_id at 4, a_sf_id at 29
-__host__ __device__ constexpr uint32_t make_idesc_mx(uint32_t sf_id) {
-  return (sf_id << 4) | ((uint32_t)(BN >> 3) << 17) | (1u << 23) | ((uint32_t)(BM >> 4) << 24) | (sf_id << 29);
+__host__ __device__ constexpr uint32_t make_idesc_mx(uint32_t sf_id, int m) {
+  return (sf_id << 4) | ((uint32_t)(BN >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24) | (sf_id << 29);
 }
 
+template <int PAIR>
 __device__ __forceinline__ void umma_mxfp8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum, uint32_t tsfa,
                                            uint32_t tsfb) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(tsfa), "r"(tsfb)
-      : "memory");
+  if (PAIR) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(tsfa), "r"(tsfb)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(tsfa), "r"(tsfb)
+        : "memory");
+  }
 }
 // 32 rows x 16 bytes of shared memory → the same 4 TMEM columns of all four lane quadrants
+template <int PAIR>
 __device__ __forceinline__ void tmem_cp_sf(uint32_t taddr, uint32_t saddr) {
   // no-swizzle K-major descriptor: 8-row x 16-byte core matrices, 128 bytes apart
-  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(d) : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)), "l"(gmem),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+  const uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+  if (PAIR) asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(d) : "memory");
+  else asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(d) : "memory");
 }
 
 __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
@@ -90,14 +108,23 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 
 struct MxParams {
   int M, N, K;
-  const uint8_t* sfa;  // [K/128][atoms_m][512]
-  const uint8_t* sfb;  // [K/128][atoms_n][512]
-  int atoms_m, atoms_n;
+  int atoms_m, atoms_n;  // atoms per K/128 row of the scale buffers: [K/128][atoms][512 B]
 };
 
+// tmap_sfa / tmap_sfb: the scale buffers as [K/128 · atoms] rows of 128 uint32 (512 B), no swizzle; boxes of 1 / 2 rows
+template <int PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                      const __grid_constant__ CUtensorMap tmap_c, const MxParams p) {
+                      const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_sfa,
+                      const __grid_constant__ CUtensorMap tmap_sfb, const MxParams p) {
+  using G = Geo<PAIR>;
+  constexpr int kStages = G::kStages;
+  constexpr uint32_t kStagePitch = G::kStagePitch;
+  constexpr uint32_t kBBytes = G::kBBytes;
+  constexpr int kTileM = G::kTileM;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + kStages * kStagePitch;
@@ -108,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + kTileM - 1) / kTileM, tiles_n = (p.N + BN - 1) / BN;
   const int num_kb = p.K / BKB;
   const int num_tiles = tiles_m * tiles_n;
 
@@ -116,6 +143,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_c);
+    prefetch_tmap(&tmap_sfa);
+    prefetch_tmap(&tmap_sfb);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -124,50 +153,60 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], PAIR ? 8 : 4);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ producer: operands by TMA, scale atoms by 1-D bulk copy
+    // ------------------------------------------------------------------ producer: operands and scale atoms by TMA
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         int tm, tn;
         tile_coords(tile, tiles_m, tiles_n, tm, tn);
-        const int m0 = tm * BM, n0 = tn * BN;
-        const int atom_n0 = n0 >> 7;
+        const int m0 = tm * kTileM + (int)crank * BM;           // this CTA's A rows
+        const int n0 = tn * BN + (int)crank * G::kBRows;        // this CTA's share of the B rows
+        const int atom_m = tm * (kTileM / 128) + (int)crank;    // this CTA's SFA atom
+        const int atom_n0 = (tn * BN) >> 7;                     // first of the tile's two SFB atoms (every CTA needs both)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStagePitch;
           uint8_t* sb = sa + kABytes;
           uint8_t* ssfa = sb + kBBytes;
           uint8_t* ssfb = ssfa + kSfaBytes;
-          mbar_expect_tx(&full_bar[stage], kStageBytes);
-          tma_load_2d(&tmap_a, &full_bar[stage], sa, kb * BKB, m0);  // box {128 k-bytes, 128 rows}
-          tma_load_2d(&tmap_b, &full_bar[stage], sb, kb * BKB, n0);  // box {128 k-bytes, 192 rows}
-          bulk_load_1d(ssfa, p.sfa + ((size_t)kb * p.atoms_m + tm) * 512, kSfaBytes, &full_bar[stage]);
-          bulk_load_1d(ssfb, p.sfb + ((size_t)kb * p.atoms_n + atom_n0) * 512, kSfbBytes, &full_bar[stage]);
+          if (!PAIR || crank == 0) mbar_expect_tx(&full_bar[stage], (PAIR ? 2u : 1u) * G::kStageBytes);
+          auto load = [&](const CUtensorMap* m, void* dst, int c0, int c1) {
+            if (PAIR) tma_load_2d_pair(m, &full_bar[stage], dst, c0, c1);
+            else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
+          };
+          load(&tmap_a, sa, kb * BKB, m0);  // box {128 k-bytes, 128 rows}
+          load(&tmap_b, sb, kb * BKB, n0);  // box {128 k-bytes, 192 | 96 rows}
+          load(&tmap_sfa, ssfa, 0, kb * p.atoms_m + atom_m);   // box {128 words, 1 atom}
+          load(&tmap_sfb, ssfb, 0, kb * p.atoms_n + atom_n0);  // box {128 words, 2 atoms}
           if (++stage == kStages) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair)
+    if (lane == 0 && crank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t tsfa = tmem_base + kSfaCol;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         int tm, tn;
         tile_coords(tile, tiles_m, tiles_n, tm, tn);
         // odd N tiles begin 64 columns into their first SFB atom = 2 TMEM columns
@@ -182,19 +221,21 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t sb = sa + kABytes;
           const uint32_t ssfa = sb + kBBytes;
           const uint32_t ssfb = ssfa + kSfaBytes;
-          tmem_cp_sf(tsfa, ssfa);
-          tmem_cp_sf(tmem_base + kSfbCol, ssfb);
-          tmem_cp_sf(tmem_base + kSfbCol + 4, ssfb + 512);
+          tmem_cp_sf<PAIR>(tsfa, ssfa);
+          tmem_cp_sf<PAIR>(tmem_base + kSfbCol, ssfb);
+          tmem_cp_sf<PAIR>(tmem_base + kSfbCol + 4, ssfb + 512);
 #pragma unroll
           for (int k = 0; k < BKB / 32; ++k) {  // UMMA_K = 32 elements = 32 bytes inside the 128 B swizzle row
             const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t bdesc = make_smem_desc(sb + k * 32, 16, 1024);
-            umma_mxfp8(tmem_d, adesc, bdesc, make_idesc_mx((uint32_t)k), (kb | k) != 0 ? 1u : 0u, tsfa, tsfb);
+            umma_mxfp8<PAIR>(tmem_d, adesc, bdesc, make_idesc_mx((uint32_t)k, kTileM), (kb | k) != 0 ? 1u : 0u, tsfa, tsfb);
           }
-          umma_commit(&empty_bar[stage]);
+          if (PAIR) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) stage = 0, phase ^= 1;
         }
-        umma_commit(&tfull_bar[acc]);
+        if (PAIR) umma_commit_pair(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == kAccStages) acc = 0, acc_phase ^= 1;
       }
     }
@@ -206,12 +247,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
       int tm, tn;
       tile_coords(tile, tiles_m, tiles_n, tm, tn);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row0 = tm * BM + q * 32;
+      const int row0 = tm * kTileM + (int)crank * BM + q * 32;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int g = 0; g < BN / 64; ++g) {
@@ -239,17 +280,22 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tempty_bar[acc]);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == kAccStages) acc = 0, acc_phase ^= 1;
     }
     if (lane == 0) bulk_wait_read<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -340,9 +386,55 @@ __global__ void __launch_bounds__(128) quantize_mxfp8_t_kernel(const __nv_bfloat
   sf[sf_offset(c, rb >> 5, atoms_c)] = (uint8_t)e8;
 }
 
-bool g_configured = false;
+int g_mx_pair_mode = -1;  // -1: from PB_MXFP8_PAIR (default on)
+
+template <int PAIR>
+int launch_mx(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tsa, const CUtensorMap& tsb,
+              const MxParams& p, int max_ctas, cudaStream_t stream) {
+  using G = Geo<PAIR>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  int grid = pbhost::num_sms();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  const int tiles = ((p.M + G::kTileM - 1) / G::kTileM) * ((p.N + BN - 1) / BN);
+  if (!PAIR) {
+    if (tiles < grid) grid = tiles;
+    gemm_mxfp8_kernel<0><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, tsa, tsb, p);
+  } else {
+    grid &= ~1;
+    if (2 * tiles < grid) grid = 2 * tiles;
+    if (grid < 2) grid = 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = G::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_mxfp8_kernel<1>, ta, tb, tc, tsa, tsb, p);
+    if (e != cudaSuccess) return (int)e;
+  }
+  PB_CHECK_LAUNCH();
+  return 0;
+}
 
 }  // namespace
+
+// 0 = single-CTA 128x192 tiles, 1 = CTA-pair 256x192 tiles (cta_group::2, default), -1 = re-read PB_MXFP8_PAIR. Returns the old mode.
+PB_EXPORT int pb_gemm_mxfp8_set_pair_mode(int mode) {
+  const int old = g_mx_pair_mode;
+  g_mx_pair_mode = mode;
+  return old;
+}
 
 // Bytes of the scale-factor buffer for an operand with `rows` rows and K contraction elements (K % 128 == 0).
 PB_EXPORT int64_t pb_mxfp8_sf_bytes(int rows, int K) { return (int64_t)(K / 128) * ((rows + 127) / 128 + 1) * 512; }
@@ -373,22 +465,19 @@ PB_EXPORT int pb_gemm_mxfp8(const void* Aq, const void* sfa, const void* Bq, con
   if ((reinterpret_cast<uintptr_t>(Aq) | reinterpret_cast<uintptr_t>(Bq) | reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(sfa) |
        reinterpret_cast<uintptr_t>(sfb)) & 15)
     return -2;
-  CUtensorMap ta, tb, tc;
+  if (g_mx_pair_mode < 0) {
+    const char* e = getenv("PB_MXFP8_PAIR");
+    g_mx_pair_mode = e ? (atoi(e) != 0) : 1;
+  }
+  const int pair = g_mx_pair_mode && M > BM;
+  const int atoms_m = (M + 127) / 128 + 1, atoms_n = (N + 127) / 128 + 1, kblocks = K / 128;
+  CUtensorMap ta, tb, tc, tsa, tsb;
   int rc;
   if ((rc = pbhost::cached_tmap(&ta, Aq, (uint64_t)M, (uint64_t)K, (uint64_t)K, BKB, BM, 1))) return rc;
-  if ((rc = pbhost::cached_tmap(&tb, Bq, (uint64_t)N, (uint64_t)K, (uint64_t)K, BKB, BN, 1))) return rc;
+  if ((rc = pbhost::cached_tmap(&tb, Bq, (uint64_t)N, (uint64_t)K, (uint64_t)K, BKB, pair ? BN / 2 : BN, 1))) return rc;
   if ((rc = pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 64, 32, 2))) return rc;
-  if (!g_configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    g_configured = true;
-  }
-  MxParams p{M, N, K, (const uint8_t*)sfa, (const uint8_t*)sfb, (M + 127) / 128 + 1, (N + 127) / 128 + 1};
-  int grid = pbhost::num_sms();
-  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  if (tiles < grid) grid = tiles;
-  gemm_mxfp8_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, tc, p);
-  PB_CHECK_LAUNCH();
-  return 0;
+  if ((rc = pbhost::cached_tmap(&tsa, sfa, (uint64_t)kblocks * atoms_m, 128, 128, 128, 1, -4))) return rc;
+  if ((rc = pbhost::cached_tmap(&tsb, sfb, (uint64_t)kblocks * atoms_n, 128, 128, 128, 2, -4))) return rc;
+  MxParams p{M, N, K, atoms_m, atoms_n};
+  return pair ? launch_mx<1>(ta, tb, tc, tsa, tsb, p, max_ctas, stream) : launch_mx<0>(ta, tb, tc, tsa, tsb, p, max_ctas, stream);
 }

@@ -86,16 +86,68 @@ struct GemmParams {
 };
 
 // Fused collective GEMMs over the NVLink symmetric heap (IO template parameter of the kernel):
-//   IO = 1  all-gather ⊕ GEMM : row block r of A lives on rank r; the TMA producer loads every tile straight out of its owner's
-//           memory (peer tensor maps), own rows first, so the gather is hidden tile by tile behind the MMAs — no staging buffer.
+//   IO = 1  all-gather ⊕ GEMM : row block r of A lives on rank r. Peer memory is NOT cached in the local L2, so a remote A tile
+//           must cross NVLink exactly once: the tiles of output column 0 of every remote row block ("gather tiles", scheduled
+//           first, owners interleaved) TMA-load their A tiles straight from the owner into the MMA ring, and an otherwise idle
+//           warp TMA-stores each consumed ring slot into a local gathered copy of A; a per-row-block flag then releases the
+//           remaining column tiles of that block, which read the local copy (L2-resident). Local row blocks are scheduled between
+//           the two, so the NVLink transfer hides behind them. (Measured on 2 GPUs: loading every tile from the peer re-fetched
+//           each remote row 22 times and ran 3.6x slower than NCCL all-gather + GEMM.)
 //   IO = 2  GEMM ⊕ reduce-scatter : every rank computes a full partial C; the epilogue TMA-reduce-adds each fp32 tile into the
-//           buffer of the rank that owns those rows (cp.reduce.async.bulk.tensor on a peer-mapped address).
+//           buffer of the rank that owns those rows (cp.reduce.async.bulk.tensor on a peer-mapped address). Row blocks are visited
+//           owner-interleaved (rank+1, rank+2, …, self) so the NVLink reduce traffic is spread over the whole kernel and, at any
+//           moment, the ranks target distinct owners.
 struct PeerMaps {
   CUtensorMap m[8];
   int n;              // ranks
   int rows_per_rank;  // multiple of the tile height
-  int rot;            // tile-row rotation = my_rank * tiles_per_rank (start on local rows)
+  int rank;
+  uint32_t* flags;    // IO = 1: one counter per 256-row block of the gathered A (zeroed by the host before the launch)
+  int idle_rounds;    // IO = 1: scheduling rounds a CTA pair sits out after a gather tile (it costs ~3 ordinary tiles: NVLink latency)
 };
+
+// IO = 1 tile schedule: [gather tiles][local tiles][dependent tiles]; kind 1 = gather (tn = 0 of a remote block), 0 = local rows,
+// 2 = dependent (waits for the block's flag, reads the local gathered copy). Lower indices never wait on higher ones.
+__device__ __forceinline__ void ag_tile(int idx, const PeerMaps& pm, int tiles_n, int tpr, int& tm, int& tn, int& kind) {
+  const int n = pm.n, G = (n - 1) * tpr, L = tpr * tiles_n;
+  if (idx < G) {
+    tm = ((pm.rank + 1 + idx % (n - 1)) % n) * tpr + idx / (n - 1);
+    tn = 0;
+    kind = 1;
+  } else if (idx < G + L) {
+    const int j = idx - G;
+    tm = pm.rank * tpr + j % tpr;
+    tn = j / tpr;
+    kind = 0;
+  } else {
+    const int j = idx - G - L, g = j % G;
+    tm = ((pm.rank + 1 + g % (n - 1)) % n) * tpr + g / (n - 1);
+    tn = 1 + j / G;
+    kind = 2;
+  }
+}
+// IO = 1 static schedule with load balancing: iteration `it` of CTA pair `sched_id` → tile index, -1 = idle slot, -2 = done.
+// Round 0 hands gather tile p to pair p < G; those pairs then sit out `idle` rounds while the others keep taking tiles.
+__device__ __forceinline__ int ag_next(int it, int sched_id, int sched_n, int G, int idle, int num_tiles) {
+  if (G == 0 || G > sched_n || idle == 0) {
+    const int t = sched_id + it * sched_n;
+    return t < num_tiles ? t : -2;
+  }
+  const int R = num_tiles - G;  // non-gather tiles, numbered in order behind the gather tiles
+  int r;
+  if (it == 0) {
+    if (sched_id < G) return sched_id;
+    r = sched_id - G;
+  } else if (it <= idle) {
+    if (sched_id < G) return -1;
+    r = (sched_n - G) * it + (sched_id - G);
+  } else {
+    r = (sched_n - G) * (idle + 1) + (it - idle - 1) * sched_n + sched_id;
+  }
+  return r < R ? G + r : -2;
+}
+// IO = 2 row-block order: raster index t → owner-interleaved tile row
+__device__ __forceinline__ int rs_tile_row(int t, const PeerMaps& pm, int tpr) { return ((pm.rank + 1 + t % pm.n) % pm.n) * tpr + t / pm.n; }
 
 // rotate the 16 interleaved pairs held in 32 consecutive fp32 accumulator registers (head-dim offset d0, sequence position pos)
 __device__ __forceinline__ void rope_regs(uint32_t (&r)[32], const float* __restrict__ cosb, const float* __restrict__ sinb, int pos, int d0,
@@ -140,7 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
+  uint64_t* copied_bar = tempty_bar + kAccStages;  // IO = 1: the gather copier has finished reading a consumed ring slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(copied_bar + kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool swiglu = PAIR && EPI == 2;
@@ -150,6 +203,18 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int split_k = p.split_k;
   const int kb_per = (num_kb + split_k - 1) / split_k;
   const int num_tiles = tiles_m * tiles_n * split_k;  // = number of work items
+  const int ag_G = (IO == 1 && pm.n > 1) ? (pm.n - 1) * (pm.rows_per_rank / kTileM) : 0;  // gather tiles (lowest indices)
+  // every role walks the same tile sequence: round-robin over the CTAs (pairs); all-gather mode inserts idle slots (ag_next)
+  auto next_tile = [&](int& it) -> int {
+    if (IO == 1 && pm.n > 1) {
+      for (;;) {
+        const int t = ag_next(it++, sched_id, sched_n, ag_G, pm.idle_rounds, num_tiles);
+        if (t != -1) return t;
+      }
+    }
+    const int t = sched_id + (it++) * sched_n;
+    return t < num_tiles ? t : -2;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -163,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+      mbar_init(&copied_bar[i], 1);
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -185,17 +251,33 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
-        int tm, tn;
-        tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn);
-        if (IO != 0) tm = (tm + pm.rot) % tiles_m;
+      const int tpr = IO != 0 ? pm.rows_per_rank / kTileM : 0;  // tile rows per rank
+      // gather tiles have the lowest indices: this CTA's are tiles sched_id, sched_id + sched_n, … below G
+      const int gather_fills = ag_G > sched_id ? ((ag_G - sched_id + sched_n - 1) / sched_n) * num_kb : 0;
+      int fill = 0;
+      for (int it = 0, tile; (tile = next_tile(it)) >= 0;) {
+        int tm, tn, kind = 0;
+        if (IO == 1 && pm.n > 1) {
+          ag_tile(tile, pm, tiles_n, tpr, tm, tn, kind);
+        } else {
+          tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn);
+          if (IO == 2) tm = rs_tile_row(tm, pm, tpr);
+        }
         const int kb0 = (tile % split_k) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
         if (kb0 >= kb1) continue;  // empty K slice (split does not divide K): every role skips it identically
         const int m0 = tm * kTileM + (int)crank * BM;      // this CTA's A rows
         // this CTA's share of the B rows (SwiGLU mode: leader = gate rows, partner = the matching up rows)
         const int n0 = swiglu ? (int)crank * p.swiglu_ff + tn * 128 : tn * BN + (int)crank * kBRows;
+        if (IO == 1 && kind == 2) {  // the block's gather tile (both CTAs of that pair) has stored these rows locally
+          SpinGuard guard;
+          while (pb::ld_acquire_gpu_u32(pm.flags + tm) < 2u) guard.tick();
+          fence_proxy_async_all();  // generic-proxy acquire → the TMA (async-proxy) reads below
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          // the slot's previous fill was a gather fill (they are the first fills of every CTA): the copier must have drained it
+          if (IO == 1 && fill >= kStages && fill - kStages < gather_fills) mbar_wait(&copied_bar[stage], phase ^ 1);
+          ++fill;
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
           // PAIR: the leader's barrier collects the bytes of BOTH CTAs' loads (complete_tx may precede expect_tx in a phase)
@@ -204,9 +286,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (PAIR) tma_load_2d_pair(m, &full_bar[stage], dst, c0, c1);
             else tma_load_2d(m, &full_bar[stage], dst, c0, c1);
           };
-          if (IO == 1) {  // A row block m0 lives on rank m0 / rows_per_rank: load it from there (NVLink for remote owners)
+          if (IO == 1) {
+            // gather / local tiles read the owner's block (NVLink for remote owners); dependent tiles read the local gathered copy
             const int owner = m0 / pm.rows_per_rank;
-            load(&pm.m[owner], sa, kb * BK, m0 - owner * pm.rows_per_rank);
+            if (kind == 2) load(&tmap_a, sa, kb * BK, m0);
+            else load(&pm.m[owner], sa, kb * BK, m0 - owner * pm.rows_per_rank);
           } else if (A_MN == 0) {
             load(&tmap_a, sa, kb * BK, m0);  // box {64 k, 128 m}
           } else {
@@ -233,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
+      for (int it = 0, tile; (tile = next_tile(it)) >= 0;) {
         const int kb0 = (tile % split_k) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
         if (kb0 >= kb1) continue;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
@@ -265,6 +349,32 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (++acc == kAccStages) acc = 0, acc_phase ^= 1;
       }
     }
+  } else if (IO == 1 && warp == 3) {
+    // ------------------------------------------------------------------ gather copier (all-gather ⊕ GEMM only)
+    // follows the ring in consumption order: once the MMAs have retired a slot (empty barrier), a gather tile's A slab is
+    // TMA-stored into the local gathered copy before the producer may refill the slot; after the tile, the block's flag is bumped
+    if (lane == 0) {
+      const int tpr = pm.rows_per_rank / kTileM;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0, tile; (tile = next_tile(it)) >= 0;) {
+        int tm = 0, tn = 0, kind = 0;
+        if (pm.n > 1) ag_tile(tile, pm, tiles_n, tpr, tm, tn, kind);
+        if (kind != 1) break;  // gather tiles come first; nothing to copy afterwards (the producer stops waiting for us too)
+        const int m0 = tm * kTileM + (int)crank * BM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase);
+          tma_store_2d(&tmap_a, smem + stage * kStageBytes, kb * BK, m0);
+          bulk_commit();
+          bulk_wait_read<0>();
+          mbar_arrive(&copied_bar[stage]);
+          if (++stage == kStages) stage = 0, phase ^= 1;
+        }
+        bulk_wait_all();          // the rows are in local memory …
+        fence_proxy_async_all();  // … async-proxy writes ordered before the generic-proxy release below
+        pb::red_add_release_gpu_u32(pm.flags + tm, 1u);
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     // TMEM → registers → 128B-swizzled smem slab (32 rows x 128 B per warp) → TMA store / reduce-add.
@@ -276,10 +386,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
-    for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
-      int tm, tn;
-      tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn);
-      if (IO != 0) tm = (tm + pm.rot) % tiles_m;
+    const int tpr = IO != 0 ? pm.rows_per_rank / kTileM : 0;
+    for (int it = 0, tile; (tile = next_tile(it)) >= 0;) {
+      int tm, tn, kind = 0;
+      if (IO == 1 && pm.n > 1) {
+        ag_tile(tile, pm, tiles_n, tpr, tm, tn, kind);
+      } else {
+        tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn);
+        if (IO == 2) tm = rs_tile_row(tm, pm, tpr);
+      }
       if ((tile % split_k) * kb_per >= num_kb) continue;  // empty K slice
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -592,23 +707,39 @@ PB_EXPORT int pb_gemm_bf16_swiglu(const void* A, const void* W13, void* gate_up,
 // all-gather ⊕ GEMM:  C[n·M_local, N] = [A_0; A_1; …; A_{n-1}] · Bᵀ, A_r = rank r's [M_local, K] block in the symmetric heap.
 // a_peers[r] is the address of rank r's block AS MAPPED IN THIS PROCESS. The caller brackets the call with heap barriers (every
 // rank's block written before, nobody overwrites it until all ranks are done). K-major operands, bf16 output, CTA-pair tiles.
-PB_EXPORT int pb_gemm_allgather(const void* const* a_peers, int n, int rank, const void* B, void* C, int M_local, int N, int K, int lda,
-                                int ldb, int ldc, cudaStream_t stream) {
+// a_full: local [n·M_local, K] bf16 scratch that receives the remote row blocks (by-product: the gathered A, minus the local block);
+// flags: n·M_local/256 uint32 counters in local memory (zeroed here, on the stream).
+PB_EXPORT int pb_gemm_allgather(const void* const* a_peers, int n, int rank, const void* B, void* C, void* a_full, uint32_t* flags,
+                                int M_local, int N, int K, int lda, int ldb, int ldc, cudaStream_t stream) {
   if (n < 1 || n > 8 || rank < 0 || rank >= n || M_local % (2 * BM) != 0) return -6;
-  if ((lda % 8) || (ldb % 8) || (ldc % 8)) return -1;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8) || (K % 8)) return -1;
   PeerMaps pm = {};
   pm.n = n;
   pm.rows_per_rank = M_local;
-  pm.rot = rank * (M_local / (2 * BM));
+  pm.rank = rank;
+  pm.flags = flags;
+  {
+    static int idle = -1;
+    if (idle < 0) {
+      const char* e = getenv("PB_AG_IDLE_ROUNDS");
+      idle = e ? atoi(e) : 2;
+    }
+    pm.idle_rounds = idle;
+  }
   int rc;
+  if (n > 1) {
+    cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)(n * (M_local / (2 * BM))), stream);
+    if (e != cudaSuccess) return (int)e;
+  }
   for (int r = 0; r < n; ++r)
     if ((rc = pbhost::cached_tmap(&pm.m[r], a_peers[r], (uint64_t)M_local, (uint64_t)K, (uint64_t)lda, BK, BM))) return rc;
   const int M = n * M_local;
-  CUtensorMap tb, tc;
+  CUtensorMap tfull, tb, tc;
+  if ((rc = pbhost::cached_tmap(&tfull, a_full, (uint64_t)M, (uint64_t)K, (uint64_t)K, BK, BM))) return rc;
   if ((rc = pbhost::cached_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BN / 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 64, 32, 2))) return rc;
   GemmParams p{M, N, K, ldc, 0, 0, 0, 0, 1, C, nullptr, nullptr, 1, 0, 64, 0};
-  return launch<0, 0, 1, 0, 1>(pm.m[rank], tb, tc, tc, p, 0, stream, &pm);
+  return launch<0, 0, 1, 0, 1>(tfull, tb, tc, tc, p, 0, stream, &pm);
 }
 
 // GEMM ⊕ reduce-scatter:  every rank holds a K-shard (A [M, K_local], B [N, K_local]); rank r ends up with rows
@@ -620,7 +751,7 @@ PB_EXPORT int pb_gemm_reduce_scatter(const void* A, const void* B, float* const*
   PeerMaps pm = {};
   pm.n = n;
   pm.rows_per_rank = M / n;
-  pm.rot = rank * (pm.rows_per_rank / (2 * BM));
+  pm.rank = rank;
   int rc;
   for (int r = 0; r < n; ++r)
     if ((rc = pbhost::cached_tmap(&pm.m[r], c_peers[r], (uint64_t)pm.rows_per_rank, (uint64_t)N, (uint64_t)ldc, 32, 32, 4))) return rc;

@@ -25,6 +25,7 @@ EncodeFn get_encode() {
 }
 
 // rows x cols (cols contiguous) matrix with row stride ld (elements); box = box_cols x box_rows; esize 1 (fp8/bytes) | 2 (bf16) | 4 (f32)
+// esize -4: rows of `cols` uint32 words, NO swizzle (MXFP8 scale-factor atoms: 128 words = 512 bytes per row)
 static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                      uint32_t box_rows, int esize) {
   EncodeFn enc = get_encode();
@@ -37,13 +38,15 @@ static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t 
     ctx_bound = true;
   }
   cuuint64_t dims[2] = {cols, rows};
+  const bool raw = esize == -4;
+  if (raw) esize = 4;
   cuuint64_t strides[1] = {ld * (uint64_t)esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapDataType dt = esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = raw ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = enc(map, dt, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, raw ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -11 - (int)r;
 }

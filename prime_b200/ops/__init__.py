@@ -22,5 +22,6 @@ from .functional import (  # noqa: F401
     rope_qkv,
     set_gemm_pair_mode,
     set_gemm_split_k,
+    set_mxfp8_pair_mode,
     swiglu,
 )

@@ -200,6 +200,12 @@ def gemm_mxfp8(aq: torch.Tensor, asf: torch.Tensor, bq: torch.Tensor, bsf: torch
     return out
 
 
+def set_mxfp8_pair_mode(on: bool | None) -> int:
+    """Scheduler of the MXFP8 GEMM: ``False`` = one CTA per 128×192 tile, ``True`` = CTA pair (``cta_group::2``) per 256×192 tile,
+    ``None`` = re-read ``PB_MXFP8_PAIR``. Returns the previous mode."""
+    return int(_lib.load().pb_gemm_mxfp8_set_pair_mode(-1 if on is None else int(bool(on))))
+
+
 class _LinearMXFP8Fn(torch.autograd.Function):
     """y = x Wᵀ with the forward and the input-gradient GEMMs in block-scaled fp8; the weight gradient stays bf16 with fp32
     accumulation into ``main_grad`` (its contraction runs over tokens, where per-32 blocks along the token axis would need a

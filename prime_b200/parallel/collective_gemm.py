@@ -1,8 +1,10 @@
 """Fused collective ⊕ GEMM kernels over the NVLink symmetric heap — the tensor-parallel building blocks.
 
-``all_gather_gemm``      C = [A₀; A₁; …] · Bᵀ where block r of A lives on rank r. The TMA producer of the tcgen05 GEMM loads every
-                         A tile straight out of its owner's memory (own rows first), so the gather is hidden tile by tile behind
-                         the MMAs and no gathered copy of A is ever materialised (column-parallel linear on sequence-sharded input).
+``all_gather_gemm``      C = [A₀; A₁; …] · Bᵀ where block r of A lives on rank r. The first column tile of every remote row block
+                         TMA-loads its A tiles straight out of the owner's memory into the MMA ring and, as the MMAs retire them,
+                         an idle warp stores them into a local gathered copy; per-block flags then release the block's other
+                         column tiles. Every remote row crosses NVLink exactly once, hidden behind the local row blocks
+                         (column-parallel linear on sequence-sharded input). The gathered copy is a by-product (``self.gathered``).
 ``gemm_reduce_scatter``  every rank multiplies its K-shard; the GEMM epilogue TMA-reduce-adds each fp32 tile into the buffer of the
                          rank that owns those rows (row-parallel linear → sequence-sharded output).
 
@@ -31,6 +33,9 @@ class CollectiveGemm:
         self.slot = heap.alloc_flags(self.n)
         self.epoch = 0
         self.lib = heap.lib
+        self._gathered: dict[tuple[int, int], torch.Tensor] = {}
+        self._flags = torch.zeros(4096, dtype=torch.int32, device=heap.device)  # one per 256-row block (kernel zeroes what it uses)
+        self.gathered: torch.Tensor | None = None  # last all_gather_gemm's [n·M_local, K] copy (remote blocks only)
 
     def _barrier(self) -> None:
         self.epoch += 1
@@ -49,9 +54,14 @@ class CollectiveGemm:
         assert a_sym.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and b.shape[1] == K and M_local % 256 == 0
         if out is None:
             out = torch.empty((self.n * M_local, N), dtype=torch.bfloat16, device=a_sym.device)
+        assert self.n * M_local // 256 <= self._flags.numel()
+        full = self._gathered.get((M_local, K))
+        if full is None:
+            full = self._gathered[(M_local, K)] = torch.empty((self.n * M_local, K), dtype=torch.bfloat16, device=a_sym.device)
+        self.gathered = full
         self._barrier()  # every rank's block is written
-        rc = self.lib.pb_gemm_allgather(self._peer_array(a_sym), self.n, self.idx, b.data_ptr(), out.data_ptr(), M_local, N, K,
-                                        a_sym.stride(0), b.stride(0), out.stride(0), _stream())  # fmt: skip
+        rc = self.lib.pb_gemm_allgather(self._peer_array(a_sym), self.n, self.idx, b.data_ptr(), out.data_ptr(), full.data_ptr(),
+                                        self._flags.data_ptr(), M_local, N, K, a_sym.stride(0), b.stride(0), out.stride(0), _stream())  # fmt: skip
         _lib.check(rc, "pb_gemm_allgather")
         _count()
         self._barrier()  # nobody may overwrite its block while a peer is still reading it

@@ -456,8 +456,20 @@ def test_quantize_mxfp8_matches_reference(R, C, transpose):
     assert _rel_err(deq, tgt) < 0.04
 
 
+@pytest.mark.parametrize("pair", [False, True])
 @pytest.mark.parametrize("M,N,K", [(128, 192, 128), (256, 384, 512), (300, 520, 256), (1024, 2112, 1024), (4096, 3072, 2048), (136, 8, 128)])
-def test_gemm_mxfp8_matches_dequantized_reference(M, N, K):
+def test_gemm_mxfp8_matches_dequantized_reference(M, N, K, pair):
+    from prime_b200 import ops
+    from prime_b200.ops import reference as Rf
+
+    old = ops.set_mxfp8_pair_mode(pair)
+    try:
+        _check_gemm_mxfp8(M, N, K)
+    finally:
+        ops.set_mxfp8_pair_mode(None if old < 0 else bool(old))
+
+
+def _check_gemm_mxfp8(M, N, K):
     from prime_b200 import ops
     from prime_b200.ops import reference as Rf
 

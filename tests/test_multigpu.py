@@ -112,9 +112,13 @@ CG_WORKER = textwrap.dedent(
     # ---- all-gather + GEMM
     a_sym = heap.alloc(M_local * K, torch.bfloat16).view(M_local, K)
     a_sym.copy_(A_full[r * M_local:(r + 1) * M_local])
-    C = cg.all_gather_gemm(a_sym, B)
+    for _ in range(2):  # twice: flags and the gathered scratch are reusable
+        C = cg.all_gather_gemm(a_sym, B)
     ref = A_full.float() @ B.float().t()
     e_ag = float((C.float() - ref).norm() / ref.norm())
+    for o in range(n):  # by-product: the remote row blocks, copied exactly once over NVLink
+        if o != r:
+            assert torch.equal(cg.gathered[o * M_local:(o + 1) * M_local], A_full[o * M_local:(o + 1) * M_local]), "gathered copy differs"
     # ---- GEMM + reduce-scatter (K sharded)
     Kl = K // n
     M = n * M_local
