@@ -13,10 +13,10 @@
 // .32x128b.warpx4 broadcasts into the four TMEM lane quadrants. The "+1" atom of padding lets a 192-column tile that starts in
 // the middle of an atom always fetch two whole atoms.
 //
-// Tile 128 x 192 x 128(K bytes): 2 x 192 accumulator columns (double-buffered epilogue overlap) + 4 + 8 scale-factor columns fit
+// Tile 128 x 192 x 128(K bytes): 2 x 192 accumulator columns (double-buffered epilogue overlap) + 2 x (4 + 8) scale-factor columns fit
 // the 512-column TMEM; odd N tiles start 64 columns into an SFB atom, which is a +2-column offset of the SFB TMEM address.
 // Warp roles as in gemm_sm100.cu: w0 TMA producer, w1 MMA issuer (also issues the tcgen05.cp — cp and mma execute in issue
-// order, so the single SF TMEM slot is rewritten safely for the next stage), w2 TMEM alloc, w4..7 epilogue.
+// order; two alternating 12-column scale slots), w2 TMEM alloc, w4..7 epilogue.
 #include <cuda.h>
 #include <cuda_fp8.h>
 
@@ -38,8 +38,8 @@ constexpr uint32_t kSfaBytes = 512;           // one atom: 128 rows x 4 K-blocks
 constexpr uint32_t kSfbBytes = 1024;          // two atoms
 constexpr uint32_t kStagingBytes = 4 * 2 * 4096;
 constexpr int kGroupM = 16;
-constexpr uint32_t kSfaCol = kAccStages * BN;  // 384
-constexpr uint32_t kSfbCol = kSfaCol + 4;      // 388 .. 395
+constexpr uint32_t kSfaCol = kAccStages * BN;  // 384: first of two scale-factor slots
+constexpr uint32_t kSfCols = 12;               // per slot: SFA 4 columns + SFB 8 columns (two atoms)
 
 // PAIR = 0: one CTA per 128 x 192 tile. PAIR = 1 (cta_group::2): a CTA pair per 256 x 192 tile — each CTA stages its own 128 A rows,
 // HALF of B (96 rows), its own SFA atom and the whole SFB; the leader issues M = 256 block-scaled MMAs and the tcgen05.cp copies
@@ -205,25 +205,35 @@ __global__ void __launch_bounds__(kThreads, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t tsfa = tmem_base + kSfaCol;
+      uint32_t fillno = 0;
+      // The scales of a stage go into one of two 12-column TMEM slots right before its MMAs (tcgen05.cp and tcgen05.mma execute
+      // in issue order). Measured alternatives (profiles/mxfp8_gemm_bench_r1.json): copying one stage AHEAD was slower (it costs a
+      // ring stage of TMA lookahead), one slot vs two made no difference, and dropping the copies altogether gains ~15 % — the
+      // three copies per 384-clk stage occupy the tensor pipe; moving them to tcgen05.st from idle warps is the known next step.
+      auto copy_sf = [&](int st, uint32_t slot) {
+        const uint32_t ssfa = smem_u32(smem + st * kStagePitch) + kABytes + kBBytes;
+        const uint32_t ssfb = ssfa + kSfaBytes;
+        const uint32_t t = tmem_base + kSfaCol + slot * kSfCols;
+        tmem_cp_sf<PAIR>(t, ssfa);
+        tmem_cp_sf<PAIR>(t + 4, ssfb);
+        tmem_cp_sf<PAIR>(t + 8, ssfb + 512);
+      };
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         int tm, tn;
         tile_coords(tile, tiles_m, tiles_n, tm, tn);
         // odd N tiles begin 64 columns into their first SFB atom = 2 TMEM columns
-        const uint32_t tsfb = tmem_base + kSfbCol + (uint32_t)(((tn * BN) & 127) >> 5);
+        const uint32_t sfb_shift = (uint32_t)(((tn * BN) & 127) >> 5);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          copy_sf(stage, fillno & 1);
           const uint32_t sa = smem_u32(smem + stage * kStagePitch);
           const uint32_t sb = sa + kABytes;
-          const uint32_t ssfa = sb + kBBytes;
-          const uint32_t ssfb = ssfa + kSfaBytes;
-          tmem_cp_sf<PAIR>(tsfa, ssfa);
-          tmem_cp_sf<PAIR>(tmem_base + kSfbCol, ssfb);
-          tmem_cp_sf<PAIR>(tmem_base + kSfbCol + 4, ssfb + 512);
+          const uint32_t tsfa = tmem_base + kSfaCol + (fillno & 1) * kSfCols;
+          const uint32_t tsfb = tsfa + 4 + sfb_shift;
 #pragma unroll
           for (int k = 0; k < BKB / 32; ++k) {  // UMMA_K = 32 elements = 32 bytes inside the 128 B swizzle row
             const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);
@@ -233,6 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (PAIR) umma_commit_pair(&empty_bar[stage]);
           else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) stage = 0, phase ^= 1;
+          ++fillno;
         }
         if (PAIR) umma_commit_pair(&tfull_bar[acc]);
         else umma_commit(&tfull_bar[acc]);

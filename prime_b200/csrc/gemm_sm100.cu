@@ -709,8 +709,9 @@ PB_EXPORT int pb_gemm_bf16_swiglu(const void* A, const void* W13, void* gate_up,
 // rank's block written before, nobody overwrites it until all ranks are done). K-major operands, bf16 output, CTA-pair tiles.
 // a_full: local [n·M_local, K] bf16 scratch that receives the remote row blocks (by-product: the gathered A, minus the local block);
 // flags: n·M_local/256 uint32 counters in local memory (zeroed here, on the stream).
+// b_mn_major: B stored [K, N] (the transposed weight of a backward GEMM) instead of [N, K].
 PB_EXPORT int pb_gemm_allgather(const void* const* a_peers, int n, int rank, const void* B, void* C, void* a_full, uint32_t* flags,
-                                int M_local, int N, int K, int lda, int ldb, int ldc, cudaStream_t stream) {
+                                int M_local, int N, int K, int lda, int ldb, int ldc, int b_mn_major, cudaStream_t stream) {
   if (n < 1 || n > 8 || rank < 0 || rank >= n || M_local % (2 * BM) != 0) return -6;
   if ((lda % 8) || (ldb % 8) || (ldc % 8) || (K % 8)) return -1;
   PeerMaps pm = {};
@@ -736,16 +737,18 @@ PB_EXPORT int pb_gemm_allgather(const void* const* a_peers, int n, int rank, con
   const int M = n * M_local;
   CUtensorMap tfull, tb, tc;
   if ((rc = pbhost::cached_tmap(&tfull, a_full, (uint64_t)M, (uint64_t)K, (uint64_t)K, BK, BM))) return rc;
-  if ((rc = pbhost::cached_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BN / 2))) return rc;
+  if (!b_mn_major) rc = pbhost::cached_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BN / 2);
+  else rc = pbhost::cached_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
   if ((rc = pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 64, 32, 2))) return rc;
-  GemmParams p{M, N, K, ldc, 0, 0, 0, 0, 1, C, nullptr, nullptr, 1, 0, 64, 0};
-  return launch<0, 0, 1, 0, 1>(tfull, tb, tc, tc, p, 0, stream, &pm);
+  GemmParams p{M, N, K, ldc, 0, b_mn_major, 0, 0, 1, C, nullptr, nullptr, 1, 0, 64, 0};
+  return b_mn_major ? launch<0, 1, 1, 0, 1>(tfull, tb, tc, tc, p, 0, stream, &pm) : launch<0, 0, 1, 0, 1>(tfull, tb, tc, tc, p, 0, stream, &pm);
 }
 
 // GEMM ⊕ reduce-scatter:  every rank holds a K-shard (A [M, K_local], B [N, K_local]); rank r ends up with rows
 // [r·M/n, (r+1)·M/n) of Σ_ranks A·Bᵀ in its fp32 buffer c_peers[r] ([M/n, N], zeroed by the caller before the opening barrier).
 PB_EXPORT int pb_gemm_reduce_scatter(const void* A, const void* B, float* const* c_peers, int n, int rank, int M, int N, int K, int lda,
-                                     int ldb, int ldc, cudaStream_t stream) {
+                                     int ldb, int ldc, int b_mn_major, cudaStream_t stream) {
   if (n < 1 || n > 8 || rank < 0 || rank >= n || M % n != 0 || (M / n) % (2 * BM) != 0) return -6;
   if ((lda % 8) || (ldb % 8) || (ldc % 4)) return -1;
   PeerMaps pm = {};
@@ -757,7 +760,10 @@ PB_EXPORT int pb_gemm_reduce_scatter(const void* A, const void* B, float* const*
     if ((rc = pbhost::cached_tmap(&pm.m[r], c_peers[r], (uint64_t)pm.rows_per_rank, (uint64_t)N, (uint64_t)ldc, 32, 32, 4))) return rc;
   CUtensorMap ta, tb;
   if ((rc = pbhost::cached_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, BM))) return rc;
-  if ((rc = pbhost::cached_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BN / 2))) return rc;
-  GemmParams p{M, N, K, ldc, 0, 0, 1, 1, 1, c_peers[rank], nullptr, nullptr, 1, 0, 64, 0};
-  return launch<0, 0, 1, 0, 2>(ta, tb, pm.m[rank], pm.m[rank], p, 0, stream, &pm);
+  if (!b_mn_major) rc = pbhost::cached_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BN / 2);
+  else rc = pbhost::cached_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
+  GemmParams p{M, N, K, ldc, 0, b_mn_major, 1, 1, 1, c_peers[rank], nullptr, nullptr, 1, 0, 64, 0};
+  return b_mn_major ? launch<0, 1, 1, 0, 2>(ta, tb, pm.m[rank], pm.m[rank], p, 0, stream, &pm)
+                    : launch<0, 0, 1, 0, 2>(ta, tb, pm.m[rank], pm.m[rank], p, 0, stream, &pm);
 }

@@ -46,37 +46,50 @@ class CollectiveGemm:
         arr = (ctypes.c_void_p * self.n)(*[self.heap.peer_ptr(r, t) for r in self.ranks])
         return arr
 
-    def all_gather_gemm(self, a_sym: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    def all_gather_gemm(self, a_sym: torch.Tensor, b: torch.Tensor, out: torch.Tensor | None = None, *, b_mn_major: bool = False,
+                        gathered: torch.Tensor | None = None, copy_local: bool = False) -> torch.Tensor:  # fmt: skip
         """``a_sym``: this rank's [M_local, K] bf16 block, allocated with ``heap.alloc`` at the SAME offset on every rank
-        (M_local % 256 == 0); ``b``: [N, K] bf16 (local). Returns C [n·M_local, N] bf16."""
+        (M_local % 256 == 0); ``b``: [N, K] bf16 (local), or stored [K, N] with ``b_mn_major``. Returns C [n·M_local, N] bf16.
+
+        ``gathered``: caller-owned [n·M_local, K] buffer for the by-product (kept for a backward pass); with ``copy_local`` the
+        local block is copied in as well, so it ends up holding the complete gathered A."""
         M_local, K = a_sym.shape
-        N = b.shape[0]
-        assert a_sym.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and b.shape[1] == K and M_local % 256 == 0
+        N = b.shape[1] if b_mn_major else b.shape[0]
+        assert a_sym.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and b.shape[0 if b_mn_major else 1] == K and M_local % 256 == 0
+        assert a_sym.is_contiguous() and b.stride(1) == 1
         if out is None:
             out = torch.empty((self.n * M_local, N), dtype=torch.bfloat16, device=a_sym.device)
         assert self.n * M_local // 256 <= self._flags.numel()
-        full = self._gathered.get((M_local, K))
+        full = gathered
         if full is None:
-            full = self._gathered[(M_local, K)] = torch.empty((self.n * M_local, K), dtype=torch.bfloat16, device=a_sym.device)
+            full = self._gathered.get((M_local, K))
+            if full is None:
+                full = self._gathered[(M_local, K)] = torch.empty((self.n * M_local, K), dtype=torch.bfloat16, device=a_sym.device)
+        assert full.shape == (self.n * M_local, K) and full.is_contiguous() and full.dtype == torch.bfloat16
         self.gathered = full
         self._barrier()  # every rank's block is written
         rc = self.lib.pb_gemm_allgather(self._peer_array(a_sym), self.n, self.idx, b.data_ptr(), out.data_ptr(), full.data_ptr(),
-                                        self._flags.data_ptr(), M_local, N, K, a_sym.stride(0), b.stride(0), out.stride(0), _stream())  # fmt: skip
+                                        self._flags.data_ptr(), M_local, N, K, a_sym.stride(0), b.stride(0), out.stride(0),
+                                        int(b_mn_major), _stream())  # fmt: skip
         _lib.check(rc, "pb_gemm_allgather")
         _count()
+        if copy_local:
+            full[self.idx * M_local : (self.idx + 1) * M_local].copy_(a_sym)
         self._barrier()  # nobody may overwrite its block while a peer is still reading it
         return out
 
-    def gemm_reduce_scatter(self, a: torch.Tensor, b: torch.Tensor, out_sym: torch.Tensor) -> torch.Tensor:
-        """``a``: [M, K_local], ``b``: [N, K_local] (this rank's K shard, local memory); ``out_sym``: this rank's [M/n, N] fp32 buffer
-        from ``heap.alloc`` (same offset everywhere). On return it holds rows [idx·M/n, (idx+1)·M/n) of Σ_ranks a·bᵀ."""
+    def gemm_reduce_scatter(self, a: torch.Tensor, b: torch.Tensor, out_sym: torch.Tensor, *, b_mn_major: bool = False) -> torch.Tensor:
+        """``a``: [M, K_local], ``b``: [N, K_local] (or stored [K_local, N] with ``b_mn_major``) — this rank's K shard, local memory;
+        ``out_sym``: this rank's [M/n, N] fp32 buffer from ``heap.alloc`` (same offset everywhere). On return it holds rows
+        [idx·M/n, (idx+1)·M/n) of Σ_ranks a·bᵀ."""
         M, K = a.shape
-        N = b.shape[0]
+        N = b.shape[1] if b_mn_major else b.shape[0]
+        assert b.shape[0 if b_mn_major else 1] == K and a.stride(1) == 1 and b.stride(1) == 1
         assert out_sym.dtype == torch.float32 and out_sym.shape == (M // self.n, N) and (M // self.n) % 256 == 0
         out_sym.zero_()
         self._barrier()  # all output buffers are zeroed
         rc = self.lib.pb_gemm_reduce_scatter(a.data_ptr(), b.data_ptr(), self._peer_array(out_sym), self.n, self.idx, M, N, K,
-                                             a.stride(0), b.stride(0), out_sym.stride(0), _stream())  # fmt: skip
+                                             a.stride(0), b.stride(0), out_sym.stride(0), int(b_mn_major), _stream())  # fmt: skip
         _lib.check(rc, "pb_gemm_reduce_scatter")
         _count()
         self._barrier()  # every rank's contributions have landed (TMA reduce completes before the kernel retires)

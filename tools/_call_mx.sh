@@ -1,2 +1,4 @@
-timeout 400 python -m pytest tests/test_kernels_gpu.py -q -k "mxfp8 or fp8 or flash_attention" 2>&1 | tail -15
-timeout 200 python tools/mxfp8_bench.py > gpurun_out/mxfp8_bench.json 2> gpurun_out/mxfp8_bench.err; tail -3 gpurun_out/mxfp8_bench.err; head -c 1500 gpurun_out/mxfp8_bench.json
+PB_MX_DEBUG=0 timeout 300 python tools/mxfp8_bench.py 2>gpurun_out/mx.err > gpurun_out/mxfp8_bench.json; tail -2 gpurun_out/mx.err; python -c "
+import json,sys; d=json.load(open('gpurun_out/mxfp8_bench.json'))
+for r in d['rows']: print(' ', r['shape'], r['mxfp8_tflops'], r['mxfp8_single_cta_tflops'], r['bf16_tflops'])
+print(json.dumps(d['sustained_w13_shape']))"
