@@ -19,8 +19,9 @@ class PortMapping(ApiModel):
 
 
 class _Connectable(ApiModel):
-    ssh_connection: str | list[str] | None = None
-    ip: str | list[str] | None = None
+    # multi-node pods report one entry per node; nodes that are still provisioning come back as null
+    ssh_connection: str | list[str | None] | None = None
+    ip: str | list[str | None] | None = None
 
     @field_validator("ssh_connection", "ip", mode="before")
     @classmethod
