@@ -24,6 +24,9 @@ namespace {
 
 constexpr int kThreads = 384;  // w0 TMA · w1 MMA · w2 TMEM alloc · w3 idle · w4..7 math group 0 (even tiles) · w8..11 math group 1 (odd tiles)
 
+__device__ __forceinline__ void ld_shared_f4(uint32_t saddr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(saddr));
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -31,8 +34,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 __global__ void __launch_bounds__(256) bwd_delta_kernel(const pb::bf16x8* __restrict__ dout, const pb::bf16x8* __restrict__ out,
-                                                        float* __restrict__ delta, int64_t tokens, int S, int H, int vec_per_head) {
-  // one warp per (token, head)
+                                                        float* __restrict__ delta, int64_t tokens, int S, int H, int vec_per_head,
+                                                        float scale) {
+  // one warp per (token, head); writes delta·scale (the only form the two kernels below use)
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= tokens * H) return;
@@ -51,13 +55,13 @@ __global__ void __launch_bounds__(256) bwd_delta_kernel(const pb::bf16x8* __rest
   if (lane == 0) {
     const int64_t bidx = tok / S;
     const int s = (int)(tok - bidx * S);
-    delta[(bidx * H + h) * S + s] = acc;
+    delta[(bidx * H + h) * S + s] = acc * scale;
   }
 }
 
 struct BwdParams {
   const float* lse2;
-  const float* delta;
+  const float* delta;  // rowsum(dO∘O) · scale
   int B, S, H, Hkv;
   float scale, scale_log2;
   int causal;
@@ -122,35 +126,39 @@ __device__ __forceinline__ void store_row_chunk_packed(uint32_t block_base, int 
 }
 
 // ----------------------------------------------------------------------------------------------------- dK / dV
-template <int D>
+template <int D, int PST>
 struct DkvCfg {
   static constexpr int kChunks = D / 64;
   static constexpr uint32_t kKVBytes = 128 * D * 2;           // resident K or V (128 rows)
   static constexpr uint32_t kQBytes = 64 * D * 2;             // one Q or dO tile (64 rows)
   static constexpr uint32_t kPBytes = 128 * 128;              // Pᵀ or dSᵀ : [128 kv rows x 64 q]
   static constexpr uint32_t kOffV = kKVBytes;
-  // Q/dO ring of 4: a slot is held from its TMA load (≈2600 clk to land, measured) until dV/dK of its tile retire, and S/dP are
-  // issued TWO tiles ahead, so tiles it, it+1 (in the math groups), it+2 (S/dP issued) and it+3 (loading) are all resident. The
-  // 32 KB for the 4th slot come from single-buffering Pᵀ/dSᵀ: a math group packs its tile in registers and only waits for the
-  // previous tile's dV/dK MMAs right before storing (they retired long ago unless the groups have drifted together).
-  static constexpr int kQStages = 4;
+  // Smem budget (224 KB of operands): K,V 64 KB + Q/dO ring kQStages x 32 KB + Pᵀ/dSᵀ kPStages x 32 KB. Two variants, A/B-tested
+  // (PB_ATTN_BWD_PSTAGES): 4 input stages + ONE Pᵀ/dSᵀ buffer (a math group waits for the previous tile's dV/dK MMAs right before
+  // storing) — best while the math phase was the bottleneck; or 3 input stages + TWO buffers (a group only waits for its own
+  // tile of two iterations ago), which takes the dV/dK MMAs of the other group's tile off the store's critical path.
+  static constexpr int kPStages = PST;
+  static constexpr int kQStages = PST == 2 ? 3 : 4;
   static constexpr uint32_t kOffQ = 2 * kKVBytes;
   static constexpr uint32_t kOffdO = kOffQ + kQStages * kQBytes;
   static constexpr uint32_t kOffP = kOffdO + kQStages * kQBytes;
-  static constexpr uint32_t kOffdS = kOffP + kPBytes;
-  static constexpr uint32_t kOffBar = kOffdS + kPBytes;
-  static constexpr uint32_t kSmem = kOffBar + 256 + 1024;
+  static constexpr uint32_t kOffdS = kOffP + kPStages * kPBytes;
+  static constexpr uint32_t kOffBar = kOffdS + kPStages * kPBytes;
+  // per-query lse / delta·scale of the current and the next tile of each math group: [group][slot][lse 64 | delta 64] fp32
+  static constexpr uint32_t kOffAux = kOffBar + 256;
+  static constexpr uint32_t kSmem = kOffAux + 2 * 2 * 512;  // the dynamic smem base is declared 1024-aligned (checked at entry)
   static constexpr uint32_t tS = 0, tdP = 128, tdV = 256, tdK = 256 + D;
 };
 
-template <int D>
+template <int D, int PST>
 __global__ void __launch_bounds__(kThreads, 1)
     bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __grid_constant__ CUtensorMap tmap_qkv64,
                     const __grid_constant__ CUtensorMap tmap_do64, const __grid_constant__ CUtensorMap tmap_dqkv,
                     const BwdParams p) {
-  using C = DkvCfg<D>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using C = DkvCfg<D, PST>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if (smem_u32(smem_raw) & 1023) __trap();  // SWIZZLE_128B tiles need it and there is no slack left to realign by hand
+  uint8_t* smem = smem_raw;
   uint8_t* sK = smem;
   uint8_t* sV = smem + C::kOffV;
   uint8_t* sQ = smem + C::kOffQ;
@@ -165,7 +173,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* s_empty = bars + 11;   // 2 (4 warps)
   uint64_t* p_full = bars + 13;    // 2 (4 warps)
   uint64_t* acc_done = bars + 15;  // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* all_done = bars + 17;  // 1: every dV/dK MMA of this block has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jb = blockIdx.x;  // KV block (128 rows)
@@ -186,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
+    mbar_init(all_done, 1);
     for (int i = 0; i < C::kQStages; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
@@ -297,7 +307,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         trace_ev(p, 1, tr_n, 3, it);  // Pᵀ/dSᵀ ready → issue dV, dK
         tc_fence_after();
         const int qs = it % C::kQStages;
-        const uint32_t pa = smem_u32(sP), da = smem_u32(sdS);  // single-buffered: see DkvCfg
+        const uint32_t pbuf = PST == 2 ? (uint32_t)st * C::kPBytes : 0u;  // see DkvCfg
+        const uint32_t pa = smem_u32(sP) + pbuf, da = smem_u32(sdS) + pbuf;
         const uint32_t q0 = smem_u32(sQ + qs * C::kQBytes), d0 = smem_u32(sdO + qs * C::kQBytes);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)  // K = 64 query rows
@@ -310,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         umma_commit(&q_empty[qs]);
         umma_commit(&acc_done[st]);
       }
+      umma_commit(all_done);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax-backward math + epilogue
@@ -317,27 +329,32 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int half = (warp - 4) >> 2;  // math group: owns the tiles of this parity and, in the epilogue, dV (0) or dK (1)
     const int r = q * 32 + lane;       // KV row in the block == TMEM lane
     const int kv_idx = jb * 128 + r;   // position in the sequence
+    const int kv_warp_min = jb * 128 + q * 32;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     // Two math groups leapfrog over the tiles (group g owns the tiles — and therefore the S/dP TMEM stage and the Pᵀ/dSᵀ smem
     // stage — of parity g). TMEM can only be read at 64 B/clk per SM, so one group's 64 KB of S/dP loads overlap the other
     // group's exp2/FMA/pack/st.shared phase instead of every warp queueing on the same resource at the same time.
     int tr_n = 0;
+    // lse and delta·scale are per QUERY, i.e. per register column of this kv-row-per-thread layout: 128 warp-uniform values per
+    // tile. As 32 LDG.128 in the math phase they were its critical path (ncu source view: the first FFMA/FMUL after each load
+    // carried the stall samples; with the smem carve-out at 224 KB the loads mostly miss L1). Now warp 0 of the group copies
+    // the NEXT tile's 512 bytes global → smem with one cp.async per lane while the current tile is being processed, and the
+    // math phase reads them back as broadcast LDS.128 (29 clk).
+    const uint32_t aux_base = smem_u32(smem + C::kOffAux) + (uint32_t)half * 1024u;
+    auto stage_aux = [&](int itn, uint32_t slot) {
+      const int hn = hk * group + itn / tiles_per_head;
+      const int64_t off = ((int64_t)(b * p.H + hn)) * p.S + (it0 + itn % tiles_per_head) * 64 + (lane & 15) * 4;
+      const float* src = (lane & 16) ? p.delta + off : p.lse2 + off;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(aux_base + slot * 512u + (uint32_t)lane * 16u), "l"(src) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (q == 0 && half < n_it) stage_aux(half, 0u);
     for (int it = half; it < n_it; it += 2) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int h = hk * group + it / tiles_per_head;
       const int qpos0 = (it0 + it % tiles_per_head) * 64;
-      const float* lse_row = p.lse2 + ((int64_t)(b * p.H + h)) * p.S + qpos0;
-      const float* del_row = p.delta + ((int64_t)(b * p.H + h)) * p.S + qpos0;
-      if (it + 2 < n_it && lane < 4) {
-        // this group's NEXT tile: pull its 64 lse and 64 delta values (4 cache lines) into L1 now, so the 32 warp-uniform
-        // 128-bit loads in the math phase hit L1 instead of exposing an L2 round trip each
-        const int nx = it + 2;
-        const int hn = hk * group + nx / tiles_per_head;
-        const int64_t off = ((int64_t)(b * p.H + hn)) * p.S + (it0 + nx % tiles_per_head) * 64 + (lane & 1) * 32;
-        const float* a = (lane & 2) ? p.delta + off : p.lse2 + off;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-      }
+      const uint32_t aux = aux_base + (uint32_t)(((it - half) >> 1) & 1) * 512u;
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 1, it);  // start waiting for S/dP
       mbar_wait(&s_full[st], ph);
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 2, it);  // S/dP ready
@@ -350,8 +367,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         tmem_ld_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
         tmem_ld_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[c * 32]));
       }
-      const float4* lse4 = reinterpret_cast<const float4*>(lse_row);
-      const float4* del4 = reinterpret_cast<const float4*>(del_row);
+      // group rendezvous (named barrier 1 + group, 128 threads): every warp has finished reading the other slot (tile it-2),
+      // and warp 0's copy of THIS tile's values — issued a whole tile ago — is complete and visible
+      if (q == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+      if (q == 0 && it + 2 < n_it) stage_aux(it + 2, (uint32_t)((((it - half) >> 1) + 1) & 1));
       tmem_ld_wait();
       // S/dP of this stage now live in registers → the MMA warp may overwrite the stage with tile it+2
       tc_fence_before();
@@ -363,32 +383,54 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto tile_math = [&](auto masked) {
 #pragma unroll
         for (int j4 = 0; j4 < 16; ++j4) {
-          const float4 L = __ldg(lse4 + j4), Dl = __ldg(del4 + j4);
-          const float ls[4] = {L.x, L.y, L.z, L.w}, dl[4] = {Dl.x * p.scale, Dl.y * p.scale, Dl.z * p.scale, Dl.w * p.scale};
-          float pv[4], dsv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int qc = j4 * 4 + e;
-            pv[e] = fast_exp2(fmaf(__uint_as_float(sv[qc]), p.scale_log2, -ls[e]));
-            if (decltype(masked)::value && kv_idx > qpos0 + qc) pv[e] = 0.f;
-            dsv[e] = pv[e] * fmaf(__uint_as_float(dv[qc]), p.scale, -dl[e]);
+          // diagonal tiles: per 4-column group the warp's 32 kv rows are either all masked (nothing to compute), all visible
+          // (common path) or cut by the diagonal (per-element select) — warp-uniform branches
+          bool cut = false;
+          if (decltype(masked)::value) {
+            const int qa = qpos0 + j4 * 4;
+            if (kv_warp_min > qa + 3) {
+              pk[2 * j4] = pk[2 * j4 + 1] = dk[2 * j4] = dk[2 * j4 + 1] = 0u;
+              continue;
+            }
+            cut = kv_warp_min + 31 > qa;
           }
-          pk[2 * j4] = pack_bf16x2(__float_as_uint(pv[0]), __float_as_uint(pv[1]));
-          pk[2 * j4 + 1] = pack_bf16x2(__float_as_uint(pv[2]), __float_as_uint(pv[3]));
-          dk[2 * j4] = pack_bf16x2(__float_as_uint(dsv[0]), __float_as_uint(dsv[1]));
-          dk[2 * j4 + 1] = pack_bf16x2(__float_as_uint(dsv[2]), __float_as_uint(dsv[3]));
+          float ls[4], dl[4];
+          ld_shared_f4(aux + j4 * 16, ls);
+          ld_shared_f4(aux + 256 + j4 * 16, dl);
+          auto group4 = [&](auto cut_here) {
+            float pv[4], dsv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int qc = j4 * 4 + e;
+              pv[e] = fast_exp2(fmaf(__uint_as_float(sv[qc]), p.scale_log2, -ls[e]));
+              if (decltype(cut_here)::value && kv_idx > qpos0 + qc) pv[e] = 0.f;
+              dsv[e] = pv[e] * fmaf(__uint_as_float(dv[qc]), p.scale, -dl[e]);
+            }
+            pk[2 * j4] = pack_bf16x2(__float_as_uint(pv[0]), __float_as_uint(pv[1]));
+            pk[2 * j4 + 1] = pack_bf16x2(__float_as_uint(pv[2]), __float_as_uint(pv[3]));
+            dk[2 * j4] = pack_bf16x2(__float_as_uint(dsv[0]), __float_as_uint(dsv[1]));
+            dk[2 * j4 + 1] = pack_bf16x2(__float_as_uint(dsv[2]), __float_as_uint(dsv[3]));
+          };
+          if (decltype(masked)::value && cut) group4(std::true_type{});
+          else group4(std::false_type{});
         }
       };
       if (need_mask) tile_math(std::true_type{});
       else tile_math(std::false_type{});
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 6, it);  // math done (registers hold the packed tile)
-      // the single Pᵀ/dSᵀ buffer was last read by dV/dK of the previous tile (the other group's)
-      if (it >= 1) mbar_wait(&acc_done[(it - 1) & 1], ((it - 1) >> 1) & 1);
+      // one buffer: it was last read by dV/dK of the previous tile (the other group's); two buffers: by this group's own
+      // tile of two iterations ago
+      if (PST == 2) {
+        if (it >= 2) mbar_wait(&acc_done[st], ph ^ 1);
+      } else if (it >= 1) {
+        mbar_wait(&acc_done[(it - 1) & 1], ((it - 1) >> 1) & 1);
+      }
+      const uint32_t pbuf = PST == 2 ? (uint32_t)st * C::kPBytes : 0u;
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 4, it);  // P/dS buffer free
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        store_row_chunk_packed(smem_u32(sP), r, c, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
-        store_row_chunk_packed(smem_u32(sdS), r, c, *reinterpret_cast<uint32_t(*)[16]>(&dk[c * 16]));
+        store_row_chunk_packed(smem_u32(sP) + pbuf, r, c, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
+        store_row_chunk_packed(smem_u32(sdS) + pbuf, r, c, *reinterpret_cast<uint32_t(*)[16]>(&dk[c * 16]));
       }
       fence_proxy_async();
       __syncwarp();
@@ -396,9 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 5, it);  // math + stores done
     }
     // epilogue: dV, dK → bf16 → staging (the Pᵀ/dSᵀ region, 64 KB) → TMA stores into dqkv
-    const int tl = n_it - 1;
-    mbar_wait(&acc_done[tl & 1], (tl >> 1) & 1);
-    if (n_it >= 2) mbar_wait(&acc_done[(tl - 1) & 1], ((tl - 1) >> 1) & 1);
+    mbar_wait(all_done, 0);  // committed after the last tile's MMAs (parity waits on the per-stage barriers can alias, see bwd_dq)
     tc_fence_after();
     uint8_t* stage = sQ;  // the Q/dO rings are idle now: [which(dV,dK)][chunk c] blocks of [128 rows x 128 B]
     {
@@ -458,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                   const __grid_constant__ CUtensorMap tmap_do128, const __grid_constant__ CUtensorMap tmap_dqkv,
                   const BwdParams p) {
   using C = DqCfg<D>;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + C::kOffdO;
@@ -605,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int q_idx = qb * 128 + r;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float lse = p.lse2[((int64_t)bh) * p.S + q_idx];
-    const float del_s = p.delta[((int64_t)bh) * p.S + q_idx] * p.scale;
+    const float del_s = p.delta[((int64_t)bh) * p.S + q_idx];
     for (int t = half; t < n_kv; t += 2) {  // the two math groups leapfrog over the kv tiles (see the dK/dV kernel)
       const int st = t & 1;
       const uint32_t ph = (t >> 1) & 1;
@@ -697,7 +737,9 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
                int H, int Hkv, float scale, int causal, const float* rope_cos, const float* rope_sin, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(bwd_dkdv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DkvCfg<D>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(bwd_dkdv_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DkvCfg<D, 1>::kSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(bwd_dkdv_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DkvCfg<D, 2>::kSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DqCfg<D>::kSmem);
     if (e != cudaSuccess) return (int)e;
@@ -708,7 +750,7 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
     const int64_t warps = (int64_t)rows * H;
     const int64_t blocks = (warps * 32 + 255) / 256;
     bwd_delta_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const pb::bf16x8*)dout, (const pb::bf16x8*)out, delta, (int64_t)rows, S,
-                                                          H, D / 8);
+                                                          H, D / 8, scale);
   }
   CUtensorMap tq128, tq64, tdo64, tdo128, tdq;
   int rc;
@@ -718,7 +760,13 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   if ((rc = pbhost::cached_tmap(&tdo128, dout, rows, wo, wo, 64, 128, 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tdq, dqkv, rows, wqkv, wqkv, 64, 32, 2))) return rc;
   BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace, rope_cos, rope_sin};
-  bwd_dkdv_kernel<D><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
+  static int pstages = 0;
+  if (pstages == 0) {
+    const char* ev = getenv("PB_ATTN_BWD_PSTAGES");
+    pstages = (ev && atoi(ev) == 1) ? 1 : 2;
+  }
+  if (pstages == 2) bwd_dkdv_kernel<D, 2><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 2>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
+  else bwd_dkdv_kernel<D, 1><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 1>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
   bwd_dq_kernel<D><<<dim3(S / 128, B * H), kThreads, DqCfg<D>::kSmem, stream>>>(tq128, tq64, tdo128, tdq, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
