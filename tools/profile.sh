@@ -8,8 +8,11 @@ $NCU --import-source on -k regex:gemm_bf16_kernel -s 30 -c 2 -o gpurun_out/ncu/g
 $NCU --import-source on -k regex:'flash_fwd_kernel|bwd_dkdv_kernel|bwd_dq_kernel|bwd_delta_kernel' -s 16 -c 4 -o gpurun_out/ncu/attn -f python tools/attn_bench.py > gpurun_out/ncu/attn.log 2>&1
 $NCU -k regex:'rmsnorm|rope|swiglu|cross_entropy|colsum|grad_reduce|norm_publish|adamw_push|pseudograd|outer_nesterov|cast_push' -c 40 -o gpurun_out/ncu/ops -f \
     python tools/op_bench.py --once > gpurun_out/ncu/ops.log 2>&1
-for r in gemm attn ops; do
+$NCU --import-source on -k regex:'gemm_mxfp8_kernel|quantize_mxfp8' -s 6 -c 4 -o gpurun_out/ncu/mxfp8 -f python tools/mxfp8_bench.py > gpurun_out/ncu/mxfp8.log 2>&1
+for r in gemm attn ops mxfp8; do
   ncu -i gpurun_out/ncu/$r.ncu-rep --page raw --csv > gpurun_out/ncu/$r.raw.csv 2>/dev/null
+  # per-instruction stall samples of the tensor-core kernels (read with tools/ncu_source_hotspots.py)
+  if [ "$r" = attn ] || [ "$r" = mxfp8 ]; then ncu -i gpurun_out/ncu/$r.ncu-rep --page source --csv > gpurun_out/ncu/$r.source.csv 2>/dev/null; fi
   sz=$(stat -c %s gpurun_out/ncu/$r.ncu-rep 2>/dev/null || echo 0)
   if [ "$sz" -gt 12000000 ]; then rm -f gpurun_out/ncu/$r.ncu-rep; echo "dropped $r.ncu-rep ($sz bytes), kept CSV"; fi
 done
