@@ -137,8 +137,11 @@ struct DkvCfg {
   // (PB_ATTN_BWD_PSTAGES): 4 input stages + ONE Pᵀ/dSᵀ buffer (a math group waits for the previous tile's dV/dK MMAs right before
   // storing) — best while the math phase was the bottleneck; or 3 input stages + TWO buffers (a group only waits for its own
   // tile of two iterations ago), which takes the dV/dK MMAs of the other group's tile off the store's critical path.
+  //   PST = 0: Pᵀ/dSᵀ never touch shared memory — the math warps write them (bf16, tcgen05.st) over the S/dP columns they have
+  //   just read, and dV/dK take their A operand from TMEM (tcgen05.mma with [tmem] A). The 64 KB go to a 5-deep input ring,
+  //   the st.shared + proxy fence disappear, but S/dP of tile it+2 can only be issued behind dV/dK of tile it (same columns).
   static constexpr int kPStages = PST;
-  static constexpr int kQStages = PST == 2 ? 3 : 4;
+  static constexpr int kQStages = PST == 0 ? 5 : PST == 2 ? 3 : 4;
   static constexpr uint32_t kOffQ = 2 * kKVBytes;
   static constexpr uint32_t kOffdO = kOffQ + kQStages * kQBytes;
   static constexpr uint32_t kOffP = kOffdO + kQStages * kQBytes;
@@ -167,14 +170,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* sdS = smem + C::kOffdS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
   uint64_t* kv_full = bars;        // 1
-  uint64_t* q_full = bars + 1;     // 4
-  uint64_t* q_empty = bars + 5;    // 4
-  uint64_t* s_full = bars + 9;     // 2
-  uint64_t* s_empty = bars + 11;   // 2 (4 warps)
-  uint64_t* p_full = bars + 13;    // 2 (4 warps)
-  uint64_t* acc_done = bars + 15;  // 2
-  uint64_t* all_done = bars + 17;  // 1: every dV/dK MMA of this block has retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* q_full = bars + 1;     // up to 5
+  uint64_t* q_empty = bars + 6;    // up to 5
+  uint64_t* s_full = bars + 11;    // 2
+  uint64_t* s_empty = bars + 13;   // 2 (4 warps)
+  uint64_t* p_full = bars + 15;    // 2 (4 warps)
+  uint64_t* acc_done = bars + 17;  // 2
+  uint64_t* all_done = bars + 19;  // 1: every dV/dK MMA of this block has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jb = blockIdx.x;  // KV block (128 rows)
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int qs = it % C::kQStages;
         mbar_wait(&q_full[qs], (it / C::kQStages) & 1);
         trace_ev(p, 1, tr_n, 1, it);  // Q/dO landed
-        mbar_wait(&s_empty[st], ph ^ 1);
+        if (PST != 0) mbar_wait(&s_empty[st], ph ^ 1);  // PST = 0: program order (issued behind dV/dK of tile it-2) is the guarantee
         trace_ev(p, 1, tr_n, 2, it);  // S/dP stage free → issue S, dP
         tc_fence_after();
         const uint32_t k0 = smem_u32(sK), v0 = smem_u32(sV);
@@ -291,6 +294,30 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto sd_ready = [&](int it) {  // can S/dP of tile `it` be issued without blocking?
         return mbar_test_wait(&q_full[it % C::kQStages], (it / C::kQStages) & 1) && mbar_test_wait(&s_empty[it & 1], ((it >> 1) & 1) ^ 1);
       };
+      if (PST == 0) {
+        // Pᵀ/dSᵀ live in TMEM on top of S/dP of their own stage: S/dP(it+2) must follow dV/dK(it) in the (in-order) tensor pipe
+        issue_sd(0);
+        if (n_it > 1) issue_sd(1);
+        for (int it = 0; it < n_it; ++it) {
+          const int st = it & 1;
+          mbar_wait(&p_full[st], (it >> 1) & 1);
+          trace_ev(p, 1, tr_n, 3, it);
+          tc_fence_after();
+          const int qs = it % C::kQStages;
+          const uint32_t q0 = smem_u32(sQ + qs * C::kQBytes), d0 = smem_u32(sdO + qs * C::kQBytes);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)  // K = 64 query rows = 8 TMEM columns of packed bf16 pairs per step
+            umma_bf16_ts(tmem_base + C::tdV, tmem_base + C::tS + st * 64 + kk * 8, make_smem_desc(d0 + kk * 2048, 64 * 128, 1024), idesc_a,
+                         (it | kk) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ts(tmem_base + C::tdK, tmem_base + C::tdP + st * 64 + kk * 8, make_smem_desc(q0 + kk * 2048, 64 * 128, 1024), idesc_a,
+                         (it | kk) != 0 ? 1u : 0u);
+          umma_commit(&q_empty[qs]);
+          if (it + 2 < n_it) issue_sd(it + 2);
+        }
+        umma_commit(all_done);
+      } else {
       issue_sd(0);
       int sd_next = 1;  // next tile whose S/dP has not been issued
       for (int it = 0; it < n_it; ++it) {
@@ -322,6 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         umma_commit(&acc_done[st]);
       }
       umma_commit(all_done);
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax-backward math + epilogue
@@ -376,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       // S/dP of this stage now live in registers → the MMA warp may overwrite the stage with tile it+2
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (PST != 0 && lane == 0) mbar_arrive(&s_empty[st]);
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 3, it);  // TMEM loads done
       // only the (at most two) diagonal tiles need the causal mask: keep the per-element compare/select out of the common path
       uint32_t pk[32], dk[32];  // Pᵀ and dSᵀ rows of this thread, packed bf16x2
@@ -418,6 +446,18 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (need_mask) tile_math(std::true_type{});
       else tile_math(std::false_type{});
       if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 6, it);  // math done (registers hold the packed tile)
+      if (PST == 0) {
+        // overwrite the S / dP columns of this stage (already in registers) with the packed bf16 rows: the A operands of dV / dK
+        if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 4, it);
+        tmem_st_32x32b_x32(tmem_base + C::tS + st * 64 + lane_addr, pk);
+        tmem_st_32x32b_x32(tmem_base + C::tdP + st * 64 + lane_addr, dk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[st]);
+        if (q == 0 && lane == 0) trace_ev(p, 2 + half, tr_n, 5, it);
+        continue;
+      }
       // one buffer: it was last read by dV/dK of the previous tile (the other group's); two buffers: by this group's own
       // tile of two iterations ago
       if (PST == 2) {
@@ -731,6 +771,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 unsigned long long* g_bwd_trace = nullptr;
+int g_bwd_pstages = -1;  // dK/dV kernel variant: 2 (default) | 1 | 0 = Pᵀ/dSᵀ in TMEM (see DkvCfg); -1 = read PB_ATTN_BWD_PSTAGES
 
 template <int D>
 int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv, int B, int S,
@@ -740,6 +781,8 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
     cudaError_t e = cudaFuncSetAttribute(bwd_dkdv_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DkvCfg<D, 1>::kSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(bwd_dkdv_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DkvCfg<D, 2>::kSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(bwd_dkdv_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DkvCfg<D, 0>::kSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DqCfg<D>::kSmem);
     if (e != cudaSuccess) return (int)e;
@@ -760,12 +803,14 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   if ((rc = pbhost::cached_tmap(&tdo128, dout, rows, wo, wo, 64, 128, 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tdq, dqkv, rows, wqkv, wqkv, 64, 32, 2))) return rc;
   BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace, rope_cos, rope_sin};
-  static int pstages = 0;
-  if (pstages == 0) {
+  if (g_bwd_pstages < 0) {
     const char* ev = getenv("PB_ATTN_BWD_PSTAGES");
-    pstages = (ev && atoi(ev) == 1) ? 1 : 2;
+    g_bwd_pstages = ev ? atoi(ev) : 2;
+    if (g_bwd_pstages < 0 || g_bwd_pstages > 2) g_bwd_pstages = 2;
   }
-  if (pstages == 2) bwd_dkdv_kernel<D, 2><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 2>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
+  const int pstages = g_bwd_pstages;
+  if (pstages == 0) bwd_dkdv_kernel<D, 0><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 0>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
+  else if (pstages == 2) bwd_dkdv_kernel<D, 2><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 2>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
   else bwd_dkdv_kernel<D, 1><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 1>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
   bwd_dq_kernel<D><<<dim3(S / 128, B * H), kThreads, DqCfg<D>::kSmem, stream>>>(tq128, tq64, tdo128, tdq, p);
   cudaError_t e = cudaGetLastError();
@@ -776,6 +821,14 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
 
 // Device buffer of 4 roles x 256 events x 3 u64 that CTA (0,0) of the dK/dV kernel fills (nullptr = tracing off).
 PB_EXPORT void pb_flash_attn_bwd_set_trace(unsigned long long* buf) { g_bwd_trace = buf; }
+
+// dK/dV kernel variant (see DkvCfg): 2 = two smem Pᵀ/dSᵀ buffers + 3-deep input ring (default), 1 = one buffer + 4-deep ring,
+// 0 = Pᵀ/dSᵀ in TMEM as the A operand of tcgen05.mma + 5-deep ring, -1 = re-read PB_ATTN_BWD_PSTAGES. Returns the old value.
+PB_EXPORT int pb_flash_attn_bwd_set_variant(int v) {
+  const int old = g_bwd_pstages;
+  g_bwd_pstages = v;
+  return old;
+}
 
 // delta: [B, H, S] fp32 scratch.  dqkv: [B, S, (H+2Hkv)·D] bf16, fully overwritten.
 PB_EXPORT int pb_flash_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse2, float* delta, void* dqkv,

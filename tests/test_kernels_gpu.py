@@ -312,6 +312,20 @@ def test_flash_attention_fwd_bwd(B, S, H, Hkv, D, causal):
     assert _rel_err(g[:, :, H + Hkv :], gr[:, :, H + Hkv :]) < 3e-2, "dV"
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("B,S,H,Hkv,D", [(1, 512, 4, 2, 128), (2, 384, 8, 8, 64)])
+def test_flash_attention_bwd_dkdv_variants(B, S, H, Hkv, D, variant):
+    """The three dK/dV pipelines (two / one shared-memory P buffers, or P and dS as TMEM operands of tcgen05.mma) agree."""
+    from prime_b200.ops import _lib
+
+    lib = _lib.load()
+    old = lib.pb_flash_attn_bwd_set_variant(variant)
+    try:
+        test_flash_attention_fwd_bwd(B, S, H, Hkv, D, True)
+    finally:
+        lib.pb_flash_attn_bwd_set_variant(old)
+
+
 @pytest.mark.parametrize("H,Hkv,D", [(4, 4, 128), (8, 2, 64)])
 def test_rope_attention_fused_node_matches_reference(H, Hkv, D):
     """RoPE ⊕ flash attention as one autograd node (in-place rotation, in-place inverse rotation of its own dQKV)."""
