@@ -312,6 +312,20 @@ def test_flash_attention_fwd_bwd(B, S, H, Hkv, D, causal):
     assert _rel_err(g[:, :, H + Hkv :], gr[:, :, H + Hkv :]) < 3e-2, "dV"
 
 
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("B,S,H,Hkv,D", [(2, 256, 4, 4, 128), (1, 512, 4, 2, 128), (1, 1024, 2, 2, 128), (3, 768, 2, 1, 128)])
+def test_flash_attention_fwd_two_tile_kernel(B, S, H, Hkv, D, causal):
+    """Second-generation forward (two query tiles per CTA, P as a TMEM operand) against the same fp32 reference."""
+    from prime_b200.ops import _lib
+
+    lib = _lib.load()
+    old = lib.pb_flash_attn_fwd_set_variant(2)
+    try:
+        test_flash_attention_fwd_bwd(B, S, H, Hkv, D, causal)
+    finally:
+        lib.pb_flash_attn_fwd_set_variant(old)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("B,S,H,Hkv,D", [(1, 512, 4, 2, 128), (2, 384, 8, 8, 64)])
 def test_flash_attention_bwd_dkdv_variants(B, S, H, Hkv, D, variant):

@@ -1,7 +1,6 @@
-for ps in 0 2; do
-echo "PSTAGES=$ps"
-PB_ATTN_BWD_PSTAGES=$ps timeout 300 python -m pytest tests/test_kernels_gpu.py -q -x -k "flash_attention or rope_attention or qkv_gemm_rope" 2>&1 | tail -6 | cut -c1-250
-PB_ATTN_BWD_PSTAGES=$ps timeout 200 python tools/attn_bench.py 2>/dev/null | tee gpurun_out/attn_bench_v7_ps$ps.json | cut -c1-330
-PB_ATTN_BWD_PSTAGES=$ps timeout 100 python tools/attn_trace.py > gpurun_out/attn_trace_v7_ps$ps.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/attn_trace_v7_ps$ps.json')); print('cycles_per_tile', d['cycles_per_tile']); print([ (t['wait_for_S'], t['tmem_load'], t['math'], t['wait_p_buffer'], t['math_store']) for t in d['per_tile'][2:8]])"
-done
+mkdir -p gpurun_out/ncu
+ncu --set full --clock-control none --import-source on -k regex:flash_fwd2_kernel -s 3 -c 1 -o gpurun_out/ncu/fwd2 -f python tools/attn_bench.py > gpurun_out/ncu/fwd2.log 2>&1
+ncu -i gpurun_out/ncu/fwd2.ncu-rep --page source --csv > gpurun_out/ncu/fwd2.source.csv 2>/dev/null
+ncu -i gpurun_out/ncu/fwd2.ncu-rep --page raw --csv > gpurun_out/ncu/fwd2.raw.csv 2>/dev/null
+python tools/ncu_source_hotspots.py gpurun_out/ncu/fwd2.source.csv 25 | tee gpurun_out/fwd2_hotspots.txt | head -60
+rm -f gpurun_out/ncu/fwd2.ncu-rep
