@@ -22,15 +22,19 @@ using namespace tc;
 
 namespace {
 
-constexpr int BQ = 128, BKV = 128, D = 128;
+constexpr int BQ = 128, D = 128;
 constexpr int kThreads = 352;
 constexpr float kRescaleThreshold = 8.f;  // log2 units
-constexpr uint32_t kTileBytes = 128 * D * 2;            // one Q / K / V tile: 32 KB as [2 column chunks][128 rows x 128 B]
+constexpr uint32_t kTileBytes = 128 * D * 2;            // one Q tile: 32 KB as [2 column chunks][128 rows x 128 B]
 constexpr uint32_t kOffK = 2 * kTileBytes;
-constexpr uint32_t kOffV = kOffK + 2 * kTileBytes;
-constexpr uint32_t kOffStage = kOffV + 2 * kTileBytes;  // per group: [128 rows x 128 B] output staging for one 64-column chunk
+constexpr uint32_t kRingBytes = 2 * kTileBytes;         // 64 KB per K ring and per V ring
+constexpr uint32_t kOffV = kOffK + kRingBytes;
+constexpr uint32_t kOffStage = kOffV + kRingBytes;      // per group: [128 rows x 128 B] output staging for one 64-column chunk
 constexpr uint32_t kOffBar = kOffStage + 2 * 16384;
 constexpr uint32_t kSmem = kOffBar + 256;
+// BKV = key tile. 128: one S buffer per group, QKᵀ(t+1) can only follow P·V(t) (P aliases S) — the softmax warps then wait for S a
+// quarter of the time (ncu source view). 64: the group's 128 S columns hold TWO buffers, QKᵀ(t+1) runs while softmax(t) is busy,
+// and the same 64 KB rings hold four 16 KB stages each.
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -53,26 +57,32 @@ struct Fwd2Params {
   int causal;
 };
 
+template <int BKV>
 __global__ void __launch_bounds__(kThreads, 1)
-    flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_o, const Fwd2Params p) {
+    flash_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_kv,
+                      const __grid_constant__ CUtensorMap tmap_o, const Fwd2Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operands need 1024-byte aligned tiles
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kOffK;
   uint8_t* sV = smem + kOffV;
+  constexpr int NSB = 128 / BKV;                        // S buffers per group
+  constexpr int kStages = (int)(kRingBytes / (BKV * D * 2));  // 2 | 4
+  constexpr uint32_t kKVBytes = BKV * D * 2;            // one K or V tile as [2 column chunks][BKV rows x 128 B]
+  constexpr uint32_t kChunk = BKV * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars;         // 1  both Q tiles of an item have landed (one phase per item)
   uint64_t* q_empty = bars + 1;    // 1  every QKᵀ of the item has retired
-  uint64_t* k_full = bars + 2;     // 2  K / V rings on one global kv-tile counter
-  uint64_t* k_empty = bars + 4;    // 2
-  uint64_t* v_full = bars + 6;     // 2
-  uint64_t* v_empty = bars + 8;    // 2
-  uint64_t* s_full = bars + 10;    // 2  per group: S_g of its next tile is complete (one phase per group tile)
-  uint64_t* p_full = bars + 12;    // 2  per group (4 warp arrivals): P_g is in TMEM, O_g rescaled if it had to be
-  uint64_t* o_done = bars + 14;    // 2  per group: P·V of its tile has retired (O_g stable, S_g columns reusable)
-  uint64_t* o_free = bars + 16;    // 2  per group (4 warp arrivals): the epilogue has read O_g out of TMEM (one phase per item)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* k_full = bars + 2;     // up to 4: K / V rings on one global kv-tile counter
+  uint64_t* k_empty = bars + 6;
+  uint64_t* v_full = bars + 10;
+  uint64_t* v_empty = bars + 14;
+  uint64_t* s_full = bars + 18;    // [group][buffer]: S of that buffer's next tile is complete
+  uint64_t* p_full = bars + 22;    // 2  per group (4 warp arrivals): P_g is in TMEM, O_g rescaled if it had to be
+  uint64_t* o_done = bars + 24;    // 2  per group: P·V of its tile has retired (O_g stable)
+  uint64_t* o_free = bars + 26;    // 2  per group (4 warp arrivals): the epilogue has read O_g out of TMEM (one phase per item)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npairs = p.S / (2 * BQ);
@@ -82,21 +92,24 @@ __global__ void __launch_bounds__(kThreads, 1)
     pb = npairs - 1 - w / BH;
     bh = w % BH;
   };
-  auto tiles_of = [&](int pb, int g) { return p.causal ? 2 * pb + g + 1 : p.S / BKV; };
+  auto tiles_of = [&](int pb, int g) { return p.causal ? (2 * pb + g + 1) * (128 / BKV) : p.S / BKV; };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_qkv);
+    prefetch_tmap(&tmap_kv);
     prefetch_tmap(&tmap_o);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&p_full[i], 4);
       mbar_init(&o_done[i], 1);
       mbar_init(&o_free[i], 4);
@@ -128,17 +141,17 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int c = 0; c < 2; ++c) tma_load_2d(&tmap_qkv, q_full, sQ + g * kTileBytes + c * (128 * 128), col_q + c * 64, row0 + g * BQ);
         const int n_kv = tiles_of(pb, 1);
         for (int t = 0; t < n_kv; ++t, ++kt) {
-          const int st = kt & 1;
-          const uint32_t ph = (kt >> 1) & 1;
+          const int st = kt % kStages;
+          const uint32_t ph = (kt / kStages) & 1;
           const int krow = b * p.S + t * BKV;
           mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_expect_tx(&k_full[st], kTileBytes);
+          mbar_expect_tx(&k_full[st], kKVBytes);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) tma_load_2d(&tmap_qkv, &k_full[st], sK + st * kTileBytes + c * (128 * 128), col_k + c * 64, krow);
+          for (int c = 0; c < 2; ++c) tma_load_2d(&tmap_kv, &k_full[st], sK + st * kKVBytes + c * kChunk, col_k + c * 64, krow);
           mbar_wait(&v_empty[st], ph ^ 1);
-          mbar_expect_tx(&v_full[st], kTileBytes);
+          mbar_expect_tx(&v_full[st], kKVBytes);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) tma_load_2d(&tmap_qkv, &v_full[st], sV + st * kTileBytes + c * (128 * 128), col_v + c * 64, krow);
+          for (int c = 0; c < 2; ++c) tma_load_2d(&tmap_kv, &v_full[st], sV + st * kKVBytes + c * kChunk, col_v + c * 64, krow);
         }
       }
     }
@@ -147,30 +160,47 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc_bf16(BQ, BKV, 0, 0);  // S = Q Kᵀ : both K-major
       constexpr uint32_t idesc_o = idesc_bf16(BQ, D, 0, 1);    // O += P V : P (TMEM) K-major, V MN-major
+      constexpr int LA = NSB - 1;  // how many tiles QKᵀ may run ahead of the group's P·V
       int kt0 = 0, it = 0;
-      int ng[2] = {0, 0};  // per-group tile counters (global): phase of s_full / p_full / o_done
-      auto issue_qk = [&](int g, int kt) {  // S_g = Q_g · K(kt)ᵀ; the caller guarantees K(kt) has landed and S_g is reusable
-        const int st = kt & 1;
-        const uint32_t a0 = smem_u32(sQ + g * kTileBytes), b0 = smem_u32(sK + st * kTileBytes);
+      int ng[2] = {0, 0};  // per-group tile counters (global): phases of p_full / o_done, S buffer = counter % NSB
+      // S_g[buffer of tile n] = Q_g · K(kt)ᵀ; the caller guarantees K(kt) has landed; the buffer is reusable by program order
+      auto issue_qk = [&](int g, int kt, int n) {
+        const int st = kt % kStages;
+        const int buf = n % NSB;
+        const uint32_t a0 = smem_u32(sQ + g * kTileBytes), b0 = smem_u32(sK + st * kKVBytes);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + g * 128, make_smem_desc(a0 + c * (128 * 128) + k * 32, 16, 1024),
-                      make_smem_desc(b0 + c * (128 * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
-        umma_commit(&s_full[g]);
+            umma_bf16(tmem_base + g * 128 + buf * BKV, make_smem_desc(a0 + c * (128 * 128) + k * 32, 16, 1024),
+                      make_smem_desc(b0 + c * kChunk + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
+        umma_commit(&s_full[g * 2 + buf]);
+      };
+      auto wait_k = [&](int kt) {
+        mbar_wait(&k_full[kt % kStages], (kt / kStages) & 1);
+        tc_fence_after();
       };
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         int pb, bh;
         item(w, pb, bh);
         const int n0 = tiles_of(pb, 0), n1 = tiles_of(pb, 1);  // n0 <= n1
         mbar_wait(q_full, it & 1);
-        mbar_wait(&k_full[kt0 & 1], (kt0 >> 1) & 1);
-        tc_fence_after();
-        issue_qk(0, kt0);
-        issue_qk(1, kt0);
-        umma_commit(&k_empty[kt0 & 1]);
-        if (n1 == 1) umma_commit(q_empty);
+        // K tile j is used by group 0 (if j < n0) and group 1, always in this order; its ring slot is released behind group 1's
+        auto qk_pair_release = [&](int g, int j) {
+          if (g == 1) {
+            umma_commit(&k_empty[(kt0 + j) % kStages]);
+            if (j + 1 == n1) umma_commit(q_empty);  // the item's last QKᵀ
+          }
+        };
+        for (int j = 0; j <= LA && j < n1; ++j) {
+          wait_k(kt0 + j);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (j >= (g == 0 ? n0 : n1)) continue;
+            issue_qk(g, kt0 + j, ng[g] + j);
+            qk_pair_release(g, j);
+          }
+        }
         for (int t = 0; t < n1; ++t) {
           const int kt = kt0 + t;
 #pragma unroll
@@ -180,26 +210,23 @@ __global__ void __launch_bounds__(kThreads, 1)
             // P_g(t) is in TMEM (and O_g was rescaled if a row max jumped)
             mbar_wait(&p_full[g], ng[g] & 1);
             if (t == 0 && it > 0) mbar_wait(&o_free[g], (it - 1) & 1);  // the previous item's epilogue has drained O_g
-            mbar_wait(&v_full[kt & 1], (kt >> 1) & 1);
+            mbar_wait(&v_full[kt % kStages], (kt / kStages) & 1);
             tc_fence_after();
-            const uint32_t b0 = smem_u32(sV + (kt & 1) * kTileBytes);
+            const uint32_t b0 = smem_u32(sV + (kt % kStages) * kKVBytes);
+            const uint32_t tP = tmem_base + g * 128 + (ng[g] % NSB) * BKV;
 #pragma unroll
             for (int kk = 0; kk < BKV / 16; ++kk)  // 16 keys = 8 TMEM columns of packed bf16 pairs per step
-              umma_bf16_ts(tmem_base + 256 + g * 128, tmem_base + g * 128 + kk * 8, make_smem_desc(b0 + kk * 2048, BKV * 128, 1024),
-                           idesc_o, (t | kk) != 0 ? 1u : 0u);
+              umma_bf16_ts(tmem_base + 256 + g * 128, tP + kk * 8, make_smem_desc(b0 + kk * 2048, kChunk, 1024), idesc_o,
+                           (t | kk) != 0 ? 1u : 0u);
             umma_commit(&o_done[g]);
-            ++ng[g];
-            if (g == 1) umma_commit(&v_empty[kt & 1]);  // group 1 uses every V tile and comes last
-            if (t + 1 < ntl) {  // next QKᵀ of this group goes BEHIND its P·V: P_g aliases the S_g columns
-              const int kn = kt + 1;
-              mbar_wait(&k_full[kn & 1], (kn >> 1) & 1);
-              tc_fence_after();
-              issue_qk(g, kn);
-              if (g == 1) {
-                umma_commit(&k_empty[kn & 1]);
-                if (t + 2 == n1) umma_commit(q_empty);  // that was the item's last QKᵀ
-              }
+            if (g == 1) umma_commit(&v_empty[kt % kStages]);  // group 1 uses every V tile and comes last
+            const int tn = t + 1 + LA;  // the QKᵀ that reuses the S buffer P_g(t) has just been read from
+            if (tn < ntl) {
+              wait_k(kt0 + tn);
+              issue_qk(g, kt0 + tn, ng[g] + 1 + LA);
+              qk_pair_release(g, tn);
             }
+            ++ng[g];
           }
         }
         kt0 += n1;
@@ -211,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int g = (warp - 3) >> 2;
     const int r = q * 32 + lane;      // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t tS = tmem_base + g * 128 + lane_addr, tO = tmem_base + 256 + g * 128 + lane_addr;
+    const uint32_t tS0 = tmem_base + g * 128 + lane_addr, tO = tmem_base + 256 + g * 128 + lane_addr;
     uint8_t* stage = smem + kOffStage + g * 16384;
     const uint32_t row_sw = (uint32_t)(lane & 7);
     int ng = 0, it = 0;
@@ -223,19 +250,23 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int n_kv = tiles_of(pb, g);
       const int row0 = b * p.S + qt * BQ;
       float m_used = -INFINITY, l = 0.f;         // reference max of the exponentials (log2 domain) and the row sum relative to it
+      const int qpos = qt * BQ + r;              // this row's position in the sequence
       for (int t = 0; t < n_kv; ++t, ++ng) {
-        mbar_wait(&s_full[g], ng & 1);
+        const int buf = ng % NSB;
+        const uint32_t tS = tS0 + buf * BKV;
+        mbar_wait(&s_full[g * 2 + buf], (ng / NSB) & 1);
         tc_fence_after();
         uint32_t v[BKV];
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32b_x32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
         tmem_ld_wait();
-        const bool diag = p.causal && t == qt;
+        const bool diag = p.causal && (t + 1) * BKV - 1 > qt * BQ;  // some key of this tile lies behind some query of the tile
+        const int lim = qpos - t * BKV;                             // keys j <= lim of this tile are visible to this row
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (diag) {
 #pragma unroll
           for (int j = 0; j < BKV; ++j)
-            if (j <= r) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
+            if (j <= lim) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
         } else {
 #pragma unroll
           for (int j = 0; j < BKV; ++j) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
@@ -275,8 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1)
               float e0 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + j]), p.scale_log2, -m_used));
               float e1 = fast_exp2(fmaf(__uint_as_float(v[c * 32 + j + 1]), p.scale_log2, -m_used));
               if (decltype(masked)::value) {
-                if (c * 32 + j > r) e0 = 0.f;
-                if (c * 32 + j + 1 > r) e1 = 0.f;
+                if (c * 32 + j > lim) e0 = 0.f;
+                if (c * 32 + j + 1 > lim) e1 = 0.f;
               }
               l4[(j >> 1) & 3] += e0 + e1;
               pk[j >> 1] = pack_bf16x2(__float_as_uint(e0), __float_as_uint(e1));
@@ -347,21 +378,29 @@ PB_EXPORT int pb_flash_attn_fwd2(const void* qkv, void* out, float* lse2, int B,
                                  cudaStream_t stream) {
   if (S % (2 * BQ) != 0 || H % Hkv != 0) return -1;
   static bool configured = false;
+  static int bkv = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(flash_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    cudaError_t e = cudaFuncSetAttribute(flash_fwd2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(flash_fwd2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return (int)e;
+    const char* ev = getenv("PB_ATTN_FWD2_BKV");
+    bkv = (ev && atoi(ev) == 128) ? 128 : 64;
     configured = true;
   }
   const uint64_t rows = (uint64_t)B * S, wqkv = (uint64_t)(H + 2 * Hkv) * D, wo = (uint64_t)H * D;
-  CUtensorMap tq, to;
+  CUtensorMap tq, tkv, to;
   int rc = pbhost::cached_tmap(&tq, qkv, rows, wqkv, wqkv, 64, 128, 2);
+  if (rc) return rc;
+  rc = pbhost::cached_tmap(&tkv, qkv, rows, wqkv, wqkv, 64, (uint32_t)bkv, 2);
   if (rc) return rc;
   rc = pbhost::cached_tmap(&to, out, rows, wo, wo, 64, 32, 2);
   if (rc) return rc;
   Fwd2Params p{lse2, B, S, H, Hkv, scale * 1.4426950408889634f, causal};
   const int items = (S / (2 * BQ)) * B * H;
   const int grid = items < pbhost::num_sms() ? items : pbhost::num_sms();
-  flash_fwd2_kernel<<<grid, kThreads, kSmem, stream>>>(tq, to, p);
+  if (bkv == 64) flash_fwd2_kernel<64><<<grid, kThreads, kSmem, stream>>>(tq, tkv, to, p);
+  else flash_fwd2_kernel<128><<<grid, kThreads, kSmem, stream>>>(tq, tkv, to, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

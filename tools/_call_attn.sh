@@ -1,6 +1,5 @@
-mkdir -p gpurun_out/ncu
-ncu --set full --clock-control none --import-source on -k regex:flash_fwd2_kernel -s 3 -c 1 -o gpurun_out/ncu/fwd2 -f python tools/attn_bench.py > gpurun_out/ncu/fwd2.log 2>&1
-ncu -i gpurun_out/ncu/fwd2.ncu-rep --page source --csv > gpurun_out/ncu/fwd2.source.csv 2>/dev/null
-ncu -i gpurun_out/ncu/fwd2.ncu-rep --page raw --csv > gpurun_out/ncu/fwd2.raw.csv 2>/dev/null
-python tools/ncu_source_hotspots.py gpurun_out/ncu/fwd2.source.csv 25 | tee gpurun_out/fwd2_hotspots.txt | head -60
-rm -f gpurun_out/ncu/fwd2.ncu-rep
+for bkv in 64 128; do
+echo "BKV=$bkv"
+PB_ATTN_FWD2_BKV=$bkv timeout 300 python -m pytest tests/test_kernels_gpu.py -q -x -k "two_tile_kernel or rope_attention or qkv_gemm_rope" 2>&1 | tail -3 | cut -c1-300
+PB_ATTN_FWD2_BKV=$bkv timeout 200 python tools/attn_bench.py 2>/dev/null | tee gpurun_out/attn_bench_v9_bkv$bkv.json | cut -c1-250
+done
