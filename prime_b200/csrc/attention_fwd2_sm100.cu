@@ -31,7 +31,7 @@ constexpr uint32_t kRingBytes = 2 * kTileBytes;         // 64 KB per K ring and 
 constexpr uint32_t kOffV = kOffK + kRingBytes;
 constexpr uint32_t kOffStage = kOffV + kRingBytes;      // per group: [128 rows x 128 B] output staging for one 64-column chunk
 constexpr uint32_t kOffBar = kOffStage + 2 * 16384;
-constexpr uint32_t kSmem = kOffBar + 256;
+constexpr uint32_t kSmem = kOffBar + 320;
 // BKV = key tile. 128: one S buffer per group, QKᵀ(t+1) can only follow P·V(t) (P aliases S) — the softmax warps then wait for S a
 // quarter of the time (ncu source view). 64: the group's 128 S columns hold TWO buffers, QKᵀ(t+1) runs while softmax(t) is busy,
 // and the same 64 KB rings hold four 16 KB stages each.
@@ -78,11 +78,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* k_empty = bars + 6;
   uint64_t* v_full = bars + 10;
   uint64_t* v_empty = bars + 14;
+  // The per-tile barriers exist once per (group, S buffer): a softmax group can run a whole tile ahead of the MMA thread's
+  // bookkeeping when it has two buffers, and a single barrier would then advance two phases between two looks at it — a parity wait
+  // cannot tell that from zero phases. With one barrier per buffer, tile n+2 can only signal after tile n has been consumed.
   uint64_t* s_full = bars + 18;    // [group][buffer]: S of that buffer's next tile is complete
-  uint64_t* p_full = bars + 22;    // 2  per group (4 warp arrivals): P_g is in TMEM, O_g rescaled if it had to be
-  uint64_t* o_done = bars + 24;    // 2  per group: P·V of its tile has retired (O_g stable)
-  uint64_t* o_free = bars + 26;    // 2  per group (4 warp arrivals): the epilogue has read O_g out of TMEM (one phase per item)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* p_full = bars + 22;    // [group][buffer] (4 warp arrivals): P is in TMEM, O_g rescaled if it had to be
+  uint64_t* o_done = bars + 26;    // [group][buffer]: P·V of that tile has retired (O_g stable)
+  uint64_t* o_free = bars + 30;    // 2  per group (4 warp arrivals): the epilogue has read O_g out of TMEM (one phase per item)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npairs = p.S / (2 * BQ);
@@ -108,12 +111,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_done[i], 1);
-      mbar_init(&o_free[i], 4);
     }
+    for (int i = 0; i < 2; ++i) mbar_init(&o_free[i], 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -208,17 +211,19 @@ __global__ void __launch_bounds__(kThreads, 1)
             const int ntl = g == 0 ? n0 : n1;
             if (t >= ntl) continue;
             // P_g(t) is in TMEM (and O_g was rescaled if a row max jumped)
-            mbar_wait(&p_full[g], ng[g] & 1);
+            const int buf = ng[g] % NSB;
+            const uint32_t bph = (ng[g] / NSB) & 1;
+            mbar_wait(&p_full[g * 2 + buf], bph);
             if (t == 0 && it > 0) mbar_wait(&o_free[g], (it - 1) & 1);  // the previous item's epilogue has drained O_g
             mbar_wait(&v_full[kt % kStages], (kt / kStages) & 1);
             tc_fence_after();
             const uint32_t b0 = smem_u32(sV + (kt % kStages) * kKVBytes);
-            const uint32_t tP = tmem_base + g * 128 + (ng[g] % NSB) * BKV;
+            const uint32_t tP = tmem_base + g * 128 + buf * BKV;
 #pragma unroll
             for (int kk = 0; kk < BKV / 16; ++kk)  // 16 keys = 8 TMEM columns of packed bf16 pairs per step
               umma_bf16_ts(tmem_base + 256 + g * 128, tP + kk * 8, make_smem_desc(b0 + kk * 2048, kChunk, 1024), idesc_o,
                            (t | kk) != 0 ? 1u : 0u);
-            umma_commit(&o_done[g]);
+            umma_commit(&o_done[g * 2 + buf]);
             if (g == 1) umma_commit(&v_empty[kt % kStages]);  // group 1 uses every V tile and comes last
             const int tn = t + 1 + LA;  // the QKᵀ that reuses the S buffer P_g(t) has just been read from
             if (tn < ntl) {
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         if (t > 0 && __any_sync(0xffffffffu, grow)) {
           // O_g *= alpha (rows that did not grow multiply by 1): needs P·V of the previous tile finished
-          mbar_wait(&o_done[g], (ng - 1) & 1);
+          mbar_wait(&o_done[g * 2 + (ng - 1) % NSB], ((ng - 1) / NSB) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < D / 32; ++c) {
@@ -321,10 +326,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[g]);
+        if (lane == 0) mbar_arrive(&p_full[g * 2 + buf]);
       }
       // ---- epilogue of the item: O_g / l → bf16 → staging → TMA store, 64 columns at a time
-      mbar_wait(&o_done[g], (ng - 1) & 1);
+      mbar_wait(&o_done[g * 2 + (ng - 1) % NSB], ((ng - 1) / NSB) & 1);
       tc_fence_after();
       const float inv_l = 1.f / l;
 #pragma unroll 1
@@ -385,7 +390,7 @@ PB_EXPORT int pb_flash_attn_fwd2(const void* qkv, void* out, float* lse2, int B,
     e = cudaFuncSetAttribute(flash_fwd2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (e != cudaSuccess) return (int)e;
     const char* ev = getenv("PB_ATTN_FWD2_BKV");
-    bkv = (ev && atoi(ev) == 128) ? 128 : 64;
+    bkv = (ev && atoi(ev) == 64) ? 64 : 128;
     configured = true;
   }
   const uint64_t rows = (uint64_t)B * S, wqkv = (uint64_t)(H + 2 * Hkv) * D, wo = (uint64_t)H * D;
