@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out/ncu
 NCU="ncu --set full --clock-control none"
 $NCU --import-source on -k regex:gemm_bf16_kernel -s 30 -c 2 -o gpurun_out/ncu/gemm -f python tools/gemm_bench.py > gpurun_out/ncu/gemm.log 2>&1
-$NCU --import-source on -k regex:'flash_fwd_kernel|bwd_dkdv_kernel|bwd_dq_kernel|bwd_delta_kernel' -s 16 -c 4 -o gpurun_out/ncu/attn -f python tools/attn_bench.py > gpurun_out/ncu/attn.log 2>&1
+$NCU --import-source on -k regex:'flash_fwd|bwd_dkdv_kernel|bwd_dq_kernel|bwd_delta_kernel' -s 16 -c 4 -o gpurun_out/ncu/attn -f python tools/attn_bench.py > gpurun_out/ncu/attn.log 2>&1
 $NCU -k regex:'rmsnorm|rope|swiglu|cross_entropy|colsum|grad_reduce|norm_publish|adamw_push|pseudograd|outer_nesterov|cast_push' -c 40 -o gpurun_out/ncu/ops -f \
     python tools/op_bench.py --once > gpurun_out/ncu/ops.log 2>&1
 $NCU --import-source on -k regex:'gemm_mxfp8_kernel|quantize_mxfp8' -s 6 -c 4 -o gpurun_out/ncu/mxfp8 -f python tools/mxfp8_bench.py > gpurun_out/ncu/mxfp8.log 2>&1
