@@ -70,6 +70,7 @@ struct BwdParams {
   // interleaved-pair convention) so no separate pass over the 200 MB dQKV tensor is needed. nullptr = plain attention backward.
   const float* rope_cos;
   const float* rope_sin;
+  int l2_prefetch;  // issue cp.async.bulk.prefetch for the input tile a ring-depth ahead (PB_ATTN_BWD_L2PF, A/B switch)
 };
 
 // inverse RoPE on 32 consecutive head-dim columns [c32*32, c32*32+32) of one row at sequence position `pos`
@@ -92,7 +93,8 @@ __device__ __forceinline__ void rope_inverse_chunk(float (&x)[32], const float* 
   }
 }
 
-// trace record: [role 0..3][slot] = {event code, tile, clock}; role 0 loader, 1 MMA, 2 math group 0, 3 math group 1
+// trace record: [role 0..7][slot] = {event code, tile, clock}; roles 0..3 = dK/dV kernel (loader, MMA, math group 0, math group 1),
+// 4..7 = the same four roles of the dQ kernel
 __device__ __forceinline__ void trace_ev(const BwdParams& p, int role, int& n, int code, int tile) {
   if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && n < 256) {
     unsigned long long* e = p.trace + ((size_t)role * 256 + n) * 3;
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         {  // the tile that will be loaded kQStages iterations from now: start moving it HBM → L2 (measured: a cold 32 KB
            // Q/dO stage takes ≈3900 clk to land, and only one load can be in flight with every slot held until dV/dK retire)
           const int nx = it + C::kQStages;
-          if (nx < n_it) {
+          if (p.l2_prefetch && nx < n_it) {
             const int hn = hk * group + nx / tiles_per_head;
             const int qn = b * p.S + (it0 + nx % tiles_per_head) * 64;
 #pragma unroll
@@ -601,11 +603,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         tma_load_2d(&tmap_qkv128, q_full, sQ + c * (128 * 128), col_q + c * 64, row0);
         tma_load_2d(&tmap_do128, q_full, sdO + c * (128 * 128), col_q + c * 64, row0);
       }
+      int tr_n = 0;
       for (int t = 0; t < n_kv; ++t) {
         const int st = t % C::kKVStages;
         const uint32_t ph = (t / C::kKVStages) & 1;
         const int krow = b * p.S + t * 64;
-        if (t + C::kKVStages < n_kv) {
+        if (p.l2_prefetch && t + C::kKVStages < n_kv) {
           const int kn = b * p.S + (t + C::kKVStages) * 64;
 #pragma unroll
           for (int c = 0; c < C::kChunks; ++c) {
@@ -614,6 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
         mbar_wait(&kv_empty[st], ph ^ 1);
+        trace_ev(p, 4, tr_n, 1, t);
         mbar_expect_tx(&kv_full[st], 2 * C::kKVBytes);
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
@@ -627,12 +631,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       constexpr uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);  // S[128 q x 64 kv] = Q Kᵀ
       constexpr uint32_t idesc_a = idesc_bf16(128, D, 0, 1);   // dQ[128 q x D] += dS · K   (K tile as MN-major B)
       mbar_wait(q_full, 0);
+      int tr_n = 0;
       auto issue_sd = [&](int t) {
         const int st = t & 1;
         const uint32_t ph = (t >> 1) & 1;
         const int ks = t % C::kKVStages;
         mbar_wait(&kv_full[ks], (t / C::kKVStages) & 1);
+        trace_ev(p, 5, tr_n, 1, t);
         mbar_wait(&s_empty[st], ph ^ 1);
+        trace_ev(p, 5, tr_n, 2, t);
         tc_fence_after();
         const uint32_t q0 = smem_u32(sQ), d0 = smem_u32(sdO);
         const uint32_t k0 = smem_u32(sK + ks * C::kKVBytes), v0 = smem_u32(sV + ks * C::kKVBytes);
@@ -666,6 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (sd_next == t + 2 && sd_next < n_kv && sd_ready(sd_next)) issue_sd(sd_next++);
           }
         }
+        trace_ev(p, 5, tr_n, 3, t);
         tc_fence_after();
         const int ks = t % C::kKVStages;
         const uint32_t da = smem_u32(sdS + st * C::kdSBytes), k0 = smem_u32(sK + ks * C::kKVBytes);
@@ -686,10 +694,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float lse = p.lse2[((int64_t)bh) * p.S + q_idx];
     const float del_s = p.delta[((int64_t)bh) * p.S + q_idx];
+    int tr_n = 0;
+    const bool tr = q == 0 && lane == 0;
     for (int t = half; t < n_kv; t += 2) {  // the two math groups leapfrog over the kv tiles (see the dK/dV kernel)
       const int st = t & 1;
       const uint32_t ph = (t >> 1) & 1;
+      if (tr) trace_ev(p, 6 + half, tr_n, 1, t);
       mbar_wait(&s_full[st], ph);
+      if (tr) trace_ev(p, 6 + half, tr_n, 2, t);
       tc_fence_after();
       const int kv0 = t * 64;
       const bool need_mask = p.causal && (kv0 + 64 > qb * 128);
@@ -703,7 +715,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (tr) trace_ev(p, 6 + half, tr_n, 3, t);
       if (t >= 2) mbar_wait(&acc_done[st], ph ^ 1);
+      if (tr) trace_ev(p, 6 + half, tr_n, 4, t);
       auto tile_math = [&](auto masked) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -722,6 +736,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);
+      if (tr) trace_ev(p, 6 + half, tr_n, 5, t);
     }
     // NOT acc_done[last tile's stage]: a group only follows its OWN stage's barrier inside the loop, so it can reach this point
     // while the other stage is still two phases behind — a parity wait would then match the phase BEFORE the previous one and
@@ -802,7 +817,12 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   if ((rc = pbhost::cached_tmap(&tdo64, dout, rows, wo, wo, 64, 64, 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tdo128, dout, rows, wo, wo, 64, 128, 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tdq, dqkv, rows, wqkv, wqkv, 64, 32, 2))) return rc;
-  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace, rope_cos, rope_sin};
+  static int l2pf = -1;
+  if (l2pf < 0) {
+    const char* ev = getenv("PB_ATTN_BWD_L2PF");
+    l2pf = ev ? (atoi(ev) != 0) : 1;
+  }
+  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace, rope_cos, rope_sin, l2pf};
   if (g_bwd_pstages < 0) {
     const char* ev = getenv("PB_ATTN_BWD_PSTAGES");
     g_bwd_pstages = ev ? atoi(ev) : 2;

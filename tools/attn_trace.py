@@ -22,6 +22,39 @@ CODES = {"loader": {1: "issue_load"}, "mma": {1: "q_landed", 2: "issue_S_dP", 3:
          "math1": {1: "wait_S", 2: "S_ready", 3: "tmem_loaded", 4: "p_stage_free", 5: "done", 6: "math_done"}}  # fmt: skip
 
 
+def summarize_dq(ev):
+    """dQ kernel, CTA (0,0) = the last query block (sees every kv tile): roles loader / MMA / math group 0 / 1."""
+    names = {0: {1: "issue_load"}, 1: {1: "kv_landed", 2: "issue_S_dP", 3: "issue_dQ"},
+             2: {1: "wait_S", 2: "S_ready", 3: "tmem_loaded", 4: "ds_buffer_free", 5: "done"},
+             3: {1: "wait_S", 2: "S_ready", 3: "tmem_loaded", 4: "ds_buffer_free", 5: "done"}}
+    firsts = [int(ev[r, 0, 2]) for r in range(4) if ev[r, 0, 0] != 0]
+    if not firsts:
+        return None
+    t0 = min(firsts)
+    by = {}
+    last = 0
+    for r in range(4):
+        for k in range(256):
+            code, tile, clk = (int(x) for x in ev[r, k])
+            if code == 0:
+                break
+            role = ["loader", "mma", "math0", "math1"][r]
+            by.setdefault(tile, {})[f"{role}.{names[r].get(code, code)}"] = clk - t0
+            last = max(last, clk - t0)
+    rows = []
+    for tile in sorted(by):
+        d = by[tile]
+        g = "math0" if tile % 2 == 0 else "math1"
+        rows.append({"tile": tile, "load_issue": d.get("loader.issue_load"), "kv_landed": d.get("mma.kv_landed"), "S_issue": d.get("mma.issue_S_dP"),
+                     "S_ready": d.get(f"{g}.S_ready"), "wait_for_S": d.get(f"{g}.S_ready", 0) - d.get(f"{g}.wait_S", 0),
+                     "tmem_load": d.get(f"{g}.tmem_loaded", 0) - d.get(f"{g}.S_ready", 0),
+                     "wait_ds_buffer": d.get(f"{g}.ds_buffer_free", 0) - d.get(f"{g}.tmem_loaded", 0),
+                     "math_store": d.get(f"{g}.done", 0) - d.get(f"{g}.ds_buffer_free", 0),
+                     "S_issue_to_ready": d.get(f"{g}.S_ready", 0) - d.get("mma.issue_S_dP", 0),
+                     "done_to_dQ_issue": d.get("mma.issue_dQ", 0) - d.get(f"{g}.done", 0)})  # fmt: skip
+    return {"total_cycles": last, "tiles": len(rows), "cycles_per_tile": round(last / max(1, len(rows))), "per_tile": rows}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--S", type=int, default=1024)
@@ -33,14 +66,16 @@ def main():
     out = A.flash_attention_qkv(qkv, H, H, True)
     dout = torch.randn_like(out)
     out.backward(dout, retain_graph=True)  # warm-up
-    buf = torch.zeros(4 * 256 * 3, dtype=torch.int64, device=dev)
+    buf = torch.zeros(8 * 256 * 3, dtype=torch.int64, device=dev)
     lib = _lib.load()
     lib.pb_flash_attn_bwd_set_trace(buf.data_ptr())
     qkv.grad = None
     out.backward(dout)
     torch.cuda.synchronize()
     lib.pb_flash_attn_bwd_set_trace(None)
-    ev = buf.view(4, 256, 3).cpu().numpy()
+    ev_all = buf.view(8, 256, 3).cpu().numpy()
+    dq = summarize_dq(ev_all[4:])
+    ev = ev_all[:4]
     t0 = min(int(ev[r, 0, 2]) for r in range(4) if ev[r, 0, 0] != 0)
     timeline = []
     for r, role in enumerate(ROLES):
@@ -69,7 +104,7 @@ def main():
                      "load_issue": d.get("loader.issue_load"), "q_landed": d.get("mma.q_landed")})  # fmt: skip
     span = timeline[-1]["cyc"] if timeline else 0
     print(json.dumps({"shape": {"B": B, "S": S, "H": H, "D": D}, "cta": "kv block 0 (sees every query tile: the longest CTA)", "total_cycles": span,
-                      "tiles": len(rows), "cycles_per_tile": round(span / max(1, len(rows))), "per_tile": rows}, indent=1))  # fmt: skip
+                      "tiles": len(rows), "cycles_per_tile": round(span / max(1, len(rows))), "per_tile": rows, "dq_kernel": dq}, indent=1))  # fmt: skip
 
 
 if __name__ == "__main__":
