@@ -70,6 +70,7 @@ struct BwdParams {
   // interleaved-pair convention) so no separate pass over the 200 MB dQKV tensor is needed. nullptr = plain attention backward.
   const float* rope_cos;
   const float* rope_sin;
+  int tma3d;        // streamed operand tiles as ONE 3-D TMA box per operand instead of one 2-D box per 64-column chunk
   int l2_prefetch;  // issue cp.async.bulk.prefetch for the input tile a ring-depth ahead (PB_ATTN_BWD_L2PF, A/B switch)
 };
 
@@ -159,6 +160,7 @@ template <int D, int PST>
 __global__ void __launch_bounds__(kThreads, 1)
     bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __grid_constant__ CUtensorMap tmap_qkv64,
                     const __grid_constant__ CUtensorMap tmap_do64, const __grid_constant__ CUtensorMap tmap_dqkv,
+                    const __grid_constant__ CUtensorMap tmap_qkv64_3d, const __grid_constant__ CUtensorMap tmap_do64_3d,
                     const BwdParams p) {
   using C = DkvCfg<D, PST>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -250,10 +252,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_wait(&q_empty[st], ph ^ 1);
         trace_ev(p, 0, tr_n, 1, it);  // slot free → issue the Q/dO loads of tile `it`
         mbar_expect_tx(&q_full[st], 2 * C::kQBytes);
+        if (p.tma3d) {
+          tma_load_3d(&tmap_qkv64_3d, &q_full[st], sQ + st * C::kQBytes, 0, qrow, h * D / 64);
+          tma_load_3d(&tmap_do64_3d, &q_full[st], sdO + st * C::kQBytes, 0, qrow, h * D / 64);
+        } else {
 #pragma unroll
-        for (int c = 0; c < C::kChunks; ++c) {
-          tma_load_2d(&tmap_qkv64, &q_full[st], sQ + st * C::kQBytes + c * (64 * 128), h * D + c * 64, qrow);
-          tma_load_2d(&tmap_do64, &q_full[st], sdO + st * C::kQBytes + c * (64 * 128), h * D + c * 64, qrow);
+          for (int c = 0; c < C::kChunks; ++c) {
+            tma_load_2d(&tmap_qkv64, &q_full[st], sQ + st * C::kQBytes + c * (64 * 128), h * D + c * 64, qrow);
+            tma_load_2d(&tmap_do64, &q_full[st], sdO + st * C::kQBytes + c * (64 * 128), h * D + c * 64, qrow);
+          }
         }
       }
     }
@@ -538,7 +545,7 @@ template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
     bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __grid_constant__ CUtensorMap tmap_qkv64,
                   const __grid_constant__ CUtensorMap tmap_do128, const __grid_constant__ CUtensorMap tmap_dqkv,
-                  const BwdParams p) {
+                  const __grid_constant__ CUtensorMap tmap_qkv64_3d, const BwdParams p) {
   using C = DqCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -619,10 +626,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_wait(&kv_empty[st], ph ^ 1);
         trace_ev(p, 4, tr_n, 1, t);
         mbar_expect_tx(&kv_full[st], 2 * C::kKVBytes);
+        if (p.tma3d) {
+          tma_load_3d(&tmap_qkv64_3d, &kv_full[st], sK + st * C::kKVBytes, 0, krow, col_k / 64);
+          tma_load_3d(&tmap_qkv64_3d, &kv_full[st], sV + st * C::kKVBytes, 0, krow, col_v / 64);
+        } else {
 #pragma unroll
-        for (int c = 0; c < C::kChunks; ++c) {
-          tma_load_2d(&tmap_qkv64, &kv_full[st], sK + st * C::kKVBytes + c * (64 * 128), col_k + c * 64, krow);
-          tma_load_2d(&tmap_qkv64, &kv_full[st], sV + st * C::kKVBytes + c * (64 * 128), col_v + c * 64, krow);
+          for (int c = 0; c < C::kChunks; ++c) {
+            tma_load_2d(&tmap_qkv64, &kv_full[st], sK + st * C::kKVBytes + c * (64 * 128), col_k + c * 64, krow);
+            tma_load_2d(&tmap_qkv64, &kv_full[st], sV + st * C::kKVBytes + c * (64 * 128), col_v + c * 64, krow);
+          }
         }
       }
     }
@@ -817,22 +829,30 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   if ((rc = pbhost::cached_tmap(&tdo64, dout, rows, wo, wo, 64, 64, 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tdo128, dout, rows, wo, wo, 64, 128, 2))) return rc;
   if ((rc = pbhost::cached_tmap(&tdq, dqkv, rows, wqkv, wqkv, 64, 32, 2))) return rc;
+  CUtensorMap tq64_3d, tdo64_3d;
+  if ((rc = pbhost::cached_tmap3(&tq64_3d, qkv, rows, wqkv, wqkv, 64, D / 64))) return rc;
+  if ((rc = pbhost::cached_tmap3(&tdo64_3d, dout, rows, wo, wo, 64, D / 64))) return rc;
+  static int tma3d = -1;
+  if (tma3d < 0) {
+    const char* ev = getenv("PB_ATTN_BWD_TMA3D");
+    tma3d = ev ? (atoi(ev) != 0) : 1;
+  }
   static int l2pf = -1;
   if (l2pf < 0) {
     const char* ev = getenv("PB_ATTN_BWD_L2PF");
     l2pf = ev ? (atoi(ev) != 0) : 1;
   }
-  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace, rope_cos, rope_sin, l2pf};
+  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace, rope_cos, rope_sin, tma3d, l2pf};
   if (g_bwd_pstages < 0) {
     const char* ev = getenv("PB_ATTN_BWD_PSTAGES");
     g_bwd_pstages = ev ? atoi(ev) : 2;
     if (g_bwd_pstages < 0 || g_bwd_pstages > 2) g_bwd_pstages = 2;
   }
   const int pstages = g_bwd_pstages;
-  if (pstages == 0) bwd_dkdv_kernel<D, 0><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 0>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
-  else if (pstages == 2) bwd_dkdv_kernel<D, 2><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 2>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
-  else bwd_dkdv_kernel<D, 1><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 1>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, p);
-  bwd_dq_kernel<D><<<dim3(S / 128, B * H), kThreads, DqCfg<D>::kSmem, stream>>>(tq128, tq64, tdo128, tdq, p);
+  if (pstages == 0) bwd_dkdv_kernel<D, 0><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 0>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, tq64_3d, tdo64_3d, p);
+  else if (pstages == 2) bwd_dkdv_kernel<D, 2><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 2>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, tq64_3d, tdo64_3d, p);
+  else bwd_dkdv_kernel<D, 1><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 1>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, tq64_3d, tdo64_3d, p);
+  bwd_dq_kernel<D><<<dim3(S / 128, B * H), kThreads, DqCfg<D>::kSmem, stream>>>(tq128, tq64, tdo128, tdq, tq64_3d, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

@@ -51,6 +51,26 @@ static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t 
   return r == CUDA_SUCCESS ? 0 : -11 - (int)r;
 }
 
+// 3-D view of a bf16 [rows, cols] matrix as {64 columns, rows, cols/64 column chunks}: ONE box of {64, box_rows, chunks} lands in
+// shared memory as `chunks` consecutive [box_rows x 128 B] 128B-swizzled blocks — the operand layout of the attention kernels —
+// with a single cp.async.bulk.tensor.3d instead of one 2-D box per 64-column chunk.
+static int make_tmap3(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t chunks) {
+  EncodeFn enc = get_encode();
+  if (!enc) return -10;
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
+  cuuint64_t dims[3] = {64, rows, cols / 64};
+  cuuint64_t strides[2] = {ld * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11 - (int)r;
+}
+
 struct MapKey {
   const void* ptr;
   uint64_t rows, cols, ld;
@@ -87,6 +107,23 @@ int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
   return 0;
 }
 
+
+int cached_tmap3(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t chunks) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key{ptr, rows, cols, ld, chunks, box_rows, 33};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    CUtensorMap m;
+    int rc = make_tmap3(&m, ptr, rows, cols, ld, box_rows, chunks);
+    if (rc) return rc;
+    if (cache.size() > 8192) cache.clear();
+    it = cache.emplace(key, m).first;
+  }
+  *out = it->second;
+  return 0;
+}
 
 int num_sms() {
   static int n = 0;

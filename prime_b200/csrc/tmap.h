@@ -9,5 +9,7 @@ namespace pbhost {
 // esize: 1 = fp8 (bytes), 2 = bf16, 4 = fp32.  Returns 0 on success.
 int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                 uint32_t box_rows, int esize = 2);
+// {64 columns, rows, cols/64 chunks} view with boxes of {64, box_rows, chunks}: one TMA instruction per multi-chunk operand tile.
+int cached_tmap3(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t chunks);
 int num_sms();
 }  // namespace pbhost
