@@ -539,9 +539,14 @@ struct DqCfg {
   static constexpr uint32_t kOffBar = kOffdS + 2 * kdSBytes;
   static constexpr uint32_t kSmem = kOffBar + 256 + 1024;
   static constexpr uint32_t tS = 0, tdP = 128, tdQ = 256;
+  // QT = 1 (D = 128): the resident Q and dO tiles are copied ONCE into tensor memory (2 x 64 columns of packed bf16 — exactly the
+  // 128 columns S, dP and dQ leave free) and S = Q·Kᵀ, dP = dO·Vᵀ take their A operand from there. A 128x64x16 MMA with both
+  // operands in shared memory fetches 6 KB in its 32 clk (192 B/clk against 128 B/clk of smem bandwidth) and the tensor core
+  // re-read all 64 KB of Q and dO for every 64 keys; with A in TMEM the same instruction fetches 2 KB.
+  static constexpr uint32_t tQ = 384, tdO = 448;
 };
 
-template <int D>
+template <int D, int QT>
 __global__ void __launch_bounds__(kThreads, 1)
     bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_qkv128, const __grid_constant__ CUtensorMap tmap_qkv64,
                   const __grid_constant__ CUtensorMap tmap_do128, const __grid_constant__ CUtensorMap tmap_dqkv,
@@ -563,7 +568,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* p_full = bars + 13;    // 2 (4 warps)
   uint64_t* acc_done = bars + 15;  // 2
   uint64_t* all_done = bars + 17;  // 1: every dQ MMA of this block has retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* a_in_tmem = bars + 18; // 8 warps: Q and dO have been copied into tensor memory (QT = 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqb = p.S / 128;
@@ -584,6 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(all_done, 1);
+    mbar_init(a_in_tmem, 8);
     for (int i = 0; i < C::kKVStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
@@ -643,6 +650,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       constexpr uint32_t idesc_s = idesc_bf16(128, 64, 0, 0);  // S[128 q x 64 kv] = Q Kᵀ
       constexpr uint32_t idesc_a = idesc_bf16(128, D, 0, 1);   // dQ[128 q x D] += dS · K   (K tile as MN-major B)
       mbar_wait(q_full, 0);
+      if (QT) {
+        mbar_wait(a_in_tmem, 0);
+        tc_fence_after();
+      }
       int tr_n = 0;
       auto issue_sd = [&](int t) {
         const int st = t & 1;
@@ -655,6 +666,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_after();
         const uint32_t q0 = smem_u32(sQ), d0 = smem_u32(sdO);
         const uint32_t k0 = smem_u32(sK + ks * C::kKVBytes), v0 = smem_u32(sV + ks * C::kKVBytes);
+        if (QT) {
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk)  // 16 head-dim elements = 8 TMEM columns of packed bf16 pairs per step
+            umma_bf16_ts(tmem_base + C::tS + st * 64, tmem_base + C::tQ + kk * 8,
+                         make_smem_desc(k0 + (kk >> 2) * (64 * 128) + (kk & 3) * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk)
+            umma_bf16_ts(tmem_base + C::tdP + st * 64, tmem_base + C::tdO + kk * 8,
+                         make_smem_desc(v0 + (kk >> 2) * (64 * 128) + (kk & 3) * 32, 16, 1024), idesc_s, kk != 0 ? 1u : 0u);
+        } else {
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c)
 #pragma unroll
@@ -667,6 +688,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int k = 0; k < 4; ++k)
             umma_bf16(tmem_base + C::tdP + st * 64, make_smem_desc(d0 + c * (128 * 128) + k * 32, 16, 1024),
                       make_smem_desc(v0 + c * (64 * 128) + k * 32, 16, 1024), idesc_s, (c | k) != 0 ? 1u : 0u);
+        }
         umma_commit(&s_full[st]);
       };
       auto sd_ready = [&](int t) {
@@ -706,6 +728,27 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float lse = p.lse2[((int64_t)bh) * p.S + q_idx];
     const float del_s = p.delta[((int64_t)bh) * p.S + q_idx];
+    if (QT) {
+      // group 0 copies Q, group 1 copies dO: thread = row = TMEM lane; un-swizzle the row's 16-byte pieces out of the
+      // [2 chunks][128 rows x 128 B] tile and store the 64 packed words in head-dim order
+      mbar_wait(q_full, 0);
+      const uint32_t src = smem_u32(half ? sdO : sQ) + (uint32_t)r * 128u;
+      const uint32_t dst = tmem_base + (half ? C::tdO : C::tQ) + lane_addr;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t w[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w[4 * j]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
+                       : "r"(src + (uint32_t)c * (128u * 128u) + (((uint32_t)j ^ (uint32_t)(r & 7)) << 4)));
+        tmem_st_32x32b_x32(dst + c * 32, w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_in_tmem);
+    }
     int tr_n = 0;
     const bool tr = q == 0 && lane == 0;
     for (int t = half; t < n_kv; t += 2) {  // the two math groups leapfrog over the kv tiles (see the dK/dV kernel)
@@ -811,7 +854,9 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(bwd_dkdv_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DkvCfg<D, 0>::kSmem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DqCfg<D>::kSmem);
+    e = cudaFuncSetAttribute(bwd_dq_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DqCfg<D>::kSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(bwd_dq_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DqCfg<D>::kSmem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -852,7 +897,13 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   if (pstages == 0) bwd_dkdv_kernel<D, 0><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 0>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, tq64_3d, tdo64_3d, p);
   else if (pstages == 2) bwd_dkdv_kernel<D, 2><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 2>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, tq64_3d, tdo64_3d, p);
   else bwd_dkdv_kernel<D, 1><<<dim3(S / 128, B * Hkv), kThreads, DkvCfg<D, 1>::kSmem, stream>>>(tq128, tq64, tdo64, tdq, tq64_3d, tdo64_3d, p);
-  bwd_dq_kernel<D><<<dim3(S / 128, B * H), kThreads, DqCfg<D>::kSmem, stream>>>(tq128, tq64, tdo128, tdq, tq64_3d, p);
+  static int dq_ts = -1;
+  if (dq_ts < 0) {
+    const char* ev = getenv("PB_ATTN_BWD_DQ_TS");
+    dq_ts = ev ? (atoi(ev) != 0) : 0;  // measured neutral (0.528 vs 0.524 ms): the kernel is not bound by operand fetch
+  }
+  if (dq_ts && D == 128) bwd_dq_kernel<D, 1><<<dim3(S / 128, B * H), kThreads, DqCfg<D>::kSmem, stream>>>(tq128, tq64, tdo128, tdq, tq64_3d, p);
+  else bwd_dq_kernel<D, 0><<<dim3(S / 128, B * H), kThreads, DqCfg<D>::kSmem, stream>>>(tq128, tq64, tdo128, tdq, tq64_3d, p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
