@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t ph = (it >> 1) & 1;
         {  // two tiles ahead whenever it costs nothing; never block in front of dV/dK of tile `it`
           SpinGuard guard;
-          while (!mbar_try_wait(&p_full[st], ph)) {
+          while (!mbar_test_wait(&p_full[st], ph)) {  // test_wait: try_wait may park the thread for a time slice, and the opportunistic issue below must not wait for that
             guard.tick();
             if (sd_next == it + 2 && sd_next < n_it && sd_ready(sd_next)) issue_sd(sd_next++);
           }
@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t ph = (t >> 1) & 1;
         {
           SpinGuard guard;
-          while (!mbar_try_wait(&p_full[st], ph)) {
+          while (!mbar_test_wait(&p_full[st], ph)) {  // test_wait: try_wait may park the thread for a time slice, and the opportunistic issue below must not wait for that
             guard.tick();
             if (sd_next == t + 2 && sd_next < n_kv && sd_ready(sd_next)) issue_sd(sd_next++);
           }

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           // softmax group has pulled tile g into registers, so when K(g+2) has landed too the group finds its next tile waiting.
           // Never block on it here — a blocking wait in front of P·V(t) measurably slows the whole pipeline down.
           SpinGuard guard;
-          while (!mbar_try_wait(&p_full[st], ph)) {
+          while (!mbar_test_wait(&p_full[st], ph)) {  // test_wait: try_wait may park the thread for a time slice, and the opportunistic issue below must not wait for that
             guard.tick();
             if (s_next == t + 2 && s_next < n_kv && s_ready(g + 2)) {
               issue_s(g + 2, s_next + 1 == n_kv);

@@ -52,7 +52,16 @@ def summarize_dq(ev):
                      "math_store": d.get(f"{g}.done", 0) - d.get(f"{g}.ds_buffer_free", 0),
                      "S_issue_to_ready": d.get(f"{g}.S_ready", 0) - d.get("mma.issue_S_dP", 0),
                      "done_to_dQ_issue": d.get("mma.issue_dQ", 0) - d.get(f"{g}.done", 0)})  # fmt: skip
-    return {"total_cycles": last, "tiles": len(rows), "cycles_per_tile": round(last / max(1, len(rows))), "per_tile": rows}
+    timeline = []
+    for r in range(4):
+        for k in range(256):
+            code, tile, clk = (int(x) for x in ev[r, k])
+            if code == 0:
+                break
+            timeline.append((clk - t0, ["loader", "mma", "math0", "math1"][r], str(names[r].get(code, code)), tile))
+    timeline.sort()
+    return {"total_cycles": last, "tiles": len(rows), "cycles_per_tile": round(last / max(1, len(rows))), "per_tile": rows,
+            "timeline": [{"cyc": c, "role": ro, "event": e, "tile": t} for c, ro, e, t in timeline]}
 
 
 def main():
