@@ -12,7 +12,7 @@ from ..core import APIError, Config
 from ..utils.display import DEPLOYMENT_STATUS_COLORS, colorize
 from ..utils.json_help import list_json_help
 from ..utils.time_utils import format_time_ago
-from ._common import OUTPUT_OPT, api, console, emit, handle_errors, make_app, paginate_hint
+from ._common import OUTPUT_OPT, api, console, emit, fail, handle_errors, make_app, paginate_hint
 
 app = make_app("Deploy trained adapters for inference")
 IN_FLIGHT = {"DEPLOYING", "UNLOADING"}
@@ -49,10 +49,15 @@ def _stop(blocker: tuple[str, int]) -> None:
 
 @app.command("list", epilog=list_json_help("models", {"id": "str", "display_name": "str|null", "base_model": "str", "status": "str", "deployment_status": "str"}))
 @handle_errors
-def list_deployments(limit: int = typer.Option(50, help="Maximum rows"), offset: int = typer.Option(0), output: str = OUTPUT_OPT) -> None:
-    """List trained adapters and where they stand."""
-    adapters, total = DeploymentsClient(api()).list_adapters(team_id=Config(writable=False).team_id, limit=limit, offset=offset)
-    payload = {"models": [a.model_dump(mode="json") for a in adapters], "total": total, "offset": offset, "limit": limit}
+def list_deployments(team: Optional[str] = typer.Option(None, "--team", "-t", help="Filter by team ID"),
+                     num: int = typer.Option(20, "--num", "-n", help="Items per page"),
+                     page: int = typer.Option(1, "--page", "-p", help="Page number"), output: str = OUTPUT_OPT) -> None:  # fmt: skip
+    """List trained adapters and where they stand (reference flags: packages/prime/src/prime_cli/commands/deployments.py:34-40)."""
+    if num < 1 or page < 1:
+        raise fail("--num and --page must be at least 1")
+    limit, offset = num, (page - 1) * num
+    adapters, total = DeploymentsClient(api()).list_adapters(team_id=team or Config(writable=False).team_id, limit=limit, offset=offset)
+    payload = {"models": [a.model_dump(mode="json") for a in adapters], "total": total, "page": page, "per_page": num}
     emit(output, payload, f"Models (Total: {total})",
          [("ID", "cyan"), "Name", ("Base model", "blue"), "Step", "Status", "Deployment", ("Created", "magenta")],
          [[a.id, a.display_name or "", a.base_model, a.step if a.step is not None else "", a.status,

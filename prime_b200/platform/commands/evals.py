@@ -283,7 +283,7 @@ def _clip(s: Any, n: int = 30) -> str:
 @app.command("list", epilog=list_json_help("evaluations", {"evaluation_id": "str", "name": "str", "model_name": "str", "status": "str", "total_samples": "int"}))
 @handle_errors
 def list_evals(output: str = typer.Option("table", "--output", "-o", help="table|json"), num: int = typer.Option(20, "--num", "-n", help="Items per page"),
-               page: int = typer.Option(1, "--page", "-p"), env: Optional[str] = typer.Option(None, "--env", "-e", help="Filter by environment name")) -> None:  # fmt: skip
+               page: int = typer.Option(1, "--page", "-p"), env: Optional[str] = typer.Option(None, "--env", "--env-name", "-e", help="Filter by environment (e.g. 'gsm8k' or 'owner/gsm8k')")) -> None:  # fmt: skip
     """List evaluations of the active account."""
     if page < 1 or num < 1:
         raise fail("--page and --num must be >= 1")
@@ -387,9 +387,9 @@ def push_single_eval(path_str: str, env_slug: str | None, run_id: str | None, ev
 @app.command("push", epilog=json_output_help({"evaluation_id": "str"}, "Auto-discovery batch push: {results: [{path, status, eval_id?, error?}]}"))
 def push_eval(
     config_path: Optional[str] = typer.Argument(None, help="Run directory with metadata.json + results.jsonl (auto-discovers outputs/evals/ when omitted)"),
-    env_id: Optional[str] = typer.Option(None, "--env", "-e", help="Environment slug (owner/name) or name"),
+    env_id: Optional[str] = typer.Option(None, "--env", "--env-id", "-e", help="Environment slug (owner/name) or name"),
     run_id: Optional[str] = typer.Option(None, "--run-id", "-r", help="Attach to a training run instead of an environment"),
-    eval_id: Optional[str] = typer.Option(None, "--eval", help="Update this existing evaluation"),
+    eval_id: Optional[str] = typer.Option(None, "--eval", "--eval-id", help="Push to this existing evaluation id"),
     output: str = typer.Option("pretty", "--output", "-o", help="json|pretty"),
     is_public: bool = typer.Option(False, "--public", help="Make the evaluation public"),
 ) -> None:

@@ -28,7 +28,7 @@ from ..utils.hosted_eval import PROGRESS_BAR, get_new_log_lines
 from ..utils.json_help import json_output_help, list_json_help
 from ..utils.prompt import confirm_or_skip
 from ..utils.time_utils import format_time_ago
-from ._common import OUTPUT_OPT, api, console, emit, fail, handle_errors, make_app
+from ._common import OUTPUT_OPT, api, console, emit, fail, handle_errors, make_app, paginate_hint
 
 app = make_app("Hosted RL training", default_cmd="run")
 LEVEL_STYLES = {"DEBUG": "dim", "INFO": "cyan", "WARNING": "yellow", "WARN": "yellow", "ERROR": "red", "CRITICAL": "bold red", "SUCCESS": "green"}
@@ -415,30 +415,43 @@ def list_models(output: str = OUTPUT_OPT) -> None:
          [[m.name, "[yellow]at capacity[/yellow]" if m.at_capacity else "[green]available[/green]"] for m in models])  # fmt: skip
 
 
-def _list_runs(output: str, team_id: str | None) -> None:
-    runs = RLClient(api()).list_runs(team_id=team_id or Config(writable=False).team_id)
-    rows = [run_row(r) for r in sorted(runs, key=lambda r: r.created_at, reverse=True)]
-    emit(output, {"runs": rows, "total_count": len(rows)}, f"RL Runs (Total: {len(rows)})",
+def _list_runs(output: str, team: str | None, num: int, page: int) -> None:
+    """The runs endpoint is not paginated: sort newest first and page client-side, like the reference
+    (packages/prime/src/prime_cli/commands/rl.py:945-978)."""
+    if num < 1 or page < 1:
+        raise fail("--num and --page must be at least 1")
+    runs = sorted(RLClient(api()).list_runs(team_id=team or Config(writable=False).team_id), key=lambda r: r.created_at, reverse=True)
+    total = len(runs)
+    rows = [run_row(r) for r in runs[(page - 1) * num : page * num]]
+    if output != "json" and not rows:
+        console.print("[yellow]No more results.[/yellow]" if page > 1 else "[yellow]No RL training runs found.[/yellow]")
+        return
+    emit(output, {"runs": rows, "total": total, "total_count": total, "page": page, "per_page": num}, f"RL Runs (Total: {total})",
          [("ID", "cyan"), ("Name", "blue"), "Status", ("Model", "green"), "Environments", "Steps", ("Created", "magenta")],
          [[r["id"], r["name"] or "", colorize(r["status"], RUN_STATUS_COLORS), r["model"], ", ".join(map(str, r["environments"])), r["max_steps"],
-           format_time_ago(r["created_at"])] for r in rows])  # fmt: skip
+           format_time_ago(r["created_at"])] for r in rows],
+         paginate_hint(total, (page - 1) * num, num, "runs"))  # fmt: skip
 
 
-_RUN_LIST_HELP = list_json_help("runs", {"id": "str", "name": "str|null", "status": "str", "model": "str", "created_at": "str"})
+_RUN_LIST_HELP = list_json_help("runs", {"id": "str", "name": "str|null", "status": "str", "model": "str", "created_at": "str"},
+                                {"total": "int", "page": "int", "per_page": "int"})  # fmt: skip
+_TEAM_OPT = typer.Option(None, "--team", "--team-id", "-t", help="Filter by team ID")
+_NUM_OPT = typer.Option(20, "--num", "-n", help="Items per page")
+_PAGE_OPT = typer.Option(1, "--page", "-p", help="Page number")
 
 
 @app.command("list", epilog=_RUN_LIST_HELP)
 @handle_errors
-def list_runs(output: str = OUTPUT_OPT, team_id: Optional[str] = typer.Option(None, "--team-id")) -> None:
+def list_runs(team: Optional[str] = _TEAM_OPT, num: int = _NUM_OPT, page: int = _PAGE_OPT, output: str = OUTPUT_OPT) -> None:
     """Your RL runs, newest first."""
-    _list_runs(output, team_id)
+    _list_runs(output, team, num, page)
 
 
 @app.command("ls", hidden=True)
 @handle_errors
-def ls_runs(output: str = OUTPUT_OPT, team_id: Optional[str] = typer.Option(None, "--team-id")) -> None:
+def ls_runs(team: Optional[str] = _TEAM_OPT, num: int = _NUM_OPT, page: int = _PAGE_OPT, output: str = OUTPUT_OPT) -> None:
     """Alias of 'list'."""
-    _list_runs(output, team_id)
+    _list_runs(output, team, num, page)
 
 
 @app.command("get", epilog=json_output_help({"id": "str", "status": "str", "error_message": "str|null"}))
@@ -540,18 +553,20 @@ def init_config(path: str = typer.Argument("rl.toml", help="Where to write the t
 
 @app.command("metrics")
 @handle_errors
-def get_metrics(run_id: str = typer.Argument(...), min_step: Optional[int] = typer.Option(None), max_step: Optional[int] = typer.Option(None),
-                limit: Optional[int] = typer.Option(None)) -> None:  # fmt: skip
+def get_metrics(run_id: str = typer.Argument(...), min_step: Optional[int] = typer.Option(None, "--min-step", help="Minimum step (inclusive)"),
+                max_step: Optional[int] = typer.Option(None, "--max-step", help="Maximum step (inclusive)"),
+                limit: Optional[int] = typer.Option(None, "--limit", "-n", help="Maximum number of records")) -> None:  # fmt: skip
     """Training metrics as JSON."""
     output_data_as_json({"run_id": run_id, "metrics": RLClient(api()).get_metrics(run_id, min_step, max_step, limit)}, console)
 
 
 @app.command("rollouts")
 @handle_errors
-def get_rollouts(run_id: str = typer.Argument(...), step: int = typer.Option(..., "--step", "-s"), page: int = typer.Option(1),
-                 limit: int = typer.Option(100)) -> None:  # fmt: skip
+def get_rollouts(run_id: str = typer.Argument(...), step: int = typer.Option(..., "--step", "-s", help="Step number"),
+                 page: int = typer.Option(1, "--page", "-p", help="Page number (1-indexed)"),
+                 num: int = typer.Option(100, "--num", "--limit", "-n", help="Items per page")) -> None:  # fmt: skip
     """Rollout samples of one step as JSON."""
-    output_data_as_json(RLClient(api()).get_rollouts(run_id, step, page, limit), console)
+    output_data_as_json(RLClient(api()).get_rollouts(run_id, step, page, num), console)
 
 
 @app.command("progress")
@@ -571,7 +586,9 @@ def get_distributions(run_id: str = typer.Argument(...), type: Optional[str] = t
 
 @app.command("checkpoints", epilog=list_json_help("checkpoints", {"id": "str", "step": "int", "status": "str", "size_bytes": "int|null", "storage_url": "str"}))
 @handle_errors
-def list_checkpoints(run_id: str = typer.Argument(...), status: Optional[str] = typer.Option(None, help="Filter, e.g. READY"), output: str = OUTPUT_OPT) -> None:
+def list_checkpoints(run_id: str = typer.Argument(...),
+                     status: Optional[str] = typer.Option(None, "--status", "-s", help="Filter by status (READY, PENDING, UPLOADING, FAILED)"),
+                     output: str = OUTPUT_OPT) -> None:  # fmt: skip
     """Checkpoints written by a run (pass an id as `checkpoint_id` to warm-start another run)."""
     from ..utils.formatters import format_size
 

@@ -342,7 +342,7 @@ _PORT_FIELDS = {"exposure_id": "str", "sandbox_id": "str", "port": "int", "name"
 @handle_errors
 def expose_port(sandbox_id: str = typer.Argument(...), port: int = typer.Argument(..., help="Port inside the sandbox"),
                 name: Optional[str] = typer.Option(None, help="Friendly name"),
-                protocol: str = typer.Option("HTTP", help="HTTP (public URL) or TCP (host:port endpoint)"), output: str = OUTPUT_OPT) -> None:  # fmt: skip
+                protocol: str = typer.Option("HTTP", "--protocol", "-p", help="HTTP (public URL) or TCP (host:port endpoint)"), output: str = OUTPUT_OPT) -> None:  # fmt: skip
     """Expose a sandbox port to the internet."""
     proto = protocol.upper()
     if proto not in ("HTTP", "TCP"):

@@ -147,3 +147,28 @@ def test_whoami_persists_user_id_and_shows_scopes(fake_api):
     assert Config(writable=False).user_id == "u-42"
     fake_api({("GET", "/user/whoami"): {"data": "nope"}}, who_mod)
     assert runner.invoke(app, ["whoami"]).exit_code == 1
+
+
+def test_reference_pagination_flags_on_rl_and_deployments(fake_api):
+    """`--team/-t`, `--num/-n`, `--page/-p` as in the reference (rl list pages client-side: the endpoint returns everything)."""
+    from prime_b200.platform.commands import deployments as dep_mod
+    from prime_b200.platform.commands import rl as rl_mod
+
+    def run(i):
+        return {"id": f"r{i}", "name": f"run{i}", "userId": "u", "teamId": None, "status": "RUNNING", "baseModel": "Qwen/Qwen3-4B",
+                "environments": [{"id": "gsm8k"}], "rolloutsPerExample": 8, "seqLen": 2048, "maxSteps": 10, "batchSize": 32,
+                "createdAt": f"2026-01-{i + 1:02d}T00:00:00Z", "updatedAt": T}  # fmt: skip
+
+    api = fake_api({("GET", "/rft/runs"): {"runs": [run(i) for i in range(5)]}}, rl_mod)
+    out = json.loads(runner.invoke(app, ["rl", "list", "-n", "2", "-p", "2", "-t", "team9", "--output", "json"]).output)
+    assert [r["id"] for r in out["runs"]] == ["r2", "r1"] and out["total"] == 5 and out["page"] == 2 and out["per_page"] == 2
+    assert api.called("GET", "/rft/runs")[0][2] == {"team_id": "team9"}
+    assert "No more results" in runner.invoke(app, ["rl", "ls", "--page", "9"]).output
+    assert runner.invoke(app, ["rl", "list", "--num", "0"]).exit_code == 1
+    api2 = fake_api({("GET", "/rft/adapters"): {"adapters": [], "total": 45}}, dep_mod)
+    out = json.loads(runner.invoke(app, ["deployments", "list", "-n", "20", "-p", "3", "-t", "team9", "--output", "json"]).output)
+    assert out["total"] == 45 and out["page"] == 3 and out["per_page"] == 20
+    assert api2.called("GET", "/rft/adapters")[0][2] == {"team_id": "team9", "limit": 20, "offset": 40}
+    for argv in (["eval", "list", "--help"], ["eval", "push", "--help"]):
+        helptext = runner.invoke(app, argv).output
+        assert "--env" in helptext
