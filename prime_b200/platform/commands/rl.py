@@ -465,7 +465,7 @@ def get_run(run_id: str = typer.Argument(...), output: str = OUTPUT_OPT) -> None
 
 @app.command("stop")
 @handle_errors
-def stop_run(run_id: str = typer.Argument(...), yes: bool = typer.Option(False, "--yes", "-y")) -> None:
+def stop_run(run_id: str = typer.Argument(...), yes: bool = typer.Option(False, "--yes", "-y", "--force", "-f", help="Skip confirmation")) -> None:
     """Stop a running run (checkpoints written so far are kept)."""
     if not confirm_or_skip(f"Stop run {run_id}?", yes):
         raise typer.Exit(0)
@@ -475,7 +475,7 @@ def stop_run(run_id: str = typer.Argument(...), yes: bool = typer.Option(False, 
 
 @app.command("delete")
 @handle_errors
-def delete_run(run_id: str = typer.Argument(...), yes: bool = typer.Option(False, "--yes", "-y")) -> None:
+def delete_run(run_id: str = typer.Argument(...), yes: bool = typer.Option(False, "--yes", "-y", "--force", "-f", help="Skip confirmation")) -> None:
     """Delete a run and its records."""
     if not confirm_or_skip(f"Delete run {run_id}? This cannot be undone.", yes):
         raise typer.Exit(0)
@@ -485,7 +485,7 @@ def delete_run(run_id: str = typer.Argument(...), yes: bool = typer.Option(False
 
 @app.command("restart")
 @handle_errors
-def restart_run(run_id: str = typer.Argument(...), yes: bool = typer.Option(False, "--yes", "-y")) -> None:
+def restart_run(run_id: str = typer.Argument(...), yes: bool = typer.Option(False, "--yes", "-y", "--force", "-f", help="Skip confirmation")) -> None:
     """Restart a RUNNING run from its latest checkpoint (server side)."""
     client = RLClient(api())
     run = client.get_run(run_id)
