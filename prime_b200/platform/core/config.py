@@ -145,7 +145,8 @@ class Config:
     def team_role(self) -> str | None:
         return self.data.get("team_role") or None
 
-    def set_team(self, team_id: str | None, team_name: str | None = None, team_role: str | None = None) -> None:
+    def set_team(self, value: str | None = None, team_name: str | None = None, team_role: str | None = None, *, team_id: str | None = None) -> None:
+        team_id = value if value is not None else team_id  # `value` is the reference's parameter name; `team_id` kept for callers
         self.data["team_id"] = team_id or None
         self.data["team_name"] = team_name if team_id else None
         self.data["team_role"] = team_role if team_id else None
@@ -192,6 +193,10 @@ class Config:
     @property
     def current_environment(self) -> str:
         return self.data.get("current_environment") or BUILTIN_CONTEXT
+
+    def set_current_environment(self, value: str) -> None:
+        """Remember which named context is active (reference: packages/prime/src/prime_cli/core/config.py:212-215)."""
+        self._set("current_environment", value)
 
     @property
     def share_resources_with_team(self) -> bool:

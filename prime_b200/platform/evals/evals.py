@@ -329,3 +329,18 @@ class AsyncEvalsClient(_Common):
 
     async def get_samples(self, evaluation_id: str, page: int = 1, limit: int = 100) -> dict[str, Any]:
         return await self.client.request("GET", f"/evaluations/{evaluation_id}/samples", params={"page": page, "limit": limit})
+
+    async def aclose(self) -> None:
+        """Close the transport (reference: packages/prime-evals/src/prime_evals/evals.py:727-737)."""
+        closer = getattr(self.client, "aclose", None)
+        if closer is not None:
+            await closer()
+        if self._http is not None:
+            await self._http.aclose()
+
+    async def __aenter__(self) -> "AsyncEvalsClient":
+        return self
+
+    async def __aexit__(self, *exc: Any) -> None:
+        await self.aclose()
+
