@@ -54,3 +54,11 @@ def validate_output_format(fmt: str, console=None) -> str:
         (console or get_console()).print(f"[red]Error:[/red] --output must be 'table' or 'json', got {fmt!r}")
         raise typer.Exit(1)
     return fmt
+
+
+def get_eval_viewer_url(evaluation_id: str) -> str:
+    """Dashboard page of one evaluation (reference: packages/prime/src/prime_cli/utils/display.py:47-50)."""
+    from ..core import Config
+
+    return f"{Config(writable=False).frontend_url.rstrip('/')}/dashboard/evaluations/{evaluation_id}"
+

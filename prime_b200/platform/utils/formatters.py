@@ -59,3 +59,20 @@ def format_resources(cpu: float | None = None, memory_gb: float | None = None, d
     if gpu:
         parts.append(f"{gpu}x {gpu_type or 'GPU'}")
     return ", ".join(parts) or "N/A"
+
+
+# ---- names the reference exports (packages/prime/src/prime_cli/utils/formatters.py:24-70), kept for drop-in imports
+def obfuscate_secrets(secrets: Mapping[str, Any] | None) -> dict[str, str]:
+    """Keys only: every value is shown as ``***`` (secrets are never echoed, not even partially)."""
+    return {k: "***" for k in (secrets or {})}
+
+
+def format_gpu_spec(gpu_type: str, gpu_count: int) -> str:
+    return f"{gpu_type} x{gpu_count}"
+
+
+def format_file_size(size_bytes: int) -> str:
+    """``1536`` → ``1.5 KB``; plain byte counts below 1 KiB."""
+    n = int(size_bytes)
+    return f"{n} bytes" if n < 1024 else format_size(n)
+

@@ -18,3 +18,9 @@ def list_json_help(key: str, item_fields: dict[str, str], extra: dict[str, str] 
     shape: dict[str, Any] = {key: [item_fields]}
     shape.update(extra or {})
     return json_output_help(shape)
+
+
+def json_help(*lines: str) -> str:
+    """Epilog for commands that ALWAYS print JSON (reference: packages/prime/src/prime_cli/utils/json_help.py:16-18)."""
+    return "\n".join(["JSON output:", "", *lines])
+

@@ -220,3 +220,9 @@ def default_group(default_cmd_name: str = "run"):
             super().__init__(*a, default_cmd_name=default_cmd_name, **kw)
 
     return _G
+
+
+# names under which the reference exposes the same two classes (packages/prime/src/prime_cli/utils/plain.py:40, :158)
+PrimeConsole = Out
+PlainAwareTyperGroup = PlainGroup
+

@@ -147,3 +147,15 @@ async def test_async_client_roundtrip():
     async with AsyncAPIClient(api_key="k", transport=httpx.MockTransport(h)) as c:
         r = await c.post("/sandbox", json={"a": 1})
     assert r == {"path": "/api/v1/sandbox", "body": {"a": 1}}
+
+
+def test_reference_helper_names_are_importable():
+    """Drop-in names of the reference's utils (SURVEY §2.2.1 #4-#6, #13)."""
+    from prime_b200.platform.utils import display, formatters, json_help, plain
+
+    assert formatters.obfuscate_secrets({"HF_TOKEN": "hf_abc", "K": "v"}) == {"HF_TOKEN": "***", "K": "***"}
+    assert formatters.format_gpu_spec("B200_180GB", 8) == "B200_180GB x8"
+    assert formatters.format_file_size(12) == "12 bytes" and formatters.format_file_size(1536) == "1.5 KB" and formatters.format_file_size(5 << 30) == "5.0 GB"
+    assert json_help.json_help(".id = string").startswith("JSON output:")
+    assert display.get_eval_viewer_url("ev1").endswith("/dashboard/evaluations/ev1")
+    assert plain.PrimeConsole is plain.Out and plain.PlainAwareTyperGroup is plain.PlainGroup
