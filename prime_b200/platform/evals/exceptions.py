@@ -7,6 +7,10 @@ class EvalsAPIError(APIError):
     pass
 
 
+class EnvironmentNotFoundError(EvalsAPIError):
+    """The hub has no environment under that slug / name / id (reference: packages/prime-evals/src/prime_evals/exceptions.py:10-13)."""
+
+
 class EvaluationNotFoundError(EvalsAPIError):
     pass
 

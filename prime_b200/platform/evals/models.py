@@ -101,3 +101,16 @@ class Environment(BaseModel):
     owner: str | None = None
     version: str | None = None
     description: str | None = None
+
+
+class PushSamplesRequest(BaseModel):
+    """Body of ``POST /evaluations/{id}/samples`` (reference: packages/prime-evals/src/prime_evals/models.py:114-117)."""
+
+    samples: list[dict[str, Any]]
+
+
+class FinalizeEvaluationRequest(BaseModel):
+    """Body of ``POST /evaluations/{id}/finalize`` (reference: packages/prime-evals/src/prime_evals/models.py:120-123)."""
+
+    metrics: dict[str, Any] | None = None
+

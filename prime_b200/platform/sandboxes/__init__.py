@@ -37,3 +37,5 @@ from .models import (  # noqa: F401
 from .sandbox import AsyncSandboxClient, AsyncTemplateClient, SandboxClient, TemplateClient  # noqa: F401
 
 __version__ = "0.1.0"
+
+TimeoutError = APITimeoutError  # the reference exports the transport timeout under this short name as well

@@ -1,5 +1,6 @@
 """Expose a local port through a managed ``frpc`` child process."""
 
+from ..core import Config  # noqa: F401
 from .binary import FRPC_VERSION, get_frpc_path  # noqa: F401
 from .client import TunnelClient  # noqa: F401
 from .exceptions import (  # noqa: F401

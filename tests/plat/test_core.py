@@ -159,3 +159,25 @@ def test_reference_helper_names_are_importable():
     assert json_help.json_help(".id = string").startswith("JSON output:")
     assert display.get_eval_viewer_url("ev1").endswith("/dashboard/evaluations/ev1")
     assert plain.PrimeConsole is plain.Out and plain.PlainAwareTyperGroup is plain.PlainGroup
+
+
+def test_package_export_surfaces_match_the_reference():
+    """Every name the five reference packages export from their __init__ resolves here too."""
+    import prime_b200.platform as P
+    import prime_b200.platform.evals as E
+    import prime_b200.platform.mcp as M
+    import prime_b200.platform.sandboxes as S
+    import prime_b200.platform.tunnel as Tn
+
+    for name in ("APIClient", "APIError", "APITimeoutError", "AsyncAPIClient", "AsyncSandboxClient", "CommandRequest", "CommandResponse",
+                 "CommandTimeoutError", "Config", "CreateSandboxRequest", "Sandbox", "SandboxClient", "SandboxNotRunningError", "SandboxStatus",
+                 "UpdateSandboxRequest"):  # fmt: skip
+        assert getattr(P, name) is not None
+    assert S.TimeoutError is S.APITimeoutError
+    for name in ("APIError", "APITimeoutError", "Config", "EnvironmentNotFoundError", "FinalizeEvaluationRequest", "PaymentRequiredError",
+                 "PushSamplesRequest", "UnauthorizedError", "EvalsClient", "AsyncEvalsClient"):  # fmt: skip
+        assert hasattr(E, name), name
+    assert E.PushSamplesRequest(samples=[{"a": 1}]).model_dump() == {"samples": [{"a": 1}]}
+    assert E.FinalizeEvaluationRequest().metrics is None
+    assert Tn.Config is P.Config
+    assert callable(M.make_prime_request) and M.pods.__name__.endswith("tools.pods") and M.ssh and M.availability
