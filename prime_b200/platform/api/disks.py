@@ -52,6 +52,12 @@ class DiskCreateRequest(ApiModel):
     data_center_id: str | None = None
 
 
+class DiskUpdateRequest(ApiModel):
+    """Body of ``PATCH /disks/{id}`` (reference: packages/prime/src/prime_cli/api/disks.py, DiskUpdateRequest)."""
+
+    name: str
+
+
 class DiskDeleteResponse(ApiModel):
     status: str
 
