@@ -46,3 +46,18 @@ class OutputCollector:
 
     def result(self) -> tuple[str, str, int | None]:
         return "".join(self.stdout), "".join(self.stderr), self.exit_code
+
+
+# ---- the reference's functional spelling of the same two steps (rpc_command_session.py:69-108), for code written against it
+COMMAND_SESSION_START_RPC_METHOD = START_METHOD
+build_command_session_start_request = build_start_request
+
+
+def collect_command_session_start_event(response, stdout_parts: list[str], stderr_parts: list[str]) -> int | None:
+    """Append the event's output to the caller's lists; returns the exit code once the ``end`` event arrives, else ``None``."""
+    c = OutputCollector()
+    c.feed(response)
+    stdout_parts.extend(c.stdout)
+    stderr_parts.extend(c.stderr)
+    return c.exit_code
+
