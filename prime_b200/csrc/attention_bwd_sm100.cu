@@ -70,6 +70,7 @@ struct BwdParams {
   // interleaved-pair convention) so no separate pass over the 200 MB dQKV tensor is needed. nullptr = plain attention backward.
   const float* rope_cos;
   const float* rope_sin;
+  int split_issue;  // S/dP and the accumulating MMAs (dQ | dV,dK) are issued by two different threads (warp 1 / warp 3)
   int tma3d;        // streamed operand tiles as ONE 3-D TMA box per operand instead of one 2-D box per 64-column chunk
   int l2_prefetch;  // issue cp.async.bulk.prefetch for the input tile a ring-depth ahead (PB_ATTN_BWD_L2PF, A/B switch)
 };
@@ -326,6 +327,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (it + 2 < n_it) issue_sd(it + 2);
         }
         umma_commit(all_done);
+      } else if (p.split_issue) {
+        for (int it = 0; it < n_it; ++it) issue_sd(it);  // dV/dK are issued by warp 3 (see bwd_dq_kernel); s_empty keeps this ≤ 2 tiles ahead
       } else {
       issue_sd(0);
       int sd_next = 1;  // next tile whose S/dP has not been issued
@@ -359,6 +362,35 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       umma_commit(all_done);
       }
+    }
+  } else if (warp == 3) {
+    if (lane == 0 && p.split_issue && PST != 0) {
+      // ------------------------------------------------------------------ second MMA issuer: dV += Pᵀ·dO, dK += dSᵀ·Q
+      constexpr uint32_t idesc_a = idesc_bf16(128, D, 0, 1);
+      mbar_wait(kv_full, 0);
+      int tr_n = 128;
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const int qs = it % C::kQStages;
+        mbar_wait(&p_full[st], (it >> 1) & 1);
+        mbar_wait(&q_full[qs], (it / C::kQStages) & 1);  // landed long ago: acquire for this thread
+        trace_ev(p, 1, tr_n, 3, it);
+        tc_fence_after();
+        const uint32_t pbuf = PST == 2 ? (uint32_t)st * C::kPBytes : 0u;
+        const uint32_t pa = smem_u32(sP) + pbuf, da = smem_u32(sdS) + pbuf;
+        const uint32_t q0 = smem_u32(sQ + qs * C::kQBytes), d0 = smem_u32(sdO + qs * C::kQBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + C::tdV, make_smem_desc(pa + kk * 32, 16, 1024), make_smem_desc(d0 + kk * 2048, 64 * 128, 1024), idesc_a,
+                    (it | kk) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + C::tdK, make_smem_desc(da + kk * 32, 16, 1024), make_smem_desc(q0 + kk * 2048, 64 * 128, 1024), idesc_a,
+                    (it | kk) != 0 ? 1u : 0u);
+        umma_commit(&q_empty[qs]);
+        umma_commit(&acc_done[st]);
+      }
+      umma_commit(all_done);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax-backward math + epilogue
@@ -694,6 +726,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto sd_ready = [&](int t) {
         return mbar_test_wait(&kv_full[t % C::kKVStages], (t / C::kKVStages) & 1) && mbar_test_wait(&s_empty[t & 1], ((t >> 1) & 1) ^ 1);
       };
+      if (p.split_issue) {
+        // this thread only feeds S/dP (back-pressured by s_empty: at most two tiles ahead); dQ is issued by warp 3. One thread doing
+        // both spends ≈1150 clk inside a batch of 16 S/dP MMAs (the operand-bound tensor pipe back-pressures the issue) and
+        // cannot see the other group's p_full meanwhile — dQ(t) then went out ≈500 clk late on every tile (trace)
+        for (int t = 0; t < n_kv; ++t) issue_sd(t);
+      } else {
       issue_sd(0);  // S/dP: one tile ahead mandatory, two ahead opportunistic (see the dK/dV kernel)
       int sd_next = 1;
       for (int t = 0; t < n_kv; ++t) {
@@ -715,6 +753,29 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int kk = 0; kk < 4; ++kk)  // K = 64 kv rows
           umma_bf16(tmem_base + C::tdQ, make_smem_desc(da + kk * 32, 16, 1024), make_smem_desc(k0 + kk * 2048, 64 * 128, 1024),
                     idesc_a, (t | kk) != 0 ? 1u : 0u);
+        umma_commit(&kv_empty[ks]);
+        umma_commit(&acc_done[st]);
+      }
+      umma_commit(all_done);
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0 && p.split_issue) {
+      // ------------------------------------------------------------------ second MMA issuer: dQ += dS·K as soon as dS(t) is in smem
+      constexpr uint32_t idesc_a = idesc_bf16(128, D, 0, 1);
+      int tr_n = 128;  // upper half of the MMA role's trace slots
+      for (int t = 0; t < n_kv; ++t) {
+        const int st = t & 1;
+        const int ks = t % C::kKVStages;
+        mbar_wait(&p_full[st], (t >> 1) & 1);
+        mbar_wait(&kv_full[ks], (t / C::kKVStages) & 1);  // landed long ago (S of this tile used it): acquire for this thread
+        trace_ev(p, 5, tr_n, 3, t);
+        tc_fence_after();
+        const uint32_t da = smem_u32(sdS + st * C::kdSBytes), k0 = smem_u32(sK + ks * C::kKVBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + C::tdQ, make_smem_desc(da + kk * 32, 16, 1024), make_smem_desc(k0 + kk * 2048, 64 * 128, 1024), idesc_a,
+                    (t | kk) != 0 ? 1u : 0u);
         umma_commit(&kv_empty[ks]);
         umma_commit(&acc_done[st]);
       }
@@ -877,6 +938,11 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   CUtensorMap tq64_3d, tdo64_3d;
   if ((rc = pbhost::cached_tmap3(&tq64_3d, qkv, rows, wqkv, wqkv, 64, D / 64))) return rc;
   if ((rc = pbhost::cached_tmap3(&tdo64_3d, dout, rows, wo, wo, 64, D / 64))) return rc;
+  static int split_issue = -1;
+  if (split_issue < 0) {
+    const char* ev = getenv("PB_ATTN_BWD_SPLIT_ISSUE");
+    split_issue = ev ? (atoi(ev) != 0) : 1;
+  }
   static int tma3d = -1;
   if (tma3d < 0) {
     const char* ev = getenv("PB_ATTN_BWD_TMA3D");
@@ -887,7 +953,7 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
     const char* ev = getenv("PB_ATTN_BWD_L2PF");
     l2pf = ev ? (atoi(ev) != 0) : 1;
   }
-  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace, rope_cos, rope_sin, tma3d, l2pf};
+  BwdParams p{lse2, delta, B, S, H, Hkv, scale, scale * 1.4426950408889634f, causal, g_bwd_trace, rope_cos, rope_sin, split_issue, tma3d, l2pf};
   if (g_bwd_pstages < 0) {
     const char* ev = getenv("PB_ATTN_BWD_PSTAGES");
     g_bwd_pstages = ev ? atoi(ev) : 2;

@@ -37,7 +37,7 @@ def summarize_dq(ev):
         for k in range(256):
             code, tile, clk = (int(x) for x in ev[r, k])
             if code == 0:
-                break
+                continue
             role = ["loader", "mma", "math0", "math1"][r]
             by.setdefault(tile, {})[f"{role}.{names[r].get(code, code)}"] = clk - t0
             last = max(last, clk - t0)
@@ -57,7 +57,7 @@ def summarize_dq(ev):
         for k in range(256):
             code, tile, clk = (int(x) for x in ev[r, k])
             if code == 0:
-                break
+                continue
             timeline.append((clk - t0, ["loader", "mma", "math0", "math1"][r], str(names[r].get(code, code)), tile))
     timeline.sort()
     return {"total_cycles": last, "tiles": len(rows), "cycles_per_tile": round(last / max(1, len(rows))), "per_tile": rows,
@@ -91,7 +91,7 @@ def main():
         for k in range(256):
             code, tile, clk = (int(x) for x in ev[r, k])
             if code == 0:
-                break
+                continue
             timeline.append({"role": role, "event": CODES[role].get(code, str(code)), "tile": tile, "cyc": clk - t0})
     timeline.sort(key=lambda e: e["cyc"])
     # per-tile phase summary
