@@ -88,10 +88,11 @@ def start_tunnel(port: int = typer.Option(8765, "--port", "-p", help="Local port
             console.print(f"\n[red]Tunnel limit reached:[/red] {e}\n[dim]Delete an existing tunnel before creating a new one.[/dim]")
             raise typer.Exit(1)
         except TunnelTimeoutError as e:
-            console.print(f"\n[red]Connection timed out:[/red] {e}")
+            console.print(f"\n[red]Connection timed out:[/red] {e}\n[dim]{e.hint}[/dim]")
             raise typer.Exit(1)
         except Exception as e:
-            console.print(f"[red]Error:[/red] {e}")
+            hint = getattr(e, "hint", None)
+            console.print(f"[red]Error:[/red] {e}" + (f"\n[dim]{hint}[/dim]" if hint else ""))
             raise typer.Exit(1)
         finally:
             await tunnel.stop()
