@@ -158,17 +158,7 @@ def load_hosted_eval_configs(config_path: str) -> list[dict[str, Any]]:
 
 # ------------------------------------------------------------------------------------------------- hosted plumbing
 def hosted_payload(c: HostedEvalConfig) -> dict[str, Any]:
-    ec: dict[str, Any] = {"num_examples": c.num_examples, "rollouts_per_example": c.rollouts_per_example,
-                          "allow_sandbox_access": c.allow_sandbox_access, "allow_instances_access": c.allow_instances_access}  # fmt: skip
-    for k in ("env_args", "custom_secrets", "sampling_args", "api_base_url", "api_key_var"):
-        if getattr(c, k):
-            ec[k] = getattr(c, k)
-    if c.timeout_minutes is not None:
-        ec["timeout_minutes"] = c.timeout_minutes
-    p: dict[str, Any] = {"environment_ids": [c.environment_id], "inference_model": c.inference_model, "eval_config": ec}
-    if c.name:
-        p["name"] = c.name
-    return p
+    return c.payload()
 
 
 def create_hosted(client: APIClient, c: HostedEvalConfig, environment_ids: list[str] | None = None) -> dict[str, Any]:
@@ -256,7 +246,7 @@ def follow_logs(client: APIClient, eval_id: str, poll_interval: float, sleep=tim
                 console.print(ln, markup=False, highlight=False)
             shown = logs
         raw, st = parse_status(data)
-        if st in EvalStatus.terminal_statuses():
+        if st is not None and st.is_terminal:
             console.print()
             print_eval_status(data)
             url = get_eval_viewer_url(eval_id)

@@ -9,7 +9,6 @@ environment ids, and serialises to the API with ``None`` omitted.
 from __future__ import annotations
 
 import json
-import re
 import time
 import tomllib
 from pathlib import Path
@@ -24,7 +23,7 @@ from ..core import APIError, Config
 from ..utils.display import RUN_STATUS_COLORS, colorize, output_data_as_json, validate_output_format
 from ..utils.env_vars import EnvParseError, collect_env_vars
 from ..utils.formatters import strip_ansi
-from ..utils.hosted_eval import PROGRESS_BAR, get_new_log_lines
+from ..utils.hosted_eval import get_new_log_lines, tqdm_line
 from ..utils.json_help import json_output_help, list_json_help
 from ..utils.prompt import confirm_or_skip
 from ..utils.time_utils import format_time_ago
@@ -292,7 +291,7 @@ def clean_logs(text: str) -> list[str]:
             out.append(f)
             continue
         plain = strip_ansi(line)
-        if (PROGRESS_BAR.search(plain) or re.search(r"\d+%\|", plain)) and "100%" not in plain:
+        if tqdm_line(plain) == "":
             continue  # tqdm refreshes: keep only the completed bar
         if plain.strip():
             out.append(plain)

@@ -6,7 +6,7 @@ from datetime import datetime
 from enum import Enum
 from typing import Any
 
-from pydantic import BaseModel, ConfigDict, Field, model_validator
+from pydantic import BaseModel, ConfigDict, Field, create_model, model_validator
 
 from ..api._base import ApiModel
 
@@ -29,11 +29,38 @@ class AdvancedConfigs(BaseModel):
     model_config = ConfigDict(extra="allow")
 
 
-class Sandbox(ApiModel):
+class _Wire(BaseModel):
+    """Request bodies go out in snake_case, ``None`` omitted."""
+
+    def wire(self) -> dict[str, Any]:
+        return self.model_dump(by_alias=False, exclude_none=True)
+
+
+class _Stamps(ApiModel):
+    """Who owns a record and when it changed — shared by sandboxes and registry credentials."""
+
+    created_at: datetime
+    updated_at: datetime
+    user_id: str | None = None
+    team_id: str | None = None
+
+
+class Sandbox(_Stamps):
+    """One sandbox as the API returns it (camelCase on the wire; ``ApiModel`` supplies the aliases)."""
+
+    # identity + state
     id: str
     name: str
+    status: str
+    labels: list[str] = Field(default_factory=list)
+    # what runs
     docker_image: str
     start_command: str | None = None
+    environment_vars: dict[str, Any] | None = None
+    secrets: dict[str, Any] | None = None
+    registry_credentials_id: str | None = None
+    advanced_configs: AdvancedConfigs | None = None
+    # what it runs on
     cpu_cores: float
     memory_gb: float = Field(..., alias="memoryGB")
     disk_size_gb: float = Field(..., alias="diskSizeGB")
@@ -42,23 +69,14 @@ class Sandbox(ApiModel):
     gpu_type: str | None = None
     vm: bool = False
     network_access: bool = True
-    status: str
+    kubernetes_job_id: str | None = None
+    # lifecycle
     timeout_minutes: int
-    environment_vars: dict[str, Any] | None = None
-    secrets: dict[str, Any] | None = None
-    advanced_configs: AdvancedConfigs | None = None
-    labels: list[str] = Field(default_factory=list)
-    created_at: datetime
-    updated_at: datetime
     started_at: datetime | None = None
     terminated_at: datetime | None = None
     exit_code: int | None = None
     error_type: str | None = None
     error_message: str | None = None
-    user_id: str | None = None
-    team_id: str | None = None
-    kubernetes_job_id: str | None = None
-    registry_credentials_id: str | None = None
 
 
 class SandboxListResponse(ApiModel):
@@ -69,17 +87,13 @@ class SandboxListResponse(ApiModel):
     has_next: bool
 
 
-class _Wire(BaseModel):
-    """Request bodies go out in snake_case, ``None`` omitted."""
-
-    def wire(self) -> dict[str, Any]:
-        return self.model_dump(by_alias=False, exclude_none=True)
-
-
 class CreateSandboxRequest(_Wire):
     name: str
     docker_image: str
     start_command: str | None = "tail -f /dev/null"
+    environment_vars: dict[str, str] | None = None
+    secrets: dict[str, str] | None = None
+    registry_credentials_id: str | None = None
     cpu_cores: float = 1.0
     memory_gb: float = 2.0
     disk_size_gb: float = 5.0
@@ -88,12 +102,9 @@ class CreateSandboxRequest(_Wire):
     vm: bool = False
     network_access: bool = True
     timeout_minutes: int = 60
-    environment_vars: dict[str, str] | None = None
-    secrets: dict[str, str] | None = None
     labels: list[str] = Field(default_factory=list)
     team_id: str | None = None
     advanced_configs: AdvancedConfigs | None = None
-    registry_credentials_id: str | None = None
 
     @model_validator(mode="after")
     def _gpu_rules(self) -> "CreateSandboxRequest":
@@ -107,20 +118,18 @@ class CreateSandboxRequest(_Wire):
         return self
 
 
-class UpdateSandboxRequest(_Wire):
-    name: str | None = None
-    docker_image: str | None = None
-    start_command: str | None = None
-    cpu_cores: float | None = None
-    memory_gb: float | None = None
-    disk_size_gb: float | None = None
-    gpu_count: int | None = None
-    gpu_type: str | None = None
-    timeout_minutes: int | None = None
-    environment_vars: dict[str, str] | None = None
-    registry_credentials_id: str | None = None
-    secrets: dict[str, str] | None = None
-    network_access: bool | None = None
+# A PATCH body is the create body with everything optional, minus what cannot change after creation.
+_FROZEN_AFTER_CREATE = ("vm", "labels", "team_id", "advanced_configs")
+UpdateSandboxRequest = create_model(  # type: ignore[call-overload]
+    "UpdateSandboxRequest",
+    __base__=_Wire,
+    __module__=__name__,
+    **{
+        field: (info.annotation | None, None)
+        for field, info in CreateSandboxRequest.model_fields.items()
+        if field not in _FROZEN_AFTER_CREATE
+    },
+)
 
 
 class CommandRequest(_Wire):
@@ -162,14 +171,10 @@ class BulkDeleteSandboxResponse(BaseModel):
     message: str
 
 
-class RegistryCredentialSummary(ApiModel):
+class RegistryCredentialSummary(_Stamps):
     id: str
     name: str
     server: str
-    created_at: datetime
-    updated_at: datetime
-    user_id: str | None = None
-    team_id: str | None = None
 
 
 class DockerImageCheckResponse(BaseModel):

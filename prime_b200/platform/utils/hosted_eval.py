@@ -1,21 +1,24 @@
-"""Hosted-evaluation helpers: status enum, request config, log cleaning (ANSI + tqdm bars), incremental log diffing
-(reference: packages/prime/src/prime_cli/utils/hosted_eval.py:12-112)."""
+"""Hosted evaluations, client side: run states, the request a run is created from, and turning the raw container log
+(ANSI colours, tqdm redraws, placeholder messages while the container boots) into lines worth printing — including
+"what is new since the last poll" for ``--follow``.
+
+Behaviour matches the reference's helpers (packages/prime/src/prime_cli/utils/hosted_eval.py:12-112); the structure is
+ours: one classifier for tqdm lines (shared with ``rl logs``), the wire payload built by the config itself, and the
+poll-to-poll overlap found longest-first.
+"""
 
 from __future__ import annotations
 
 import re
-from dataclasses import dataclass
+from dataclasses import dataclass, fields
 from enum import Enum
 from typing import Any
 
 from .formatters import strip_ansi
 
-_BAR_CHARS = "█▏▎▍▌▋▊▉ "
-PROGRESS_BAR = re.compile(rf".*\|[{_BAR_CHARS}]{{10,}}\|.*")
-_PCT = re.compile(r"\d+%\|")
-_DONE = re.compile(rf"([^|]*100%\|[{_BAR_CHARS}]+\|[^\n]*?)(?=\d+%\||$)")
-STATUS_MESSAGES = ("Waiting for container to start...", "No logs available", "Unable to retrieve logs",
-                   "Failed to fetch logs from sandbox", "The hosted eval is still initializing")  # fmt: skip
+# ---------------------------------------------------------------------------------------------------------- run states
+_TERMINAL = frozenset({"COMPLETED", "FAILED", "TIMEOUT", "CANCELLED"})
+_COLOURS = {"PENDING": "yellow", "RUNNING": "cyan", "COMPLETED": "green", "CANCELLED": "yellow", "FAILED": "red", "TIMEOUT": "red"}
 
 
 class EvalStatus(str, Enum):
@@ -26,17 +29,24 @@ class EvalStatus(str, Enum):
     TIMEOUT = "TIMEOUT"
     CANCELLED = "CANCELLED"
 
+    @property
+    def is_terminal(self) -> bool:
+        return self.value in _TERMINAL
+
     @classmethod
     def terminal_statuses(cls) -> set["EvalStatus"]:
-        return {cls.COMPLETED, cls.FAILED, cls.TIMEOUT, cls.CANCELLED}
+        return {s for s in cls if s.is_terminal}
 
     @property
     def color(self) -> str:
-        return {"PENDING": "yellow", "RUNNING": "cyan", "COMPLETED": "green", "CANCELLED": "yellow"}.get(self.value, "red")
+        return _COLOURS.get(self.value, "white")
 
 
+# ------------------------------------------------------------------------------------------------------- run request
 @dataclass
 class HostedEvalConfig:
+    """Everything ``prime eval run --hosted`` sends. ``payload()`` is the POST body."""
+
     environment_id: str
     inference_model: str
     num_examples: int
@@ -51,6 +61,25 @@ class HostedEvalConfig:
     api_base_url: str | None = None
     api_key_var: str | None = None
 
+    _TOP_LEVEL = ("environment_id", "inference_model", "name")
+    _SEND_IF_TRUTHY = ("env_args", "custom_secrets", "sampling_args", "api_base_url", "api_key_var")
+
+    def payload(self) -> dict[str, Any]:
+        run: dict[str, Any] = {}
+        for f in fields(self):
+            value = getattr(self, f.name)
+            if f.name in self._TOP_LEVEL:
+                continue
+            if f.name in self._SEND_IF_TRUTHY and not value:
+                continue
+            if value is None:
+                continue
+            run[f.name] = value
+        body: dict[str, Any] = {"environment_ids": [self.environment_id], "inference_model": self.inference_model, "eval_config": run}
+        if self.name:
+            body["name"] = self.name
+        return body
+
 
 @dataclass
 class HostedEvalResult:
@@ -64,16 +93,36 @@ class HostedEvalResult:
     logs: str | None = None
 
 
+# ----------------------------------------------------------------------------------------------------------- log text
+_BLOCKS = "█▏▎▍▌▋▊▉ "
+PROGRESS_BAR = re.compile(rf".*\|[{_BLOCKS}]{{10,}}\|.*")  # a drawn bar at least ten cells wide
+_TQDM_HEAD = re.compile(r"\d+%\|")  # "NN%|" — tqdm's prefix, whatever the bar is drawn with
+_FINISHED = re.compile(rf"([^|]*100%\|[{_BLOCKS}]+\|[^\n]*?)(?=\d+%\||$)")
+
+STATUS_MESSAGES = ("Waiting for container to start...", "No logs available", "Unable to retrieve logs",
+                   "Failed to fetch logs from sandbox", "The hosted eval is still initializing")  # fmt: skip
+
+
+def tqdm_line(line: str) -> str | None:
+    """Classify one ANSI-free line: ``None`` = not tqdm output; ``""`` = an intermediate redraw (drop it);
+    otherwise the text of the finished bar (several redraws can share a line when ``\\r`` was flattened)."""
+    if not (PROGRESS_BAR.search(line) or _TQDM_HEAD.search(line)):
+        return None
+    if "100%" not in line:
+        return ""
+    done = _FINISHED.search(line)
+    return (done.group(1) if done else line).strip()
+
+
 def filter_progress_bars(text: str) -> str:
-    """Drop tqdm refresh lines; keep only the final 100 % rendering of each bar."""
-    kept: list[str] = []
+    kept = []
     for line in text.splitlines():
-        if PROGRESS_BAR.search(line) or _PCT.search(line):
-            if "100%" in line:
-                m = _DONE.search(line)
-                kept.append((m.group(1) if m else line).strip())
-        elif line.strip():
-            kept.append(line)
+        bar = tqdm_line(line)
+        if bar is None:
+            if line.strip():
+                kept.append(line)
+        elif bar:
+            kept.append(bar)
     return "\n".join(kept)
 
 
@@ -82,18 +131,16 @@ def is_status_message(text: str) -> bool:
 
 
 def clean_logs(text: str) -> str:
-    cleaned = filter_progress_bars(strip_ansi(text))
-    return "" if is_status_message(cleaned) else cleaned
+    body = filter_progress_bars(strip_ansi(text))
+    return "" if is_status_message(body) else body
 
 
 def get_new_log_lines(old_logs: str, new_logs: str) -> list[str]:
-    """Lines of ``new_logs`` not already shown: longest suffix of old == prefix of new (tail windows slide)."""
-    new = new_logs.splitlines()
-    if not old_logs:
-        return new
-    old = old_logs.splitlines()
-    overlap = 0
-    for i in range(1, min(len(old), len(new)) + 1):
-        if old[-i:] == new[:i]:
-            overlap = i
-    return new[overlap:]
+    """The API returns a sliding tail window, so consecutive polls overlap: skip the longest prefix of the new window
+    that is a suffix of the old one."""
+    fresh = new_logs.splitlines()
+    seen = old_logs.splitlines() if old_logs else []
+    for n in range(min(len(seen), len(fresh)), 0, -1):
+        if seen[-n:] == fresh[:n]:
+            return fresh[n:]
+    return fresh

@@ -267,6 +267,13 @@ def test_hosted_eval_log_cleaning_and_overlap():
     assert he.get_new_log_lines("a\nb\nc", "b\nc\nd\ne") == ["d", "e"]  # sliding tail window
     assert he.get_new_log_lines("a\nb", "x\ny") == ["x", "y"] and he.get_new_log_lines("a\nb", "a\nb") == []
     assert he.EvalStatus("COMPLETED") is he.EvalStatus.COMPLETED
+    assert he.EvalStatus.TIMEOUT.is_terminal and not he.EvalStatus.RUNNING.is_terminal
+    assert he.EvalStatus.terminal_statuses() == {he.EvalStatus.COMPLETED, he.EvalStatus.FAILED, he.EvalStatus.TIMEOUT, he.EvalStatus.CANCELLED}
+    assert he.tqdm_line("plain text") is None and he.tqdm_line(" 10%|#   | 1/10") == "" and he.tqdm_line("100%|####| 10/10").startswith("100%")
+    body = he.HostedEvalConfig("env-1", "m", 5, 3, env_args={}, timeout_minutes=0, name="n", sampling_args={"t": 1}).payload()
+    assert body == {"environment_ids": ["env-1"], "inference_model": "m", "name": "n",
+                    "eval_config": {"num_examples": 5, "rollouts_per_example": 3, "timeout_minutes": 0, "allow_sandbox_access": False,
+                                    "allow_instances_access": False, "sampling_args": {"t": 1}}}  # fmt: skip
 
 
 # ------------------------------------------------------------------------------------------------ Connect-RPC helpers

@@ -145,6 +145,9 @@ def test_whoami_persists_user_id_and_shows_scopes(fake_api):
     r = runner.invoke(app, ["whoami"])
     assert r.exit_code == 0 and "u-42" in r.output and "ada@example.com" in r.output and "Personal" in r.output and "pods" in r.output
     assert Config(writable=False).user_id == "u-42"
+    doc = json.loads(runner.invoke(app, ["whoami", "-o", "json"]).output)
+    assert doc["user"]["slug"] == "ada" and doc["team"] is None and doc["scope"]["billing"] is None
+    assert who_mod.permission_rows({"pods": {"read": True, "write": False}, "billing": None}) == [("pods", "✓", "✗"), ("billing", "-", "-")]
     fake_api({("GET", "/user/whoami"): {"data": "nope"}}, who_mod)
     assert runner.invoke(app, ["whoami"]).exit_code == 1
 

@@ -216,6 +216,11 @@ def test_upgrade_picks_the_installers_tool():
                             which=lambda t: "/usr/bin/" + t)  # fmt: skip
     assert ok and [c[0] for c in ran] == ["uv", "pip"]  # falls through to the next recipe when the first fails
     assert not up_mod.run_upgrade("pipx", runner=lambda *a, **k: SimpleNamespace(returncode=0, stderr=""), which=lambda t: None)  # tool not installed
+    # version/flag logic: --check only reports, --force upgrades even when current, otherwise nothing to do
+    assert up_mod.decide("1.0.0", "1.1.0", check=True, force=False) == ("report", True)
+    assert up_mod.decide("1.1.0", "1.1.0", check=False, force=True) == ("upgrade", False)
+    assert up_mod.decide("1.1.0", "1.1.0", check=False, force=False) == ("current", False)
+    assert up_mod.decide("1.0.0", "1.1.0", check=False, force=False) == ("upgrade", True)
 
 
 def test_sse_parser():
