@@ -1,4 +1,5 @@
-"""(reference: packages/prime-evals/src/prime_evals/models.py:8-135)"""
+"""Evaluations SDK wire models (same fields as the reference: packages/prime-evals/src/prime_evals/models.py:8-135;
+create request and stored record share one description base instead of repeating it)."""
 
 from __future__ import annotations
 
@@ -19,29 +20,20 @@ class EvaluationStatus(str, Enum):
     CANCELLED = "CANCELLED"
 
 
-class Evaluation(ApiModel):
-    id: str = Field(..., alias="evaluation_id")
+class _Described(BaseModel):
+    """What an evaluation is *about* — the part a creator supplies and the API echoes back unchanged."""
+
     name: str
     model_name: str | None = None
     dataset: str | None = None
     framework: str | None = None
     task_type: str | None = None
-    eval_type: str | None = None
     description: str | None = None
-    status: str | None = None
-    environment_ids: list[str] | None = None
-    suite_id: str | None = None
-    run_id: str | None = None
-    version_id: str | None = None
     tags: list[str] = Field(default_factory=list)
     metadata: dict[str, Any] | None = None
     metrics: dict[str, Any] | None = None
-    total_samples: int | None = None
-    created_at: datetime | None = None
-    updated_at: datetime | None = None
-    finalized_at: datetime | None = None
-    user_id: str | None = None
-    team_id: str | None = None
+    suite_id: str | None = None
+    run_id: str | None = None
 
 
 class EnvironmentReference(BaseModel):
@@ -49,19 +41,26 @@ class EnvironmentReference(BaseModel):
     version_id: str | None = None
 
 
-class CreateEvaluationRequest(BaseModel):
-    name: str
+class CreateEvaluationRequest(_Described):
+    """``POST /evaluations/``: the description plus what it ran on (environments, or a suite / training run)."""
+
     environments: list[dict[str, str]] | None = None
-    suite_id: str | None = None
-    run_id: str | None = None
-    model_name: str | None = None
-    dataset: str | None = None
-    framework: str | None = None
-    task_type: str | None = None
-    description: str | None = None
-    tags: list[str] = Field(default_factory=list)
-    metadata: dict[str, Any] | None = None
-    metrics: dict[str, Any] | None = None
+
+
+class Evaluation(_Described, ApiModel):
+    """An evaluation as stored: the description plus identity, state and bookkeeping the server adds."""
+
+    id: str = Field(..., alias="evaluation_id")
+    status: str | None = None
+    eval_type: str | None = None
+    environment_ids: list[str] | None = None
+    version_id: str | None = None
+    total_samples: int | None = None
+    created_at: datetime | None = None
+    updated_at: datetime | None = None
+    finalized_at: datetime | None = None
+    user_id: str | None = None
+    team_id: str | None = None
 
 
 class Sample(ApiModel):
