@@ -8,7 +8,6 @@ native library on the *current* torch stream (so they compose with streams and C
 
 from __future__ import annotations
 
-import math
 
 import torch
 

@@ -22,8 +22,7 @@ Both share bucket layout and optimizer state, so checkpoints move freely between
 from __future__ import annotations
 
 import ctypes
-import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Iterable
 
 import torch

@@ -11,7 +11,7 @@ from ..helper.short_id import generate_short_id, generate_short_id_disk
 from ..utils.display import status_color
 from ..utils.json_help import list_json_help
 from ..utils.plain import get_console
-from ._common import OUTPUT_OPT, api, console, emit, handle_errors, make_app
+from ._common import OUTPUT_OPT, api, emit, handle_errors, make_app
 
 _err = get_console(stderr=True)
 

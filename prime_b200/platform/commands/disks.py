@@ -13,7 +13,7 @@ import typer
 from ..api.availability import AvailabilityClient
 from ..api.disks import Disk, DisksClient
 from ..helper.short_id import generate_short_id_disk
-from ..utils.display import POD_STATUS_COLORS, colorize, output_data_as_json, validate_output_format
+from ..utils.display import POD_STATUS_COLORS, colorize, validate_output_format
 from ..utils.json_help import json_output_help, list_json_help
 from ..utils.plain import is_plain_mode
 from ..utils.prompt import confirm_or_skip

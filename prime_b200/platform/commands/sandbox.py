@@ -17,7 +17,7 @@ import typer
 
 from ..core import Config
 from ..sandboxes import CommandTimeoutError, CreateSandboxRequest, Sandbox, SandboxClient, SandboxNotRunningError
-from ..utils.display import SANDBOX_STATUS_COLORS, build_table, colorize, output_data_as_json
+from ..utils.display import SANDBOX_STATUS_COLORS, colorize, output_data_as_json
 from ..utils.formatters import obfuscate_env_vars
 from ..utils.json_help import json_output_help, list_json_help
 from ..utils.prompt import confirm_or_skip

@@ -16,7 +16,7 @@ import json
 import time
 import warnings
 from concurrent.futures import ThreadPoolExecutor, as_completed
-from typing import Any, Awaitable, Callable
+from typing import Any, Callable
 
 import httpx
 

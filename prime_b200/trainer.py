@@ -8,7 +8,6 @@ across workers ⊕ Nesterov).
 
 from __future__ import annotations
 
-import time
 from dataclasses import dataclass
 
 import torch
