@@ -157,6 +157,21 @@ def _declare(lib: ctypes.CDLL) -> None:
         "pb_outer_nesterov": [PP, PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), PP, i64, vp],
         "pb_outer_nesterov_f32": [PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), vp],
         "pb_cast_push": [vp, i64, PP, i64, vp],
+        # NVLS: VMM allocations shared by fd, multicast objects, multimem kernels (csrc/multicast.cu)
+        "pb_mc_supported": [i32],
+        "pb_vmm_granularity": [i32, i32, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],
+        "pb_vmm_create": [i32, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(i32)],
+        "pb_vmm_import": [i32, ctypes.POINTER(ctypes.c_uint64)],
+        "pb_vmm_map": [ctypes.c_uint64, ctypes.c_size_t, ctypes.c_size_t, i32, ctypes.POINTER(vp)],
+        "pb_vmm_unmap": [vp, ctypes.c_size_t],
+        "pb_vmm_release": [ctypes.c_uint64],
+        "pb_mc_create": [i32, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(i32)],
+        "pb_mc_add_device": [ctypes.c_uint64, i32],
+        "pb_mc_bind": [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_size_t],
+        "pb_mc_unbind": [ctypes.c_uint64, i32, ctypes.c_size_t],
+        "pb_mc_all_reduce_grid": [],
+        "pb_mc_all_reduce": [vp, i64, i32, vp, vp, i32, i32, u32, vp, vp],
+        "pb_mc_grad_reduce": [vp, i64, i64, f32, vp, vp, vp, i32, u32, i32, vp, i32, vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name, None)

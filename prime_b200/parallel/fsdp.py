@@ -157,6 +157,9 @@ class ShardedEngine:
             self.slot_grad = self.heap.alloc_flags(len(self.buckets) * F)
             self.slot_norm = self.heap.alloc_flags(F)
             self.slot_bar = self.heap.alloc_flags(F)
+            # NVLS reduce-scatter: only when the heap has a multicast mapping AND it spans exactly this FSDP group (the switch
+            # sums every device bound to the object, so a heap shared by several DiLoCo workers cannot use it)
+            self._nvls = F > 1 and hasattr(self.heap, "mc_ptr") and self.heap.world_size == F
             self.sumsq_partial = torch.zeros(self.lib_grid(), dtype=torch.float32, device=dev)
             self.gnorm_buf = torch.zeros(1, dtype=torch.float32, device=dev)
         else:
@@ -271,8 +274,19 @@ class ShardedEngine:
                     _lib.check(self.lib.pb_signal(ctypes.byref(pp), slot_base + r, self._epoch, s), "pb_signal")
                     _count()
                     wait_flags = self.heap.flags.data_ptr()
-                gp = self.heap.peers(ranks, self.grad_flat)
                 out = self.gshard[b.shard_start :] if F > 1 else self.grad_flat[b.start :]
+                if self._nvls:  # the switch sums the F copies: one multimem.ld_reduce per 16 bytes instead of F peer loads
+                    _lib.check(
+                        self.lib.pb_mc_grad_reduce(
+                            self.heap.mc_ptr(self.grad_flat), b.start + r * b.shard_size, b.shard_size, 1.0 / F, out.data_ptr(),
+                            self.sumsq_partial.data_ptr(), wait_flags, slot_base, self._epoch, F, self.heap.err.data_ptr(),
+                            self.reduce_ctas if self.overlap else 0, s,
+                        ),
+                        "pb_mc_grad_reduce",
+                    )  # fmt: skip
+                    _count()
+                    return
+                gp = self.heap.peers(ranks, self.grad_flat)
                 _lib.check(
                     self.lib.pb_grad_reduce(
                         ctypes.byref(gp), b.start + r * b.shard_size, b.shard_size, 1.0 / F, out.data_ptr(),

@@ -72,7 +72,14 @@ class Trainer:
             pad = (len(list(self.model.parameters())) + 64) * 8 + (self.model.args.n_layers + 3) * mesh.fsdp_size * 1024
             total = n + pad
             nbytes = total * 6 + (total // mesh.fsdp_size) * 2 + (64 << 20)
-            self.heap = SymmetricHeap(nbytes, mesh.world.rank, mesh.world.world_size, dist_exchange(), self.device)
+            heap_cls = SymmetricHeap
+            if _want_nvls() and mesh.world.world_size > 1:
+                from .parallel.multicast import MulticastHeap, nvls_available
+
+                if not nvls_available(self.device.index or 0):
+                    raise RuntimeError("PB_NVLS=1 but this device cannot join an NVSwitch multicast object")
+                heap_cls = MulticastHeap  # VMM + multicast mapping: the gradient reduce-scatter is summed inside the switch
+            self.heap = heap_cls(nbytes, mesh.world.rank, mesh.world.world_size, dist_exchange(), self.device)
 
         o = cfg.optim
         hyper = AdamHyper(o.optim.lr, o.optim.betas1, o.optim.betas2, o.optim.eps, o.optim.weight_decay,
@@ -201,6 +208,12 @@ def _count_launches(n: int) -> None:
     from .ops.functional import _count
 
     _count(n)
+
+
+def _want_nvls() -> bool:
+    import os
+
+    return os.environ.get("PB_NVLS", "0") == "1"
 
 
 def _env_world() -> int:

@@ -59,12 +59,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(nproc, cfg, steps, tmp_path):
+def _run(nproc, cfg, steps, tmp_path, env=None):
     script = tmp_path / "w.py"
     script.write_text(WORKER.format(root=str(ROOT), cfg=cfg, steps=steps))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(script)]  # fmt: skip
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, **(env or {})})
     assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
     return json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
 
@@ -79,6 +79,26 @@ def test_fsdp2_fused_matches_collective(tmp_path):
     assert r["rel"] < 2e-3 and r["prel"] < 5e-3, r
     assert abs(r["ga"] - r["gb"]) < 2e-2 * r["gb"], r
     assert r["hashes"][0] == r["hashes"][1], r  # both ranks hold identical bf16 parameters
+    assert r["la"][-1] < r["la"][0]
+
+
+# The NVLS path was written after the round's GPU budget was spent: it compiles (LDGMC / multimem in the SASS) and its host
+# logic is covered on CPU, but it has not run on hardware yet. Until it has, these two tests are opt-in so that an untested
+# path cannot stop a `-x` run of the suite.
+nvls_opt_in = pytest.mark.skipif(os.environ.get("PB_TEST_NVLS") != "1", reason="NVLS path not yet validated on hardware; set PB_TEST_NVLS=1")
+
+
+@nvls_opt_in
+def test_fsdp2_nvls_reduce_scatter_matches_collective(tmp_path):
+    """PB_NVLS=1: the heap is VMM-backed with a multicast mapping and the gradient reduce-scatter is summed by the switch."""
+    from prime_b200.parallel.multicast import nvls_available
+
+    if not nvls_available(0):
+        pytest.skip("multicast unsupported on this box")
+    r = _run(2, {**BASE, "mesh": {"fsdp_size": 2}}, 5, tmp_path, env={"PB_NVLS": "1"})
+    assert r["rel"] < 2e-3 and r["prel"] < 5e-3, r
+    assert abs(r["ga"] - r["gb"]) < 2e-2 * r["gb"], r
+    assert r["hashes"][0] == r["hashes"][1], r
     assert r["la"][-1] < r["la"][0]
 
 
@@ -225,3 +245,84 @@ def test_sequence_parallel_mlp_forward_backward(tmp_path):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
     for errs in json.loads(line[len("RESULT "):]):
         assert errs["y"] < 1.5e-2 and errs["dx"] < 1.5e-2 and errs["dw13"] < 1.5e-2 and errs["dw2"] < 1.5e-2, errs
+
+
+NVLS_WORKER = textwrap.dedent(
+    """
+    import ctypes, json, os, sys, torch
+    import torch.distributed as dist
+    sys.path.insert(0, {root!r})
+    from prime_b200.ops import _lib
+    from prime_b200.parallel.multicast import MulticastHeap, nvls_available
+    from prime_b200.parallel.symm import dist_exchange
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    dev = torch.device("cuda", rank)
+    if not nvls_available(rank):
+        if rank == 0:
+            print("RESULT " + json.dumps(dict(skipped="multicast unsupported on this box")))
+        dist.destroy_process_group()
+        sys.exit(0)
+    heap = MulticastHeap(64 << 20, rank, world, dist_exchange(), dev)
+    lib = _lib.load()
+    out = dict()
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    n = 1 << 20
+    parts = [torch.randn(n, generator=g) for _ in range(world)]  # every rank knows every rank's input
+    want = torch.stack(parts).sum(0)
+    # in-place all-reduce through the switch, f32 then bf16, twice each (the barrier counters must carry across launches)
+    x32 = heap.alloc(n, torch.float32)
+    xb = heap.alloc(n, torch.bfloat16)
+    for rep in range(2):
+        x32.copy_(parts[rank]); xb.copy_(parts[rank].bfloat16())
+        heap.all_reduce_(x32); heap.all_reduce_(xb)
+        torch.cuda.synchronize()
+        out[f"f32_{{rep}}"] = float((x32.cpu() - want).abs().max() / want.abs().max())
+        wb = torch.stack([p.bfloat16().float() for p in parts]).sum(0)
+        out[f"bf16_{{rep}}"] = float((xb.float().cpu() - wb).abs().max() / wb.abs().max())
+    # NVLS gradient reduce-scatter against the peer-load kernel: same shard, same scale, same sum of squares
+    grads = heap.alloc(n, torch.float32)
+    grads.copy_(parts[rank])
+    torch.cuda.synchronize(); dist.barrier()
+    shard = n // world
+    off = rank * shard
+    grid = lib.pb_grad_reduce_grid()
+    o_mc, o_p2p = torch.zeros(shard, device=dev), torch.zeros(shard, device=dev)
+    ss_mc, ss_p2p = torch.zeros(grid, device=dev), torch.zeros(grid, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.pb_mc_grad_reduce(heap.mc_ptr(grads), off, shard, 0.5, o_mc.data_ptr(), ss_mc.data_ptr(), None, 0, 0, world,
+                                     heap.err.data_ptr(), 0, s), "pb_mc_grad_reduce")
+    pp = heap.peers(range(world), grads)
+    _lib.check(lib.pb_grad_reduce(ctypes.byref(pp), off, shard, 0.5, o_p2p.data_ptr(), ss_p2p.data_ptr(), None, 0, 0,
+                                  heap.err.data_ptr(), 0, s), "pb_grad_reduce")
+    torch.cuda.synchronize()
+    out["rs"] = float((o_mc - o_p2p).abs().max() / o_p2p.abs().max())
+    out["rs_sumsq"] = abs(float(ss_mc.sum()) / float(ss_p2p.sum()) - 1.0)
+    heap.check_errors()
+    dist.barrier()
+    heap.close()
+    if rank == 0:
+        print("RESULT " + json.dumps(out))
+    dist.destroy_process_group()
+    """
+)
+
+
+@nvls_opt_in
+def test_nvls_multicast_all_reduce_and_grad_reduce(tmp_path):
+    """multimem.ld_reduce / multimem.st over a VMM heap bound to an NVSwitch multicast object: the in-place all-reduce matches
+    the dense sum, and the NVLS gradient reduce-scatter matches the peer-load kernel it can replace (PB_NVLS=1)."""
+    script = tmp_path / "nvls_worker.py"
+    script.write_text(NVLS_WORKER.format(root=str(ROOT)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script)]  # fmt: skip
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1][len("RESULT "):])
+    if "skipped" in res:
+        pytest.skip(res["skipped"])
+    assert max(res["f32_0"], res["f32_1"]) < 1e-6, res
+    assert max(res["bf16_0"], res["bf16_1"]) < 1e-2, res
+    assert res["rs"] < 1e-6 and res["rs_sumsq"] < 1e-5, res
