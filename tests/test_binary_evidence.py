@@ -64,6 +64,10 @@ def test_blackwell_paths_are_present(sass):
     comm = body("adamw_push_kernel")
     assert "STG.E.128" in comm  # 128-bit peer stores
     assert "LD.E.STRONG.SYS" in body("outer_nesterov") or "STRONG.SYS" in body("outer_nesterov")
+    # NVLS: the reduction is a multimem load (LDGMC), in f32 and in bf16 with fp32 accumulation in the switch
+    assert "LDGMC.E.ADD.F32x4" in body("mc_grad_reduce_kernel")
+    allred = body("mc_all_reduce_kernel")
+    assert "LDGMC.E.ADD.F32x4" in allred and "BF16x8" in allred and "REDG.E.ADD.STRONG.SYS" in allred
 
 
 def test_ncu_source_hotspots_condenses_runs(tmp_path, capsys):
