@@ -51,7 +51,7 @@ def validate_output_format(fmt: str, console=None) -> str:
     if fmt not in ("table", "json"):
         import typer
 
-        (console or get_console()).print(f"[red]Error:[/red] --output must be 'table' or 'json', got {fmt!r}")
+        (console or get_console()).print(f"[red]Error:[/red] Invalid output format {fmt!r}: --output takes 'table' or 'json'")
         raise typer.Exit(1)
     return fmt
 
