@@ -42,7 +42,10 @@ def secret_list(output: str = OUTPUT_OPT) -> None:
     """List secrets of the active account (values are never returned)."""
     cfg = Config(writable=False)
     rows = fetch_secrets(api(), cfg)
-    emit(output, {"secrets": rows, "total_count": len(rows)}, f"Secrets ({scope_of(cfg)})",
+    if not rows and output == "table":
+        console.print(f"[yellow]No {scope_of(cfg)} secrets found.[/yellow]\n[dim]Create one with: prime secret create[/dim]")
+        return
+    emit(output, {"secrets": rows, "total_count": len(rows)}, f"{scope_of(cfg).capitalize()} Secrets",
          [("ID", "cyan"), ("Name", "green"), "Description", "File", ("Updated", "magenta")],
          [[s.get("id"), s.get("name"), s.get("description") or "", "yes" if s.get("isFile") else "", format_time_ago(s.get("updatedAt"))] for s in rows])  # fmt: skip
 
@@ -129,6 +132,6 @@ def secret_delete(secret_id: Optional[str] = typer.Argument(None, help="Secret I
 def secret_get(secret_id: str = typer.Argument(..., help="Secret ID"), output: str = OUTPUT_OPT) -> None:
     """Show a secret's metadata."""
     s = api().get(f"/secrets/{secret_id}", params=team_params(Config(writable=False))).get("data", {})
-    emit(output, s, "Secret", [("Field", "cyan"), ("Value", "green")],
+    emit(output, s, "Secret Details", [("Field", "cyan"), ("Value", "green")],
          [["ID", s.get("id")], ["Name", s.get("name")], ["Description", s.get("description") or ""], ["File", bool(s.get("isFile"))],
           ["Created", s.get("createdAt")], ["Updated", s.get("updatedAt")]])  # fmt: skip
