@@ -88,12 +88,17 @@ def to_plain(obj: Any, markup: bool = True) -> str:
 class Out:
     """Console façade used by every command."""
 
-    def __init__(self, stderr: bool = False):
+    def __init__(self, stderr: bool = False, file: Any = None, **rich_options: Any):
+        """``file`` and any other ``rich.console.Console`` option (markup, highlight, no_color, emoji, width, …) pass through to
+        the rich side; plain mode writes to the same ``file``."""
         self.stderr = stderr
-        self._rich = Console(stderr=stderr)
+        self._file = file
+        self._rich = Console(stderr=stderr, file=file, **rich_options)
 
     @property
     def file(self):
+        if self._file is not None:
+            return self._file
         return sys.stderr if self.stderr else sys.stdout
 
     def print(self, *objects: Any, sep: str = " ", end: str = "\n", markup: bool | None = None, **kw: Any) -> None:
@@ -129,8 +134,8 @@ class Out:
             self._rich.print_exception()
 
 
-def get_console(stderr: bool = False) -> Out:
-    return Out(stderr=stderr)
+def get_console(stderr: bool = False, **console_options: Any) -> Out:
+    return Out(stderr=stderr, **console_options)
 
 
 # --------------------------------------------------------------------------- Typer integration
