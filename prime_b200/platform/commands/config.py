@@ -98,7 +98,12 @@ def set_team_id(team_id: str = typer.Argument(..., help="Team ID (empty string =
             pass
     c.set_team(team_id or None, team_name=name, team_role=role)
     c.update_current_environment_file()
-    console.print(f"[green]Team ID {team_id} configured successfully![/green]" if team_id else "[green]Switched to personal account.[/green]")
+    if not team_id:
+        console.print("[green]Team ID cleared. Using personal account.[/green]")
+    elif name:
+        console.print(f"[green]Team '{name}' ({team_id}) configured successfully![/green]")
+    else:  # the listing was unreachable or does not contain it: the id is stored all the same
+        console.print(f"[green]Team ID '{team_id}' configured successfully![/green]")
 
 
 @app.command("remove-team-id")
