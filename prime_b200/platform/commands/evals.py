@@ -126,8 +126,13 @@ def validate_hosted_entry(merged: dict[str, Any], config_path: Path) -> dict[str
     ea = merged.get("env_args")
     if ea is not None and not (isinstance(ea, dict) and all(isinstance(k, str) and isinstance(v, str) for k, v in ea.items())):
         raise fail("`env_args` must be a table of strings")
-    if merged.get("sampling_args") is not None and not isinstance(merged["sampling_args"], dict):
-        raise fail("`sampling_args` must be a table")
+    if merged.get("sampling_args") is not None:
+        if not isinstance(merged["sampling_args"], dict):
+            raise fail("`sampling_args` must be a table")
+        try:  # it travels as JSON: TOML dates/times (and anything else json cannot encode) are caught here, not by the server
+            json.dumps(merged["sampling_args"])
+        except (TypeError, ValueError) as e:
+            raise fail(f"`sampling_args` must be JSON-serializable ({e})")
     for field, (typ, desc) in HOSTED_TYPES.items():
         v = merged.get(field)
         if v is not None and (type(v) is not typ or (typ is str and not v)):
@@ -218,6 +223,10 @@ def print_eval_status(data: dict[str, Any]) -> None:
         console.print(f"  {k}: {v}")
     if data.get("error_message"):
         console.print(f"[red]Error:[/red] {data['error_message']}")
+    # where to look at it: the URL the server names (self-hosted frontends differ), else the one derived from the id
+    where = data.get("viewer_url") or (get_eval_viewer_url(data["evaluation_id"]) if data.get("evaluation_id") else None)
+    if where:
+        console.print(f"[dim]View: {where}[/dim]")
 
 
 def follow_logs(client: APIClient, eval_id: str, poll_interval: float, sleep=time.sleep) -> None:
@@ -248,9 +257,7 @@ def follow_logs(client: APIClient, eval_id: str, poll_interval: float, sleep=tim
         raw, st = parse_status(data)
         if st is not None and st.is_terminal:
             console.print()
-            print_eval_status(data)
-            url = get_eval_viewer_url(eval_id)
-            console.print(f"\n[dim]View results:[/dim] [link={url}]{url}[/link]")
+            print_eval_status({"evaluation_id": eval_id, **data})
             if st is not EvalStatus.COMPLETED:
                 raise typer.Exit(1)
             return
@@ -431,8 +438,10 @@ def logs_cmd(eval_id: str = typer.Argument(...), tail: int = typer.Option(LOGS_T
 @handle_errors
 def stop_cmd(eval_id: str = typer.Argument(...)) -> None:
     """Cancel a running hosted evaluation."""
-    api().patch(f"/hosted-evaluations/{eval_id}/cancel")
-    console.print(f"[green]✓ Cancellation requested for {eval_id}[/green]")
+    answer = api().patch(f"/hosted-evaluations/{eval_id}/cancel")
+    said = answer.get("message") if isinstance(answer, dict) else None
+    console.print(f"[green]✓ {said or f'Evaluation {eval_id} cancelled.'}[/green]")  # the server's own words when it has any
+    console.print(f"[dim]View results:[/dim] {get_eval_viewer_url(eval_id)}")
 
 
 # ------------------------------------------------------------------------------------------------- run
