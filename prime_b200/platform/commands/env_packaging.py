@@ -177,10 +177,16 @@ def safe_tar_extract(tar: tarfile.TarFile, dest: Path) -> None:
 
 
 def validate_path_component(component: str, what: str) -> None:
-    if not component:
-        raise ValueError(f"{what} cannot be empty")
-    if ".." in component or "/" in component or "\\" in component or "\x00" in component:
-        raise ValueError(f"{what} contains unsafe characters")
+    """``owner`` / ``name`` / ``version`` become directory names under the wheel cache: each must be ONE harmless path segment."""
+    problems = (
+        (not component, "cannot be empty"),
+        ("\x00" in component, "cannot contain null bytes"),
+        (".." in component, "cannot contain '..'"),
+        ("/" in component or "\\" in component, "cannot contain path separators"),
+    )
+    for bad, why in problems:
+        if bad:
+            raise ValueError(f"Invalid {what}: {why}")
 
 
 def env_cache_dir() -> Path:

@@ -318,15 +318,22 @@ def has_eval_files(d: Path) -> bool:
 
 
 def validate_eval_path(path_str: str) -> Path:
+    """→ the run directory to push. Being pointed at ``metadata.json`` / ``results.jsonl`` INSIDE a complete run directory is
+    forgiven (it means the directory); everything else gets an error that names what is missing."""
     p = Path(path_str)
+    pair = "metadata.json and results.jsonl"
     if p.is_file():
-        if p.name in ("metadata.json", "results.jsonl") and has_eval_files(p.parent):
-            return p.parent  # be forgiving: a file inside the run directory means the directory
-        raise ValueError(f"Expected a directory containing metadata.json and results.jsonl, got file: {p}")
+        if p.name not in ("metadata.json", "results.jsonl"):
+            raise ValueError(f"Expected a directory path containing {pair}, but got file: {p}")
+        if has_eval_files(p.parent):
+            return p.parent
+        raise ValueError(f"Directory '{p.parent}' must contain both {pair}")
     if p.is_dir():
         missing = [n for n in ("metadata.json", "results.jsonl") if not (p / n).exists()]
+        if len(missing) == 2:
+            raise ValueError(f"Directory '{p}' is missing both {pair}")
         if missing:
-            raise ValueError(f"Directory '{p}' is missing {' and '.join(missing)}")
+            raise ValueError(f"Directory '{p}' is missing {missing[0]}")
         return p
     raise FileNotFoundError(f"Path not found: {p}")
 
@@ -391,6 +398,8 @@ def push_eval(
     is_public: bool = typer.Option(False, "--public", help="Make the evaluation public"),
 ) -> None:
     """Upload local evaluation results."""
+    if eval_id and is_public:  # visibility is a property given at creation; an existing evaluation keeps the one it has
+        raise fail("The --public flag cannot be used with --eval-id. Visibility can only be set when creating a new evaluation.")
     try:
         if config_path:
             eid = push_single_eval(config_path, env_id, run_id, eval_id, is_public)
