@@ -146,6 +146,14 @@ class CheckpointManager:
         self.last_snapshot_s = 0.0
         self.last_write_s = 0.0
         self.last_bytes = 0
+        self._pending_meta: dict[str, Any] = {}
+        # host-side (gloo) group for the status exchange of asynchronous checkpoints: polling must not touch the device
+        self._side = None
+        if world_size > 1 and dist.is_initialized():
+            try:
+                self._side = dist.new_group(backend="gloo")
+            except Exception:  # noqa: BLE001
+                self._side = None
         if rank == 0:
             self.root.mkdir(parents=True, exist_ok=True)
 
@@ -238,17 +246,53 @@ class CheckpointManager:
         self._barrier()
         return handle
 
+    def _status(self, done: bool, failed: bool) -> tuple[bool, bool]:
+        """(every rank done, any rank failed) — one tiny all-reduce; on the gloo side group when there is one."""
+        if self.world == 1 or not dist.is_initialized():
+            return done, failed
+        dev = "cpu" if self._side is not None else self.device
+        t = torch.tensor([0 if done else 1, 1 if failed else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self._side)
+        return int(t[0]) == 0, int(t[1]) == 1
+
+    def _finish(self, h: SaveHandle, failed: bool) -> None:
+        self._pending = None
+        if failed:  # every rank raises together: nobody is left waiting in a barrier
+            cause = h.error[0] if h.error else None
+            raise RuntimeError(f"checkpoint step {h.step} failed on {'this rank' if h.error else 'another rank'}") from cause
+        if self.rank == 0:
+            self._publish(h.step, self._pending_meta)
+        self._barrier()
+
+    def poll(self) -> bool:
+        """Call once per training step on every rank: publishes the asynchronously written checkpoint as soon as ALL shards are on
+        disk (instead of at the next ``save``/exit, which left the newest checkpoint invisible to resume for a whole interval).
+        Never blocks on the writer thread. Returns True when a checkpoint was published by this call."""
+        h = self._pending
+        if h is None or self.world == 1:
+            return False
+        mine_done = h.thread is None or not h.thread.is_alive()
+        done, failed = self._status(mine_done, bool(h.error) and mine_done)
+        if failed or done:
+            if h.thread is not None:
+                h.thread.join()
+            self._finish(h, failed)
+            return not failed
+        return False
+
     def wait(self) -> None:
         """Finish the in-flight checkpoint (called before the next save, before exit, and by tests)."""
-        h, self._pending = self._pending, None
+        h = self._pending
         if h is None:
             return
-        h.wait()
-        if self.world > 1:
-            self._barrier()  # every shard is on disk
-            if self.rank == 0:
-                self._publish(h.step, self._pending_meta)
-            self._barrier()
+        if h.thread is not None:
+            h.thread.join()
+        if self.world == 1:
+            self._pending = None
+            h.wait()
+            return
+        _, failed = self._status(True, bool(h.error))  # exchange error status BEFORE anybody raises or enters the barrier
+        self._finish(h, failed)
 
     def load(self, path: Path) -> tuple[dict[str, torch.Tensor], dict[str, Any], dict[str, Any]]:
         meta = json.loads((Path(path) / "meta.json").read_text())
@@ -267,7 +311,11 @@ def trainer_state(trainer) -> tuple[dict[str, torch.Tensor], dict[str, Any]]:
         "trainer_step": trainer.step_count, "engine_step": eng.step_count, "fsdp_size": eng.F, "fsdp_rank": eng.mesh.fsdp_rank,
         "layout": [[b.name, b.start, b.size, b.shard_start, b.shard_size] for b in eng.buckets],
         "data": trainer.loader.state_dict(),
+        "shard_params": bool(getattr(eng, "shard_params", False)),
     }  # fmt: skip
+    tensors["rng_cpu"] = torch.get_rng_state()
+    if eng.device.type == "cuda":
+        tensors["rng_cuda"] = torch.cuda.get_rng_state(eng.device)
     if outer is not None:
         tensors.update(theta0=outer.theta0, momentum=outer.momentum)
         extra["outer_step"] = outer.outer_step_count
@@ -288,7 +336,17 @@ def restore_trainer(trainer, tensors: dict[str, torch.Tensor], extra: dict[str, 
             outer.theta0.copy_(tensors["theta0"])
             outer.momentum.copy_(tensors["momentum"])
             outer.outer_step_count = int(extra.get("outer_step", 0))
+        elif outer is not None:
+            # the run was saved without [diloco] and is resumed with it: the outer parameters start at the LOADED weights (not at
+            # the constructor's random init, whose pseudo-gradient would wipe out the checkpoint at the first outer step)
+            outer.theta0.copy_(eng.master)
+            outer.momentum.zero_()
+            outer.outer_step_count = 0
         eng.publish_params()
+        if "rng_cpu" in tensors:
+            torch.set_rng_state(tensors["rng_cpu"].cpu())
+        if "rng_cuda" in tensors and eng.device.type == "cuda":
+            torch.cuda.set_rng_state(tensors["rng_cuda"].cpu(), eng.device)
     trainer.step_count = int(extra["trainer_step"])
     if not skip_dataloader:
         trainer.loader.load_state_dict(extra["data"])

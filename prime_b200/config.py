@@ -50,13 +50,16 @@ class OptimConfig(_Section):
     total_steps: int = 88_000
     batch_size: int = 512  # global sequences per optimizer step, per DiLoCo worker
     max_norm: float = 1.0
-    clip_mode: Literal["exact", "delayed", "none"] = "exact"
+    # "delayed" (clip with the previous step's norm) is not offered: the fused norm exchange is already off the critical path
+    clip_mode: Literal["exact", "none"] = "exact"
 
 
 class TrainConfig(_Section):
     micro_bs: int = 16
     ac_ckpt: bool | int = False
-    reshard_after_forward: bool = False  # 180 GB HBM: keep bf16 params resident
+    # ZeRO-3: bf16 parameters sharded 1/F, gathered from the peers INSIDE the consuming GEMMs (parallel/fsdp.py). None = automatic:
+    # on for models of 5 B parameters and more when fsdp_size > 1, off below that (180 GB HBM: small models stay resident)
+    reshard_after_forward: bool | None = None
     cuda_graphs: bool = False
     log_model_hash: bool = False
     attn_impl: Literal["auto", "native", "sdpa"] = "auto"

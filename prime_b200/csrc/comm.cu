@@ -14,7 +14,8 @@
 using namespace pb;
 
 constexpr int kMaxPeers = 8;
-constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;  // 20 s
+// Bound of every device-side wait (default 20 s; elastic jobs lower it so a dead peer is detected within a heartbeat period).
+__device__ unsigned long long g_spin_timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
 
 struct PeerPtrs {
   void* p[kMaxPeers];
@@ -27,17 +28,29 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// Spin until *flag >= expect (monotone epochs). Returns false on timeout.
+// Spin until *flag >= expect (monotone epochs). Returns false on timeout, or as soon as the error word is non-zero (another
+// wait already timed out, or the host's watchdog aborted the step because a peer died: SymmetricHeap.abort()).
+// err[0] = 1 timeout / 2 host abort; err[1] = flag address offset that timed out (diagnostic).
 __device__ __forceinline__ bool spin_wait_ge(const uint32_t* flag, uint32_t expect, uint32_t* err) {
-  const unsigned long long t0 = globaltimer_ns();
+  if ((int32_t)(ld_acquire_sys_u32(flag) - expect) >= 0) return true;
+  const unsigned long long t0 = globaltimer_ns(), limit = g_spin_timeout_ns;
+  uint32_t spins = 0;
   while ((int32_t)(ld_acquire_sys_u32(flag) - expect) < 0) {
     __nanosleep(64);
-    if (globaltimer_ns() - t0 > kSpinTimeoutNs) {
-      if (err) atomicExch(err, 1u);
-      return false;
+    if ((++spins & 63u) == 0) {
+      if (err && *reinterpret_cast<volatile uint32_t*>(err) != 0u) return false;
+      if (globaltimer_ns() - t0 > limit) {
+        if (err) atomicCAS(err, 0u, 1u);
+        return false;
+      }
     }
   }
   return true;
+}
+
+PB_EXPORT int pb_set_spin_timeout_ms(unsigned long long ms) {
+  const unsigned long long ns = ms * 1000000ull;
+  return (int)cudaMemcpyToSymbol(g_spin_timeout_ns, &ns, sizeof(ns));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -118,8 +131,12 @@ __global__ void __launch_bounds__(512) grad_reduce_kernel(PeerPtrs grads, int64_
                                                           uint32_t* err) {
   __shared__ float red[32];
   if (wait_flags != nullptr) {
-    if ((int)threadIdx.x < grads.n) spin_wait_ge(wait_flags + slot_base + threadIdx.x, expect, err);
+    __shared__ int s_fail;
+    if (threadIdx.x == 0) s_fail = 0;
     __syncthreads();
+    if ((int)threadIdx.x < grads.n && !spin_wait_ge(wait_flags + slot_base + threadIdx.x, expect, err)) s_fail = 1;
+    __syncthreads();
+    if (s_fail) return;  // a peer never signalled: leave the shard untouched, the host raises on the error word
   }
   const int64_t nvec = n >> 2;
   float ss = 0.f;
@@ -150,6 +167,59 @@ PB_EXPORT int pb_grad_reduce(const PeerPtrs* grads, int64_t off, int64_t n, floa
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   grad_reduce_kernel<<<grid, 512, 0, stream>>>(*grads, off, n, scale, out, sumsq_partial, wait_flags, slot_base, expect,
                                                err);
+  PB_CHECK_LAUNCH();
+  return 0;
+}
+
+// Segmented variant for row-sharded (ZeRO-3) buckets: the rank's shard of a bucket is one row block PER PARAMETER, i.e. up to
+// kMaxSegs strided pieces of the full-size gradient buffer. out[dst_off[s] + i] = scale * Σ_p grads[p][src_off[s] + i].
+constexpr int kMaxSegs = 16;
+struct SegTable {
+  int64_t src_off[kMaxSegs], dst_off[kMaxSegs], n[kMaxSegs];
+  int nseg;
+};
+__global__ void __launch_bounds__(512) grad_reduce_segs_kernel(PeerPtrs grads, SegTable segs, float scale, float* __restrict__ out,
+                                                               float* __restrict__ sumsq_partial, const uint32_t* wait_flags,
+                                                               int slot_base, uint32_t expect, uint32_t* err) {
+  __shared__ float red[32];
+  if (wait_flags != nullptr) {
+    __shared__ int s_fail;
+    if (threadIdx.x == 0) s_fail = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < grads.n && !spin_wait_ge(wait_flags + slot_base + threadIdx.x, expect, err)) s_fail = 1;
+    __syncthreads();
+    if (s_fail) return;
+  }
+  float ss = 0.f;
+  for (int sidx = 0; sidx < segs.nseg; ++sidx) {
+    const int64_t nvec = segs.n[sidx] >> 2, so = segs.src_off[sidx];
+    float4* o4 = reinterpret_cast<float4*>(out + segs.dst_off[sidx]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p) {
+        if (p < grads.n) {
+          const float4 v = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.p[p]) + so) + i);
+          acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+        }
+      }
+      acc.x *= scale, acc.y *= scale, acc.z *= scale, acc.w *= scale;
+      o4[i] = acc;
+      ss += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+    }
+  }
+  ss = block_sum(ss, red);
+  if (threadIdx.x == 0) sumsq_partial[blockIdx.x] += ss;
+}
+PB_EXPORT int pb_grad_reduce_segs(const PeerPtrs* grads, const SegTable* segs, float scale, float* out, float* sumsq_partial,
+                                  const uint32_t* wait_flags, int slot_base, uint32_t expect, uint32_t* err, int max_ctas,
+                                  cudaStream_t stream) {
+  if (segs->nseg < 0 || segs->nseg > kMaxSegs) return -1;
+  for (int i = 0; i < segs->nseg; ++i)
+    if ((segs->n[i] | segs->src_off[i] | segs->dst_off[i]) & 3) return -1;
+  int grid = pb_grad_reduce_grid();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  grad_reduce_segs_kernel<<<grid, 512, 0, stream>>>(*grads, *segs, scale, out, sumsq_partial, wait_flags, slot_base, expect, err);
   PB_CHECK_LAUNCH();
   return 0;
 }
@@ -190,12 +260,14 @@ __global__ void __launch_bounds__(512) adamw_push_kernel(float* __restrict__ p32
                                                          const uint32_t* wait_flags, int flag_slot, uint32_t epoch,
                                                          PeerPtrs dst, int64_t dst_off, float* gnorm_out, uint32_t* err) {
   __shared__ float s_clip;
+  __shared__ int s_fail;
   if (threadIdx.x == 0) {
     float clip = 1.f;
+    s_fail = 0;
     if (norm_slots != nullptr) {
       float tot = 0.f;
       for (int i = 0; i < n_norm; ++i) {
-        if (wait_flags) spin_wait_ge(wait_flags + flag_slot + i, epoch, err);
+        if (wait_flags && !spin_wait_ge(wait_flags + flag_slot + i, epoch, err)) s_fail = 1;
         tot += reinterpret_cast<const volatile float*>(norm_slots)[i];
       }
       const float gn = sqrtf(tot);
@@ -205,6 +277,7 @@ __global__ void __launch_bounds__(512) adamw_push_kernel(float* __restrict__ p32
     s_clip = clip;
   }
   __syncthreads();
+  if (s_fail) return;  // global norm unknown: do not touch the optimizer state (the step is void, the host raises)
   const float clip = s_clip;
   const float step_size = a.lr / a.bc1;
   const float inv_sqrt_bc2 = rsqrtf(a.bc2);
@@ -255,152 +328,226 @@ PB_EXPORT int pb_adamw_push(float* p32, const float* g32, float* m, float* v, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// DiLoCo outer step, kernel 1: pseudo-gradient ⊕ symmetric int8 block quantisation.
-//   delta = theta0 - theta ;  q = round(delta / (absmax/127)) ; one fp32 scale per `block` elements.
-// One CTA (256 thr) per 1024-element block, 4 elements per thread.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pseudograd_quant_kernel(const float* __restrict__ theta0,
-                                                               const float* __restrict__ theta, int8_t* __restrict__ q,
-                                                               float* __restrict__ scales, int64_t n) {
-  __shared__ float red[32];
-  for (int64_t blk = blockIdx.x; blk * 1024 < n; blk += gridDim.x) {
-    const int64_t base = blk * 1024 + threadIdx.x * 4;
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
-    if (base + 3 < n) {
-      const float4 a = *reinterpret_cast<const float4*>(theta0 + base);
-      const float4 b = *reinterpret_cast<const float4*>(theta + base);
-      d[0] = a.x - b.x, d[1] = a.y - b.y, d[2] = a.z - b.z, d[3] = a.w - b.w;
-    } else {
-      for (int k = 0; k < 4; ++k)
-        if (base + k < n) d[k] = theta0[base + k] - theta[base + k];
-    }
-    float am = fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fmaxf(fabsf(d[2]), fabsf(d[3])));
-    am = block_max(am, red);
-    const float scale = am / 127.f;
-    const float inv = scale > 0.f ? 1.f / scale : 0.f;
-    if (threadIdx.x == 0) scales[blk] = scale;
-    char4 o;
-    o.x = (signed char)fmaxf(-127.f, fminf(127.f, rintf(d[0] * inv)));
-    o.y = (signed char)fmaxf(-127.f, fminf(127.f, rintf(d[1] * inv)));
-    o.z = (signed char)fmaxf(-127.f, fminf(127.f, rintf(d[2] * inv)));
-    o.w = (signed char)fmaxf(-127.f, fminf(127.f, rintf(d[3] * inv)));
-    if (base + 3 < n) {
-      *reinterpret_cast<char4*>(q + base) = o;
-    } else {
-      const signed char ov[4] = {o.x, o.y, o.z, o.w};
-      for (int k = 0; k < 4; ++k)
-        if (base + k < n) q[base + k] = ov[k];
-    }
-  }
-}
-
-PB_EXPORT int pb_pseudograd_quant(const float* theta0, const float* theta, int8_t* q, float* scales, int64_t n,
-                                  cudaStream_t stream) {
-  int64_t blocks = (n + 1023) / 1024;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  pseudograd_quant_kernel<<<(unsigned)blocks, 256, 0, stream>>>(theta0, theta, q, scales, n);
-  PB_CHECK_LAUNCH();
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// DiLoCo outer step, kernel 2: int8 all-gather by peer loads ⊕ dequantise-sum (fixed worker order)
-// ⊕ Nesterov SGD on theta0 ⊕ reset of the inner fp32 master ⊕ bf16 write-back to the FSDP group.
-// `qs.p[w]` / `ss.p[w]` are worker w's int8 payload / scales for THIS shard (peer-mapped).
+// DiLoCo outer step.  Shard space (theta0 / momentum / inner master / int8 payload) is one contiguous index range per rank;
+// the bf16 parameter buffer is bucketed, so the write-back position of shard element i is  dst_start[b] + (i - shard_start[b])
+// for the bucket b that contains i (tables in device memory, <= a few hundred entries, every boundary a multiple of 1024).
+// With that table ONE launch covers every bucket (round 1 launched one kernel per bucket).
+//
+// Vector widths: 16 elements per thread — int8 payload = one 16-byte load per worker (ld.relaxed.sys.v4: peer data, L2-bypass),
+// fp32 state = 4 x float4, bf16 parameters = two 16-byte stores per FSDP peer (round 1: 4-byte int8 loads, 8-byte bf16 stores).
+// A 1024-element quantisation block is owned by 64 threads (2 warps); a 256-thread CTA walks 4 blocks per iteration.
 // ------------------------------------------------------------------------------------------------
 struct OuterArgs {
   float lr, momentum, inv_workers;
   int nesterov;
 };
+struct BucketTable {
+  const int64_t* shard_start;  // [nb + 1] ascending, shard_start[nb] = n
+  const int64_t* dst_start;    // [nb] element offset in the bf16 parameter buffer
+  int nb;
+};
 
+__device__ __forceinline__ int64_t table_dst(const BucketTable& t, int64_t i) {
+  int lo = 0, hi = t.nb - 1;
+  while (lo < hi) {  // last bucket whose shard_start <= i
+    const int mid = (lo + hi + 1) >> 1;
+    if (t.shard_start[mid] <= i) lo = mid;
+    else hi = mid - 1;
+  }
+  return t.dst_start[lo] + (i - t.shard_start[lo]);
+}
+
+__device__ __forceinline__ void dequant16(const uint4& q, float sc, float (&g)[16]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[j * 4 + k] += (float)(int8_t)((w[j] >> (8 * k)) & 0xffu) * sc;
+  }
+}
+
+// kernel 1: pseudo-gradient ⊕ symmetric int8 block quantisation.  delta = theta0 - theta; q = rint(delta / (absmax/127)).
+__global__ void __launch_bounds__(256) pseudograd_quant_kernel(const float* __restrict__ theta0, const float* __restrict__ theta,
+                                                               int8_t* __restrict__ q, float* __restrict__ scales, int64_t n) {
+  __shared__ float s_max[8];
+  const int grp = threadIdx.x >> 6, t64 = threadIdx.x & 63, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nblk = n >> 10;
+  for (int64_t blk0 = (int64_t)blockIdx.x * 4; blk0 < nblk; blk0 += (int64_t)gridDim.x * 4) {
+    const int64_t blk = blk0 + grp;
+    const bool on = blk < nblk;
+    const int64_t base = blk * 1024 + t64 * 16;
+    float d[16];
+    float am = 0.f;
+    if (on) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a = ldg_stream_f4(reinterpret_cast<const float4*>(theta0 + base) + j);
+        const float4 b = ldg_stream_f4(reinterpret_cast<const float4*>(theta + base) + j);
+        d[4 * j] = a.x - b.x, d[4 * j + 1] = a.y - b.y, d[4 * j + 2] = a.z - b.z, d[4 * j + 3] = a.w - b.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) am = fmaxf(am, fabsf(d[k]));
+    }
+    am = warp_max(am);
+    __syncthreads();
+    if (lane == 0) s_max[warp] = am;
+    __syncthreads();
+    am = fmaxf(s_max[grp * 2], s_max[grp * 2 + 1]);
+    if (!on) continue;
+    const float scale = am / 127.f;
+    const float inv = scale > 0.f ? 1.f / scale : 0.f;
+    if (t64 == 0) scales[blk] = scale;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t pk = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int v = (int)fmaxf(-127.f, fminf(127.f, rintf(d[4 * j + k] * inv)));
+        pk |= ((uint32_t)v & 0xffu) << (8 * k);
+      }
+      w[j] = pk;
+    }
+    *reinterpret_cast<uint4*>(q + base) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+PB_EXPORT int pb_pseudograd_quant(const float* theta0, const float* theta, int8_t* q, float* scales, int64_t n,
+                                  cudaStream_t stream) {
+  if (n % 1024 != 0) return -1;
+  int64_t ctas = (n / 1024 + 3) / 4;
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  if (ctas < 1) ctas = 1;
+  pseudograd_quant_kernel<<<(unsigned)ctas, 256, 0, stream>>>(theta0, theta, q, scales, n);
+  PB_CHECK_LAUNCH();
+  return 0;
+}
+
+// kernel 2: int8 all-gather by peer loads ⊕ dequantise-sum (fixed worker order → bitwise identical theta0 on every worker)
+// ⊕ Nesterov SGD on theta0 ⊕ reset of the inner fp32 master ⊕ bf16 write-back to the FSDP group.
+// `qs.p[w]` / `ss.p[w]` = worker w's int8 payload / scales for THIS rank's shard (peer-mapped).
 __global__ void __launch_bounds__(256) outer_nesterov_kernel(PeerPtrs qs, PeerPtrs ss, float* __restrict__ theta0,
                                                              float* __restrict__ mom, float* __restrict__ theta, int64_t n,
-                                                             OuterArgs a, PeerPtrs dst, int64_t dst_off) {
-  for (int64_t blk = blockIdx.x; blk * 1024 < n; blk += gridDim.x) {
-    const int64_t base = blk * 1024 + threadIdx.x * 4;
-    if (base >= n) continue;
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool full = base + 3 < n;
+                                                             OuterArgs a, PeerPtrs dst, BucketTable tab) {
+  const int grp = threadIdx.x >> 6, t64 = threadIdx.x & 63, lane = threadIdx.x & 31;
+  const int64_t nblk = n >> 10;
+  for (int64_t blk0 = (int64_t)blockIdx.x * 4; blk0 < nblk; blk0 += (int64_t)gridDim.x * 4) {
+    const int64_t blk = blk0 + grp;
+    if (blk >= nblk) continue;  // whole warps drop out together (a block is two full warps)
+    const int64_t base = blk * 1024 + t64 * 16;
+    float g[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) g[k] = 0.f;
 #pragma unroll
     for (int w = 0; w < kMaxPeers; ++w) {
       if (w < qs.n) {
-        const float sc = *reinterpret_cast<const volatile float*>(reinterpret_cast<const float*>(ss.p[w]) + blk);
-        const int8_t* qp = reinterpret_cast<const int8_t*>(qs.p[w]) + base;
-        if (full) {
-          int packed;
-          asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(packed) : "l"(qp));
-          g[0] += (float)(int8_t)(packed & 0xff) * sc;
-          g[1] += (float)(int8_t)((packed >> 8) & 0xff) * sc;
-          g[2] += (float)(int8_t)((packed >> 16) & 0xff) * sc;
-          g[3] += (float)(int8_t)((packed >> 24) & 0xff) * sc;
-        } else {
-          for (int k = 0; k < 4; ++k)
-            if (base + k < n) g[k] += (float)reinterpret_cast<const volatile int8_t*>(qp)[k] * sc;
-        }
+        float sc = 0.f;
+        if (lane == 0) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(sc) : "l"(reinterpret_cast<const float*>(ss.p[w]) + blk));
+        sc = __shfl_sync(0xffffffffu, sc, 0);
+        const uint4 qv = ld_relaxed_sys_u4(reinterpret_cast<const uint4*>(reinterpret_cast<const int8_t*>(qs.p[w]) + base));
+        dequant16(qv, sc, g);
       }
     }
-    float outv[4];
-    for (int k = 0; k < 4; ++k) {
-      if (base + k < n) {
-        const float gk = g[k] * a.inv_workers;
-        const float mk = a.momentum * mom[base + k] + gk;
-        mom[base + k] = mk;
-        const float upd = a.nesterov ? gk + a.momentum * mk : mk;
-        const float t = theta0[base + k] - a.lr * upd;
-        theta0[base + k] = t;
-        theta[base + k] = t;
-        outv[k] = t;
-      }
-    }
-    if (full) {
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(outv[0], outv[1]), hi = __floats2bfloat162_rn(outv[2], outv[3]);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    float outv[16];
 #pragma unroll
-      for (int q = 0; q < kMaxPeers; ++q)
-        if (q < dst.n) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst.p[q]) + dst_off + base) = pk;
-    } else {
-      for (int k = 0; k < 4; ++k)
-        if (base + k < n)
-          for (int q = 0; q < dst.n; ++q)
-            (reinterpret_cast<__nv_bfloat16*>(dst.p[q]) + dst_off)[base + k] = __float2bfloat16(outv[k]);
+    for (int j = 0; j < 4; ++j) {
+      float4 t0 = reinterpret_cast<const float4*>(theta0 + base)[j];
+      float4 mm = reinterpret_cast<const float4*>(mom + base)[j];
+      float* tp = &t0.x;
+      float* mp = &mm.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gk = g[4 * j + k] * a.inv_workers;
+        const float mk = a.momentum * mp[k] + gk;
+        mp[k] = mk;
+        const float upd = a.nesterov ? gk + a.momentum * mk : mk;
+        tp[k] = tp[k] - a.lr * upd;
+        outv[4 * j + k] = tp[k];
+      }
+      reinterpret_cast<float4*>(theta0 + base)[j] = t0;
+      reinterpret_cast<float4*>(mom + base)[j] = mm;
+      reinterpret_cast<float4*>(theta + base)[j] = t0;
+    }
+    const int64_t d0 = table_dst(tab, base);
+    const float lo8[8] = {outv[0], outv[1], outv[2], outv[3], outv[4], outv[5], outv[6], outv[7]};
+    const float hi8[8] = {outv[8], outv[9], outv[10], outv[11], outv[12], outv[13], outv[14], outv[15]};
+    const bf16x8 plo = pack8(lo8), phi = pack8(hi8);
+#pragma unroll
+    for (int qd = 0; qd < kMaxPeers; ++qd) {
+      if (qd < dst.n) {
+        bf16x8* o = reinterpret_cast<bf16x8*>(reinterpret_cast<__nv_bfloat16*>(dst.p[qd]) + d0);
+        stg_v4(o, plo);
+        stg_v4(o + 1, phi);
+      }
     }
   }
 }
 
 PB_EXPORT int pb_outer_nesterov(const PeerPtrs* qs, const PeerPtrs* ss, float* theta0, float* mom, float* theta, int64_t n,
-                                const OuterArgs* a, const PeerPtrs* dst, int64_t dst_off, cudaStream_t stream) {
-  if (dst_off % 4 != 0) return -1;
-  int64_t blocks = (n + 1023) / 1024;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  outer_nesterov_kernel<<<(unsigned)blocks, 256, 0, stream>>>(*qs, *ss, theta0, mom, theta, n, *a, *dst, dst_off);
+                                const OuterArgs* a, const PeerPtrs* dst, const int64_t* shard_start, const int64_t* dst_start,
+                                int nb, cudaStream_t stream) {
+  if (n % 1024 != 0 || nb < 1) return -1;
+  int64_t ctas = (n / 1024 + 3) / 4;
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  if (ctas < 1) ctas = 1;
+  BucketTable tab{shard_start, dst_start, nb};
+  outer_nesterov_kernel<<<(unsigned)ctas, 256, 0, stream>>>(*qs, *ss, theta0, mom, theta, n, *a, *dst, tab);
   PB_CHECK_LAUNCH();
   return 0;
 }
 
-// fp32 (uncompressed) outer path: all-gather of pseudo-gradients by peer loads, same update.
-__global__ void __launch_bounds__(256) outer_nesterov_f32_kernel(PeerPtrs thetas /*peer inner masters*/,
-                                                                 float* __restrict__ theta0, float* __restrict__ mom,
-                                                                 float* __restrict__ theta_tmp, int64_t n, OuterArgs a) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float t0 = theta0[i];
-    float g = 0.f;
-    for (int w = 0; w < thetas.n; ++w) g += t0 - *reinterpret_cast<const volatile float*>(reinterpret_cast<const float*>(thetas.p[w]) + i);
-    g *= a.inv_workers;
-    const float mk = a.momentum * mom[i] + g;
-    mom[i] = mk;
-    const float upd = a.nesterov ? g + a.momentum * mk : mk;
-    const float t = t0 - a.lr * upd;
-    theta0[i] = t;
-    theta_tmp[i] = t;  // caller copies into the inner master after a barrier (peers still read theta)
+// fp32 (uncompressed) outer path: the workers' inner masters live in the symmetric heap; every worker loads the peers' masters
+// directly (16-byte ld.relaxed.sys), forms the averaged pseudo-gradient in fixed worker order, applies Nesterov to theta0, stages
+// the new master in `theta_new` (peers are still reading `thetas.p[self]`; the caller copies it back after the closing barrier) and
+// pushes the bf16 parameters to the FSDP group.
+__global__ void __launch_bounds__(256) outer_nesterov_f32_kernel(PeerPtrs thetas, float* __restrict__ theta0, float* __restrict__ mom,
+                                                                 float* __restrict__ theta_new, int64_t n, OuterArgs a, PeerPtrs dst,
+                                                                 BucketTable tab) {
+  const int64_t nvec = n >> 3;  // 8 elements per thread-iteration → one 16-byte bf16 store per peer
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float outv[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t j = i * 2 + h;
+      float4 t0 = reinterpret_cast<const float4*>(theta0)[j];
+      float4 mm = reinterpret_cast<const float4*>(mom)[j];
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < kMaxPeers; ++w) {
+        if (w < thetas.n) {
+          const float4 tw = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(thetas.p[w]) + j);
+          g.x += t0.x - tw.x, g.y += t0.y - tw.y, g.z += t0.z - tw.z, g.w += t0.w - tw.w;
+        }
+      }
+      float* tp = &t0.x;
+      float* mp = &mm.x;
+      const float* gp = &g.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gk = gp[k] * a.inv_workers;
+        const float mk = a.momentum * mp[k] + gk;
+        mp[k] = mk;
+        const float upd = a.nesterov ? gk + a.momentum * mk : mk;
+        tp[k] = tp[k] - a.lr * upd;
+        outv[h * 4 + k] = tp[k];
+      }
+      reinterpret_cast<float4*>(theta0)[j] = t0;
+      reinterpret_cast<float4*>(mom)[j] = mm;
+      reinterpret_cast<float4*>(theta_new)[j] = t0;
+    }
+    const int64_t d0 = table_dst(tab, i * 8);
+    const bf16x8 pk = pack8(outv);
+#pragma unroll
+    for (int qd = 0; qd < kMaxPeers; ++qd)
+      if (qd < dst.n) stg_v4(reinterpret_cast<bf16x8*>(reinterpret_cast<__nv_bfloat16*>(dst.p[qd]) + d0), pk);
   }
 }
-PB_EXPORT int pb_outer_nesterov_f32(const PeerPtrs* thetas, float* theta0, float* mom, float* theta_tmp, int64_t n,
-                                    const OuterArgs* a, cudaStream_t stream) {
-  outer_nesterov_f32_kernel<<<148 * 4, 256, 0, stream>>>(*thetas, theta0, mom, theta_tmp, n, *a);
+PB_EXPORT int pb_outer_nesterov_f32(const PeerPtrs* thetas, float* theta0, float* mom, float* theta_new, int64_t n, const OuterArgs* a,
+                                    const PeerPtrs* dst, const int64_t* shard_start, const int64_t* dst_start, int nb,
+                                    cudaStream_t stream) {
+  if (n % 8 != 0 || nb < 1) return -1;
+  BucketTable tab{shard_start, dst_start, nb};
+  outer_nesterov_f32_kernel<<<148 * 4, 256, 0, stream>>>(*thetas, theta0, mom, theta_new, n, *a, *dst, tab);
   PB_CHECK_LAUNCH();
   return 0;
 }

@@ -38,14 +38,20 @@ constexpr uint32_t kStagingBytes = 4 /*epilogue warps*/ * 2 /*buffers*/ * 4096; 
 constexpr int kGroupM = 16;  // raster: super-rows of 16 M-tiles keep the A slab L2-resident
 
 // per-variant geometry: PAIR=0 one CTA owns 128 x 256; PAIR=1 a CTA pair owns 256 x 256 and each CTA stages half of B
-template <int PAIR>
+constexpr uint32_t kCopyChunkBytes = 128 * BK * 2;  // IO = 3 weight-gather copier: one {64 col, 128 row} box = 16 KB
+constexpr int kCopyBufs = 2;
+constexpr int kGatherSub = 4;  // IO = 3: readiness flags per rank block (a block is released to the MMA tiles in quarters)
+
+template <int PAIR, int IO = 0>
 struct Geo {
   static constexpr int kTileM = PAIR ? 2 * BM : BM;        // rows of C per scheduled tile
   static constexpr int kBRows = PAIR ? BN / 2 : BN;        // B rows staged by one CTA
   static constexpr uint32_t kBBytes = kBRows * BK * 2;     // 16 KB | 32 KB
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = PAIR ? 6 : 4;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // IO = 3 gives one ring stage (32 KB) to the weight-gather copier's two 16 KB bounce buffers
+  static constexpr int kStages = PAIR ? (IO == 3 ? 5 : 6) : 4;
+  static constexpr uint32_t kCopyBytes = IO == 3 ? kCopyBufs * kCopyChunkBytes : 0;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kCopyBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 using namespace tc;
@@ -56,11 +62,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int a_mn, int b_mn, int m) {
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
-  const int per_group = kGroupM * tiles_n;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn, int group_m = kGroupM) {
+  const int per_group = group_m * tiles_n;
   const int g = tile / per_group;
-  const int first_m = g * kGroupM;
-  const int gsz = min(kGroupM, tiles_m - first_m);
+  const int first_m = g * group_m;
+  const int gsz = min(group_m, tiles_m - first_m);
   const int r = tile - g * per_group;
   tm = first_m + r % gsz;
   tn = r / gsz;
@@ -83,6 +89,7 @@ struct GemmParams {
   // accumulator holds gate in columns [0,128) and up in [128,256) for the same features. The epilogue stores gate and up (bf16,
   // for the backward) into C = gate_up [M, 2·FF] and h = silu(gate)·up into the second output [M, FF].
   int swiglu_ff;
+  int group_m;  // raster super-row height in M tiles (0 = kGroupM)
 };
 
 // Fused collective GEMMs over the NVLink symmetric heap (IO template parameter of the kernel):
@@ -97,13 +104,29 @@ struct GemmParams {
 //           buffer of the rank that owns those rows (cp.reduce.async.bulk.tensor on a peer-mapped address). Row blocks are visited
 //           owner-interleaved (rank+1, rank+2, …, self) so the NVLink reduce traffic is spread over the whole kernel and, at any
 //           moment, the ranks target distinct owners.
+//   IO = 3  parameter all-gather ⊕ GEMM (ZeRO-3 / reshard_after_forward): the WEIGHT (operand B, stored [rows, cols]) is sharded by
+//           rows over the ranks of the FSDP group — rank r owns rows [r·rpr, (r+1)·rpr) in its symmetric-heap shard. Nothing is
+//           gathered ahead of the kernel: warp 3 of EVERY CTA is a copier that TMA-loads {64 x 128} boxes of the peers' shards
+//           over NVLink into a 16 KB bounce buffer and TMA-stores them into a local full-size copy of the weight, walking the rank
+//           blocks in consumption order (own block first); a per-quarter-block counter releases the MMA tiles, whose TMA producer
+//           waits on the counters of exactly the B rows it is about to load and reads them from the local copy (L2-resident).
+//           K-major B (forward): the output-column order is rotated to start at the own block; MN-major B (input gradient, the
+//           contraction runs over the sharded rows): the K loop is rotated instead. The shards are read-only during
+//           forward/backward, so no inter-rank barrier is needed around the kernel.
 struct PeerMaps {
   CUtensorMap m[8];
   int n;              // ranks
-  int rows_per_rank;  // multiple of the tile height
+  int rows_per_rank;  // IO 1/2: multiple of the tile height; IO 3: rows of B owned by each rank
   int rank;
   uint32_t* flags;    // IO = 1: one counter per 256-row block of the gathered A (zeroed by the host before the launch)
+                      // IO = 3: n * kGatherSub counters (chunks landed per quarter block), zeroed before the launch
   int idle_rounds;    // IO = 1: scheduling rounds a CTA pair sits out after a gather tile (it costs ~3 ordinary tiles: NVLink latency)
+  // IO = 3
+  int order[8];       // rank blocks in the order the copiers fetch them (= the order the tiles consume them)
+  int cpr;            // 128-row chunk rows per rank block = ceil(rows_per_rank / 128)
+  int col_chunks;     // cols / 64
+  int spc;            // chunk rows per readiness counter = ceil(cpr / kGatherSub)
+  int start;          // first output-column tile (K-major B) / first k-block (MN-major B) of the rotated order
 };
 
 // IO = 1 tile schedule: [gather tiles][local tiles][dependent tiles]; kind 1 = gather (tn = 0 of a remote block), 0 = local rows,
@@ -175,9 +198,9 @@ __device__ __forceinline__ void rope_regs(uint32_t (&r)[32], const float* __rest
 template <int A_MN, int B_MN, int PAIR, int EPI, int IO>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_h, const GemmParams p,
-                     const __grid_constant__ PeerMaps pm) {
-  using G = Geo<PAIR>;
+                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_h,
+                     const __grid_constant__ CUtensorMap tmap_g, const GemmParams p, const __grid_constant__ PeerMaps pm) {
+  using G = Geo<PAIR, IO>;
   constexpr int kStages = G::kStages;
   constexpr uint32_t kStageBytes = G::kStageBytes;
   constexpr int kBRows = G::kBRows;
@@ -188,12 +211,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + kStages * kStageBytes;  // 1024-aligned: 4 warps x 2 buffers x 4 KB
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint8_t* copy_buf = staging + kStagingBytes;  // IO = 3: kCopyBufs x 16 KB bounce buffers of the weight-gather copier
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(copy_buf + G::kCopyBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + kAccStages;
   uint64_t* copied_bar = tempty_bar + kAccStages;  // IO = 1: the gather copier has finished reading a consumed ring slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(copied_bar + kStages);
+  uint64_t* cp_bar = copied_bar + kStages;         // IO = 3: a peer box has landed in bounce buffer i
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cp_bar + kCopyBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool swiglu = PAIR && EPI == 2;
@@ -215,12 +240,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int t = sched_id + (it++) * sched_n;
     return t < num_tiles ? t : -2;
   };
+  const int group_m = p.group_m > 0 ? p.group_m : kGroupM;
+  // IO = 3 rotations (see PeerMaps): K-major B → output columns start at the own rank block; MN-major B → the K loop does
+  const int tn_rot = (IO == 3 && B_MN == 0) ? pm.start : 0;
+  const int kb_rot = (IO == 3 && B_MN == 1) ? pm.start : 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_c);
     prefetch_tmap(&tmap_h);
+    if (IO == 3) prefetch_tmap(&tmap_g);
     if (IO != 0)
       for (int i = 0; i < pm.n; ++i) prefetch_tmap(&pm.m[i]);
   }
@@ -230,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&empty_bar[i], 1);
       mbar_init(&copied_bar[i], 1);
     }
+    for (int i = 0; i < kCopyBufs; ++i) mbar_init(&cp_bar[i], 1);
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs in a pair)
@@ -255,25 +286,50 @@ __global__ void __launch_bounds__(kThreads, 1)
       // gather tiles have the lowest indices: this CTA's are tiles sched_id, sched_id + sched_n, … below G
       const int gather_fills = ag_G > sched_id ? ((ag_G - sched_id + sched_n - 1) / sched_n) * num_kb : 0;
       int fill = 0;
+      // IO = 3: wait until the copiers have landed B rows [r0, r1] in the local full copy. One readiness counter per quarter of a
+      // rank block; a counter that was seen complete stays complete for the rest of the kernel (bit in `ready`).
+      uint32_t ready = 0;
+      auto gate_rows = [&](int r0, int r1) {
+        if (IO != 3) return;
+        const int rpr = pm.rows_per_rank;
+        for (int x = r0; x <= r1;) {
+          const int b = x / rpr, cr = (x - b * rpr) >> 7;
+          const int q = min(cr / pm.spc, kGatherSub - 1);
+          const int id = b * kGatherSub + q;
+          const int cr_end = q == kGatherSub - 1 ? pm.cpr : min(pm.cpr, (q + 1) * pm.spc);  // chunk rows [q*spc, cr_end)
+          if (!((ready >> id) & 1u)) {
+            const uint32_t expect = (uint32_t)((cr_end - q * pm.spc) * pm.col_chunks);
+            SpinGuard guard;
+            while (pb::ld_acquire_gpu_u32(pm.flags + id) < expect) guard.tick();
+            fence_proxy_async_all();  // generic-proxy acquire → the TMA (async-proxy) reads of those rows
+            ready |= 1u << id;
+          }
+          x = b * rpr + min(rpr, cr_end * 128);  // first row of the next quarter (or of the next rank block)
+        }
+      };
       for (int it = 0, tile; (tile = next_tile(it)) >= 0;) {
         int tm, tn, kind = 0;
         if (IO == 1 && pm.n > 1) {
           ag_tile(tile, pm, tiles_n, tpr, tm, tn, kind);
         } else {
-          tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn);
+          tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn, group_m);
           if (IO == 2) tm = rs_tile_row(tm, pm, tpr);
+          if (IO == 3 && tn_rot) tn = (tn + tn_rot) % tiles_n;
         }
         const int kb0 = (tile % split_k) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
         if (kb0 >= kb1) continue;  // empty K slice (split does not divide K): every role skips it identically
         const int m0 = tm * kTileM + (int)crank * BM;      // this CTA's A rows
         // this CTA's share of the B rows (SwiGLU mode: leader = gate rows, partner = the matching up rows)
         const int n0 = swiglu ? (int)crank * p.swiglu_ff + tn * 128 : tn * BN + (int)crank * kBRows;
+        if (IO == 3 && B_MN == 0) gate_rows(n0, min(n0 + kBRows, pm.rows_per_rank * pm.n) - 1);  // my B rows have landed locally
         if (IO == 1 && kind == 2) {  // the block's gather tile (both CTAs of that pair) has stored these rows locally
           SpinGuard guard;
           while (pb::ld_acquire_gpu_u32(pm.flags + tm) < 2u) guard.tick();
           fence_proxy_async_all();  // generic-proxy acquire → the TMA (async-proxy) reads below
         }
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kbi = kb0; kbi < kb1; ++kbi) {
+          const int kb = kb_rot ? (kbi + kb_rot) % num_kb : kbi;
+          if (IO == 3 && B_MN == 1) gate_rows(kb * BK, min(kb * BK + BK, pm.rows_per_rank * pm.n) - 1);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           // the slot's previous fill was a gather fill (they are the first fills of every CTA): the copier must have drained it
           if (IO == 1 && fill >= kStages && fill - kStages < gather_fills) mbar_wait(&copied_bar[stage], phase ^ 1);
@@ -375,6 +431,59 @@ __global__ void __launch_bounds__(kThreads, 1)
         pb::red_add_release_gpu_u32(pm.flags + tm, 1u);
       }
     }
+  } else if (IO == 3 && warp == 3) {
+    // ------------------------------------------------------------------ weight-gather copier (parameter all-gather ⊕ GEMM)
+    // Every CTA of the grid takes the {64 col x 128 row} boxes g = blockIdx.x, blockIdx.x + gridDim.x, … of the whole weight in
+    // consumption order: peer shard --TMA load (NVLink)--> bounce buffer --TMA store--> local full copy, then bumps the
+    // readiness counter of the box's quarter block once the store has fully completed. Two boxes are in flight per CTA
+    // (148 x 32 KB per ~3 us of NVLink latency is well above what the MMA tiles consume).
+    if (lane == 0) {
+      const int cpb = pm.cpr * pm.col_chunks;  // boxes per rank block
+      const int total = cpb * pm.n;
+      const int mine = total > (int)blockIdx.x ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      auto box = [&](int i, int& owner, int& cr, int& cc) {
+        const int g = (int)blockIdx.x + i * (int)gridDim.x;
+        const int j = g / cpb, c = g - j * cpb;
+        owner = pm.order[j];
+        cr = c / pm.col_chunks;
+        cc = c - cr * pm.col_chunks;
+      };
+      auto fetch = [&](int i) {  // rows past the end of the owner's shard are zero-filled by the TMA unit
+        int owner, cr, cc;
+        box(i, owner, cr, cc);
+        const int buf = i % kCopyBufs;
+        mbar_expect_tx(&cp_bar[buf], kCopyChunkBytes);
+        tma_load_2d(&pm.m[owner], &cp_bar[buf], copy_buf + buf * kCopyChunkBytes, cc * BK, cr * 128);
+      };
+      for (int i = 0; i < kCopyBufs && i < mine; ++i) fetch(i);  // both NVLink loads in flight from the start
+      uint32_t ph[kCopyBufs] = {0, 0};
+      int prev_id = -1;
+      for (int i = 0; i < mine; ++i) {
+        int owner, cr, cc;
+        box(i, owner, cr, cc);
+        const int buf = i % kCopyBufs;
+        mbar_wait(&cp_bar[buf], ph[buf]);
+        ph[buf] ^= 1;
+        // … and clipped by the store: dimension 1 of the 3-D map is the rows of ONE rank block
+        tma_store_3d(&tmap_g, copy_buf + buf * kCopyChunkBytes, cc * BK, cr * 128, owner);
+        bulk_commit();
+        if (prev_id >= 0) {  // the previous box's WRITES are complete (not only its smem reads): publish it
+          asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+          fence_proxy_async_all();
+          pb::red_add_release_gpu_u32(pm.flags + prev_id, 1u);
+        }
+        prev_id = owner * kGatherSub + min(cr / pm.spc, kGatherSub - 1);
+        if (i + kCopyBufs < mine) {
+          bulk_wait_read<0>();  // this buffer has been read out by the store above
+          fetch(i + kCopyBufs);
+        }
+      }
+      if (prev_id >= 0) {
+        bulk_wait_all();
+        fence_proxy_async_all();
+        pb::red_add_release_gpu_u32(pm.flags + prev_id, 1u);
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     // TMEM → registers → 128B-swizzled smem slab (32 rows x 128 B per warp) → TMA store / reduce-add.
@@ -392,8 +501,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (IO == 1 && pm.n > 1) {
         ag_tile(tile, pm, tiles_n, tpr, tm, tn, kind);
       } else {
-        tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn);
+        tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn, group_m);
         if (IO == 2) tm = rs_tile_row(tm, pm, tpr);
+        if (IO == 3 && tn_rot) tn = (tn + tn_rot) % tiles_n;
       }
       if ((tile % split_k) * kb_per >= num_kb) continue;  // empty K slice
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -550,10 +660,11 @@ int g_split_k_mode = -1;  // -1 auto, 0/1 off, n>1 forced
 
 template <int A_MN, int B_MN, int PAIR, int EPI = 0, int IO = 0>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& th, const GemmParams& p,
-           int max_ctas, cudaStream_t stream, const PeerMaps* pmp = nullptr) {
+           int max_ctas, cudaStream_t stream, const PeerMaps* pmp = nullptr, const CUtensorMap* tgp = nullptr) {
   static const PeerMaps kNoPeers = {};
   const PeerMaps& pm = pmp ? *pmp : kNoPeers;
-  using G = Geo<PAIR>;
+  const CUtensorMap& tg = tgp ? *tgp : tc;
+  using G = Geo<PAIR, IO>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, PAIR, EPI, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -572,7 +683,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   const int tiles = ((p.M + G::kTileM - 1) / G::kTileM) * tiles_n * p.split_k;
   if (!PAIR) {
     if (tiles < grid) grid = tiles;
-    gemm_bf16_kernel<A_MN, B_MN, 0, EPI, IO><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, th, p, pm);
+    gemm_bf16_kernel<A_MN, B_MN, 0, EPI, IO><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, th, tg, p, pm);
   } else {
     grid &= ~1;
     if (2 * tiles < grid) grid = 2 * tiles;
@@ -589,7 +700,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1, EPI, IO>, ta, tb, tc, th, p, pm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1, EPI, IO>, ta, tb, tc, th, tg, p, pm);
     if (e != cudaSuccess) return (int)e;
   }
   cudaError_t e = cudaGetLastError();
@@ -766,4 +877,76 @@ PB_EXPORT int pb_gemm_reduce_scatter(const void* A, const void* B, float* const*
   GemmParams p{M, N, K, ldc, 0, b_mn_major, 1, 1, 1, c_peers[rank], nullptr, nullptr, 1, 0, 64, 0};
   return b_mn_major ? launch<0, 1, 1, 0, 2>(ta, tb, pm.m[rank], pm.m[rank], p, 0, stream, &pm)
                     : launch<0, 0, 1, 0, 2>(ta, tb, pm.m[rank], pm.m[rank], p, 0, stream, &pm);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// parameter all-gather ⊕ GEMM (IO = 3; ZeRO-3 / train.reshard_after_forward): the weight W [rowsW, colsW] is sharded by rows
+// over n ranks (rank r: rows [r·rowsW/n, (r+1)·rowsW/n) at w_peers[r], the address AS MAPPED IN THIS PROCESS). The kernel gathers
+// it into w_full (local, [rowsW, colsW]) tile by tile WHILE it multiplies; no collective, no barrier (shards are read-only here).
+//   b_mn_major = 0 (forward)        C[M, rowsW] = A[M, colsW] · Wᵀ          epi: 0 plain | 1 RoPE on the leading columns | 2 SwiGLU
+//   b_mn_major = 1 (input gradient) C[M, colsW] = A[M, rowsW] · W           epi 0 only
+// SwiGLU: W = W13 [2·FF, colsW] = [gate rows | up rows], C = gate_up [M, 2·FF], H = silu(gate)·up [M, FF].
+// flags: n·4 uint32 in local memory (zeroed here, on the stream). bf16 everywhere, CTA-pair tiles (M > 128).
+PB_EXPORT int pb_gemm_wgather(const void* A, const void* const* w_peers, int n, int rank, void* w_full, uint32_t* flags, void* C,
+                              void* H, int M, int rowsW, int colsW, int lda, int ldc, int ldh, int b_mn_major, int epi,
+                              const float* rope_cos, const float* rope_sin, int rope_S, int rope_cols, int rope_D,
+                              cudaStream_t stream) {
+  if (n < 1 || n > 8 || rank < 0 || rank >= n || rowsW % n != 0 || colsW % 64 != 0) return -6;
+  if ((lda % 8) || (ldc % 8)) return -1;
+  if (epi != 0 && b_mn_major) return -7;
+  const int N = b_mn_major ? colsW : rowsW, K = b_mn_major ? rowsW : colsW;
+  const int FF = epi == 2 ? rowsW / 2 : 0;
+  if (epi == 2 && (FF % 64 != 0 || H == nullptr || (ldh % 8))) return -5;
+  if (epi == 1) {
+    if (rope_cos == nullptr || rope_sin == nullptr || rope_S <= 0 || M % rope_S != 0) return -3;
+    if ((rope_D != 64 && rope_D != 128) || rope_cols % rope_D != 0 || rope_cols > N) return -4;
+  }
+  if (M <= BM) return -8;  // CTA-pair scheduler only (training shapes); tiny M goes through an explicit gather on the host side
+  const int rpr = rowsW / n;
+  PeerMaps pm = {};
+  pm.n = n;
+  pm.rows_per_rank = rpr;
+  pm.rank = rank;
+  pm.flags = flags;
+  pm.cpr = (rpr + 127) / 128;
+  pm.col_chunks = colsW / 64;
+  pm.spc = (pm.cpr + kGatherSub - 1) / kGatherSub;
+  if (epi == 2 && n % 2 == 0) {
+    // a tile needs gate rows (blocks < n/2) and the matching up rows (blocks >= n/2): fetch them pairwise, own pair first
+    const int h = n / 2, g0 = rank % h;
+    for (int t = 0; t < h; ++t) {
+      const int g = (g0 + t) % h;
+      pm.order[2 * t] = rank >= h ? g + h : g;
+      pm.order[2 * t + 1] = rank >= h ? g : g + h;
+    }
+    pm.start = (g0 * rpr) / 128;  // tiles are 128 features wide
+  } else {
+    for (int t = 0; t < n; ++t) pm.order[t] = (rank + t) % n;
+    if (epi == 2) pm.start = 0;
+    else pm.start = b_mn_major ? (rank * rpr) / BK : (rank * rpr) / BN;
+  }
+  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)(n * kGatherSub), stream);
+  if (e != cudaSuccess) return (int)e;
+  int rc;
+  for (int r = 0; r < n; ++r)
+    if ((rc = pbhost::cached_tmap(&pm.m[r], w_peers[r], (uint64_t)rpr, (uint64_t)colsW, (uint64_t)colsW, BK, 128))) return rc;
+  CUtensorMap tg, ta, tb, tc, th;
+  if ((rc = pbhost::cached_tmap_blocks(&tg, w_full, (uint64_t)rpr, (uint64_t)colsW, (uint64_t)n, BK, 128))) return rc;
+  if ((rc = pbhost::cached_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, BM))) return rc;
+  if (!b_mn_major) rc = pbhost::cached_tmap(&tb, w_full, (uint64_t)rowsW, (uint64_t)colsW, (uint64_t)colsW, BK, BN / 2);
+  else rc = pbhost::cached_tmap(&tb, w_full, (uint64_t)rowsW, (uint64_t)colsW, (uint64_t)colsW, 64, BK);
+  if (rc) return rc;
+  if ((rc = pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)(epi == 2 ? 2 * FF : N), (uint64_t)ldc, 64, 32, 2))) return rc;
+  th = tc;
+  if (epi == 2 && (rc = pbhost::cached_tmap(&th, H, (uint64_t)M, (uint64_t)FF, (uint64_t)ldh, 64, 32, 2))) return rc;
+  static int group_m = -1;
+  if (group_m < 0) {
+    const char* ev = getenv("PB_WG_GROUP_M");
+    group_m = ev ? atoi(ev) : 0;
+  }
+  GemmParams p{M, epi == 2 ? 2 * FF : N, K, ldc, 0, b_mn_major, 0, 0, 1, C, rope_cos, rope_sin, rope_S, rope_cols, rope_D, FF, group_m};
+  if (epi == 2) return launch<0, 0, 1, 2, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg);
+  if (epi == 1) return launch<0, 0, 1, 1, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg);
+  return b_mn_major ? launch<0, 1, 1, 0, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg) : launch<0, 0, 1, 0, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg);
 }

@@ -125,6 +125,37 @@ int cached_tmap3(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols
   return 0;
 }
 
+// [blocks][rows][cols] bf16 (dense: block stride = rows*cols) with boxes of {box_cols, box_rows, 1}: a box never crosses a block, rows
+// past the end of a block are clipped on stores / zero-filled on loads (the weight-gather copier of gemm_sm100.cu relies on that).
+int cached_tmap_blocks(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t blocks, uint32_t box_cols, uint32_t box_rows) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key{ptr, rows, cols, blocks, box_cols, box_rows, 34};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    EncodeFn enc = get_encode();
+    if (!enc) return -10;
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+      cudaFree(nullptr);
+      ctx_bound = true;
+    }
+    CUtensorMap m;
+    cuuint64_t dims[3] = {cols, rows, blocks};
+    cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -11 - (int)r;
+    if (cache.size() > 8192) cache.clear();
+    it = cache.emplace(key, m).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -11,5 +11,7 @@ int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
                 uint32_t box_rows, int esize = 2);
 // {64 columns, rows, cols/64 chunks} view with boxes of {64, box_rows, chunks}: one TMA instruction per multi-chunk operand tile.
 int cached_tmap3(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t chunks);
+// dense [blocks][rows][cols] bf16 view, boxes {box_cols, box_rows, 1} (rows clipped per block)
+int cached_tmap_blocks(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t blocks, uint32_t box_cols, uint32_t box_rows);
 int num_sms();
 }  // namespace pbhost

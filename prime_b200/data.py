@@ -85,23 +85,38 @@ class MemmapTokenDataset:
 
 
 class PinnedPrefetcher:
-    """Double-buffered pinned-host → device pipeline."""
+    """Ring of ``depth`` pinned-host → device slots; the H2D copy of batch i+k overlaps the compute of batch i.
 
-    def __init__(self, dataset, batch_size: int, device: torch.device, depth: int = 2):
+    Contract: a batch returned by :meth:`next` stays valid until the following ``next()`` call *returns* (the trainer
+    enqueues every kernel that reads batch i before it asks for batch i+1).  Two hazards are fenced per slot:
+
+    * host side — the pinned buffer of a slot is rewritten on the CPU only after the previous H2D copy out of it has
+      finished (``copied[i].synchronize()``); otherwise a host that runs ahead of the GPU (CUDA graphs, log_interval > 1,
+      ``read_loss=False`` benches) would let the pending DMA read a newer or torn batch;
+    * device side — the copy into a device slot waits for the event recorded after the last consumer of that slot
+      (``consumed[i]``), not for everything enqueued on the compute stream, so prefetch really runs ahead.
+    """
+
+    def __init__(self, dataset, batch_size: int, device: torch.device, depth: int = 4):
         self.ds, self.bs, self.device = dataset, batch_size, device
         self.cuda = device.type == "cuda"
         S = dataset.seq_len
-        self.depth = depth
-        self.host = [torch.empty((2, batch_size, S), dtype=torch.int64, pin_memory=self.cuda) for _ in range(depth)]
+        self.depth = max(2, depth)
+        self.host = [torch.empty((2, batch_size, S), dtype=torch.int64, pin_memory=self.cuda) for _ in range(self.depth)]
         if self.cuda:
-            self.dev = [torch.empty((2, batch_size, S), dtype=torch.int64, device=device) for _ in range(depth)]
+            self.dev = [torch.empty((2, batch_size, S), dtype=torch.int64, device=device) for _ in range(self.depth)]
             self.stream = torch.cuda.Stream(device=device)
-            self.events = [torch.cuda.Event() for _ in range(depth)]
+            self.copied = [torch.cuda.Event() for _ in range(self.depth)]  # H2D out of host[i] / into dev[i] finished
+            self.consumed = [torch.cuda.Event() for _ in range(self.depth)]  # every kernel reading dev[i] was enqueued before this
+            self._copied_armed = [False] * self.depth
+            self._consumed_armed = [False] * self.depth
         self.slot = 0
+        self._handed: int | None = None  # slot currently owned by the consumer
         self.h2d_bytes_per_batch = 2 * batch_size * S * 8
+        self.host_waits = 0  # times the CPU had to wait for an in-flight DMA before reusing a pinned slot (diagnostic)
         self._inflight: list[int] = []
         self._states: list[dict] = []  # dataset state BEFORE each in-flight batch was drawn (checkpoint = oldest one)
-        for _ in range(depth - 1):
+        for _ in range(self.depth - 1):
             self._issue()
 
     def state_dict(self) -> dict:
@@ -120,21 +135,36 @@ class PinnedPrefetcher:
 
         self._states.append(copy.deepcopy(self.ds.state_dict()))
         x, y = self.ds.next_batch(self.bs)
+        if self.cuda and self._copied_armed[i]:
+            if not self.copied[i].query():
+                self.host_waits += 1
+            self.copied[i].synchronize()  # the DMA that last read host[i] is done: safe to rewrite it on the CPU
         self.host[i][0].copy_(torch.from_numpy(np.ascontiguousarray(x)))
         self.host[i][1].copy_(torch.from_numpy(np.ascontiguousarray(y)))
         if self.cuda:
-            # the previous consumer of this device slot must be done before we overwrite it
-            self.stream.wait_stream(torch.cuda.current_stream())
+            if self._consumed_armed[i]:
+                self.stream.wait_event(self.consumed[i])  # the last consumer of dev[i] is done before we overwrite it
             with torch.cuda.stream(self.stream):
                 self.dev[i].copy_(self.host[i], non_blocking=True)
-                self.events[i].record(self.stream)
+                self.copied[i].record(self.stream)
+            self._copied_armed[i] = True
         self._inflight.append(i)
         self.slot = (self.slot + 1) % self.depth
+
+    def _release_handed(self) -> None:
+        if self.cuda and self._handed is not None:
+            self.consumed[self._handed].record(torch.cuda.current_stream())
+            self._consumed_armed[self._handed] = True
+        self._handed = None
 
     def reset(self) -> None:
         """Drop prefetched batches (they were drawn before a dataset ``load_state_dict``) and refill the pipeline."""
         if self.cuda:
+            torch.cuda.current_stream().synchronize()
             self.stream.synchronize()
+            self._copied_armed = [False] * self.depth
+            self._consumed_armed = [False] * self.depth
+        self._handed = None
         self._inflight.clear()
         self._states.clear()
         self.slot = 0
@@ -142,12 +172,14 @@ class PinnedPrefetcher:
             self._issue()
 
     def next(self) -> Batch:
+        self._release_handed()  # the batch handed out last time has been fully enqueued by now
         self._issue()
         i = self._inflight.pop(0)
         self._states.pop(0)
         if self.cuda:
-            torch.cuda.current_stream().wait_event(self.events[i])
+            torch.cuda.current_stream().wait_event(self.copied[i])
             t = self.dev[i]
+            self._handed = i
         else:
             t = self.host[i].clone()
         return Batch(t[0], t[1])

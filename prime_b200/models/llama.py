@@ -206,7 +206,7 @@ class Transformer(nn.Module):
     def forward_hidden(self, tokens: torch.Tensor) -> torch.Tensor:
         B, S = tokens.shape
         cos, sin = self.rope_tables(S, tokens.device)
-        h = self.tok_embeddings(tokens)
+        h = ops.embedding(tokens, self.tok_embeddings.weight)
         delta = None
         ac = self.ac_ckpt if torch.is_grad_enabled() else False
         for i, layer in enumerate(self.layers):

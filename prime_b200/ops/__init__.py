@@ -6,6 +6,8 @@ from .functional import (  # noqa: F401
     attention,
     attention_qkv,
     cross_entropy,
+    embedding,
+    gemm_wgather,
     gemm,
     gemm_mxfp8,
     launch_count,

@@ -109,6 +109,22 @@ class AdamArgs(ctypes.Structure):
     _fields_ = [(k, ctypes.c_float) for k in ("lr", "beta1", "beta2", "eps", "weight_decay", "bc1", "bc2", "max_norm")]
 
 
+class SegTable(ctypes.Structure):
+    """Up to 16 (src offset, dst offset, length) pieces of a row-sharded bucket (csrc/comm.cu: grad_reduce_segs)."""
+
+    _fields_ = [("src_off", ctypes.c_int64 * 16), ("dst_off", ctypes.c_int64 * 16), ("n", ctypes.c_int64 * 16), ("nseg", ctypes.c_int)]
+
+    @classmethod
+    def of(cls, segs) -> "SegTable":
+        segs = list(segs)
+        assert len(segs) <= 16, "at most 16 row-sharded parameters per bucket"
+        t = cls()
+        for i, (src, dst, n) in enumerate(segs):
+            t.src_off[i], t.dst_off[i], t.n[i] = int(src), int(dst), int(n)
+        t.nseg = len(segs)
+        return t
+
+
 class OuterArgs(ctypes.Structure):
     _fields_ = [("lr", ctypes.c_float), ("momentum", ctypes.c_float), ("inv_workers", ctypes.c_float), ("nesterov", ctypes.c_int)]
 
@@ -154,8 +170,15 @@ def _declare(lib: ctypes.CDLL) -> None:
         "pb_norm_publish": [vp, i32, PP, PP, i32, i32, u32, vp],
         "pb_adamw_push": [vp, vp, vp, vp, i64, ctypes.POINTER(AdamArgs), vp, i32, vp, i32, u32, PP, i64, vp, vp, vp],
         "pb_pseudograd_quant": [vp, vp, vp, vp, i64, vp],
-        "pb_outer_nesterov": [PP, PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), PP, i64, vp],
-        "pb_outer_nesterov_f32": [PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), vp],
+        "pb_outer_nesterov": [PP, PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), PP, vp, vp, i32, vp],
+        "pb_outer_nesterov_f32": [PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), PP, vp, vp, i32, vp],
+        "pb_set_spin_timeout_ms": [ctypes.c_ulonglong],
+        "pb_grad_reduce_segs": [PP, ctypes.POINTER(SegTable), f32, vp, vp, vp, i32, u32, vp, i32, vp],
+        "pb_embedding_fwd": [vp, i64, PP, i32, i32, vp, vp],
+        "pb_embedding_bwd": [vp, i64, vp, vp, i32, vp, vp],
+        "pb_embedding_bwd_max_chunk": [],
+        "pb_allgather_copy": [PP, i64, vp, vp],
+        "pb_gemm_wgather": [vp, ctypes.POINTER(vp), i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp],
         "pb_cast_push": [vp, i64, PP, i64, vp],
         # NVLS: VMM allocations shared by fd, multicast objects, multimem kernels (csrc/multicast.cu)
         "pb_mc_supported": [i32],

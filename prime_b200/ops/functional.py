@@ -95,6 +95,83 @@ def set_gemm_split_k(mode: int) -> int:
     return int(_lib.load().pb_gemm_set_split_k(int(mode)))
 
 
+def _take_fresh(param: torch.Tensor) -> bool:
+    """True exactly once per optimizer step and parameter (the sharded engine arms ``_mg_fresh`` in ``zero_grad``): the first
+    gradient write of the step OVERWRITES main_grad, which is what lets the engine skip the 4·N-byte memset."""
+    if getattr(param, "_mg_fresh", False):
+        param._mg_fresh = False
+        return True
+    return False
+
+
+def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor) -> torch.Tensor | None:
+    """dW = dyᵀ·x: fused fp32 accumulation into ``weight.main_grad`` when the engine attached one, else a bf16 gradient."""
+    main_grad = getattr(weight, "main_grad", None)
+    if main_grad is not None:
+        gemm(dy2, x2, a_mn_major=True, b_mn_major=True, out=main_grad, accumulate=not _take_fresh(weight))
+        return None
+    return gemm(dy2, x2, a_mn_major=True, b_mn_major=True)
+
+
+def gemm_wgather(a: torch.Tensor, z, *, b_mn_major: bool = False, out: torch.Tensor | None = None, rope: tuple | None = None,
+                 swiglu_h: torch.Tensor | None = None) -> torch.Tensor:  # fmt: skip
+    """Parameter all-gather ⊕ GEMM (ZeRO-3): ``z`` is the ``RowShard`` of a weight W [rows, cols] sharded by rows over the FSDP group.
+
+    ``b_mn_major=False``: C[M, rows] = a[M, cols]·Wᵀ (forward; ``rope`` = RoPE epilogue, ``swiglu_h`` = SwiGLU epilogue with W = W13,
+    C = gate_up, ``swiglu_h`` = h).  ``b_mn_major=True``: C[M, cols] = a[M, rows]·W (input gradient).  The peers' row blocks are
+    pulled over NVLink by copier warps INSIDE the GEMM kernel (csrc/gemm_sm100.cu, IO = 3); nothing is gathered beforehand."""
+    import ctypes
+
+    assert a.dtype == torch.bfloat16 and a.dim() == 2 and a.stride(1) == 1
+    M = a.shape[0]
+    N = z.cols if b_mn_major else z.rows
+    assert a.shape[1] == (z.rows if b_mn_major else z.cols)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    lib = _lib.load()
+    epi = 2 if swiglu_h is not None else (1 if rope is not None else 0)
+    if M <= 128:
+        # tiny M (unit tests, debug models): explicit gather by peer loads, then the plain kernels
+        pp = _lib.PeerPtrs.of(z.peer_ptrs[i] for i in range(z.n))
+        _lib.check(lib.pb_allgather_copy(ctypes.byref(pp), z.rpr * z.cols * 2, z.full_ptr, _stream()), "pb_allgather_copy")
+        _count()
+        w = torch.as_tensor(_RawBuffer(z.full_ptr, z.rows * z.cols * 2), device=a.device).view(torch.bfloat16).view(z.rows, z.cols)
+        if epi == 2:
+            FF = z.rows // 2
+            gemm(a, w, out=out)
+            _lib.check(lib.pb_swiglu_fwd(out.data_ptr(), swiglu_h.data_ptr(), M, FF, _stream()), "pb_swiglu_fwd")
+            _count()
+        elif epi == 1:
+            cos, sin, seq_len, rot_cols, head_dim = rope
+            rc = lib.pb_gemm_bf16_rope(a.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, a.shape[1], a.stride(0), w.stride(0), out.stride(0), 0,
+                                       cos.data_ptr(), sin.data_ptr(), seq_len, rot_cols, head_dim, _stream())  # fmt: skip
+            _lib.check(rc, "pb_gemm_bf16_rope")
+            _count()
+        else:
+            gemm(a, w, b_mn_major=b_mn_major, out=out)
+        return out
+    cos = sin = None
+    seq_len, rot_cols, head_dim = 1, 0, 64
+    if rope is not None:
+        cos, sin, seq_len, rot_cols, head_dim = rope
+        assert cos.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous() and cos.shape[0] >= seq_len
+    rc = lib.pb_gemm_wgather(
+        a.data_ptr(), z.peer_ptrs, z.n, z.rank, z.full_ptr, z.flags.data_ptr(), out.data_ptr(), _ptr(swiglu_h), M, z.rows, z.cols,
+        a.stride(0), out.stride(0), swiglu_h.stride(0) if swiglu_h is not None else 0, int(b_mn_major), epi,
+        _ptr(cos), _ptr(sin), seq_len, rot_cols, head_dim, _stream(),
+    )  # fmt: skip
+    _lib.check(rc, "pb_gemm_wgather")
+    _count(2)
+    return out
+
+
+class _RawBuffer:
+    """Raw device pointer → torch (zero copy) through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x Wᵀ.  Weight gradient accumulates straight into ``weight.main_grad`` (fp32, fused in the GEMM
     epilogue) when the FSDP engine has attached one; otherwise a bf16 gradient is returned."""
@@ -108,7 +185,10 @@ class _LinearFn(torch.autograd.Function):
         ctx.x_shape = x.shape
         # allocate with the final shape: a Function output must not be a view (RoPE / the loss rotate / overwrite it in place)
         y = torch.empty((*x.shape[:-1], weight.shape[0]), dtype=x.dtype, device=x.device)
-        if rope is None:
+        z = getattr(weight, "z3", None)
+        if z is not None:  # ZeRO-3: the weight is gathered from the peers' shards inside the GEMM
+            gemm_wgather(x2, z, out=y.view(-1, weight.shape[0]), rope=rope)
+        elif rope is None:
             gemm(x2, weight, out=y.view(-1, weight.shape[0]))
         else:
             # fused QKV projection: the GEMM epilogue rotates the Q/K head columns while the tile is in registers. The consumer
@@ -132,14 +212,13 @@ class _LinearFn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(ctx.x_shape, dtype=dy.dtype, device=dy.device)
-            gemm(dy2, weight, b_mn_major=True, out=dx.view(-1, ctx.x_shape[-1]))
-        if ctx.needs_input_grad[1]:
-            main_grad = getattr(weight, "main_grad", None)
-            if main_grad is not None:
-                gemm(dy2, x2, a_mn_major=True, b_mn_major=True, out=main_grad, accumulate=True)
-                dw = None
+            z = getattr(weight, "z3", None)
+            if z is not None:
+                gemm_wgather(dy2, z, b_mn_major=True, out=dx.view(-1, ctx.x_shape[-1]))
             else:
-                dw = gemm(dy2, x2, a_mn_major=True, b_mn_major=True)
+                gemm(dy2, weight, b_mn_major=True, out=dx.view(-1, ctx.x_shape[-1]))
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dy2, x2, weight)
         return dx, dw, None
 
 
@@ -236,12 +315,8 @@ class _LinearMXFP8Fn(torch.autograd.Function):
             dx = torch.empty(ctx.x_shape, dtype=dy.dtype, device=dy.device)
             gemm_mxfp8(dyq, dysf, wtq, wtsf, out=dx.view(-1, ctx.x_shape[-1]))
         if ctx.needs_input_grad[1]:
-            main_grad = getattr(weight, "main_grad", None)
             if x2.is_cuda:
-                if main_grad is not None:
-                    gemm(dy2, x2, a_mn_major=True, b_mn_major=True, out=main_grad, accumulate=True)
-                else:
-                    dw = gemm(dy2, x2, a_mn_major=True, b_mn_major=True)
+                dw = _wgrad(dy2, x2, weight)
             else:
                 dw = (dy2.float().t() @ x2.float()).to(weight.dtype)
         return dx, dw
@@ -277,6 +352,65 @@ def linear_qkv_rope(x: torch.Tensor, weight: torch.Tensor, cos: torch.Tensor, si
     Must be consumed by ``rope_attention_qkv(..., pre_rotated=True)``, whose backward undoes the rotation in its own epilogues."""
     head_dim = weight.shape[0] // (n_heads + 2 * n_kv_heads)
     return _LinearFn.apply(x, weight, (cos, sin, x.shape[1], (n_heads + n_kv_heads) * head_dim, head_dim))
+
+
+# --------------------------------------------------------------------------- embedding
+
+
+class _EmbeddingFn(torch.autograd.Function):
+    """Row gather out of the parameter (ZeRO-3: out of the peers' shards over NVLink) and a deterministic, sort-based scatter-add of
+    the gradient into the fp32 ``main_grad`` (csrc/embedding.cu) — no torch indexing / radix-sort / atomics kernels."""
+
+    @staticmethod
+    def forward(ctx, tokens: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        import ctypes
+
+        lib = _lib.load()
+        V, dim = weight.shape
+        t = tokens.reshape(-1)
+        t = t if t.is_contiguous() else t.contiguous()
+        assert t.dtype == torch.int64
+        z = getattr(weight, "z3", None)
+        if z is not None:
+            pp, rpr = _lib.PeerPtrs.of(z.peer_ptrs[i] for i in range(z.n)), z.rpr
+        else:
+            assert weight.is_contiguous()
+            pp, rpr = _lib.PeerPtrs.of([weight.data_ptr()]), V
+        out = torch.empty((*tokens.shape, dim), dtype=weight.dtype, device=weight.device)
+        _lib.check(lib.pb_embedding_fwd(t.data_ptr(), t.numel(), ctypes.byref(pp), rpr, dim, out.data_ptr(), _stream()), "pb_embedding_fwd")
+        _count()
+        ctx.save_for_backward(t)
+        ctx.weight = weight
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: torch.Tensor):
+        lib = _lib.load()
+        (t,) = ctx.saved_tensors
+        weight = ctx.weight
+        V, dim = weight.shape
+        d2 = dout.reshape(-1, dim)
+        d2 = d2 if d2.is_contiguous() else d2.contiguous()
+        main_grad = getattr(weight, "main_grad", None)
+        if main_grad is not None:
+            if _take_fresh(weight):
+                main_grad.zero_()
+            grad, ret = main_grad, None
+        else:
+            grad = torch.zeros((V, dim), dtype=torch.float32, device=dout.device)
+            ret = grad
+        scratch = torch.empty(min(t.numel(), lib.pb_embedding_bwd_max_chunk()), dtype=torch.int64, device=dout.device)
+        _lib.check(lib.pb_embedding_bwd(t.data_ptr(), t.numel(), d2.data_ptr(), grad.data_ptr(), dim, scratch.data_ptr(), _stream()),
+                   "pb_embedding_bwd")  # fmt: skip
+        _count(2 * ((t.numel() + 16383) // 16384))
+        return None, (None if ret is None else ret.to(weight.dtype))
+
+
+def embedding(tokens: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``weight[tokens]`` for a bf16 [V, dim] table (dim % 8 == 0)."""
+    if weight.is_cuda and weight.dtype == torch.bfloat16 and weight.shape[1] % 8 == 0:
+        return _EmbeddingFn.apply(tokens, weight)
+    return torch.nn.functional.embedding(tokens, weight)
 
 
 # --------------------------------------------------------------------------- RMSNorm
@@ -329,7 +463,7 @@ class _RMSNormFn(torch.autograd.Function):
         partial = torch.empty((grid, D), dtype=torch.float32, device=h.device)
         main_grad = getattr(weight, "main_grad", None)
         if main_grad is not None:
-            dw32, acc = main_grad, 1
+            dw32, acc = main_grad, 0 if _take_fresh(weight) else 1
         else:
             dw32, acc = torch.empty(D, dtype=torch.float32, device=h.device), 0
         rc = lib.pb_rmsnorm_bwd(_ptr(dy2), _ptr(h), _ptr(weight), _ptr(rstd), _ptr(dres), _ptr(dx), _ptr(partial),
@@ -455,10 +589,14 @@ class _LinearSwiGLUFn(torch.autograd.Function):
         FF = w13.shape[0] // 2
         gate_up = torch.empty((M, 2 * FF), dtype=x.dtype, device=x.device)
         h = torch.empty((*x.shape[:-1], FF), dtype=x.dtype, device=x.device)
-        rc = lib.pb_gemm_bf16_swiglu(x2.data_ptr(), w13.data_ptr(), gate_up.data_ptr(), h.data_ptr(), M, FF, K, x2.stride(0), w13.stride(0),
-                                     2 * FF, FF, _stream())  # fmt: skip
-        _lib.check(rc, "pb_gemm_bf16_swiglu")
-        _count()
+        z = getattr(w13, "z3", None)
+        if z is not None:
+            gemm_wgather(x2, z, out=gate_up, swiglu_h=h.view(M, FF))
+        else:
+            rc = lib.pb_gemm_bf16_swiglu(x2.data_ptr(), w13.data_ptr(), gate_up.data_ptr(), h.data_ptr(), M, FF, K, x2.stride(0), w13.stride(0),
+                                         2 * FF, FF, _stream())  # fmt: skip
+            _lib.check(rc, "pb_gemm_bf16_swiglu")
+            _count()
         ctx.save_for_backward(x2, w13, gate_up)
         ctx.x_shape = x.shape
         return h
@@ -477,13 +615,13 @@ class _LinearSwiGLUFn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(ctx.x_shape, dtype=dh.dtype, device=dh.device)
-            gemm(dgu, w13, b_mn_major=True, out=dx.view(-1, ctx.x_shape[-1]))
-        if ctx.needs_input_grad[1]:
-            main_grad = getattr(w13, "main_grad", None)
-            if main_grad is not None:
-                gemm(dgu, x2, a_mn_major=True, b_mn_major=True, out=main_grad, accumulate=True)
+            z = getattr(w13, "z3", None)
+            if z is not None:
+                gemm_wgather(dgu, z, b_mn_major=True, out=dx.view(-1, ctx.x_shape[-1]))
             else:
-                dw = gemm(dgu, x2, a_mn_major=True, b_mn_major=True)
+                gemm(dgu, w13, b_mn_major=True, out=dx.view(-1, ctx.x_shape[-1]))
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dgu, x2, w13)
         return dx, dw
 
 

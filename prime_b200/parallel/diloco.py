@@ -63,18 +63,32 @@ class DilocoOuter:
         self.momentum = torch.zeros(n, dtype=torch.float32, device=dev)
         self.outer_step_count = 0
         self.last_bytes_on_wire = 0
-        self.last_seconds = 0.0
-        # ``collective=True``: elastic jobs — workers are separate process worlds, so the exchange goes through a
-        # (re-creatable) process group instead of the symmetric heap, which cannot span independently launched workers
+        self.last_seconds = 0.0  # host wall clock of the last step() call (enqueue time on CUDA: use device_seconds())
+        self._ev: tuple | None = None
+        self.total_device_ms = 0.0
+        self.timed_steps = 0
+        # ``collective=True``: the exchange goes through a (re-creatable) process group instead of the symmetric heap
         self.fused = engine.backend == "fused" and not collective
         if self.fused:
             heap = engine.heap
-            self.q = heap.alloc(n, torch.int8)
-            self.scales = heap.alloc(n // SHARD_ALIGN, torch.float32)
             world = heap.world_size
             self.slot_bar = heap.alloc_flags(world)
             self.slot_bar2 = heap.alloc_flags(world)
             self._epoch = 0
+            if hyper.compression == "int8":
+                self.q = heap.alloc(n, torch.int8)
+                self.scales = heap.alloc(n // SHARD_ALIGN, torch.float32)
+            else:
+                if not engine.master_in_heap:
+                    raise ValueError("fused fp32 outer step needs the inner masters in the symmetric heap (ShardedEngine(master_in_heap=True))")
+                self.theta_new = torch.empty(n, dtype=torch.float32, device=dev)
+            # shard index → position in the bf16 parameter buffer, one entry per bucket (see BucketTable in csrc/comm.cu); one
+            # launch per destination set (replicated engine: one; ZeRO-3: local shard buffer + the small replicated bucket)
+            self._ranges = []
+            for lo, hi, dst, starts, dsts in engine.outer_ranges():
+                self._ranges.append((lo, hi, dst, torch.tensor(starts, dtype=torch.int64, device=dev),
+                                     torch.tensor(dsts, dtype=torch.int64, device=dev)))  # fmt: skip
+            self._ev_pool = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2)]
 
     @property
     def num_workers(self) -> int:
@@ -88,12 +102,45 @@ class DilocoOuter:
     @torch.no_grad()
     def step(self) -> None:
         t0 = time.perf_counter()
+        cuda = self.engine.device.type == "cuda"
+        if cuda:
+            if self.fused:
+                ev = self._ev_pool[self.outer_step_count % 2]
+            else:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self._harvest()
+            ev[0].record()
         if self.fused:
             self._step_fused()
         else:
             self._step_collective()
+        if cuda:
+            ev[1].record()
+            self._ev = ev
         self.outer_step_count += 1
         self.last_seconds = time.perf_counter() - t0
+
+    def _harvest(self) -> None:
+        if self._ev is not None:
+            self._ev[1].synchronize()
+            self.total_device_ms += self._ev[0].elapsed_time(self._ev[1])
+            self.timed_steps += 1
+            self._ev = None
+
+    def device_seconds(self) -> float:
+        """Device time (CUDA events on the launching stream) of the most recent outer step; synchronises on its end event."""
+        if self._ev is None:
+            return self.last_seconds
+        self._ev[1].synchronize()
+        return self._ev[0].elapsed_time(self._ev[1]) / 1e3
+
+    def reset_timing(self) -> None:
+        self._harvest()
+        self.total_device_ms, self.timed_steps = 0.0, 0
+
+    def mean_device_seconds(self) -> float:
+        self._harvest()
+        return self.total_device_ms / 1e3 / max(1, self.timed_steps)
 
     def _step_fused(self) -> None:
         eng, heap, lib = self.engine, self.engine.heap, self.engine.lib
@@ -101,33 +148,42 @@ class DilocoOuter:
         n = eng.shard_total
         W = self.num_workers
         all_ranks = list(range(heap.world_size))
+        args = _lib.OuterArgs(self.hyper.lr, self.hyper.momentum, 1.0 / W, int(self.hyper.nesterov))
         if self.hyper.compression == "int8":
             _lib.check(lib.pb_pseudograd_quant(self.theta0.data_ptr(), eng.master.data_ptr(), self.q.data_ptr(),
                                                self.scales.data_ptr(), n, s), "pb_pseudograd_quant")  # fmt: skip
             self._epoch += 1
             heap.barrier(all_ranks, self.slot_bar, self._epoch, s)  # everyone's payload is published
-            args = _lib.OuterArgs(self.hyper.lr, self.hyper.momentum, 1.0 / W, int(self.hyper.nesterov))
-            dst = heap.peers(self.mesh.fsdp_ranks, eng.param_flat)
-            r = self.mesh.fsdp_rank
-            for b in eng.buckets:
-                lo = b.shard_start
+            for lo, hi, dst, tab_s, tab_d in self._ranges:
                 qs = _lib.PeerPtrs.of(heap.peer_ptr(w, self.q) + lo for w in self.ranks)
                 ss = _lib.PeerPtrs.of(heap.peer_ptr(w, self.scales) + (lo // SHARD_ALIGN) * 4 for w in self.ranks)
                 _lib.check(
-                    lib.pb_outer_nesterov(ctypes.byref(qs), ctypes.byref(ss), self.theta0[lo:].data_ptr(),
-                                          self.momentum[lo:].data_ptr(), eng.master[lo:].data_ptr(), b.shard_size,
-                                          ctypes.byref(args), ctypes.byref(dst), b.start + r * b.shard_size, s),
+                    lib.pb_outer_nesterov(ctypes.byref(qs), ctypes.byref(ss), self.theta0[lo:].data_ptr(), self.momentum[lo:].data_ptr(),
+                                          eng.master[lo:].data_ptr(), hi - lo, ctypes.byref(args), ctypes.byref(dst), tab_s.data_ptr(),
+                                          tab_d.data_ptr(), tab_d.numel(), s),
                     "pb_outer_nesterov",
                 )  # fmt: skip
             self._epoch += 1
             heap.barrier(all_ranks, self.slot_bar2, self._epoch, s)  # payloads consumed, params landed
             self.last_bytes_on_wire = (W - 1) * (n + 4 * (n // SHARD_ALIGN))
-            _count(3 + len(eng.buckets))
+            _count(3 + len(self._ranges))
         else:
+            # uncompressed: every worker reads the peers' fp32 inner masters straight out of the heap
             self._epoch += 1
-            heap.barrier(all_ranks, self.slot_bar, self._epoch, s)
-            # uncompressed: peers read each other's fp32 inner masters directly (they must live in the heap)
-            raise NotImplementedError("fused fp32 outer path requires heap-resident masters; use compression='int8'")
+            heap.barrier(all_ranks, self.slot_bar, self._epoch, s)  # every worker finished its inner steps
+            for lo, hi, dst, tab_s, tab_d in self._ranges:
+                ths = _lib.PeerPtrs.of(heap.peer_ptr(w, eng.master) + lo * 4 for w in self.ranks)
+                _lib.check(
+                    lib.pb_outer_nesterov_f32(ctypes.byref(ths), self.theta0[lo:].data_ptr(), self.momentum[lo:].data_ptr(),
+                                              self.theta_new[lo:].data_ptr(), hi - lo, ctypes.byref(args), ctypes.byref(dst),
+                                              tab_s.data_ptr(), tab_d.data_ptr(), tab_d.numel(), s),
+                    "pb_outer_nesterov_f32",
+                )  # fmt: skip
+            self._epoch += 1
+            heap.barrier(all_ranks, self.slot_bar2, self._epoch, s)  # nobody reads the old masters any more
+            eng.master.copy_(self.theta_new)
+            self.last_bytes_on_wire = (W - 1) * 4 * n
+            _count(3 + len(self._ranges))
 
     def _step_collective(self) -> None:
         eng, h = self.engine, self.hyper

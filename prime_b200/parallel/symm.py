@@ -109,8 +109,28 @@ class SymmetricHeap:
         )
 
     def check_errors(self) -> None:
-        if int(self.err[0].item()) != 0:
-            raise RuntimeError("device-side peer wait timed out (a rank stalled or died)")
+        """Raise if any device-side wait gave up (synchronises with the device). The comm kernels skip their stores when a wait
+        fails, so the optimizer state is untouched but the step is void: callers must not continue or checkpoint past this."""
+        code = int(self.err[0].item())
+        if code != 0:
+            why = {1: "timed out", 2: "was aborted by the host watchdog"}.get(code, f"failed (code {code})")
+            raise RuntimeError(f"device-side peer wait {why} on rank {self.rank}: a rank of the NVLink group stalled or died")
+
+    def clear_errors(self) -> None:
+        self.err.zero_()
+
+    def abort(self) -> None:
+        """Host watchdog hook: make every device-side spin of this rank return immediately (a peer is known to be dead).
+        Written from a side stream so it overtakes the spinning kernel."""
+        if not hasattr(self, "_abort_stream"):
+            self._abort_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self._abort_word = torch.full((1,), 2, dtype=torch.int32, device=self.device)
+        with torch.cuda.stream(self._abort_stream):
+            self.err[:1].copy_(self._abort_word, non_blocking=True)
+
+    def set_spin_timeout(self, seconds: float) -> None:
+        """Bound of every device-side flag wait (default 20 s). Elastic jobs lower it to a heartbeat period."""
+        _lib.check(self.lib.pb_set_spin_timeout_ms(int(max(1.0, seconds * 1e3))), "pb_set_spin_timeout_ms")
 
     def close(self) -> None:
         for r, p in enumerate(self.peer_base):

@@ -43,6 +43,34 @@ class _StopFlag:
                 pass
 
 
+class _StopConsensus:
+    """All ranks of a process world leave the loop at the SAME step: a signal sent to the whole process group reaches the ranks
+    on different sides of a step boundary, and a rank that entered ``ckpt.save()`` (a barrier) while a peer started another
+    ``inner_step`` (flag waits / collectives) would hang. One MAX all-reduce of a single int over a gloo side group — host
+    memory only, no device sync — per step; single-rank worlds skip it."""
+
+    def __init__(self, stop: _StopFlag):
+        self.stop = stop
+        self.group = None
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            try:
+                self.group = dist.new_group(backend="gloo")
+            except Exception:  # noqa: BLE001 — no gloo in this build: fall back to the default group
+                self.group = dist.group.WORLD
+
+    def __call__(self) -> bool:
+        mine = 1 if self.stop.set_by is not None else 0
+        if self.group is None:
+            return bool(mine)
+        dev = "cpu" if dist.get_backend(self.group) == "gloo" else torch.device("cuda", torch.cuda.current_device())
+        t = torch.tensor([mine], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        agreed = bool(int(t.item()))
+        if agreed and self.stop.set_by is None:
+            self.stop.set_by = "peer"
+        return agreed
+
+
 def _elastic_setup(cfg: Config, trainer: Trainer, log) -> Any:
     from .parallel.elastic import ElasticConfig, ElasticContext, display_name
 
@@ -146,14 +174,16 @@ def train(cfg: Config, *, max_steps: int | None = None) -> dict[str, Any]:
     step_delay = float(__import__("os").environ.get("PRIME_B200_STEP_DELAY_S", "0"))  # fault-injection aid for the elastic tests
     last: dict[str, Any] = {}
     cuda = mesh.device.type == "cuda"
+    should_stop = _StopConsensus(stop)
     try:
-        while trainer.step_count < total and stop.set_by is None:
+        while trainer.step_count < total and not should_stop():
             r = trainer.inner_step()
             step = trainer.step_count
             if step_delay:
                 time.sleep(step_delay)
             if step % cfg.monitor.log_interval == 0 or r.did_outer or step == total:
                 loss = float(r.loss)  # the only device→host sync of the step
+                trainer.check_health()  # a device-side peer wait timed out → raise here instead of training on a void step
                 dt = timer.lap()
                 # tokens of this worker-world only: MFU is per-GPU of THIS process world; global tok/s is scaled by membership
                 meter.update(trainer.tokens_per_step * cfg.monitor.log_interval, dt)
@@ -174,7 +204,10 @@ def train(cfg: Config, *, max_steps: int | None = None) -> dict[str, Any]:
                              f" | outer {last['outer_s'] * 1e3:.1f} ms, {last['outer_bytes'] / 2**20:.1f} MiB on the wire" if r.did_outer else "")  # fmt: skip
                     jsonl.write({"time": time.time(), **last})
                     prom.write(last)
+            if ckpt is not None:
+                ckpt.poll()  # publish an asynchronously written checkpoint as soon as every rank's shard is on disk
             if ckpt is not None and cfg.ckpt.interval and step % cfg.ckpt.interval == 0:
+                trainer.check_health()
                 tensors, extra = trainer_state(trainer)
                 ckpt.save(step, tensors, extra, meta)
                 if leader:
@@ -184,6 +217,7 @@ def train(cfg: Config, *, max_steps: int | None = None) -> dict[str, Any]:
         if ckpt is not None and (stop.set_by is not None or (cfg.ckpt.interval and trainer.step_count % cfg.ckpt.interval != 0)):
             # synchronised final checkpoint so a restart resumes exactly here (only at an outer boundary is it DiLoCo-consistent;
             # mid-H checkpoints still restore this worker's own inner state exactly)
+            trainer.check_health()
             tensors, extra = trainer_state(trainer)
             ckpt.save(trainer.step_count, tensors, extra, meta)
     finally:

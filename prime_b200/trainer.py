@@ -54,24 +54,30 @@ class Trainer:
         self.model.attn_impl = cfg.train.attn_impl
         self.model.ac_ckpt = cfg.train.ac_ckpt
         self.model.set_fp8(cfg.train.fp8)  # MXFP8 forward / dgrad GEMMs (opt-in; the headline benchmark is bf16)
-        # options kept for config compatibility whose mechanism this engine does not need (or does not have yet): say so once
-        if mesh.world.rank == 0:
-            import warnings
-
-            if cfg.train.reshard_after_forward:
-                warnings.warn("train.reshard_after_forward is ignored: bf16 parameters stay resident (180 GB HBM); see DESIGN.md §1.1")
-            if cfg.optim.clip_mode == "delayed":
-                warnings.warn("optim.clip_mode='delayed' behaves like 'exact': the fused norm all-reduce is already off the critical path")
-
         self.heap = None
         use_fused = cuda and cfg.train.fused_comm
+        n_params = sum(p.numel() for p in self.model.parameters())
+        reshard = cfg.train.reshard_after_forward
+        if reshard is None:
+            reshard = n_params >= 5e9
+        shard_params = bool(reshard) and use_fused and mesh.fsdp_size > 1
+        if cfg.train.reshard_after_forward and not shard_params:
+            raise ValueError("train.reshard_after_forward=true needs CUDA, train.fused_comm=true and mesh.fsdp_size > 1 "
+                             "(the parameter gather runs inside the GEMM kernels over the symmetric NVLink heap)")  # fmt: skip
+        if shard_params and cfg.train.fp8:
+            raise ValueError("train.fp8 and train.reshard_after_forward cannot be combined yet (the MXFP8 GEMM has no gather variant)")
+        fp32_outer = cfg.diloco is not None and cfg.diloco.compression == "no" and use_fused and not cfg.mesh.elastic
         if use_fused:
             from .parallel.symm import SymmetricHeap, dist_exchange
 
-            n = sum(p.numel() for p in self.model.parameters())
-            pad = (len(list(self.model.parameters())) + 64) * 8 + (self.model.args.n_layers + 3) * mesh.fsdp_size * 1024
-            total = n + pad
-            nbytes = total * 6 + (total // mesh.fsdp_size) * 2 + (64 << 20)
+            F = mesh.fsdp_size
+            pad = (len(list(self.model.parameters())) + 64) * 8 + (self.model.args.n_layers + 4) * F * 1024
+            total = n_params + pad
+            per_shard = total // F + (self.model.args.n_layers + 4) * 1024
+            # fp32 main_grad (+ bf16 params when replicated, + the bf16 shard under ZeRO-3) + int8 outer payload and scales
+            nbytes = total * 4 + (per_shard * 2 if shard_params else total * 2) + per_shard * 2 + (64 << 20)
+            if fp32_outer:
+                nbytes += per_shard * 4
             heap_cls = SymmetricHeap
             if _want_nvls() and mesh.world.world_size > 1:
                 from .parallel.multicast import MulticastHeap, nvls_available
@@ -84,7 +90,8 @@ class Trainer:
         o = cfg.optim
         hyper = AdamHyper(o.optim.lr, o.optim.betas1, o.optim.betas2, o.optim.eps, o.optim.weight_decay,
                           o.max_norm if o.clip_mode != "none" else 0.0)  # fmt: skip
-        self.engine = ShardedEngine(self.model, mesh, hyper, backend="fused" if use_fused else "collective", heap=self.heap)
+        self.engine = ShardedEngine(self.model, mesh, hyper, backend="fused" if use_fused else "collective", heap=self.heap,
+                                    shard_params=shard_params, master_in_heap=fp32_outer, fresh_grads=not cfg.train.cuda_graphs)  # fmt: skip
         self.outer: DilocoOuter | None = None
         if cfg.diloco is not None:
             d = cfg.diloco
@@ -159,6 +166,8 @@ class Trainer:
 
     def inner_step(self, batches: list[Batch] | None = None) -> StepResult:
         eng = self.engine
+        if eng.trace is not None:
+            eng.trace.begin_step()
         eng.zero_grad()
         self._loss_acc.zero_()
         for i in range(self.accum):
@@ -194,6 +203,12 @@ class Trainer:
         return StepResult(self._loss_acc / self.accum, lr, eng.last_grad_norm, tokens, did_outer)
 
     # ------------------------------------------------------------------ helpers
+    def check_health(self) -> None:
+        """Raise if a device-side peer wait timed out (a rank stalled or died): the kernels then skipped their stores, so the
+        step is void and nothing may be checkpointed. Synchronises; call it where the loop already does (log / outer / ckpt)."""
+        if self.heap is not None:
+            self.heap.check_errors()
+
     def flops_per_step(self) -> float:
         return self.model.flops_per_token(self.cfg.data.seq_length) * self.tokens_per_step
 

@@ -51,3 +51,33 @@ def test_prefetcher_state_is_the_consumer_position():
     pf2.load_state_dict(sd)
     got = [pf2.next().input_ids.clone() for _ in range(3)]
     assert all(torch.equal(a, b) for a, b in zip(expect, got)) and not torch.equal(first.input_ids, expect[0])
+
+
+import pytest
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth", [2, 4])
+def test_prefetcher_no_host_dma_race_when_host_runs_ahead(depth):
+    """The CPU enqueues many batches while the GPU is still busy with a long kernel (what CUDA graphs / log_interval > 1 do):
+    every batch the device sees must be exactly the dataset's next batch, inputs and labels of the same draw."""
+    dev = torch.device("cuda", 0)
+    V, S, B, N = 30000, 512, 8, 24
+    pf = PinnedPrefetcher(FakeTokenDataset(V, S, seed=5), B, dev, depth=depth)
+    oracle = FakeTokenDataset(V, S, seed=5)
+    sums_x = torch.zeros(N, dtype=torch.int64, device=dev)
+    sums_y = torch.zeros(N, dtype=torch.int64, device=dev)
+    first_x = torch.zeros(N, dtype=torch.int64, device=dev)
+    a = torch.randn(8192, 8192, device=dev, dtype=torch.bfloat16)
+    for i in range(N):
+        if i % 3 == 0:  # keep the GPU far behind the host
+            for _ in range(6):
+                a = (a @ a).clamp_(-1, 1)
+        b = pf.next()
+        sums_x[i] = b.input_ids.sum()
+        sums_y[i] = b.labels.sum()
+        first_x[i] = b.input_ids[0, 0]
+    torch.cuda.synchronize()
+    for i in range(N):
+        x, y = oracle.next_batch(B)
+        assert int(sums_x[i]) == int(x.sum()) and int(sums_y[i]) == int(y.sum()) and int(first_x[i]) == int(x[0, 0]), f"batch {i} torn"

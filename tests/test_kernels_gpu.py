@@ -551,3 +551,130 @@ def test_model_fp8_mode_tracks_bf16_loss():
         grads[fp8] = model.layers[0].feed_forward.w2.grad.float().clone()
     assert abs(losses[True] - losses[False]) < 0.02 * abs(losses[False]), losses
     assert _rel_err(grads[True], grads[False]) < 0.15
+
+
+# ------------------------------------------------------------------ round 2: embedding, fp32 outer step, per-element bounds
+def _max_rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max |a-b| / (|b| + 5 % of max|b|): a wrong row / tile shows up here even when the Frobenius ratio stays small."""
+    a, b = a.float(), b.float()
+    return float(((a - b).abs() / (b.abs() + 0.05 * b.abs().max())).max())
+
+
+@pytest.mark.parametrize("T,V,D", [(4096, 32000, 2048), (20000, 2048, 256), (130, 1000, 1024)])
+def test_embedding_fwd_bwd_deterministic(T, V, D):
+    from prime_b200 import ops
+
+    dev = _dev()
+    torch.manual_seed(T)
+    W = torch.randn(V, D, device=dev, dtype=torch.bfloat16)
+    tok = torch.randint(0, V, (T,), device=dev)
+    tok[: T // 4] = tok[0]  # a heavily repeated token: one long run after the sort
+    W.main_grad = torch.zeros(V, D, device=dev, dtype=torch.float32)
+    Wp = torch.nn.Parameter(W)
+    Wp.main_grad = W.main_grad
+    out = ops.embedding(tok.view(1, T), Wp)
+    assert torch.equal(out[0], W[tok])
+    dout = torch.randn(1, T, D, device=dev, dtype=torch.bfloat16)
+    out.backward(dout)
+    ref = torch.zeros(V, D, device=dev, dtype=torch.float32).index_add_(0, tok, dout[0].float())
+    assert _rel_err(Wp.main_grad, ref) < 1e-5 and _max_rel(Wp.main_grad, ref) < 1e-3
+    first = Wp.main_grad.clone()
+    Wp.main_grad.zero_()
+    ops.embedding(tok.view(1, T), Wp).backward(dout)
+    assert torch.equal(first, Wp.main_grad)  # bitwise reproducible (sorted, one owner per row, no atomics)
+
+
+def test_outer_step_fused_fp32_matches_reference():
+    from prime_b200.models.llama import build_model
+    from prime_b200.ops import reference as R
+    from prime_b200.parallel.diloco import DilocoOuter, OuterHyper
+    from prime_b200.parallel.fsdp import AdamHyper, ShardedEngine
+    from prime_b200.parallel.mesh import WorldInfo, build_mesh
+    from prime_b200.parallel.symm import SymmetricHeap
+
+    dev = _dev()
+    m = build_model("debugmodel", device=dev, dtype=torch.bfloat16, seed=4)
+    mesh = build_mesh(WorldInfo(), device=dev)
+    heap = SymmetricHeap(256 << 20, 0, 1, lambda h: [h], dev)
+    eng = ShardedEngine(m, mesh, AdamHyper(), backend="fused", heap=heap, master_in_heap=True)
+    outer = DilocoOuter(eng, OuterHyper(lr=0.7, momentum=0.9, nesterov=True, compression="no"))
+    theta0 = outer.theta0.clone()
+    eng.master.add_(torch.randn_like(eng.master) * 1e-3)
+    pseudo = theta0 - eng.master
+    mom = torch.zeros_like(theta0)
+    R.nesterov_outer_step(theta0, pseudo, mom, lr=0.7, momentum=0.9, nesterov=True)
+    outer.step()
+    torch.cuda.synchronize()
+    heap.check_errors()
+    torch.testing.assert_close(outer.theta0, theta0, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(eng.master, theta0, rtol=1e-5, atol=1e-7)
+    b = eng.buckets[1]
+    got = eng.param_flat[b.pstart : b.pstart + b.shard_size].float()
+    torch.testing.assert_close(got, theta0[b.shard_start : b.shard_start + b.shard_size].to(torch.bfloat16).float())
+    assert outer.device_seconds() > 0
+    heap.close()
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(512, 768, 1024, False, False), (384, 1000, 136, False, True), (640, 264, 2048, True, True)])
+def test_gemm_per_element_bound(M, N, K, a_mn, b_mn):
+    """Per-element check next to the norm checks above (a wrong row or tile passes a Frobenius-ratio test)."""
+    from prime_b200 import ops
+
+    torch.manual_seed(M * 3 + N)
+    A = torch.randn(M, K, device=_dev(), dtype=torch.bfloat16)
+    B = torch.randn(N, K, device=_dev(), dtype=torch.bfloat16)
+    ref = A.float() @ B.float().t()
+    out = ops.gemm(A.t().contiguous() if a_mn else A, B.t().contiguous() if b_mn else B, a_mn_major=a_mn, b_mn_major=b_mn)
+    # bf16 output rounding is 2^-9 relative; the bound is per element, relative to |ref| + 5 % of the largest magnitude
+    assert _max_rel(out, ref) < 1.5e-2
+    out32 = torch.zeros(M, N, device=_dev(), dtype=torch.float32)
+    ops.gemm(A.t().contiguous() if a_mn else A, B.t().contiguous() if b_mn else B, a_mn_major=a_mn, b_mn_major=b_mn, out=out32)
+    assert _max_rel(out32, ref) < 1e-4
+
+
+@pytest.mark.parametrize("causal", [True, False])
+def test_flash_attention_per_element_bound(causal):
+    from prime_b200 import ops
+    from prime_b200.ops import reference as R
+
+    dev = _dev()
+    B, S, H, D = 2, 512, 4, 128
+    torch.manual_seed(11)
+    qkv = (torch.randn(B, S, 3 * H * D, device=dev) * 0.7).to(torch.bfloat16).requires_grad_(True)
+    out = ops.attention_qkv(qkv, H, H, causal=causal, impl="native")
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    x = qkv.detach().float().view(B, S, 3 * H, D).requires_grad_(True)
+    ref = R.attention(x[:, :, :H], x[:, :, H : 2 * H], x[:, :, 2 * H :], causal).reshape(B, S, H * D)
+    ref.backward(dout.float())
+    assert _max_rel(out, ref) < 3e-2
+    assert _max_rel(qkv.grad, x.grad.view(B, S, -1)) < 4e-2
+
+
+def test_fresh_grad_mode_matches_memset_mode():
+    """zero_grad without the 4·N-byte memset (first wgrad of a step overwrites) must give the same gradients."""
+    import copy
+
+    from prime_b200.models.llama import build_model
+    from prime_b200.parallel.fsdp import AdamHyper, ShardedEngine
+    from prime_b200.parallel.mesh import WorldInfo, build_mesh
+
+    dev = _dev()
+    m1 = build_model("debugmodel", device=dev, dtype=torch.bfloat16, seed=9)
+    m2 = copy.deepcopy(m1)
+    mesh = build_mesh(WorldInfo(), device=dev)
+    e1 = ShardedEngine(m1, mesh, AdamHyper(), backend="collective", fresh_grads=True)
+    e2 = ShardedEngine(m2, mesh, AdamHyper(), backend="collective", fresh_grads=False)
+    V = m1.args.vocab_size
+    for step in range(2):
+        for m, e in ((m1, e1), (m2, e2)):
+            torch.manual_seed(100 + step)
+            e.zero_grad()
+            for micro in range(2):
+                tok = torch.randint(0, V, (2, 64), device=dev)
+                e.set_micro_step(micro == 1)
+                m.loss(tok, tok, grad_scale=0.5).backward()
+            e.finish_backward()
+        assert torch.equal(e1.grad_flat, e2.grad_flat)
+        e1.step()
+        e2.step()
