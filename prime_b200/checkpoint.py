@@ -168,6 +168,9 @@ class CheckpointManager:
             self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
                 for k, v in staged.items():
+                    if not v.is_cuda:  # host-side state (RNG): already a private copy
+                        host[k] = v
+                        continue
                     buf = self._pinned.get(k)
                     if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
                         buf = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)

@@ -90,6 +90,12 @@ struct GemmParams {
   // for the backward) into C = gate_up [M, 2·FF] and h = silu(gate)·up into the second output [M, FF].
   int swiglu_ff;
   int group_m;  // raster super-row height in M tiles (0 = kGroupM)
+  // optional SwiGLU-BACKWARD epilogue (EPI = 3; the down-projection's input-gradient GEMM dh = dy·W2, N = FF): the epilogue reads the
+  // saved bf16 gate/up activations of the same (row, feature) straight from `aux` = gate_up [M, 2·FF] and stores
+  // d_gate = dh·up·silu'(gate) and d_up = dh·silu(gate) into C = d_gate_up [M, 2·FF] — dh never exists in memory and the
+  // stand-alone swiglu_bwd pass (3 % of the Llama-1B step in round 1) disappears. swiglu_ff = FF.
+  const void* aux;
+  int ld_aux;
 };
 
 // Fused collective GEMMs over the NVLink symmetric heap (IO template parameter of the kernel):
@@ -191,7 +197,7 @@ __device__ __forceinline__ void rope_regs(uint32_t (&r)[32], const float* __rest
   }
 }
 
-// EPI: 0 = plain, 1 = RoPE on the leading output columns, 2 = SwiGLU (PAIR only). Separate instantiations on purpose: the fused
+// EPI: 0 = plain, 1 = RoPE on the leading output columns, 2 = SwiGLU (PAIR only), 3 = SwiGLU backward. Separate instantiations on purpose: the fused
 // epilogues need 170-230 registers per thread, and a plain GEMM compiled with that footprint fills the SM's register file, so
 // the gradient-reduction / optimizer kernels of the comm stream can no longer co-reside with it during the backward pass
 // (measured: the 2-GPU step gained only a third of what the 1-GPU step gained when the epilogues were runtime branches).
@@ -535,6 +541,60 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (lane == 0) bulk_commit();
           buf ^= 1;
         }
+      } else if constexpr (EPI == 3) {
+        // dh tile (fp32, TMEM) ⊗ saved gate/up (bf16, global) → d_gate | d_up (bf16): two 64-column slabs per group, one TMA store each
+        const int FF = p.swiglu_ff;
+        const __nv_bfloat16* aux = reinterpret_cast<const __nv_bfloat16*>(p.aux);
+        uint8_t* stage_g = my_stage;
+        uint8_t* stage_u = my_stage + 4096;
+#pragma unroll 1
+        for (int g = 0; g < BN / 64; ++g) {
+          const int f0 = tn * BN + g * 64;
+          const bool ok = f0 < FF;  // warp-uniform (FF % 64 == 0)
+          const bool rok = ok && (row0 + lane) < p.M;
+          if (lane == 0) bulk_wait_read<0>();  // both slabs are free again
+          __syncwarp();
+          const uint4* gp = reinterpret_cast<const uint4*>(aux + (int64_t)(row0 + lane) * p.ld_aux + f0);
+          const uint4* up = reinterpret_cast<const uint4*>(aux + (int64_t)(row0 + lane) * p.ld_aux + FF + f0);
+          const uint32_t sg = smem_u32(stage_g) + lane * 128, su = smem_u32(stage_u) + lane * 128;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + g * 64 + half * 32, r);
+            uint4 gq[4], uq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              gq[j] = rok ? __ldg(gp + half * 4 + j) : make_uint4(0, 0, 0, 0);
+              uq[j] = rok ? __ldg(up + half * 4 + j) : make_uint4(0, 0, 0, 0);
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t gw[4] = {gq[j].x, gq[j].y, gq[j].z, gq[j].w}, uw[4] = {uq[j].x, uq[j].y, uq[j].z, uq[j].w};
+              uint32_t og[4], ou[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
+                const float2 uf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[e]));
+                const float d0 = __uint_as_float(r[j * 8 + 2 * e]), d1 = __uint_as_float(r[j * 8 + 2 * e + 1]);
+                const float s0 = 1.f / (1.f + __expf(-gf.x)), s1 = 1.f / (1.f + __expf(-gf.y));
+                const float dg0 = d0 * uf.x * s0 * (1.f + gf.x * (1.f - s0)), dg1 = d1 * uf.y * s1 * (1.f + gf.y * (1.f - s1));
+                const float du0 = d0 * gf.x * s0, du1 = d1 * gf.y * s1;
+                og[e] = pack_bf16x2(__float_as_uint(dg0), __float_as_uint(dg1));
+                ou[e] = pack_bf16x2(__float_as_uint(du0), __float_as_uint(du1));
+              }
+              st_shared_v4(sg + (((half * 4 + j) ^ row_sw) << 4), og[0], og[1], og[2], og[3]);
+              st_shared_v4(su + (((half * 4 + j) ^ row_sw) << 4), ou[0], ou[1], ou[2], ou[3]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && ok) {
+            tma_store_2d(&tmap_c, stage_g, f0, row0);
+            tma_store_2d(&tmap_c, stage_u, FF + f0, row0);
+          }
+          if (lane == 0) bulk_commit();
+        }
       } else if constexpr (swiglu) {
         // pack 64 fp32 accumulator columns to bf16, stage them in the swizzled slab and TMA-store them at (col0, row0)
         auto emit64 = [&](const uint32_t (&w)[32], const CUtensorMap* map, int col0, bool in_range) {
@@ -814,6 +874,23 @@ PB_EXPORT int pb_gemm_bf16_swiglu(const void* A, const void* W13, void* gate_up,
   return gemm_impl(A, W13, gate_up, M, 2 * FF, K, lda, ldb, ld_gu, 0, 0, 0, 0, 0, nullptr, nullptr, 1, 0, 64, stream, H, ld_h, FF);
 }
 
+// d_gate_up = swiglu'(gate_up) ⊙ (dy·W2) in ONE kernel (EPI = 3): dy [M, K=dim], W2 [dim, FF] (MN-major B: the contraction runs over
+// its rows), gate_up [M, 2·FF] saved by the forward, d_gate_up [M, 2·FF]. bf16, unit inner strides, CTA-pair tiles (M > 128).
+PB_EXPORT int pb_gemm_bf16_swiglu_bwd(const void* dY, const void* W2, const void* gate_up, void* d_gate_up, int M, int FF, int K,
+                                      int lda, int ldb, int ld_gu, int ld_dgu, cudaStream_t stream) {
+  if (M <= BM || FF % 64 != 0) return -5;
+  if ((lda % 8) || (ldb % 8) || (ld_gu % 8) || (ld_dgu % 8)) return -1;
+  if ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(W2) | reinterpret_cast<uintptr_t>(gate_up) |
+       reinterpret_cast<uintptr_t>(d_gate_up)) & 15) return -2;
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = pbhost::cached_tmap(&ta, dY, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, BM))) return rc;
+  if ((rc = pbhost::cached_tmap(&tb, W2, (uint64_t)K, (uint64_t)FF, (uint64_t)ldb, 64, BK))) return rc;
+  if ((rc = pbhost::cached_tmap(&tc, d_gate_up, (uint64_t)M, (uint64_t)(2 * FF), (uint64_t)ld_dgu, 64, 32, 2))) return rc;
+  GemmParams p{M, FF, K, ld_dgu, 0, 1, 0, 0, 1, d_gate_up, nullptr, nullptr, 1, 0, 64, FF, 0, gate_up, ld_gu};
+  return launch<0, 1, 1, 3>(ta, tb, tc, tc, p, 0, stream);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // all-gather ⊕ GEMM:  C[n·M_local, N] = [A_0; A_1; …; A_{n-1}] · Bᵀ, A_r = rank r's [M_local, K] block in the symmetric heap.
 // a_peers[r] is the address of rank r's block AS MAPPED IN THIS PROCESS. The caller brackets the call with heap barriers (every
@@ -888,16 +965,18 @@ PB_EXPORT int pb_gemm_reduce_scatter(const void* A, const void* B, float* const*
 //   b_mn_major = 1 (input gradient) C[M, colsW] = A[M, rowsW] · W           epi 0 only
 // SwiGLU: W = W13 [2·FF, colsW] = [gate rows | up rows], C = gate_up [M, 2·FF], H = silu(gate)·up [M, FF].
 // flags: n·4 uint32 in local memory (zeroed here, on the stream). bf16 everywhere, CTA-pair tiles (M > 128).
+// epi = 3 (with b_mn_major = 1): SwiGLU-backward epilogue, W = W2 [dim, FF]; H = the saved gate_up [M, 2·FF] (read), C = d_gate_up.
 PB_EXPORT int pb_gemm_wgather(const void* A, const void* const* w_peers, int n, int rank, void* w_full, uint32_t* flags, void* C,
                               void* H, int M, int rowsW, int colsW, int lda, int ldc, int ldh, int b_mn_major, int epi,
                               const float* rope_cos, const float* rope_sin, int rope_S, int rope_cols, int rope_D,
                               cudaStream_t stream) {
   if (n < 1 || n > 8 || rank < 0 || rank >= n || rowsW % n != 0 || colsW % 64 != 0) return -6;
   if ((lda % 8) || (ldc % 8)) return -1;
-  if (epi != 0 && b_mn_major) return -7;
+  if ((epi == 1 || epi == 2) && b_mn_major) return -7;
+  if (epi == 3 && !b_mn_major) return -7;
   const int N = b_mn_major ? colsW : rowsW, K = b_mn_major ? rowsW : colsW;
-  const int FF = epi == 2 ? rowsW / 2 : 0;
-  if (epi == 2 && (FF % 64 != 0 || H == nullptr || (ldh % 8))) return -5;
+  const int FF = epi == 2 ? rowsW / 2 : (epi == 3 ? colsW : 0);
+  if ((epi == 2 || epi == 3) && (FF % 64 != 0 || H == nullptr || (ldh % 8))) return -5;
   if (epi == 1) {
     if (rope_cos == nullptr || rope_sin == nullptr || rope_S <= 0 || M % rope_S != 0) return -3;
     if ((rope_D != 64 && rope_D != 128) || rope_cols % rope_D != 0 || rope_cols > N) return -4;
@@ -937,7 +1016,7 @@ PB_EXPORT int pb_gemm_wgather(const void* A, const void* const* w_peers, int n, 
   if (!b_mn_major) rc = pbhost::cached_tmap(&tb, w_full, (uint64_t)rowsW, (uint64_t)colsW, (uint64_t)colsW, BK, BN / 2);
   else rc = pbhost::cached_tmap(&tb, w_full, (uint64_t)rowsW, (uint64_t)colsW, (uint64_t)colsW, 64, BK);
   if (rc) return rc;
-  if ((rc = pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)(epi == 2 ? 2 * FF : N), (uint64_t)ldc, 64, 32, 2))) return rc;
+  if ((rc = pbhost::cached_tmap(&tc, C, (uint64_t)M, (uint64_t)(epi >= 2 ? 2 * FF : N), (uint64_t)ldc, 64, 32, 2))) return rc;
   th = tc;
   if (epi == 2 && (rc = pbhost::cached_tmap(&th, H, (uint64_t)M, (uint64_t)FF, (uint64_t)ldh, 64, 32, 2))) return rc;
   static int group_m = -1;
@@ -945,7 +1024,9 @@ PB_EXPORT int pb_gemm_wgather(const void* A, const void* const* w_peers, int n, 
     const char* ev = getenv("PB_WG_GROUP_M");
     group_m = ev ? atoi(ev) : 0;
   }
-  GemmParams p{M, epi == 2 ? 2 * FF : N, K, ldc, 0, b_mn_major, 0, 0, 1, C, rope_cos, rope_sin, rope_S, rope_cols, rope_D, FF, group_m};
+  GemmParams p{M, epi == 2 ? 2 * FF : N, K, ldc, 0, b_mn_major, 0, 0, 1, C, rope_cos, rope_sin, rope_S, rope_cols, rope_D, FF, group_m,
+               epi == 3 ? H : nullptr, epi == 3 ? ldh : 0};
+  if (epi == 3) return launch<0, 1, 1, 3, 3>(ta, tb, tc, tc, p, 0, stream, &pm, &tg);
   if (epi == 2) return launch<0, 0, 1, 2, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg);
   if (epi == 1) return launch<0, 0, 1, 1, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg);
   return b_mn_major ? launch<0, 1, 1, 0, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg) : launch<0, 0, 1, 0, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg);

@@ -130,7 +130,7 @@ class FeedForward(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.fp8:
             return ops.linear_mxfp8(ops.swiglu(ops.linear_mxfp8(x, self.w13)), self.w2)
-        return ops.linear(ops.linear_swiglu(x, self.w13), self.w2)  # SwiGLU rides in the gate/up GEMM epilogue on CUDA
+        return ops.mlp_swiglu(x, self.w13, self.w2)  # SwiGLU forward AND backward ride in GEMM epilogues on CUDA
 
 
 class TransformerBlock(nn.Module):

@@ -143,6 +143,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "pb_gemm_bf16": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "pb_gemm_bf16_rope": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp],
         "pb_gemm_bf16_swiglu": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "pb_gemm_bf16_swiglu_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "pb_gemm_allgather": [vp, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "pb_gemm_reduce_scatter": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "pb_quantize_mxfp8": [vp, i64, vp, vp, i32, i32, i32, vp],

@@ -114,11 +114,12 @@ def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor) -> torch.T
 
 
 def gemm_wgather(a: torch.Tensor, z, *, b_mn_major: bool = False, out: torch.Tensor | None = None, rope: tuple | None = None,
-                 swiglu_h: torch.Tensor | None = None) -> torch.Tensor:  # fmt: skip
+                 swiglu_h: torch.Tensor | None = None, swiglu_bwd_gu: torch.Tensor | None = None) -> torch.Tensor:  # fmt: skip
     """Parameter all-gather ⊕ GEMM (ZeRO-3): ``z`` is the ``RowShard`` of a weight W [rows, cols] sharded by rows over the FSDP group.
 
     ``b_mn_major=False``: C[M, rows] = a[M, cols]·Wᵀ (forward; ``rope`` = RoPE epilogue, ``swiglu_h`` = SwiGLU epilogue with W = W13,
-    C = gate_up, ``swiglu_h`` = h).  ``b_mn_major=True``: C[M, cols] = a[M, rows]·W (input gradient).  The peers' row blocks are
+    C = gate_up, ``swiglu_h`` = h).  ``b_mn_major=True``: C[M, cols] = a[M, rows]·W (input gradient; with ``swiglu_bwd_gu`` = the
+    saved gate_up the epilogue turns dh into d_gate_up [M, 2·cols] on the fly).  The peers' row blocks are
     pulled over NVLink by copier warps INSIDE the GEMM kernel (csrc/gemm_sm100.cu, IO = 3); nothing is gathered beforehand."""
     import ctypes
 
@@ -127,16 +128,20 @@ def gemm_wgather(a: torch.Tensor, z, *, b_mn_major: bool = False, out: torch.Ten
     N = z.cols if b_mn_major else z.rows
     assert a.shape[1] == (z.rows if b_mn_major else z.cols)
     if out is None:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        out = torch.empty((M, 2 * N if swiglu_bwd_gu is not None else N), dtype=torch.bfloat16, device=a.device)
     lib = _lib.load()
-    epi = 2 if swiglu_h is not None else (1 if rope is not None else 0)
+    epi = 3 if swiglu_bwd_gu is not None else (2 if swiglu_h is not None else (1 if rope is not None else 0))
     if M <= 128:
         # tiny M (unit tests, debug models): explicit gather by peer loads, then the plain kernels
         pp = _lib.PeerPtrs.of(z.peer_ptrs[i] for i in range(z.n))
         _lib.check(lib.pb_allgather_copy(ctypes.byref(pp), z.rpr * z.cols * 2, z.full_ptr, _stream()), "pb_allgather_copy")
         _count()
         w = torch.as_tensor(_RawBuffer(z.full_ptr, z.rows * z.cols * 2), device=a.device).view(torch.bfloat16).view(z.rows, z.cols)
-        if epi == 2:
+        if epi == 3:
+            dh = gemm(a, w, b_mn_major=True)
+            _lib.check(lib.pb_swiglu_bwd(swiglu_bwd_gu.data_ptr(), dh.data_ptr(), out.data_ptr(), M, z.cols, _stream()), "pb_swiglu_bwd")
+            _count()
+        elif epi == 2:
             FF = z.rows // 2
             gemm(a, w, out=out)
             _lib.check(lib.pb_swiglu_fwd(out.data_ptr(), swiglu_h.data_ptr(), M, FF, _stream()), "pb_swiglu_fwd")
@@ -155,9 +160,10 @@ def gemm_wgather(a: torch.Tensor, z, *, b_mn_major: bool = False, out: torch.Ten
     if rope is not None:
         cos, sin, seq_len, rot_cols, head_dim = rope
         assert cos.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous() and cos.shape[0] >= seq_len
+    aux = swiglu_h if swiglu_h is not None else swiglu_bwd_gu
     rc = lib.pb_gemm_wgather(
-        a.data_ptr(), z.peer_ptrs, z.n, z.rank, z.full_ptr, z.flags.data_ptr(), out.data_ptr(), _ptr(swiglu_h), M, z.rows, z.cols,
-        a.stride(0), out.stride(0), swiglu_h.stride(0) if swiglu_h is not None else 0, int(b_mn_major), epi,
+        a.data_ptr(), z.peer_ptrs, z.n, z.rank, z.full_ptr, z.flags.data_ptr(), out.data_ptr(), _ptr(aux), M, z.rows, z.cols,
+        a.stride(0), out.stride(0), aux.stride(0) if aux is not None else 0, int(b_mn_major), epi,
         _ptr(cos), _ptr(sin), seq_len, rot_cols, head_dim, _stream(),
     )  # fmt: skip
     _lib.check(rc, "pb_gemm_wgather")
@@ -623,6 +629,78 @@ class _LinearSwiGLUFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = _wgrad(dgu, x2, w13)
         return dx, dw
+
+
+class _MLPSwiGLUFn(torch.autograd.Function):
+    """y = (silu(x W1ᵀ)·(x W3ᵀ)) W2ᵀ as ONE autograd node so that the backward can fuse across the two projections:
+    the down-projection's input-gradient GEMM (dh = dy·W2) applies the SwiGLU derivative in its epilogue and writes d_gate_up
+    directly (``pb_gemm_bf16_swiglu_bwd``) — dh is never stored or re-read and the stand-alone swiglu_bwd pass is gone.
+    Forward: gate/up GEMM with the SwiGLU epilogue, then the down projection. Saves exactly what the two separate nodes saved."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M, K = x2.shape
+        FF = w13.shape[0] // 2
+        gate_up = torch.empty((M, 2 * FF), dtype=x.dtype, device=x.device)
+        h = torch.empty((M, FF), dtype=x.dtype, device=x.device)
+        z13, z2 = getattr(w13, "z3", None), getattr(w2, "z3", None)
+        if z13 is not None:
+            gemm_wgather(x2, z13, out=gate_up, swiglu_h=h)
+        else:
+            rc = lib.pb_gemm_bf16_swiglu(x2.data_ptr(), w13.data_ptr(), gate_up.data_ptr(), h.data_ptr(), M, FF, K, x2.stride(0), w13.stride(0),
+                                         2 * FF, FF, _stream())  # fmt: skip
+            _lib.check(rc, "pb_gemm_bf16_swiglu")
+            _count()
+        y = torch.empty((*x.shape[:-1], w2.shape[0]), dtype=x.dtype, device=x.device)
+        if z2 is not None:
+            gemm_wgather(h, z2, out=y.view(M, -1))
+        else:
+            gemm(h, w2, out=y.view(M, -1))
+        ctx.save_for_backward(x2, w13, w2, gate_up, h)
+        ctx.x_shape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        lib = _lib.load()
+        x2, w13, w2, gate_up, h = ctx.saved_tensors
+        M, FF = h.shape
+        dy2 = dy.reshape(M, -1)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dw2 = _wgrad(dy2, h, w2) if ctx.needs_input_grad[2] else None
+        dgu = torch.empty_like(gate_up)
+        z13, z2 = getattr(w13, "z3", None), getattr(w2, "z3", None)
+        if z2 is not None:
+            gemm_wgather(dy2, z2, b_mn_major=True, out=dgu, swiglu_bwd_gu=gate_up)
+        else:
+            rc = lib.pb_gemm_bf16_swiglu_bwd(dy2.data_ptr(), w2.data_ptr(), gate_up.data_ptr(), dgu.data_ptr(), M, FF, dy2.shape[1],
+                                             dy2.stride(0), w2.stride(0), gate_up.stride(0), dgu.stride(0), _stream())  # fmt: skip
+            _lib.check(rc, "pb_gemm_bf16_swiglu_bwd")
+            _count()
+        dx = dw13 = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(ctx.x_shape, dtype=dy.dtype, device=dy.device)
+            if z13 is not None:
+                gemm_wgather(dgu, z13, b_mn_major=True, out=dx.view(M, -1))
+            else:
+                gemm(dgu, w13, b_mn_major=True, out=dx.view(M, -1))
+        if ctx.needs_input_grad[1]:
+            dw13 = _wgrad(dgu, x2, w13)
+        return dx, dw13, dw2
+
+
+def mlp_swiglu(x: torch.Tensor, w13: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
+    """SwiGLU MLP ``linear(swiglu(linear(x, w13)), w2)``; on CUDA one autograd node with the SwiGLU forward AND backward fused into
+    GEMM epilogues (M > 128, hidden % 64 == 0), otherwise the composition of the separate ops."""
+    if (not _NO_EPILOGUE_FUSION and x.is_cuda and x.dtype == torch.bfloat16 and (w13.shape[0] // 2) % 64 == 0
+            and x.numel() // x.shape[-1] > 128 and w2.stride(1) == 1 and w13.stride(1) == 1):  # fmt: skip
+        return _MLPSwiGLUFn.apply(x, w13, w2)
+    return linear(linear_swiglu(x, w13), w2)
 
 
 def linear_swiglu(x: torch.Tensor, w13: torch.Tensor) -> torch.Tensor:

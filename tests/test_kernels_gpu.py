@@ -678,3 +678,33 @@ def test_fresh_grad_mode_matches_memset_mode():
         assert torch.equal(e1.grad_flat, e2.grad_flat)
         e1.step()
         e2.step()
+
+
+@pytest.mark.parametrize("M,D,FF", [(512, 256, 1024), (1024, 2048, 5632), (384, 136, 192)])
+def test_mlp_swiglu_fused_backward(M, D, FF):
+    """One autograd node for the SwiGLU MLP: the SwiGLU derivative rides in the down-projection's dgrad epilogue (EPI = 3)."""
+    from prime_b200 import ops
+
+    dev = _dev()
+    torch.manual_seed(M + FF)
+    x = (torch.randn(2, M // 2, D, device=dev) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    w13 = (torch.randn(2 * FF, D, device=dev) * D**-0.5).to(torch.bfloat16).requires_grad_(True)
+    w2 = (torch.randn(D, FF, device=dev) * FF**-0.5).to(torch.bfloat16).requires_grad_(True)
+    y = ops.mlp_swiglu(x, w13, w2)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr, w13r, w2r = (t.detach().float().requires_grad_(True) for t in (x, w13, w2))
+    gu = xr @ w13r.t()
+    gub = gu.to(torch.bfloat16).float() + (gu - gu.detach())  # the kernel rounds gate/up to bf16 before the activation
+    h = torch.nn.functional.silu(gub[..., :FF]) * gub[..., FF:]
+    yr = h @ w2r.t()
+    yr.backward(dy.float())
+    assert _rel_err(y, yr) < 1e-2 and _max_rel(y, yr) < 4e-2
+    assert _rel_err(x.grad, xr.grad) < 1.5e-2 and _max_rel(x.grad, xr.grad) < 6e-2
+    assert _rel_err(w13.grad, w13r.grad) < 1.5e-2 and _rel_err(w2.grad, w2r.grad) < 1.5e-2
+    # and it agrees with the composition of the separate ops (same kernels except the fused epilogue)
+    x2, w13b, w2b = (t.detach().clone().requires_grad_(True) for t in (x, w13, w2))
+    y2 = ops.linear(ops.linear_swiglu(x2, w13b), w2b)
+    y2.backward(dy)
+    assert torch.equal(y, y2)
+    assert _rel_err(x.grad, x2.grad) < 4e-3 and _rel_err(w13.grad, w13b.grad) < 4e-3

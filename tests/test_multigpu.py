@@ -388,6 +388,16 @@ WG_WORKER = textwrap.dedent(
     out["swiglu_gu"] = errs(gu, gur)
     gb = gur.to(torch.bfloat16).float()
     out["swiglu_h"] = errs(h, torch.nn.functional.silu(gb[:, :FF]) * gb[:, FF:])
+    # SwiGLU-backward epilogue on the down-projection's input gradient: W2 [K, FF] sharded by rows, d_gate_up = swiglu'(gu) ⊙ (dy·W2)
+    W2 = (torch.randn(K, FF, device=dev) * 0.05).to(torch.bfloat16)
+    z2, _ = shard(W2)
+    dy2 = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
+    torch.cuda.synchronize(); dist.barrier()
+    dgu = ops.gemm_wgather(dy2, z2, b_mn_major=True, swiglu_bwd_gu=gu)
+    dh = dy2.float() @ W2.float()
+    gf, uf = gu[:, :FF].float(), gu[:, FF:].float()
+    sg = torch.sigmoid(gf)
+    out["swiglu_bwd"] = errs(dgu, torch.cat((dh * uf * sg * (1 + gf * (1 - sg)), dh * gf * sg), dim=1))
     # RoPE epilogue on the leading (Q, K) head columns of a fused QKV projection
     H, D, S = 4, 128, 256
     Wq = (torch.randn(3 * H * D, K, device=dev) * 0.05).to(torch.bfloat16)

@@ -58,8 +58,12 @@ def rows_of(path: Path):
         if len(r) != len(header):
             continue
         rec = dict(zip(header, r))
-        row = {"kernel": re.sub(r"\(.*", "", re.sub(r"<.*", "", rec.get("Kernel Name", "?"))).replace("void ", "").strip(), "id": rec.get("ID")}
-        tmpl = re.search(r"<([^>]*)>", rec.get("Kernel Name", ""))
+        # kernels in anonymous namespaces are reported as "<unnamed>::name<args>(…)": strip the qualifier BEFORE cutting at the
+        # first template bracket (round 1 printed blank names for the GEMM / attention rows because of it)
+        full = rec.get("Kernel Name", "?").replace("void ", "")
+        full = re.sub(r"(<unnamed>|\(anonymous namespace\))::", "", full)
+        row = {"kernel": re.sub(r"\(.*", "", re.sub(r"<.*", "", full)).strip(), "id": rec.get("ID")}
+        tmpl = re.search(r"<([^>]*)>", full)
         if tmpl:
             row["tmpl"] = tmpl.group(1)
         for metric, short in WANT.items():
