@@ -428,7 +428,10 @@ PB_EXPORT int pb_pseudograd_quant(const float* theta0, const float* theta, int8_
 // `qs.p[w]` / `ss.p[w]` = worker w's int8 payload / scales for THIS rank's shard (peer-mapped).
 __global__ void __launch_bounds__(256) outer_nesterov_kernel(PeerPtrs qs, PeerPtrs ss, float* __restrict__ theta0,
                                                              float* __restrict__ mom, float* __restrict__ theta, int64_t n,
-                                                             OuterArgs a, PeerPtrs dst, BucketTable tab) {
+                                                             OuterArgs a, PeerPtrs dst, BucketTable tab, const uint32_t* err) {
+  // a failed flag barrier in front of this kernel (a worker died between the rendezvous and the exchange) leaves the error word
+  // set: the peers' payloads are not trustworthy, so nothing is read or updated and the host retries on the re-formed group
+  if (err != nullptr && *reinterpret_cast<const volatile uint32_t*>(err) != 0u) return;
   const int grp = threadIdx.x >> 6, t64 = threadIdx.x & 63, lane = threadIdx.x & 31;
   const int64_t nblk = n >> 10;
   for (int64_t blk0 = (int64_t)blockIdx.x * 4; blk0 < nblk; blk0 += (int64_t)gridDim.x * 4) {
@@ -485,13 +488,13 @@ __global__ void __launch_bounds__(256) outer_nesterov_kernel(PeerPtrs qs, PeerPt
 
 PB_EXPORT int pb_outer_nesterov(const PeerPtrs* qs, const PeerPtrs* ss, float* theta0, float* mom, float* theta, int64_t n,
                                 const OuterArgs* a, const PeerPtrs* dst, const int64_t* shard_start, const int64_t* dst_start,
-                                int nb, cudaStream_t stream) {
+                                int nb, const uint32_t* err, cudaStream_t stream) {
   if (n % 1024 != 0 || nb < 1) return -1;
   int64_t ctas = (n / 1024 + 3) / 4;
   if (ctas > 148 * 8) ctas = 148 * 8;
   if (ctas < 1) ctas = 1;
   BucketTable tab{shard_start, dst_start, nb};
-  outer_nesterov_kernel<<<(unsigned)ctas, 256, 0, stream>>>(*qs, *ss, theta0, mom, theta, n, *a, *dst, tab);
+  outer_nesterov_kernel<<<(unsigned)ctas, 256, 0, stream>>>(*qs, *ss, theta0, mom, theta, n, *a, *dst, tab, err);
   PB_CHECK_LAUNCH();
   return 0;
 }
@@ -502,7 +505,8 @@ PB_EXPORT int pb_outer_nesterov(const PeerPtrs* qs, const PeerPtrs* ss, float* t
 // pushes the bf16 parameters to the FSDP group.
 __global__ void __launch_bounds__(256) outer_nesterov_f32_kernel(PeerPtrs thetas, float* __restrict__ theta0, float* __restrict__ mom,
                                                                  float* __restrict__ theta_new, int64_t n, OuterArgs a, PeerPtrs dst,
-                                                                 BucketTable tab) {
+                                                                 BucketTable tab, const uint32_t* err) {
+  if (err != nullptr && *reinterpret_cast<const volatile uint32_t*>(err) != 0u) return;
   const int64_t nvec = n >> 3;  // 8 elements per thread-iteration → one 16-byte bf16 store per peer
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float outv[8];
@@ -544,10 +548,10 @@ __global__ void __launch_bounds__(256) outer_nesterov_f32_kernel(PeerPtrs thetas
 }
 PB_EXPORT int pb_outer_nesterov_f32(const PeerPtrs* thetas, float* theta0, float* mom, float* theta_new, int64_t n, const OuterArgs* a,
                                     const PeerPtrs* dst, const int64_t* shard_start, const int64_t* dst_start, int nb,
-                                    cudaStream_t stream) {
+                                    const uint32_t* err, cudaStream_t stream) {
   if (n % 8 != 0 || nb < 1) return -1;
   BucketTable tab{shard_start, dst_start, nb};
-  outer_nesterov_f32_kernel<<<148 * 4, 256, 0, stream>>>(*thetas, theta0, mom, theta_new, n, *a, *dst, tab);
+  outer_nesterov_f32_kernel<<<148 * 4, 256, 0, stream>>>(*thetas, theta0, mom, theta_new, n, *a, *dst, tab, err);
   PB_CHECK_LAUNCH();
   return 0;
 }

@@ -368,10 +368,125 @@ __global__ void __launch_bounds__(512) cross_entropy_kernel(bf16x8* __restrict__
   }
 }
 
+// Register-resident variant: every thread keeps its share of the row (VPT 16-byte vectors, all loads issued up front) in registers,
+// so the logits are read from memory exactly once and the normalise/overwrite pass needs no second trip through L2 — and the
+// loads of a row are all in flight together instead of one per loop iteration (round 1: 0.59 of the HBM roof).
+template <int VPT>
+__global__ void __launch_bounds__(1024) cross_entropy_reg_kernel(bf16x8* __restrict__ logits, const int64_t* __restrict__ targets,
+                                                                 float* __restrict__ losses, const float* __restrict__ scale_ptr,
+                                                                 int V, int64_t ignore_index) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const int nvec = V / 8;
+  bf16x8* zr = logits + row * nvec;
+  const int64_t tgt = targets[row];
+  bf16x8 v[VPT];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int c = threadIdx.x + k * blockDim.x;
+    if (c < nvec) v[k] = ldg_stream(zr + c);
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int c = threadIdx.x + k * blockDim.x;
+    if (c < nvec) {
+      float z[8];
+      unpack8(v[k], z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m = fmaxf(m, z[j]);
+    }
+  }
+  const float gm = block_max(m, red);
+  float s = 0.f, zt = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int c = threadIdx.x + k * blockDim.x;
+    if (c < nvec) {
+      float z[8];
+      unpack8(v[k], z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s += __expf(z[j] - gm);
+        if ((int64_t)(c * 8 + j) == tgt) zt = z[j];
+      }
+    }
+  }
+  const float gs = block_sum(s, red);
+  const float ztg = block_sum(zt, red);  // exactly one thread holds the target logit (0 elsewhere)
+  const bool valid = (tgt != ignore_index);
+  const float scale = valid ? *scale_ptr : 0.f;
+  if (threadIdx.x == 0) losses[row] = valid ? (gm + __logf(gs) - ztg) : 0.f;
+  const float inv = 1.f / gs;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int c = threadIdx.x + k * blockDim.x;
+    if (c < nvec) {
+      float z[8], o[8];
+      unpack8(v[k], z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float p = __expf(z[j] - gm) * inv;
+        if ((int64_t)(c * 8 + j) == tgt) p -= 1.f;
+        o[j] = p * scale;
+      }
+      stg_stream(zr + c, pack8(o));
+    }
+  }
+}
+
+static int launch_cross_entropy(void* logits, const int64_t* targets, float* losses, const float* scale_ptr, int64_t R, int V,
+                                int64_t ignore_index, cudaStream_t stream) {
+  if (V % 8 != 0) return -1;
+  const int nvec = V / 8;
+  if (nvec <= 512 * 8)
+    cross_entropy_reg_kernel<8><<<(unsigned)R, 512, 0, stream>>>((bf16x8*)logits, targets, losses, scale_ptr, V, ignore_index);
+  else if (nvec <= 1024 * 16)
+    cross_entropy_reg_kernel<16><<<(unsigned)R, 1024, 0, stream>>>((bf16x8*)logits, targets, losses, scale_ptr, V, ignore_index);
+  else
+    cross_entropy_kernel<<<(unsigned)R, 512, 0, stream>>>((bf16x8*)logits, targets, losses, scale_ptr, V, ignore_index);
+  PB_CHECK_LAUNCH();
+  return 0;
+}
+
 PB_EXPORT int pb_cross_entropy_fwd_bwd(void* logits, const int64_t* targets, float* losses, const float* scale_ptr,
                                        int64_t R, int V, int64_t ignore_index, cudaStream_t stream) {
-  if (V % 8 != 0) return -1;
-  cross_entropy_kernel<<<(unsigned)R, 512, 0, stream>>>((bf16x8*)logits, targets, losses, scale_ptr, V, ignore_index);
+  return launch_cross_entropy(logits, targets, losses, scale_ptr, R, V, ignore_index, stream);
+}
+
+// Whole loss node without a single framework kernel: count the valid targets → gradient scale; the row kernel; a fixed-order sum
+// of the per-row losses → mean loss (deterministic). work: >= 2 floats of scratch ([0] = grad_scale / n_valid, [1] = 1 / n_valid).
+__global__ void __launch_bounds__(1024) ce_count_kernel(const int64_t* __restrict__ targets, int64_t R, int64_t ignore_index,
+                                                        float grad_scale, float* __restrict__ work) {
+  __shared__ float red[32];
+  float n = 0.f;
+  for (int64_t i = threadIdx.x; i < R; i += blockDim.x) n += targets[i] != ignore_index ? 1.f : 0.f;
+  n = block_sum(n, red);
+  if (threadIdx.x == 0) {
+    const float inv = 1.f / fmaxf(n, 1.f);
+    work[0] = grad_scale * inv;
+    work[1] = inv;
+  }
+}
+__global__ void __launch_bounds__(1024) ce_finalize_kernel(const float* __restrict__ losses, int64_t R, const float* __restrict__ work,
+                                                           float* __restrict__ loss_out, float* __restrict__ loss_acc) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < R; i += blockDim.x) s += losses[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float mean = s * work[1];
+    *loss_out = mean;
+    if (loss_acc != nullptr) *loss_acc += mean;  // running sum over the micro-batches of a step (the trainer's logging value)
+  }
+}
+PB_EXPORT int pb_cross_entropy_loss(void* logits, const int64_t* targets, float* losses, float* work, float* loss_out, float* loss_acc,
+                                    int64_t R, int V, int64_t ignore_index, float grad_scale, cudaStream_t stream) {
+  ce_count_kernel<<<1, 1024, 0, stream>>>(targets, R, ignore_index, grad_scale, work);
+  PB_CHECK_LAUNCH();
+  int rc = launch_cross_entropy(logits, targets, losses, work, R, V, ignore_index, stream);
+  if (rc) return rc;
+  ce_finalize_kernel<<<1, 1024, 0, stream>>>(losses, R, work, loss_out, loss_acc);
   PB_CHECK_LAUNCH();
   return 0;
 }

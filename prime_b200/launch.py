@@ -310,7 +310,12 @@ def supervise(run_dir: Path, resume: bool = False) -> int:
         if spec.elastic:
             env["GLOBAL_UNIQUE_ID"] = name
         if slices[k] is not None:
-            env["CUDA_VISIBLE_DEVICES"] = slices[k]
+            if spec.elastic:
+                # elastic workers keep every GPU VISIBLE and are told which ones are theirs: the fused outer step maps the other
+                # workers' exchange buffers by cudaIpc, which cannot reach a device hidden by CUDA_VISIBLE_DEVICES
+                env["PRIME_B200_DEVICES"] = ",".join(str(k * spec.gpus + j) for j in range(spec.gpus))  # indices into the visible pool
+            else:
+                env["CUDA_VISIBLE_DEVICES"] = slices[k]
         workers.append(_Worker(name, worker_command(spec, run, name, port, resume), env))
 
     status: dict[str, Any] = {"state": "RUNNING", "supervisor_pid": os.getpid(), "started_at": time.time(), "finished_at": None,

@@ -224,10 +224,11 @@ class Transformer(nn.Module):
     def forward(self, tokens: torch.Tensor) -> torch.Tensor:
         return ops.linear(self.forward_hidden(tokens), self.output)
 
-    def loss(self, tokens: torch.Tensor, targets: torch.Tensor, *, grad_scale: float = 1.0) -> torch.Tensor:
-        """Mean next-token loss; gradient (not value) is scaled by ``grad_scale``; call ``.backward()`` on it."""
+    def loss(self, tokens: torch.Tensor, targets: torch.Tensor, *, grad_scale: float = 1.0, loss_acc: torch.Tensor | None = None) -> torch.Tensor:
+        """Mean next-token loss; gradient (not value) is scaled by ``grad_scale``; call ``.backward()`` on it. ``loss_acc``: fp32
+        scalar that additionally receives ``+= loss`` inside the loss kernel (the trainer's running sum over micro-batches)."""
         logits = self.forward(tokens)
-        return ops.cross_entropy(logits, targets, grad_scale=grad_scale, unit_upstream=True)
+        return ops.cross_entropy(logits, targets, grad_scale=grad_scale, unit_upstream=True, loss_acc=loss_acc)
 
     # ------------------------------------------------------------------ accounting
     def num_params(self, exclude_embedding: bool = False) -> int:

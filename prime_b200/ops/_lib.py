@@ -140,6 +140,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "pb_swiglu_fwd": [vp, vp, i64, i32, vp],
         "pb_swiglu_bwd": [vp, vp, vp, i64, i32, vp],
         "pb_cross_entropy_fwd_bwd": [vp, vp, vp, vp, i64, i32, i64, vp],
+        "pb_cross_entropy_loss": [vp, vp, vp, vp, vp, vp, i64, i32, i64, f32, vp],
         "pb_gemm_bf16": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "pb_gemm_bf16_rope": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp],
         "pb_gemm_bf16_swiglu": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
@@ -171,8 +172,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "pb_norm_publish": [vp, i32, PP, PP, i32, i32, u32, vp],
         "pb_adamw_push": [vp, vp, vp, vp, i64, ctypes.POINTER(AdamArgs), vp, i32, vp, i32, u32, PP, i64, vp, vp, vp],
         "pb_pseudograd_quant": [vp, vp, vp, vp, i64, vp],
-        "pb_outer_nesterov": [PP, PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), PP, vp, vp, i32, vp],
-        "pb_outer_nesterov_f32": [PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), PP, vp, vp, i32, vp],
+        "pb_outer_nesterov": [PP, PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), PP, vp, vp, i32, vp, vp],
+        "pb_outer_nesterov_f32": [PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), PP, vp, vp, i32, vp, vp],
         "pb_set_spin_timeout_ms": [ctypes.c_ulonglong],
         "pb_grad_reduce_segs": [PP, ctypes.POINTER(SegTable), f32, vp, vp, vp, i32, u32, vp, i32, vp],
         "pb_embedding_fwd": [vp, i64, PP, i32, i32, vp, vp],

@@ -715,26 +715,26 @@ def linear_swiglu(x: torch.Tensor, w13: torch.Tensor) -> torch.Tensor:
 
 class _CrossEntropyFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, targets, ignore_index, grad_scale, unit_upstream):
+    def forward(ctx, logits, targets, ignore_index, grad_scale, unit_upstream, loss_acc):
         lib = _lib.load()
         V = logits.shape[-1]
         z = logits.reshape(-1, V)
         assert z.is_contiguous()
         t = targets.reshape(-1)
+        t = t if t.is_contiguous() else t.contiguous()
         R = z.shape[0]
-        n_valid = (t != ignore_index).sum().clamp_(min=1).to(torch.float32)
-        scale = (1.0 / n_valid).reshape(1)
-        kscale = scale * grad_scale if grad_scale != 1.0 else scale
-        losses = torch.empty(R, dtype=torch.float32, device=z.device)
-        # logits are overwritten with d(mean loss)/d(logits): nothing else needs them afterwards
-        rc = lib.pb_cross_entropy_fwd_bwd(_ptr(z), _ptr(t), _ptr(losses), _ptr(kscale), R, V, ignore_index, _stream())
-        _lib.check(rc, "pb_cross_entropy_fwd_bwd")
-        _count()
+        work = torch.empty(R + 4, dtype=torch.float32, device=z.device)  # [0:2] scales, [2] loss, [4:] per-row losses
+        # valid-target count → gradient scale, the fused row kernel (logits are overwritten with d(mean loss)/d(logits): nothing else
+        # needs them afterwards) and a fixed-order sum of the row losses — three native launches, no framework kernel
+        rc = lib.pb_cross_entropy_loss(_ptr(z), _ptr(t), work[4:].data_ptr(), work.data_ptr(), work[2:].data_ptr(), _ptr(loss_acc), R, V,
+                                       ignore_index, float(grad_scale), _stream())  # fmt: skip
+        _lib.check(rc, "pb_cross_entropy_loss")
+        _count(3)
         # NOTE: deliberately not mark_dirty(): the logits are consumed, not returned; their storage now holds the gradient
         ctx.save_for_backward(z)
         ctx.shape = logits.shape
         ctx.unit_upstream = unit_upstream
-        return (losses.sum() * scale).reshape(())
+        return work[2].reshape(())
 
     @staticmethod
     def backward(ctx, dloss):
@@ -742,7 +742,7 @@ class _CrossEntropyFn(torch.autograd.Function):
         # dz already holds the gradient for dloss == 1; rescale for loss scaling / grad accumulation
         if not ctx.unit_upstream:
             dz = dz * dloss.to(dz.dtype)
-        return dz.view(ctx.shape), None, None, None, None
+        return dz.view(ctx.shape), None, None, None, None, None
 
 
 def cross_entropy(
@@ -752,16 +752,20 @@ def cross_entropy(
     *,
     grad_scale: float = 1.0,
     unit_upstream: bool = False,
+    loss_acc: torch.Tensor | None = None,
 ) -> torch.Tensor:
     """Mean token cross-entropy.  On CUDA the logits buffer is consumed (overwritten with its gradient).
 
     ``grad_scale`` folds a gradient multiplier (e.g. 1/grad-accumulation-steps) into the fused kernel; the
     returned loss value is NOT scaled.  ``unit_upstream=True`` promises the loss is back-propagated with a
-    unit upstream gradient, which removes one full pass over the logits gradient.
+    unit upstream gradient, which removes one full pass over the logits gradient.  ``loss_acc``: optional fp32 scalar the
+    (unscaled) loss is also added to, inside the finalising kernel — the trainer's per-step running sum.
     """
     if logits.is_cuda:
-        return _CrossEntropyFn.apply(logits, targets, ignore_index, float(grad_scale), bool(unit_upstream))
+        return _CrossEntropyFn.apply(logits, targets, ignore_index, float(grad_scale), bool(unit_upstream), loss_acc)
     loss = reference.cross_entropy(logits, targets, ignore_index)
+    if loss_acc is not None:
+        loss_acc += loss.detach().float()
     if grad_scale != 1.0:
         # same contract on CPU: value unscaled, gradient scaled
         loss = loss.detach() + (loss - loss.detach()) * grad_scale

@@ -69,6 +69,15 @@ class DilocoOuter:
         self.timed_steps = 0
         # ``collective=True``: the exchange goes through a (re-creatable) process group instead of the symmetric heap
         self.fused = engine.backend == "fused" and not collective
+        self.exchange = None  # ElasticExchange: fused outer step across separately launched workers (attach_exchange)
+        if engine.backend == "fused":
+            # shard index → position in the bf16 parameter buffer, one entry per bucket (see BucketTable in csrc/comm.cu); one
+            # launch per destination set (replicated engine: one; ZeRO-3: local shard buffer + the small replicated bucket)
+            self._ranges = []
+            for lo, hi, dst, starts, dsts in engine.outer_ranges():
+                self._ranges.append((lo, hi, dst, torch.tensor(starts, dtype=torch.int64, device=dev),
+                                     torch.tensor(dsts, dtype=torch.int64, device=dev)))  # fmt: skip
+            self._ev_pool = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2)]
         if self.fused:
             heap = engine.heap
             world = heap.world_size
@@ -82,17 +91,17 @@ class DilocoOuter:
                 if not engine.master_in_heap:
                     raise ValueError("fused fp32 outer step needs the inner masters in the symmetric heap (ShardedEngine(master_in_heap=True))")
                 self.theta_new = torch.empty(n, dtype=torch.float32, device=dev)
-            # shard index → position in the bf16 parameter buffer, one entry per bucket (see BucketTable in csrc/comm.cu); one
-            # launch per destination set (replicated engine: one; ZeRO-3: local shard buffer + the small replicated bucket)
-            self._ranges = []
-            for lo, hi, dst, starts, dsts in engine.outer_ranges():
-                self._ranges.append((lo, hi, dst, torch.tensor(starts, dtype=torch.int64, device=dev),
-                                     torch.tensor(dsts, dtype=torch.int64, device=dev)))  # fmt: skip
-            self._ev_pool = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(2)]
+
+    def attach_exchange(self, exchange) -> None:
+        """Elastic jobs: run the fused kernel pair over an ``ElasticExchange`` (cudaIpc regions published through the global store)
+        instead of a process group. Needs the fused engine; int8 compression only."""
+        if self.engine.backend != "fused" or self.hyper.compression != "int8":
+            raise ValueError("the elastic NVLink exchange needs the fused engine and int8 compression")
+        self.exchange = exchange
 
     @property
     def num_workers(self) -> int:
-        return len(self.ranks)
+        return len(self.exchange.members) if self.exchange is not None else len(self.ranks)
 
     def set_membership(self, ranks, group) -> None:
         """Elastic join/drop: swap the set of peers contributing to the next outer step."""
@@ -104,13 +113,15 @@ class DilocoOuter:
         t0 = time.perf_counter()
         cuda = self.engine.device.type == "cuda"
         if cuda:
-            if self.fused:
+            if self.engine.backend == "fused":
                 ev = self._ev_pool[self.outer_step_count % 2]
             else:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             self._harvest()
             ev[0].record()
-        if self.fused:
+        if self.exchange is not None:
+            self._step_exchange()
+        elif self.fused:
             self._step_fused()
         else:
             self._step_collective()
@@ -160,7 +171,7 @@ class DilocoOuter:
                 _lib.check(
                     lib.pb_outer_nesterov(ctypes.byref(qs), ctypes.byref(ss), self.theta0[lo:].data_ptr(), self.momentum[lo:].data_ptr(),
                                           eng.master[lo:].data_ptr(), hi - lo, ctypes.byref(args), ctypes.byref(dst), tab_s.data_ptr(),
-                                          tab_d.data_ptr(), tab_d.numel(), s),
+                                          tab_d.data_ptr(), tab_d.numel(), heap.err.data_ptr(), s),
                     "pb_outer_nesterov",
                 )  # fmt: skip
             self._epoch += 1
@@ -176,7 +187,7 @@ class DilocoOuter:
                 _lib.check(
                     lib.pb_outer_nesterov_f32(ctypes.byref(ths), self.theta0[lo:].data_ptr(), self.momentum[lo:].data_ptr(),
                                               self.theta_new[lo:].data_ptr(), hi - lo, ctypes.byref(args), ctypes.byref(dst),
-                                              tab_s.data_ptr(), tab_d.data_ptr(), tab_d.numel(), s),
+                                              tab_s.data_ptr(), tab_d.data_ptr(), tab_d.numel(), heap.err.data_ptr(), s),
                     "pb_outer_nesterov_f32",
                 )  # fmt: skip
             self._epoch += 1
@@ -184,6 +195,37 @@ class DilocoOuter:
             eng.master.copy_(self.theta_new)
             self.last_bytes_on_wire = (W - 1) * 4 * n
             _count(3 + len(self._ranges))
+
+    def _step_exchange(self) -> None:
+        """Same kernel pair as ``_step_fused`` over the elastic exchange regions (see parallel/elastic_exchange.py). Synchronises at
+        the end and raises if a member never reached a barrier — θ₀, momentum and the master are untouched in that case."""
+        from .elastic_exchange import SLOT_A, SLOT_B
+
+        eng, lib, x = self.engine, self.engine.lib, self.exchange
+        s = torch.cuda.current_stream().cuda_stream
+        n = eng.shard_total
+        W = len(x.members)
+        args = _lib.OuterArgs(self.hyper.lr, self.hyper.momentum, 1.0 / W, int(self.hyper.nesterov))
+        _lib.check(lib.pb_pseudograd_quant(self.theta0.data_ptr(), eng.master.data_ptr(), x.q.data_ptr(), x.scales.data_ptr(), n, s),
+                   "pb_pseudograd_quant")  # fmt: skip
+        x.barrier(SLOT_A, s)  # every member's payload is published
+        qs_all, ss_all = x.payload_ptrs()
+        for lo, hi, dst, tab_s, tab_d in self._ranges:
+            qs = _lib.PeerPtrs.of(qs_all.p[i] + lo for i in range(W))
+            ss = _lib.PeerPtrs.of(ss_all.p[i] + (lo // SHARD_ALIGN) * 4 for i in range(W))
+            _lib.check(
+                lib.pb_outer_nesterov(ctypes.byref(qs), ctypes.byref(ss), self.theta0[lo:].data_ptr(), self.momentum[lo:].data_ptr(),
+                                      eng.master[lo:].data_ptr(), hi - lo, ctypes.byref(args), ctypes.byref(dst), tab_s.data_ptr(),
+                                      tab_d.data_ptr(), tab_d.numel(), x.err.data_ptr(), s),
+                "pb_outer_nesterov",
+            )  # fmt: skip
+        x.barrier(SLOT_B, s)  # payloads consumed
+        if eng.F > 1:  # the bf16 write-back went to the FSDP peers of THIS worker: close it like the inner step does
+            eng._epoch += 1
+            eng.heap.barrier(self.mesh.fsdp_ranks, eng.slot_bar, eng._epoch, s)
+        self.last_bytes_on_wire = (W - 1) * (n + 4 * (n // SHARD_ALIGN))
+        _count(3 + len(self._ranges))
+        x.finish()
 
     def _step_collective(self) -> None:
         eng, h = self.engine, self.hyper

@@ -29,6 +29,15 @@ class WorldInfo:
     global_addr: str = "127.0.0.1"
     global_port: int = 29600
 
+    @property
+    def device_index(self) -> int:
+        """CUDA device of this rank. ``PRIME_B200_DEVICES="4,5"`` (set by ``launch.py`` for elastic workers) maps local ranks onto
+        a slice of the box WITHOUT hiding the other GPUs: the fused elastic outer step maps the exchange buffers of other workers'
+        GPUs through cudaIpc, which needs those devices visible to this process (CUDA_VISIBLE_DEVICES slicing would hide them)."""
+        pool = os.environ.get("PRIME_B200_DEVICES", "")
+        ids = [int(x) for x in pool.split(",") if x.strip()]
+        return ids[self.local_rank] if self.local_rank < len(ids) else self.local_rank
+
     @classmethod
     def from_env(cls) -> "WorldInfo":
         e = os.environ
@@ -50,13 +59,13 @@ def init_distributed(backend: str = "auto", timeout_s: float = 600.0) -> WorldIn
     if backend == "auto":
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if torch.cuda.is_available():
-        torch.cuda.set_device(info.local_rank)
+        torch.cuda.set_device(info.device_index)
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         kwargs = {}
         if backend == "nccl":
-            kwargs["device_id"] = torch.device("cuda", info.local_rank)
+            kwargs["device_id"] = torch.device("cuda", info.device_index)
         dist.init_process_group(
             backend, rank=info.rank, world_size=info.world_size, timeout=datetime.timedelta(seconds=timeout_s), **kwargs
         )
@@ -110,7 +119,7 @@ def resolve_shape(world_size: int, num_workers: int = 0, fsdp_size: int = 0) -> 
 def build_mesh(world: WorldInfo, num_workers: int = 0, fsdp_size: int = 0, device: torch.device | None = None) -> Mesh:
     num_workers, fsdp_size = resolve_shape(world.world_size, num_workers, fsdp_size)
     if device is None:
-        device = torch.device("cuda", world.local_rank) if torch.cuda.is_available() else torch.device("cpu")
+        device = torch.device("cuda", world.device_index) if torch.cuda.is_available() else torch.device("cpu")
     mesh = Mesh(world=world, num_workers=num_workers, fsdp_size=fsdp_size, device=device)
     mesh.fsdp_ranks = [mesh.worker_id * fsdp_size + i for i in range(fsdp_size)]
     mesh.diloco_ranks = [w * fsdp_size + mesh.fsdp_rank for w in range(num_workers)]

@@ -82,6 +82,16 @@ def _elastic_setup(cfg: Config, trainer: Trainer, log) -> Any:
     eng, outer = trainer.engine, trainer.outer
     state = [eng.master, eng.exp_avg, eng.exp_avg_sq, outer.theta0, outer.momentum]
     retries = max(1, cfg.diloco.retry_all_reduce)
+    xchg = None
+    if eng.backend == "fused" and cfg.diloco.compression in ("int8", "uint8") and __import__("os").environ.get("PRIME_B200_ELASTIC_FUSED", "1") != "0":
+        # fused outer step across the separately launched workers: cudaIpc exchange regions published through the global store
+        from .parallel.elastic_exchange import ElasticExchange
+
+        xchg = ElasticExchange(ctx.store, ctx.wid, mesh.fsdp_rank, eng.shard_total, mesh.device)
+        outer.attach_exchange(xchg)
+        trainer.heap.set_spin_timeout(max(2.0, min(20.0, cfg.mesh.heartbeat_timeout_s / 2)))  # a dead peer costs seconds, not 20
+        ctx.exchange = xchg
+        log.info("elastic: fused NVLink outer exchange (cudaIpc region of %.1f MiB per rank)", xchg.nbytes / 2**20)
 
     def meet() -> None:
         m = ctx.rendezvous()
@@ -91,6 +101,8 @@ def _elastic_setup(cfg: Config, trainer: Trainer, log) -> Any:
             trainer.step_count, eng.step_count, outer.outer_step_count = got["trainer_step"], got["engine_step"], got["outer_step"]
             eng.publish_params()
         outer.set_membership(list(range(m.size)), m.pg)
+        if xchg is not None:
+            xchg.connect(m.workers, m.epoch)
         trainer.global_workers = m.size
         for _, msg in ctx.events:
             log.info("elastic: %s", msg)
@@ -114,6 +126,8 @@ def _elastic_setup(cfg: Config, trainer: Trainer, log) -> Any:
                 meet()
         log.warning("elastic: giving up on the exchange; taking a local outer step")
         outer.set_membership([0], None)
+        if xchg is not None:
+            xchg.connect([ctx.wid], ctx.epoch)
         plain_step()
 
     outer.step = guarded_step  # type: ignore[method-assign]
@@ -225,6 +239,9 @@ def train(cfg: Config, *, max_steps: int | None = None) -> dict[str, Any]:
             ckpt.wait()
         if elastic is not None:
             elastic.close()
+            if getattr(elastic, "exchange", None) is not None:
+                torch.cuda.synchronize()
+                elastic.exchange.close()
         if clocks is not None:
             last["clocks"] = clocks.finish()
         jsonl.close()

@@ -37,7 +37,7 @@ class Trainer:
         if mesh is None:
             world = init_distributed(cfg.mesh.backend) if (_env_world() > 1 or dist.is_initialized()) else WorldInfo.from_env()
             if torch.cuda.is_available():
-                torch.cuda.set_device(world.local_rank)
+                torch.cuda.set_device(world.device_index)
             if cfg.mesh.elastic:  # this process world IS one worker; other workers are reached through the elastic coordinator
                 mesh = build_mesh(world, 1, world.world_size)
             else:
@@ -138,7 +138,7 @@ class Trainer:
         scale = 1.0 / self.accum
 
         def micro() -> torch.Tensor:
-            loss = self.model.loss(self._g_tokens, self._g_labels, grad_scale=scale)
+            loss = self.model.loss(self._g_tokens, self._g_labels, grad_scale=scale, loss_acc=self._loss_acc)
             loss.backward()
             eng.fold_micro_grads()
             return loss.detach()
@@ -183,13 +183,12 @@ class Trainer:
                 if last:
                     eng.finish_backward()
             else:
-                loss = self.model.loss(batch.input_ids, batch.labels, grad_scale=1.0 / self.accum)
+                loss = self.model.loss(batch.input_ids, batch.labels, grad_scale=1.0 / self.accum, loss_acc=self._loss_acc)
                 loss.backward()
                 if last:
                     eng.finish_backward()
                 else:
                     eng.fold_micro_grads()
-            self._loss_acc += loss.detach().float()
         lr = self.current_lr()
         eng.step(lr)
         self.step_count += 1

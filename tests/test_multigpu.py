@@ -82,13 +82,9 @@ def test_fsdp2_fused_matches_collective(tmp_path):
     assert r["la"][-1] < r["la"][0]
 
 
-# The NVLS path was written after the round's GPU budget was spent: it compiles (LDGMC / multimem in the SASS) and its host
-# logic is covered on CPU, but it has not run on hardware yet. Until it has, these two tests are opt-in so that an untested
-# path cannot stop a `-x` run of the suite.
-nvls_opt_in = pytest.mark.skipif(os.environ.get("PB_TEST_NVLS") != "1", reason="NVLS path not yet validated on hardware; set PB_TEST_NVLS=1")
-
-
-@nvls_opt_in
+# NVLS (multimem.ld_reduce / multimem.st over a VMM heap bound to an NVSwitch multicast object) was brought up on hardware in
+# round 2 (2 x B200: both tests green, gpurun_out/r2b_pytest_nvls.txt); the tests skip themselves only where the driver reports
+# no multicast support.
 def test_fsdp2_nvls_reduce_scatter_matches_collective(tmp_path):
     """PB_NVLS=1: the heap is VMM-backed with a multicast mapping and the gradient reduce-scatter is summed by the switch."""
     from prime_b200.parallel.multicast import nvls_available
@@ -310,7 +306,6 @@ NVLS_WORKER = textwrap.dedent(
 )
 
 
-@nvls_opt_in
 def test_nvls_multicast_all_reduce_and_grad_reduce(tmp_path):
     """multimem.ld_reduce / multimem.st over a VMM heap bound to an NVSwitch multicast object: the in-place all-reduce matches
     the dense sum, and the NVLS gradient reduce-scatter matches the peer-load kernel it can replace (PB_NVLS=1)."""

@@ -47,6 +47,10 @@ def main():
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm = float(peaks.get("hbm_gbs", 6571.0))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    from prime_b200.utils.clocks import ClockSampler
+
+    sampler = ClockSampler(0)
+    sampler.start()
     iters, warm = (1, 0) if a.once else (10, 3)
     B, S, D, FF, V, H, HD = 16, 1024, 2048, 5632, 32000, 16, 128
     T = B * S
@@ -77,7 +81,14 @@ def main():
     logits = torch.randn(T, V, device=dev, dtype=bf)
     tg = torch.randint(0, V, (T,), device=dev)
     add("cross_entropy_fwd+bwd(in place)", lambda: F.cross_entropy(logits, tg, grad_scale=1.0, unit_upstream=True), 2 * T * V * 2)
-    del x, res, xg, y, dy, qkv, gu, o, do, logits
+    emb = torch.nn.Parameter(torch.randn(V, D, device=dev, dtype=bf))
+    emb.main_grad = torch.zeros(V, D, device=dev, dtype=torch.float32)
+    tok = torch.randint(0, V, (B, S), device=dev)
+    add("embedding_fwd (native row gather)", lambda: F.embedding(tok, emb), 2 * T * D * 2)
+    eo = F.embedding(tok, emb)
+    deo = torch.randn_like(eo)
+    add("embedding_bwd (sort + segmented sum into fp32 main_grad)", lambda: torch.autograd.grad(eo, emb, deo, retain_graph=True, allow_unused=True), T * D * 2 + 2 * T * D * 4)
+    del x, res, xg, y, dy, qkv, gu, o, do, logits, emb, eo, deo
     torch.cuda.empty_cache()
 
     cfg = Config.model_validate({"name_model": a.model, "data": {"seq_length": S}, "optim": {"batch_size": 16}, "train": {"micro_bs": 16},
@@ -94,7 +105,7 @@ def main():
     add("inner step: zero_grad + grad_reduce+norm + clip⊕AdamW⊕bf16 cast⊕param push (F=1)", inner, n * (4 + 8 + 30))
     add("outer step: pseudograd⊕int8 quant → dequant⊕Nesterov⊕master reset⊕bf16 push (W=1)", tr.outer.step, n * (9 + 23))
     out = {"shapes": {"tokens": T, "dim": D, "ffn": FF, "vocab": V, "params": n}, "hbm_gbs_measured": hbm, "mode": "once" if a.once else "median of 10, L2 flushed", "rows": rows,
-           "launches": ops.launch_count()}  # fmt: skip
+           "launches": ops.launch_count(), "clocks": sampler.finish()}  # fmt: skip
     print(json.dumps(out, indent=1))
     tr.close()
 
