@@ -125,6 +125,9 @@ PB_EXPORT int pb_barrier(const PeerPtrs* flags, int base_slot, int my_idx, uint3
 //   sumsq_partial[blockIdx] += sum_i out[i]^2  (accumulated over buckets; folded by phase 2)
 // If wait_flags != nullptr the kernel first waits for flag[slot_base + p] >= expect for every peer p.
 // ------------------------------------------------------------------------------------------------
+// U = independent 16-byte vectors per thread and iteration: with few peers a thread otherwise has one or two loads in flight and
+// the kernel runs at half the memory roof (ncu r2: F = 1 → dram 50 %, warps 49 %); U·F loads are issued before any is consumed.
+template <int U, int P>
 __global__ void __launch_bounds__(512) grad_reduce_kernel(PeerPtrs grads, int64_t off, int64_t n, float scale,
                                                           float* __restrict__ out, float* __restrict__ sumsq_partial,
                                                           const uint32_t* wait_flags, int slot_base, uint32_t expect,
@@ -139,19 +142,31 @@ __global__ void __launch_bounds__(512) grad_reduce_kernel(PeerPtrs grads, int64_
     if (s_fail) return;  // a peer never signalled: leave the shard untouched, the host raises on the error word
   }
   const int64_t nvec = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   float ss = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * U) {
+    float4 v[U][P];  // P = compile-time bound on the number of peers (registers are allocated for P, not for kMaxPeers)
 #pragma unroll
-    for (int p = 0; p < kMaxPeers; ++p) {
-      if (p < grads.n) {
-        const float4 v = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.p[p]) + off) + i);
-        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+        if (p < grads.n && i < nvec)
+          v[u][p] = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.p[p]) + off) + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < nvec) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+          if (p < grads.n) acc.x += v[u][p].x, acc.y += v[u][p].y, acc.z += v[u][p].z, acc.w += v[u][p].w;  // fixed rank order
+        acc.x *= scale, acc.y *= scale, acc.z *= scale, acc.w *= scale;
+        reinterpret_cast<float4*>(out)[i] = acc;
+        ss += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
       }
     }
-    acc.x *= scale, acc.y *= scale, acc.z *= scale, acc.w *= scale;
-    reinterpret_cast<float4*>(out)[i] = acc;
-    ss += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
   }
   ss = block_sum(ss, red);
   if (threadIdx.x == 0) sumsq_partial[blockIdx.x] += ss;
@@ -165,8 +180,14 @@ PB_EXPORT int pb_grad_reduce(const PeerPtrs* grads, int64_t off, int64_t n, floa
   if (n % 4 != 0 || off % 4 != 0) return -1;
   int grid = pb_grad_reduce_grid();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  grad_reduce_kernel<<<grid, 512, 0, stream>>>(*grads, off, n, scale, out, sumsq_partial, wait_flags, slot_base, expect,
-                                               err);
+  if (grads->n == 1)
+    grad_reduce_kernel<4, 1><<<grid, 512, 0, stream>>>(*grads, off, n, scale, out, sumsq_partial, wait_flags, slot_base, expect, err);
+  else if (grads->n == 2)
+    grad_reduce_kernel<4, 2><<<grid, 512, 0, stream>>>(*grads, off, n, scale, out, sumsq_partial, wait_flags, slot_base, expect, err);
+  else if (grads->n <= 4)
+    grad_reduce_kernel<2, 4><<<grid, 512, 0, stream>>>(*grads, off, n, scale, out, sumsq_partial, wait_flags, slot_base, expect, err);
+  else
+    grad_reduce_kernel<1, 8><<<grid, 512, 0, stream>>>(*grads, off, n, scale, out, sumsq_partial, wait_flags, slot_base, expect, err);
   PB_CHECK_LAUNCH();
   return 0;
 }

@@ -369,66 +369,82 @@ __global__ void __launch_bounds__(512) cross_entropy_kernel(bf16x8* __restrict__
 }
 
 // Register-resident variant: every thread keeps its share of the row (VPT 16-byte vectors, all loads issued up front) in registers,
-// so the logits are read from memory exactly once and the normalise/overwrite pass needs no second trip through L2 — and the
-// loads of a row are all in flight together instead of one per loop iteration (round 1: 0.59 of the HBM roof).
-template <int VPT>
-__global__ void __launch_bounds__(1024) cross_entropy_reg_kernel(bf16x8* __restrict__ logits, const int64_t* __restrict__ targets,
-                                                                 float* __restrict__ losses, const float* __restrict__ scale_ptr,
-                                                                 int V, int64_t ignore_index) {
+// so the logits are read from memory exactly once and the loads of a row are all in flight together (round 1: one load per loop
+// iteration, 0.59 of the HBM roof). The first cut of this kernel was ISSUE-bound (ncu: sm 79 %, dram 39 %): two MUFU.EX2 per element
+// (16/clk/SM → 0.23 ms of MUFU alone for a 16384 x 32000 tile) and 64-bit target-index compares per element. Now:
+//   pass 1  row max on packed bf16x2 (HMNMX2: one instruction per two logits)
+//   pass 2  e = exp2(z·log2e − max·log2e): one FFMA + one MUFU per element, summed in fp32, and written BACK into the registers as
+//           bf16 (p ∈ (0, 1]); the target logit is picked by ONE range check per vector
+//   pass 3  p·(scale/sum) from the stored e — no second exponential; the target's −1 is patched in by the one thread that owns it
+template <int VPT, int THREADS>
+__global__ void __launch_bounds__(THREADS) cross_entropy_reg_kernel(bf16x8* __restrict__ logits, const int64_t* __restrict__ targets,
+                                                                    float* __restrict__ losses, const float* __restrict__ scale_ptr,
+                                                                    int V, int64_t ignore_index) {
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   const int nvec = V / 8;
   bf16x8* zr = logits + row * nvec;
-  const int64_t tgt = targets[row];
+  const int64_t tgt64 = targets[row];
+  const bool valid = (tgt64 != ignore_index);
+  const int tgt = valid ? (int)tgt64 : -1;
   bf16x8 v[VPT];
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
-    const int c = threadIdx.x + k * blockDim.x;
+    const int c = threadIdx.x + k * THREADS;
     if (c < nvec) v[k] = ldg_stream(zr + c);
   }
-  float m = -INFINITY;
+  __nv_bfloat162 m2 = __float2bfloat162_rn(-INFINITY);
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
-    const int c = threadIdx.x + k * blockDim.x;
+    const int c = threadIdx.x + k * THREADS;
     if (c < nvec) {
-      float z[8];
-      unpack8(v[k], z);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m = fmaxf(m, z[j]);
+      for (int j = 0; j < 4; ++j) m2 = __hmax2(m2, v[k].v[j]);
     }
   }
-  const float gm = block_max(m, red);
+  const float2 mf = __bfloat1622float2(m2);
+  const float gm = block_max(fmaxf(mf.x, mf.y), red);
+  const float gml2 = gm * 1.4426950408889634f;
   float s = 0.f, zt = 0.f;
+  int t_k = -1, t_j = 0;  // which of my registers holds the target (at most one thread of the block)
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
-    const int c = threadIdx.x + k * blockDim.x;
+    const int c = threadIdx.x + k * THREADS;
     if (c < nvec) {
       float z[8];
       unpack8(v[k], z);
+      const unsigned d = (unsigned)(tgt - c * 8);
+      if (d < 8u) {
+        t_k = k, t_j = (int)d;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j == (int)d) zt = z[j];
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        s += __expf(z[j] - gm);
-        if ((int64_t)(c * 8 + j) == tgt) zt = z[j];
+        z[j] = exp2f(fmaf(z[j], 1.4426950408889634f, -gml2));
+        s += z[j];
       }
+      v[k] = pack8(z);
     }
   }
   const float gs = block_sum(s, red);
   const float ztg = block_sum(zt, red);  // exactly one thread holds the target logit (0 elsewhere)
-  const bool valid = (tgt != ignore_index);
   const float scale = valid ? *scale_ptr : 0.f;
   if (threadIdx.x == 0) losses[row] = valid ? (gm + __logf(gs) - ztg) : 0.f;
-  const float inv = 1.f / gs;
+  const float f = scale / gs;
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
-    const int c = threadIdx.x + k * blockDim.x;
+    const int c = threadIdx.x + k * THREADS;
     if (c < nvec) {
-      float z[8], o[8];
-      unpack8(v[k], z);
+      float o[8];
+      unpack8(v[k], o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float p = __expf(z[j] - gm) * inv;
-        if ((int64_t)(c * 8 + j) == tgt) p -= 1.f;
-        o[j] = p * scale;
+      for (int j = 0; j < 8; ++j) o[j] *= f;
+      if (k == t_k) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j == t_j) o[j] -= scale;
       }
       stg_stream(zr + c, pack8(o));
     }
@@ -440,10 +456,9 @@ static int launch_cross_entropy(void* logits, const int64_t* targets, float* los
   if (V % 8 != 0) return -1;
   const int nvec = V / 8;
   if (nvec <= 512 * 8)
-    cross_entropy_reg_kernel<8><<<(unsigned)R, 512, 0, stream>>>((bf16x8*)logits, targets, losses, scale_ptr, V, ignore_index);
-  else if (nvec <= 1024 * 16)
-    cross_entropy_reg_kernel<16><<<(unsigned)R, 1024, 0, stream>>>((bf16x8*)logits, targets, losses, scale_ptr, V, ignore_index);
-  else
+    cross_entropy_reg_kernel<8, 512><<<(unsigned)R, 512, 0, stream>>>((bf16x8*)logits, targets, losses, scale_ptr, V, ignore_index);
+  else  // larger vocabularies (Llama-3: 128256) would spill the register-resident row: two-pass kernel
+
     cross_entropy_kernel<<<(unsigned)R, 512, 0, stream>>>((bf16x8*)logits, targets, losses, scale_ptr, V, ignore_index);
   PB_CHECK_LAUNCH();
   return 0;

@@ -131,10 +131,9 @@ PB_EXPORT int pb_embedding_fwd(const int64_t* tokens, int64_t T, const PeerPtrs*
 
 PB_EXPORT int pb_embedding_bwd_max_chunk() { return 16384; }
 
-// scratch: >= min(T, 16384) uint64. grad [V, dim] fp32 is accumulated into (+=).
-PB_EXPORT int pb_embedding_bwd(const int64_t* tokens, int64_t T, const void* dout, float* grad, int dim, unsigned long long* scratch,
-                               cudaStream_t stream) {
-  if (dim % 8 != 0) return -1;
+// Step 1 (can run as soon as the token ids exist, e.g. on a side stream during the FORWARD pass — it is one CTA for ~0.2 ms):
+// sorted[pos0 .. pos0+n) = (token << 32 | position) keys of every 16384-token chunk, ascending.
+PB_EXPORT int pb_embedding_sort(const int64_t* tokens, int64_t T, unsigned long long* sorted, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(embedding_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
@@ -145,13 +144,30 @@ PB_EXPORT int pb_embedding_bwd(const int64_t* tokens, int64_t T, const void* dou
     const int n = (int)((T - pos0) < 16384 ? (T - pos0) : 16384);
     int n_pad = 2;
     while (n_pad < n) n_pad <<= 1;
-    embedding_sort_kernel<<<1, 1024, (size_t)n_pad * 8, stream>>>(tokens + pos0, n, n_pad, (int)pos0, scratch);
-    PB_CHECK_LAUNCH();
-    dim3 grid((n + kRange - 1) / kRange, (dim + 1023) / 1024);
-    embedding_bwd_kernel<<<grid, 128, 0, stream>>>(scratch, n, reinterpret_cast<const __nv_bfloat16*>(dout), grad, dim);
+    embedding_sort_kernel<<<1, 1024, (size_t)n_pad * 8, stream>>>(tokens + pos0, n, n_pad, (int)pos0, sorted + pos0);
     PB_CHECK_LAUNCH();
   }
   return 0;
+}
+
+// Step 2: grad [V, dim] fp32 += segmented sums of dout rows, chunk after chunk in stream order (fixed summation order).
+PB_EXPORT int pb_embedding_scatter(const unsigned long long* sorted, int64_t T, const void* dout, float* grad, int dim, cudaStream_t stream) {
+  if (dim % 8 != 0) return -1;
+  for (int64_t pos0 = 0; pos0 < T; pos0 += 16384) {
+    const int n = (int)((T - pos0) < 16384 ? (T - pos0) : 16384);
+    dim3 grid((n + kRange - 1) / kRange, (dim + 1023) / 1024);
+    embedding_bwd_kernel<<<grid, 128, 0, stream>>>(sorted + pos0, n, reinterpret_cast<const __nv_bfloat16*>(dout), grad, dim);
+    PB_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+// both steps on one stream. scratch: >= T uint64.
+PB_EXPORT int pb_embedding_bwd(const int64_t* tokens, int64_t T, const void* dout, float* grad, int dim, unsigned long long* scratch,
+                               cudaStream_t stream) {
+  int rc = pb_embedding_sort(tokens, T, scratch, stream);
+  if (rc) return rc;
+  return pb_embedding_scatter(scratch, T, dout, grad, dim, stream);
 }
 
 PB_EXPORT int pb_allgather_copy(const PeerPtrs* src, int64_t bytes_per_rank, void* dst, cudaStream_t stream) {

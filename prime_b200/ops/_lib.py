@@ -179,6 +179,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "pb_embedding_fwd": [vp, i64, PP, i32, i32, vp, vp],
         "pb_embedding_bwd": [vp, i64, vp, vp, i32, vp, vp],
         "pb_embedding_bwd_max_chunk": [],
+        "pb_embedding_sort": [vp, i64, vp, vp],
+        "pb_embedding_scatter": [vp, i64, vp, vp, i32, vp],
         "pb_allgather_copy": [PP, i64, vp, vp],
         "pb_gemm_wgather": [vp, ctypes.POINTER(vp), i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp],
         "pb_cast_push": [vp, i64, PP, i64, vp],

@@ -385,14 +385,31 @@ class _EmbeddingFn(torch.autograd.Function):
         out = torch.empty((*tokens.shape, dim), dtype=weight.dtype, device=weight.device)
         _lib.check(lib.pb_embedding_fwd(t.data_ptr(), t.numel(), ctypes.byref(pp), rpr, dim, out.data_ptr(), _stream()), "pb_embedding_fwd")
         _count()
-        ctx.save_for_backward(t)
         ctx.weight = weight
+        ctx.sorted_ev = None
+        if torch.is_grad_enabled() and weight.requires_grad:
+            # the backward needs the positions sorted by token: a one-CTA kernel (~0.2 ms) that depends only on the token ids, so it
+            # runs NOW on a side stream underneath the forward GEMMs instead of on the critical path at the end of the backward
+            sorted_keys = torch.empty(t.numel(), dtype=torch.int64, device=weight.device)
+            if torch.cuda.is_current_stream_capturing():
+                _lib.check(lib.pb_embedding_sort(t.data_ptr(), t.numel(), sorted_keys.data_ptr(), _stream()), "pb_embedding_sort")
+            else:
+                side = _side_stream(weight.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    _lib.check(lib.pb_embedding_sort(t.data_ptr(), t.numel(), sorted_keys.data_ptr(), side.cuda_stream), "pb_embedding_sort")
+                    ctx.sorted_ev = torch.cuda.Event()
+                    ctx.sorted_ev.record(side)
+                t.record_stream(side)
+                sorted_keys.record_stream(side)
+            _count((t.numel() + 16383) // 16384)
+            ctx.save_for_backward(sorted_keys)
         return out
 
     @staticmethod
     def backward(ctx, dout: torch.Tensor):
         lib = _lib.load()
-        (t,) = ctx.saved_tensors
+        (sorted_keys,) = ctx.saved_tensors
         weight = ctx.weight
         V, dim = weight.shape
         d2 = dout.reshape(-1, dim)
@@ -405,11 +422,22 @@ class _EmbeddingFn(torch.autograd.Function):
         else:
             grad = torch.zeros((V, dim), dtype=torch.float32, device=dout.device)
             ret = grad
-        scratch = torch.empty(min(t.numel(), lib.pb_embedding_bwd_max_chunk()), dtype=torch.int64, device=dout.device)
-        _lib.check(lib.pb_embedding_bwd(t.data_ptr(), t.numel(), d2.data_ptr(), grad.data_ptr(), dim, scratch.data_ptr(), _stream()),
-                   "pb_embedding_bwd")  # fmt: skip
-        _count(2 * ((t.numel() + 16383) // 16384))
+        if ctx.sorted_ev is not None:
+            torch.cuda.current_stream().wait_event(ctx.sorted_ev)
+        T = sorted_keys.numel()
+        _lib.check(lib.pb_embedding_scatter(sorted_keys.data_ptr(), T, d2.data_ptr(), grad.data_ptr(), dim, _stream()), "pb_embedding_scatter")
+        _count((T + 16383) // 16384)
         return None, (None if ret is None else ret.to(weight.dtype))
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    s = _SIDE_STREAMS.get(device)
+    if s is None:
+        s = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+    return s
 
 
 def embedding(tokens: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:

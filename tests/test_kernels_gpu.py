@@ -695,7 +695,7 @@ def test_mlp_swiglu_fused_backward(M, D, FF):
     y.backward(dy)
     xr, w13r, w2r = (t.detach().float().requires_grad_(True) for t in (x, w13, w2))
     gu = xr @ w13r.t()
-    gub = gu.to(torch.bfloat16).float() + (gu - gu.detach())  # the kernel rounds gate/up to bf16 before the activation
+    gub = gu + (gu.to(torch.bfloat16).float() - gu).detach()  # the kernel rounds gate/up to bf16 before the activation (straight-through)
     h = torch.nn.functional.silu(gub[..., :FF]) * gub[..., FF:]
     yr = h @ w2r.t()
     yr.backward(dy.float())

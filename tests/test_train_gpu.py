@@ -29,7 +29,7 @@ def test_gpu_train_checkpoint_resume_exact(tmp_path):
     train(load_config(BASE + ["--ckpt.path", str(b), "--ckpt.interval", "4", "--monitor.jsonl_path", str(b / "l1.jsonl")]), max_steps=4)
     assert ck.list_steps(b) == [4]
     shard, extra = ck.read_shard(b / "step_000004" / "rank_00000.pbck")
-    assert set(shard) == {"master", "exp_avg", "exp_avg_sq", "theta0", "momentum"} and extra["trainer_step"] == 4
+    assert {"master", "exp_avg", "exp_avg_sq", "theta0", "momentum", "rng_cpu", "rng_cuda"} == set(shard) and extra["trainer_step"] == 4
     train(load_config(BASE + ["--ckpt.path", str(b), "--ckpt.resume", "latest", "--monitor.jsonl_path", str(b / "l2.jsonl")]))
     resumed = {**_losses(b / "l1.jsonl"), **_losses(b / "l2.jsonl")}
     assert resumed == straight
