@@ -36,26 +36,32 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __global__ void __launch_bounds__(256) bwd_delta_kernel(const pb::bf16x8* __restrict__ dout, const pb::bf16x8* __restrict__ out,
                                                         float* __restrict__ delta, int64_t tokens, int S, int H, int vec_per_head,
                                                         float scale) {
-  // one warp per (token, head); writes delta·scale (the only form the two kernels below use)
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // one warp per TOKEN: it walks the token's H·D row in fully coalesced 512-byte steps (32 lanes x 16 B) and reduces inside groups
+  // of `vec_per_head` lanes (D = 128 → 16 lanes, two heads per step; D = 64 → 8 lanes, four heads per step). Round 1 gave a warp to
+  // every (token, head) pair, which left half of the lanes (D = 128) or three quarters (D = 64) without a vector to load.
+  // Writes delta·scale (the only form the two kernels below use).
+  const int64_t tok = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (w >= tokens * H) return;
-  const int64_t tok = w / H;
-  const int h = (int)(w - tok * H);
-  const int64_t base = (tok * H + h) * vec_per_head;
-  float acc = 0.f;
-  for (int i = lane; i < vec_per_head; i += 32) {
-    float a[8], b[8];
-    pb::unpack8(pb::ldg_stream(dout + base + i), a);
-    pb::unpack8(pb::ldg_stream(out + base + i), b);
+  if (tok >= tokens) return;
+  const int vec_per_tok = H * vec_per_head;
+  const int64_t base = tok * vec_per_tok;
+  const int64_t bidx = tok / S;
+  const int s = (int)(tok - bidx * S);
+  for (int i0 = 0; i0 < vec_per_tok; i0 += 32) {
+    const int i = i0 + lane;
+    float acc = 0.f;
+    if (i < vec_per_tok) {
+      float a[8], b[8];
+      pb::unpack8(pb::ldg_stream(dout + base + i), a);
+      pb::unpack8(pb::ldg_stream(out + base + i), b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc += a[j] * b[j];
-  }
-  acc = pb::warp_sum(acc);
-  if (lane == 0) {
-    const int64_t bidx = tok / S;
-    const int s = (int)(tok - bidx * S);
-    delta[(bidx * H + h) * S + s] = acc * scale;
+      for (int j = 0; j < 8; ++j) acc += a[j] * b[j];
+    }
+    for (int o = vec_per_head >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((lane & (vec_per_head - 1)) == 0 && i < vec_per_tok) {
+      const int h = i / vec_per_head;
+      delta[(bidx * H + h) * S + s] = acc * scale;
+    }
   }
 }
 
@@ -923,7 +929,7 @@ int launch_bwd(const void* qkv, const void* out, const void* dout, const float* 
   }
   const uint64_t rows = (uint64_t)B * S, wqkv = (uint64_t)(H + 2 * Hkv) * D, wo = (uint64_t)H * D;
   {
-    const int64_t warps = (int64_t)rows * H;
+    const int64_t warps = (int64_t)rows;  // one warp per token (vec_per_head = D / 8 is 8 or 16: a power of two <= 32)
     const int64_t blocks = (warps * 32 + 255) / 256;
     bwd_delta_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const pb::bf16x8*)dout, (const pb::bf16x8*)out, delta, (int64_t)rows, S,
                                                           H, D / 8, scale);

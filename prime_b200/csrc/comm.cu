@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(512) adamw_push_kernel(float* __restrict__ p32
                                                          float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                          AdamArgs a, const float* norm_slots, int n_norm,
                                                          const uint32_t* wait_flags, int flag_slot, uint32_t epoch,
-                                                         PeerPtrs dst, int64_t dst_off, float* gnorm_out, uint32_t* err) {
+                                                         PeerPtrs dst, int64_t dst_off, float* gnorm_out, uint32_t* err,
+                                                         __nv_bfloat16* mc_dst) {
+  // mc_dst != nullptr: the parameter buffer's NVSwitch MULTICAST address (parallel/multicast.py) — one multimem.st per 16 bytes
+  // lands in every rank's copy, so the all-gather leaves this GPU once instead of once per peer (1/F of the outbound bytes)
   __shared__ float s_clip;
   __shared__ int s_fail;
   if (threadIdx.x == 0) {
@@ -331,19 +334,26 @@ __global__ void __launch_bounds__(512) adamw_push_kernel(float* __restrict__ p32
       reinterpret_cast<float4*>(v)[j] = vv;
     }
     const bf16x8 packed = pack8(out);
+    if (mc_dst != nullptr) {
+      const uint4& r = *reinterpret_cast<const uint4*>(&packed);
+      asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<bf16x8*>(mc_dst + dst_off) + i),
+                   "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w)
+                   : "memory");
+    } else {
 #pragma unroll
-    for (int q = 0; q < kMaxPeers; ++q)
-      if (q < dst.n) stg_v4(reinterpret_cast<bf16x8*>(reinterpret_cast<__nv_bfloat16*>(dst.p[q]) + dst_off) + i, packed);
+      for (int q = 0; q < kMaxPeers; ++q)
+        if (q < dst.n) stg_v4(reinterpret_cast<bf16x8*>(reinterpret_cast<__nv_bfloat16*>(dst.p[q]) + dst_off) + i, packed);
+    }
   }
 }
 
 PB_EXPORT int pb_adamw_push(float* p32, const float* g32, float* m, float* v, int64_t n, const AdamArgs* a,
                             const float* norm_slots, int n_norm, const uint32_t* wait_flags, int flag_slot,
                             uint32_t epoch, const PeerPtrs* dst, int64_t dst_off, float* gnorm_out, uint32_t* err,
-                            cudaStream_t stream) {
+                            void* mc_dst, cudaStream_t stream) {
   if (n % 8 != 0 || dst_off % 8 != 0) return -1;
   adamw_push_kernel<<<148 * 2, 512, 0, stream>>>(p32, g32, m, v, n, *a, norm_slots, n_norm, wait_flags, flag_slot, epoch,
-                                                 *dst, dst_off, gnorm_out, err);
+                                                 *dst, dst_off, gnorm_out, err, reinterpret_cast<__nv_bfloat16*>(mc_dst));
   PB_CHECK_LAUNCH();
   return 0;
 }

@@ -133,6 +133,16 @@ struct PeerMaps {
   int col_chunks;     // cols / 64
   int spc;            // chunk rows per readiness counter = ceil(cpr / kGatherSub)
   int start;          // first output-column tile (K-major B) / first k-block (MN-major B) of the rotated order
+  int gate;           // 1: B is gathered by THIS kernel and the tiles wait for it; 0: B is already resident in the local scratch
+  // gather-AHEAD list: the weight the NEXT GEMM of the layer sequence consumes (forward: wqkv → wo → w13 → w2 → next layer;
+  // backward: the reverse dgrad order). After (or instead of) its own weight the copier pulls this one into ITS scratch region, so
+  // the next kernel finds its operand resident and runs un-gated: in steady state every gather hides under the previous GEMM and
+  // only the first kernel of a pass waits for NVLink (measured without it, 4 x B200: forward +6 %, dgrad +40…90 % — the first wave
+  // of dgrad tiles needs every rank block).
+  CUtensorMap nm[8];
+  int nn;             // ranks holding the next weight (0 = nothing to prefetch)
+  int ncpr, ncol_chunks;
+  int norder[8];
 };
 
 // IO = 1 tile schedule: [gather tiles][local tiles][dependent tiles]; kind 1 = gather (tn = 0 of a remote block), 0 = local rows,
@@ -205,7 +215,8 @@ template <int A_MN, int B_MN, int PAIR, int EPI, int IO>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_h,
-                     const __grid_constant__ CUtensorMap tmap_g, const GemmParams p, const __grid_constant__ PeerMaps pm) {
+                     const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_g2, const GemmParams p,
+                     const __grid_constant__ PeerMaps pm) {
   using G = Geo<PAIR, IO>;
   constexpr int kStages = G::kStages;
   constexpr uint32_t kStageBytes = G::kStageBytes;
@@ -248,15 +259,18 @@ __global__ void __launch_bounds__(kThreads, 1)
   };
   const int group_m = p.group_m > 0 ? p.group_m : kGroupM;
   // IO = 3 rotations (see PeerMaps): K-major B → output columns start at the own rank block; MN-major B → the K loop does
-  const int tn_rot = (IO == 3 && B_MN == 0) ? pm.start : 0;
-  const int kb_rot = (IO == 3 && B_MN == 1) ? pm.start : 0;
+  const int tn_rot = (IO == 3 && B_MN == 0 && pm.gate) ? pm.start : 0;
+  const int kb_rot = (IO == 3 && B_MN == 1 && pm.gate) ? pm.start : 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_c);
     prefetch_tmap(&tmap_h);
-    if (IO == 3) prefetch_tmap(&tmap_g);
+    if (IO == 3) {
+      prefetch_tmap(&tmap_g);
+      prefetch_tmap(&tmap_g2);
+    }
     if (IO != 0)
       for (int i = 0; i < pm.n; ++i) prefetch_tmap(&pm.m[i]);
   }
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       // rank block; a counter that was seen complete stays complete for the rest of the kernel (bit in `ready`).
       uint32_t ready = 0;
       auto gate_rows = [&](int r0, int r1) {
-        if (IO != 3) return;
+        if (IO != 3 || !pm.gate) return;
         const int rpr = pm.rows_per_rank;
         for (int x = r0; x <= r1;) {
           const int b = x / rpr, cr = (x - b * rpr) >> 7;
@@ -444,51 +458,57 @@ __global__ void __launch_bounds__(kThreads, 1)
     // readiness counter of the box's quarter block once the store has fully completed. Two boxes are in flight per CTA
     // (148 x 32 KB per ~3 us of NVLink latency is well above what the MMA tiles consume).
     if (lane == 0) {
-      const int cpb = pm.cpr * pm.col_chunks;  // boxes per rank block
-      const int total = cpb * pm.n;
-      const int mine = total > (int)blockIdx.x ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-      auto box = [&](int i, int& owner, int& cr, int& cc) {
-        const int g = (int)blockIdx.x + i * (int)gridDim.x;
-        const int j = g / cpb, c = g - j * cpb;
-        owner = pm.order[j];
-        cr = c / pm.col_chunks;
-        cc = c - cr * pm.col_chunks;
-      };
-      auto fetch = [&](int i) {  // rows past the end of the owner's shard are zero-filled by the TMA unit
-        int owner, cr, cc;
-        box(i, owner, cr, cc);
-        const int buf = i % kCopyBufs;
-        mbar_expect_tx(&cp_bar[buf], kCopyChunkBytes);
-        tma_load_2d(&pm.m[owner], &cp_bar[buf], copy_buf + buf * kCopyChunkBytes, cc * BK, cr * 128);
-      };
-      for (int i = 0; i < kCopyBufs && i < mine; ++i) fetch(i);  // both NVLink loads in flight from the start
       uint32_t ph[kCopyBufs] = {0, 0};
-      int prev_id = -1;
-      for (int i = 0; i < mine; ++i) {
-        int owner, cr, cc;
-        box(i, owner, cr, cc);
-        const int buf = i % kCopyBufs;
-        mbar_wait(&cp_bar[buf], ph[buf]);
-        ph[buf] ^= 1;
-        // … and clipped by the store: dimension 1 of the 3-D map is the rows of ONE rank block
-        tma_store_3d(&tmap_g, copy_buf + buf * kCopyChunkBytes, cc * BK, cr * 128, owner);
-        bulk_commit();
-        if (prev_id >= 0) {  // the previous box's WRITES are complete (not only its smem reads): publish it
-          asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+      // one list = one weight: (peer maps, local store map, rank order, geometry); `flags` != nullptr → publish per-quarter counters
+      auto gather_list = [&](const CUtensorMap* maps, const CUtensorMap* store_map, const int* order, int n, int cpr, int col_chunks,
+                             int spc, uint32_t* flags) {
+        const int cpb = cpr * col_chunks;  // boxes per rank block
+        const int total = cpb * n;
+        const int mine = total > (int)blockIdx.x ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        auto box = [&](int i, int& owner, int& cr, int& cc) {
+          const int g = (int)blockIdx.x + i * (int)gridDim.x;
+          const int j = g / cpb, c = g - j * cpb;
+          owner = order[j];
+          cr = c / col_chunks;
+          cc = c - cr * col_chunks;
+        };
+        auto fetch = [&](int i) {  // rows past the end of the owner's shard are zero-filled by the TMA unit
+          int owner, cr, cc;
+          box(i, owner, cr, cc);
+          const int buf = i % kCopyBufs;
+          mbar_expect_tx(&cp_bar[buf], kCopyChunkBytes);
+          tma_load_2d(&maps[owner], &cp_bar[buf], copy_buf + buf * kCopyChunkBytes, cc * BK, cr * 128);
+        };
+        for (int i = 0; i < kCopyBufs && i < mine; ++i) fetch(i);  // both NVLink loads in flight from the start
+        int prev_id = -1;
+        for (int i = 0; i < mine; ++i) {
+          int owner, cr, cc;
+          box(i, owner, cr, cc);
+          const int buf = i % kCopyBufs;
+          mbar_wait(&cp_bar[buf], ph[buf]);
+          ph[buf] ^= 1;
+          // … and clipped by the store: dimension 1 of the 3-D map is the rows of ONE rank block
+          tma_store_3d(store_map, copy_buf + buf * kCopyChunkBytes, cc * BK, cr * 128, owner);
+          bulk_commit();
+          if (flags != nullptr && prev_id >= 0) {  // the previous box's WRITES are complete (not only its smem reads): publish it
+            asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+            fence_proxy_async_all();
+            pb::red_add_release_gpu_u32(flags + prev_id, 1u);
+          }
+          prev_id = owner * kGatherSub + min(cr / spc, kGatherSub - 1);
+          if (i + kCopyBufs < mine) {
+            bulk_wait_read<0>();  // this buffer has been read out by the store above
+            fetch(i + kCopyBufs);
+          }
+        }
+        bulk_wait_all();  // every box of this list is in local memory (the NEXT kernel relies on that for a gather-ahead list)
+        if (flags != nullptr && prev_id >= 0) {
           fence_proxy_async_all();
-          pb::red_add_release_gpu_u32(pm.flags + prev_id, 1u);
+          pb::red_add_release_gpu_u32(flags + prev_id, 1u);
         }
-        prev_id = owner * kGatherSub + min(cr / pm.spc, kGatherSub - 1);
-        if (i + kCopyBufs < mine) {
-          bulk_wait_read<0>();  // this buffer has been read out by the store above
-          fetch(i + kCopyBufs);
-        }
-      }
-      if (prev_id >= 0) {
-        bulk_wait_all();
-        fence_proxy_async_all();
-        pb::red_add_release_gpu_u32(pm.flags + prev_id, 1u);
-      }
+      };
+      if (pm.gate) gather_list(pm.m, &tmap_g, pm.order, pm.n, pm.cpr, pm.col_chunks, pm.spc, pm.flags);
+      if (pm.nn > 0) gather_list(pm.nm, &tmap_g2, pm.norder, pm.nn, pm.ncpr, pm.ncol_chunks, 1, nullptr);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
@@ -720,10 +740,12 @@ int g_split_k_mode = -1;  // -1 auto, 0/1 off, n>1 forced
 
 template <int A_MN, int B_MN, int PAIR, int EPI = 0, int IO = 0>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& th, const GemmParams& p,
-           int max_ctas, cudaStream_t stream, const PeerMaps* pmp = nullptr, const CUtensorMap* tgp = nullptr) {
+           int max_ctas, cudaStream_t stream, const PeerMaps* pmp = nullptr, const CUtensorMap* tgp = nullptr,
+           const CUtensorMap* tg2p = nullptr) {
   static const PeerMaps kNoPeers = {};
   const PeerMaps& pm = pmp ? *pmp : kNoPeers;
   const CUtensorMap& tg = tgp ? *tgp : tc;
+  const CUtensorMap& tg2 = tg2p ? *tg2p : tg;
   using G = Geo<PAIR, IO>;
   static bool configured = false;
   if (!configured) {
@@ -743,7 +765,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   const int tiles = ((p.M + G::kTileM - 1) / G::kTileM) * tiles_n * p.split_k;
   if (!PAIR) {
     if (tiles < grid) grid = tiles;
-    gemm_bf16_kernel<A_MN, B_MN, 0, EPI, IO><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, th, tg, p, pm);
+    gemm_bf16_kernel<A_MN, B_MN, 0, EPI, IO><<<grid, kThreads, G::kSmemBytes, stream>>>(ta, tb, tc, th, tg, tg2, p, pm);
   } else {
     grid &= ~1;
     if (2 * tiles < grid) grid = 2 * tiles;
@@ -760,7 +782,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1, EPI, IO>, ta, tb, tc, th, tg, p, pm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, 1, EPI, IO>, ta, tb, tc, th, tg, tg2, p, pm);
     if (e != cudaSuccess) return (int)e;
   }
   cudaError_t e = cudaGetLastError();
@@ -966,9 +988,13 @@ PB_EXPORT int pb_gemm_reduce_scatter(const void* A, const void* B, float* const*
 // SwiGLU: W = W13 [2·FF, colsW] = [gate rows | up rows], C = gate_up [M, 2·FF], H = silu(gate)·up [M, FF].
 // flags: n·4 uint32 in local memory (zeroed here, on the stream). bf16 everywhere, CTA-pair tiles (M > 128).
 // epi = 3 (with b_mn_major = 1): SwiGLU-backward epilogue, W = W2 [dim, FF]; H = the saved gate_up [M, 2·FF] (read), C = d_gate_up.
+// own_resident = 1: W is already complete in w_full (gathered ahead by the previous kernel): no gather, no gating.
+// next_peers != nullptr: additionally gather the weight [next_rows, next_cols] (same n ranks) the NEXT GEMM will consume into
+// next_full — un-gated, complete when this kernel retires.
 PB_EXPORT int pb_gemm_wgather(const void* A, const void* const* w_peers, int n, int rank, void* w_full, uint32_t* flags, void* C,
                               void* H, int M, int rowsW, int colsW, int lda, int ldc, int ldh, int b_mn_major, int epi,
                               const float* rope_cos, const float* rope_sin, int rope_S, int rope_cols, int rope_D,
+                              int own_resident, const void* const* next_peers, void* next_full, int next_rows, int next_cols,
                               cudaStream_t stream) {
   if (n < 1 || n > 8 || rank < 0 || rank >= n || rowsW % n != 0 || colsW % 64 != 0) return -6;
   if ((lda % 8) || (ldc % 8)) return -1;
@@ -991,6 +1017,22 @@ PB_EXPORT int pb_gemm_wgather(const void* A, const void* const* w_peers, int n, 
   pm.cpr = (rpr + 127) / 128;
   pm.col_chunks = colsW / 64;
   pm.spc = (pm.cpr + kGatherSub - 1) / kGatherSub;
+  pm.gate = own_resident ? 0 : 1;
+  CUtensorMap tg2;
+  bool have_next = false;
+  if (next_peers != nullptr && next_full != nullptr && next_rows > 0) {
+    if (next_rows % n != 0 || next_cols % 64 != 0) return -6;
+    const int nrpr = next_rows / n;
+    pm.nn = n;
+    pm.ncpr = (nrpr + 127) / 128;
+    pm.ncol_chunks = next_cols / 64;
+    for (int t = 0; t < n; ++t) pm.norder[t] = (rank + 1 + t) % n;  // remote blocks first (they take longest), own block last
+    int rc2;
+    for (int r = 0; r < n; ++r)
+      if ((rc2 = pbhost::cached_tmap(&pm.nm[r], next_peers[r], (uint64_t)nrpr, (uint64_t)next_cols, (uint64_t)next_cols, BK, 128))) return rc2;
+    if ((rc2 = pbhost::cached_tmap_blocks(&tg2, next_full, (uint64_t)nrpr, (uint64_t)next_cols, (uint64_t)n, BK, 128))) return rc2;
+    have_next = true;
+  }
   if (epi == 2 && n % 2 == 0) {
     // a tile needs gate rows (blocks < n/2) and the matching up rows (blocks >= n/2): fetch them pairwise, own pair first
     const int h = n / 2, g0 = rank % h;
@@ -1005,8 +1047,10 @@ PB_EXPORT int pb_gemm_wgather(const void* A, const void* const* w_peers, int n, 
     if (epi == 2) pm.start = 0;
     else pm.start = b_mn_major ? (rank * rpr) / BK : (rank * rpr) / BN;
   }
-  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)(n * kGatherSub), stream);
-  if (e != cudaSuccess) return (int)e;
+  if (!own_resident) {
+    cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(uint32_t) * (size_t)(n * kGatherSub), stream);
+    if (e != cudaSuccess) return (int)e;
+  }
   int rc;
   for (int r = 0; r < n; ++r)
     if ((rc = pbhost::cached_tmap(&pm.m[r], w_peers[r], (uint64_t)rpr, (uint64_t)colsW, (uint64_t)colsW, BK, 128))) return rc;
@@ -1026,8 +1070,10 @@ PB_EXPORT int pb_gemm_wgather(const void* A, const void* const* w_peers, int n, 
   }
   GemmParams p{M, epi == 2 ? 2 * FF : N, K, ldc, 0, b_mn_major, 0, 0, 1, C, rope_cos, rope_sin, rope_S, rope_cols, rope_D, FF, group_m,
                epi == 3 ? H : nullptr, epi == 3 ? ldh : 0};
-  if (epi == 3) return launch<0, 1, 1, 3, 3>(ta, tb, tc, tc, p, 0, stream, &pm, &tg);
-  if (epi == 2) return launch<0, 0, 1, 2, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg);
-  if (epi == 1) return launch<0, 0, 1, 1, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg);
-  return b_mn_major ? launch<0, 1, 1, 0, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg) : launch<0, 0, 1, 0, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg);
+  const CUtensorMap* tg2p = have_next ? &tg2 : nullptr;
+  if (epi == 3) return launch<0, 1, 1, 3, 3>(ta, tb, tc, tc, p, 0, stream, &pm, &tg, tg2p);
+  if (epi == 2) return launch<0, 0, 1, 2, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg, tg2p);
+  if (epi == 1) return launch<0, 0, 1, 1, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg, tg2p);
+  return b_mn_major ? launch<0, 1, 1, 0, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg, tg2p)
+                    : launch<0, 0, 1, 0, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg, tg2p);
 }

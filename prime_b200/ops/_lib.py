@@ -170,7 +170,7 @@ def _declare(lib: ctypes.CDLL) -> None:
         "pb_grad_reduce_grid": [],
         "pb_grad_reduce": [PP, i64, i64, f32, vp, vp, vp, i32, u32, vp, i32, vp],
         "pb_norm_publish": [vp, i32, PP, PP, i32, i32, u32, vp],
-        "pb_adamw_push": [vp, vp, vp, vp, i64, ctypes.POINTER(AdamArgs), vp, i32, vp, i32, u32, PP, i64, vp, vp, vp],
+        "pb_adamw_push": [vp, vp, vp, vp, i64, ctypes.POINTER(AdamArgs), vp, i32, vp, i32, u32, PP, i64, vp, vp, vp, vp],
         "pb_pseudograd_quant": [vp, vp, vp, vp, i64, vp],
         "pb_outer_nesterov": [PP, PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), PP, vp, vp, i32, vp, vp],
         "pb_outer_nesterov_f32": [PP, vp, vp, vp, i64, ctypes.POINTER(OuterArgs), PP, vp, vp, i32, vp, vp],
@@ -182,7 +182,8 @@ def _declare(lib: ctypes.CDLL) -> None:
         "pb_embedding_sort": [vp, i64, vp, vp],
         "pb_embedding_scatter": [vp, i64, vp, vp, i32, vp],
         "pb_allgather_copy": [PP, i64, vp, vp],
-        "pb_gemm_wgather": [vp, ctypes.POINTER(vp), i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp],
+        "pb_gemm_wgather": [vp, ctypes.POINTER(vp), i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32,
+                            i32, ctypes.POINTER(vp), vp, i32, i32, vp],
         "pb_cast_push": [vp, i64, PP, i64, vp],
         # NVLS: VMM allocations shared by fd, multicast objects, multimem kernels (csrc/multicast.cu)
         "pb_mc_supported": [i32],

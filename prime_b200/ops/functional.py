@@ -113,14 +113,42 @@ def _wgrad(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor) -> torch.T
     return gemm(dy2, x2, a_mn_major=True, b_mn_major=True)
 
 
+# Which weight currently sits, complete, in each gather scratch region: full_ptr → (id of the RowShard, shard version).
+# Everything runs on one stream in program order, so "the kernel that gathers it has been enqueued" is all that needs tracking.
+_RESIDENT: dict[int, tuple[int, int]] = {}
+
+
+def reset_gather_cache() -> None:
+    """Forget what the gather scratch holds (CUDA-graph capture: a captured micro-step must not depend on what an earlier
+    micro-step happened to leave resident; engine construction / teardown)."""
+    _RESIDENT.clear()
+
+
+def _resident(z) -> bool:
+    return z.full_ptr != 0 and _RESIDENT.get(z.full_ptr) == (id(z), z.ver[0])
+
+
+def _mark_resident(z) -> None:
+    _RESIDENT[z.full_ptr] = (id(z), z.ver[0])
+
+
+def _full_weight(z, device) -> torch.Tensor:
+    if z.full is not None:
+        return z.full
+    return torch.as_tensor(_RawBuffer(z.full_ptr, z.rows * z.cols * 2), device=device).view(torch.bfloat16).view(z.rows, z.cols)
+
+
 def gemm_wgather(a: torch.Tensor, z, *, b_mn_major: bool = False, out: torch.Tensor | None = None, rope: tuple | None = None,
                  swiglu_h: torch.Tensor | None = None, swiglu_bwd_gu: torch.Tensor | None = None) -> torch.Tensor:  # fmt: skip
     """Parameter all-gather ⊕ GEMM (ZeRO-3): ``z`` is the ``RowShard`` of a weight W [rows, cols] sharded by rows over the FSDP group.
 
     ``b_mn_major=False``: C[M, rows] = a[M, cols]·Wᵀ (forward; ``rope`` = RoPE epilogue, ``swiglu_h`` = SwiGLU epilogue with W = W13,
     C = gate_up, ``swiglu_h`` = h).  ``b_mn_major=True``: C[M, cols] = a[M, rows]·W (input gradient; with ``swiglu_bwd_gu`` = the
-    saved gate_up the epilogue turns dh into d_gate_up [M, 2·cols] on the fly).  The peers' row blocks are
-    pulled over NVLink by copier warps INSIDE the GEMM kernel (csrc/gemm_sm100.cu, IO = 3); nothing is gathered beforehand."""
+    saved gate_up the epilogue turns dh into d_gate_up [M, 2·cols] on the fly).
+
+    The peers' row blocks are pulled over NVLink by copier warps INSIDE the GEMM kernel (csrc/gemm_sm100.cu, IO = 3). The same
+    kernel also gathers AHEAD the weight the next GEMM of the pass will consume (``z.next_fwd`` / ``z.next_bwd``), so in steady
+    state a kernel finds its own operand already resident (no gating, full speed) and only carries the next one's transfer."""
     import ctypes
 
     assert a.dtype == torch.bfloat16 and a.dim() == 2 and a.stride(1) == 1
@@ -131,21 +159,40 @@ def gemm_wgather(a: torch.Tensor, z, *, b_mn_major: bool = False, out: torch.Ten
         out = torch.empty((M, 2 * N if swiglu_bwd_gu is not None else N), dtype=torch.bfloat16, device=a.device)
     lib = _lib.load()
     epi = 3 if swiglu_bwd_gu is not None else (2 if swiglu_h is not None else (1 if rope is not None else 0))
-    if M <= 128:
-        # tiny M (unit tests, debug models): explicit gather by peer loads, then the plain kernels
-        pp = _lib.PeerPtrs.of(z.peer_ptrs[i] for i in range(z.n))
-        _lib.check(lib.pb_allgather_copy(ctypes.byref(pp), z.rpr * z.cols * 2, z.full_ptr, _stream()), "pb_allgather_copy")
-        _count()
-        w = torch.as_tensor(_RawBuffer(z.full_ptr, z.rows * z.cols * 2), device=a.device).view(torch.bfloat16).view(z.rows, z.cols)
-        if epi == 3:
-            dh = gemm(a, w, b_mn_major=True)
-            _lib.check(lib.pb_swiglu_bwd(swiglu_bwd_gu.data_ptr(), dh.data_ptr(), out.data_ptr(), M, z.cols, _stream()), "pb_swiglu_bwd")
+    own_resident = _resident(z)
+    nz = z.next_bwd if b_mn_major else z.next_fwd
+    if nz is not None and (nz.full_ptr == 0 or _resident(nz) or nz.n != z.n):
+        nz = None
+    if M <= 128 or (own_resident and nz is None):
+        # operand complete in the local scratch (gathered ahead by the previous kernel), or tiny M (unit tests, debug models: explicit
+        # gather by peer loads first): the plain kernels
+        if not own_resident:
+            pp = _lib.PeerPtrs.of(z.peer_ptrs[i] for i in range(z.n))
+            _lib.check(lib.pb_allgather_copy(ctypes.byref(pp), z.rpr * z.cols * 2, z.full_ptr, _stream()), "pb_allgather_copy")
             _count()
+            _mark_resident(z)
+        w = _full_weight(z, a.device)
+        if epi == 3:
+            if M > 128:
+                rc = lib.pb_gemm_bf16_swiglu_bwd(a.data_ptr(), w.data_ptr(), swiglu_bwd_gu.data_ptr(), out.data_ptr(), M, z.cols, z.rows,
+                                                 a.stride(0), w.stride(0), swiglu_bwd_gu.stride(0), out.stride(0), _stream())  # fmt: skip
+                _lib.check(rc, "pb_gemm_bf16_swiglu_bwd")
+                _count()
+            else:
+                dh = gemm(a, w, b_mn_major=True)
+                _lib.check(lib.pb_swiglu_bwd(swiglu_bwd_gu.data_ptr(), dh.data_ptr(), out.data_ptr(), M, z.cols, _stream()), "pb_swiglu_bwd")
+                _count()
         elif epi == 2:
             FF = z.rows // 2
-            gemm(a, w, out=out)
-            _lib.check(lib.pb_swiglu_fwd(out.data_ptr(), swiglu_h.data_ptr(), M, FF, _stream()), "pb_swiglu_fwd")
-            _count()
+            if M > 128 and FF % 64 == 0:
+                rc = lib.pb_gemm_bf16_swiglu(a.data_ptr(), w.data_ptr(), out.data_ptr(), swiglu_h.data_ptr(), M, FF, z.cols, a.stride(0),
+                                             w.stride(0), out.stride(0), swiglu_h.stride(0), _stream())  # fmt: skip
+                _lib.check(rc, "pb_gemm_bf16_swiglu")
+                _count()
+            else:
+                gemm(a, w, out=out)
+                _lib.check(lib.pb_swiglu_fwd(out.data_ptr(), swiglu_h.data_ptr(), M, FF, _stream()), "pb_swiglu_fwd")
+                _count()
         elif epi == 1:
             cos, sin, seq_len, rot_cols, head_dim = rope
             rc = lib.pb_gemm_bf16_rope(a.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, a.shape[1], a.stride(0), w.stride(0), out.stride(0), 0,
@@ -164,10 +211,15 @@ def gemm_wgather(a: torch.Tensor, z, *, b_mn_major: bool = False, out: torch.Ten
     rc = lib.pb_gemm_wgather(
         a.data_ptr(), z.peer_ptrs, z.n, z.rank, z.full_ptr, z.flags.data_ptr(), out.data_ptr(), _ptr(aux), M, z.rows, z.cols,
         a.stride(0), out.stride(0), aux.stride(0) if aux is not None else 0, int(b_mn_major), epi,
-        _ptr(cos), _ptr(sin), seq_len, rot_cols, head_dim, _stream(),
+        _ptr(cos), _ptr(sin), seq_len, rot_cols, head_dim,
+        int(own_resident), nz.peer_ptrs if nz is not None else None, nz.full_ptr if nz is not None else None,
+        nz.rows if nz is not None else 0, nz.cols if nz is not None else 0, _stream(),
     )  # fmt: skip
     _lib.check(rc, "pb_gemm_wgather")
-    _count(2)
+    _count(1 if own_resident else 2)
+    _mark_resident(z)
+    if nz is not None:
+        _mark_resident(nz)
     return out
 
 
@@ -387,7 +439,7 @@ class _EmbeddingFn(torch.autograd.Function):
         _count()
         ctx.weight = weight
         ctx.sorted_ev = None
-        if torch.is_grad_enabled() and weight.requires_grad:
+        if ctx.needs_input_grad[1]:  # (autograd runs forward() with grad mode off: needs_input_grad is the reliable signal)
             # the backward needs the positions sorted by token: a one-CTA kernel (~0.2 ms) that depends only on the token ids, so it
             # runs NOW on a side stream underneath the forward GEMMs instead of on the critical path at the end of the backward
             sorted_keys = torch.empty(t.numel(), dtype=torch.int64, device=weight.device)
@@ -409,6 +461,8 @@ class _EmbeddingFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout: torch.Tensor):
         lib = _lib.load()
+        if not ctx.saved_tensors:
+            return None, None
         (sorted_keys,) = ctx.saved_tensors
         weight = ctx.weight
         V, dim = weight.shape

@@ -129,6 +129,8 @@ class DilocoOuter:
             ev[1].record()
             self._ev = ev
         self.outer_step_count += 1
+        if hasattr(self.engine, "_pver"):
+            self.engine._pver[0] += 1  # the bf16 parameters changed: gathered scratch copies of the ZeRO-3 path are stale
         self.last_seconds = time.perf_counter() - t0
 
     def _harvest(self) -> None:

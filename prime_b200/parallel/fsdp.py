@@ -76,6 +76,12 @@ class RowShard:
     full_ptr: int  # local [rows, cols] scratch the kernel gathers into (== the parameter tensor's storage)
     flags: torch.Tensor  # n * 4 readiness counters (zeroed by the launcher)
     shard: torch.Tensor  # this rank's [rpr, cols] block (view into the engine's bf16 shard buffer)
+    full: torch.Tensor | None = None  # the scratch as a [rows, cols] tensor (plain kernels run on it when the weight is resident)
+    # gather-ahead chain: the weight the NEXT GEMM of the pass consumes (forward order / backward dgrad order); the kernel that
+    # computes with this weight also pulls that one into its scratch (ops.functional.gemm_wgather)
+    next_fwd: "RowShard | None" = None
+    next_bwd: "RowShard | None" = None
+    ver: list = field(default_factory=lambda: [0])  # shared with the engine: bumped whenever the shards change (optimizer / outer step)
 
 
 class _Boundary(torch.autograd.Function):
@@ -136,6 +142,7 @@ class ShardedEngine:
         self.last_grad_norm: torch.Tensor | None = None
         self._last_micro = True
         self._epoch = 0
+        self._pver = [0]  # parameter-shard version: bumped whenever the bf16 shards change (gathered scratch copies go stale)
         self.capture_mode = False  # True while a CUDA graph of the micro-step is captured/replayed: no comm in backward
         self.trace = None  # optional StepTrace (utils/steptrace.py): CUDA events around the phases of the step
         if self.device.type == "cuda":
@@ -143,6 +150,9 @@ class ShardedEngine:
             self.comm_stream = torch.cuda.Stream(device=self.device) if overlap else None
         else:
             self.lib, self.comm_stream = None, None
+        from ..ops.functional import reset_gather_cache
+
+        reset_gather_cache()
         self._build_buckets()
         self._allocate()
         self._install_hooks()
@@ -280,6 +290,25 @@ class ShardedEngine:
         # reduced gradient shard; with F == 1 the shard *is* the bucket, so alias instead of copying
         self.gshard = self.grad_flat if F == 1 else torch.zeros(self.shard_total, dtype=torch.float32, device=dev)
         self._params = [p for b in self.buckets for _, p, _ in b.params]
+        if self.shard_params:
+            self._link_gather_chain()
+
+    def _link_gather_chain(self) -> None:
+        """Order in which the GEMMs consume the sharded weights: forward wqkv → wo → w13 → w2 per layer, then the head; backward
+        (input gradients) the reverse. Each weight points at its successor so the kernel computing with it can gather that one ahead."""
+        m = self.model
+        if not (hasattr(m, "layers") and hasattr(m, "output")):
+            return
+        seq = []
+        for layer in m.layers:
+            seq += [layer.attention.wqkv, layer.attention.wo, layer.feed_forward.w13, layer.feed_forward.w2]
+        seq.append(m.output)
+        zs = [getattr(p, "z3", None) for p in seq]
+        if any(z is None for z in zs):
+            return
+        for a, b in zip(zs[:-1], zs[1:]):
+            a.next_fwd = b
+            b.next_bwd = a
 
     def _attach_rows_bucket(self, b: Bucket) -> None:
         """ZeRO-3: copy this rank's row block of every weight into the shard buffer, then re-point the parameter at the shared
@@ -304,7 +333,8 @@ class ShardedEngine:
             peers = (ctypes.c_void_p * F)(*[heap.peer_ptr(q, shard) for q in ranks])
             p.data = full
             p.main_grad = self.grad_flat[b.start + off : b.start + off + p.numel()].view(p.shape)
-            p.z3 = RowShard(rows, cols, F, r, rpr, peers, full_ptr, self._gather_flags, shard)
+            p.z3 = RowShard(rows, cols, F, r, rpr, peers, full_ptr, self._gather_flags, shard, full=full if b.name != "embed" else None,
+                            ver=self._pver)
             segs.append((b.start + off + r * piece, lo, piece))
         b.segs = _lib.SegTable.of(segs)
 
@@ -424,6 +454,19 @@ class ShardedEngine:
                     _count()
                     wait_flags = self.heap.flags.data_ptr()
                 ctas = self.reduce_ctas if (F > 1 and self.overlap) else 0
+                if b.kind == "rows" and self._nvls:  # ZeRO-3 + NVLS: each parameter's row block is summed inside the switch
+                    segs = b.segs
+                    for i in range(segs.nseg):
+                        _lib.check(
+                            self.lib.pb_mc_grad_reduce(
+                                self.heap.mc_ptr(self.grad_flat), segs.src_off[i], segs.n[i], 1.0 / F, self.gshard[segs.dst_off[i] :].data_ptr(),
+                                self.sumsq_partial.data_ptr(), wait_flags if i == 0 else None, slot_base, self._epoch, F,
+                                self.heap.err.data_ptr(), self.reduce_ctas if self.overlap else 0, s,
+                            ),
+                            "pb_mc_grad_reduce",
+                        )  # fmt: skip
+                    _count(segs.nseg)
+                    return
                 if b.kind == "rows":  # ZeRO-3 bucket: one row block per parameter
                     gp = self.heap.peers(ranks, self.grad_flat)
                     _lib.check(
@@ -498,6 +541,7 @@ class ShardedEngine:
             self._step_collective(lr, bc1, bc2)
         for b in self.buckets:
             b.ready, b.work = False, None
+        self._pver[0] += 1
 
     def _param_dst(self, b: Bucket) -> tuple[_lib.PeerPtrs, int]:
         """Where the bf16 image of bucket ``b``'s master shard goes: (destination buffers, element offset)."""
@@ -550,7 +594,9 @@ class ShardedEngine:
                         self.master[sl].data_ptr(), g.data_ptr(), self.exp_avg[sl].data_ptr(), self.exp_avg_sq[sl].data_ptr(),
                         b.shard_size, ctypes.byref(args), heap.norm_slots.data_ptr(), F, heap.flags.data_ptr(),
                         self.slot_norm, self._epoch, ctypes.byref(dst), dst_off,
-                        self.gnorm_buf.data_ptr(), heap.err.data_ptr(), s,
+                        self.gnorm_buf.data_ptr(), heap.err.data_ptr(),
+                        # NVLS heap spanning exactly this FSDP group: the all-gather is ONE multicast store per 16 bytes
+                        heap.mc_ptr(self.param_flat) if (self._nvls and b.kind == "flat") else None, s,
                     ),
                     "pb_adamw_push",
                 )  # fmt: skip
@@ -588,6 +634,7 @@ class ShardedEngine:
     def publish_params(self) -> None:
         """fp32 master shard → parameter buffers of the whole FSDP group (cast + all-gather; ZeRO-3: cast into the local shard)."""
         F, r = self.F, self.mesh.fsdp_rank
+        self._pver[0] += 1
         if self.backend == "fused":
             main = torch.cuda.current_stream()
             ranks = self.mesh.fsdp_ranks

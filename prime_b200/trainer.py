@@ -138,6 +138,7 @@ class Trainer:
         scale = 1.0 / self.accum
 
         def micro() -> torch.Tensor:
+            ops.reset_gather_cache()  # ZeRO-3: a captured micro-step gathers every weight itself, whatever ran before it
             loss = self.model.loss(self._g_tokens, self._g_labels, grad_scale=scale, loss_acc=self._loss_acc)
             loss.backward()
             eng.fold_micro_grads()
@@ -179,6 +180,10 @@ class Trainer:
                 self._g_labels.copy_(batch.labels, non_blocking=True)
                 self._graph.replay()
                 _count_launches(self._graph_launches)
+                if eng.shard_params:
+                    from . import ops as _ops
+
+                    _ops.reset_gather_cache()
                 loss = self._g_loss
                 if last:
                     eng.finish_backward()

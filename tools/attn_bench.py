@@ -32,6 +32,10 @@ def timeit(fn, iters=10, warm=3, flush=None):
 def main():
     dev = torch.device("cuda", 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    from prime_b200.utils.clocks import ClockSampler
+
+    sampler = ClockSampler(0, period_s=0.05)
+    sampler.start()
     rows = []
     for name, B, S, H, Hkv, D in [("1B mb16", 16, 1024, 16, 16, 128), ("7B-like", 8, 2048, 32, 32, 128), ("150M", 16, 1024, 16, 16, 64)]:
         W = (H + 2 * Hkv) * D
@@ -67,7 +71,8 @@ def main():
                      "sdpa_bwd_tflops": round(2.5 * fl_f / (rboth - rfwd) / 1e9, 1)})  # fmt: skip
         print(rows[-1], flush=True)
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / "attn_bench.json").write_text(json.dumps(rows, indent=1))
+    (ROOT / "gpurun_out" / "attn_bench.json").write_text(json.dumps({"rows": rows, "clocks": sampler.finish(),
+                                                                      "timing": "CUDA events, median, 256 MB L2 flush between iterations; same process for both arms"}, indent=1))
 
 
 if __name__ == "__main__":

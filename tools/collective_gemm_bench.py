@@ -48,6 +48,11 @@ def main():
     heap = SymmetricHeap(2 << 30, r, n, dist_exchange(), dev)
     cg = CollectiveGemm(heap, list(range(n)))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    from prime_b200.utils.clocks import ClockSampler
+
+    sampler = ClockSampler(torch.cuda.current_device(), period_s=0.05)
+    if r == 0:
+        sampler.start()
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     peak = float(peaks.get("bf16_tflops_sustained", 1386.0)) * 1e12
     T, D, FF = 16384, 2048, 5632
@@ -95,7 +100,7 @@ def main():
                  "roofline_ms": round(max(fl / peak, remote / 900e9) * 1e3, 4)})  # fmt: skip
     heap.check_errors()
     if r == 0:
-        print(json.dumps({"n_gpus": n, "rows": rows}, indent=1))
+        print(json.dumps({"n_gpus": n, "rows": rows, "clocks": sampler.finish()}, indent=1))
     dist.barrier()
     heap.close()
     dist.destroy_process_group()

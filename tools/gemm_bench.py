@@ -39,6 +39,10 @@ def main():
         pass
     peak = peaks.get("bf16_tflops", 1590.0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    from prime_b200.utils.clocks import ClockSampler
+
+    sampler = ClockSampler(0, period_s=0.05)
+    sampler.start()
     T = 16384
     shapes = [
         ("qkv fwd", T, 6144, 2048, False, False),
@@ -67,7 +71,8 @@ def main():
         print(rows[-1], flush=True)
     out_dir = ROOT / "gpurun_out"
     out_dir.mkdir(exist_ok=True)
-    (out_dir / "gemm_bench.json").write_text(json.dumps(rows, indent=1))
+    (out_dir / "gemm_bench.json").write_text(json.dumps({"rows": rows, "clocks": sampler.finish(), "peak_used_tflops": peak,
+                                                         "timing": "CUDA events, median of 10, 256 MB L2 flush between iterations"}, indent=1))
 
 
 if __name__ == "__main__":

@@ -61,6 +61,11 @@ def main():
     heap = MulticastHeap((a.max_mib * 2 + 64) << 20, r, n, dist_exchange(), dev)
     lib = _lib.load()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    from prime_b200.utils.clocks import ClockSampler
+
+    sampler = ClockSampler(torch.cuda.current_device(), period_s=0.05)
+    if r == 0:
+        sampler.start()
     stream = torch.cuda.current_stream().cuda_stream
     grid = lib.pb_grad_reduce_grid()
     rows = []
@@ -96,7 +101,8 @@ def main():
         heap._cursor = heap.offset_of(x32)  # bump allocator: give the block back before the next size
         mib *= 4
     if r == 0 and a.out:
-        Path(a.out).write_text(json.dumps({"rows": rows, "note": "device-timed, max over ranks, median of 10, L2 flushed"}, indent=1))
+        Path(a.out).write_text(json.dumps({"rows": rows, "clocks": sampler.finish(),
+                                           "note": "device-timed, max over ranks, median of 10, L2 flushed"}, indent=1))
     dist.barrier()
     heap.close()
     dist.destroy_process_group()

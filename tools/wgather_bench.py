@@ -117,7 +117,7 @@ def main():
                      "nccl_allgather_plus_gemm_ms": round(t_n, 4), "fused_tflops": round(fl / t_f / 1e9, 1),
                      "gather_cost_vs_resident": round(t_f / t_l, 3), "speedup_vs_nccl": round(t_n / t_f, 3),
                      "remote_MB": round(remote / 1e6, 1), "remote_GBps_if_serial": round(remote / t_f / 1e6, 1),
-                     "roofline_ms": round(roof * 1e3, 4), "achieved_over_roofline": round(t_f / roof, 3)})  # fmt: skip
+                     "roofline_ms": round(roof * 1e3, 4), "achieved_over_roofline": round(t_f / 1e3 / roof, 3)})  # fmt: skip
         del z, s, full
 
     bench("wqkv", 3 * D, D, "fwd")
