@@ -138,7 +138,10 @@ def main() -> None:
         "name_model": args.model,
         "type_model": "llama2",
         "data": {"seq_length": seq, "fake": True},
-        "optim": {"batch_size": micro_bs * accum * fsdp, "warmup_steps": 10, "total_steps": 100000, "optim": {"lr": 4e-4}},
+        # a randomly initialised 7B model diverges within ten steps of a 10-step ramp to 4e-4 (seen: NaN at step 8 on 4 GPUs); the
+        # throughput does not depend on the learning rate, so the large models ramp over 1000 steps like their configs/ files
+        "optim": {"batch_size": micro_bs * accum * fsdp, "warmup_steps": 10 if args.model in ("150M", "1B") else 1000, "total_steps": 100000,
+                  "optim": {"lr": 4e-4 if args.model in ("150M", "1B") else 3e-4}},
         "train": {"micro_bs": micro_bs, "fused_comm": not args.no_fused_comm, "attn_impl": args.attn, "cuda_graphs": bool(args.graphs),
                   "fp8": args.fp8, "reshard_after_forward": None if args.reshard == "auto" else bool(int(args.reshard))},
         "mesh": {"num_workers": workers, "fsdp_size": fsdp},
@@ -159,6 +162,8 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    losses: list[float] = []
+
     def run_region(n_steps: int, read_loss: bool) -> tuple[float, float, int]:
         """Returns (device ms, host s, launches) for n_steps inner steps incl. >= 1 outer step."""
         sync_all()
@@ -175,6 +180,7 @@ def main() -> None:
                 trainer.outer.step()
             if read_loss:
                 last = float(r.loss.item())  # device→host read of the step result, every step
+                losses.append(round(last, 4))
         e1.record()
         sync_all()
         host = time.perf_counter() - t0
@@ -291,6 +297,7 @@ def main() -> None:
                 "ms_per_step": round(max(e2e_host_s * 1e3, e2e_ms) / K, 3),
             },
             "gpu_launches": launches,
+            "losses_e2e_region": losses,
             "outer_allreduce": outer_info,
             "outer_allreduce_GBps": outer_info["GBps"] if outer_info else None,
             "mfu_of_measured_sustained_peak": None,
