@@ -255,6 +255,8 @@ class B0Trainer:
         W = cfg.workers
         cuda = self.device.type == "cuda"
         if cuda:
+            if self.world > 1:
+                dist.barrier()  # line the ranks up: arrival skew between workers is not part of the exchange time (same as the engine arm)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         params = [self._local(p) for p in self.model.parameters()]

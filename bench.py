@@ -224,10 +224,16 @@ def main() -> None:
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         osec = float(t.item())
+        skew = torch.tensor([trainer.outer.mean_skew_seconds()], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(skew, op=dist.ReduceOp.MAX)
         wire = trainer.outer.last_bytes_on_wire
         shard_elems = trainer.engine.shard_total
         outer_info = {
             "ms": round(osec * 1e3, 4),
+            # device time the slowest-waiting rank spent at the alignment barrier IN FRONT of the timed window (workers drift apart
+            # over the inner steps; that wait is arrival skew, not exchange time — it is inside `value`, outside `ms`)
+            "arrival_skew_ms": round(float(skew.item()) * 1e3, 4),
             "bytes_on_wire_per_rank": wire,
             # bytes a rank must RECEIVE from the other workers (int8 payload + one fp32 scale per 1024) over the device time of the
             # whole fused outer step (quantise + barrier + peer loads ⊕ dequant-sum ⊕ Nesterov ⊕ bf16 write-back + barrier)

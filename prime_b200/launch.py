@@ -226,6 +226,47 @@ def free_port() -> int:
         return s.getsockname()[1]
 
 
+def descendants(pid: int) -> list[int]:
+    """Every live descendant of ``pid`` (children first). torchrun starts its ranks in their OWN sessions, so a signal to the
+    launcher's process group does not reach them: a SIGKILL of "the worker" has to walk the tree (seen on the 8-GPU box: killpg
+    took torchrun down, the ranks trained on as orphans next to their respawned successors)."""
+    try:
+        import psutil
+
+        return [c.pid for c in psutil.Process(pid).children(recursive=True)]
+    except Exception:  # noqa: BLE001 — psutil missing or the process is already gone: fall back to /proc
+        kids: dict[int, list[int]] = {}
+        for d in os.listdir("/proc"):
+            if d.isdigit():
+                try:
+                    with open(f"/proc/{d}/stat") as f:
+                        ppid = int(f.read().rsplit(")", 1)[1].split()[1])
+                    kids.setdefault(ppid, []).append(int(d))
+                except (OSError, ValueError, IndexError):
+                    pass
+        out, todo = [], [pid]
+        while todo:
+            for c in kids.get(todo.pop(), []):
+                out.append(c)
+                todo.append(c)
+        return out
+
+
+def signal_tree(pid: int, sig: int) -> None:
+    """Deliver ``sig`` to the process group of ``pid`` AND to every descendant (collected first: they re-parent once the root dies).
+    SIGTERM is forwarded by torchrun itself, so only the hard kill really needs the walk — doing it for both keeps one code path."""
+    tree = descendants(pid) if sig == signal.SIGKILL else []
+    try:
+        os.killpg(pid, sig)
+    except (ProcessLookupError, PermissionError):
+        pass
+    for c in tree:
+        try:
+            os.kill(c, sig)
+        except (ProcessLookupError, PermissionError):
+            pass
+
+
 def gpu_slices(workers: int, per_worker: int, pool: str | None) -> list[str | None]:
     """``CUDA_VISIBLE_DEVICES`` for each worker: consecutive slices of the visible pool (or of 0..N-1)."""
     if per_worker <= 0 or workers <= 1:
@@ -274,10 +315,7 @@ class _Worker:
 
     def signal(self, sig: int) -> None:
         if self.proc is not None and self.proc.poll() is None:
-            try:
-                os.killpg(self.proc.pid, sig)
-            except ProcessLookupError:
-                pass
+            signal_tree(self.proc.pid, sig)
 
     def snapshot(self) -> dict[str, Any]:
         return {"name": self.name, "pid": self.proc.pid if self.proc else None, "starts": self.starts, "exit_code": self.exit_code}
@@ -422,7 +460,7 @@ def stop_run(run: Run, *, force: bool = False, wait_s: float = 120.0) -> dict[st
             for w in st.get("workers", []):
                 if w.get("pid") and w.get("exit_code") is None:
                     try:
-                        os.killpg(w["pid"], signal.SIGKILL)
+                        signal_tree(w["pid"], signal.SIGKILL)
                     except (ProcessLookupError, PermissionError):
                         pass
     t0 = time.monotonic()

@@ -66,6 +66,8 @@ class DilocoOuter:
         self.last_seconds = 0.0  # host wall clock of the last step() call (enqueue time on CUDA: use device_seconds())
         self._ev: tuple | None = None
         self.total_device_ms = 0.0
+        self.total_skew_ms = 0.0
+        self._pre = None
         self.timed_steps = 0
         # ``collective=True``: the exchange goes through a (re-creatable) process group instead of the symmetric heap
         self.fused = engine.backend == "fused" and not collective
@@ -83,6 +85,7 @@ class DilocoOuter:
             world = heap.world_size
             self.slot_bar = heap.alloc_flags(world)
             self.slot_bar2 = heap.alloc_flags(world)
+            self.slot_align = heap.alloc_flags(world)
             self._epoch = 0
             if hyper.compression == "int8":
                 self.q = heap.alloc(n, torch.int8)
@@ -118,6 +121,15 @@ class DilocoOuter:
             else:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             self._harvest()
+            if self.fused and self.engine.heap.world_size > 1:
+                # line the ranks up first: workers drift apart over H inner steps, and the time a fast rank spends waiting for the
+                # slowest one is arrival skew, not part of the exchange — it is timed separately (``last_skew_seconds``)
+                pre = torch.cuda.Event(enable_timing=True)
+                pre.record()
+                self._epoch += 1
+                self.engine.heap.barrier(list(range(self.engine.heap.world_size)), self.slot_align, self._epoch,
+                                         torch.cuda.current_stream().cuda_stream)
+                self._pre = pre
             ev[0].record()
         if self.exchange is not None:
             self._step_exchange()
@@ -137,6 +149,9 @@ class DilocoOuter:
         if self._ev is not None:
             self._ev[1].synchronize()
             self.total_device_ms += self._ev[0].elapsed_time(self._ev[1])
+            if getattr(self, "_pre", None) is not None:
+                self.total_skew_ms += self._pre.elapsed_time(self._ev[0])
+                self._pre = None
             self.timed_steps += 1
             self._ev = None
 
@@ -149,7 +164,12 @@ class DilocoOuter:
 
     def reset_timing(self) -> None:
         self._harvest()
-        self.total_device_ms, self.timed_steps = 0.0, 0
+        self.total_device_ms, self.total_skew_ms, self.timed_steps = 0.0, 0.0, 0
+
+    def mean_skew_seconds(self) -> float:
+        """Mean device time a rank waited at the alignment barrier in front of the outer step (arrival skew between workers)."""
+        self._harvest()
+        return self.total_skew_ms / 1e3 / max(1, self.timed_steps)
 
     def mean_device_seconds(self) -> float:
         self._harvest()

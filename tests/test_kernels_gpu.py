@@ -708,3 +708,87 @@ def test_mlp_swiglu_fused_backward(M, D, FF):
     y2.backward(dy)
     assert torch.equal(y, y2)
     assert _rel_err(x.grad, x2.grad) < 4e-3 and _rel_err(w13.grad, w13b.grad) < 4e-3
+
+
+@pytest.mark.parametrize("mode", ["fwd", "dgrad", "swiglu", "swiglu_bwd", "rope", "ahead"])
+def test_weight_gather_gemm_single_rank(mode):
+    """IO = 3 (parameter all-gather ⊕ GEMM) with a 1-rank group: the copier, the readiness counters, the gated TMA producer, the
+    rotated tile / K order and the gather-ahead list all run (the "peer" is this GPU), so the ZeRO-3 kernel is covered on a
+    single-GPU box and under compute-sanitizer; the multi-GPU variants live in tests/test_multigpu.py."""
+    import ctypes
+
+    from prime_b200 import ops
+    from prime_b200.ops import reference
+    from prime_b200.parallel.fsdp import RowShard
+    from prime_b200.parallel.symm import SymmetricHeap
+
+    dev = _dev()
+    heap = SymmetricHeap(256 << 20, 0, 1, lambda h: [h], dev)
+    torch.manual_seed(17)
+    M, K = 768, 512
+
+    def shard(W):
+        rows, cols = W.shape
+        sh = heap.alloc(rows * cols, torch.bfloat16).view(rows, cols)
+        sh.copy_(W)
+        full = torch.zeros(rows, cols, dtype=torch.bfloat16, device=dev)
+        flags = torch.zeros(64, dtype=torch.int32, device=dev)
+        peers = (ctypes.c_void_p * 1)(heap.peer_ptr(0, sh))
+        return RowShard(rows, cols, 1, 0, rows, peers, full.data_ptr(), flags, sh, full=full), full
+
+    x = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
+    try:
+        if mode in ("fwd", "dgrad", "ahead"):
+            W = (torch.randn(1088, K, device=dev) * 0.05).to(torch.bfloat16)  # 1088 rows: the last 128-row box is clipped
+            z, full = shard(W)
+            if mode == "fwd":
+                y = ops.gemm_wgather(x, z)
+                ref = x.float() @ W.float().t()
+            elif mode == "dgrad":
+                dy = (torch.randn(M, 1088, device=dev) * 0.5).to(torch.bfloat16)
+                y = ops.gemm_wgather(dy, z, b_mn_major=True)
+                ref = dy.float() @ W.float()
+            else:
+                W2 = (torch.randn(640, 1088, device=dev) * 0.05).to(torch.bfloat16)
+                z2, full2 = shard(W2)
+                z.next_fwd = z2
+                y1 = ops.gemm_wgather(x, z)
+                torch.cuda.synchronize()
+                assert torch.equal(full2, W2) and ops.functional._resident(z2)  # gathered ahead by the first kernel
+                y = ops.gemm_wgather(y1, z2)  # resident: plain kernel
+                ref = y1.float() @ W2.float().t()
+            assert torch.equal(full, W)
+        elif mode in ("swiglu", "swiglu_bwd"):
+            FF = 576
+            W13 = (torch.randn(2 * FF, K, device=dev) * 0.05).to(torch.bfloat16)
+            z13, _ = shard(W13)
+            gu = torch.empty(M, 2 * FF, dtype=torch.bfloat16, device=dev)
+            h = torch.empty(M, FF, dtype=torch.bfloat16, device=dev)
+            ops.gemm_wgather(x, z13, out=gu, swiglu_h=h)
+            gur = (x.float() @ W13.float().t()).to(torch.bfloat16).float()
+            if mode == "swiglu":
+                y, ref = h, torch.nn.functional.silu(gur[:, :FF]) * gur[:, FF:]
+                assert _rel_err(gu, gur) < 1e-2
+            else:
+                W2 = (torch.randn(K, FF, device=dev) * 0.05).to(torch.bfloat16)
+                z2, _ = shard(W2)
+                dy = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
+                y = ops.gemm_wgather(dy, z2, b_mn_major=True, swiglu_bwd_gu=gu)
+                dh = dy.float() @ W2.float()
+                g, u = gu[:, :FF].float(), gu[:, FF:].float()
+                sg = torch.sigmoid(g)
+                ref = torch.cat((dh * u * sg * (1 + g * (1 - sg)), dh * g * sg), dim=1)
+        else:
+            H, D, S = 2, 128, 256
+            Wq = (torch.randn(3 * H * D, K, device=dev) * 0.05).to(torch.bfloat16)
+            zq, _ = shard(Wq)
+            cos, sin = reference.rope_tables(S, D, 10000.0, device=dev)
+            y = ops.gemm_wgather(x, zq, rope=(cos, sin, S, 2 * H * D, D))
+            r = (x.float() @ Wq.float().t()).view(-1, S, 3 * H, D)
+            ref = torch.cat((reference.rope(r[:, :, : 2 * H], cos, sin), r[:, :, 2 * H :]), dim=2).reshape(M, -1)
+        torch.cuda.synchronize()
+        heap.check_errors()
+        assert _rel_err(y, ref) < 1e-2 and _max_rel(y, ref) < 5e-2
+    finally:
+        ops.reset_gather_cache()
+        heap.close()

@@ -1,0 +1,73 @@
+"""Diagnostic: run a few steps of a large model in replicated-parameter mode and report, per step, loss / grad-norm and the first
+bucket whose gradient, master or bf16 parameter buffer contains a non-finite value.
+
+    python tools/debug_7b.py --model 7B --seq 2048 --micro-bs 1 --steps 4            # 1 GPU (F = 1, fused backend)
+    torchrun --nproc-per-node 2 tools/debug_7b.py --model 7B --fsdp 2 ...
+"""
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from prime_b200.config import Config  # noqa: E402
+from prime_b200.trainer import Trainer  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="7B")
+    ap.add_argument("--seq", type=int, default=2048)
+    ap.add_argument("--micro-bs", type=int, default=1)
+    ap.add_argument("--accum", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--fsdp", type=int, default=0)
+    ap.add_argument("--reshard", type=int, default=0)
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    F = a.fsdp or world
+    cfg = Config.model_validate({
+        "name_model": a.model, "data": {"seq_length": a.seq, "fake": True},
+        "optim": {"batch_size": a.micro_bs * a.accum * F, "warmup_steps": 1000, "optim": {"lr": 3e-4}},
+        "train": {"micro_bs": a.micro_bs, "reshard_after_forward": bool(a.reshard)}, "mesh": {"num_workers": world // F, "fsdp_size": F},
+    })  # fmt: skip
+    t = Trainer(cfg)
+    eng = t.engine
+    rank = t.mesh.world.rank
+    rows = []
+    for step in range(a.steps):
+        r = t.inner_step()
+        torch.cuda.synchronize()
+        row = {"step": step + 1, "loss": float(r.loss), "gnorm": float(r.grad_norm)}
+        bad = {}
+        for name, buf, key in (("grad_flat", eng.grad_flat, "start"), ("param_flat", eng.param_flat, "pstart")):
+            for b in eng.buckets:
+                if b.kind != "flat" and name == "param_flat":
+                    continue
+                lo = getattr(b, key)
+                seg = buf[lo : lo + b.size]
+                n = int((~torch.isfinite(seg.float() if seg.dtype != torch.float32 else seg)).sum())
+                if n:
+                    bad.setdefault(name, []).append((b.name, n, float(seg.float().abs().nan_to_num(0, 0, 0).max())))
+                    break
+        for name, buf in (("master", eng.master), ("exp_avg_sq", eng.exp_avg_sq), ("gshard", eng.gshard)):
+            n = int((~torch.isfinite(buf)).sum())
+            if n:
+                bad[name] = n
+        row["nonfinite"] = bad
+        row["grad_absmax"] = float(eng.grad_flat.abs().nan_to_num(0, 0, 0).max())
+        rows.append(row)
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+        if bad:
+            break
+    t.check_health()
+    t.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,7 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
 
 
 def read_jsonl(p: Path) -> list[dict]:
@@ -72,7 +73,9 @@ def main() -> None:
             for w in st.get("workers", []):
                 if w["name"] == a.victim and w.get("pid"):
                     victim_pid = w["pid"]
-                    os.killpg(victim_pid, signal.SIGKILL)
+                    from prime_b200.launch import signal_tree
+
+                    signal_tree(victim_pid, signal.SIGKILL)  # torchrun AND its ranks (they live in their own sessions)
                     killed_at = time.time()
                     events.append({"t": round(killed_at - t0, 2), "event": f"SIGKILL process group of {a.victim} (pid {victim_pid}) at steps {steps}"})
         if st.get("state") in ("COMPLETED", "FAILED", "STOPPED"):
