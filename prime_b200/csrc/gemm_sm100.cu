@@ -42,16 +42,20 @@ constexpr uint32_t kCopyChunkBytes = 128 * BK * 2;  // IO = 3 weight-gather copi
 constexpr int kCopyBufs = 2;
 constexpr int kGatherSub = 4;  // IO = 3: readiness flags per rank block (a block is released to the MMA tiles in quarters)
 
-template <int PAIR, int IO = 0>
+constexpr uint32_t kAuxSlabBytes = 4096;  // EPI = 3: one {64 col x 32 row} bf16 slab (gate or up) per epilogue warp
+
+template <int PAIR, int IO = 0, int EPI = 0>
 struct Geo {
   static constexpr int kTileM = PAIR ? 2 * BM : BM;        // rows of C per scheduled tile
   static constexpr int kBRows = PAIR ? BN / 2 : BN;        // B rows staged by one CTA
   static constexpr uint32_t kBBytes = kBRows * BK * 2;     // 16 KB | 32 KB
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   // IO = 3 gives one ring stage (32 KB) to the weight-gather copier's two 16 KB bounce buffers
-  static constexpr int kStages = PAIR ? (IO == 3 ? 5 : 6) : 4;
+  // EPI = 3 (SwiGLU backward) gives one more stage to the TMA-staged gate/up slabs its epilogue reads (2 x 4 KB per epilogue warp)
+  static constexpr int kStages = PAIR ? 6 - (IO == 3 ? 1 : 0) - (EPI == 3 ? 1 : 0) : 4;
   static constexpr uint32_t kCopyBytes = IO == 3 ? kCopyBufs * kCopyChunkBytes : 0;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kCopyBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kAuxBytes = EPI == 3 ? 4 * 2 * kAuxSlabBytes : 0;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kCopyBytes + kAuxBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 using namespace tc;
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                      const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_h,
                      const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_g2, const GemmParams p,
                      const __grid_constant__ PeerMaps pm) {
-  using G = Geo<PAIR, IO>;
+  using G = Geo<PAIR, IO, EPI>;
   constexpr int kStages = G::kStages;
   constexpr uint32_t kStageBytes = G::kStageBytes;
   constexpr int kBRows = G::kBRows;
@@ -229,13 +233,15 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + kStages * kStageBytes;  // 1024-aligned: 4 warps x 2 buffers x 4 KB
   uint8_t* copy_buf = staging + kStagingBytes;  // IO = 3: kCopyBufs x 16 KB bounce buffers of the weight-gather copier
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(copy_buf + G::kCopyBytes);
+  uint8_t* aux_buf = copy_buf + G::kCopyBytes;  // EPI = 3: per epilogue warp one gate and one up slab (TMA-loaded)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux_buf + G::kAuxBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + kAccStages;
   uint64_t* copied_bar = tempty_bar + kAccStages;  // IO = 1: the gather copier has finished reading a consumed ring slot
   uint64_t* cp_bar = copied_bar + kStages;         // IO = 3: a peer box has landed in bounce buffer i
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cp_bar + kCopyBufs);
+  uint64_t* aux_bar = cp_bar + kCopyBufs;          // EPI = 3: epilogue warp q's gate/up slabs have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool swiglu = PAIR && EPI == 2;
@@ -281,6 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&copied_bar[i], 1);
     }
     for (int i = 0; i < kCopyBufs; ++i) mbar_init(&cp_bar[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&aux_bar[i], 1);
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs in a pair)
@@ -522,6 +529,23 @@ __global__ void __launch_bounds__(kThreads, 1)
     uint32_t acc_phase = 0;
     int buf = 0;
     const int tpr = IO != 0 ? pm.rows_per_rank / kTileM : 0;
+    // EPI = 3: the saved gate/up activations of this warp's 32 rows reach the epilogue through TMA — one {64 x 32} slab each per
+    // 64-feature group, requested one group AHEAD (for group 0 of the NEXT tile as soon as the current tile's last group has been
+    // read), so the load runs under the output staging / store of the previous group. (First version: every thread fetched its own
+    // row with 16-byte LDGs — 32 different lines per instruction, no L1 left beside 224 KB of shared memory: the GEMM ran 2x its
+    // MMA time, slower than the un-fused pair of kernels.)
+    uint32_t aux_phase = 0;
+    bool aux_pending = false;
+    auto aux_coords = [&](int t, int& tm_, int& tn_) {
+      tile_coords(t / split_k, tiles_m, tiles_n, tm_, tn_, group_m);
+      if (IO == 3 && tn_rot) tn_ = (tn_ + tn_rot) % tiles_n;
+    };
+    auto aux_issue = [&](int tm_, int tn_, int g_) {  // lane 0 only
+      const int f0 = tn_ * BN + g_ * 64, r0 = tm_ * kTileM + (int)crank * BM + q * 32;
+      mbar_expect_tx(&aux_bar[q], 2 * kAuxSlabBytes);
+      tma_load_2d(&tmap_h, &aux_bar[q], aux_buf + q * 2 * kAuxSlabBytes, f0, r0);
+      tma_load_2d(&tmap_h, &aux_bar[q], aux_buf + q * 2 * kAuxSlabBytes + kAuxSlabBytes, p.swiglu_ff + f0, r0);
+    };
     for (int it = 0, tile; (tile = next_tile(it)) >= 0;) {
       int tm, tn, kind = 0;
       if (IO == 1 && pm.n > 1) {
@@ -530,6 +554,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         tile_coords(tile / split_k, tiles_m, tiles_n, tm, tn, group_m);
         if (IO == 2) tm = rs_tile_row(tm, pm, tpr);
         if (IO == 3 && tn_rot) tn = (tn + tn_rot) % tiles_n;
+      }
+      if (EPI == 3 && !aux_pending) {  // first tile of this CTA
+        if (lane == 0) aux_issue(tm, tn, 0);
+        aux_pending = true;
       }
       if ((tile % split_k) * kb_per >= num_kb) continue;  // empty K slice
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -562,21 +590,21 @@ __global__ void __launch_bounds__(kThreads, 1)
           buf ^= 1;
         }
       } else if constexpr (EPI == 3) {
-        // dh tile (fp32, TMEM) ⊗ saved gate/up (bf16, global) → d_gate | d_up (bf16): two 64-column slabs per group, one TMA store each
+        // dh tile (fp32, TMEM) ⊗ saved gate/up (bf16, TMA-staged slabs) → d_gate | d_up (bf16): two 64-column slabs per group, one
+        // TMA store each
         const int FF = p.swiglu_ff;
-        const __nv_bfloat16* aux = reinterpret_cast<const __nv_bfloat16*>(p.aux);
         uint8_t* stage_g = my_stage;
         uint8_t* stage_u = my_stage + 4096;
+        const uint32_t in_g = smem_u32(aux_buf + q * 2 * kAuxSlabBytes) + lane * 128, in_u = in_g + kAuxSlabBytes;
+        const uint32_t sg = smem_u32(stage_g) + lane * 128, su = smem_u32(stage_u) + lane * 128;
 #pragma unroll 1
         for (int g = 0; g < BN / 64; ++g) {
           const int f0 = tn * BN + g * 64;
           const bool ok = f0 < FF;  // warp-uniform (FF % 64 == 0)
-          const bool rok = ok && (row0 + lane) < p.M;
-          if (lane == 0) bulk_wait_read<0>();  // both slabs are free again
+          mbar_wait(&aux_bar[q], aux_phase);  // this group's gate / up slabs have landed
+          aux_phase ^= 1;
+          if (lane == 0) bulk_wait_read<0>();  // both output slabs are free again
           __syncwarp();
-          const uint4* gp = reinterpret_cast<const uint4*>(aux + (int64_t)(row0 + lane) * p.ld_aux + f0);
-          const uint4* up = reinterpret_cast<const uint4*>(aux + (int64_t)(row0 + lane) * p.ld_aux + FF + f0);
-          const uint32_t sg = smem_u32(stage_g) + lane * 128, su = smem_u32(stage_u) + lane * 128;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t r[32];
@@ -584,8 +612,8 @@ __global__ void __launch_bounds__(kThreads, 1)
             uint4 gq[4], uq[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              gq[j] = rok ? __ldg(gp + half * 4 + j) : make_uint4(0, 0, 0, 0);
-              uq[j] = rok ? __ldg(up + half * 4 + j) : make_uint4(0, 0, 0, 0);
+              gq[j] = ld_shared_v4(in_g + (((half * 4 + j) ^ row_sw) << 4));
+              uq[j] = ld_shared_v4(in_u + (((half * 4 + j) ^ row_sw) << 4));
             }
             tmem_ld_wait();
 #pragma unroll
@@ -608,12 +636,26 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
           fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && row0 < p.M && ok) {
-            tma_store_2d(&tmap_c, stage_g, f0, row0);
-            tma_store_2d(&tmap_c, stage_u, FF + f0, row0);
+          __syncwarp();  // every lane has read the input slabs and written the output slabs
+          if (lane == 0) {
+            // request the next group's inputs first (next tile's group 0 after the last group), then store this group
+            if (g + 1 < BN / 64) {
+              aux_issue(tm, tn, g + 1);
+            } else {
+              int it2 = it;
+              const int nt = next_tile(it2);
+              if (nt >= 0) {
+                int tm2, tn2;
+                aux_coords(nt, tm2, tn2);
+                aux_issue(tm2, tn2, 0);
+              }
+            }
+            if (row0 < p.M && ok) {
+              tma_store_2d(&tmap_c, stage_g, f0, row0);
+              tma_store_2d(&tmap_c, stage_u, FF + f0, row0);
+            }
+            bulk_commit();
           }
-          if (lane == 0) bulk_commit();
         }
       } else if constexpr (swiglu) {
         // pack 64 fp32 accumulator columns to bf16, stage them in the swizzled slab and TMA-store them at (col0, row0)
@@ -746,7 +788,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   const PeerMaps& pm = pmp ? *pmp : kNoPeers;
   const CUtensorMap& tg = tgp ? *tgp : tc;
   const CUtensorMap& tg2 = tg2p ? *tg2p : tg;
-  using G = Geo<PAIR, IO>;
+  using G = Geo<PAIR, IO, EPI>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, PAIR, EPI, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -909,8 +951,10 @@ PB_EXPORT int pb_gemm_bf16_swiglu_bwd(const void* dY, const void* W2, const void
   if ((rc = pbhost::cached_tmap(&ta, dY, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, BM))) return rc;
   if ((rc = pbhost::cached_tmap(&tb, W2, (uint64_t)K, (uint64_t)FF, (uint64_t)ldb, 64, BK))) return rc;
   if ((rc = pbhost::cached_tmap(&tc, d_gate_up, (uint64_t)M, (uint64_t)(2 * FF), (uint64_t)ld_dgu, 64, 32, 2))) return rc;
+  CUtensorMap taux;  // saved gate_up [M, 2·FF], {64 x 32} boxes: the epilogue's input slabs
+  if ((rc = pbhost::cached_tmap(&taux, gate_up, (uint64_t)M, (uint64_t)(2 * FF), (uint64_t)ld_gu, 64, 32, 2))) return rc;
   GemmParams p{M, FF, K, ld_dgu, 0, 1, 0, 0, 1, d_gate_up, nullptr, nullptr, 1, 0, 64, FF, 0, gate_up, ld_gu};
-  return launch<0, 1, 1, 3>(ta, tb, tc, tc, p, 0, stream);
+  return launch<0, 1, 1, 3>(ta, tb, tc, taux, p, 0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -1071,7 +1115,11 @@ PB_EXPORT int pb_gemm_wgather(const void* A, const void* const* w_peers, int n, 
   GemmParams p{M, epi == 2 ? 2 * FF : N, K, ldc, 0, b_mn_major, 0, 0, 1, C, rope_cos, rope_sin, rope_S, rope_cols, rope_D, FF, group_m,
                epi == 3 ? H : nullptr, epi == 3 ? ldh : 0};
   const CUtensorMap* tg2p = have_next ? &tg2 : nullptr;
-  if (epi == 3) return launch<0, 1, 1, 3, 3>(ta, tb, tc, tc, p, 0, stream, &pm, &tg, tg2p);
+  if (epi == 3) {
+    CUtensorMap taux;
+    if ((rc = pbhost::cached_tmap(&taux, H, (uint64_t)M, (uint64_t)(2 * FF), (uint64_t)ldh, 64, 32, 2))) return rc;
+    return launch<0, 1, 1, 3, 3>(ta, tb, tc, taux, p, 0, stream, &pm, &tg, tg2p);
+  }
   if (epi == 2) return launch<0, 0, 1, 2, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg, tg2p);
   if (epi == 1) return launch<0, 0, 1, 1, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg, tg2p);
   return b_mn_major ? launch<0, 1, 1, 0, 3>(ta, tb, tc, th, p, 0, stream, &pm, &tg, tg2p)

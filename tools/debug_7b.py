@@ -39,27 +39,38 @@ def main():
     eng = t.engine
     rank = t.mesh.world.rank
     rows = []
+
+    def nonfinite(buf: torch.Tensor, chunk: int = 1 << 28) -> tuple[int, float]:
+        n, mx = 0, 0.0
+        for lo in range(0, buf.numel(), chunk):
+            seg = buf[lo : lo + chunk]
+            fin = torch.isfinite(seg)
+            n += int((~fin).sum())
+            mx = max(mx, float(torch.where(fin, seg, torch.zeros_like(seg)).abs().max()))
+            del fin
+        return n, mx
+
     for step in range(a.steps):
         r = t.inner_step()
         torch.cuda.synchronize()
         row = {"step": step + 1, "loss": float(r.loss), "gnorm": float(r.grad_norm)}
+        if rank == 0:
+            print(json.dumps(row), flush=True)
         bad = {}
         for name, buf, key in (("grad_flat", eng.grad_flat, "start"), ("param_flat", eng.param_flat, "pstart")):
             for b in eng.buckets:
                 if b.kind != "flat" and name == "param_flat":
                     continue
                 lo = getattr(b, key)
-                seg = buf[lo : lo + b.size]
-                n = int((~torch.isfinite(seg.float() if seg.dtype != torch.float32 else seg)).sum())
+                n, mx = nonfinite(buf[lo : lo + b.size])
                 if n:
-                    bad.setdefault(name, []).append((b.name, n, float(seg.float().abs().nan_to_num(0, 0, 0).max())))
+                    bad.setdefault(name, []).append((b.name, n, mx))
                     break
         for name, buf in (("master", eng.master), ("exp_avg_sq", eng.exp_avg_sq), ("gshard", eng.gshard)):
-            n = int((~torch.isfinite(buf)).sum())
+            n, mx = nonfinite(buf)
             if n:
-                bad[name] = n
+                bad[name] = (n, mx)
         row["nonfinite"] = bad
-        row["grad_absmax"] = float(eng.grad_flat.abs().nan_to_num(0, 0, 0).max())
         rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
