@@ -51,11 +51,12 @@ struct Geo {
   static constexpr uint32_t kBBytes = kBRows * BK * 2;     // 16 KB | 32 KB
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   // IO = 3 gives one ring stage (32 KB) to the weight-gather copier's two 16 KB bounce buffers
-  // EPI = 3 (SwiGLU backward) gives one more stage to the TMA-staged gate/up slabs its epilogue reads (2 x 4 KB per epilogue warp)
-  static constexpr int kStages = PAIR ? 6 - (IO == 3 ? 1 : 0) - (EPI == 3 ? 1 : 0) : 4;
+  // EPI = 3 (SwiGLU backward) gives two stages to the TMA-staged gate/up slabs its epilogue reads: per epilogue warp a
+  // double-buffered pair of 4 KB slabs (the loads run two 64-feature groups ahead of the math)
+  static constexpr int kStages = PAIR ? 6 - (IO == 3 ? 1 : 0) - (EPI == 3 ? 2 : 0) : 4;
   static constexpr uint32_t kCopyBytes = IO == 3 ? kCopyBufs * kCopyChunkBytes : 0;
-  static constexpr uint32_t kAuxBytes = EPI == 3 ? 4 * 2 * kAuxSlabBytes : 0;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kCopyBytes + kAuxBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kAuxBytes = EPI == 3 ? 4 * 2 * 2 * kAuxSlabBytes : 0;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kCopyBytes + kAuxBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 using namespace tc;
@@ -240,8 +241,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* tempty_bar = tfull_bar + kAccStages;
   uint64_t* copied_bar = tempty_bar + kAccStages;  // IO = 1: the gather copier has finished reading a consumed ring slot
   uint64_t* cp_bar = copied_bar + kStages;         // IO = 3: a peer box has landed in bounce buffer i
-  uint64_t* aux_bar = cp_bar + kCopyBufs;          // EPI = 3: epilogue warp q's gate/up slabs have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 4);
+  uint64_t* aux_bar = cp_bar + kCopyBufs;          // EPI = 3: [warp q][set]: that warp's gate/up slabs of one group have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool swiglu = PAIR && EPI == 2;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(&copied_bar[i], 1);
     }
     for (int i = 0; i < kCopyBufs; ++i) mbar_init(&cp_bar[i], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs in a pair)
@@ -530,22 +531,39 @@ __global__ void __launch_bounds__(kThreads, 1)
     int buf = 0;
     const int tpr = IO != 0 ? pm.rows_per_rank / kTileM : 0;
     // EPI = 3: the saved gate/up activations of this warp's 32 rows reach the epilogue through TMA — one {64 x 32} slab each per
-    // 64-feature group, requested one group AHEAD (for group 0 of the NEXT tile as soon as the current tile's last group has been
-    // read), so the load runs under the output staging / store of the previous group. (First version: every thread fetched its own
-    // row with 16-byte LDGs — 32 different lines per instruction, no L1 left beside 224 KB of shared memory: the GEMM ran 2x its
-    // MMA time, slower than the un-fused pair of kernels.)
-    uint32_t aux_phase = 0;
-    bool aux_pending = false;
-    auto aux_coords = [&](int t, int& tm_, int& tn_) {
-      tile_coords(t / split_k, tiles_m, tiles_n, tm_, tn_, group_m);
-      if (IO == 3 && tn_rot) tn_ = (tn_ + tn_rot) % tiles_n;
+    // 64-feature group, double-buffered and requested TWO groups ahead (a look-ahead cursor walks this CTA's tile sequence), so an
+    // HBM-latency load is never on the epilogue's critical path. (v1: every thread fetched its own row with 16-byte LDGs — 32 lines
+    // per instruction, no L1 beside 224 KB of shared memory: 2.0x the MMA time. v2: single-buffered slabs one group ahead: 1.7x.)
+    uint32_t aux_phase[2] = {0, 0};
+    int aux_k = 0;                  // groups consumed so far (set = aux_k & 1)
+    int la_it = 0, la_tile = -2, la_tm = 0, la_tn = 0, la_g = BN / 64;  // look-ahead cursor: next group to request
+    int la_k = 0;                   // groups requested so far
+    auto aux_request_next = [&]() {  // lane 0 only: request the next group of this CTA's sequence into set (la_k & 1)
+      if (la_g == BN / 64) {         // move the cursor to the next tile
+        if (la_tile == -1) return;   // sequence exhausted
+        const int t = next_tile(la_it);
+        if (t < 0) {
+          la_tile = -1;
+          return;
+        }
+        la_tile = t;
+        tile_coords(t / split_k, tiles_m, tiles_n, la_tm, la_tn, group_m);
+        if (IO == 3 && tn_rot) la_tn = (la_tn + tn_rot) % tiles_n;
+        la_g = 0;
+      }
+      const int set = la_k & 1;
+      const int f0 = la_tn * BN + la_g * 64, r0 = la_tm * kTileM + (int)crank * BM + q * 32;
+      uint8_t* dst = aux_buf + (q * 2 + set) * 2 * kAuxSlabBytes;
+      mbar_expect_tx(&aux_bar[q * 2 + set], 2 * kAuxSlabBytes);
+      tma_load_2d(&tmap_h, &aux_bar[q * 2 + set], dst, f0, r0);
+      tma_load_2d(&tmap_h, &aux_bar[q * 2 + set], dst + kAuxSlabBytes, p.swiglu_ff + f0, r0);
+      ++la_g;
+      ++la_k;
     };
-    auto aux_issue = [&](int tm_, int tn_, int g_) {  // lane 0 only
-      const int f0 = tn_ * BN + g_ * 64, r0 = tm_ * kTileM + (int)crank * BM + q * 32;
-      mbar_expect_tx(&aux_bar[q], 2 * kAuxSlabBytes);
-      tma_load_2d(&tmap_h, &aux_bar[q], aux_buf + q * 2 * kAuxSlabBytes, f0, r0);
-      tma_load_2d(&tmap_h, &aux_bar[q], aux_buf + q * 2 * kAuxSlabBytes + kAuxSlabBytes, p.swiglu_ff + f0, r0);
-    };
+    if (EPI == 3 && lane == 0) {
+      aux_request_next();
+      aux_request_next();
+    }
     for (int it = 0, tile; (tile = next_tile(it)) >= 0;) {
       int tm, tn, kind = 0;
       if (IO == 1 && pm.n > 1) {
@@ -555,10 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (IO == 2) tm = rs_tile_row(tm, pm, tpr);
         if (IO == 3 && tn_rot) tn = (tn + tn_rot) % tiles_n;
       }
-      if (EPI == 3 && !aux_pending) {  // first tile of this CTA
-        if (lane == 0) aux_issue(tm, tn, 0);
-        aux_pending = true;
-      }
+
       if ((tile % split_k) * kb_per >= num_kb) continue;  // empty K slice
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -595,14 +610,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int FF = p.swiglu_ff;
         uint8_t* stage_g = my_stage;
         uint8_t* stage_u = my_stage + 4096;
-        const uint32_t in_g = smem_u32(aux_buf + q * 2 * kAuxSlabBytes) + lane * 128, in_u = in_g + kAuxSlabBytes;
         const uint32_t sg = smem_u32(stage_g) + lane * 128, su = smem_u32(stage_u) + lane * 128;
 #pragma unroll 1
         for (int g = 0; g < BN / 64; ++g) {
           const int f0 = tn * BN + g * 64;
           const bool ok = f0 < FF;  // warp-uniform (FF % 64 == 0)
-          mbar_wait(&aux_bar[q], aux_phase);  // this group's gate / up slabs have landed
-          aux_phase ^= 1;
+          const int set = aux_k & 1;
+          const uint32_t in_g = smem_u32(aux_buf + (q * 2 + set) * 2 * kAuxSlabBytes) + lane * 128, in_u = in_g + kAuxSlabBytes;
+          mbar_wait(&aux_bar[q * 2 + set], aux_phase[set]);  // this group's gate / up slabs have landed (requested two groups ago)
+          aux_phase[set] ^= 1;
+          ++aux_k;
           if (lane == 0) bulk_wait_read<0>();  // both output slabs are free again
           __syncwarp();
 #pragma unroll
@@ -638,18 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           fence_proxy_async();
           __syncwarp();  // every lane has read the input slabs and written the output slabs
           if (lane == 0) {
-            // request the next group's inputs first (next tile's group 0 after the last group), then store this group
-            if (g + 1 < BN / 64) {
-              aux_issue(tm, tn, g + 1);
-            } else {
-              int it2 = it;
-              const int nt = next_tile(it2);
-              if (nt >= 0) {
-                int tm2, tn2;
-                aux_coords(nt, tm2, tn2);
-                aux_issue(tm2, tn2, 0);
-              }
-            }
+            aux_request_next();  // refill the input set just consumed (two groups ahead of the math)
             if (row0 < p.M && ok) {
               tma_store_2d(&tmap_c, stage_g, f0, row0);
               tma_store_2d(&tmap_c, stage_u, FF + f0, row0);

@@ -394,6 +394,9 @@ def linear_mxfp8(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
 
 
 _NO_EPILOGUE_FUSION = bool(int(__import__("os").environ.get("PB_NO_EPILOGUE_FUSION", "0")))
+# SwiGLU backward inside the down-projection's dgrad epilogue (EPI = 3) vs dgrad + stand-alone kernel. Default = what measured faster
+# in the step (DESIGN.md §1.6 has the numbers of both); PB_SWIGLU_BWD_FUSED=0/1 overrides.
+_SWIGLU_BWD_FUSED = bool(int(__import__("os").environ.get("PB_SWIGLU_BWD_FUSED", "1")))
 
 
 def rope_fusable(x: torch.Tensor, n_heads: int, n_kv_heads: int, head_dim: int) -> bool:
@@ -757,7 +760,16 @@ class _MLPSwiGLUFn(torch.autograd.Function):
         dw2 = _wgrad(dy2, h, w2) if ctx.needs_input_grad[2] else None
         dgu = torch.empty_like(gate_up)
         z13, z2 = getattr(w13, "z3", None), getattr(w2, "z3", None)
-        if z2 is not None:
+        if not _SWIGLU_BWD_FUSED:
+            # two kernels: dh = dy·W2 (plain / gather-fused dgrad), then the stand-alone SwiGLU backward (0.82 of the HBM roof)
+            dh = torch.empty((M, FF), dtype=dy.dtype, device=dy.device)
+            if z2 is not None:
+                gemm_wgather(dy2, z2, b_mn_major=True, out=dh)
+            else:
+                gemm(dy2, w2, b_mn_major=True, out=dh)
+            _lib.check(lib.pb_swiglu_bwd(_ptr(gate_up), _ptr(dh), _ptr(dgu), M, FF, _stream()), "pb_swiglu_bwd")
+            _count()
+        elif z2 is not None:
             gemm_wgather(dy2, z2, b_mn_major=True, out=dgu, swiglu_bwd_gu=gate_up)
         else:
             rc = lib.pb_gemm_bf16_swiglu_bwd(dy2.data_ptr(), w2.data_ptr(), gate_up.data_ptr(), dgu.data_ptr(), M, FF, dy2.shape[1],
