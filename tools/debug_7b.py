@@ -71,8 +71,9 @@ def main():
             if n:
                 bad[name] = (n, mx)
         row["nonfinite"] = bad
+        row["rank"] = rank
         rows.append(row)
-        if rank == 0:
+        if rank == 0 or bad:
             print(json.dumps(row), flush=True)
         if bad:
             break
