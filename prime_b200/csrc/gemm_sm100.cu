@@ -53,9 +53,11 @@ struct Geo {
   // IO = 3 gives one ring stage (32 KB) to the weight-gather copier's two 16 KB bounce buffers
   // EPI = 3 (SwiGLU backward) gives two stages to the TMA-staged gate/up slabs its epilogue reads: per epilogue warp a
   // double-buffered pair of 4 KB slabs (the loads run two 64-feature groups ahead of the math)
-  static constexpr int kStages = PAIR ? 6 - (IO == 3 ? 1 : 0) - (EPI == 3 ? 2 : 0) : 4;
+  // (with IO = 3 the copier already took a stage: single-buffered slabs there, four stages left in both combinations)
+  static constexpr int kAuxSets = EPI == 3 ? (IO == 3 ? 1 : 2) : 0;
+  static constexpr int kStages = PAIR ? 6 - (IO == 3 ? 1 : 0) - (EPI == 3 ? kAuxSets : 0) : 4;
   static constexpr uint32_t kCopyBytes = IO == 3 ? kCopyBufs * kCopyChunkBytes : 0;
-  static constexpr uint32_t kAuxBytes = EPI == 3 ? 4 * 2 * 2 * kAuxSlabBytes : 0;
+  static constexpr uint32_t kAuxBytes = 4 * kAuxSets * 2 * kAuxSlabBytes;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kCopyBytes + kAuxBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
@@ -551,9 +553,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (IO == 3 && tn_rot) la_tn = (la_tn + tn_rot) % tiles_n;
         la_g = 0;
       }
-      const int set = la_k & 1;
+      constexpr int kSets = G::kAuxSets > 0 ? G::kAuxSets : 1;
+      const int set = la_k % kSets;
       const int f0 = la_tn * BN + la_g * 64, r0 = la_tm * kTileM + (int)crank * BM + q * 32;
-      uint8_t* dst = aux_buf + (q * 2 + set) * 2 * kAuxSlabBytes;
+      uint8_t* dst = aux_buf + (q * kSets + set) * 2 * kAuxSlabBytes;
       mbar_expect_tx(&aux_bar[q * 2 + set], 2 * kAuxSlabBytes);
       tma_load_2d(&tmap_h, &aux_bar[q * 2 + set], dst, f0, r0);
       tma_load_2d(&tmap_h, &aux_bar[q * 2 + set], dst + kAuxSlabBytes, p.swiglu_ff + f0, r0);
@@ -561,8 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       ++la_k;
     };
     if (EPI == 3 && lane == 0) {
-      aux_request_next();
-      aux_request_next();
+      for (int i = 0; i < G::kAuxSets; ++i) aux_request_next();
     }
     for (int it = 0, tile; (tile = next_tile(it)) >= 0;) {
       int tm, tn, kind = 0;
@@ -615,8 +617,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int g = 0; g < BN / 64; ++g) {
           const int f0 = tn * BN + g * 64;
           const bool ok = f0 < FF;  // warp-uniform (FF % 64 == 0)
-          const int set = aux_k & 1;
-          const uint32_t in_g = smem_u32(aux_buf + (q * 2 + set) * 2 * kAuxSlabBytes) + lane * 128, in_u = in_g + kAuxSlabBytes;
+          constexpr int kSets = G::kAuxSets > 0 ? G::kAuxSets : 1;
+          const int set = aux_k % kSets;
+          const uint32_t in_g = smem_u32(aux_buf + (q * kSets + set) * 2 * kAuxSlabBytes) + lane * 128, in_u = in_g + kAuxSlabBytes;
           mbar_wait(&aux_bar[q * 2 + set], aux_phase[set]);  // this group's gate / up slabs have landed (requested two groups ago)
           aux_phase[set] ^= 1;
           ++aux_k;

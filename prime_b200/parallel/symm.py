@@ -62,6 +62,12 @@ class SymmetricHeap:
             p = ctypes.c_void_p()
             _lib.check(self.lib.pb_ipc_open_handle(ctypes.create_string_buffer(h, hsize), ctypes.byref(p)), "pb_ipc_open_handle")
             self.peer_base.append(int(p.value))
+        # Rendezvous AFTER every rank has mapped every peer: nobody may start writing its heap while a peer is still inside
+        # cudaIpcOpenMemHandle on it. (Seen with 44 GB heaps on 4 and 8 GPUs: bf16 weights of late layers — copied into the heap
+        # while slower peers were still opening it — came out corrupted on some ranks; 7 GB heaps never showed it.)
+        torch.cuda.synchronize(device)
+        if world_size > 1:
+            exchange(b"mapped")
         self._whole = torch.as_tensor(_DevBuffer(self.base, self.nbytes), device=device)
         self._cursor = 0
         # control block: flags + error word + norm slots

@@ -50,8 +50,32 @@ def main():
             del fin
         return n, mx
 
+    # per-layer finiteness of the residual stream for every forward, and a checksum of the bf16 weights around the first step
+    fw = []
+
+    def hook(i):
+        def f(mod, inp, out):
+            h = out[0] if isinstance(out, tuple) else out
+            if len(fw) < 4 * len(t.model.layers):
+                fw.append((i, int((~torch.isfinite(h)).sum()), float(h.detach().float().abs().nan_to_num(0, 0, 0).max())))
+        return f
+
+    for i, layer in enumerate(t.model.layers):
+        layer.register_forward_hook(hook(i))
+
+    def wsum():
+        return [float(p.detach().float().abs().sum()) for p in (t.model.tok_embeddings.weight, t.model.layers[0].attention.wqkv,
+                                                                 t.model.layers[-1].feed_forward.w2, t.model.output)]
+
+    torch.cuda.synchronize()
+    print(json.dumps({"rank": rank, "weights_before": wsum(), "param_flat_nonfinite": nonfinite(eng.param_flat)[0]}), flush=True)
     for step in range(a.steps):
         r = t.inner_step()
+        if step == 0:
+            torch.cuda.synchronize()
+            bad = [x for x in fw if x[1]]
+            print(json.dumps({"rank": rank, "fwd_layers_seen": len(fw), "first_bad": bad[:2], "absmax_by_layer_first_fwd": [round(x[2], 2) for x in fw[: len(t.model.layers)]][::4],
+                              "absmax_second_fwd": [round(x[2], 2) for x in fw[len(t.model.layers): 2 * len(t.model.layers)]][::4], "weights_after_step": wsum()}), flush=True)
         torch.cuda.synchronize()
         row = {"step": step + 1, "loss": float(r.loss), "gnorm": float(r.grad_norm)}
         if rank == 0:
