@@ -481,24 +481,39 @@ __global__ void __launch_bounds__(256) outer_nesterov_kernel(PeerPtrs qs, PeerPt
     const int64_t blk = blk0 + grp;
     if (blk >= nblk) continue;  // whole warps drop out together (a block is two full warps)
     const int64_t base = blk * 1024 + t64 * 16;
+    // Every load of the iteration is issued before the first use. Round 1/2a loaded "scale, shuffle, payload" peer by peer: the
+    // shuffle needs the scale, so each peer cost a full NVLink round trip (≈2 µs) before the next peer's loads could even issue —
+    // W = 8 ran at 377 GB/s per rank. Now lane w fetches peer w's scale (one instruction for all peers), the W payload loads
+    // and the local theta0 / momentum loads follow back to back, and only then are the scales broadcast and consumed.
+    float sc_l = 0.f;
+    const float* sp = nullptr;
+#pragma unroll
+    for (int w = 0; w < kMaxPeers; ++w)
+      if (lane == w) sp = reinterpret_cast<const float*>(ss.p[w]);  // select chain: a dynamic index would spill the struct to local memory
+    if (lane < qs.n) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(sc_l) : "l"(sp + blk));
+    uint4 qv[kMaxPeers];
+#pragma unroll
+    for (int w = 0; w < kMaxPeers; ++w)
+      if (w < qs.n) qv[w] = ld_relaxed_sys_u4(reinterpret_cast<const uint4*>(reinterpret_cast<const int8_t*>(qs.p[w]) + base));
+    float4 t0v[4], mmv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      t0v[j] = reinterpret_cast<const float4*>(theta0 + base)[j];
+      mmv[j] = reinterpret_cast<const float4*>(mom + base)[j];
+    }
     float g[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) g[k] = 0.f;
 #pragma unroll
-    for (int w = 0; w < kMaxPeers; ++w) {
-      if (w < qs.n) {
-        float sc = 0.f;
-        if (lane == 0) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(sc) : "l"(reinterpret_cast<const float*>(ss.p[w]) + blk));
-        sc = __shfl_sync(0xffffffffu, sc, 0);
-        const uint4 qv = ld_relaxed_sys_u4(reinterpret_cast<const uint4*>(reinterpret_cast<const int8_t*>(qs.p[w]) + base));
-        dequant16(qv, sc, g);
-      }
+    for (int w = 0; w < kMaxPeers; ++w) {  // fixed worker order → bitwise identical sums on every worker
+      const float sc = __shfl_sync(0xffffffffu, sc_l, w);
+      if (w < qs.n) dequant16(qv[w], sc, g);
     }
     float outv[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float4 t0 = reinterpret_cast<const float4*>(theta0 + base)[j];
-      float4 mm = reinterpret_cast<const float4*>(mom + base)[j];
+      float4 t0 = t0v[j];
+      float4 mm = mmv[j];
       float* tp = &t0.x;
       float* mp = &mm.x;
 #pragma unroll
@@ -556,13 +571,17 @@ __global__ void __launch_bounds__(256) outer_nesterov_f32_kernel(PeerPtrs thetas
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int64_t j = i * 2 + h;
+      float4 twv[kMaxPeers];  // all peer loads in flight before the first use
+#pragma unroll
+      for (int w = 0; w < kMaxPeers; ++w)
+        if (w < thetas.n) twv[w] = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(thetas.p[w]) + j);
       float4 t0 = reinterpret_cast<const float4*>(theta0)[j];
       float4 mm = reinterpret_cast<const float4*>(mom)[j];
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int w = 0; w < kMaxPeers; ++w) {
         if (w < thetas.n) {
-          const float4 tw = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(thetas.p[w]) + j);
+          const float4 tw = twv[w];
           g.x += t0.x - tw.x, g.y += t0.y - tw.y, g.z += t0.z - tw.z, g.w += t0.w - tw.w;
         }
       }

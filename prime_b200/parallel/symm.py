@@ -62,9 +62,12 @@ class SymmetricHeap:
             p = ctypes.c_void_p()
             _lib.check(self.lib.pb_ipc_open_handle(ctypes.create_string_buffer(h, hsize), ctypes.byref(p)), "pb_ipc_open_handle")
             self.peer_base.append(int(p.value))
-        # Rendezvous AFTER every rank has mapped every peer: nobody may start writing its heap while a peer is still inside
-        # cudaIpcOpenMemHandle on it. (Seen with 44 GB heaps on 4 and 8 GPUs: bf16 weights of late layers — copied into the heap
-        # while slower peers were still opening it — came out corrupted on some ranks; 7 GB heaps never showed it.)
+        # Rendezvous AFTER every rank has zeroed its own heap and mapped every peer: nobody may start writing into a peer's heap
+        # while that peer's clearing memset (``pb_ipc_alloc``: asynchronous on the null stream, ≈10 ms for a 44 GB heap) is still
+        # running, or while a peer is still inside cudaIpcOpenMemHandle on it. Seen with 44 GB heaps on 4 and 8 GPUs: bf16
+        # weights of LATE layers (high addresses — the memset reaches them last), pushed by a faster peer, came out wrong on
+        # some ranks before the first forward; 7 GB heaps never showed it. The synchronize makes the local memset complete,
+        # the second exchange makes that true of every rank before anyone returns.
         torch.cuda.synchronize(device)
         if world_size > 1:
             exchange(b"mapped")
