@@ -111,8 +111,11 @@ def quantize_int8_blockwise(x: torch.Tensor, block: int = 1024) -> tuple[torch.T
         xf = F.pad(xf, (0, pad))
     xb = xf.view(nb, block)
     amax = xb.abs().amax(dim=1)
-    scale = amax / 127.0
-    inv = torch.where(scale > 0, 1.0 / scale, torch.zeros_like(scale))
+    # tensor ÷ tensor: ``amax / 127.0`` (tensor ÷ Python scalar) is evaluated by torch as amax · (1/127), which differs from the
+    # IEEE quotient the kernel computes by one ulp for some blocks — enough to round a tie the other way in a few elements per
+    # million and make the fused-vs-reference comparison data dependent
+    scale = torch.div(amax, torch.full_like(amax, 127.0))
+    inv = torch.where(scale > 0, torch.ones_like(scale) / scale, torch.zeros_like(scale))
     q = torch.clamp(torch.round(xb * inv[:, None]), -127, 127).to(torch.int8)
     return q.view(-1)[:n].contiguous(), scale
 
