@@ -19,8 +19,9 @@ that times out sets the region's error word, ``outer_nesterov`` sees it and leav
 All GPUs of the box must be visible to every worker (``launch.py`` passes ``PRIME_B200_DEVICES`` instead of slicing
 ``CUDA_VISIBLE_DEVICES``).
 
-Barrier epochs are ``(membership epoch << 8) + sequence``: the membership epoch grows at every rendezvous for every member, so
-a value left in a flag by an earlier membership (or by a dead worker's previous incarnation) can never satisfy a later wait.
+Barrier epochs are ``(membership epoch << 20) + sequence`` (compared wrap-safe on the device): the membership epoch grows at
+every rendezvous for every member, so a value left in a flag by an earlier membership (or by a dead worker's previous
+incarnation) can never satisfy a later wait — as long as one membership lasts fewer than 2^19 outer steps (two barriers each).
 """
 
 from __future__ import annotations
@@ -37,6 +38,7 @@ FLAG_WORDS = 64
 ERR_WORDS = 16
 SLOT_A, SLOT_B = 0, 16  # first flag slot of the two barriers (≤ 16 workers per box)
 QBLOCK = 1024
+SEQ_BITS = 20  # barrier sequence numbers per membership epoch (see the module docstring)
 
 
 class ElasticExchange:
@@ -59,6 +61,7 @@ class ElasticExchange:
         self._whole = whole
         hbuf = ctypes.create_string_buffer(self.lib.pb_ipc_handle_size())
         _lib.check(self.lib.pb_ipc_get_handle(self.base, hbuf), "pb_ipc_get_handle")
+        torch.cuda.synchronize(device)  # pb_ipc_alloc's clearing memset is asynchronous: finish it before any peer can map and write flags
         self.store.set(self._key(wid), json.dumps({"handle": bytes(hbuf.raw).hex(), "nbytes": self.nbytes, "n": n_elems,
                                                    "device": torch.cuda.current_device()}))  # fmt: skip
         self._open: dict[str, int] = {}  # worker id (with incarnation) → mapped base of its region for my fsdp_rank
@@ -101,7 +104,7 @@ class ElasticExchange:
     # ------------------------------------------------------------------ device-side sync
     def barrier(self, slot: int, stream: int) -> None:
         self._seq += 1
-        epoch = ((self._mem_epoch << 8) + self._seq) & 0xFFFFFFFF
+        epoch = ((self._mem_epoch << SEQ_BITS) + self._seq) & 0xFFFFFFFF
         flags = _lib.PeerPtrs.of(self._bases())
         _lib.check(self.lib.pb_barrier(ctypes.byref(flags), slot, self.index, epoch, self.err.data_ptr(), stream), "pb_barrier")
 

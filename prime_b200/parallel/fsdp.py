@@ -683,6 +683,15 @@ class ShardedEngine:
     def load_state_dict(self, sd: dict) -> None:
         if sd["fsdp_size"] != self.F:
             raise ValueError(f"checkpoint was written with fsdp_size={sd['fsdp_size']}, engine has {self.F}")
+        if bool(sd.get("shard_params", False)) != self.shard_params:
+            # the two modes cut the optimizer shards differently (contiguous 1/F slices of a bucket vs one row block per weight)
+            raise ValueError(
+                f"checkpoint was written with train.reshard_after_forward={bool(sd.get('shard_params', False))} (shard layout differs), "
+                f"engine runs with {self.shard_params}: resume with the same setting"
+            )
+        layout = [(b.name, b.start, b.size, b.shard_start, b.shard_size) for b in self.buckets]
+        if "layout" in sd and [tuple(x) for x in sd["layout"]] != layout:
+            raise ValueError("checkpoint bucket layout does not match this model / mesh (different model size or parameter set)")
         self.step_count = int(sd["step"])
         self.master.copy_(sd["master"])
         self.exp_avg.copy_(sd["exp_avg"])

@@ -90,3 +90,18 @@ def test_activation_checkpointing_is_exact(ac):
     l0, m0, g0 = run(False)
     l1, m1, g1 = run(ac)
     assert l0 == l1 and g0 == g1 and torch.equal(m0, m1)
+
+
+def test_load_state_dict_rejects_other_shard_layouts():
+    m = build_model("debugmodel", dtype=torch.float32, seed=5)
+    eng = ShardedEngine(m, _mesh(), AdamHyper(), backend="collective")
+    sd = {k: (v.clone() if isinstance(v, torch.Tensor) else copy.deepcopy(v)) for k, v in eng.state_dict().items()}
+    eng.load_state_dict(sd)  # round trip
+    with pytest.raises(ValueError, match="reshard_after_forward"):
+        eng.load_state_dict({**sd, "shard_params": True})  # written by a ZeRO-3 run: row-block shards, not bucket slices
+    with pytest.raises(ValueError, match="fsdp_size"):
+        eng.load_state_dict({**sd, "fsdp_size": 2})
+    bad = [list(x) for x in sd["layout"]]
+    bad[1][2] += 1024
+    with pytest.raises(ValueError, match="layout"):
+        eng.load_state_dict({**sd, "layout": [tuple(x) for x in bad]})
