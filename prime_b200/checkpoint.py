@@ -353,3 +353,51 @@ def restore_trainer(trainer, tensors: dict[str, torch.Tensor], extra: dict[str, 
     trainer.step_count = int(extra["trainer_step"])
     if not skip_dataloader:
         trainer.loader.load_state_dict(extra["data"])
+
+
+# ------------------------------------------------------------------------------------------------- offline assembly
+def assemble_full_model(path: str | Path, name_model: str, type_model: str = "llama2", *, dtype: torch.dtype = torch.float32, **overrides):
+    """Rebuild the complete model on the CPU from a published checkpoint step directory: every ``rank_*.pbck`` holds its rank's
+    1/F slice of the fp32 master weights, cut either as contiguous bucket slices (replicated-parameter mode) or as one row block
+    per weight (ZeRO-3). The layout is recomputed with the engine's own planner, so there is one source of truth.
+    Used by ``python -m prime_b200.models.hf export`` and ``examples/inspect_checkpoint.py``; DiLoCo workers are identical after
+    an outer step, the first worker's shards are taken."""
+    from .models.llama import build_model
+    from .parallel.fsdp import ShardedEngine
+
+    d = Path(path)
+    meta = json.loads((d / "meta.json").read_text())
+    shards: dict[int, torch.Tensor] = {}
+    extra0: dict[str, Any] | None = None
+    for r in range(int(meta["world_size"])):
+        f = d / f"rank_{r:05d}.pbck"
+        tensors, extra = read_shard(f, "cpu")
+        fr = int(extra["fsdp_rank"])
+        if fr not in shards:
+            shards[fr] = tensors["master"].float()
+            extra0 = extra0 or extra
+        if len(shards) == int(extra["fsdp_size"]):
+            break
+    assert extra0 is not None
+    F = int(extra0["fsdp_size"])
+    if sorted(shards) != list(range(F)):
+        raise ValueError(f"checkpoint {d} is incomplete: have fsdp ranks {sorted(shards)} of {F}")
+    model = build_model(name_model, type_model, dtype=dtype, seed=None, **overrides)
+    plan = ShardedEngine.__new__(ShardedEngine)  # layout planner only: no buffers, no hooks, no process group
+    plan.model, plan.F, plan.shard_params = model, F, bool(extra0.get("shard_params", False))
+    plan._build_buckets()
+    layout = [[b.name, b.start, b.size, b.shard_start, b.shard_size] for b in plan.buckets]
+    if layout != [list(x) for x in extra0["layout"]]:
+        raise ValueError(f"checkpoint {d} was written for a different model than {type_model}/{name_model} (bucket layout differs)")
+    with torch.no_grad():
+        for b in plan.buckets:
+            if b.kind == "rows":
+                for (_, p, _), (soff, piece) in zip(b.params, b.pieces):
+                    rows, cols = p.shape
+                    blocks = [shards[r][b.shard_start + soff : b.shard_start + soff + piece].view(rows // F, cols) for r in range(F)]
+                    p.copy_(torch.cat(blocks, dim=0))
+            else:
+                full = torch.cat([shards[r][b.shard_start : b.shard_start + b.shard_size] for r in range(F)])
+                for _, p, off in b.params:
+                    p.copy_(full[off : off + p.numel()].view(p.shape))
+    return model

@@ -36,6 +36,7 @@ class ModelArgs:
     rope_theta: float = 10000.0
     max_seq_len: int = 2048
     depth_init: bool = True
+    intermediate_size: int | None = None  # explicit FFN width (imported checkpoints); None = derived from dim / multiple_of
 
     @property
     def head_dim(self) -> int:
@@ -47,6 +48,8 @@ class ModelArgs:
 
     @property
     def ffn_hidden(self) -> int:
+        if self.intermediate_size is not None:
+            return self.intermediate_size
         hidden = int(2 * (4 * self.dim) / 3)
         if self.ffn_dim_multiplier is not None:
             hidden = int(self.ffn_dim_multiplier * hidden)

@@ -1,6 +1,8 @@
+import pytest
 import torch
 
 from prime_b200.models.llama import (
+    Transformer,
     build_model,
     from_reference_state_dict,
     get_model_args,
@@ -58,3 +60,70 @@ def test_fused_residual_chain_matches_plain():
         h = h + layer.feed_forward(y)
     ref = R.rmsnorm(h, m.norm.weight, m.args.norm_eps)
     torch.testing.assert_close(m.forward_hidden(tok), ref, rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- Hugging Face interchange
+def _tiny_hf(kv_heads: int = 2):
+    transformers = pytest.importorskip("transformers")
+    cfg = transformers.LlamaConfig(vocab_size=512, hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+                                   num_key_value_heads=kv_heads, max_position_embeddings=128, rms_norm_eps=1e-5, rope_theta=10000.0,
+                                   tie_word_embeddings=False, attn_implementation="eager")  # fmt: skip
+    torch.manual_seed(3)
+    return transformers.LlamaForCausalLM(cfg).eval()
+
+
+@pytest.mark.parametrize("kv_heads", [4, 2])
+def test_hf_import_matches_transformers_logits(kv_heads):
+    """HF rotates (x[i], x[i + D/2]) and permutes q/k rows per head; this engine rotates interleaved pairs. After the import the
+    two models must be the same function (MHA and GQA)."""
+    from prime_b200.models import hf
+
+    ref = _tiny_hf(kv_heads)
+    args = hf.args_from_hf_config(ref.config.to_dict())
+    assert (args.dim, args.n_layers, args.n_heads, args.kv_heads, args.ffn_hidden, args.vocab_size) == (64, 2, 4, kv_heads, 176, 512)
+    m = Transformer(args).float()
+    hf.load_hf_state_dict(m, ref.state_dict())
+    tok = torch.randint(0, 512, (2, 48))
+    with torch.no_grad():
+        want = ref(tok).logits
+        got = m(tok)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+    # and back: the exported state dict is exactly what transformers had
+    back = hf.to_hf_state_dict(m)
+    for k, v in ref.state_dict().items():
+        torch.testing.assert_close(back[k], v, rtol=0, atol=0, msg=k)
+
+
+def test_hf_export_directory_loads_in_transformers(tmp_path):
+    transformers = pytest.importorskip("transformers")
+    pytest.importorskip("safetensors")
+    from prime_b200.models import hf
+
+    m = build_model("debugmodel", dtype=torch.float32, seed=11, n_kv_heads=4)
+    names = hf.save_hf_dir(m, tmp_path / "one")
+    assert names == ["model.safetensors"]
+    sharded = hf.save_hf_dir(m, tmp_path / "many", max_shard_bytes=2 << 20)  # force an index + several shards
+    assert len(sharded) > 1 and (tmp_path / "many" / "model.safetensors.index.json").exists()
+    tok = torch.randint(0, m.args.vocab_size, (1, 40))
+    with torch.no_grad():
+        want = m(tok)
+    for d in ("one", "many"):
+        loaded = transformers.AutoModelForCausalLM.from_pretrained(tmp_path / d, torch_dtype=torch.float32, attn_implementation="eager").eval()
+        with torch.no_grad():
+            torch.testing.assert_close(loaded(tok).logits, want, rtol=1e-4, atol=1e-4)
+        again = hf.load_hf_dir(tmp_path / d, dtype=torch.float32)  # and our own reader takes both layouts
+        for (k, a), (_, b) in zip(m.named_parameters(), again.named_parameters()):
+            torch.testing.assert_close(a, b, rtol=0, atol=0, msg=k)
+
+
+def test_hf_config_refuses_what_it_cannot_represent():
+    from prime_b200.models import hf
+
+    base = hf.hf_config_from_args(build_model("debugmodel", dtype=torch.float32).args)
+    assert hf.args_from_hf_config(base).ffn_hidden == base["intermediate_size"]
+    with pytest.raises(ValueError, match="rope_scaling"):
+        hf.args_from_hf_config({**base, "rope_scaling": {"rope_type": "llama3", "factor": 8.0}})
+    with pytest.raises(ValueError, match="Llama"):
+        hf.args_from_hf_config({**base, "model_type": "mistral", "architectures": ["MistralForCausalLM"]})
+    with pytest.raises(ValueError, match="bias"):
+        hf.args_from_hf_config({**base, "attention_bias": True})
