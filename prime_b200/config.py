@@ -28,7 +28,9 @@ class _Section(BaseModel):
 class DataConfig(_Section):
     seq_length: int = 1024
     fake: bool = True  # synthetic tokens (no network in the sandbox)
-    dataset_name_or_paths: str = ""
+    dataset_name_or_paths: str = ""  # comma-separated token files (.bin / .npy), directories or globs (tools/tokenize_corpus.py writes them)
+    token_dtype: Literal["auto", "uint16", "uint32"] = "auto"  # raw .bin files: auto = uint16 up to 65 536 vocabulary entries, else uint32
+    shuffle: bool = True  # per-epoch permutation of the sequence windows (seeded by data.seed)
     num_workers: int = 2
     seed: int = 1337
     pin_memory: bool = True

@@ -47,41 +47,118 @@ class FakeTokenDataset:
         self.n_served = sd["n_served"]
 
 
-class MemmapTokenDataset:
-    """Flat uint16/uint32 token file(s); each rank reads a strided set of windows."""
+def _expand_paths(spec: str) -> list[Path]:
+    """Comma-separated files, directories (every ``*.bin`` / ``*.npy`` inside, sorted) or glob patterns."""
+    import glob
 
-    def __init__(self, paths: str, seq_len: int, rank: int = 0, world: int = 1, dtype=np.uint16):
-        files = [Path(p) for p in paths.split(",") if p]
-        if not files:
-            raise ValueError("no dataset paths given")
-        self.arrays = [np.memmap(f, dtype=dtype, mode="r") for f in files]
+    out: list[Path] = []
+    for part in (x.strip() for x in spec.split(",")):
+        if not part:
+            continue
+        p = Path(part)
+        if p.is_dir():
+            found = sorted(f for f in p.iterdir() if f.suffix in (".bin", ".npy"))
+        elif any(c in part for c in "*?["):
+            found = sorted(Path(f) for f in glob.glob(part, recursive=True))
+        else:
+            found = [p]
+        if not found:
+            raise FileNotFoundError(f"dataset path {part!r} matches no token file")
+        out += found
+    if not out:
+        raise ValueError("no dataset paths given")
+    return out
+
+
+def _open_tokens(f: Path, dtype) -> np.ndarray:
+    if f.suffix == ".npy":
+        a = np.load(f, mmap_mode="r")
+        if a.ndim != 1 or a.dtype.kind not in "ui":
+            raise ValueError(f"{f}: expected a 1-D integer token array, got {a.dtype} {a.shape}")
+        return a
+    meta = f.with_suffix(".meta.json")  # written by tools/tokenize_corpus.py next to every shard
+    if meta.exists():
+        import json
+
+        dtype = np.dtype(json.loads(meta.read_text())["dtype"])
+    if f.stat().st_size % np.dtype(dtype).itemsize:
+        raise ValueError(f"{f}: {f.stat().st_size} bytes is not a whole number of {np.dtype(dtype).name} tokens — set data.token_dtype "
+                         "(or keep the .meta.json that tools/tokenize_corpus.py wrote next to the shard)")  # fmt: skip
+    return np.memmap(f, dtype=dtype, mode="r")
+
+
+class MemmapTokenDataset:
+    """Pre-tokenised corpus: flat token files (raw ``.bin`` of uint16 / uint32, or 1-D ``.npy``), cut into windows of
+    ``seq_len + 1`` tokens (inputs and next-token labels).
+
+    * every data rank reads a disjoint strided subset of the windows (sample k of rank r is window ``k·world + r`` of the epoch);
+    * ``shuffle``: the window order of every epoch is an affine permutation ``(a·i + b) mod N`` with ``gcd(a, N) = 1`` derived
+      from (seed, epoch) — a bijection evaluated in O(1), so a 100-billion-token corpus needs no index array and the position
+      is one integer (``cursor``) in the checkpoint;
+    * token ids are range-checked against the model's vocabulary on the way out (a uint16 file read as uint32, or a tokenizer
+      that does not belong to the model, otherwise shows up as a device-side index fault in the embedding much later).
+    """
+
+    def __init__(self, paths: str, seq_len: int, rank: int = 0, world: int = 1, dtype=None, *, vocab_size: int | None = None,
+                 shuffle: bool = True, seed: int = 0):  # fmt: skip
+        if dtype is None:
+            dtype = np.uint16 if (vocab_size or 0) <= 65536 else np.uint32
+        self.files = _expand_paths(paths)
+        self.arrays = [_open_tokens(f, dtype) for f in self.files]
         self.seq_len, self.rank, self.world = seq_len, rank, world
-        self.cursor = 0
-        self.windows = sum((len(a) - 1) // seq_len for a in self.arrays)
+        self.vocab_size, self.shuffle, self.seed = vocab_size, shuffle, seed
+        per_file = np.array([(len(a) - 1) // seq_len for a in self.arrays], dtype=np.int64)
+        self.first_window = np.concatenate([[0], np.cumsum(per_file)])  # window index → file by searchsorted
+        self.windows = int(self.first_window[-1])
+        if self.windows < world:
+            raise ValueError(f"dataset has {self.windows} windows of {seq_len} tokens — fewer than the {world} data ranks")
+        self.cursor = 0  # samples drawn by THIS rank
+        self._perm_epoch, self._perm = -1, (1, 0)
+
+    # -------------------------------------------------------------- order
+    def _affine(self, epoch: int) -> tuple[int, int]:
+        if epoch != self._perm_epoch:
+            import math
+
+            rng = np.random.default_rng([self.seed, epoch])
+            n = self.windows
+            a = int(rng.integers(1, max(n, 2)))
+            while math.gcd(a, n) != 1:
+                a = a + 1 if a + 1 < n else 1
+            self._perm_epoch, self._perm = epoch, (a, int(rng.integers(0, n)))
+        return self._perm
+
+    def _index(self, k: int) -> int:
+        """Window of this rank's k-th sample."""
+        g = k * self.world + self.rank
+        epoch, i = divmod(g, self.windows)
+        if not self.shuffle:
+            return i
+        a, b = self._affine(epoch)
+        return (a * i + b) % self.windows
 
     def _window(self, idx: int) -> np.ndarray:
-        for a in self.arrays:
-            n = (len(a) - 1) // self.seq_len
-            if idx < n:
-                s = idx * self.seq_len
-                return np.asarray(a[s : s + self.seq_len + 1], dtype=np.int64)
-            idx -= n
-        raise IndexError
+        f = int(np.searchsorted(self.first_window, idx, side="right")) - 1
+        s = (idx - int(self.first_window[f])) * self.seq_len
+        return np.asarray(self.arrays[f][s : s + self.seq_len + 1], dtype=np.int64)
 
     def next_batch(self, batch_size: int) -> tuple[np.ndarray, np.ndarray]:
-        rows = []
-        for _ in range(batch_size):
-            idx = (self.cursor * self.world + self.rank) % self.windows
-            rows.append(self._window(idx))
-            self.cursor += 1
-        full = np.stack(rows)
+        full = np.stack([self._window(self._index(self.cursor + j)) for j in range(batch_size)])
+        self.cursor += batch_size
+        if self.vocab_size is not None and int(full.max()) >= self.vocab_size:
+            raise ValueError(f"token id {int(full.max())} ≥ vocab_size {self.vocab_size}: wrong tokenizer for this model, or the file's "
+                             "dtype is not what data.token_dtype says")  # fmt: skip
         return full[:, :-1], full[:, 1:]
+
+    @property
+    def epoch(self) -> int:
+        return (self.cursor * self.world) // self.windows
 
     def state_dict(self) -> dict:
         return {"cursor": self.cursor}
 
     def load_state_dict(self, sd: dict) -> None:
-        self.cursor = sd["cursor"]
+        self.cursor = int(sd["cursor"])
 
 
 class PinnedPrefetcher:
@@ -188,4 +265,6 @@ class PinnedPrefetcher:
 def build_dataset(cfg_data, vocab_size: int, rank: int, world: int):
     if cfg_data.fake or not cfg_data.dataset_name_or_paths:
         return FakeTokenDataset(vocab_size, cfg_data.seq_length, cfg_data.seed, rank, world)
-    return MemmapTokenDataset(cfg_data.dataset_name_or_paths, cfg_data.seq_length, rank, world)
+    dt = {"auto": None, "uint16": np.uint16, "uint32": np.uint32}[getattr(cfg_data, "token_dtype", "auto")]
+    return MemmapTokenDataset(cfg_data.dataset_name_or_paths, cfg_data.seq_length, rank, world, dt, vocab_size=vocab_size,
+                              shuffle=getattr(cfg_data, "shuffle", True), seed=cfg_data.seed)  # fmt: skip
