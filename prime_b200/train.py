@@ -189,6 +189,7 @@ def train(cfg: Config, *, max_steps: int | None = None) -> dict[str, Any]:
     last: dict[str, Any] = {}
     cuda = mesh.device.type == "cuda"
     should_stop = _StopConsensus(stop)
+    logged_at = trainer.step_count  # step of the previous log line: a line can come off the log_interval grid (outer step, last step)
     try:
         while trainer.step_count < total and not should_stop():
             r = trainer.inner_step()
@@ -199,11 +200,12 @@ def train(cfg: Config, *, max_steps: int | None = None) -> dict[str, Any]:
                 loss = float(r.loss)  # the only device→host sync of the step
                 trainer.check_health()  # a device-side peer wait timed out → raise here instead of training on a void step
                 dt = timer.lap()
+                n_steps, logged_at = max(1, step - logged_at), step
                 # tokens of this worker-world only: MFU is per-GPU of THIS process world; global tok/s is scaled by membership
-                meter.update(trainer.tokens_per_step * cfg.monitor.log_interval, dt)
+                meter.update(trainer.tokens_per_step * n_steps, dt)
                 scale = trainer.global_workers if cfg.mesh.elastic else 1
                 last = {"step": step, "loss": round(loss, 5), "lr": r.lr, "grad_norm": float(r.grad_norm) if r.grad_norm is not None else None,
-                        "tokens_per_s": round(meter.tokens_per_s * scale, 1), "mfu": round(meter.mfu, 4), "step_s": round(dt / cfg.monitor.log_interval, 4),
+                        "tokens_per_s": round(meter.tokens_per_s * scale, 1), "mfu": round(meter.mfu, 4), "step_s": round(dt / n_steps, 4),
                         "workers": trainer.global_workers, "outer": r.did_outer, "total_tokens": meter.total_tokens * scale}  # fmt: skip
                 if r.did_outer and trainer.outer is not None:
                     last["outer_s"] = round(trainer.outer.last_seconds, 4)

@@ -106,6 +106,12 @@ class Trainer:
         self.micro_bs = min(cfg.train.micro_bs, per_rank)
         self.accum = max(1, per_rank // self.micro_bs)
         self.tokens_per_step = self.micro_bs * self.accum * cfg.data.seq_length * mesh.world.world_size
+        effective = self.micro_bs * self.accum * mesh.fsdp_size
+        if effective != o.batch_size:
+            import warnings
+
+            warnings.warn(f"optim.batch_size={o.batch_size} is not a multiple of fsdp_size × micro_bs = {mesh.fsdp_size} × {self.micro_bs}: "
+                          f"every worker steps on {effective} sequences", stacklevel=2)  # fmt: skip
         if cfg.mesh.elastic:  # no global rank exists: derive a stable, distinct data stream from the worker's name
             import os
             import zlib
