@@ -58,7 +58,6 @@ from .models import (
     SandboxStatus,
     SSHSession,
 )
-from .rpc_command_session import START_METHOD, OutputCollector, build_start_request
 
 # --------------------------------------------------------------------------------------- policy
 CONNECT_ERRORS = (httpx.RemoteProtocolError, httpx.ConnectError, httpx.PoolTimeout)  # NOT ReadTimeout: may have executed
@@ -375,17 +374,45 @@ class AsyncAuthCache:
 
 # --------------------------------------------------------------------------------------- sync client
 class SandboxClient:
-    def __init__(self, api_client: APIClient | None = None):
+    """All gateway traffic of one client shares ONE pooled, thread-safe ``httpx.Client`` with per-request timeouts (keep-alive
+    connections, one TLS context). The reference builds a fresh ``httpx.Client`` for every gateway request — a new TLS context
+    (≈20 ms of ``load_verify_locations``) and a new connection per command; `tools/platform_bench.py` measures the difference."""
+
+    def __init__(self, api_client: APIClient | None = None, max_connections: int = 100, max_keepalive_connections: int = 32):
         self.client = api_client or APIClient(user_agent=sandboxes_user_agent(), retry=TRANSPORT_RETRY)
         self._auth_cache = AuthCache(self.client.config.config_dir / "sandbox_auth_cache.json", self.client)
         self._sleep = time.sleep  # injectable for tests
+        self._limits = httpx.Limits(max_connections=max_connections, max_keepalive_connections=max_keepalive_connections)
+        self._gw: httpx.Client | None = None
+        self._gw_lock = threading.Lock()
+
+    def _pool(self) -> httpx.Client:
+        gw = self._gw
+        if gw is None or gw.is_closed:
+            with self._gw_lock:
+                gw = self._gw
+                if gw is None or gw.is_closed:
+                    gw = self._gw = httpx.Client(limits=self._limits, timeout=None)
+        return gw
+
+    def close(self) -> None:
+        """Release the pooled gateway connections (the client stays usable: the pool is rebuilt on demand)."""
+        with self._gw_lock:
+            gw, self._gw = self._gw, None
+        if gw is not None and not gw.is_closed:
+            gw.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
     # ---- gateway I/O with the idempotency-aware retry split
     def _gateway(self, method: str, url: str, *, idempotent: bool, headers: dict, timeout: float, **kw) -> httpx.Response:
         for attempt in range(GATEWAY_ATTEMPTS):
             try:
-                with httpx.Client(timeout=timeout) as c:
-                    resp = c.request(method, url, headers=headers, **kw)
+                resp = self._pool().request(method, url, headers=headers, timeout=timeout, **kw)
                 if idempotent and resp.status_code in RETRYABLE_5XX:
                     resp.raise_for_status()
                 return resp
@@ -473,6 +500,8 @@ class SandboxClient:
         from connectrpc.client import ConnectClientSync
         from connectrpc.code import Code
         from connectrpc.errors import ConnectError
+
+        from .rpc_command_session import START_METHOD, OutputCollector, build_start_request  # protobuf: only VM sandboxes pay for the import
 
         limit = timeout if timeout is not None else DEFAULT_COMMAND_TIMEOUT
         rpc = ConnectClientSync(gateway_url(auth))
@@ -828,6 +857,8 @@ class AsyncSandboxClient:
         from connectrpc.client import ConnectClient
         from connectrpc.code import Code
         from connectrpc.errors import ConnectError
+
+        from .rpc_command_session import START_METHOD, OutputCollector, build_start_request
 
         limit = timeout if timeout is not None else DEFAULT_COMMAND_TIMEOUT
         rpc = ConnectClient(gateway_url(auth))

@@ -182,17 +182,16 @@ def test_retry_split_by_idempotency(isolated_home, monkeypatch):
     c, _ = make_client(isolated_home)
     calls = []
 
+    built = []
+
     class FakeHttpxClient:
-        def __init__(self, timeout=None):
-            pass
+        is_closed = False
 
-        def __enter__(self):
-            return self
-
-        def __exit__(self, *a):
-            return False
+        def __init__(self, timeout=None, limits=None):
+            built.append(self)
 
         def request(self, method, url, headers=None, **kw):
+            assert kw.pop("timeout") == 1  # the pooled client carries no default: every request brings its own limit
             calls.append(method)
             if len(calls) < 3:
                 return resp(503, {"detail": "x"}, url=url, method=method)
@@ -204,6 +203,7 @@ def test_retry_split_by_idempotency(isolated_home, monkeypatch):
     calls.clear()
     r = c._gateway_post("https://gw.example/ns/job/exec", headers={}, timeout=1, json={})
     assert r.status_code == 503 and len(calls) == 1  # not retried: the server saw it
+    assert len(built) == 1  # one pooled gateway client for all of it (the reference builds one per request)
 
 
 def test_retryable_predicate():
