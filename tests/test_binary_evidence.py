@@ -88,3 +88,21 @@ def test_ncu_source_hotspots_condenses_runs(tmp_path, capsys):
     out = capsys.readouterr().out
     assert "4 instructions, 100 stall samples" in out
     assert "exec       100" in out and "FFMA 90" in out and "(90.0 %)" in out
+
+
+def test_step_composition_is_reproducible_from_the_committed_launch_list(capsys):
+    """profiles/step_composition_r2_final.md is what tools/launch_breakdown.py prints for the committed ncu launch list."""
+    import sys
+
+    sys.path.insert(0, str(ROOT))
+    from tools.launch_breakdown import family, main
+
+    csv = ROOT / "profiles" / "launches_1gpu_step_r2_final.csv"
+    if not csv.exists():
+        pytest.skip("launch list not committed")
+    main(str(csv))
+    out = capsys.readouterr().out
+    rows = {ln.split("|")[1].strip(): float(ln.split("|")[4].strip().rstrip(" %")) for ln in out.splitlines() if ln.startswith("| ") and ln.rstrip().endswith("% |") and "`" not in ln}
+    assert rows["GEMM (tcgen05)"] > 70 and rows["attention"] < 16 and rows["torch / runtime kernels"] < 0.5, rows
+    assert family("void <unnamed>::gemm_bf16_kernel<1, 1, 1, 0, 0>(CUtensorMap_st)") == "GEMM (tcgen05)"
+    assert family("void at::native::vectorized_elementwise_kernel<4, at::native::FillFunctor<float>>") == "torch / runtime kernels"
