@@ -2,7 +2,7 @@
 
 from ..core import APIError, APITimeoutError, Config, PaymentRequiredError, UnauthorizedError  # noqa: F401
 from ..core.client import APIClient, AsyncAPIClient  # noqa: F401
-from .evals import AsyncEvalsClient, EvalsClient, build_batches  # noqa: F401
+from .evals import AsyncEvalsClient, EvalsClient, build_batches, encode_batches  # noqa: F401
 from .exceptions import EnvironmentNotFoundError, EvalsAPIError, EvaluationNotFoundError, InvalidEvaluationError, InvalidSampleError  # noqa: F401
 from .models import (  # noqa: F401
     CreateEvaluationRequest,

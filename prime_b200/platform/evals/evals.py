@@ -16,7 +16,7 @@ import json
 import time
 import warnings
 from concurrent.futures import ThreadPoolExecutor, as_completed
-from typing import Any, Callable
+from typing import Any
 
 import httpx
 
@@ -57,6 +57,36 @@ def build_batches(samples: list[dict[str, Any]], max_payload_bytes: int = MAX_PA
     if cur:
         batches.append(cur)
     return batches, skipped
+
+
+def encode_batches(samples: list[dict[str, Any]], max_payload_bytes: int = MAX_PAYLOAD_BYTES) -> tuple[list[tuple[bytes, int]], int]:
+    """Same cut as :func:`build_batches` (same size accounting, so the same batch boundaries), but every sample is serialised
+    exactly ONCE: the request bodies are assembled from the per-sample encodings that the size check produced anyway. The
+    reference measures a sample with ``json.dumps`` and then lets httpx serialise the whole batch again.
+    → ([(request body, number of samples)], skipped)"""
+    out: list[tuple[bytes, int]] = []
+    cur: list[str] = []
+    used, skipped = ENVELOPE_BYTES, 0
+
+    def flush() -> None:
+        out.append((('{"samples": [' + ", ".join(cur) + "]}").encode("ascii"), len(cur)))
+
+    for i, s in enumerate(samples):
+        enc = json.dumps(s)  # ensure_ascii: characters == bytes
+        size = len(enc) + 1
+        if size + ENVELOPE_BYTES > max_payload_bytes:
+            warnings.warn(f"Sample {i} exceeds maximum payload size ({size} bytes > {max_payload_bytes - ENVELOPE_BYTES} "
+                          "bytes limit), skipping", stacklevel=3)  # fmt: skip
+            skipped += 1
+            continue
+        if cur and used + size > max_payload_bytes:
+            flush()
+            cur, used = [], ENVELOPE_BYTES
+        cur.append(enc)
+        used += size
+    if cur:
+        flush()
+    return out, skipped
 
 
 def normalise_env_ref(env: str | dict[str, str]) -> tuple[str, str, dict[str, str]] | None:
@@ -143,8 +173,20 @@ class _Common:
 
 
 class EvalsClient(_Common):
-    _post: Callable[..., httpx.Response] = staticmethod(httpx.post)  # injectable for tests
     _sleep = staticmethod(time.sleep)
+    _http: httpx.Client | None = None
+
+    def _post(self, url: str, **kw: Any) -> httpx.Response:
+        """Sample uploads share one pooled client (``httpx.post`` — what the reference calls — builds a client, i.e. a TLS context
+        and a connection, per batch). Injectable for tests."""
+        if self._http is None or self._http.is_closed:
+            self._http = httpx.Client(timeout=30.0)
+        return self._http.post(url, **kw)
+
+    def close(self) -> None:
+        if self._http is not None and not self._http.is_closed:
+            self._http.close()
+        self._http = None
 
     def _resolve_one(self, kind: str, value: str) -> str:
         endpoint, body, err = lookup_request(kind, value, self.client.config.team_id)
@@ -178,13 +220,19 @@ class EvalsClient(_Common):
             check_resolved(resolved, fields.get("run_id"))
         return self.client.request("POST", "/evaluations/", json=evaluation_payload(name, resolved, self.client.config.team_id, is_public, **fields))
 
-    def _upload_batch(self, evaluation_id: str, batch: list[dict]) -> int:
+    def _upload_batch(self, evaluation_id: str, batch: list[dict] | tuple[bytes, int]) -> int:
+        """``batch``: an encoded (body, count) pair from :func:`encode_batches`, or a plain list of samples."""
+        if isinstance(batch, tuple):
+            body, count = batch
+        else:
+            body, count = json.dumps({"samples": batch}).encode("ascii"), len(batch)
         url, headers = self._upload_target(evaluation_id)
+        headers = {**headers, "Content-Type": "application/json"}
         for attempt in range(UPLOAD_ATTEMPTS):
             try:
-                r = self._post(url, json={"samples": batch}, headers=headers, timeout=30.0)
+                r = self._post(url, content=body, headers=headers, timeout=30.0)
                 r.raise_for_status()
-                return len(batch)
+                return count
             except (httpx.HTTPStatusError, httpx.RequestError) as e:
                 if attempt + 1 < UPLOAD_ATTEMPTS and is_retryable_upload(e):
                     self._sleep(upload_backoff(attempt))
@@ -200,7 +248,7 @@ class EvalsClient(_Common):
             return {"samples_pushed": 0, "samples_skipped": 0}
         if max_workers < 1:
             raise ValueError("max_workers must be at least 1")
-        batches, skipped = build_batches(samples, max_payload_bytes)
+        batches, skipped = encode_batches(samples, max_payload_bytes)
         pushed, errors = 0, []
         with ThreadPoolExecutor(max_workers=max_workers) as pool:
             futs = {pool.submit(self._upload_batch, evaluation_id, b): i for i, b in enumerate(batches)}
@@ -270,13 +318,18 @@ class AsyncEvalsClient(_Common):
         body = evaluation_payload(name, resolved, self.client.config.team_id, is_public, **fields)
         return await self.client.request("POST", "/evaluations/", json=body)
 
-    async def _upload_batch(self, http: httpx.AsyncClient, evaluation_id: str, batch: list[dict]) -> int:
+    async def _upload_batch(self, http: httpx.AsyncClient, evaluation_id: str, batch: list[dict] | tuple[bytes, int]) -> int:
+        if isinstance(batch, tuple):
+            body, count = batch
+        else:
+            body, count = json.dumps({"samples": batch}).encode("ascii"), len(batch)
         url, headers = self._upload_target(evaluation_id)
+        headers = {**headers, "Content-Type": "application/json"}
         for attempt in range(UPLOAD_ATTEMPTS):
             try:
-                r = await http.post(url, json={"samples": batch}, headers=headers, timeout=30.0)
+                r = await http.post(url, content=body, headers=headers, timeout=30.0)
                 r.raise_for_status()
-                return len(batch)
+                return count
             except (httpx.HTTPStatusError, httpx.RequestError) as e:
                 if attempt + 1 < UPLOAD_ATTEMPTS and is_retryable_upload(e):
                     await self._sleep(upload_backoff(attempt))
@@ -292,12 +345,12 @@ class AsyncEvalsClient(_Common):
             return {"samples_pushed": 0, "samples_skipped": 0}
         if max_concurrent < 1:
             raise ValueError("max_concurrent must be at least 1")
-        batches, skipped = build_batches(samples, max_payload_bytes)
+        batches, skipped = encode_batches(samples, max_payload_bytes)
         sem = asyncio.Semaphore(max_concurrent)
         own = self._http is None
         http = self._http or httpx.AsyncClient()
 
-        async def one(i: int, b: list[dict]) -> int | str:
+        async def one(i: int, b: tuple[bytes, int]) -> int | str:
             async with sem:
                 try:
                     return await self._upload_batch(http, evaluation_id, b)

@@ -225,8 +225,10 @@ def test_eval_push_discovers_parses_and_uploads(tmp_path, monkeypatch):
 
     uploads = []
 
-    def fake_post(url, json=None, headers=None, timeout=None):
-        uploads.append((url, json, headers))
+    def fake_post(url, content=None, headers=None, timeout=None):
+        import json as _json
+
+        uploads.append((url, _json.loads(content), headers))
         return httpx.Response(200, json={}, request=httpx.Request("POST", url))
 
     monkeypatch.setattr(EvalsClient, "_post", staticmethod(fake_post))

@@ -121,3 +121,21 @@ def test_new_evaluations_are_private_unless_asked(tmp_path, public):
     evals = RecordingEvals()
     assert push_single_eval(str(tmp_path), "gsm8k", None, None, is_public=public, evals=evals) == "eval-new"
     assert evals.created["is_public"] is public and evals.created["environments"] == [{"name": "gsm8k"}]
+
+
+def test_encoded_batches_cut_where_build_batches_cuts():
+    """The upload path serialises every sample once; its batches must be exactly the reference's (same size accounting)."""
+    import json
+
+    from prime_b200.platform.evals import build_batches, encode_batches
+
+    samples = [{"example_id": i, "reward": i / 7, "completion": [{"role": "assistant", "content": "é✓" * (50 + 13 * (i % 29))}]} for i in range(400)]
+    for limit in (2_000, 10_000, 2 * 1024 * 1024):
+        plain, skipped_a = build_batches(samples, limit)
+        encoded, skipped_b = encode_batches(samples, limit)
+        assert skipped_a == skipped_b and [len(b) for b in plain] == [n for _, n in encoded]
+        for batch, (body, n) in zip(plain, encoded):
+            assert json.loads(body) == {"samples": batch} and len(body) <= limit and body.isascii()
+    with pytest.warns(UserWarning, match="exceeds maximum payload size"):
+        enc, skipped = encode_batches([{"x": "y" * 5000}, {"x": "ok"}], 1000)
+    assert skipped == 1 and [n for _, n in enc] == [1]
