@@ -9,6 +9,8 @@ from pydantic import Field, field_validator
 
 from ._base import ApiModel, unwrap_single_none, wrap
 
+clean_connection_fields = unwrap_single_none  # the reference's public name of the same validator helper (api/pods.py:9)
+
 
 class PortMapping(ApiModel):
     internal: str

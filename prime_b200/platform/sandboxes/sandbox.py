@@ -372,6 +372,11 @@ class AsyncAuthCache:
             self._store.save()
 
 
+# the reference's public names of the two caches (sandbox.py: SandboxAuthCache / AsyncSandboxAuthCache)
+SandboxAuthCache = AuthCache
+AsyncSandboxAuthCache = AsyncAuthCache
+
+
 # --------------------------------------------------------------------------------------- sync client
 class SandboxClient:
     """All gateway traffic of one client shares ONE pooled, thread-safe ``httpx.Client`` with per-request timeouts (keep-alive

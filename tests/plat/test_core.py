@@ -181,3 +181,53 @@ def test_package_export_surfaces_match_the_reference():
     assert E.FinalizeEvaluationRequest().metrics is None
     assert Tn.Config is P.Config
     assert callable(M.make_prime_request) and M.pods.__name__.endswith("tools.pods") and M.ssh and M.availability
+
+
+# ------------------------------------------------------------------------------------------------ drop-in import names
+def test_compat_aliases_resolve_reference_import_paths():
+    """Code written against the reference packages keeps its imports: the aliases are the real module objects."""
+    import sys
+
+    from prime_b200 import compat
+
+    registered = compat.install()
+    try:
+        assert {"prime_sandboxes", "prime_evals", "prime_tunnel", "prime_cli", "prime_sandboxes.models", "prime_cli.api.pods"} <= set(registered)
+        from prime_cli.api.pods import PodsClient, clean_connection_fields  # noqa: F401
+        from prime_cli.core import Config as CliConfig
+        from prime_evals import EvalsClient
+        from prime_sandboxes import APIError, CreateSandboxRequest, SandboxClient
+        from prime_sandboxes.models import Sandbox
+        from prime_sandboxes.sandbox import SandboxAuthCache  # noqa: F401
+
+        import prime_b200.platform.sandboxes as real
+
+        assert SandboxClient is real.SandboxClient and Sandbox is real.Sandbox and CreateSandboxRequest is real.CreateSandboxRequest
+        from prime_b200.platform.core import APIError as CoreAPIError
+        from prime_b200.platform.core import Config
+        from prime_b200.platform.evals import EvalsClient as RealEvals
+
+        assert APIError is CoreAPIError and CliConfig is Config and EvalsClient is RealEvals  # ONE class hierarchy: except clauses keep matching
+        from prime_cli.main import app  # the Typer root
+
+        assert app.info.name == "prime"
+    finally:
+        compat.uninstall()
+    assert "prime_sandboxes" not in sys.modules and "prime_cli.api.pods" not in sys.modules
+
+
+def test_compat_covers_every_public_name_of_the_reference():
+    from pathlib import Path
+
+    from prime_b200 import compat
+
+    ref = Path("/root/reference/packages")
+    if not ref.is_dir():
+        pytest.skip("reference tree not mounted")
+    try:
+        res = compat.check(ref)
+    finally:
+        compat.uninstall()
+    assert set(res) == {"prime_cli", "prime_sandboxes", "prime_evals", "prime_tunnel", "prime_mcp"}
+    for pkg, r in res.items():
+        assert "error" not in r and r["missing"] == [] and r["public_names"] >= 5, (pkg, r)
