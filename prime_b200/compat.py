@@ -126,6 +126,80 @@ def check(packages_dir: str | Path) -> dict[str, dict]:
     return out
 
 
+_SIG_CODE = r"""
+import importlib, inspect, json, sys
+out = {}
+for modname in sys.argv[1:]:
+    try:
+        m = importlib.import_module(modname)
+    except Exception as e:
+        out[modname] = {"!": type(e).__name__ + ": " + str(e)[:100]}
+        continue
+    names = getattr(m, "__all__", None) or [n for n, v in vars(m).items() if not n.startswith("_") and inspect.isclass(v) and v.__module__ == m.__name__]
+    d = {}
+    for n in names:
+        v = getattr(m, n, None)
+        if inspect.isclass(v):
+            meths = {}
+            for mn, mv in inspect.getmembers(v):
+                if (mn.startswith("_") and mn != "__init__") or not (inspect.isfunction(mv) or inspect.ismethod(mv)):
+                    continue
+                try:
+                    meths[mn] = [p for p in inspect.signature(mv).parameters if p != "self"]
+                except Exception:
+                    meths[mn] = None
+            d[n] = meths
+        elif inspect.isfunction(v):
+            d[n] = {"()": list(inspect.signature(v).parameters)}
+    out[modname] = d
+print(json.dumps(out))
+"""
+SIGNATURE_MODULES = ("prime_sandboxes", "prime_evals", "prime_tunnel", "prime_mcp", "prime_cli.api.pods", "prime_cli.api.availability",
+                     "prime_cli.api.disks", "prime_cli.api.rl", "prime_cli.api.deployments", "prime_cli.api.inference", "prime_cli.core.client",
+                     "prime_cli.core.config")  # fmt: skip
+
+
+def check_signatures(packages_dir: str | Path) -> dict:
+    """Every public class of the reference's SDK packages and API clients: do its public methods exist here, and does each
+    accept the reference's parameter names? (pydantic validator methods — ``validate_*`` — are implementation detail and ignored)"""
+    import inspect
+    import os
+
+    env = {**os.environ, "PYTHONPATH": os.pathsep.join(str(Path(packages_dir) / d / "src") for d in _REF_DIRS.values())}
+    r = subprocess.run([sys.executable, "-c", _SIG_CODE, *SIGNATURE_MODULES], env=env, capture_output=True, text=True, cwd="/", timeout=300)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr[-2000:])
+    ref = json.loads(r.stdout.strip().splitlines()[-1])
+    install()
+    compared, missing, param_diffs, errors = 0, [], [], []
+    for modname, classes in ref.items():
+        if "!" in classes:
+            errors.append(f"{modname}: {classes['!']}")
+            continue
+        mod = sys.modules.get(modname) or importlib.import_module(modname)
+        for cname, meths in classes.items():
+            cls = getattr(mod, cname, None)
+            if cls is None:
+                missing.append(f"{modname}.{cname}")
+                continue
+            for mn, params in meths.items():
+                if mn.startswith("validate_"):
+                    continue
+                compared += 1
+                f = cls if mn == "()" else getattr(cls, mn, None)
+                if f is None:
+                    missing.append(f"{modname}.{cname}.{mn}")
+                    continue
+                try:
+                    ours = [p for p in inspect.signature(f).parameters if p != "self"]
+                except (TypeError, ValueError):
+                    continue
+                catch_all = any(p.kind is inspect.Parameter.VAR_KEYWORD for p in inspect.signature(f).parameters.values())
+                if params is not None and not catch_all and any(p not in ours for p in params):
+                    param_diffs.append(f"{modname}.{cname}.{mn}: reference {params}, here {ours}")
+    return {"methods_compared": compared, "missing": missing, "parameter_name_differences": param_diffs, "errors": errors}
+
+
 def main(argv: list[str] | None = None) -> int:
     import argparse
 
@@ -133,14 +207,19 @@ def main(argv: list[str] | None = None) -> int:
     sub = ap.add_subparsers(dest="cmd", required=True)
     c = sub.add_parser("check")
     c.add_argument("--reference", default="/root/reference/packages")
+    c.add_argument("--methods", action="store_true", help="also compare the public methods and parameter names of every public class")
     sub.add_parser("list")
     a = ap.parse_args(argv)
     if a.cmd == "list":
         print(json.dumps(install(), indent=1))
         return 0
-    res = check(a.reference)
+    res: dict = check(a.reference)
+    bad = any(v.get("missing") or v.get("error") for v in res.values())
+    if a.methods:
+        res["signatures"] = check_signatures(a.reference)
+        bad = bad or bool(res["signatures"]["missing"] or res["signatures"]["parameter_name_differences"] or res["signatures"]["errors"])
     print(json.dumps(res, indent=1))
-    return 1 if any(v.get("missing") or v.get("error") for v in res.values()) else 0
+    return 1 if bad else 0
 
 
 if __name__ == "__main__":

@@ -281,7 +281,12 @@ class EvalsClient(_Common):
 class AsyncEvalsClient(_Common):
     _sleep = staticmethod(asyncio.sleep)
 
-    def __init__(self, api_client: Any, http: httpx.AsyncClient | None = None) -> None:
+    def __init__(self, api_client: Any = None, http: httpx.AsyncClient | None = None, *, api_key: str | None = None) -> None:
+        """``AsyncEvalsClient(api_key="…")`` / ``AsyncEvalsClient("…")`` as in the reference (evals.py:383-384), or an explicit client."""
+        if api_client is None or isinstance(api_client, str):
+            from ..core.client import AsyncAPIClient
+
+            api_client = AsyncAPIClient(api_key=api_key or api_client, user_agent=user_agent("prime-b200-evals"))
         super().__init__(api_client)
         self._http = http
 

@@ -38,8 +38,15 @@ class SandboxImagePullError(SandboxNotRunningError):
 class _OpTimeout(RuntimeError):
     template = "{what} timed out after {timeout}s in sandbox {sandbox_id}"
 
-    def __init__(self, sandbox_id: str, target: str, timeout: int):
+    target_name = "target"  # the reference's name of the second constructor argument / attribute (command, file_path)
+
+    def __init__(self, sandbox_id: str, target: str | None = None, timeout: int | None = None, **named: str):
+        if target is None and self.target_name in named:
+            target = named.pop(self.target_name)
+        if named or target is None or timeout is None:
+            raise TypeError(f"{type(self).__name__}(sandbox_id, {self.target_name}, timeout)")
         self.sandbox_id, self.target, self.timeout = sandbox_id, target, timeout
+        setattr(self, self.target_name, target)
         super().__init__(self.template.format(what=self.describe(target), timeout=timeout, sandbox_id=sandbox_id))
 
     def describe(self, target: str) -> str:
@@ -47,16 +54,22 @@ class _OpTimeout(RuntimeError):
 
 
 class CommandTimeoutError(_OpTimeout):
+    target_name = "command"
+
     def describe(self, target: str) -> str:
         return f"Command '{target}'"
 
 
 class UploadTimeoutError(_OpTimeout):
+    target_name = "file_path"
+
     def describe(self, target: str) -> str:
         return f"Upload to '{target}'"
 
 
 class DownloadTimeoutError(_OpTimeout):
+    target_name = "file_path"
+
     def describe(self, target: str) -> str:
         return f"Download from '{target}'"
 

@@ -1114,6 +1114,15 @@ class AsyncTemplateClient:
     def __init__(self, api_client: AsyncAPIClient | None = None):
         self.client = api_client or AsyncAPIClient(user_agent=sandboxes_user_agent())
 
+    async def aclose(self) -> None:
+        await self.client.aclose()
+
+    async def __aenter__(self):
+        return self
+
+    async def __aexit__(self, *exc):
+        await self.aclose()
+
     async def list_registry_credentials(self) -> list[RegistryCredentialSummary]:
         resp = await self.client.request("GET", "/template/registry-credentials")
         return [RegistryCredentialSummary.model_validate(x) for x in resp.get("credentials", resp.get("data", []))]

@@ -9,7 +9,8 @@ from typing import Any
 
 import httpx
 
-from ..core.client import IDEMPOTENT_RETRY, TRANSPORT_RETRY, RetryPolicy, user_agent
+from ..core.client import IDEMPOTENT_RETRY, TRANSPORT_RETRY, RetryPolicy
+from ..core.client import user_agent as _default_user_agent
 from ..core.config import Config
 from .exceptions import TunnelAuthError, TunnelError, TunnelLimitReachedError, TunnelTimeoutError
 from .models import TunnelInfo
@@ -38,12 +39,12 @@ def interpret(resp: httpx.Response, operation: str) -> dict[str, Any]:
 
 class TunnelClient:
     def __init__(self, api_key: str | None = None, timeout: float = 30.0, config: Config | None = None,
-                 transport: httpx.AsyncBaseTransport | None = None):  # fmt: skip
+                 transport: httpx.AsyncBaseTransport | None = None, user_agent: str | None = None):  # fmt: skip
         self.config = config or Config(writable=False)
         self.api_key = api_key or self.config.api_key
         self.base_url = self.config.base_url
         self._timeout, self._transport = timeout, transport
-        self._headers = {"Content-Type": "application/json", "User-Agent": user_agent("prime-b200-tunnel")}
+        self._headers = {"Content-Type": "application/json", "User-Agent": user_agent or _default_user_agent("prime-b200-tunnel")}
         if self.api_key:
             self._headers["Authorization"] = f"Bearer {self.api_key}"
         self._http: httpx.AsyncClient | None = None

@@ -231,3 +231,47 @@ def test_compat_covers_every_public_name_of_the_reference():
     assert set(res) == {"prime_cli", "prime_sandboxes", "prime_evals", "prime_tunnel", "prime_mcp"}
     for pkg, r in res.items():
         assert "error" not in r and r["missing"] == [] and r["public_names"] >= 5, (pkg, r)
+
+
+def test_reference_constructor_spellings_are_accepted(isolated_home):
+    """Signature differences found by comparing 1 470 public methods with the reference: keyword names a caller may use."""
+    import asyncio
+
+    from prime_b200.platform.evals import AsyncEvalsClient
+    from prime_b200.platform.sandboxes import AsyncTemplateClient, CommandTimeoutError, DownloadTimeoutError, UploadTimeoutError
+    from prime_b200.platform.tunnel.client import TunnelClient
+
+    e = CommandTimeoutError(sandbox_id="s1", command="sleep 9", timeout=5)
+    assert (e.sandbox_id, e.command, e.target, e.timeout) == ("s1", "sleep 9", "sleep 9", 5) and "Command 'sleep 9' timed out after 5s" in str(e)
+    assert UploadTimeoutError("s1", file_path="/a", timeout=3).file_path == "/a" and DownloadTimeoutError("s1", "/b", 2).file_path == "/b"
+    with pytest.raises(TypeError):
+        CommandTimeoutError("s1", timeout=5)
+
+    async def go():
+        c = AsyncEvalsClient(api_key="k1")
+        assert c.client.api_key == "k1"
+        await c.aclose()
+        async with AsyncEvalsClient("k2") as c2:
+            assert c2.client.api_key == "k2"
+        async with AsyncTemplateClient() as t:
+            assert hasattr(t, "check_docker_image")
+        tc = TunnelClient(api_key="k", user_agent="my-agent/1.0", timeout=5)
+        assert tc._headers["User-Agent"] == "my-agent/1.0"
+        await tc.close()
+
+    asyncio.run(go())
+
+
+def test_compat_every_public_method_of_the_reference_exists_with_its_parameter_names():
+    from pathlib import Path
+
+    from prime_b200 import compat
+
+    ref = Path("/root/reference/packages")
+    if not ref.is_dir():
+        pytest.skip("reference tree not mounted")
+    try:
+        res = compat.check_signatures(ref)
+    finally:
+        compat.uninstall()
+    assert res["methods_compared"] > 1400 and res["missing"] == [] and res["parameter_name_differences"] == [] and res["errors"] == [], res
