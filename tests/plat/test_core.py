@@ -275,3 +275,21 @@ def test_compat_every_public_method_of_the_reference_exists_with_its_parameter_n
     finally:
         compat.uninstall()
     assert res["methods_compared"] > 1400 and res["missing"] == [] and res["parameter_name_differences"] == [] and res["errors"] == [], res
+
+
+def test_wire_requests_are_identical_to_the_reference(capsys):
+    """tools/wire_diff.py: one script (reference import names) against both implementations and a recording server — the HTTP
+    requests (method, path, query, JSON body, auth header) and the parsed results of 42 SDK / API-client calls must not differ."""
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[2]
+    if not Path("/root/reference/packages").is_dir():
+        pytest.skip("reference tree not mounted")
+    sys.path.insert(0, str(root))
+    from tools import wire_diff
+
+    rc = wire_diff.main()
+    out = json.loads(capsys.readouterr().out)
+    assert rc == 0 and out["calls"] >= 42 and out["requests_reference"] == out["requests_ours"] >= 48
+    assert out["outcome_differences"] == [] and out["request_differences"] == [] and set(out["outcomes"].values()) == {"ok"}

@@ -1,0 +1,242 @@
+#!/usr/bin/env python
+"""Differential wire test: ONE script, written against the reference's import names, runs against the unmodified reference
+packages and against this repo (through ``prime_b200.compat``); a recording fake server logs every HTTP request each arm
+sends. The request sequences (method, path, query, JSON body) and the outcome of every call must be identical.
+
+    python tools/wire_diff.py > profiles/wire_diff.json        # exit code 1 on any difference
+
+What it covers: 40 SDK / API-client calls (sandbox lifecycle, command execution, file transfer, ports, SSH sessions, bulk delete,
+evaluation create / push / finalize / list, pods, disks, availability). What it cannot cover: responses of the real service.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+from pathlib import Path
+from urllib.parse import parse_qsl, urlsplit
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path(os.environ.get("PRIME_REFERENCE_PACKAGES", "/root/reference/packages"))
+REF_PATHS = [str(REF / p / "src") for p in ("prime", "prime-evals", "prime-sandboxes", "prime-tunnel", "prime-mcp-server")]
+T = "2025-01-01T00:00:00Z"
+SB = {"id": "s1", "name": "bench", "dockerImage": "python:3.11-slim", "startCommand": None, "cpuCores": 2, "memoryGB": 4, "diskSizeGB": 10,
+      "diskMountPath": "/workspace", "gpuCount": 0, "gpuType": None, "vm": False, "status": "RUNNING", "timeoutMinutes": 60, "createdAt": T,
+      "updatedAt": T, "userId": "u1", "teamId": None}  # fmt: skip
+PORT = {"exposure_id": "e1", "sandbox_id": "s1", "port": 8000, "name": "web", "url": "https://x", "tls_socket": "x:443", "protocol": "HTTP"}
+POD = {"id": "p1", "name": "pod", "gpuName": "H100_80GB", "gpuCount": 1, "status": "ACTIVE", "createdAt": T, "updatedAt": T, "providerType": "x",
+       "installationStatus": "FINISHED", "teamId": None, "socket": "ON_DEMAND", "priceHr": 1.0, "userId": "u1", "type": "HOSTED", "resources": None,
+       "ip": "1.2.3.4", "sshConnection": [None]}  # fmt: skip
+DISK = {"id": "d1", "name": "disk", "size": 100, "status": "ACTIVE", "createdAt": T, "updatedAt": T, "providerType": "x", "userId": "u1", "teamId": None,
+        "priceHr": 0.1, "info": {"country": "US", "dataCenterId": "dc", "cloudId": "c", "isMultinode": False}, "pods": [], "clusters": []}  # fmt: skip
+
+
+def respond(method: str, path: str, host: str):
+    r = [
+        ("POST", r"/api/v1/sandbox/s1/auth$", {"gateway_url": f"http://{host}/gw", "user_ns": "ns", "job_id": "job", "token": "tok", "expires_at": "2099-01-01T00:00:00Z", "is_vm": False}),
+        ("POST", r"/api/v1/sandbox/s1/expose$", PORT), ("GET", r"/api/v1/sandbox/s1/expose$", {"exposures": [PORT]}),
+        ("GET", r"/api/v1/sandbox/expose/all$", {"exposures": [PORT]}), ("DELETE", r"/api/v1/sandbox/s1/expose/e1$", {}),
+        ("POST", r"/api/v1/sandbox/s1/ssh-session$", {"session_id": "ss1", "exposure_id": "e1", "sandbox_id": "s1", "host": "h", "port": 22, "external_endpoint": "h:22", "expires_at": "2099-01-01T00:00:00Z", "ttl_seconds": 600, "gateway_url": "g", "user_ns": "ns", "job_id": "job", "token": "t"}),
+        ("DELETE", r"/api/v1/sandbox/s1/ssh-session/ss1$", {}),
+        ("GET", r"/api/v1/sandbox/s1/logs$", {"logs": "hello"}), ("GET", r"/api/v1/sandbox/s1/error-context$", {"status": "RUNNING"}),
+        ("GET", r"/api/v1/sandbox/s1$", SB), ("DELETE", r"/api/v1/sandbox/s1$", {"status": "deleted"}),
+        ("DELETE", r"/api/v1/sandbox$", {"succeeded": ["s1"], "failed": [], "message": "ok"}),
+        ("POST", r"/api/v1/sandbox$", SB), ("GET", r"/api/v1/sandbox$", {"sandboxes": [SB], "total": 1, "page": 1, "perPage": 50, "hasNext": False}),
+        ("POST", r"/gw/ns/job/exec$", {"stdout": "ok\n", "stderr": "", "exit_code": 0}),
+        ("POST", r"/gw/ns/job/upload$", {"success": True, "path": "/tmp/a.txt", "size": 5, "timestamp": T}),
+        ("GET", r"/gw/ns/job/read-file$", {"content": "hello", "size": 5}), ("GET", r"/gw/ns/job/download$", b"hello"),
+        ("POST", r"/api/v1/environmentshub/lookup$", {"data": {"id": "env1"}}), ("GET", r"/api/v1/environmentshub/", {"data": {"id": "env1"}}),
+        ("POST", r"/api/v1/evaluations/ev1/samples$", {"status": "ok"}), ("POST", r"/api/v1/evaluations/ev1/finalize$", {"evaluation_id": "ev1", "status": "COMPLETED"}),
+        ("GET", r"/api/v1/evaluations/ev1/samples$", {"samples": [], "total": 0}), ("GET", r"/api/v1/evaluations/ev1$", {"evaluation_id": "ev1", "name": "n"}),
+        ("PUT", r"/api/v1/evaluations/ev1$", {"evaluation_id": "ev1"}), ("POST", r"/api/v1/evaluations/$", {"evaluation_id": "ev1", "id": "ev1"}),
+        ("GET", r"/api/v1/evaluations/$", {"evaluations": [], "total": 0}),
+        ("GET", r"/api/v1/pods/status$", {"data": [{"podId": "p1", "providerType": "x", "status": "ACTIVE", "sshConnection": [None], "ip": "1.2.3.4"}]}),
+        ("GET", r"/api/v1/pods/history$", {"total_count": 0, "offset": 0, "limit": 100, "data": []}),
+        ("GET", r"/api/v1/pods/p1$", POD), ("DELETE", r"/api/v1/pods/p1$", {}), ("POST", r"/api/v1/pods/?$", POD),
+        ("GET", r"/api/v1/pods/?$", {"total_count": 1, "offset": 0, "limit": 100, "data": [POD]}),
+        ("GET", r"/api/v1/disks/d1$", DISK), ("DELETE", r"/api/v1/disks/d1$", {"status": "deleted"}), ("PATCH", r"/api/v1/disks/d1$", {"status": "ok"}),
+        ("POST", r"/api/v1/disks/?$", DISK), ("GET", r"/api/v1/disks/?$", {"total_count": 1, "offset": 0, "limit": 100, "data": [DISK]}),
+        ("GET", r"/api/v1/availability/gpu-summary$", {"H100_80GB": {}}), ("GET", r"/api/v1/availability/disks$", {"items": []}),
+        ("GET", r"/api/v1/availability/?", {"H100_80GB": []}),
+    ]  # fmt: skip
+    for m, pat, body in r:
+        if m == method and re.search(pat, path):
+            return body
+    return {}
+
+
+class Recorder(BaseHTTPRequestHandler):
+    protocol_version = "HTTP/1.1"
+    log: list = []
+    lock = threading.Lock()
+
+    def log_message(self, *a):  # noqa: D102
+        pass
+
+    def _handle(self):
+        u = urlsplit(self.path)
+        n = int(self.headers.get("Content-Length") or 0)
+        raw = self.rfile.read(n) if n else b""
+        if u.path == "/__log":
+            body = json.dumps(Recorder.log).encode()
+            Recorder.log = []
+        else:
+            ctype = self.headers.get("Content-Type", "")
+            if "json" in ctype and raw:
+                payload = json.loads(raw)
+            elif "multipart" in ctype:
+                payload = {"multipart_bytes": "<file>", "has_hello": b"hello" in raw}
+            else:
+                payload = raw.decode("utf-8", "replace") if raw else None
+            with Recorder.lock:
+                Recorder.log.append({"method": self.command, "path": u.path, "query": sorted(parse_qsl(u.query)), "body": payload,
+                                     "auth": self.headers.get("Authorization")})  # fmt: skip
+            out = respond(self.command, u.path, self.headers.get("Host"))
+            body = out if isinstance(out, bytes) else json.dumps(out).encode()
+        head = f"HTTP/1.1 200 OK\r\nContent-Type: application/json\r\nContent-Length: {len(body)}\r\n\r\n".encode()
+        self.wfile.write(head + body)
+        self.wfile.flush()
+
+    do_GET = do_POST = do_PUT = do_DELETE = do_PATCH = _handle  # noqa: N815
+
+
+SCENARIO = r'''
+import json, os, sys, tempfile
+if sys.argv[1] == "ours":
+    import prime_b200.compat as compat
+    compat.install()
+from prime_sandboxes import APIClient, CreateSandboxRequest, SandboxClient
+from prime_evals import EvalsClient
+from prime_evals import APIClient as EvalsAPI
+from prime_cli.core import APIClient as CliAPI
+from prime_cli.api.pods import PodsClient
+from prime_cli.api.disks import DisksClient
+from prime_cli.api.availability import AvailabilityClient
+
+results = []
+def call(label, fn):
+    try:
+        r = fn()
+        if hasattr(r, "model_dump"):
+            r = r.model_dump(mode="json")
+        elif isinstance(r, list) and r and hasattr(r[0], "model_dump"):
+            r = [x.model_dump(mode="json") for x in r]
+        elif isinstance(r, dict):
+            r = {k: (v.model_dump(mode="json") if hasattr(v, "model_dump") else ([x.model_dump(mode="json") if hasattr(x, "model_dump") else x for x in v] if isinstance(v, list) else v)) for k, v in r.items()}
+        results.append([label, "ok", json.loads(json.dumps(r, default=str))])
+    except Exception as e:
+        results.append([label, "raised", type(e).__name__])
+
+tmp = tempfile.mkdtemp()
+src = os.path.join(tmp, "a.txt"); open(src, "w").write("hello")
+c = SandboxClient(APIClient(api_key="k"))
+call("create", lambda: c.create(CreateSandboxRequest(name="bench", docker_image="python:3.11-slim", cpu_cores=2, memory_gb=4, disk_size_gb=10, timeout_minutes=60, labels=["a", "b"], environment_vars={"X": "1"})))
+call("get", lambda: c.get("s1"))
+call("list", lambda: c.list(status="RUNNING", labels=["a"], page=2, per_page=10, exclude_terminated=True))
+call("list_default", lambda: c.list())
+call("logs", lambda: c.get_logs("s1"))
+call("exec", lambda: c.execute_command("s1", "echo ok", working_dir="/w", env={"A": "1"}, timeout=7))
+call("exec_default", lambda: c.execute_command("s1", "true"))
+call("upload", lambda: c.upload_file("s1", "/tmp/a.txt", src))
+call("upload_bytes", lambda: c.upload_bytes("s1", "/tmp/b.txt", b"hello", "b.txt"))
+call("read", lambda: c.read_file("s1", "/tmp/a.txt"))
+call("download", lambda: c.download_file("s1", "/tmp/a.txt", os.path.join(tmp, "out.txt")))
+call("expose", lambda: c.expose("s1", 8000, name="web"))
+call("list_ports", lambda: c.list_exposed_ports("s1"))
+call("list_all_ports", lambda: c.list_all_exposed_ports())
+call("unexpose", lambda: c.unexpose("s1", "e1"))
+call("ssh_open", lambda: c.create_ssh_session("s1", ttl_seconds=600))
+call("ssh_close", lambda: c.close_ssh_session("s1", "ss1"))
+call("wait", lambda: c.wait_for_creation("s1", max_attempts=2))
+call("bulk_wait", lambda: c.bulk_wait_for_creation(["s1"], max_attempts=2))
+call("bulk_delete_ids", lambda: c.bulk_delete(sandbox_ids=["s1"]))
+call("bulk_delete_labels", lambda: c.bulk_delete(labels=["a"]))
+call("delete", lambda: c.delete("s1"))
+
+e = EvalsClient(EvalsAPI(api_key="k"))
+call("eval_create", lambda: e.create_evaluation(name="n", environments=[{"id": "env1"}], model_name="m", framework="verifiers", metadata={"k": 1}, metrics={"r": 0.5}))
+call("eval_create_slug", lambda: e.create_evaluation(name="n2", environments=["owner/env"], model_name="m"))
+call("eval_push", lambda: e.push_samples("ev1", [{"example_id": i, "reward": 0.5, "task": "t"} for i in range(5)]))
+call("eval_finalize", lambda: e.finalize_evaluation("ev1", metrics={"r": 1.0}))
+call("eval_get", lambda: e.get_evaluation("ev1"))
+call("eval_list", lambda: e.list_evaluations(env_name="x", skip=5, limit=10))
+call("eval_samples", lambda: e.get_samples("ev1", page=2, limit=5))
+call("eval_update", lambda: e.update_evaluation("ev1", name="renamed"))
+
+api = CliAPI(api_key="k")
+pods, disks, av = PodsClient(api), DisksClient(api), AvailabilityClient(api)
+call("pods_list", lambda: pods.list(offset=5, limit=10))
+call("pods_get", lambda: pods.get("p1"))
+call("pods_status", lambda: pods.get_status(["p1"]))
+call("pods_history", lambda: pods.history())
+call("pods_create", lambda: pods.create({"pod": {"name": "x", "gpuType": "H100_80GB", "gpuCount": 1}, "provider": {"type": "x"}}))
+call("pods_delete", lambda: pods.delete("p1"))
+call("disks_list", lambda: disks.list())
+call("disks_get", lambda: disks.get("d1"))
+call("disks_update", lambda: disks.update("d1", "newname"))
+call("disks_delete", lambda: disks.delete("d1"))
+call("avail_get", lambda: av.get(regions=["united_states"], gpu_count=8, gpu_type="H100_80GB"))
+call("avail_disks", lambda: av.get_disks(regions=["united_states"]))
+print(json.dumps(results))
+'''
+
+
+def run_arm(arm: str, base: str) -> tuple[list, list]:
+    import urllib.request
+
+    with tempfile.TemporaryDirectory() as home:
+        env = {**os.environ, "HOME": home, "PRIME_API_BASE_URL": base, "PRIME_BASE_URL": base, "PRIME_API_KEY": "k", "PRIME_DISABLE_VERSION_CHECK": "1",
+               "PYTHONPATH": os.pathsep.join(REF_PATHS if arm == "reference" else [str(ROOT)])}  # fmt: skip
+        env.pop("PRIME_TEAM_ID", None)
+        r = subprocess.run([sys.executable, "-c", SCENARIO, arm], env=env, capture_output=True, text=True, cwd=home, timeout=600)
+    if r.returncode != 0:
+        raise SystemExit(f"{arm}: {r.stderr[-3000:]}")
+    results = json.loads(r.stdout.strip().splitlines()[-1])
+    log = json.loads(urllib.request.urlopen(base + "/__log").read())
+    return results, log
+
+
+def normalise(log: list) -> list:
+    out = []
+    for e in log:
+        e = dict(e)
+        if isinstance(e["body"], dict):  # generated identifiers
+            e["body"] = {k: v for k, v in e["body"].items() if k not in ("request_id",)}
+        out.append(e)
+    # uploads of one evaluation run 4-way concurrently: order inside a run of identical paths is not defined
+    return sorted(out, key=lambda e: json.dumps(e, sort_keys=True)) if False else out
+
+
+def main() -> int:
+    srv = ThreadingHTTPServer(("127.0.0.1", 0), Recorder)
+    srv.daemon_threads = True
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    base = f"http://127.0.0.1:{srv.server_address[1]}"
+    ref_res, ref_log = run_arm("reference", base)
+    our_res, our_log = run_arm("ours", base)
+    ref_log, our_log = normalise(ref_log), normalise(our_log)
+    diffs = []
+    for (la, sa, va), (lb, sb, vb) in zip(ref_res, our_res):
+        if (la, sa) != (lb, sb) or va != vb:
+            diffs.append({"call": la, "reference": [sa, va], "ours": [sb, vb]})
+    req_diffs = []
+    for i in range(max(len(ref_log), len(our_log))):
+        a = ref_log[i] if i < len(ref_log) else None
+        b = our_log[i] if i < len(our_log) else None
+        if a != b:
+            req_diffs.append({"index": i, "reference": a, "ours": b})
+    out = {"calls": len(ref_res), "requests_reference": len(ref_log), "requests_ours": len(our_log), "outcome_differences": diffs,
+           "request_differences": req_diffs[:40], "outcomes": {lab: st for lab, st, _ in our_res}}  # fmt: skip
+    print(json.dumps(out, indent=1))
+    srv.shutdown()
+    return 1 if diffs or req_diffs else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
