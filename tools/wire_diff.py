@@ -5,8 +5,10 @@ sends. The request sequences (method, path, query, JSON body) and the outcome of
 
     python tools/wire_diff.py > profiles/wire_diff.json        # exit code 1 on any difference
 
-What it covers: 40 SDK / API-client calls (sandbox lifecycle, command execution, file transfer, ports, SSH sessions, bulk delete,
-evaluation create / push / finalize / list, pods, disks, availability). What it cannot cover: responses of the real service.
+What it covers: 51 SDK / API-client calls — sandbox lifecycle, command execution, file transfer, ports, SSH sessions, bulk delete,
+evaluation create / push / finalize / list, pods, disks, availability — and injected failures: 404 / 401 / 402 / 422, a flaky idempotent
+GET (retried), a 503 on a non-idempotent POST (not retried), gateway 502 ``sandbox_not_found``, 408, 409. A failure counts as the same
+when this repo raises the reference's exception class or a subclass of it. What it cannot cover: responses of the real service.
 """
 
 from __future__ import annotations
@@ -71,6 +73,37 @@ def respond(method: str, path: str, host: str):
     return {}
 
 
+FLAKY: dict[str, int] = {}
+
+
+def scripted_failure(method: str, path: str, query: dict, payload):
+    """Failure injection keyed by what the client asks for (both arms ask for the same things): → (status, body) or None."""
+    cmd = payload.get("command") if isinstance(payload, dict) else None
+    if path.endswith("/sandbox/missing"):
+        return 404, {"detail": "Sandbox not found"}
+    if path.endswith("/sandbox/unauth"):
+        return 401, {"detail": "Invalid API key"}
+    if path.endswith("/sandbox/broke"):
+        return 402, {"detail": "Insufficient funds"}
+    if path.endswith("/sandbox/invalid"):
+        return 422, {"detail": [{"loc": ["body", "cpu_cores"], "msg": "too many", "type": "value_error"}]}
+    if path.endswith("/read-file") and query.get("path") == "/flaky":  # idempotent: retried on 5xx
+        FLAKY["read"] = FLAKY.get("read", 0) + 1
+        if FLAKY["read"] % 3 != 0:
+            return 503, {"detail": "try again"}
+    if path.endswith("/exec") and cmd == "five-oh-three":  # not idempotent: the server may have seen it — no retry
+        return 503, {"detail": "upstream"}
+    if path.endswith("/exec") and cmd == "gone":
+        return 502, {"error": "sandbox_not_found", "detail": "sandbox_not_found"}
+    if path.endswith("/exec") and cmd == "slow":
+        return 408, {"detail": "timeout"}
+    if path.endswith("/exec") and cmd == "conflict":
+        return 409, {"detail": "Sandbox is not running"}
+    if path.endswith("/sandbox/dead/error-context"):
+        return 200, {"status": "TERMINATED", "errorType": "OOM_KILLED", "errorMessage": "out of memory"}
+    return None
+
+
 class Recorder(BaseHTTPRequestHandler):
     protocol_version = "HTTP/1.1"
     log: list = []
@@ -97,8 +130,12 @@ class Recorder(BaseHTTPRequestHandler):
             with Recorder.lock:
                 Recorder.log.append({"method": self.command, "path": u.path, "query": sorted(parse_qsl(u.query)), "body": payload,
                                      "auth": self.headers.get("Authorization")})  # fmt: skip
-            out = respond(self.command, u.path, self.headers.get("Host"))
+            code, out = scripted_failure(self.command, u.path, dict(parse_qsl(u.query)), payload) or (200, respond(self.command, u.path, self.headers.get("Host")))
             body = out if isinstance(out, bytes) else json.dumps(out).encode()
+            head = f"HTTP/1.1 {code} X\r\nContent-Type: application/json\r\nContent-Length: {len(body)}\r\n\r\n".encode()
+            self.wfile.write(head + body)
+            self.wfile.flush()
+            return
         head = f"HTTP/1.1 200 OK\r\nContent-Type: application/json\r\nContent-Length: {len(body)}\r\n\r\n".encode()
         self.wfile.write(head + body)
         self.wfile.flush()
@@ -131,7 +168,7 @@ def call(label, fn):
             r = {k: (v.model_dump(mode="json") if hasattr(v, "model_dump") else ([x.model_dump(mode="json") if hasattr(x, "model_dump") else x for x in v] if isinstance(v, list) else v)) for k, v in r.items()}
         results.append([label, "ok", json.loads(json.dumps(r, default=str))])
     except Exception as e:
-        results.append([label, "raised", type(e).__name__])
+        results.append([label, "raised", [type(e).__name__, str(e)[:160], [k.__name__ for k in type(e).__mro__]]])
 
 tmp = tempfile.mkdtemp()
 src = os.path.join(tmp, "a.txt"); open(src, "w").write("hello")
@@ -158,6 +195,16 @@ call("bulk_wait", lambda: c.bulk_wait_for_creation(["s1"], max_attempts=2))
 call("bulk_delete_ids", lambda: c.bulk_delete(sandbox_ids=["s1"]))
 call("bulk_delete_labels", lambda: c.bulk_delete(labels=["a"]))
 call("delete", lambda: c.delete("s1"))
+
+call("err_404", lambda: c.get("missing"))
+call("err_401", lambda: c.get("unauth"))
+call("err_402", lambda: c.get("broke"))
+call("err_422", lambda: c.get("invalid"))
+call("retry_get_5xx", lambda: c.read_file("s1", "/flaky"))
+call("no_retry_post_5xx", lambda: c.execute_command("s1", "five-oh-three"))
+call("gateway_gone", lambda: c.execute_command("s1", "gone"))
+call("gateway_408", lambda: c.execute_command("s1", "slow", timeout=3))
+call("gateway_409", lambda: c.execute_command("s1", "conflict"))
 
 e = EvalsClient(EvalsAPI(api_key="k"))
 call("eval_create", lambda: e.create_evaluation(name="n", environments=[{"id": "env1"}], model_name="m", framework="verifiers", metadata={"k": 1}, metrics={"r": 0.5}))
@@ -221,9 +268,18 @@ def main() -> int:
     ref_res, ref_log = run_arm("reference", base)
     our_res, our_log = run_arm("ours", base)
     ref_log, our_log = normalise(ref_log), normalise(our_log)
-    diffs = []
+    diffs, wording = [], []
     for (la, sa, va), (lb, sb, vb) in zip(ref_res, our_res):
-        if (la, sa) != (lb, sb) or va != vb:
+        if (la, sa) != (lb, sb):
+            diffs.append({"call": la, "reference": [sa, va], "ours": [sb, vb]})
+        elif sa == "raised":
+            # same failure ⇔ what this repo raises IS-A what the reference raises (an ``except`` written for the reference still
+            # catches it); the message text is informational — the reference's five packages word the same error differently
+            if va[0] not in vb[2]:
+                diffs.append({"call": la, "reference": va[:2], "ours": vb[:2]})
+            elif va[:2] != vb[:2]:
+                wording.append({"call": la, "reference": va[:2], "ours": vb[:2]})
+        elif va != vb:
             diffs.append({"call": la, "reference": [sa, va], "ours": [sb, vb]})
     req_diffs = []
     for i in range(max(len(ref_log), len(our_log))):
@@ -232,7 +288,8 @@ def main() -> int:
         if a != b:
             req_diffs.append({"index": i, "reference": a, "ours": b})
     out = {"calls": len(ref_res), "requests_reference": len(ref_log), "requests_ours": len(our_log), "outcome_differences": diffs,
-           "request_differences": req_diffs[:40], "outcomes": {lab: st for lab, st, _ in our_res}}  # fmt: skip
+           "same_exception_class_different_wording": wording,
+           "request_differences": req_diffs[:40], "outcomes": {lab: (st if st == "ok" else f"raised {v[0]}") for lab, st, v in our_res}}  # fmt: skip
     print(json.dumps(out, indent=1))
     srv.shutdown()
     return 1 if diffs or req_diffs else 0
