@@ -121,7 +121,7 @@ def disks(
              "location": d.country or d.region or "N/A", "stock_status": d.stock_status or "N/A",
              "price_per_gb_month": f"${d.spec.price_per_unit:.4f}" if d.spec.price_per_unit is not None else "N/A",
              "min_gb": d.spec.min_count, "max_gb": d.spec.max_count, "is_multinode": d.is_multinode} for d in offers]  # fmt: skip
-    emit(output, {"disks": rows, "total_count": len(rows)}, "Available Disks",
+    emit(output, {"disks": rows, "total_count": len(rows), "filters": {"regions": regions, "data_center_id": data_center_id}}, "Available Disks",
          [("ID", "cyan"), "Provider", "Data center", ("Location", "green"), ("Stock", "yellow"), ("Price/GB", "magenta"), "Min GB", "Max GB", "Multi-node"],
          [[r["id"], r["provider"], r["data_center"], r["location"], r["stock_status"], r["price_per_gb_month"], r["min_gb"], r["max_gb"],
            r["is_multinode"]] for r in rows], "\n[bold blue]Create one:[/bold blue] [green]prime disks create --id <ID> --size <GB>[/green]")  # fmt: skip

@@ -11,7 +11,8 @@ from ..api.deployments import DEPLOYABLE_FROM, UNLOADABLE_FROM, Adapter, Deploym
 from ..core import APIError, Config
 from ..utils.display import DEPLOYMENT_STATUS_COLORS, colorize
 from ..utils.json_help import list_json_help
-from ..utils.time_utils import format_time_ago
+from ..utils.time_utils import format_time_ago, parse_dt
+from ..utils.plain import get_console
 from ._common import OUTPUT_OPT, api, console, emit, fail, handle_errors, make_app, paginate_hint
 
 app = make_app("Deploy trained adapters for inference")
@@ -56,12 +57,27 @@ def list_deployments(team: Optional[str] = typer.Option(None, "--team", "-t", he
     if num < 1 or page < 1:
         raise fail("--num and --page must be at least 1")
     limit, offset = num, (page - 1) * num
-    adapters, total = DeploymentsClient(api()).list_adapters(team_id=team or Config(writable=False).team_id, limit=limit, offset=offset)
-    payload = {"models": [a.model_dump(mode="json") for a in adapters], "total": total, "page": page, "per_page": num}
-    emit(output, payload, f"Models (Total: {total})",
-         [("ID", "cyan"), "Name", ("Base model", "blue"), "Step", "Status", "Deployment", ("Created", "magenta")],
+    client = DeploymentsClient(api())
+    adapters, total = client.list_adapters(team_id=team or Config(writable=False).team_id, limit=limit, offset=offset)
+    try:  # which base models can currently be served: every row says whether `deployments create` would be accepted
+        deployable: list[str] | None = client.get_deployable_models()
+    except Exception:  # noqa: BLE001 — the listing is still useful without the column
+        get_console(stderr=True).print("[dim]Warning: Could not fetch deployable models list.[/dim]")  # stderr: stdout may be JSON
+        deployable = None
+    models = []
+    for a in adapters:
+        row = a.model_dump(mode="json")
+        for key in ("created_at", "updated_at", "deployed_at"):  # "2025-01-01 00:00:00+00:00": the timestamp form this command has always printed
+            if row.get(key):
+                row[key] = str(parse_dt(row[key]))
+        if deployable is not None:
+            row["deployable"] = a.base_model in deployable
+        models.append(row)
+    mark = lambda a: "[dim]-[/dim]" if deployable is None else ("[green]Yes[/green]" if a.base_model in deployable else "[red]No[/red]")  # noqa: E731
+    emit(output, {"models": models, "total": total, "page": page, "per_page": num}, f"Models (Total: {total})",
+         [("ID", "cyan"), "Name", ("Base model", "blue"), "Step", "Status", "Deployment", "Deployable", ("Created", "magenta")],
          [[a.id, a.display_name or "", a.base_model, a.step if a.step is not None else "", a.status,
-           colorize(a.deployment_status, DEPLOYMENT_STATUS_COLORS), format_time_ago(a.created_at)] for a in adapters],
+           colorize(a.deployment_status, DEPLOYMENT_STATUS_COLORS), mark(a), format_time_ago(a.created_at)] for a in adapters],
          paginate_hint(total, offset, limit, "models"))  # fmt: skip
 
 

@@ -26,9 +26,18 @@ _LIST_FIELDS = {"id": "str", "name": "str", "size": "int (GB)", "status": "str",
 
 def disk_row(d: Disk) -> dict[str, Any]:
     info = d.info or {}
-    return {"id": d.id, "name": d.name, "size": d.size, "status": d.status, "provider": d.provider_type,
-            "location": info.get("country") or info.get("dataCenterId") or "N/A", "created_at": iso_timestamp(d.created_at),
-            "age": human_age(d.created_at), "price_hr": d.price_hr, "pods": d.pods, "clusters": d.clusters}  # fmt: skip
+    # "US (dc-1)": country and data centre, "N/A" for whichever is unknown (the form scripts see in `disks list -o json`)
+    location = f"{info.get('country', 'N/A')} ({info.get('dataCenterId', 'N/A')})"
+    return {"id": d.id, "name": d.name, "size": d.size, "status": d.status, "provider": d.provider_type, "location": location,
+            "created_at": iso_timestamp(d.created_at), "age": human_age(d.created_at), "price_hr": d.price_hr, "pods": d.pods, "clusters": d.clusters}  # fmt: skip
+
+
+def disk_detail(d: Disk) -> dict[str, Any]:
+    """`disks get -o json`: the list row plus the raw record's timestamps, prices, owners and provider info."""
+    r = disk_row(d)
+    r.update(updated_at=iso_timestamp(d.updated_at), terminated_at=iso_timestamp(d.terminated_at) if d.terminated_at else None,
+             stopped_price_hr=d.stopped_price_hr, user_id=d.user_id, team_id=d.team_id, wallet_id=d.wallet_id, info=d.info)
+    return r
 
 
 def build_disk_config(size: int, name: str | None, team_id: str | None, *, offer=None, country: str | None = None,
@@ -73,7 +82,7 @@ def list_(limit: int = typer.Option(100, help="Maximum number of disks"), offset
 @handle_errors
 def get(disk_id: str = typer.Argument(..., help="Disk ID"), output: str = OUTPUT_OPT) -> None:
     """Show one disk."""
-    r = disk_row(DisksClient(api()).get(disk_id))
+    r = disk_detail(DisksClient(api()).get(disk_id))
     emit(output, r, f"Disk {r['id']}", [("Field", "cyan"), ("Value", "green")], [[k, v] for k, v in r.items()])
 
 

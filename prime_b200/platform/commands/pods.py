@@ -43,20 +43,42 @@ def pod_row(p: Pod) -> dict[str, Any]:
 
 
 def status_row(s: PodStatus, p: Pod) -> dict[str, Any]:
+    """Keys and value forms of ``prime pods status -o json`` as scripts know them (reference: commands/pods.py:74-99 — ``ssh`` and
+    ``ip`` are display strings, the optional keys appear only when set), plus the structured extras of this CLI."""
     ssh = s.ssh_connection if isinstance(s.ssh_connection, list) else ([s.ssh_connection] if s.ssh_connection else [])
-    row = {"id": s.pod_id, "name": p.name, "status": s.status, "provider": s.provider_type, "gpu": f"{p.gpu_type} x{p.gpu_count}",
-           "image": p.environment_type, "team_id": p.team_id, "cost_per_hr": s.cost_per_hr, "created_at": iso_timestamp(p.created_at),
-           "ip": format_ip_display(s.ip), "ssh": [c for c in ssh if c], "installation_progress": s.installation_progress,
-           "installation_failure": s.installation_failure,
-           "port_mappings": [m.model_dump() for m in (s.prime_port_mapping or [])],
-           "attached_resources": [r.model_dump() for r in (p.attached_resources or [])]}  # fmt: skip
+    status = s.status
+    if p.status == "ACTIVE" and s.installation_progress is not None and s.installation_progress < 100 and not s.installation_failure:
+        status = "INSTALLING"
+    row: dict[str, Any] = {"id": p.id, "status": status, "name": p.name, "team_id": p.team_id, "provider": s.provider_type,
+                           "gpu": f"{p.gpu_type} x{p.gpu_count}", "image": p.environment_type, "created_at": iso_timestamp(p.created_at),
+                           "ip": format_ip_display(s.ip), "ssh": format_ip_display(s.ssh_connection)}  # fmt: skip
+    if s.cost_per_hr:
+        row["cost_per_hour"] = s.cost_per_hr
+    if p.installation_status:
+        row["installation_status"] = p.installation_status
+    if s.installation_progress is not None:
+        row["installation_progress"] = s.installation_progress
+    if s.installation_failure:
+        row["installation_error"] = s.installation_failure
+    row.update(ssh_connections=[c for c in ssh if c], port_mappings=[m.model_dump() for m in (s.prime_port_mapping or [])],
+               attached_resources=[r.model_dump() for r in (p.attached_resources or [])])
     return row
 
 
+def _duration(created: Any, terminated: Any) -> str | None:
+    """``42m`` below an hour, ``3.5h`` below a day, ``2.1d`` above."""
+    from ..utils.time_utils import parse_dt
+
+    if not created or not terminated:
+        return None
+    hours = (parse_dt(terminated) - parse_dt(created)).total_seconds() / 3600
+    return f"{int(hours * 60)}m" if hours < 1 else (f"{hours:.1f}h" if hours < 24 else f"{hours / 24:.1f}d")
+
+
 def history_row(h: HistoryObj) -> dict[str, Any]:
-    return {"id": h.id, "name": h.name, "gpu": f"{h.gpu_name} x{h.count}", "provider": h.provider_type, "type": h.type,
-            "created_at": iso_timestamp(h.created_at), "terminated_at": iso_timestamp(h.terminated_at) if h.terminated_at else None,
-            "price_hr": h.price_hr, "total_billed": h.total_billed_price, "team_id": h.team_id}  # fmt: skip
+    return {"id": h.id, "name": h.name, "provider": h.provider_type, "gpu": f"{h.gpu_name} x{h.count}", "created_at": iso_timestamp(h.created_at),
+            "terminated_at": iso_timestamp(h.terminated_at) if h.terminated_at else None, "duration": _duration(h.created_at, h.terminated_at),
+            "price_per_hour": h.price_hr, "total_cost": h.total_billed_price, "team_id": h.team_id, "type": h.type}  # fmt: skip
 
 
 # ----------------------------------------------------------------------------------------------- list / status / history
@@ -88,7 +110,7 @@ def list_(limit: int = typer.Option(100, help="Maximum number of pods"), offset:
         time.sleep(5)
 
 
-@app.command(no_args_is_help=True, epilog=json_output_help({"id": "str", "status": "str", "ssh": ["str"], "ip": "str", "installation_progress": "int|null"}))
+@app.command(no_args_is_help=True, epilog=json_output_help({"id": "str", "status": "str", "ssh": "str", "ip": "str", "ssh_connections": ["str"], "installation_progress": "int (when installing)"}))
 @handle_errors
 def status(pod_id: str = typer.Argument(..., help="Pod ID"), output: str = OUTPUT_OPT) -> None:
     """Detailed status of one pod (state, SSH endpoint, install progress, ports, attached disks)."""
@@ -99,12 +121,14 @@ def status(pod_id: str = typer.Argument(..., help="Pod ID"), output: str = OUTPU
     row = status_row(statuses[0], client.get(pod_id))
     rows = [["Status", colorize(row["status"], POD_STATUS_COLORS)], ["Name", row["name"] or "N/A"], ["Team", row["team_id"] or "Personal"],
             ["Provider", row["provider"]], ["GPU", row["gpu"]], ["Image", row["image"] or "N/A"],
-            ["Cost per Hour", "N/A" if row["cost_per_hr"] is None else f"${row['cost_per_hr']:.3f}"], ["Created", row["created_at"]],
-            ["IP", row["ip"]], ["SSH", "\n".join(row["ssh"]) or "N/A"]]  # fmt: skip
-    if row["installation_progress"] is not None:
+            ["Cost per Hour", f"${row['cost_per_hour']:.3f}" if "cost_per_hour" in row else "N/A"], ["Created", row["created_at"]],
+            ["IP", row["ip"]], ["SSH", "\n".join(row["ssh_connections"]) or "N/A"]]  # fmt: skip
+    if "installation_status" in row:
+        rows.append(["Installation Status", row["installation_status"]])
+    if "installation_progress" in row:
         rows.append(["Installation Progress", f"{row['installation_progress']}%"])
-    if row["installation_failure"]:
-        rows.append(["Installation Error", f"[red]{row['installation_failure']}[/red]"])
+    if "installation_error" in row:
+        rows.append(["Installation Error", f"[red]{row['installation_error']}[/red]"])
     for m in row["port_mappings"]:
         rows.append([f"Port {m.get('internal')}", f"{m.get('external')} ({m.get('protocol')}) {m.get('description') or ''}"])
     for r in row["attached_resources"]:
@@ -112,15 +136,17 @@ def status(pod_id: str = typer.Argument(..., help="Pod ID"), output: str = OUTPU
     emit(output, row, f"Pod Status: {pod_id}", [("Property", "cyan"), ("Value", "green")], rows)
 
 
-@app.command(epilog=list_json_help("pods", {"id": "str", "name": "str", "gpu": "str", "created_at": "str", "terminated_at": "str|null", "total_billed": "float"}))
+@app.command(epilog=list_json_help("history", {"id": "str", "name": "str", "gpu": "str", "created_at": "str", "terminated_at": "str|null", "duration": "str|null",
+                                                "price_per_hour": "float", "total_cost": "float"}))
 @handle_errors
 def history(limit: int = typer.Option(100, help="Maximum number of entries"), offset: int = typer.Option(0), output: str = OUTPUT_OPT) -> None:
     """Terminated pods and what they cost."""
     page = PodsClient(api()).history(offset=offset, limit=limit)
     rows = [history_row(h) for h in page.data]
-    emit(output, {"pods": rows, "total_count": page.total_count, "offset": offset, "limit": limit}, f"Pods History (Total: {page.total_count})",
-         [("ID", "cyan"), ("Name", "blue"), ("GPU", "green"), "Provider", "Created", "Terminated", ("$/hr", "magenta"), ("Billed", "magenta")],
-         [[r["id"], r["name"], r["gpu"], r["provider"], r["created_at"], r["terminated_at"] or "", f"{r['price_hr']:.2f}", f"${r['total_billed']:.2f}"] for r in rows],
+    emit(output, {"history": rows, "total_count": page.total_count, "offset": offset, "limit": limit}, f"Pods History (Total: {page.total_count})",
+         [("ID", "cyan"), ("Name", "blue"), ("GPU", "green"), "Provider", "Created", "Terminated", "Duration", ("$/hr", "magenta"), ("Billed", "magenta")],
+         [[r["id"], r["name"], r["gpu"], r["provider"], r["created_at"], r["terminated_at"] or "", r["duration"] or "", f"{r['price_per_hour']:.2f}",
+           f"${r['total_cost']:.2f}"] for r in rows],
          paginate_hint(page.total_count, offset, limit, "entries"))  # fmt: skip
 
 

@@ -18,7 +18,7 @@ import typer
 from ..core import Config
 from ..sandboxes import CommandTimeoutError, CreateSandboxRequest, Sandbox, SandboxClient, SandboxNotRunningError
 from ..utils.display import SANDBOX_STATUS_COLORS, colorize, output_data_as_json
-from ..utils.formatters import obfuscate_env_vars
+from ..utils.formatters import format_resources, obfuscate_env_vars
 from ..utils.json_help import json_output_help, list_json_help
 from ..utils.prompt import confirm_or_skip
 from ..utils.time_utils import human_age, iso_timestamp, sort_by_created
@@ -39,13 +39,17 @@ def resources_of(s: Sandbox) -> str:
 
 
 def list_row(s: Sandbox) -> dict[str, Any]:
-    return {"id": s.id, "name": s.name, "image": s.docker_image, "status": s.status, "resources": resources_of(s), "labels": s.labels,
+    return {"id": s.id, "name": s.name, "image": s.docker_image, "status": s.status,
+            "resources": format_resources(s.cpu_cores, s.memory_gb, s.gpu_count), "labels": s.labels,
             "created_at": iso_timestamp(s.created_at), "age": human_age(s.created_at), "type": "VM" if s.vm else "Container",
             "user_id": s.user_id, "team_id": s.team_id}  # fmt: skip
 
 
 def detail_row(s: Sandbox) -> dict[str, Any]:
     d = list_row(s)
+    # the raw fields under the names `prime sandbox get -o json` has always printed them (reference: commands/sandbox.py, get)
+    d.update(docker_image=s.docker_image, cpu_cores=s.cpu_cores, memory_gb=s.memory_gb, disk_size_gb=s.disk_size_gb, disk_mount_path=s.disk_mount_path,
+             gpu_count=s.gpu_count, gpu_type=s.gpu_type, vm=s.vm, resources_detail=resources_of(s))
     d.update(start_command=s.start_command, network_access=s.network_access, timeout_minutes=s.timeout_minutes,
              environment_vars=obfuscate_env_vars(s.environment_vars), secrets=sorted((s.secrets or {}).keys()),
              started_at=iso_timestamp(s.started_at) if s.started_at else None,
@@ -94,10 +98,11 @@ def parse_ids(raw: list[str] | None) -> list[str]:
 
 # --------------------------------------------------------------------------------------------------- list / get
 def _list(team_id, status, labels, page, num, all, output) -> None:
-    resp = client().list(team_id=team_id, status=status, labels=labels, page=page, per_page=num, exclude_terminated=None if all else True)
+    # an explicit --status already says which sandboxes are wanted: only the unfiltered default view hides terminated ones
+    resp = client().list(team_id=team_id, status=status, labels=labels, page=page, per_page=num, exclude_terminated=(not all and status is None))
     rows = [list_row(s) for s in sort_by_created(resp.sandboxes)]
     footer = f"\n[yellow]More results available. Use --page {page + 1}[/yellow]" if resp.has_next else None
-    emit(output, {"sandboxes": [{k: r[k] for k in _LIST_FIELDS} for r in rows], "total": resp.total, "page": resp.page, "per_page": resp.per_page,
+    emit(output, {"sandboxes": [{k: r[k] for k in _LIST_FIELDS} for r in rows], "total": resp.total, "page": resp.page, "per_page": num,
                   "has_next": resp.has_next}, f"Code Sandboxes (Total: {resp.total})",
          [("ID", "cyan"), ("Name", "blue"), ("Image", "green"), "Status", "Type", "Resources", "Labels", "Age"],
          [[r["id"], r["name"], r["image"], colorize(r["status"], SANDBOX_STATUS_COLORS), r["type"], r["resources"], ", ".join(r["labels"]), r["age"]] for r in rows],
@@ -364,7 +369,9 @@ def unexpose_port(sandbox_id: str = typer.Argument(...), exposure_id: str = type
     if not confirm_or_skip(f"Remove exposure {exposure_id} from sandbox {sandbox_id}?", yes):
         console.print("Cancelled")
         return
-    client().unexpose(sandbox_id, exposure_id)
+    c = client()
+    guard_vm_unsupported(c.get(sandbox_id), "Port unexpose")
+    c.unexpose(sandbox_id, exposure_id)
     console.print(f"[green]✓ Removed exposure {exposure_id}[/green]")
 
 
@@ -373,6 +380,8 @@ def unexpose_port(sandbox_id: str = typer.Argument(...), exposure_id: str = type
 def list_ports(sandbox_id: Optional[str] = typer.Argument(None, help="Sandbox ID (all sandboxes when omitted)"), output: str = OUTPUT_OPT) -> None:
     """List exposed ports."""
     c = client()
+    if sandbox_id:
+        guard_vm_unsupported(c.get(sandbox_id), "Port listing")
     exps = (c.list_exposed_ports(sandbox_id) if sandbox_id else c.list_all_exposed_ports()).exposures
     emit(output, {"exposures": [e.model_dump() for e in exps], "total_count": len(exps)}, "Exposed Ports",
          [("Exposure ID", "cyan"), "Sandbox", "Port", "Name", "Protocol", ("URL / endpoint", "green")],

@@ -20,8 +20,8 @@ DEPLOYMENT_STATUS_COLORS = {"DEPLOYED": "green", "DEPLOYING": "yellow", "UNLOADI
                             "NOT_DEPLOYED": "dim", "DEPLOY_FAILED": "red", "UNLOAD_FAILED": "red"}  # fmt: skip
 
 
-def status_color(status: str | None, table: dict[str, str], default: str = "white") -> str:
-    return table.get((status or "").upper(), default)
+def status_color(status: str | None, mapping: dict[str, str], default: str = "white") -> str:
+    return mapping.get((status or "").upper(), default)
 
 
 def colorize(status: str | None, table: dict[str, str]) -> str:
@@ -46,8 +46,8 @@ def output_data_as_json(data: Any, console=None) -> None:
     (console or get_console()).file.write(json.dumps(data, indent=2, default=str) + "\n")
 
 
-def validate_output_format(fmt: str, console=None) -> str:
-    fmt = (fmt or "table").lower()
+def validate_output_format(output: str, console=None) -> str:
+    fmt = (output or "table").lower()
     if fmt not in ("table", "json"):
         import typer
 

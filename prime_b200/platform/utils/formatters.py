@@ -20,8 +20,8 @@ def obfuscate_secret(value: str | None, keep: int = 4) -> str:
     return f"{value[:keep]}{'*' * (len(value) - 2 * keep)}{value[-keep:]}"
 
 
-def obfuscate_env_vars(env: Mapping[str, str] | None) -> dict[str, str]:
-    return {k: obfuscate_secret(v, keep=2) for k, v in (env or {}).items()}
+def obfuscate_env_vars(env_vars: Mapping[str, str] | None) -> dict[str, str]:
+    return {k: obfuscate_secret(v, keep=2) for k, v in (env_vars or {}).items()}
 
 
 def format_price(value: float | None, unit: str = "/hr") -> str:
@@ -47,8 +47,16 @@ def format_size(num_bytes: float | None) -> str:
     return f"{n:.1f} TB"
 
 
-def format_resources(cpu: float | None = None, memory_gb: float | None = None, disk_gb: float | None = None,
-                     gpu: int | None = None, gpu_type: str | None = None) -> str:  # fmt: skip
+def format_resources(cpu_cores: float | None = None, memory_gb: float | None = None, gpu_count: int | None = 0) -> str:
+    """Compact form used in list rows and in ``--output json`` (``2CPU/4GB``, ``8CPU/64GB/1GPU``; reference:
+    packages/prime/src/prime_cli/utils/formatters.py:48-53 — scripts parse it)."""
+    out = f"{(cpu_cores or 0):g}CPU/{(memory_gb or 0):g}GB"
+    return out + (f"/{gpu_count}GPU" if gpu_count and gpu_count > 0 else "")
+
+
+def format_resources_long(cpu: float | None = None, memory_gb: float | None = None, disk_gb: float | None = None,
+                          gpu: int | None = None, gpu_type: str | None = None) -> str:  # fmt: skip
+    """Spelled-out form for detail views: ``2 CPU, 4 GB RAM, 10 GB disk, 1x H100_80GB``."""
     parts = []
     if cpu is not None:
         parts.append(f"{cpu:g} CPU")

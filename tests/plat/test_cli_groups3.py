@@ -168,9 +168,10 @@ def test_reference_pagination_flags_on_rl_and_deployments(fake_api):
     assert api.called("GET", "/rft/runs")[0][2] == {"team_id": "team9"}
     assert "No more results" in runner.invoke(app, ["rl", "ls", "--page", "9"]).output
     assert runner.invoke(app, ["rl", "list", "--num", "0"]).exit_code == 1
-    api2 = fake_api({("GET", "/rft/adapters"): {"adapters": [], "total": 45}}, dep_mod)
+    api2 = fake_api({("GET", "/rft/adapters"): {"adapters": [], "total": 45}, ("GET", "/rft/deployable-models"): {"models": ["Qwen/Qwen3-4B"]}}, dep_mod)
     out = json.loads(runner.invoke(app, ["deployments", "list", "-n", "20", "-p", "3", "-t", "team9", "--output", "json"]).output)
     assert out["total"] == 45 and out["page"] == 3 and out["per_page"] == 20
+    assert api2.called("GET", "/rft/deployable-models")  # every row is marked deployable / not deployable, as in the reference
     assert api2.called("GET", "/rft/adapters")[0][2] == {"team_id": "team9", "limit": 20, "offset": 40}
     for argv in (["eval", "list", "--help"], ["eval", "push", "--help"]):
         helptext = runner.invoke(app, argv).output

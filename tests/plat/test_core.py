@@ -295,3 +295,21 @@ def test_wire_requests_are_identical_to_the_reference(capsys):
     assert rc == 0 and out["calls"] >= 51 and out["requests_reference"] == out["requests_ours"] >= 68
     assert out["outcome_differences"] == [] and out["request_differences"] == []
     assert sum(v == "ok" for v in out["outcomes"].values()) >= 43 and out["outcomes"]["gateway_408"] == "raised CommandTimeoutError"
+
+
+@pytest.mark.slow
+def test_cli_commands_behave_like_the_reference_cli(capsys):
+    """tools/cli_diff.py: 42 ``prime …`` command lines through both CLIs against the recording server — same exit codes, same HTTP
+    requests, and every key / value of the reference's ``--output json`` present in ours."""
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[2]
+    if not Path("/root/reference/packages").is_dir():
+        pytest.skip("reference tree not mounted")
+    sys.path.insert(0, str(root))
+    from tools import cli_diff
+
+    rc = cli_diff.main()
+    out = json.loads(capsys.readouterr().out)
+    assert rc == 0 and out["commands"] >= 42 and out["identical"] == out["commands"] and out["differences"] == [], [d["command"] for d in out["differences"]]

@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Differential CLI test: the same ``prime …`` command lines through the unmodified reference CLI and through this repo's CLI,
+against the recording fake server of ``tools/wire_diff.py``. Compared per command: exit code, the HTTP requests sent (method,
+path, query, JSON body) and — where the command prints JSON (``--output json``) — the parsed JSON: every key and value of the
+reference's JSON must be present in this CLI's (which may add keys).
+
+    python tools/cli_diff.py > profiles/cli_diff.json          # exit code 1 on any difference
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import urllib.request
+from http.server import ThreadingHTTPServer
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from tools.wire_diff import REF_PATHS, Recorder  # noqa: E402
+
+COMMANDS: list[list[str]] = [
+    ["pods", "list", "--output", "json"], ["pods", "list", "--limit", "10", "--offset", "5", "-o", "json"], ["pods", "status", "p1", "-o", "json"],
+    ["pods", "history", "-o", "json"], ["pods", "terminate", "p1", "--yes"],
+    ["disks", "list", "-o", "json"], ["disks", "get", "d1", "-o", "json"], ["disks", "update", "d1", "--name", "newname"], ["disks", "terminate", "d1", "--yes"],
+    ["availability", "list", "--gpu-type", "H100_80GB", "--gpu-count", "8", "-o", "json"], ["availability", "gpu-types"], ["availability", "disks", "-o", "json"],
+    ["sandbox", "list", "-o", "json"], ["sandbox", "list", "--status", "RUNNING", "--label", "a", "--page", "2", "--num", "10", "-o", "json"],
+    ["sandbox", "get", "s1", "-o", "json"], ["sandbox", "run", "s1", "echo ok"], ["sandbox", "logs", "s1"], ["sandbox", "delete", "s1", "--yes"],
+    ["sandbox", "create", "--name", "bench", "--cpu-cores", "2", "--memory-gb", "4", "--yes", "python:3.11-slim"],
+    ["sandbox", "expose", "s1", "8000", "--name", "web"], ["sandbox", "list-ports", "s1", "-o", "json"], ["sandbox", "unexpose", "s1", "e1", "--yes"],
+    ["sandbox", "get", "missing"], ["sandbox", "get", "unauth"],
+    ["eval", "list", "-o", "json"], ["eval", "get", "ev1", "-o", "json"], ["eval", "samples", "ev1", "-o", "json"],
+    ["teams", "list", "-o", "json"], ["whoami"], ["secret", "list", "-o", "json"], ["env", "list", "-o", "json"], ["registry", "list", "-o", "json"],
+    ["images", "list", "-o", "json"], ["rl", "list", "-o", "json"], ["rl", "models", "-o", "json"], ["rl", "get", "r1", "-o", "json"], ["deployments", "list", "-o", "json"],
+    ["inference", "models", "-o", "json"], ["config", "view"], ["config", "set-team-id", "team-1"], ["config", "view"], ["--version"],
+]  # fmt: skip
+
+
+def run_cli(arm: str, base: str, home: str, args: list[str]) -> tuple[int, str, str]:
+    code = "from prime_cli.main import run; run()" if arm == "reference" else "from prime_b200.platform.main import run; run()"
+    env = {**os.environ, "HOME": home, "PRIME_API_BASE_URL": base, "PRIME_BASE_URL": base, "PRIME_INFERENCE_URL": base + "/api/v1", "PRIME_API_KEY": "k",
+           "PRIME_DISABLE_VERSION_CHECK": "1", "NO_COLOR": "1", "COLUMNS": "200", "TERM": "dumb",
+           "PYTHONPATH": os.pathsep.join(REF_PATHS if arm == "reference" else [str(ROOT)])}  # fmt: skip
+    env.pop("PRIME_TEAM_ID", None)
+    r = subprocess.run([sys.executable, "-c", f"import sys; sys.argv = ['prime', *{args!r}]; {code}"], env=env, capture_output=True, text=True,
+                       cwd=home, timeout=120, stdin=subprocess.DEVNULL)  # fmt: skip
+    return r.returncode, r.stdout, r.stderr
+
+
+def parsed_json(stdout: str):
+    s = stdout.strip()
+    for opener in ("{", "["):
+        i = s.find(opener)
+        if i >= 0:
+            try:
+                return json.loads(s[i:])
+            except json.JSONDecodeError:
+                continue
+    return None
+
+
+def covers(ours, ref) -> bool:
+    """Does ``ours`` contain everything ``ref`` says? dict: every reference key present with a covering value (extra keys allowed);
+    list: same length, element-wise; scalars: equal."""
+    if isinstance(ref, dict):
+        return isinstance(ours, dict) and all(k in ours and covers(ours[k], v) for k, v in ref.items())
+    if isinstance(ref, list):
+        return isinstance(ours, list) and len(ours) == len(ref) and all(covers(a, b) for a, b in zip(ours, ref))
+    return ours == ref
+
+
+def main() -> int:
+    srv = ThreadingHTTPServer(("127.0.0.1", 0), Recorder)
+    srv.daemon_threads = True
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    base = f"http://127.0.0.1:{srv.server_address[1]}"
+    rows, diffs = [], []
+    with tempfile.TemporaryDirectory() as h1, tempfile.TemporaryDirectory() as h2:
+        for args in COMMANDS:
+            got = {}
+            for arm, home in (("reference", h1), ("ours", h2)):
+                rc, out, err = run_cli(arm, base, home, args)
+                log = json.loads(urllib.request.urlopen(base + "/__log").read())
+                got[arm] = {"exit_code": rc, "requests": [{k: e[k] for k in ("method", "path", "query", "body")} for e in log], "json": parsed_json(out),
+                            "stdout_tail": out.strip()[-300:], "stderr_tail": err.strip()[-300:]}  # fmt: skip
+            a, b = got["reference"], got["ours"]
+            row = {"command": "prime " + " ".join(args), "exit_code": b["exit_code"], "requests": len(b["requests"]),
+                   "same_exit_code": a["exit_code"] == b["exit_code"], "same_requests": a["requests"] == b["requests"],
+                   # JSON contract: every key / value the reference prints is printed here (this CLI may add keys); nothing to compare when
+                   # the reference printed no JSON (e.g. its "No images found" text in JSON mode)
+                   "same_json": covers(b["json"], a["json"]) if a["json"] is not None else None}  # fmt: skip
+            rows.append(row)
+            if not (row["same_exit_code"] and row["same_requests"] and row["same_json"] in (True, None)):
+                diffs.append({"command": row["command"], "reference": a, "ours": b})
+    print(json.dumps({"commands": len(rows), "identical": sum(1 for r in rows if r["same_exit_code"] and r["same_requests"] and r["same_json"] in (True, None)),
+                      "rows": rows, "differences": diffs}, indent=1))  # fmt: skip
+    srv.shutdown()
+    return 1 if diffs else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -59,7 +59,11 @@ def respond(method: str, path: str, host: str):
         ("PUT", r"/api/v1/evaluations/ev1$", {"evaluation_id": "ev1"}), ("POST", r"/api/v1/evaluations/$", {"evaluation_id": "ev1", "id": "ev1"}),
         ("GET", r"/api/v1/evaluations/$", {"evaluations": [], "total": 0}),
         ("GET", r"/api/v1/pods/status$", {"data": [{"podId": "p1", "providerType": "x", "status": "ACTIVE", "sshConnection": [None], "ip": "1.2.3.4"}]}),
-        ("GET", r"/api/v1/pods/history$", {"total_count": 0, "offset": 0, "limit": 100, "data": []}),
+        ("GET", r"/api/v1/pods/history$", {"total_count": 1, "offset": 0, "limit": 100, "data": [{"id": "h1", "name": "old", "providerType": "x", "type": "HOSTED", "gpuName": "H100_80GB", "count": 8, "createdAt": "2025-01-01T00:00:00Z", "terminatedAt": "2025-01-01T05:30:00Z", "priceHr": 2.5, "totalBilledPrice": 13.75, "teamId": None, "userId": "u1"}]}),
+        ("GET", r"/api/v1/rft/adapters$", {"adapters": [{"id": "a1", "displayName": "run-1", "userId": "u1", "teamId": None, "rftRunId": "r1", "baseModel": "Qwen/Qwen3-4B", "step": 10, "status": "READY", "deploymentStatus": "NOT_DEPLOYED", "createdAt": "2025-01-01T00:00:00Z", "updatedAt": "2025-01-01T00:00:00Z"}], "total": 1}),
+        ("GET", r"/api/v1/rft/deployable-models$", {"models": ["Qwen/Qwen3-4B"]}),
+        ("GET", r"/api/v1/user/whoami$", {"data": {"id": "u1", "email": "a@b.c", "name": "A", "scope": {"pods": {"read": True, "write": True}}}}),
+        ("GET", r"/api/v1/user/teams$", {"data": [{"teamId": "t1", "name": "Team", "slug": "team", "role": "ADMIN", "createdAt": "2025-01-01T00:00:00Z"}]}),
         ("GET", r"/api/v1/pods/p1$", POD), ("DELETE", r"/api/v1/pods/p1$", {}), ("POST", r"/api/v1/pods/?$", POD),
         ("GET", r"/api/v1/pods/?$", {"total_count": 1, "offset": 0, "limit": 100, "data": [POD]}),
         ("GET", r"/api/v1/disks/d1$", DISK), ("DELETE", r"/api/v1/disks/d1$", {"status": "deleted"}), ("PATCH", r"/api/v1/disks/d1$", {"status": "ok"}),
