@@ -45,9 +45,12 @@ def handle_errors(fn: Callable) -> Callable:
             raise typer.Exit(1)
         except APIError as e:
             raise fail(str(e))
-        except (KeyboardInterrupt, typer.Abort):
+        except KeyboardInterrupt:
             console.print("\n[dim]Cancelled.[/dim]")
             raise typer.Exit(130)
+        except typer.Abort:  # a prompt hit EOF or was declined by click itself: click's own convention (and the reference's exit code)
+            console.print("\n[dim]Aborted.[/dim]")
+            raise typer.Exit(1)
 
     return wrapper
 

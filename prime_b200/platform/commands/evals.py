@@ -439,8 +439,15 @@ def logs_cmd(eval_id: str = typer.Argument(...), tail: int = typer.Option(LOGS_T
     c = api()
     if follow:
         return follow_logs(c, eval_id, poll_interval)
-    text = clean_logs(c.get(f"/hosted-evaluations/{eval_id}/logs", params={"tail_lines": tail}).get("logs") or "")
-    console.print(text, markup=False, highlight=False) if text else console.print("[yellow]No logs available yet.[/yellow]")
+    # status first, then the whole log (the endpoint takes no tail parameter: the last `tail` lines are cut here), then the status line
+    status = c.get(f"/evaluations/{eval_id}")
+    text = clean_logs(c.get(f"/hosted-evaluations/{eval_id}/logs").get("logs") or "")
+    if text:
+        console.print("\n".join(text.splitlines()[-tail:]), markup=False, highlight=False)
+    else:
+        console.print("[yellow]No logs available.[/yellow]")
+    console.print()
+    print_eval_status(status)
 
 
 @app.command("stop", no_args_is_help=True)

@@ -487,10 +487,8 @@ def delete_run(run_id: str = typer.Argument(...), yes: bool = typer.Option(False
 def restart_run(run_id: str = typer.Argument(...), yes: bool = typer.Option(False, "--yes", "-y", "--force", "-f", help="Skip confirmation")) -> None:
     """Restart a RUNNING run from its latest checkpoint (server side)."""
     client = RLClient(api())
-    run = client.get_run(run_id)
-    if run.status != "RUNNING":
-        raise fail(f"Only RUNNING runs can be restarted (status: {run.status}); checkpoints of finished runs are already cleaned up.")
-    if not confirm_or_skip(f"Restart run {run_id} from its latest checkpoint?", yes):
+    # no status pre-check: the server refuses runs that are not RUNNING and says why (one request, as the reference does)
+    if not confirm_or_skip(f"Restart run {run_id} from its latest checkpoint? (only RUNNING runs can be restarted)", yes):
         raise typer.Exit(0)
     r = client.restart_run(run_id)
     console.print(f"[green]✓ Restart requested[/green] (status: {r.status})")

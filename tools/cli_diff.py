@@ -37,6 +37,19 @@ COMMANDS: list[list[str]] = [
     ["teams", "list", "-o", "json"], ["whoami"], ["secret", "list", "-o", "json"], ["env", "list", "-o", "json"], ["registry", "list", "-o", "json"],
     ["images", "list", "-o", "json"], ["rl", "list", "-o", "json"], ["rl", "models", "-o", "json"], ["rl", "get", "r1", "-o", "json"], ["deployments", "list", "-o", "json"],
     ["inference", "models", "-o", "json"], ["config", "view"], ["config", "set-team-id", "team-1"], ["config", "view"], ["--version"],
+    # second batch: mutating commands and the remaining groups
+    ["secret", "get", "sec1", "-o", "json"], ["secret", "create", "--name", "TOKEN", "--value", "v"], ["secret", "update", "sec1", "--name", "NEW"],
+    ["secret", "delete", "sec1", "--yes"],
+    ["env", "status", "owner/env"], ["env", "info", "owner/env"], ["env", "version", "list", "owner/env"], ["env", "action", "list", "owner/env"],
+    ["env", "secret", "list", "owner/env"], ["env", "var", "list", "owner/env"], ["env", "delete", "owner/env", "--force"],
+    ["rl", "stop", "r1", "--force"], ["rl", "delete", "r1", "--force"], ["rl", "restart", "r1", "--force"], ["rl", "logs", "r1", "--tail", "10"],
+    ["rl", "metrics", "r1"], ["rl", "rollouts", "r1", "--step", "1"], ["rl", "progress", "r1"], ["rl", "distributions", "r1"],
+    ["tunnel", "list"], ["tunnel", "status", "t1"], ["teams", "members", "--team-id", "t1", "-o", "json"],
+    ["registry", "check-image", "python:3.11-slim"], ["images", "delete", "img:tag", "--yes"],
+    ["config", "set-base-url", "http://example.invalid"], ["config", "set-frontend-url", "http://front.invalid"], ["config", "set-ssh-key-path", "/tmp/key"],
+    ["config", "remove-team-id"], ["config", "set-share-resources-with-team", "true"], ["config", "view"],
+    ["sandbox", "reset-cache", "--yes"], ["eval", "stop", "ev1"], ["eval", "logs", "ev1"], ["switch"], ["pods", "connect", "--help"],
+    ["sandbox", "create", "--help"], ["env", "push", "--help"], ["rl", "run", "--help"],
 ]  # fmt: skip
 
 
@@ -73,14 +86,15 @@ def covers(ours, ref) -> bool:
     return ours == ref
 
 
-def main() -> int:
+def main(stride: int = 1) -> int:
+    """``stride`` > 1 runs every stride-th command line (the test suite's quick pass; the committed profile is the full run)."""
     srv = ThreadingHTTPServer(("127.0.0.1", 0), Recorder)
     srv.daemon_threads = True
     threading.Thread(target=srv.serve_forever, daemon=True).start()
     base = f"http://127.0.0.1:{srv.server_address[1]}"
     rows, diffs = [], []
     with tempfile.TemporaryDirectory() as h1, tempfile.TemporaryDirectory() as h2:
-        for args in COMMANDS:
+        for args in COMMANDS[::stride]:
             got = {}
             for arm, home in (("reference", h1), ("ours", h2)):
                 rc, out, err = run_cli(arm, base, home, args)
@@ -103,4 +117,4 @@ def main() -> int:
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(main(int(sys.argv[1]) if len(sys.argv) > 1 else 1))
