@@ -5,7 +5,7 @@ sends. The request sequences (method, path, query, JSON body) and the outcome of
 
     python tools/wire_diff.py > profiles/wire_diff.json        # exit code 1 on any difference
 
-What it covers: 51 SDK / API-client calls — sandbox lifecycle, command execution, file transfer, ports, SSH sessions, bulk delete,
+What it covers: 88 SDK / API-client calls — sync and async sandbox and evaluation clients, RL, deployments and tunnel clients; sandbox lifecycle, command execution, file transfer, ports, SSH sessions, bulk delete,
 evaluation create / push / finalize / list, pods, disks, availability — and injected failures: 404 / 401 / 402 / 422, a flaky idempotent
 GET (retried), a 503 on a non-idempotent POST (not retried), gateway 502 ``sandbox_not_found``, 408, 409. A failure counts as the same
 when this repo raises the reference's exception class or a subclass of it. What it cannot cover: responses of the real service.
@@ -60,6 +60,16 @@ def respond(method: str, path: str, host: str):
         ("GET", r"/api/v1/evaluations/$", {"evaluations": [], "total": 0}),
         ("GET", r"/api/v1/pods/status$", {"data": [{"podId": "p1", "providerType": "x", "status": "ACTIVE", "sshConnection": [None], "ip": "1.2.3.4"}]}),
         ("GET", r"/api/v1/pods/history$", {"total_count": 1, "offset": 0, "limit": 100, "data": [{"id": "h1", "name": "old", "providerType": "x", "type": "HOSTED", "gpuName": "H100_80GB", "count": 8, "createdAt": "2025-01-01T00:00:00Z", "terminatedAt": "2025-01-01T05:30:00Z", "priceHr": 2.5, "totalBilledPrice": 13.75, "teamId": None, "userId": "u1"}]}),
+        ("GET", r"/api/v1/rft/runs/r1/logs$", {"logs": "l1\nl2"}), ("GET", r"/api/v1/rft/runs/r1/metrics$", {"metrics": [{"step": 1, "reward": 0.5}]}),
+        ("GET", r"/api/v1/rft/runs/r1/rollouts$", {"samples": [], "total": 0}), ("GET", r"/api/v1/rft/runs/r1/progress$", {"latest_step": 3}),
+        ("GET", r"/api/v1/rft/runs/r1/distributions$", {"bins": []}), ("GET", r"/api/v1/rft/runs/r1/checkpoints$", {"checkpoints": []}),
+        ("GET", r"/api/v1/rft/runs/r1$", {"run": {"id": "r1", "name": "run", "userId": "u1", "teamId": None, "status": "RUNNING", "baseModel": "Qwen/Qwen3-4B", "environments": [{"id": "owner/env"}], "rolloutsPerExample": 8, "seqLen": 2048, "maxSteps": 10, "batchSize": 32, "createdAt": T, "updatedAt": T}}), ("PUT", r"/api/v1/rft/runs/r1/(stop|restart)$", {"run": {"id": "r1", "name": "run", "userId": "u1", "teamId": None, "status": "RUNNING", "baseModel": "Qwen/Qwen3-4B", "environments": [{"id": "owner/env"}], "rolloutsPerExample": 8, "seqLen": 2048, "maxSteps": 10, "batchSize": 32, "createdAt": T, "updatedAt": T}}),
+        ("DELETE", r"/api/v1/rft/runs/r1$", {}), ("POST", r"/api/v1/rft/runs$", {"run": {"id": "r1", "name": "run", "userId": "u1", "teamId": None, "status": "RUNNING", "baseModel": "Qwen/Qwen3-4B", "environments": [{"id": "owner/env"}], "rolloutsPerExample": 8, "seqLen": 2048, "maxSteps": 10, "batchSize": 32, "createdAt": T, "updatedAt": T}}), ("GET", r"/api/v1/rft/runs$", {"runs": [{"id": "r1", "name": "run", "userId": "u1", "teamId": None, "status": "RUNNING", "baseModel": "Qwen/Qwen3-4B", "environments": [{"id": "owner/env"}], "rolloutsPerExample": 8, "seqLen": 2048, "maxSteps": 10, "batchSize": 32, "createdAt": T, "updatedAt": T}]}),
+        ("GET", r"/api/v1/rft/models$", {"models": [{"name": "Qwen/Qwen3-4B", "atCapacity": False}]}),
+        ("GET", r"/api/v1/rft/adapters/a1$", {"adapter": {"id": "a1", "displayName": "run-1", "userId": "u1", "teamId": None, "rftRunId": "r1", "baseModel": "Qwen/Qwen3-4B", "step": 10, "status": "READY", "deploymentStatus": "NOT_DEPLOYED", "createdAt": T, "updatedAt": T}}),
+        ("POST", r"/api/v1/rft/adapters/a1/(deploy|unload)$", {"adapter": {"id": "a1", "displayName": "run-1", "userId": "u1", "teamId": None, "rftRunId": "r1", "baseModel": "Qwen/Qwen3-4B", "step": 10, "status": "READY", "deploymentStatus": "DEPLOYING", "createdAt": T, "updatedAt": T}}),
+        ("GET", r"/api/v1/tunnel/t1$", {"tunnel_id": "t1", "hostname": "t1.example", "url": "https://t1.example", "frp_token": "tok", "server_host": "frp.example", "server_port": 7000, "expires_at": "2099-01-01T00:00:00Z", "status": "active", "local_port": 8080, "name": "web", "binding_secret": "b"}), ("DELETE", r"/api/v1/tunnel/t1$", {"success": True}), ("DELETE", r"/api/v1/tunnel$", {"succeeded": ["t1"], "failed": []}),
+        ("POST", r"/api/v1/tunnel$", {"tunnel_id": "t1", "hostname": "t1.example", "url": "https://t1.example", "frp_token": "tok", "server_host": "frp.example", "server_port": 7000, "expires_at": "2099-01-01T00:00:00Z", "status": "active", "local_port": 8080, "name": "web", "binding_secret": "b"}), ("GET", r"/api/v1/tunnel$", {"tunnels": [{"tunnel_id": "t1", "hostname": "t1.example", "url": "https://t1.example", "frp_token": "tok", "server_host": "frp.example", "server_port": 7000, "expires_at": "2099-01-01T00:00:00Z", "status": "active", "local_port": 8080, "name": "web", "binding_secret": "b"}]}),
         ("GET", r"/api/v1/rft/adapters$", {"adapters": [{"id": "a1", "displayName": "run-1", "userId": "u1", "teamId": None, "rftRunId": "r1", "baseModel": "Qwen/Qwen3-4B", "step": 10, "status": "READY", "deploymentStatus": "NOT_DEPLOYED", "createdAt": "2025-01-01T00:00:00Z", "updatedAt": "2025-01-01T00:00:00Z"}], "total": 1}),
         ("GET", r"/api/v1/rft/deployable-models$", {"models": ["Qwen/Qwen3-4B"]}),
         ("GET", r"/api/v1/user/whoami$", {"data": {"id": "u1", "email": "a@b.c", "name": "A", "scope": {"pods": {"read": True, "write": True}}}}),
@@ -234,6 +244,71 @@ call("disks_update", lambda: disks.update("d1", "newname"))
 call("disks_delete", lambda: disks.delete("d1"))
 call("avail_get", lambda: av.get(regions=["united_states"], gpu_count=8, gpu_type="H100_80GB"))
 call("avail_disks", lambda: av.get_disks(regions=["united_states"]))
+from prime_cli.api.rl import RLClient
+from prime_cli.api.deployments import DeploymentsClient
+rl, dep = RLClient(api), DeploymentsClient(api)
+call("rl_list", lambda: rl.list_runs(team_id="t1"))
+call("rl_models", lambda: rl.list_models())
+call("rl_get", lambda: rl.get_run("r1"))
+call("rl_stop", lambda: rl.stop_run("r1"))
+call("rl_restart", lambda: rl.restart_run("r1"))
+call("rl_delete", lambda: rl.delete_run("r1"))
+call("rl_logs", lambda: rl.get_logs("r1", tail_lines=50))
+call("rl_metrics", lambda: rl.get_metrics("r1", min_step=1, max_step=9, limit=5))
+call("rl_rollouts", lambda: rl.get_rollouts("r1", step=3, page=2, limit=10))
+call("rl_progress", lambda: rl.get_progress("r1"))
+call("rl_distributions", lambda: rl.get_distributions("r1", distribution_type="reward", step=3))
+call("rl_checkpoints", lambda: rl.list_checkpoints("r1"))
+call("rl_env_status", lambda: rl.get_environment_status("owner", "env"))
+call("rl_create", lambda: rl.create_run(model_name="Qwen/Qwen3-4B", environments=[{"id": "owner/env"}], rollouts_per_example=8, max_steps=10, batch_size=32))
+call("dep_list", lambda: dep.list_adapters(team_id="t1", limit=20, offset=40))
+call("dep_get", lambda: dep.get_adapter("a1"))
+call("dep_deployable", lambda: dep.get_deployable_models())
+call("dep_deploy", lambda: dep.deploy_adapter("a1"))
+call("dep_unload", lambda: dep.unload_adapter("a1"))
+
+import asyncio
+from prime_sandboxes import AsyncSandboxClient
+from prime_evals import AsyncEvalsClient
+from prime_tunnel.core.client import TunnelClient
+
+async def async_part():
+    async def acall(label, coro_fn):
+        try:
+            r = await coro_fn()
+            if hasattr(r, "model_dump"):
+                r = r.model_dump(mode="json")
+            elif isinstance(r, list) and r and hasattr(r[0], "model_dump"):
+                r = [x.model_dump(mode="json") for x in r]
+            results.append([label, "ok", json.loads(json.dumps(r, default=str))])
+        except Exception as e:
+            results.append([label, "raised", [type(e).__name__, str(e)[:160], [k.__name__ for k in type(e).__mro__]]])
+    ac = AsyncSandboxClient(api_key="k")
+    await acall("a_create", lambda: ac.create(CreateSandboxRequest(name="bench", docker_image="python:3.11-slim", cpu_cores=2, memory_gb=4)))
+    await acall("a_get", lambda: ac.get("s1"))
+    await acall("a_list", lambda: ac.list(labels=["a"], per_page=5))
+    await acall("a_exec", lambda: ac.execute_command("s1", "echo ok", timeout=9))
+    await acall("a_upload", lambda: ac.upload_file("s1", "/tmp/a.txt", src))
+    await acall("a_read", lambda: ac.read_file("s1", "/tmp/a.txt"))
+    await acall("a_expose", lambda: ac.expose("s1", 8000, name="web"))
+    await acall("a_bulk_delete", lambda: ac.bulk_delete(sandbox_ids=["s1"]))
+    await acall("a_missing", lambda: ac.get("missing"))
+    await acall("a_delete", lambda: ac.delete("s1"))
+    await ac.aclose()
+    ae = AsyncEvalsClient(api_key="k")
+    await acall("a_eval_create", lambda: ae.create_evaluation(name="n", environments=[{"id": "env1"}], model_name="m"))
+    await acall("a_eval_push", lambda: ae.push_samples("ev1", [{"example_id": i, "reward": 1.0} for i in range(3)]))
+    await acall("a_eval_finalize", lambda: ae.finalize_evaluation("ev1"))
+    await ae.aclose()
+    tc = TunnelClient(api_key="k")
+    await acall("t_create", lambda: tc.create_tunnel(8080, name="web"))
+    await acall("t_list", lambda: tc.list_tunnels())
+    await acall("t_get", lambda: tc.get_tunnel("t1"))
+    await acall("t_delete", lambda: tc.delete_tunnel("t1"))
+    await acall("t_bulk_delete", lambda: tc.bulk_delete_tunnels(["t1", "t2"]))
+    await tc.close()
+
+asyncio.run(async_part())
 print(json.dumps(results))
 '''
 
