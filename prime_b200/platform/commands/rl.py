@@ -252,8 +252,10 @@ max_tokens = 2048
 '''
 
 
-def generate_rl_config_template(environment: str | None = None, model: str = "Qwen/Qwen3-4B-Instruct-2507", filename: str = "rl.toml") -> str:
-    return CONFIG_TEMPLATE.format(environment=environment or "primeintellect/wordle", model=model, filename=filename)
+def generate_rl_config_template(environment: str | None = None, model: str = "PrimeIntellect/Qwen3-0.6B-Reverse-Text-SFT",
+                                filename: str = "rl.toml") -> str:  # fmt: skip
+    """Defaults = the reference template's quick-start pair: a 0.6 B model and the reverse-text environment (a run that starts in minutes)."""
+    return CONFIG_TEMPLATE.format(environment=environment or "primeintellect/reverse-text", model=model, filename=filename)
 
 
 # ------------------------------------------------------------------------------------------------- log rendering
@@ -312,6 +314,12 @@ def run_row(r: RLRun) -> dict[str, Any]:
             "runs_ahead": r.runs_ahead, "team_id": r.team_id}  # fmt: skip
 
 
+def run_json(r: RLRun) -> dict[str, Any]:
+    """What ``-o json`` prints for a run: every field of the record under its own name (``base_model``, ``environments`` as the list
+    of dicts, timestamps in ``str(datetime)`` form — the shape scripts parse) plus two convenience keys."""
+    return {**r.model_dump(), "model": r.base_model, "dashboard_url": dashboard_url(r.id)}
+
+
 def dashboard_url(run_id: str) -> str:
     return f"{Config(writable=False).frontend_url}/dashboard/training/{run_id}"
 
@@ -352,7 +360,8 @@ def print_config_summary(cfg: RLConfig, secrets: dict[str, str]) -> None:
     console.print()
 
 
-@app.command("run", epilog=json_output_help({"id": "str", "status": "str", "runs_ahead": "int|null", "dashboard_url": "str"}))
+@app.command("run", epilog=json_output_help({"run": {"id": "str", "status": "str", "…": "every field of the run"}, "id": "str", "status": "str",
+                                                 "runs_ahead": "int|null", "dashboard_url": "str"}))
 @handle_errors
 def create_run(
     config_path: str = typer.Argument(..., help="TOML config (see 'prime rl init')"),
@@ -395,7 +404,8 @@ def create_run(
     )  # fmt: skip
     url = dashboard_url(run.id)
     if output == "json":
-        return output_data_as_json({**run_row(run), "dashboard_url": url}, console)
+        # {"run": <every field of the created run>} as scripts know it (timestamps in str(datetime) form), plus the summary keys
+        return output_data_as_json({"run": run.model_dump(), **run_json(run)}, console)
     if run.status == "QUEUED":
         ahead = f" (~{run.runs_ahead} run(s) ahead)" if run.runs_ahead is not None else ""
         console.print(f"[yellow]Run {run.id} is QUEUED{ahead}[/yellow]")
@@ -421,11 +431,12 @@ def _list_runs(output: str, team: str | None, num: int, page: int) -> None:
         raise fail("--num and --page must be at least 1")
     runs = sorted(RLClient(api()).list_runs(team_id=team or Config(writable=False).team_id), key=lambda r: r.created_at, reverse=True)
     total = len(runs)
-    rows = [run_row(r) for r in runs[(page - 1) * num : page * num]]
+    shown = runs[(page - 1) * num : page * num]
+    rows = [run_row(r) for r in shown]
     if output != "json" and not rows:
         console.print("[yellow]No more results.[/yellow]" if page > 1 else "[yellow]No RL training runs found.[/yellow]")
         return
-    emit(output, {"runs": rows, "total": total, "total_count": total, "page": page, "per_page": num}, f"RL Runs (Total: {total})",
+    emit(output, {"runs": [run_json(r) for r in shown], "total": total, "total_count": total, "page": page, "per_page": num}, f"RL Runs (Total: {total})",
          [("ID", "cyan"), ("Name", "blue"), "Status", ("Model", "green"), "Environments", "Steps", ("Created", "magenta")],
          [[r["id"], r["name"] or "", colorize(r["status"], RUN_STATUS_COLORS), r["model"], ", ".join(map(str, r["environments"])), r["max_steps"],
            format_time_ago(r["created_at"])] for r in rows],
@@ -457,8 +468,9 @@ def ls_runs(team: Optional[str] = _TEAM_OPT, num: int = _NUM_OPT, page: int = _P
 @handle_errors
 def get_run(run_id: str = typer.Argument(...), output: str = OUTPUT_OPT) -> None:
     """Details of one run."""
-    row = run_row(RLClient(api()).get_run(run_id))
-    emit(output, {**row, "dashboard_url": dashboard_url(run_id)}, f"RL Run {run_id}", [("Field", "cyan"), ("Value", "green")],
+    run = RLClient(api()).get_run(run_id)
+    row = run_row(run)
+    emit(output, {"run": run.model_dump(), **run_json(run)}, f"RL Run {run_id}", [("Field", "cyan"), ("Value", "green")],
          [[k, colorize(v, RUN_STATUS_COLORS) if k == "status" else ("" if v is None else v)] for k, v in row.items()])  # fmt: skip
 
 

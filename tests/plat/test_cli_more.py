@@ -113,7 +113,7 @@ def test_rl_init_validate_and_run(tmp_path, fake_api, monkeypatch):
     r = runner.invoke(app, ["rl", "init", str(cfgp)])
     assert r.exit_code == 0 and cfgp.exists()
     cfg = rl_mod.load_config(str(cfgp))
-    assert cfg.env[0].id == "primeintellect/wordle" and cfg.sampling.max_tokens == 2048
+    assert cfg.env[0].id == "primeintellect/reverse-text" and cfg.model == "PrimeIntellect/Qwen3-0.6B-Reverse-Text-SFT" and cfg.sampling.max_tokens == 2048
     bad = tmp_path / "bad.toml"
     bad.write_text('model = "m"\nbogus_key = 1\n[[env]]\nid = "a/b"\n')
     r = runner.invoke(app, ["rl", "run", str(bad)])

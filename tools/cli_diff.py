@@ -50,7 +50,52 @@ COMMANDS: list[list[str]] = [
     ["config", "remove-team-id"], ["config", "set-share-resources-with-team", "true"], ["config", "view"],
     ["sandbox", "reset-cache", "--yes"], ["eval", "stop", "ev1"], ["eval", "logs", "ev1"], ["switch"], ["pods", "connect", "--help"],
     ["sandbox", "create", "--help"], ["env", "push", "--help"], ["rl", "run", "--help"],
+    # third batch: flows that read or write local files
+    ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
+    ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
+    ["eval", "push", "outputs/evals/gsm8k--org--m/run1", "--env", "owner/env"], ["eval", "push", "--env", "owner/env", "-o", "json"],
 ]  # fmt: skip
+
+
+RL_TOML = """model = "Qwen/Qwen3-4B-Instruct-2507"
+name = "diff-run"
+max_steps = 20
+batch_size = 64
+rollouts_per_example = 4
+learning_rate = 1e-5
+
+[[env]]
+id = "owner/env"
+args = { difficulty = "hard" }
+
+[sampling]
+max_tokens = 512
+temperature = 0.8
+
+[checkpoints]
+interval = 10
+"""
+
+
+def prepare_files(home: Path) -> None:
+    """Inputs of the file-based command lines, identical in both arms' working directories."""
+    (home / "rl.toml").write_text(RL_TOML)
+    (home / "a.txt").write_text("hello")
+    run = home / "outputs" / "evals" / "gsm8k--org--m" / "run1"
+    run.mkdir(parents=True)
+    (run / "metadata.json").write_text(json.dumps({"env_id": "gsm8k", "env": "gsm8k", "model": "org/m", "num_examples": 2, "rollouts_per_example": 1,
+                                                    "avg_reward": 0.5, "date": "2025-01-01", "time": "00:00:00", "sampling_args": {"max_tokens": 16}}))  # fmt: skip
+    (run / "results.jsonl").write_text("\n".join(json.dumps({"example_id": i, "reward": 0.5, "task": "t", "prompt": [{"role": "user", "content": "q"}],
+                                                              "completion": [{"role": "assistant", "content": "a"}]}) for i in range(2)))  # fmt: skip
+
+
+def toml_of(path: Path):
+    try:
+        import tomllib
+
+        return tomllib.loads(path.read_text())
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def run_cli(arm: str, base: str, home: str, args: list[str]) -> tuple[int, str, str]:
@@ -94,6 +139,8 @@ def main(stride: int = 1) -> int:
     base = f"http://127.0.0.1:{srv.server_address[1]}"
     rows, diffs = [], []
     with tempfile.TemporaryDirectory() as h1, tempfile.TemporaryDirectory() as h2:
+        for h in (h1, h2):
+            prepare_files(Path(h))
         for args in COMMANDS[::stride]:
             got = {}
             for arm, home in (("reference", h1), ("ours", h2)):
@@ -101,6 +148,8 @@ def main(stride: int = 1) -> int:
                 log = json.loads(urllib.request.urlopen(base + "/__log").read())
                 got[arm] = {"exit_code": rc, "requests": [{k: e[k] for k in ("method", "path", "query", "body")} for e in log], "json": parsed_json(out),
                             "stdout_tail": out.strip()[-300:], "stderr_tail": err.strip()[-300:]}  # fmt: skip
+            if args[:2] == ["rl", "init"]:  # the template each CLI wrote: compare what it configures, not its comments
+                got["reference"]["json"], got["ours"]["json"] = toml_of(Path(h1) / args[2]), toml_of(Path(h2) / args[2])
             a, b = got["reference"], got["ours"]
             row = {"command": "prime " + " ".join(args), "exit_code": b["exit_code"], "requests": len(b["requests"]),
                    "same_exit_code": a["exit_code"] == b["exit_code"], "same_requests": a["requests"] == b["requests"],
