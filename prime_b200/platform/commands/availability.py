@@ -33,10 +33,11 @@ def offer_row(g: GPUAvailability, gpu_type: str) -> dict[str, Any]:
     disk = str(g.disk.default_count)
     if g.disk.max_count is not None and g.disk.max_count != g.disk.default_count:
         disk += "+"
-    return {"id": generate_short_id(g), "cloud_id": g.cloud_id, "gpu_type": gpu_type, "gpu_count": g.gpu_count,
+    # display forms scripts already parse: "B200 180GB" (underscores → spaces), security "community" | "datacenter"
+    return {"id": generate_short_id(g), "cloud_id": g.cloud_id, "gpu_type": gpu_type.replace("_", " "), "gpu_count": g.gpu_count,
             "socket": g.socket or "N/A", "provider": g.provider or "N/A", "location": g.country or "N/A",
             "stock_status": g.stock_status, "price_per_hour": f"${price:.2f}" if price != float("inf") else "N/A",
-            "price_value": None if price == float("inf") else price, "security": g.security or "N/A",
+            "price_value": None if price == float("inf") else price, "security": "community" if g.security == "community_cloud" else "datacenter",
             "vcpus": str(g.vcpu.default_count), "memory_gb": str(g.memory.default_count), "disk_gb": disk,
             "gpu_memory": g.gpu_memory, "is_spot": g.is_spot}  # fmt: skip
 

@@ -146,7 +146,7 @@ def test_availability_list_groups_and_short_ids(fake_api):
     # /availability/multi-node is not routed → that endpoint "is down": the note goes to stderr, stdout stays valid JSON
     r = runner.invoke(app, ["availability", "list", "--gpu-type", "B200_180GB"])
     assert r.exit_code == 0, r.output
-    assert "B200_180GB" in r.output and "hyperstack" in r.output
+    assert "B200 180GB" in r.output and "hyperstack" in r.output  # display form: underscores → spaces
     res = CliRunner(mix_stderr=False).invoke(app, ["availability", "list", "--gpu-type", "B200_180GB", "-o", "json"])
     assert "multi-node" in res.stderr
     out = json.loads(res.stdout)

@@ -21,13 +21,13 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from tools.wire_diff import REF_PATHS, Recorder  # noqa: E402
+from tools.wire_diff import REF_PATHS, Recorder, covers  # noqa: E402
 
 COMMANDS: list[list[str]] = [
     ["pods", "list", "--output", "json"], ["pods", "list", "--limit", "10", "--offset", "5", "-o", "json"], ["pods", "status", "p1", "-o", "json"],
     ["pods", "history", "-o", "json"], ["pods", "terminate", "p1", "--yes"],
     ["disks", "list", "-o", "json"], ["disks", "get", "d1", "-o", "json"], ["disks", "update", "d1", "--name", "newname"], ["disks", "terminate", "d1", "--yes"],
-    ["availability", "list", "--gpu-type", "H100_80GB", "--gpu-count", "8", "-o", "json"], ["availability", "gpu-types"], ["availability", "disks", "-o", "json"],
+    ["availability", "list", "--gpu-type", "B200_180GB", "--gpu-count", "8", "-o", "json"], ["availability", "gpu-types"], ["availability", "disks", "-o", "json"],
     ["sandbox", "list", "-o", "json"], ["sandbox", "list", "--status", "RUNNING", "--label", "a", "--page", "2", "--num", "10", "-o", "json"],
     ["sandbox", "get", "s1", "-o", "json"], ["sandbox", "run", "s1", "echo ok"], ["sandbox", "logs", "s1"], ["sandbox", "delete", "s1", "--yes"],
     ["sandbox", "create", "--name", "bench", "--cpu-cores", "2", "--memory-gb", "4", "--yes", "python:3.11-slim"],
@@ -50,6 +50,7 @@ COMMANDS: list[list[str]] = [
     ["config", "remove-team-id"], ["config", "set-share-resources-with-team", "true"], ["config", "view"],
     ["sandbox", "reset-cache", "--yes"], ["eval", "stop", "ev1"], ["eval", "logs", "ev1"], ["switch"], ["pods", "connect", "--help"],
     ["sandbox", "create", "--help"], ["env", "push", "--help"], ["rl", "run", "--help"],
+    ["availability", "list", "--gpu-type", "B200_180GB", "-o", "json"], ["availability", "list", "--gpu-type", "B200_180GB", "--no-group-similar", "-o", "json"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
@@ -119,16 +120,6 @@ def parsed_json(stdout: str):
             except json.JSONDecodeError:
                 continue
     return None
-
-
-def covers(ours, ref) -> bool:
-    """Does ``ours`` contain everything ``ref`` says? dict: every reference key present with a covering value (extra keys allowed);
-    list: same length, element-wise; scalars: equal."""
-    if isinstance(ref, dict):
-        return isinstance(ours, dict) and all(k in ours and covers(ours[k], v) for k, v in ref.items())
-    if isinstance(ref, list):
-        return isinstance(ours, list) and len(ours) == len(ref) and all(covers(a, b) for a, b in zip(ours, ref))
-    return ours == ref
 
 
 def main(stride: int = 1) -> int:
