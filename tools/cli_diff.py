@@ -58,6 +58,8 @@ COMMANDS: list[list[str]] = [
     ["sandbox", "create", "--name", "x", "--gpu-count", "1", "--gpu-type", "H100_80GB", "--vm", "--yes", "img:tag"],
     ["sandbox", "create", "--env", "A=1", "--env", "B=2", "--label", "l1", "--timeout-minutes", "30", "--yes", "python:3.11-slim"],
     ["sandbox", "delete", "--all", "--yes"], ["sandbox", "delete", "--label", "a", "--yes"], ["secret", "create", "--name", "N", "--value", "v", "--description", "d"],
+    # the packaging pipeline: build the wheel, resolve, wheel upload + finalize, source archive upload + finalize
+    ["env", "push", "--path", "myenv", "--visibility", "PRIVATE"], ["env", "push", "--path", "myenv", "--auto-bump"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
@@ -89,12 +91,50 @@ def prepare_files(home: Path) -> None:
     """Inputs of the file-based command lines, identical in both arms' working directories."""
     (home / "rl.toml").write_text(RL_TOML)
     (home / "a.txt").write_text("hello")
+    make_env_project(home / "myenv")
     run = home / "outputs" / "evals" / "gsm8k--org--m" / "run1"
     run.mkdir(parents=True)
     (run / "metadata.json").write_text(json.dumps({"env_id": "gsm8k", "env": "gsm8k", "model": "org/m", "num_examples": 2, "rollouts_per_example": 1,
                                                     "avg_reward": 0.5, "date": "2025-01-01", "time": "00:00:00", "sampling_args": {"max_tokens": 16}}))  # fmt: skip
     (run / "results.jsonl").write_text("\n".join(json.dumps({"example_id": i, "reward": 0.5, "task": "t", "prompt": [{"role": "user", "content": "q"}],
                                                               "completion": [{"role": "assistant", "content": "a"}]}) for i in range(2)))  # fmt: skip
+
+
+ENV_BACKEND = '''
+import base64, hashlib, io, os, tarfile, zipfile
+NAME, VER = "myenv", "0.1.0"
+META = f"Metadata-Version: 2.1\\\\nName: {NAME}\\\\nVersion: {VER}\\\\nSummary: diff env\\\\nRequires-Python: >=3.10\\\\nRequires-Dist: verifiers>=0.1.0\\\\n"
+def _zi(name):
+    z = zipfile.ZipInfo(name, date_time=(2020, 1, 1, 0, 0, 0)); z.external_attr = 0o644 << 16; return z
+def build_wheel(wheel_directory, config_settings=None, metadata_directory=None):
+    fn = f"{NAME}-{VER}-py3-none-any.whl"
+    files = {"myenv.py": open("myenv.py", "rb").read(), f"{NAME}-{VER}.dist-info/METADATA": META.encode(),
+             f"{NAME}-{VER}.dist-info/WHEEL": b"Wheel-Version: 1.0\\\\nGenerator: diff\\\\nRoot-Is-Purelib: true\\\\nTag: py3-none-any\\\\n"}
+    rec = "".join(f"{k},sha256={base64.urlsafe_b64encode(hashlib.sha256(v).digest()).rstrip(b'=').decode()},{len(v)}\\\\n" for k, v in files.items())
+    files[f"{NAME}-{VER}.dist-info/RECORD"] = (rec + f"{NAME}-{VER}.dist-info/RECORD,,\\\\n").encode()
+    with zipfile.ZipFile(os.path.join(wheel_directory, fn), "w") as z:
+        for k, v in files.items(): z.writestr(_zi(k), v)
+    return fn
+def build_sdist(sdist_directory, config_settings=None):
+    fn = f"{NAME}-{VER}.tar.gz"
+    with tarfile.open(os.path.join(sdist_directory, fn), "w:gz") as t:
+        for f in ("pyproject.toml", "myenv.py", "README.md", "backend.py"):
+            t.add(f, arcname=f"{NAME}-{VER}/{f}")
+    return fn
+def get_requires_for_build_wheel(config_settings=None): return []
+def get_requires_for_build_sdist(config_settings=None): return []
+'''
+
+
+def make_env_project(d: Path) -> None:
+    """A minimal verifiers environment whose wheel builds OFFLINE: an in-tree PEP 517 backend (no build requirements to download)
+    that writes a deterministic wheel — both CLIs build byte-identical archives, so content hashes and uploads are comparable."""
+    d.mkdir(parents=True, exist_ok=True)
+    (d / "pyproject.toml").write_text('[project]\nname = "myenv"\nversion = "0.1.0"\ndescription = "diff env"\ntags = ["test"]\nrequires-python = ">=3.10"\n'
+                                      'dependencies = ["verifiers>=0.1.0"]\n\n[build-system]\nrequires = []\nbuild-backend = "backend"\nbackend-path = ["."]\n')
+    (d / "myenv.py").write_text("def load_environment(**kw):\n    return None\n")
+    (d / "README.md").write_text("# myenv\n")
+    (d / "backend.py").write_text(ENV_BACKEND)
 
 
 def toml_of(path: Path):
@@ -109,7 +149,7 @@ def toml_of(path: Path):
 def run_cli(arm: str, base: str, home: str, args: list[str]) -> tuple[int, str, str]:
     code = "from prime_cli.main import run; run()" if arm == "reference" else "from prime_b200.platform.main import run; run()"
     env = {**os.environ, "HOME": home, "PRIME_API_BASE_URL": base, "PRIME_BASE_URL": base, "PRIME_INFERENCE_URL": base + "/api/v1", "PRIME_API_KEY": "k",
-           "PRIME_DISABLE_VERSION_CHECK": "1", "NO_COLOR": "1", "COLUMNS": "200", "TERM": "dumb",
+           "PRIME_DISABLE_VERSION_CHECK": "1", "NO_COLOR": "1", "COLUMNS": "200", "TERM": "dumb", "UV_OFFLINE": "1",
            "PYTHONPATH": os.pathsep.join(REF_PATHS if arm == "reference" else [str(ROOT)])}  # fmt: skip
     env.pop("PRIME_TEAM_ID", None)
     r = subprocess.run([sys.executable, "-c", f"import sys; sys.argv = ['prime', *{args!r}]; {code}"], env=env, capture_output=True, text=True,
@@ -136,6 +176,10 @@ def mask(req: dict) -> dict:
     body = req.get("body")
     if isinstance(body, dict) and isinstance(body.get("name"), str):
         req = {**req, "body": {**body, "name": re.sub(r"-[a-z0-9]{4}$", "-XXXX", body["name"])}}
+    if req.get("path", "").endswith("/versions") and isinstance(body, dict) and "sha256" in body:
+        # the source tarball embeds file and gzip timestamps: its digest differs between two runs of the SAME CLI; the content hash
+        # (over the source files) and the wheel digest are the comparable identifiers
+        req = {**req, "body": {**req["body"], "sha256": "<tarball digest>"}}
     return req
 
 

@@ -64,6 +64,12 @@ def respond(method: str, path: str, host: str):
         ("POST", r"/gw/ns/job/exec$", {"stdout": "ok\n", "stderr": "", "exit_code": 0}),
         ("POST", r"/gw/ns/job/upload$", {"success": True, "path": "/tmp/a.txt", "size": 5, "timestamp": T}),
         ("GET", r"/gw/ns/job/read-file$", {"content": "hello", "size": 5}), ("GET", r"/gw/ns/job/download$", b"hello"),
+        ("POST", r"/api/v1/environmentshub/resolve$", {"data": {"id": "env1", "created": True, "owner": {"name": "owner", "type": "user"}, "name": "myenv"}}),
+        ("POST", r"/api/v1/environmentshub/env1/wheels$", {"data": {"wheel_id": "w1", "upload_url": f"http://{host}/upload/wheel"}}),
+        ("POST", r"/api/v1/environmentshub/env1/wheels/w1/finalize$", {"data": {"success": True}}),
+        ("POST", r"/api/v1/environmentshub/env1/versions$", {"data": {"version_id": "v1", "upload_url": f"http://{host}/upload/source"}}),
+        ("POST", r"/api/v1/environmentshub/env1/versions/v1/finalize$", {"data": {"success": True, "message": "ok"}}),
+        ("PUT", r"/upload/(wheel|source)$", {}),
         ("POST", r"/api/v1/environmentshub/lookup$", {"data": {"id": "env1"}}), ("GET", r"/api/v1/environmentshub/", {"data": {"id": "env1"}}),
         ("POST", r"/api/v1/evaluations/ev1/samples$", {"status": "ok"}), ("POST", r"/api/v1/evaluations/ev1/finalize$", {"evaluation_id": "ev1", "status": "COMPLETED"}),
         ("GET", r"/api/v1/evaluations/ev1/samples$", {"samples": [], "total": 0}), ("GET", r"/api/v1/evaluations/ev1$", {"evaluation_id": "ev1", "name": "n"}),
@@ -152,6 +158,10 @@ class Recorder(BaseHTTPRequestHandler):
                 payload = json.loads(raw)
             elif "multipart" in ctype:
                 payload = {"multipart_bytes": "<file>", "has_hello": b"hello" in raw}
+            elif "octet-stream" in ctype:
+                import hashlib
+
+                payload = {"bytes": len(raw), "sha256": hashlib.sha256(raw).hexdigest()} if u.path.endswith("/wheel") else {"bytes": "<tarball>", "gzip": raw[:2] == b"\x1f\x8b"}
             else:
                 payload = raw.decode("utf-8", "replace") if raw else None
             with Recorder.lock:
