@@ -545,8 +545,11 @@ def run_eval_cmd(
     slugs: list[str] = []
     eval_ids: list[str] = []
     try:
+        # resolve EVERY environment before anything is submitted: an unknown slug in the last [[eval]] table must not leave the earlier
+        # groups running (the reference resolves in file order first, then submits group by group)
+        resolved_by_target = {id(t): resolve_hosted_environment(client, t["env_id"], t["env_dir_path"], env_path) for t in targets}
         for group in group_targets(targets):
-            resolved = [resolve_hosted_environment(client, t["env_id"], t["env_dir_path"], env_path) for t in group]
+            resolved = [resolved_by_target[id(t)] for t in group]
             t = group[0]
             cfg = HostedEvalConfig(environment_id=resolved[0][1], inference_model=t["model"], num_examples=t["num_examples"],
                                    rollouts_per_example=t["rollouts_per_example"], env_args=t.get("env_args"), name=t.get("eval_name"),

@@ -280,7 +280,7 @@ def test_compat_every_public_method_of_the_reference_exists_with_its_parameter_n
 
 def test_wire_requests_are_identical_to_the_reference(capsys):
     """tools/wire_diff.py: one script (reference import names) against both implementations and a recording server — the HTTP
-    requests (method, path, query, JSON body, auth header) and the outcomes of 88 SDK / API-client calls (sync and async), injected failures and
+    requests (method, path, query, JSON body, auth header) and the outcomes of 99 SDK / API-client / MCP-tool calls (sync and async), injected failures and
     their retries included, must not differ."""
     import sys
     from pathlib import Path
@@ -293,14 +293,14 @@ def test_wire_requests_are_identical_to_the_reference(capsys):
 
     rc = wire_diff.main()
     out = json.loads(capsys.readouterr().out)
-    assert rc == 0 and out["calls"] >= 88 and out["requests_reference"] == out["requests_ours"] >= 106
+    assert rc == 0 and out["calls"] >= 99 and out["requests_reference"] == out["requests_ours"] >= 117
     assert out["outcome_differences"] == [] and out["request_differences"] == []
-    assert sum(v == "ok" for v in out["outcomes"].values()) >= 79 and out["outcomes"]["gateway_408"] == "raised CommandTimeoutError"
+    assert sum(v == "ok" for v in out["outcomes"].values()) >= 90 and out["outcomes"]["gateway_408"] == "raised CommandTimeoutError"
 
 
 @pytest.mark.slow
 def test_cli_commands_behave_like_the_reference_cli(capsys):
-    """tools/cli_diff.py: ``prime …`` command lines (a quarter of the 99 in the quick pass) through both CLIs against the recording server — same exit codes, same HTTP
+    """tools/cli_diff.py: ``prime …`` command lines (a quarter of the 102 in the quick pass) through both CLIs against the recording server — same exit codes, same HTTP
     requests, and every key / value of the reference's ``--output json`` present in ours."""
     import sys
     from pathlib import Path
@@ -311,6 +311,6 @@ def test_cli_commands_behave_like_the_reference_cli(capsys):
     sys.path.insert(0, str(root))
     from tools import cli_diff
 
-    rc = cli_diff.main(stride=1 if os.environ.get("PRIME_B200_FULL_DIFF") else 4)  # the full 99-command run is profiles/cli_diff.json
+    rc = cli_diff.main(stride=1 if os.environ.get("PRIME_B200_FULL_DIFF") else 4)  # the full 102-command run is profiles/cli_diff.json
     out = json.loads(capsys.readouterr().out)
     assert rc == 0 and out["commands"] >= 20 and out["identical"] == out["commands"] and out["differences"] == [], [d["command"] for d in out["differences"]]

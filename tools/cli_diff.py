@@ -60,6 +60,10 @@ COMMANDS: list[list[str]] = [
     ["sandbox", "delete", "--all", "--yes"], ["sandbox", "delete", "--label", "a", "--yes"], ["secret", "create", "--name", "N", "--value", "v", "--description", "d"],
     # the packaging pipeline: build the wheel, resolve, wheel upload + finalize, source archive upload + finalize
     ["env", "push", "--path", "myenv", "--visibility", "PRIVATE"], ["env", "push", "--path", "myenv", "--auto-bump"],
+    # hosted evaluations: one environment from flags, sandbox access + secrets, a TOML file with two [[eval]] tables
+    ["eval", "run", "owner/env", "--hosted", "-m", "org/m", "-n", "5", "-r", "2", "--eval-name", "diff-eval", "--timeout-minutes", "30"],
+    ["eval", "run", "owner/env", "--hosted", "-m", "org/m", "--allow-sandbox-access", "--custom-secrets", '{"A": "1"}'],
+    ["eval", "run", "evals.toml", "--hosted"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
@@ -91,6 +95,7 @@ def prepare_files(home: Path) -> None:
     """Inputs of the file-based command lines, identical in both arms' working directories."""
     (home / "rl.toml").write_text(RL_TOML)
     (home / "a.txt").write_text("hello")
+    (home / "evals.toml").write_text('model = "org/m"\nnum_examples = 5\nrollouts_per_example = 2\n\n[[eval]]\nenv_id = "owner/env"\n\n[[eval]]\nenv_id = "owner/env2"\nnum_examples = 7\n')
     make_env_project(home / "myenv")
     run = home / "outputs" / "evals" / "gsm8k--org--m" / "run1"
     run.mkdir(parents=True)

@@ -5,7 +5,8 @@ sends. The request sequences (method, path, query, JSON body) and the outcome of
 
     python tools/wire_diff.py > profiles/wire_diff.json        # exit code 1 on any difference
 
-What it covers: 88 SDK / API-client calls — sync and async sandbox and evaluation clients, RL, deployments and tunnel clients; sandbox lifecycle, command execution, file transfer, ports, SSH sessions, bulk delete,
+What it covers: 99 SDK / API-client / MCP-tool calls — sync and async sandbox and evaluation clients, RL, deployments and tunnel clients, the
+nine MCP tools; sandbox lifecycle, command execution, file transfer, ports, SSH sessions, bulk delete,
 evaluation create / push / finalize / list, pods, disks, availability — and injected failures: 404 / 401 / 402 / 422, a flaky idempotent
 GET (retried), a 503 on a non-idempotent POST (not retried), gateway 502 ``sandbox_not_found``, 408, 409. A failure counts as the same
 when this repo raises the reference's exception class or a subclass of it. What it cannot cover: responses of the real service.
@@ -70,6 +71,8 @@ def respond(method: str, path: str, host: str):
         ("POST", r"/api/v1/environmentshub/env1/versions$", {"data": {"version_id": "v1", "upload_url": f"http://{host}/upload/source"}}),
         ("POST", r"/api/v1/environmentshub/env1/versions/v1/finalize$", {"data": {"success": True, "message": "ok"}}),
         ("PUT", r"/upload/(wheel|source)$", {}),
+        ("POST", r"/api/v1/hosted-evaluations$", {"evaluation_id": "ev1", "evaluation_ids": ["ev1"], "status": "PENDING"}),
+        ("GET", r"/api/v1/environmentshub/owner/env2?/@latest$", {"data": {"id": "env1", "name": "env", "owner": "owner"}}),
         ("POST", r"/api/v1/environmentshub/lookup$", {"data": {"id": "env1"}}), ("GET", r"/api/v1/environmentshub/", {"data": {"id": "env1"}}),
         ("POST", r"/api/v1/evaluations/ev1/samples$", {"status": "ok"}), ("POST", r"/api/v1/evaluations/ev1/finalize$", {"evaluation_id": "ev1", "status": "COMPLETED"}),
         ("GET", r"/api/v1/evaluations/ev1/samples$", {"samples": [], "total": 0}), ("GET", r"/api/v1/evaluations/ev1$", {"evaluation_id": "ev1", "name": "n"}),
@@ -97,6 +100,8 @@ def respond(method: str, path: str, host: str):
         ("POST", r"/api/v1/disks/?$", DISK), ("GET", r"/api/v1/disks/?$", {"total_count": 1, "offset": 0, "limit": 100, "data": [DISK]}),
         ("GET", r"/api/v1/availability/gpus$", {"items": [OFFER, {**OFFER, "cloudId": "c2", "gpuCount": 1, "dataCenter": "dc2", "prices": {"onDemand": 4.1, "currency": "USD"}}], "totalCount": 2}),
         ("GET", r"/api/v1/availability/multi-node$", {"items": [], "totalCount": 0}),
+        ("GET", r"/api/v1/ssh_keys/?$", {"data": [{"id": "k1", "name": "k", "publicKey": "ssh-ed25519 AAAA test", "isPrimary": True}], "total_count": 1}),
+        ("POST", r"/api/v1/ssh_keys/?$", {"id": "k2", "name": "k"}), ("DELETE", r"/api/v1/ssh_keys/k1$", {}),
         ("GET", r"/api/v1/availability/gpu-summary$", {"H100_80GB": {}}), ("GET", r"/api/v1/availability/disks$", {"items": []}),
         ("GET", r"/api/v1/availability/?", {"H100_80GB": []}),
     ]  # fmt: skip
@@ -332,6 +337,37 @@ async def async_part():
     await tc.close()
 
 asyncio.run(async_part())
+
+# MCP server: the nine tools, called as the plain async functions they are (FastMCP's decorator returns them unchanged)
+try:
+    import importlib
+    mcp_mod = importlib.import_module("prime_mcp.mcp")  # not `import prime_mcp.mcp as m`: the package re-exports the FastMCP object under that name
+except Exception as e:  # the optional `mcp` dependency is not installed
+    mcp_mod = None
+    results.append(["mcp_import", "raised", [type(e).__name__, str(e)[:80], [k.__name__ for k in type(e).__mro__]]])
+
+async def mcp_part():
+    async def tcall(label, coro_fn):
+        try:
+            r = await coro_fn()
+            results.append([label, "ok", json.loads(json.dumps(r, default=str))])
+        except Exception as e:
+            results.append([label, "raised", [type(e).__name__, str(e)[:160], [k.__name__ for k in type(e).__mro__]]])
+    m = mcp_mod
+    await tcall("mcp_gpu_availability", lambda: m.check_gpu_availability(gpu_type="B200_180GB", regions="united_states", gpu_count=8))
+    await tcall("mcp_cluster_availability", lambda: m.check_cluster_availability(gpu_count=16, gpu_type="B200_180GB"))
+    await tcall("mcp_list_pods", lambda: m.list_pods(offset=5, limit=10))
+    await tcall("mcp_pod_details", lambda: m.get_pod_details("p1"))
+    await tcall("mcp_pods_status", lambda: m.get_pods_status(["p1"]))
+    await tcall("mcp_pods_history", lambda: m.get_pods_history(limit=10, offset=0))
+    await tcall("mcp_create_pod", lambda: m.create_pod(cloud_id="c1", gpu_type="B200_180GB", provider_type="hyperstack", data_center_id="dc1", name="mcp-pod", gpu_count=8, disk_size=2000, image="ubuntu_22_cuda_12"))
+    await tcall("mcp_delete_pod", lambda: m.delete_pod("p1"))
+    await tcall("mcp_ssh_keys_list", lambda: m.manage_ssh_keys(action="list"))
+    await tcall("mcp_ssh_keys_add", lambda: m.manage_ssh_keys(action="add", key_name="k", public_key="ssh-ed25519 AAAA test"))
+    await tcall("mcp_ssh_keys_delete", lambda: m.manage_ssh_keys(action="delete", key_id="k1"))
+
+if mcp_mod is not None:
+    asyncio.run(mcp_part())
 print(json.dumps(results))
 '''
 
