@@ -64,6 +64,7 @@ COMMANDS: list[list[str]] = [
     ["eval", "run", "owner/env", "--hosted", "-m", "org/m", "-n", "5", "-r", "2", "--eval-name", "diff-eval", "--timeout-minutes", "30"],
     ["eval", "run", "owner/env", "--hosted", "-m", "org/m", "--allow-sandbox-access", "--custom-secrets", '{"A": "1"}'],
     ["eval", "run", "evals.toml", "--hosted"],
+    ["env", "init", "my-new-env"], ["env", "pull", "owner/env"], ["env", "uninstall", "myenv"], ["lab", "--help"], ["gepa", "--help"], ["upgrade", "--help"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
@@ -222,6 +223,10 @@ def main(stride: int = 1) -> int:
                 log = json.loads(urllib.request.urlopen(base + "/__log").read())
                 got[arm] = {"exit_code": rc, "requests": [{k: e[k] for k in ("method", "path", "query", "body")} for e in log], "json": parsed_json(out),
                             "stdout_tail": out.strip()[-300:], "stderr_tail": err.strip()[-300:]}  # fmt: skip
+            if args[:2] == ["env", "init"]:  # the scaffold each CLI wrote: same files, same contents
+                for arm, home in (("reference", h1), ("ours", h2)):
+                    root = Path(home) / "environments"
+                    got[arm]["json"] = {str(p.relative_to(home)): (p.read_text() if p.is_file() else None) for p in sorted(root.rglob("*"))} if root.exists() else None
             if args[:2] == ["rl", "init"]:  # the template each CLI wrote: compare what it configures, not its comments
                 got["reference"]["json"], got["ours"]["json"] = toml_of(Path(h1) / args[2]), toml_of(Path(h2) / args[2])
             a, b = got["reference"], got["ours"]
