@@ -79,7 +79,7 @@ class Config:
         self.environments_dir = self.config_dir / "environments"
         self.data: dict[str, Any] = ConfigModel(ssh_key_path=self.default_ssh_key_path()).model_dump()
         if writable:
-            self.config_dir.mkdir(exist_ok=True)
+            self.config_dir.mkdir(parents=True, exist_ok=True)
             self.environments_dir.mkdir(exist_ok=True)
             if not self.config_file.exists():
                 self._write(self.data)

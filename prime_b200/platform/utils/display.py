@@ -8,7 +8,7 @@ from typing import Any, Iterable, Sequence
 
 from rich.table import Table
 
-from .plain import get_console
+from .plain import get_console, is_plain_mode
 
 POD_STATUS_COLORS = {"ACTIVE": "green", "RUNNING": "green", "PROVISIONING": "yellow", "PENDING": "yellow",
                      "INSTALLING": "yellow", "STOPPED": "dim", "TERMINATED": "red", "ERROR": "red", "FAILED": "red"}  # fmt: skip
@@ -37,8 +37,9 @@ def build_table(title: str | None, columns: Sequence[str | tuple[str, str]], row
             t.add_column(c[0], style=c[1])
         else:
             t.add_column(c)
+    blank = "-" if is_plain_mode() else ""  # plain tables are split on whitespace by their readers: an empty cell would shift the columns
     for r in rows:
-        t.add_row(*["" if v is None else str(v) for v in r])
+        t.add_row(*[blank if v is None or v == "" else str(v) for v in r])
     return t
 
 

@@ -62,7 +62,9 @@ def _strip_table(t: Table) -> str:
     t = copy.copy(t)
     t.box, t.show_lines, t.border_style, t.header_style = None, False, "", ""
     t.row_styles, t.pad_edge, t.padding = [], False, (0, 1)
-    buf = Console(record=True, file=io.StringIO(), no_color=True, markup=False, highlight=False, emoji=False, width=200)
+    # markup=True: cells carry rich markup (status colours); it has to be PARSED here so that export_text() drops it — with markup off a
+    # cell came out as the literal "[green]ACTIVE[/]" in the one mode meant for scripts and agents (found by tools/cli_diff.py)
+    buf = Console(record=True, file=io.StringIO(), no_color=True, markup=True, highlight=False, emoji=False, width=200)
     buf.print(t)
     return buf.export_text().rstrip()
 

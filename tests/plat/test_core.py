@@ -314,3 +314,14 @@ def test_cli_commands_behave_like_the_reference_cli(capsys):
     rc = cli_diff.main(stride=1 if os.environ.get("PRIME_B200_FULL_DIFF") else 4)  # the full 108-command run is profiles/cli_diff.json
     out = json.loads(capsys.readouterr().out)
     assert rc == 0 and out["commands"] >= 20 and out["identical"] == out["commands"] and out["differences"] == [], [d["command"] for d in out["differences"]]
+
+
+def test_plain_mode_tables_carry_no_markup():
+    """`--plain` is the mode for scripts and agents: a coloured status cell must come out as the bare word."""
+    from prime_b200.platform.utils.display import build_table, colorize
+    from prime_b200.platform.utils.plain import to_plain
+
+    t = build_table("Pods", [("ID", "cyan"), "Status"], [["p1", colorize("ACTIVE", {"ACTIVE": "green"})], ["p2", colorize("ERROR", {"ERROR": "red"})]])
+    text = to_plain(t)
+    assert "[green]" not in text and "[/]" not in text and "ACTIVE" in text and "ERROR" in text
+    assert [ln.split() for ln in text.splitlines()[-2:]] == [["p1", "ACTIVE"], ["p2", "ERROR"]]
