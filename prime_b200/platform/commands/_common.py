@@ -51,6 +51,19 @@ def handle_errors(fn: Callable) -> Callable:
         except typer.Abort:  # a prompt hit EOF or was declined by click itself: click's own convention (and the reference's exit code)
             console.print("\n[dim]Aborted.[/dim]")
             raise typer.Exit(1)
+        except (typer.Exit, SystemExit):
+            raise
+        except Exception as e:  # noqa: BLE001
+            # an answer the models do not expect (missing fields, a string where an object should be): one clean line instead of a
+            # traceback; PRIME_DEBUG=1 re-raises for the full story
+            import os
+
+            import pydantic
+
+            if os.environ.get("PRIME_DEBUG") or not isinstance(e, (pydantic.ValidationError, AttributeError, KeyError, TypeError, IndexError)):
+                raise
+            what = f"{e.error_count()} field(s) missing or invalid" if isinstance(e, pydantic.ValidationError) else f"{type(e).__name__}: {e}"
+            raise fail(f"Unexpected response from the API ({what}). Set PRIME_DEBUG=1 for the traceback.")
 
     return wrapper
 

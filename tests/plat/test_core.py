@@ -325,3 +325,25 @@ def test_plain_mode_tables_carry_no_markup():
     text = to_plain(t)
     assert "[green]" not in text and "[/]" not in text and "ACTIVE" in text and "ERROR" in text
     assert [ln.split() for ln in text.splitlines()[-2:]] == [["p1", "ACTIVE"], ["p2", "ERROR"]]
+
+
+def test_unexpected_response_shapes_fail_with_one_line_not_a_traceback(isolated_home, monkeypatch):
+    """A control plane that answers `{}` (or a string where an object belongs) must not crash a command with a traceback."""
+    from typer.testing import CliRunner
+
+    from prime_b200.platform.commands import registry as reg_mod
+    from prime_b200.platform.main import app
+
+    class Empty:
+        def __init__(self, *a, **k):
+            self.config = type("C", (), {"team_id": None})()
+
+        def request(self, *a, **k):
+            return {}
+
+        get = post = request
+
+    monkeypatch.setenv("PRIME_API_KEY", "k")
+    monkeypatch.setattr(reg_mod, "api", lambda *a, **k: Empty(), raising=False)
+    r = CliRunner().invoke(app, ["registry", "check-image", "python:3.11-slim"])
+    assert r.exit_code == 1 and "Unexpected response from the API" in r.output and "Traceback" not in r.output
