@@ -132,7 +132,7 @@ def test_registry_list_and_check_image(fake_api):
                     ("POST", "/template/check-docker-image"): lambda params=None, json=None: {"accessible": json["image"].startswith("ghcr.io/ok"), "details": "pull ok" if json["image"].startswith("ghcr.io/ok") else "denied"}},
                    reg_mod)  # fmt: skip
     r = runner.invoke(app, ["registry", "list"])
-    assert r.exit_code == 0 and "ghcr.io" in r.output and "personal" in r.output
+    assert r.exit_code == 0 and "ghcr.io" in r.output and "user:u" in r.output  # scope: team id, else user:<id>, else personal
     assert runner.invoke(app, ["registry", "check-image", "ghcr.io/ok/app:1"]).exit_code == 0
     r = runner.invoke(app, ["registry", "check-image", "ghcr.io/private/app:1", "--registry-credentials-id", "c1"])
     assert r.exit_code == 1 and "denied" in r.output

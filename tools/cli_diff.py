@@ -65,6 +65,11 @@ COMMANDS: list[list[str]] = [
     ["eval", "run", "owner/env", "--hosted", "-m", "org/m", "--allow-sandbox-access", "--custom-secrets", '{"A": "1"}'],
     ["eval", "run", "evals.toml", "--hosted"],
     ["env", "init", "my-new-env"], ["env", "pull", "owner/env"], ["env", "uninstall", "myenv"], ["lab", "--help"], ["gepa", "--help"], ["upgrade", "--help"],
+    # read commands against realistic payloads, JSON mode
+    ["env", "list", "--output", "json"], ["env", "list", "--output", "json", "--search", "ma", "--page", "2", "-n", "20"], ["env", "status", "owner/env", "--output", "json"],
+    ["env", "version", "list", "owner/env", "--output", "json"], ["env", "action", "list", "owner/env", "--output", "json"], ["env", "action", "logs", "owner/env", "A1"],
+    ["secret", "list", "-o", "json"], ["secret", "get", "sec1", "-o", "json"], ["teams", "members", "--team-id", "t1", "-o", "json"], ["teams", "list", "-o", "json"],
+    ["registry", "list", "-o", "json"], ["registry", "check-image", "ghcr.io/ok/img:1"], ["inference", "models", "-o", "json"], ["whoami"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],

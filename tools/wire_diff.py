@@ -71,6 +71,17 @@ def respond(method: str, path: str, host: str):
         ("POST", r"/api/v1/environmentshub/env1/versions$", {"data": {"version_id": "v1", "upload_url": f"http://{host}/upload/source"}}),
         ("POST", r"/api/v1/environmentshub/env1/versions/v1/finalize$", {"data": {"success": True, "message": "ok"}}),
         ("PUT", r"/upload/(wheel|source)$", {}),
+        ("GET", r"/api/v1/environmentshub/$", {"data": [{"owner": {"name": "owner"}, "name": "env", "description": "sums", "visibility": "PUBLIC", "latest_version": "0.2.0", "stars": 3, "updated_at": "2026-01-02T03:04:05Z", "latest_ci_status": "SUCCESS", "tags": ["t"]}], "total_count": 41}),
+        ("GET", r"/api/v1/environmentshub/owner/env/status$", {"data": {"name": "env", "visibility": "PUBLIC", "latest_version": {"semantic_version": "0.2.0", "content_hash": "abcdef0123456789", "created_at": "2026-01-02T03:04:05Z"}, "action": {"status": "FAILED", "job_id": "j1"}}}),
+        ("GET", r"/api/v1/environmentshub/owner/env/versions$", {"data": {"versions": [{"version": "0.2.0", "created_at": "2026-01-02T03:04:05Z", "sha256": "a" * 64, "size": 2}, {"version": "0.1.0", "created_at": "2025-01-02", "sha256": "b" * 64, "size": 1}]}}),
+        ("GET", r"/api/v1/environmentshub/owner/env/actions$", {"data": {"total": 30, "actions": [{"id": "A1", "job_type": "integration", "status": "RUNNING", "version": {"content_hash": "deadbeefcafe"}, "trigger": "push", "created_at": "2026-01-02T03:04:05Z"}]}}),
+        ("GET", r"/api/v1/environmentshub/owner/env/actions/A1/logs$", {"data": {"logs": "line one\nline two"}}),
+        ("GET", r"/api/v1/secrets/sec1$", {"data": {"id": "sec1", "name": "HF_TOKEN", "description": "hub", "isFile": False, "createdAt": "2026-01-02T03:04:05Z", "updatedAt": "2026-01-02T03:04:05Z"}}),
+        ("GET", r"/api/v1/secrets/$", {"data": [{"id": "sec1", "name": "HF_TOKEN", "description": "hub", "isFile": False, "createdAt": "2026-01-02T03:04:05Z", "updatedAt": "2026-01-02T03:04:05Z"}]}),
+        ("GET", r"/api/v1/teams/t1/members$", {"data": [{"userId": "u1", "userName": "Ada", "userEmail": "a@b.c", "role": "admin", "joinedAt": "2026-01-02T03:04:05Z"}]}),
+        ("GET", r"/api/v1/template/registry-credentials$", {"credentials": [{"id": "c1", "name": "ghcr", "server": "ghcr.io", "createdAt": "2026-01-02T03:04:05Z", "updatedAt": "2026-01-02T03:04:05Z", "userId": "u", "teamId": None}]}),
+        ("POST", r"/api/v1/template/check-docker-image$", {"accessible": True, "details": "pull ok"}),
+        ("GET", r"/api/v1/models$", {"object": "list", "data": [{"id": "meta/llama", "created": 1767322245, "pricing": {"input_usd_per_mtok": 0.2, "output_usd_per_mtok": 0.6}}, {"id": "q/qwen"}]}),
         ("POST", r"/api/v1/hosted-evaluations$", {"evaluation_id": "ev1", "evaluation_ids": ["ev1"], "status": "PENDING"}),
         ("GET", r"/api/v1/environmentshub/owner/env2?/@latest$", {"data": {"id": "env1", "name": "env", "owner": "owner"}}),
         ("POST", r"/api/v1/environmentshub/lookup$", {"data": {"id": "env1"}}), ("GET", r"/api/v1/environmentshub/", {"data": {"id": "env1"}}),
