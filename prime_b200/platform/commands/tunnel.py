@@ -165,8 +165,7 @@ def stop_tunnel(
         return
 
     async def delete(c: TunnelClient):
-        if len(ids) == 1:
-            return ([ids[0]], [], []) if await c.delete_tunnel(ids[0]) else ([], [{"tunnel_id": ids[0]}], [])
+        # one id or many: the bulk endpoint (`DELETE /tunnel` with the id list), as the reference's `tunnel stop` does
         r = await c.bulk_delete_tunnels(ids)
         return r.get("succeeded", []), r.get("not_found", []), r.get("failed", [])
 

@@ -70,6 +70,9 @@ COMMANDS: list[list[str]] = [
     ["env", "version", "list", "owner/env", "--output", "json"], ["env", "action", "list", "owner/env", "--output", "json"], ["env", "action", "logs", "owner/env", "A1"],
     ["secret", "list", "-o", "json"], ["secret", "get", "sec1", "-o", "json"], ["teams", "members", "--team-id", "t1", "-o", "json"], ["teams", "list", "-o", "json"],
     ["registry", "list", "-o", "json"], ["registry", "check-image", "ghcr.io/ok/img:1"], ["inference", "models", "-o", "json"], ["whoami"],
+    ["images", "push", "app:v1", "--context", "ctx"], ["images", "push", "app:v1", "--context", "ctx", "--dockerfile", "ctx/Dockerfile", "--platform", "linux/amd64"],
+    ["sandbox", "run", "s1", "--working-dir", "/w", "--env", "A=1", "--timeout", "7", "echo hi"], ["sandbox", "run", "s1", "sleep 1"],
+    ["tunnel", "stop", "t1", "--yes"], ["tunnel", "stop", "t1,t2", "--yes"], ["tunnel", "stop", "--all", "--yes"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
@@ -101,6 +104,9 @@ def prepare_files(home: Path) -> None:
     """Inputs of the file-based command lines, identical in both arms' working directories."""
     (home / "rl.toml").write_text(RL_TOML)
     (home / "a.txt").write_text("hello")
+    (home / "ctx").mkdir()
+    (home / "ctx" / "Dockerfile").write_text("FROM python:3.11-slim\nCOPY app.py /app.py\n")
+    (home / "ctx" / "app.py").write_text("print(1)\n")
     (home / "evals.toml").write_text('model = "org/m"\nnum_examples = 5\nrollouts_per_example = 2\n\n[[eval]]\nenv_id = "owner/env"\n\n[[eval]]\nenv_id = "owner/env2"\nnum_examples = 7\n')
     make_env_project(home / "myenv")
     run = home / "outputs" / "evals" / "gsm8k--org--m" / "run1"
