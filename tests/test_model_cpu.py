@@ -127,3 +127,41 @@ def test_hf_config_refuses_what_it_cannot_represent():
         hf.args_from_hf_config({**base, "model_type": "mistral", "architectures": ["MistralForCausalLM"]})
     with pytest.raises(ValueError, match="bias"):
         hf.args_from_hf_config({**base, "attention_bias": True})
+
+
+def test_b0_comparison_model_is_the_same_function_as_ours():
+    """The stock-PyTorch arm of the benchmark (baseline/torch_b0.Llama: nn.Linear, SDPA, complex-multiply RoPE, nn.RMSNorm) must be
+    the SAME network as the engine's, or the reported ratio compares different jobs. Checked here on the CPU in fp32 (the GPU suite
+    repeats it at the 1B shape against the native kernels): identical logits, loss and parameter gradients for the same weights."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    from baseline.torch_b0 import Llama as B0Llama
+
+    ours = build_model("150M", dtype=torch.float32, seed=3, n_layers=2, vocab_size=4096, max_seq_len=64)
+    a = ours.args
+    ref = B0Llama(a.dim, a.n_layers, a.n_heads, a.vocab_size, max_seq=64).float()
+    with torch.no_grad():
+        ref.tok_embeddings.weight.copy_(ours.tok_embeddings.weight)
+        ref.norm.weight.copy_(ours.norm.weight)
+        ref.output.weight.copy_(ours.output)
+        for x, y in zip(ours.layers, ref.layers):
+            y.wqkv.weight.copy_(x.attention.wqkv)
+            y.wo.weight.copy_(x.attention.wo)
+            y.w13.weight.copy_(x.feed_forward.w13)
+            y.w2.weight.copy_(x.feed_forward.w2)
+            y.attention_norm.weight.copy_(x.attention_norm.weight)
+            y.ffn_norm.weight.copy_(x.ffn_norm.weight)
+    assert sum(p.numel() for p in ref.parameters()) == ours.num_params()
+    tok = torch.randint(0, a.vocab_size, (2, 48))
+    tgt = torch.randint(0, a.vocab_size, (2, 48))
+    lo, lr = ours(tok), ref(tok)
+    torch.testing.assert_close(lo, lr, rtol=2e-4, atol=2e-4)
+    torch.nn.functional.cross_entropy(lo.reshape(-1, a.vocab_size), tgt.reshape(-1)).backward()
+    torch.nn.functional.cross_entropy(lr.reshape(-1, a.vocab_size), tgt.reshape(-1)).backward()
+    for x, y in zip(ours.layers, ref.layers):
+        torch.testing.assert_close(x.attention.wqkv.grad, y.wqkv.weight.grad, rtol=2e-3, atol=2e-5)
+        torch.testing.assert_close(x.feed_forward.w2.grad, y.w2.weight.grad, rtol=2e-3, atol=2e-5)
+    torch.testing.assert_close(ours.tok_embeddings.weight.grad, ref.tok_embeddings.weight.grad, rtol=2e-3, atol=2e-5)
+    assert abs(ours.flops_per_token(48) - ref.flops_per_token(48)) < 1e-6 * ref.flops_per_token(48)  # the MFU denominators agree too
