@@ -250,7 +250,28 @@ def main(stride: int = 1) -> int:
             rows.append(row)
             if not (row["same_exit_code"] and row["same_requests"] and row["same_json"] in (True, None)):
                 diffs.append({"command": row["command"], "reference": a, "ours": b})
-    print(json.dumps({"commands": len(rows), "read_only_requests_saved": sum(r["reads_saved"] for r in rows), "identical": sum(1 for r in rows if r["same_exit_code"] and r["same_requests"] and r["same_json"] in (True, None)),
+        # what the commands left on disk: users who switch keep their ~/.prime
+        state = {}
+        for arm, home in (("reference", h1), ("ours", h2)):
+            d = Path(home) / ".prime"
+            files = {}
+            for f in sorted(d.rglob("*.json")) if d.exists() else []:
+                try:
+                    files[str(f.relative_to(d))] = json.loads(f.read_text())
+                except (OSError, ValueError):
+                    files[str(f.relative_to(d))] = "<unreadable>"
+            state[arm] = files
+
+        def stable(v):  # expiry stamps of cached gateway tokens differ run to run
+            if isinstance(v, dict):
+                return {k: stable(x) for k, x in v.items() if k not in ("cached_at", "expires_at", "last_check", "timestamp")}
+            return v
+
+        on_disk_same = stride > 1 or covers(stable(state["ours"]), stable(state["reference"]))
+        if not on_disk_same:
+            diffs.append({"command": "<files under ~/.prime after the run>", "reference": {"exit_code": 0, "requests": [], "json": state["reference"], "stdout_tail": "", "stderr_tail": ""},
+                          "ours": {"exit_code": 0, "requests": [], "json": state["ours"], "stdout_tail": "", "stderr_tail": ""}})  # fmt: skip
+    print(json.dumps({"commands": len(rows), "files_under_dot_prime": sorted(state["ours"]), "files_under_dot_prime_identical": on_disk_same, "read_only_requests_saved": sum(r["reads_saved"] for r in rows), "identical": sum(1 for r in rows if r["same_exit_code"] and r["same_requests"] and r["same_json"] in (True, None)),
                       "rows": rows, "differences": diffs}, indent=1))  # fmt: skip
     srv.shutdown()
     return 1 if diffs else 0
