@@ -54,7 +54,7 @@ def reference_arm() -> None:
     print(json.dumps({"impl": "reference", "unavailable": why}))
 
 
-from prime_b200.utils.clocks import ClockSampler  # noqa: E402
+from prime_b200.utils.clocks import ClockSampler, NvlinkCounters  # noqa: E402
 
 MODEL_DESC = {"1B": "Llama-1B (dim 2048, 18 layers, 16 heads, vocab 32000)", "7B": "Llama-7B (dim 4096, 32 layers, 32 heads, vocab 32000)",
               "150M": "Llama-150M (dim 1024, 12 layers, 16 heads, vocab 32000)"}  # fmt: skip
@@ -204,9 +204,20 @@ def main() -> None:
         trainer.engine.trace = StepTrace(dev, max_steps=K)
 
     sampler = ClockSampler(torch.cuda.current_device())
+    nvl = nvl0 = nvl1 = None
     if rank == 0:
         sampler.start()
+        try:  # raw NVLink byte counters around the device-timed region (evidence for the multi-GPU lines; never fatal)
+            nvl = NvlinkCounters(torch.cuda.current_device())
+            nvl0 = nvl.read()
+        except Exception:  # noqa: BLE001
+            nvl = None
     dev_ms, _, launches = run_region(K, read_loss=False)
+    if nvl is not None:
+        try:
+            nvl1 = nvl.read()
+        except Exception:  # noqa: BLE001
+            nvl1 = None
     trace = trainer.engine.trace.summary() if trainer.engine.trace is not None else None
     trainer.engine.trace = None
     e2e_ms, e2e_host_s, _ = run_region(K, read_loss=True)
@@ -303,6 +314,7 @@ def main() -> None:
                 "ms_per_step": round(max(e2e_host_s * 1e3, e2e_ms) / K, 3),
             },
             "gpu_launches": launches,
+            "nvlink": NvlinkCounters.delta(nvl0, nvl1, K),
             "losses_e2e_region": losses,
             "outer_allreduce": outer_info,
             "outer_allreduce_GBps": outer_info["GBps"] if outer_info else None,

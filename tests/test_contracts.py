@@ -46,3 +46,49 @@ def test_throughput_meter_and_sinks(tmp_path):
     s.close()
     assert [json.loads(x)["step"] for x in (tmp_path / "a" / "m.jsonl").read_text().splitlines()] == [1, 2]
     JsonlSink(None).write({"ignored": True})  # disabled sink is a no-op
+
+
+def test_nvlink_counters_decode_and_delta():
+    """NvlinkCounters against a fake NVML: aggregate scope, per-link fallback, KiB → bytes, per-step delta, graceful None."""
+    from types import SimpleNamespace
+
+    from prime_b200.utils.clocks import NvlinkCounters
+
+    class FakeNvml:
+        NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX = 138, 139
+
+        def __init__(self, aggregate=True, links=4):
+            self.aggregate, self.links, self.kib = aggregate, links, {l: [1000 * (l + 1), 500 * (l + 1)] for l in range(links)}
+
+        def nvmlDeviceGetHandleByIndex(self, i):
+            return "h"
+
+        def nvmlDeviceGetFieldValues(self, h, ids):
+            out = []
+            for fid, scope in ids:
+                col = 0 if fid == 138 else 1
+                if scope == 0xFFFFFFFF:
+                    ok, val = self.aggregate, sum(v[col] for v in self.kib.values())
+                else:
+                    ok, val = scope < self.links, self.kib.get(scope, [0, 0])[col]
+                out.append(SimpleNamespace(nvmlReturn=0 if ok else 3, valueType=3, value=SimpleNamespace(ullVal=val)))
+            return out
+
+    for aggregate in (True, False):
+        nv = FakeNvml(aggregate)
+        c = NvlinkCounters(0, nvml=nv)
+        a = c.read()
+        assert a["tx_bytes"] == (1000 + 2000 + 3000 + 4000) * 1024 and a["rx_bytes"] == 5000 * 1024 and len(a["per_link"]) == 4
+        for l in nv.kib:
+            nv.kib[l][0] += 10 * 1024  # 10 MiB more on every link, transmit side
+        d = NvlinkCounters.delta(a, c.read(), steps=4)
+        assert d["tx_bytes_per_step"] == 4 * 10 * 1024 * 1024 // 4 and d["rx_bytes_per_step"] == 0 and d["links_active"] == 4
+        assert d["per_link_bytes_per_step"][0] == [10 * 1024 * 1024 // 4, 0]
+    assert NvlinkCounters(0, nvml=FakeNvml(aggregate=False, links=0)).read() is None  # no NVLink at all
+    assert NvlinkCounters.delta(None, {"tx_bytes": 1, "rx_bytes": 1, "per_link": []}, 3) is None
+
+    class Broken:
+        def nvmlDeviceGetHandleByIndex(self, i):
+            raise RuntimeError("no nvml")
+
+    assert NvlinkCounters(0, nvml=Broken()).read() is None
