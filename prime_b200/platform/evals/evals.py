@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import asyncio
 import json
+import threading
 import time
 import warnings
 from concurrent.futures import ThreadPoolExecutor, as_completed
@@ -175,13 +176,18 @@ class _Common:
 class EvalsClient(_Common):
     _sleep = staticmethod(time.sleep)
     _http: httpx.Client | None = None
+    _http_lock = threading.Lock()
 
     def _post(self, url: str, **kw: Any) -> httpx.Response:
         """Sample uploads share one pooled client (``httpx.post`` — what the reference calls — builds a client, i.e. a TLS context
-        and a connection, per batch). Injectable for tests."""
-        if self._http is None or self._http.is_closed:
-            self._http = httpx.Client(timeout=30.0)
-        return self._http.post(url, **kw)
+        and a connection, per batch). Injectable for tests. Built once even when the four upload threads arrive together."""
+        http = self._http
+        if http is None or http.is_closed:
+            with self._http_lock:
+                http = self._http
+                if http is None or http.is_closed:
+                    http = self._http = httpx.Client(timeout=30.0)
+        return http.post(url, **kw)
 
     def close(self) -> None:
         if self._http is not None and not self._http.is_closed:
