@@ -301,7 +301,8 @@ class CheckpointManager:
         meta = json.loads((Path(path) / "meta.json").read_text())
         if meta.get("world_size") != self.world:
             raise ValueError(f"checkpoint {path} was written by {meta.get('world_size')} ranks; this job has {self.world} "
-                             "(resharding a checkpoint is not supported — restart with the same mesh)")  # fmt: skip
+                             "— restart with the same mesh, or rewrite it offline: python -m prime_b200.checkpoint reshard --src <step dir> --out <new step dir> "
+                             "--model <size> --fsdp-size <F>")  # fmt: skip
         tensors, extra = read_shard(Path(path) / f"rank_{self.rank:05d}.pbck", self.device)
         return tensors, extra, meta
 
@@ -351,11 +352,65 @@ def restore_trainer(trainer, tensors: dict[str, torch.Tensor], extra: dict[str, 
         if "rng_cuda" in tensors and eng.device.type == "cuda":
             torch.cuda.set_rng_state(tensors["rng_cuda"].cpu(), eng.device)
     trainer.step_count = int(extra["trainer_step"])
-    if not skip_dataloader:
+    if not skip_dataloader and extra.get("data") is not None:  # None: a rank added by an offline reshard starts its own stream
         trainer.loader.load_state_dict(extra["data"])
 
 
-# ------------------------------------------------------------------------------------------------- offline assembly
+# ------------------------------------------------------------------------------------------------- offline assembly / resharding
+SHARDED_KINDS = ("master", "exp_avg", "exp_avg_sq", "theta0", "momentum")  # per-rank 1/F slices of parameter-shaped state
+
+
+def _layout_plan(model, fsdp_size: int, shard_params: bool):
+    """The engine's own bucket planner without buffers, hooks or a process group: one source of truth for who holds what."""
+    from .parallel.fsdp import ShardedEngine
+
+    plan = ShardedEngine.__new__(ShardedEngine)
+    plan.model, plan.F, plan.shard_params = model, int(fsdp_size), bool(shard_params)
+    plan._build_buckets()
+    return plan
+
+
+def _plan_layout(plan) -> list[list]:
+    return [[b.name, b.start, b.size, b.shard_start, b.shard_size] for b in plan.buckets]
+
+
+def _gather_params(plan, shards: dict[int, torch.Tensor]) -> dict[str, torch.Tensor]:
+    """Per-rank flat shards of one kind of state → {qualified parameter name: full tensor in the parameter's shape}."""
+    F, out = plan.F, {}
+    for b in plan.buckets:
+        if b.kind == "rows":
+            for (qn, p, _), (soff, piece) in zip(b.params, b.pieces):
+                rows, cols = p.shape
+                out[qn] = torch.cat([shards[r][b.shard_start + soff : b.shard_start + soff + piece].view(rows // F, cols) for r in range(F)], dim=0)
+        else:
+            full = torch.cat([shards[r][b.shard_start : b.shard_start + b.shard_size] for r in range(F)])
+            for qn, p, off in b.params:
+                out[qn] = full[off : off + p.numel()].view(p.shape)
+    return out
+
+
+def _scatter_params(plan, full: dict[str, torch.Tensor], rank: int, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Inverse of :func:`_gather_params` for one rank of the target layout (padding stays zero)."""
+    F = plan.F
+    shard = torch.zeros(plan.shard_total, dtype=dtype)
+    for b in plan.buckets:
+        if b.kind == "rows":
+            for (qn, p, _), (soff, piece) in zip(b.params, b.pieces):
+                rpr = p.shape[0] // F
+                shard[b.shard_start + soff : b.shard_start + soff + piece] = full[qn][rank * rpr : (rank + 1) * rpr].reshape(-1)
+        else:
+            flat = torch.zeros(b.size, dtype=dtype)
+            for qn, p, off in b.params:
+                flat[off : off + p.numel()] = full[qn].reshape(-1)
+            shard[b.shard_start : b.shard_start + b.shard_size] = flat[rank * b.shard_size : (rank + 1) * b.shard_size]
+    return shard
+
+
+def _read_all_ranks(d: Path) -> tuple[dict, list[tuple[dict[str, torch.Tensor], dict[str, Any]]]]:
+    meta = json.loads((d / "meta.json").read_text())
+    return meta, [read_shard(d / f"rank_{r:05d}.pbck", "cpu") for r in range(int(meta["world_size"]))]
+
+
 def assemble_full_model(path: str | Path, name_model: str, type_model: str = "llama2", *, dtype: torch.dtype = torch.float32, **overrides):
     """Rebuild the complete model on the CPU from a published checkpoint step directory: every ``rank_*.pbck`` holds its rank's
     1/F slice of the fp32 master weights, cut either as contiguous bucket slices (replicated-parameter mode) or as one row block
@@ -363,15 +418,13 @@ def assemble_full_model(path: str | Path, name_model: str, type_model: str = "ll
     Used by ``python -m prime_b200.models.hf export`` and ``examples/inspect_checkpoint.py``; DiLoCo workers are identical after
     an outer step, the first worker's shards are taken."""
     from .models.llama import build_model
-    from .parallel.fsdp import ShardedEngine
 
     d = Path(path)
     meta = json.loads((d / "meta.json").read_text())
     shards: dict[int, torch.Tensor] = {}
     extra0: dict[str, Any] | None = None
     for r in range(int(meta["world_size"])):
-        f = d / f"rank_{r:05d}.pbck"
-        tensors, extra = read_shard(f, "cpu")
+        tensors, extra = read_shard(d / f"rank_{r:05d}.pbck", "cpu")
         fr = int(extra["fsdp_rank"])
         if fr not in shards:
             shards[fr] = tensors["master"].float()
@@ -383,21 +436,95 @@ def assemble_full_model(path: str | Path, name_model: str, type_model: str = "ll
     if sorted(shards) != list(range(F)):
         raise ValueError(f"checkpoint {d} is incomplete: have fsdp ranks {sorted(shards)} of {F}")
     model = build_model(name_model, type_model, dtype=dtype, seed=None, **overrides)
-    plan = ShardedEngine.__new__(ShardedEngine)  # layout planner only: no buffers, no hooks, no process group
-    plan.model, plan.F, plan.shard_params = model, F, bool(extra0.get("shard_params", False))
-    plan._build_buckets()
-    layout = [[b.name, b.start, b.size, b.shard_start, b.shard_size] for b in plan.buckets]
-    if layout != [list(x) for x in extra0["layout"]]:
+    plan = _layout_plan(model, F, bool(extra0.get("shard_params", False)))
+    if _plan_layout(plan) != [list(x) for x in extra0["layout"]]:
         raise ValueError(f"checkpoint {d} was written for a different model than {type_model}/{name_model} (bucket layout differs)")
+    full = _gather_params(plan, shards)
     with torch.no_grad():
-        for b in plan.buckets:
-            if b.kind == "rows":
-                for (_, p, _), (soff, piece) in zip(b.params, b.pieces):
-                    rows, cols = p.shape
-                    blocks = [shards[r][b.shard_start + soff : b.shard_start + soff + piece].view(rows // F, cols) for r in range(F)]
-                    p.copy_(torch.cat(blocks, dim=0))
-            else:
-                full = torch.cat([shards[r][b.shard_start : b.shard_start + b.shard_size] for r in range(F)])
-                for _, p, off in b.params:
-                    p.copy_(full[off : off + p.numel()].view(p.shape))
+        for qn, p in model.named_parameters():
+            p.copy_(full[qn])
     return model
+
+
+def reshard_checkpoint(src: str | Path, dst: str | Path, name_model: str, type_model: str = "llama2", *, fsdp_size: int,
+                       shard_params: bool | None = None, **overrides) -> dict[str, Any]:  # fmt: skip
+    """Rewrite a published checkpoint for a different FSDP group size and / or parameter mode, offline on the CPU.
+
+    Every worker's optimizer state (fp32 masters, AdamW moments, and the outer θ₀ / momentum) is gathered into whole parameters with
+    the source layout and cut again with the target layout — replicated ↔ ZeRO-3 and any F that divides the weights' row counts.
+    The number of DiLoCo workers is kept (each worker keeps ITS moments). Counters, LR position and RNG state are carried over from
+    the worker's first rank; the data position of every new rank is the furthest any old rank of that worker had read (no sample is
+    repeated; with a different rank count the streams are re-striped, so bit-exact continuation of the loss curve is not expected
+    — the optimizer state is).  → {"world_size", "fsdp_size", "workers", "bytes"}; resume with ``--mesh.fsdp_size <new F>``."""
+    from .models.llama import build_model
+
+    src, dst = Path(src), Path(dst)
+    meta, ranks = _read_all_ranks(src)
+    F0 = int(ranks[0][1]["fsdp_size"])
+    world0 = len(ranks)
+    if world0 % F0:
+        raise ValueError(f"{src}: {world0} rank files do not divide into groups of fsdp_size={F0}")
+    workers = world0 // F0
+    sp0 = bool(ranks[0][1].get("shard_params", False))
+    sp1 = (sp0 if shard_params is None else bool(shard_params)) and int(fsdp_size) > 1  # a single rank holds whole parameters
+    model = build_model(name_model, type_model, dtype=torch.float32, seed=None, **overrides)
+    plan0, plan1 = _layout_plan(model, F0, sp0), _layout_plan(model, fsdp_size, sp1)
+    if _plan_layout(plan0) != [list(x) for x in ranks[0][1]["layout"]]:
+        raise ValueError(f"checkpoint {src} was written for a different model than {type_model}/{name_model} (bucket layout differs)")
+    tmp = dst.parent / f".tmp-{dst.name}"
+    if tmp.exists():
+        shutil.rmtree(tmp)
+    tmp.mkdir(parents=True)
+    written = 0
+    for w in range(workers):
+        group = ranks[w * F0 : (w + 1) * F0]
+        if sorted(int(e["fsdp_rank"]) for _, e in group) != list(range(F0)):
+            raise ValueError(f"{src}: ranks {w * F0}..{(w + 1) * F0 - 1} are not one FSDP group (rank = worker·F + fsdp_rank expected)")
+        by_rank = {int(e["fsdp_rank"]): t for t, e in group}
+        first_t, first_e = group[0]
+        kinds = [k for k in SHARDED_KINDS if k in first_t]
+        whole = {k: _gather_params(plan0, {r: by_rank[r][k].float() for r in range(F0)}) for k in kinds}
+        data_states = [e.get("data") for _, e in group]
+        furthest = max((d.get("cursor", d.get("n_served", 0)) for d in data_states if isinstance(d, dict)), default=None)
+        for r in range(fsdp_size):
+            tensors = {k: _scatter_params(plan1, whole[k], r) for k in kinds}
+            for k, v in first_t.items():  # RNG state and anything else that is not parameter-shaped: the worker's first rank's
+                if k not in tensors:
+                    tensors[k] = v
+            # data position: an old rank keeps its own stream state; a rank that did not exist before starts a fresh stream (synthetic
+            # data: seeded by its rank) or, for a corpus, at the furthest position any old rank of the worker had reached
+            data = data_states[r] if r < F0 else None
+            if isinstance(data_states[0], dict) and "cursor" in data_states[0]:
+                data = {**data_states[0], "cursor": furthest}
+            extra = {**first_e, "fsdp_size": int(fsdp_size), "fsdp_rank": r, "layout": _plan_layout(plan1), "shard_params": sp1, "data": data,
+                     "resharded_from": {"fsdp_size": F0, "shard_params": sp0, "path": str(src)}}  # fmt: skip
+            written += write_shard(tmp / f"rank_{w * fsdp_size + r:05d}.pbck", tensors, extra)
+    new_meta = {**meta, "world_size": workers * fsdp_size, "mesh": f"dl{workers}xfsdp{fsdp_size}",
+                "resharded_from": {"world_size": world0, "mesh": meta.get("mesh")}}  # fmt: skip
+    (tmp / "meta.json").write_text(json.dumps(new_meta, indent=1))
+    if dst.exists():
+        shutil.rmtree(dst)
+    os.replace(tmp, dst)
+    (dst.parent / "latest").write_text(dst.name)
+    return {"world_size": workers * fsdp_size, "fsdp_size": int(fsdp_size), "workers": workers, "bytes": written, "shard_params": sp1}
+
+
+def main(argv: list[str] | None = None) -> None:
+    import argparse
+
+    ap = argparse.ArgumentParser(prog="python -m prime_b200.checkpoint", description="Offline checkpoint tools")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    r = sub.add_parser("reshard", help="rewrite a checkpoint for another fsdp_size / parameter mode")
+    r.add_argument("--src", required=True, help="published step directory (…/step_000500)")
+    r.add_argument("--out", required=True, help="new step directory (its parent becomes a ckpt.path to resume from)")
+    r.add_argument("--model", required=True)
+    r.add_argument("--type-model", default="llama2", choices=["llama2", "llama3"])
+    r.add_argument("--fsdp-size", type=int, required=True)
+    r.add_argument("--shard-params", choices=["keep", "true", "false"], default="keep", help="ZeRO-3 row shards (train.reshard_after_forward) in the output")
+    a = ap.parse_args(argv)
+    sp = None if a.shard_params == "keep" else a.shard_params == "true"
+    print(json.dumps(reshard_checkpoint(a.src, a.out, a.model, a.type_model, fsdp_size=a.fsdp_size, shard_params=sp)))
+
+
+if __name__ == "__main__":
+    main()
