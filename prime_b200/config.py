@@ -68,6 +68,9 @@ class TrainConfig(_Section):
     fp8: bool = False
     fused_comm: bool = True  # P2P fused reduce-scatter/AdamW/all-gather kernels
     memory_profile: bool = False
+    # start from existing weights instead of the random init: a Hugging Face Llama directory (config.json + safetensors) or a .pt
+    # state dict in reference naming (models/hf.py, models/llama.py); every rank loads the same file, then training proceeds as usual
+    init_weights: str | None = None
 
 
 class CkptConfig(_Section):

@@ -51,6 +51,8 @@ class Trainer:
         overrides.setdefault("max_seq_len", max(cfg.data.seq_length, 128))
         # identical init on every rank (same seed) — workers start from the same θ₀
         self.model: Transformer = build_model(cfg.name_model, cfg.type_model, device=self.device, dtype=dtype, seed=cfg.seed, **overrides)
+        if cfg.train.init_weights:
+            load_initial_weights(self.model, cfg.train.init_weights)  # before the engine takes the parameters into its buffers
         self.model.attn_impl = cfg.train.attn_impl
         self.model.ac_ckpt = cfg.train.ac_ckpt
         self.model.set_fp8(cfg.train.fp8)  # MXFP8 forward / dgrad GEMMs (opt-in; the headline benchmark is bf16)
@@ -227,6 +229,33 @@ class Trainer:
             torch.cuda.synchronize()
             self.heap.close()
             self.heap = None
+
+
+def load_initial_weights(model: Transformer, source: str) -> None:
+    """``train.init_weights``: copy pretrained weights into ``model`` (any device / dtype). A directory is read as a Hugging Face
+    Llama checkpoint (RoPE row permutation and fused QKV / gate-up handled by ``models/hf.py``), a file as a state dict in reference
+    naming. The architecture must be the one the config names — a mismatch is an error, not a partial load."""
+    from pathlib import Path
+
+    src = Path(source)
+    if src.is_dir():
+        from .models import hf
+
+        cfg, sd = hf.read_hf_dir(src)
+        want, have = hf.args_from_hf_config(cfg), model.args
+        for f in ("dim", "n_layers", "n_heads", "vocab_size"):
+            if getattr(want, f) != getattr(have, f):
+                raise ValueError(f"train.init_weights: {src} has {f}={getattr(want, f)}, the configured model has {getattr(have, f)}")
+        if want.kv_heads != have.kv_heads or want.ffn_hidden != have.ffn_hidden:
+            raise ValueError(f"train.init_weights: {src} has kv_heads={want.kv_heads}, ffn={want.ffn_hidden}; the configured model has "
+                             f"kv_heads={have.kv_heads}, ffn={have.ffn_hidden}")  # fmt: skip
+        hf.load_hf_state_dict(model, sd)
+    elif src.is_file():
+        from .models.llama import from_reference_state_dict
+
+        from_reference_state_dict(model, torch.load(src, map_location="cpu", weights_only=True))
+    else:
+        raise FileNotFoundError(f"train.init_weights: {source} is neither a Hugging Face checkpoint directory nor a state-dict file")
 
 
 def _count_launches(n: int) -> None:

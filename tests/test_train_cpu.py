@@ -304,3 +304,29 @@ def test_resume_from_a_resharded_checkpoint_with_twice_the_ranks(tmp_path):
     assert sorted(after) == [5, 6, 7, 8] and abs(after[5] - before[4]) < 0.5  # continues where it stopped (not from a fresh init: ≈ 8.3 → would jump)
     assert ck.list_steps(tmp_path / "b") == [4, 8]
     assert len(list((tmp_path / "b" / "step_000008").glob("rank_*.pbck"))) == 2
+
+
+def test_training_starts_from_hugging_face_weights(tmp_path):
+    """train.init_weights: the run starts at the imported weights (first loss = the imported model's loss, not a random init's),
+    a different architecture is refused."""
+    pytest.importorskip("safetensors")
+    from prime_b200.models import hf
+    from prime_b200.models.llama import build_model
+    from prime_b200.trainer import Trainer
+
+    donor = build_model("debugmodel", dtype=torch.float32, seed=123)
+    hf.save_hf_dir(donor, tmp_path / "hf")
+    cfg = load_config(BASE + ["--train.init_weights", str(tmp_path / "hf")])
+    t = Trainer(cfg)
+    for (n, a), (_, b) in zip(donor.named_parameters(), t.model.named_parameters()):
+        torch.testing.assert_close(a, b.detach().float(), rtol=0, atol=0, msg=n)
+    assert torch.equal(t.outer.theta0[: 16], t.engine.master[: 16])  # θ₀ is the imported model too
+    t.close()
+    torch.save({k: v.clone() for k, v in __import__("prime_b200.models.llama", fromlist=["x"]).to_reference_state_dict(donor).items()}, tmp_path / "ref.pt")
+    t2 = Trainer(load_config(BASE + ["--train.init_weights", str(tmp_path / "ref.pt")]))
+    torch.testing.assert_close(t2.model.output.detach(), donor.output, rtol=0, atol=0)
+    t2.close()
+    with pytest.raises(ValueError, match="init_weights"):
+        Trainer(load_config(["--name_model", "10M", "--data.seq_length", "32", "--optim.batch_size", "4", "--train.micro_bs", "2", "--train.init_weights", str(tmp_path / "hf")]))
+    with pytest.raises(FileNotFoundError):
+        Trainer(load_config(BASE + ["--train.init_weights", str(tmp_path / "nope")]))
