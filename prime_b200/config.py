@@ -31,6 +31,8 @@ class DataConfig(_Section):
     dataset_name_or_paths: str = ""  # comma-separated token files (.bin / .npy), directories or globs (tools/tokenize_corpus.py writes them)
     token_dtype: Literal["auto", "uint16", "uint32"] = "auto"  # raw .bin files: auto = uint16 up to 65 536 vocabulary entries, else uint32
     shuffle: bool = True  # per-epoch permutation of the sequence windows (seeded by data.seed)
+    # held-out corpus for the periodic validation loss (same formats as dataset_name_or_paths); with data.fake a second synthetic stream
+    eval_dataset_name_or_paths: str = ""
     num_workers: int = 2
     seed: int = 1337
     pin_memory: bool = True
@@ -71,6 +73,8 @@ class TrainConfig(_Section):
     # start from existing weights instead of the random init: a Hugging Face Llama directory (config.json + safetensors) or a .pt
     # state dict in reference naming (models/hf.py, models/llama.py); every rank loads the same file, then training proceeds as usual
     init_weights: str | None = None
+    eval_interval: int = 0  # validation loss every N optimizer steps (0 = never): forward only, mean over all ranks of the world
+    eval_batches: int = 8  # micro-batches per rank and evaluation
 
 
 class CkptConfig(_Section):

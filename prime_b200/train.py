@@ -220,6 +220,12 @@ def train(cfg: Config, *, max_steps: int | None = None) -> dict[str, Any]:
                              f" | outer {last['outer_s'] * 1e3:.1f} ms, {last['outer_bytes'] / 2**20:.1f} MiB on the wire" if r.did_outer else "")  # fmt: skip
                     jsonl.write({"time": time.time(), **last})
                     prom.write(last)
+            if cfg.train.eval_interval and step % cfg.train.eval_interval == 0:
+                val = trainer.evaluate()
+                last["val_loss"] = round(val, 5)
+                if leader:
+                    log.info("step %d validation loss %.4f (%d batches per rank)", step, val, cfg.train.eval_batches)
+                    jsonl.write({"time": time.time(), "step": step, "val_loss": round(val, 5)})
             if ckpt is not None:
                 ckpt.poll()  # publish an asynchronously written checkpoint as soon as every rank's shard is on disk
             if ckpt is not None and cfg.ckpt.interval and step % cfg.ckpt.interval == 0:

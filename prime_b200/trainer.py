@@ -10,6 +10,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -213,6 +214,36 @@ class Trainer:
             did_outer = True
         tokens = self.tokens_per_step * (self.global_workers if self.cfg.mesh.elastic else 1)
         return StepResult(self._loss_acc / self.accum, lr, eng.last_grad_norm, tokens, did_outer)
+
+    # ------------------------------------------------------------------ validation
+    @torch.no_grad()
+    def evaluate(self, batches: int | None = None) -> float:
+        """Mean next-token loss over ``batches`` micro-batches per rank of the held-out stream (``data.eval_dataset_name_or_paths``; with
+        synthetic data a second stream with its own seed), averaged over the ranks of this process world. Forward only, through the
+        same model and kernels as training; the evaluation stream restarts at the same position every time, so values are comparable."""
+        import torch.distributed as dist
+
+        from .data import FakeTokenDataset, MemmapTokenDataset
+
+        cfg, V = self.cfg, self.model.args.vocab_size
+        if cfg.data.eval_dataset_name_or_paths and not cfg.data.fake:
+            ds = MemmapTokenDataset(cfg.data.eval_dataset_name_or_paths, cfg.data.seq_length, self.data_rank % max(1, self.mesh.world.world_size),
+                                    self.mesh.world.world_size, vocab_size=V, shuffle=False)  # fmt: skip
+        else:
+            ds = FakeTokenDataset(V, cfg.data.seq_length, cfg.data.seed + 7919, self.data_rank, self.data_world)
+        was_training = self.model.training
+        self.model.eval()
+        total = torch.zeros(2, dtype=torch.float64, device=self.device)
+        for _ in range(batches or cfg.train.eval_batches):
+            x, y = ds.next_batch(self.micro_bs)
+            tok, tgt = torch.from_numpy(np.ascontiguousarray(x)).to(self.device), torch.from_numpy(np.ascontiguousarray(y)).to(self.device)
+            logits = self.model(tok)
+            total[0] += torch.nn.functional.cross_entropy(logits.float().reshape(-1, logits.shape[-1]), tgt.reshape(-1), reduction="sum").double()
+            total[1] += tgt.numel()
+        if dist.is_initialized() and self.mesh.world.world_size > 1:
+            dist.all_reduce(total)
+        self.model.train(was_training)
+        return float(total[0] / total[1].clamp(min=1))
 
     # ------------------------------------------------------------------ helpers
     def check_health(self) -> None:

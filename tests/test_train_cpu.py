@@ -330,3 +330,18 @@ def test_training_starts_from_hugging_face_weights(tmp_path):
         Trainer(load_config(["--name_model", "10M", "--data.seq_length", "32", "--optim.batch_size", "4", "--train.micro_bs", "2", "--train.init_weights", str(tmp_path / "hf")]))
     with pytest.raises(FileNotFoundError):
         Trainer(load_config(BASE + ["--train.init_weights", str(tmp_path / "nope")]))
+
+
+def test_periodic_validation_loss(tmp_path):
+    """train.eval_interval: a forward-only loss on the held-out stream, logged next to the training metrics, comparable across calls."""
+    from prime_b200.trainer import Trainer
+
+    out = train(load_config(BASE + ["--train.eval_interval", "4", "--train.eval_batches", "2", "--monitor.jsonl_path", str(tmp_path / "log.jsonl"), "--optim.optim.lr", "3e-3"]))
+    rows = [json.loads(x) for x in (tmp_path / "log.jsonl").read_text().splitlines()]
+    vals = [r["val_loss"] for r in rows if "val_loss" in r and "loss" not in r]
+    assert [r["step"] for r in rows if "val_loss" in r and "loss" not in r] == [4, 8] and all(v == v for v in vals) and out["val_loss"] == vals[-1]
+    assert vals[1] < vals[0]  # same held-out batches both times: the model got better on them
+    t = Trainer(load_config(BASE))
+    a, b = t.evaluate(2), t.evaluate(2)
+    assert a == b and abs(a - 7.7) < 1.5  # ln(2048) ≈ 7.6 at init; the stream restarts for every evaluation
+    t.close()
