@@ -187,3 +187,21 @@ def test_eval_perplexity_and_generation_from_a_checkpoint(tmp_path):
     s1 = ev.main(["generate", "--ckpt", step, "--model", "debugmodel", "--prompt-ids", "97,98", "--max-new", "5", "--temperature", "1.5", "--top-k", "5", "--seed", "3", "--device", "cpu"])["ids"]
     s2 = ev.main(["generate", "--ckpt", step, "--model", "debugmodel", "--prompt-ids", "97,98", "--max-new", "5", "--temperature", "1.5", "--top-k", "5", "--seed", "3", "--device", "cpu"])["ids"]
     assert s1 == s2
+
+
+@pytest.mark.slow
+def test_finetune_example_runs_end_to_end_on_cpu(tmp_path):
+    """examples/finetune_from_hf.sh without a checkpoint: tiny donor → tokenise → train.init_weights run with validation → offline
+    perplexity → HF directory that transformers loads."""
+    import os
+    import subprocess
+    from pathlib import Path
+
+    transformers = pytest.importorskip("transformers")
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run(["bash", str(root / "examples" / "finetune_from_hf.sh")], env={**os.environ, "OUT": str(tmp_path), "PYTHONPATH": str(root)},
+                       capture_output=True, text=True, timeout=600)  # fmt: skip
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    assert "validation loss" in r.stderr + r.stdout and '"perplexity"' in r.stdout
+    m = transformers.AutoModelForCausalLM.from_pretrained(tmp_path / "hf_out", torch_dtype=torch.float32)
+    assert m.config.hidden_size == 256 and m.config.num_hidden_layers == 2
