@@ -4,7 +4,6 @@ packages/prime-tunnel/tests, packages/prime-mcp-server/tests)."""
 
 import json
 from datetime import datetime, timezone
-from types import SimpleNamespace
 
 import pytest
 from typer.testing import CliRunner
