@@ -11,8 +11,8 @@ from ..api.deployments import DEPLOYABLE_FROM, UNLOADABLE_FROM, Adapter, Deploym
 from ..core import APIError, Config
 from ..utils.display import DEPLOYMENT_STATUS_COLORS, colorize
 from ..utils.json_help import list_json_help
-from ..utils.time_utils import format_time_ago, parse_dt
 from ..utils.plain import get_console
+from ..utils.time_utils import format_time_ago, parse_dt
 from ._common import OUTPUT_OPT, api, console, emit, fail, handle_errors, make_app, paginate_hint
 
 app = make_app("Deploy trained adapters for inference")
