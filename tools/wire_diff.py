@@ -5,7 +5,7 @@ sends. The request sequences (method, path, query, JSON body) and the outcome of
 
     python tools/wire_diff.py > profiles/wire_diff.json        # exit code 1 on any difference
 
-What it covers: 99 SDK / API-client / MCP-tool calls — sync and async sandbox and evaluation clients, RL, deployments and tunnel clients, the
+What it covers: 104 SDK / API-client / MCP-tool calls — sync and async sandbox and evaluation clients, RL, deployments and tunnel clients, the
 nine MCP tools; sandbox lifecycle, command execution, file transfer, ports, SSH sessions, bulk delete,
 evaluation create / push / finalize / list, pods, disks, availability — and injected failures: 404 / 401 / 402 / 422, a flaky idempotent
 GET (retried), a 503 on a non-idempotent POST (not retried), gateway 502 ``sandbox_not_found``, 408, 409. A failure counts as the same
@@ -376,6 +376,11 @@ async def mcp_part():
     await tcall("mcp_ssh_keys_list", lambda: m.manage_ssh_keys(action="list"))
     await tcall("mcp_ssh_keys_add", lambda: m.manage_ssh_keys(action="add", key_name="k", public_key="ssh-ed25519 AAAA test"))
     await tcall("mcp_ssh_keys_delete", lambda: m.manage_ssh_keys(action="delete", key_id="k1"))
+    await tcall("mcp_ssh_keys_primary", lambda: m.manage_ssh_keys(action="set_primary", key_id="k1"))
+    await tcall("mcp_ssh_keys_bad_action", lambda: m.manage_ssh_keys(action="rotate"))
+    await tcall("mcp_ssh_keys_add_missing", lambda: m.manage_ssh_keys(action="add", key_name="k"))
+    await tcall("mcp_gpu_availability_all", lambda: m.check_gpu_availability())
+    await tcall("mcp_pods_status_empty", lambda: m.get_pods_status([]))
 
 if mcp_mod is not None:
     asyncio.run(mcp_part())
