@@ -45,6 +45,10 @@ def callback(ctx: typer.Context,
     if version_flag:
         typer.echo(f"Prime CLI version: {__version__}")
         raise typer.Exit()
+    try:
+        Config()  # the CLI (not the SDKs) materialises ~/.prime/config.json with the defaults on first use, as the reference does
+    except OSError:
+        pass  # read-only home: every command still works from the environment variables
     if context:
         known = Config(writable=False).list_environments()
         if context.lower() != "production" and context not in known:

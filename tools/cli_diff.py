@@ -73,6 +73,8 @@ COMMANDS: list[list[str]] = [
     ["images", "push", "app:v1", "--context", "ctx"], ["images", "push", "app:v1", "--context", "ctx", "--dockerfile", "ctx/Dockerfile", "--platform", "linux/amd64"],
     ["sandbox", "run", "s1", "--working-dir", "/w", "--env", "A=1", "--timeout", "7", "echo hi"], ["sandbox", "run", "s1", "sleep 1"],
     ["tunnel", "stop", "t1", "--yes"], ["tunnel", "stop", "t1,t2", "--yes"], ["tunnel", "stop", "--all", "--yes"],
+    # the local evaluation path (model validation + billing preflight, then verifiers in a child process) and a hub install
+    ["eval", "run", "owner/env", "-m", "org/m", "-n", "2", "-r", "1", "--skip-upload"], ["env", "install", "owner/env"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
