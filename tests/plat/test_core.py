@@ -347,3 +347,36 @@ def test_unexpected_response_shapes_fail_with_one_line_not_a_traceback(isolated_
     monkeypatch.setattr(reg_mod, "api", lambda *a, **k: Empty(), raising=False)
     r = CliRunner().invoke(app, ["registry", "check-image", "python:3.11-slim"])
     assert r.exit_code == 1 and "Unexpected response from the API" in r.output and "Traceback" not in r.output
+
+
+def test_mcp_tool_schemas_are_the_reference_schemas():
+    """What an MCP client sees from `list_tools`: the nine tools with the same input schemas (parameter types, defaults, required)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    pytest.importorskip("mcp")
+    ref = Path("/root/reference/packages")
+    if not ref.is_dir():
+        pytest.skip("reference tree not mounted")
+    root = Path(__file__).resolve().parents[2]
+    code = (
+        "import asyncio, importlib, json, sys\n"
+        "if sys.argv[1] == 'ours':\n"
+        "    import prime_b200.compat as c; c.install()\n"
+        "m = importlib.import_module('prime_mcp.mcp')\n"
+        "print(json.dumps({t.name: t.inputSchema for t in asyncio.run(m.mcp.list_tools())}, sort_keys=True))\n"
+    )
+    out = {}
+    for arm, path in (("reference", os.pathsep.join(str(ref / d / "src") for d in ("prime-mcp-server", "prime", "prime-sandboxes", "prime-evals", "prime-tunnel"))), ("ours", str(root))):
+        r = subprocess.run([sys.executable, "-c", code, arm], env={**os.environ, "PYTHONPATH": path}, capture_output=True, text=True, cwd="/", timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[arm] = json.loads(r.stdout.strip().splitlines()[-1])
+
+    def shape(schema):
+        props = {k: {a: b for a, b in v.items() if a not in ("title", "description")} for k, v in schema.get("properties", {}).items()}
+        return {"required": sorted(schema.get("required", [])), "properties": props}
+
+    assert sorted(out["ours"]) == sorted(out["reference"]) and len(out["ours"]) == 9
+    for name, schema in out["reference"].items():
+        assert shape(out["ours"][name]) == shape(schema), name
