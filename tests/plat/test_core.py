@@ -380,3 +380,49 @@ def test_mcp_tool_schemas_are_the_reference_schemas():
     assert sorted(out["ours"]) == sorted(out["reference"]) and len(out["ours"]) == 9
     for name, schema in out["reference"].items():
         assert shape(out["ours"][name]) == shape(schema), name
+
+
+def test_every_reference_model_field_exists_with_its_wire_name():
+    """53 pydantic models / 424 fields of the reference SDKs and API clients: each field exists here under the same name, with the
+    same explicit wire alias, and is never stricter (required here while optional there)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    ref = Path("/root/reference/packages")
+    if not ref.is_dir():
+        pytest.skip("reference tree not mounted")
+    root = Path(__file__).resolve().parents[2]
+    code = (
+        "import importlib, inspect, json, sys, pydantic\n"
+        "if sys.argv[1] == 'ours':\n"
+        "    import prime_b200.compat as c; c.install()\n"
+        "out = {}\n"
+        "for mn in ['prime_sandboxes.models', 'prime_evals.models', 'prime_tunnel.models', 'prime_cli.api.pods', 'prime_cli.api.availability',\n"
+        "           'prime_cli.api.disks', 'prime_cli.api.rl', 'prime_cli.api.deployments']:\n"
+        "    m = importlib.import_module(mn)\n"
+        "    for n, v in vars(m).items():\n"
+        "        if inspect.isclass(v) and issubclass(v, pydantic.BaseModel) and v is not pydantic.BaseModel and not n.startswith('_'):\n"
+        "            out[mn + '.' + n] = {fn: [f.alias, f.is_required()] for fn, f in v.model_fields.items()}\n"
+        "print(json.dumps(out))\n"
+    )
+    got = {}
+    for arm, path in (("reference", os.pathsep.join(str(ref / d / "src") for d in ("prime", "prime-sandboxes", "prime-evals", "prime-tunnel", "prime-mcp-server"))), ("ours", str(root))):
+        r = subprocess.run([sys.executable, "-c", code, arm], env={**os.environ, "PYTHONPATH": path}, capture_output=True, text=True, cwd="/", timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        got[arm] = json.loads(r.stdout.strip().splitlines()[-1])
+    problems, n = [], 0
+    for model, fields in got["reference"].items():
+        mine = got["ours"].get(model)
+        if mine is None:
+            problems.append(f"missing model {model}")
+            continue
+        for fn, (alias, required) in fields.items():
+            n += 1
+            if fn not in mine:
+                problems.append(f"missing field {model}.{fn}")
+            elif alias is not None and mine[fn][0] != alias:
+                problems.append(f"wire name of {model}.{fn}: {alias} there, {mine[fn][0]} here")
+            elif mine[fn][1] and not required:
+                problems.append(f"{model}.{fn} is required here, optional there")
+    assert len(got["reference"]) >= 50 and n >= 400 and not problems, problems[:10]
