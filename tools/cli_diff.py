@@ -75,6 +75,8 @@ COMMANDS: list[list[str]] = [
     ["tunnel", "stop", "t1", "--yes"], ["tunnel", "stop", "t1,t2", "--yes"], ["tunnel", "stop", "--all", "--yes"],
     # the local evaluation path (model validation + billing preflight, then verifiers in a child process) and a hub install
     ["eval", "run", "owner/env", "-m", "org/m", "-n", "2", "-r", "1", "--skip-upload"], ["env", "install", "owner/env"],
+    # the browser challenge login, headless: ephemeral RSA key, encrypted API key back, whoami, team choice (EOF → personal)
+    ["login", "--headless"], ["config", "view"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
@@ -195,6 +197,8 @@ def mask(req: dict) -> dict:
     body = req.get("body")
     if isinstance(body, dict) and isinstance(body.get("name"), str):
         req = {**req, "body": {**body, "name": re.sub(r"-[a-z0-9]{4}$", "-XXXX", body["name"])}}
+    if isinstance(body, dict) and "encryptionPublicKey" in body:  # `prime login`: a fresh RSA key pair per run
+        req = {**req, "body": {**body, "encryptionPublicKey": "<ephemeral public key>" if "BEGIN PUBLIC KEY" in str(body["encryptionPublicKey"]) else body["encryptionPublicKey"]}}
     if req.get("path", "").endswith("/versions") and isinstance(body, dict) and "sha256" in body:
         # the source tarball embeds file and gzip timestamps: its digest differs between two runs of the SAME CLI; the content hash
         # (over the source files) and the wheel digest are the comparable identifiers
@@ -264,12 +268,14 @@ def main(stride: int = 1) -> int:
                     files[str(f.relative_to(d))] = "<unreadable>"
             state[arm] = files
 
-        def stable(v):  # expiry stamps of cached gateway tokens differ run to run
+        def stable(v, home):  # expiry stamps of cached gateway tokens differ run to run; paths under the arm's private $HOME → "~"
             if isinstance(v, dict):
-                return {k: stable(x) for k, x in v.items() if k not in ("cached_at", "expires_at", "last_check", "timestamp")}
-            return v
+                return {k: stable(x, home) for k, x in v.items() if k not in ("cached_at", "expires_at", "last_check", "timestamp")}
+            if isinstance(v, list):
+                return [stable(x, home) for x in v]
+            return v.replace(home, "~") if isinstance(v, str) else v
 
-        on_disk_same = stride > 1 or covers(stable(state["ours"]), stable(state["reference"]))
+        on_disk_same = stride > 1 or covers(stable(state["ours"], h2), stable(state["reference"], h1))
         if not on_disk_same:
             diffs.append({"command": "<files under ~/.prime after the run>", "reference": {"exit_code": 0, "requests": [], "json": state["reference"], "stdout_tail": "", "stderr_tail": ""},
                           "ours": {"exit_code": 0, "requests": [], "json": state["ours"], "stdout_tail": "", "stderr_tail": ""}})  # fmt: skip

@@ -125,9 +125,24 @@ def respond(method: str, path: str, host: str):
 FLAKY: dict[str, int] = {}
 
 
+LOGIN: dict[str, str] = {}
+
+
 def scripted_failure(method: str, path: str, query: dict, payload):
     """Failure injection keyed by what the client asks for (both arms ask for the same things): → (status, body) or None."""
     cmd = payload.get("command") if isinstance(payload, dict) else None
+    if path.endswith("/auth_challenge/generate") and isinstance(payload, dict):  # `prime login`: remember the client's ephemeral public key
+        LOGIN["pem"] = payload.get("encryptionPublicKey", "")
+        return 200, {"challenge": "ABCD-1234", "status_auth_token": "status-token"}
+    if path.endswith("/auth_challenge/status"):  # … and hand the new API key back encrypted for it (RSA-OAEP / SHA-256), as the service does
+        import base64
+
+        from cryptography.hazmat.primitives import hashes, serialization
+        from cryptography.hazmat.primitives.asymmetric import padding
+
+        pub = serialization.load_pem_public_key(LOGIN["pem"].encode())
+        blob = pub.encrypt(b"pit_new_api_key", padding.OAEP(mgf=padding.MGF1(algorithm=hashes.SHA256()), algorithm=hashes.SHA256(), label=None))
+        return 200, {"result": base64.b64encode(blob).decode()}
     if path.endswith("/sandbox/missing"):
         return 404, {"detail": "Sandbox not found"}
     if path.endswith("/sandbox/unauth"):
