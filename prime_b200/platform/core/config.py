@@ -224,7 +224,11 @@ class Config:
         }
 
     def reset(self) -> None:
-        self._write(ConfigModel(ssh_key_path=self.default_ssh_key_path()).model_dump())
+        """``prime config reset``: credentials, team, API / frontend URLs, SSH key path and the active context go back to their defaults;
+        who you are (``user_id``), the inference URL and the sharing preference stay (reference: commands/config.py:363-375)."""
+        self.data.update(api_key="", team_id=None, team_name=None, team_role=None, base_url=DEFAULTS["base_url"],
+                         frontend_url=DEFAULTS["frontend_url"], ssh_key_path=self.default_ssh_key_path(), current_environment=BUILTIN_CONTEXT)  # fmt: skip
+        self._write(self.data)
 
     # ------------------------------------------------------------------ named contexts
     CONTEXT_FIELDS = ("api_key", "team_id", "team_name", "team_role", "user_id", "base_url", "frontend_url",
@@ -238,16 +242,23 @@ class Config:
         if clean == BUILTIN_CONTEXT:
             raise ValueError(f"'{BUILTIN_CONTEXT}' is built in and cannot be overwritten")
         self.environments_dir.mkdir(parents=True, exist_ok=True)
-        snapshot = {k: self.data.get(k) for k in self.CONTEXT_FIELDS}
-        self._context_path(clean).write_text(json.dumps(snapshot, indent=2))
+        self._context_path(clean).write_text(json.dumps(self._context_snapshot(), indent=2))
         return clean
+
+    def _context_snapshot(self) -> dict[str, Any]:
+        """What a named context stores: the EFFECTIVE settings — an exported ``PRIME_API_KEY`` / ``PRIME_API_BASE_URL`` is what the user is
+        working with and is what gets saved (reference: core/config.py:244-261); team name / role only when the team is not env-given."""
+        team_from_env = self._env("team_id") is not None
+        return {"api_key": self.api_key, "team_id": self.team_id, "team_name": None if team_from_env else self.team_name,
+                "team_role": None if team_from_env else self.team_role, "user_id": self.user_id, "base_url": self.base_url,
+                "frontend_url": self.frontend_url, "inference_url": self.inference_url,
+                "share_resources_with_team": self.share_resources_with_team}  # fmt: skip
 
     def update_current_environment_file(self) -> None:
         """Keep the active named context in sync with edits made while it is selected."""
         cur = self.current_environment
         if cur != BUILTIN_CONTEXT and self._context_path(cur).exists():
-            snapshot = {k: self.data.get(k) for k in self.CONTEXT_FIELDS}
-            self._context_path(cur).write_text(json.dumps(snapshot, indent=2))
+            self._context_path(cur).write_text(json.dumps(self._context_snapshot(), indent=2))
 
     def list_environments(self) -> list[str]:
         names = {BUILTIN_CONTEXT}

@@ -77,6 +77,10 @@ COMMANDS: list[list[str]] = [
     ["eval", "run", "owner/env", "-m", "org/m", "-n", "2", "-r", "1", "--skip-upload"], ["env", "install", "owner/env"],
     # the browser challenge login, headless: ephemeral RSA key, encrypted API key back, whoami, team choice (EOF → personal)
     ["login", "--headless"], ["config", "view"],
+    # named contexts and account switching: save / use / --context / switch / reset, compared through the files they leave behind
+    ["config", "set-api-key", "k-123"], ["config", "save", "staging"], ["config", "set-base-url", "http://other.invalid"], ["config", "save", "other"], ["config", "envs"],
+    ["config", "use", "staging"], ["config", "view"], ["--context", "other", "config", "view"], ["--context", "nope", "config", "view"], ["switch", "team"],
+    ["switch", "personal"], ["switch", "t1"], ["config", "reset", "--yes"], ["config", "use", "production"], ["config", "envs"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
