@@ -81,6 +81,13 @@ COMMANDS: list[list[str]] = [
     ["config", "set-api-key", "k-123"], ["config", "save", "staging"], ["config", "set-base-url", "http://other.invalid"], ["config", "save", "other"], ["config", "envs"],
     ["config", "use", "staging"], ["config", "view"], ["--context", "other", "config", "view"], ["--context", "nope", "config", "view"], ["switch", "team"],
     ["switch", "personal"], ["switch", "t1"], ["config", "reset", "--yes"], ["config", "use", "production"], ["config", "envs"],
+    # environment secrets / variables, deployments, checkpoints, pushes into an existing evaluation or a training run
+    ["env", "secret", "create", "owner/env", "--name", "TOKEN", "--value", "v", "--description", "d", "-o", "json"], ["env", "secret", "update", "owner/env", "--id", "es1", "--value", "v2"],
+    ["env", "secret", "delete", "owner/env", "--id", "es1", "--yes"], ["env", "secret", "link", "sec1", "owner/env"], ["env", "secret", "unlink", "sec1", "owner/env", "--yes"],
+    ["env", "var", "create", "owner/env", "--name", "VAR", "--value", "1"], ["deployments", "create", "a1", "--yes"], ["deployments", "delete", "a1"],
+    ["rl", "checkpoints", "r1", "-o", "json"], ["rl", "models", "-o", "json"], ["eval", "push", "outputs/evals/gsm8k--org--m/run1", "--run-id", "r1"],
+    ["eval", "push", "outputs/evals/gsm8k--org--m/run1", "--eval", "ev1", "-o", "json"], ["env", "action", "retry", "owner/env", "A1"],
+    ["env", "version", "delete", "owner/env", "aaaaaaaa", "--force"], ["images", "list", "-o", "json"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
