@@ -88,6 +88,8 @@ COMMANDS: list[list[str]] = [
     ["rl", "checkpoints", "r1", "-o", "json"], ["rl", "models", "-o", "json"], ["eval", "push", "outputs/evals/gsm8k--org--m/run1", "--run-id", "r1"],
     ["eval", "push", "outputs/evals/gsm8k--org--m/run1", "--eval", "ev1", "-o", "json"], ["env", "action", "retry", "owner/env", "A1"],
     ["env", "version", "delete", "owner/env", "aaaaaaaa", "--force"], ["images", "list", "-o", "json"],
+    ["config", "set-inference-url", "http://inf.invalid/api/v1"], ["rl", "ls", "-o", "json"], ["sandbox", "ls", "-o", "json"], ["env", "var", "update", "ev1", "owner/env", "--value", "2"],
+    ["env", "var", "delete", "ev1", "owner/env", "--yes"], ["env", "build", "--help"], ["gepa", "run", "--help"], ["lab", "setup", "--help"], ["eval", "tui", "--help"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
