@@ -300,7 +300,7 @@ def get_eval(eval_id: str = typer.Argument(...), output: str = typer.Option("jso
     output_data_as_json(data, console) if output == "json" else print_eval_status(data)
 
 
-@app.command("samples", no_args_is_help=True, epilog=json_output_help({"samples": [{"example_id": "int?", "reward": "float?"}], "total": "int?"}))
+@app.command("samples", epilog=json_output_help({"samples": [{"example_id": "int?", "reward": "float?"}], "total": "int?"}))
 @handle_errors
 def get_samples(eval_id: str = typer.Argument(...), page: int = typer.Option(1, "--page", "-p"), num: int = typer.Option(100, "--num", "-n"),
                 output: str = typer.Option("json", "--output", "-o", help="json|pretty")) -> None:  # fmt: skip

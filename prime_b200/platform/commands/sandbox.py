@@ -98,6 +98,8 @@ def parse_ids(raw: list[str] | None) -> list[str]:
 
 # --------------------------------------------------------------------------------------------------- list / get
 def _list(team_id, status, labels, page, num, all, output) -> None:
+    if num < 1 or page < 1:
+        raise fail("--num and --page must be at least 1")
     # an explicit --status already says which sandboxes are wanted: only the unfiltered default view hides terminated ones
     resp = client().list(team_id=team_id, status=status, labels=labels, page=page, per_page=num, exclude_terminated=(not all and status is None))
     rows = [list_row(s) for s in sort_by_created(resp.sandboxes)]

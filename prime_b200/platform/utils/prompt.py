@@ -71,6 +71,8 @@ def prompt_for_value(prompt_text: str, required: bool = True, hide_input: bool =
     try:
         v = typer.prompt(prompt_text + (" (empty to cancel)" if required else ""), default="", hide_input=hide_input,
                          show_default=False)  # fmt: skip
-    except (KeyboardInterrupt, typer.Abort):
+    except KeyboardInterrupt:
         return None
+    # an EMPTY answer cancels (exit 0); a closed stdin is click's Abort and stays one ("Aborted.", exit 1 — scripts that forgot a flag
+    # must not see success)
     return None if (required and not v) else v

@@ -90,6 +90,11 @@ COMMANDS: list[list[str]] = [
     ["env", "version", "delete", "owner/env", "aaaaaaaa", "--force"], ["images", "list", "-o", "json"],
     ["config", "set-inference-url", "http://inf.invalid/api/v1"], ["rl", "ls", "-o", "json"], ["sandbox", "ls", "-o", "json"], ["env", "var", "update", "ev1", "owner/env", "--value", "2"],
     ["env", "var", "delete", "ev1", "owner/env", "--yes"], ["env", "build", "--help"], ["gepa", "run", "--help"], ["lab", "setup", "--help"], ["eval", "tui", "--help"],
+    # invalid input: bad option values, missing arguments, failed validation, unknown names — same exit codes, and no request before the check
+    ["pods", "list", "-o", "yaml"], ["sandbox", "list", "--page", "0"], ["sandbox", "create"], ["sandbox", "create", "--env", "BAD", "--yes", "img"], ["disks", "create", "--size", "0", "--yes"],
+    ["rl", "list", "--num", "0"], ["env", "list", "--sort", "bogus"], ["env", "version", "delete", "owner/env", "abc"], ["sandbox", "delete"], ["sandbox", "delete", "s1", "--all", "--yes"],
+    ["tunnel", "stop"], ["eval", "push", "/nonexistent"], ["eval", "samples"], ["secret", "create"], ["config", "use", "nope"], ["config", "save", "production"], ["rl", "run", "missing.toml"],
+    ["nosuchcommand"], ["sandbox", "expose", "s1", "8000", "--protocol", "udp"], ["availability", "list", "--regions", "mars"], ["pods", "terminate"], ["deployments", "create"], ["rl", "get"],
     # third batch: flows that read or write local files
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
