@@ -5,7 +5,7 @@ sends. The request sequences (method, path, query, JSON body) and the outcome of
 
     python tools/wire_diff.py > profiles/wire_diff.json        # exit code 1 on any difference
 
-What it covers: 104 SDK / API-client / MCP-tool calls — sync and async sandbox and evaluation clients, RL, deployments and tunnel clients, the
+What it covers: 106 SDK / API-client / MCP-tool calls — sync and async sandbox and evaluation clients, RL, deployments and tunnel clients, the
 nine MCP tools; sandbox lifecycle, command execution, file transfer, ports, SSH sessions, bulk delete,
 evaluation create / push / finalize / list, pods, disks, availability — and injected failures: 404 / 401 / 402 / 422, a flaky idempotent
 GET (retried), a 503 on a non-idempotent POST (not retried), gateway 502 ``sandbox_not_found``, 408, 409. A failure counts as the same
@@ -264,6 +264,12 @@ call("bulk_delete_ids", lambda: c.bulk_delete(sandbox_ids=["s1"]))
 call("bulk_delete_labels", lambda: c.bulk_delete(labels=["a"]))
 call("delete", lambda: c.delete("s1"))
 
+def background():
+    job = c.start_background_job("s1", "sleep 1 && echo done", working_dir="/w", env={"A": "1"})
+    st = c.get_background_job("s1", job)
+    return {"files": [job.stdout_log_file[:9], job.exit_file[-5:]], "completed": st.completed}
+call("background_job", background)
+call("run_background_job", lambda: {"completed": c.run_background_job("s1", "echo hi", timeout=5, poll_interval=1).completed})
 call("err_404", lambda: c.get("missing"))
 call("err_401", lambda: c.get("unauth"))
 call("err_402", lambda: c.get("broke"))
@@ -429,12 +435,13 @@ def covers(ours, ref) -> bool:
 
 
 def normalise(log: list) -> list:
-    """Drop client-generated identifiers so that two runs are comparable."""
+    """Drop client-generated identifiers so that two runs are comparable (request ids; the random id in a background job's file names)."""
     out = []
     for e in log:
         e = dict(e)
         if isinstance(e["body"], dict):
-            e["body"] = {k: v for k, v in e["body"].items() if k not in ("request_id",)}
+            e["body"] = {k: (re.sub(r"job_[0-9a-f]{8}", "job_XXXXXXXX", v) if isinstance(v, str) else v) for k, v in e["body"].items() if k not in ("request_id",)}
+        e["query"] = [[k, re.sub(r"job_[0-9a-f]{8}", "job_XXXXXXXX", v) if isinstance(v, str) else v] for k, v in e.get("query", [])]
         out.append(e)
     return out
 
