@@ -92,3 +92,35 @@ def test_nvlink_counters_decode_and_delta():
             raise RuntimeError("no nvml")
 
     assert NvlinkCounters(0, nvml=Broken()).read() is None
+
+
+def test_native_launchers_validate_their_arguments_before_touching_the_device():
+    """The C-ABI launchers are called with shapes that come from user configs: impossible ones must come back as error codes, on any
+    machine — the checks run before the first CUDA call, so this needs no GPU (the library itself loads wherever libcudart is)."""
+    import ctypes
+
+    from prime_b200.ops import _lib
+
+    try:
+        lib = _lib.load()
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"native library not loadable here: {e}")
+    peers = (ctypes.c_void_p * 8)()
+    pp = _lib.PeerPtrs.of([0])
+    oa = _lib.OuterArgs(0.7, 0.9, 1.0, 1)
+
+    def wgather(n=2, rank=0, M=1024, rows=1024, cols=1024, lda=1024, ldc=1024, ldh=0, b_mn=0, epi=0, H=None):
+        return lib.pb_gemm_wgather(None, peers, n, rank, None, None, None, H, M, rows, cols, lda, ldc, ldh, b_mn, epi, None, None, 1, 0, 64, 0, None, None, 0, 0, None)
+
+    assert wgather(n=0) == -6 and wgather(n=9) == -6 and wgather(rank=2) == -6  # group size / rank out of range
+    assert wgather(rows=1023) == -6 and wgather(cols=1000) == -6  # rows must divide over the ranks, columns come in 64-wide TMA boxes
+    assert wgather(lda=1001) == -1  # 16-byte row pitch
+    assert wgather(epi=1, b_mn=1) == -7 and wgather(epi=3, b_mn=0) == -7  # RoPE / SwiGLU epilogues are forward-only, SwiGLU-backward is dgrad-only
+    assert wgather(epi=2, ldh=1024) == -5  # SwiGLU epilogue without an output for h
+    assert wgather(epi=1) == -3  # RoPE without tables
+    assert wgather(M=128) == -8  # below one CTA-pair tile: the host gathers explicitly instead
+    assert lib.pb_pseudograd_quant(None, None, None, None, 1000, None) == -1  # int8 blocks are 1024 elements
+    assert lib.pb_outer_nesterov(ctypes.byref(pp), ctypes.byref(pp), None, None, None, 1000, ctypes.byref(oa), ctypes.byref(pp), None, None, 1, None, None) == -1
+    assert lib.pb_outer_nesterov(ctypes.byref(pp), ctypes.byref(pp), None, None, None, 1024, ctypes.byref(oa), ctypes.byref(pp), None, None, 0, None, None) == -1  # no bucket table
+    assert lib.pb_outer_nesterov_f32(ctypes.byref(pp), None, None, None, 1001, ctypes.byref(oa), ctypes.byref(pp), None, None, 1, None, None) == -1
+    assert lib.pb_cast_push(None, 1001, ctypes.byref(pp), 0, None) == -1 and lib.pb_cast_push(None, 1024, ctypes.byref(pp), 3, None) == -1
