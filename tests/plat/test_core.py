@@ -280,7 +280,7 @@ def test_compat_every_public_method_of_the_reference_exists_with_its_parameter_n
 
 def test_wire_requests_are_identical_to_the_reference(capsys):
     """tools/wire_diff.py: one script (reference import names) against both implementations and a recording server — the HTTP
-    requests (method, path, query, JSON body, auth header) and the outcomes of 106 SDK / API-client / MCP-tool calls (sync and async), injected failures and
+    requests (method, path, query, JSON body, auth header) and the outcomes of 108 SDK / API-client / MCP-tool calls (sync and async), injected failures and
     their retries included, must not differ."""
     import sys
     from pathlib import Path
@@ -293,7 +293,7 @@ def test_wire_requests_are_identical_to_the_reference(capsys):
 
     rc = wire_diff.main()
     out = json.loads(capsys.readouterr().out)
-    assert rc == 0 and out["calls"] >= 106 and out["requests_reference"] == out["requests_ours"] >= 128
+    assert rc == 0 and out["calls"] >= 108 and out["requests_reference"] == out["requests_ours"] >= 130
     assert out["outcome_differences"] == [] and out["request_differences"] == []
     assert sum(v == "ok" for v in out["outcomes"].values()) >= 90 and out["outcomes"]["gateway_408"] == "raised CommandTimeoutError"
 

@@ -5,7 +5,7 @@ sends. The request sequences (method, path, query, JSON body) and the outcome of
 
     python tools/wire_diff.py > profiles/wire_diff.json        # exit code 1 on any difference
 
-What it covers: 106 SDK / API-client / MCP-tool calls — sync and async sandbox and evaluation clients, RL, deployments and tunnel clients, the
+What it covers: 108 SDK / API-client / MCP-tool calls — sync and async sandbox and evaluation clients, RL, deployments and tunnel clients, the
 nine MCP tools; sandbox lifecycle, command execution, file transfer, ports, SSH sessions, bulk delete,
 evaluation create / push / finalize / list, pods, disks, availability — and injected failures: 404 / 401 / 402 / 422, a flaky idempotent
 GET (retried), a 503 on a non-idempotent POST (not retried), gateway 502 ``sandbox_not_found``, 408, 409. A failure counts as the same
@@ -369,6 +369,30 @@ async def async_part():
     await tc.close()
 
 asyncio.run(async_part())
+
+# Tunnel lifecycle with a stand-in for the frpc binary (a script that keeps a copy of the config it is started with and prints the
+# line both SDKs wait for): register -> 0600 config -> child process -> "connected" -> stop -> delete
+import importlib, stat
+tun_mod = importlib.import_module("prime_tunnel.tunnel")
+fake = os.path.join(tmp, "frpc")
+open(fake, "w").write("#!/bin/sh\ncp \"$2\" \"" + tmp + "/frpc_config_seen.toml\"\necho 'login to server success'\necho 'start proxy success'\nsleep 30\n")
+os.chmod(fake, 0o755)
+tun_mod.get_frpc_path = lambda *a, **k: __import__("pathlib").Path(fake)
+
+async def tunnel_part():
+    from prime_tunnel import Tunnel
+    t = Tunnel(8080, name="web", connection_timeout=10.0)
+    try:
+        url = await t.start()
+        cfg = open(os.path.join(tmp, "frpc_config_seen.toml")).read()
+        lines = [ln for ln in cfg.splitlines() if ln.strip() and not ln.lstrip().startswith("#")]
+        results.append(["tunnel_start", "ok", {"url": url, "tunnel_id": t.tunnel_id, "running": t.is_running, "frpc_config": lines}])
+        await t.stop()
+        results.append(["tunnel_stop", "ok", {"running": t.is_running}])
+    except Exception as e:
+        results.append(["tunnel_start", "raised", [type(e).__name__, str(e)[:300], [k.__name__ for k in type(e).__mro__]]])
+
+asyncio.run(tunnel_part())
 
 # MCP server: the nine tools, called as the plain async functions they are (FastMCP's decorator returns them unchanged)
 try:
