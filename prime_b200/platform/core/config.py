@@ -231,6 +231,11 @@ class Config:
         self._write(self.data)
 
     # ------------------------------------------------------------------ named contexts
+    # the reference's class-level names for the defaults (read by its tunnel / CLI tests and by user code)
+    DEFAULT_BASE_URL = DEFAULTS["base_url"]
+    DEFAULT_FRONTEND_URL = DEFAULTS["frontend_url"]
+    DEFAULT_INFERENCE_URL = DEFAULTS["inference_url"]
+
     CONTEXT_FIELDS = ("api_key", "team_id", "team_name", "team_role", "user_id", "base_url", "frontend_url",
                       "inference_url", "share_resources_with_team")  # fmt: skip
 

@@ -59,7 +59,7 @@ def callback(ctx: typer.Context,
             raise typer.Exit(1)
         os.environ["PRIME_CONTEXT"] = context  # every Config() built by the subcommand sees it
     if ctx.invoked_subcommand is not None and ctx.invoked_subcommand != "upgrade":
-        available, latest = check_for_update(__version__)
+        available, latest = check_for_update()  # no arguments: the installed version is this package's (and tests stub it with a zero-argument callable)
         if available and latest:
             err = get_console(stderr=True)
             err.print(f"[yellow]A new version of prime is available: {latest} (installed: {__version__})[/yellow]")
