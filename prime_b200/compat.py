@@ -30,8 +30,9 @@ _P = "prime_b200.platform"
 ALIASES: dict[str, tuple[str, dict[str, str]]] = {
     "prime_sandboxes": (f"{_P}.sandboxes", {
         "sandbox": f"{_P}.sandboxes.sandbox", "models": f"{_P}.sandboxes.models", "exceptions": f"{_P}.sandboxes.exceptions",
-        "rpc_command_session": f"{_P}.sandboxes.rpc_command_session", "core": f"{_P}.core", "core.client": f"{_P}.core.client",
-        "core.config": f"{_P}.core.config"}),
+        "rpc_command_session": f"{_P}.sandboxes.rpc_command_session", "core": f"{_P}.core", "core.client": f"{_P}.sandboxes.client",
+        "core.config": f"{_P}.core.config", "_proto": f"{_P}.sandboxes.proto", "_proto.command_session": f"{_P}.sandboxes.proto",
+        "_proto.command_session.command_session_pb2": f"{_P}.sandboxes.rpc_schema"}),
     "prime_evals": (f"{_P}.evals", {
         "evals": f"{_P}.evals.evals", "models": f"{_P}.evals.models", "exceptions": f"{_P}.evals.exceptions", "core": f"{_P}.core",
         "core.client": f"{_P}.core.client", "core.config": f"{_P}.core.config"}),

@@ -106,7 +106,7 @@ def list_(
                    f"[{status_color(r['stock_status'], STOCK_COLORS)}]{r['stock_status']}[/]", r["price_per_hour"], r["security"],
                    r["vcpus"], r["memory_gb"], r["disk_gb"]] for r in rows]  # fmt: skip
     emit(output, payload, "Available GPU Resources", cols, table_rows,
-         "\n[bold blue]Deploy one of these:[/bold blue] [green]prime pods create --id <ID>[/green] (interactive setup follows)")  # fmt: skip
+         "\n[bold blue]To deploy a pod with one of these configurations:[/bold blue]\n  [green]prime pods create --id <ID>[/green]   (interactive setup follows)")  # fmt: skip
 
 
 @app.command("disks", epilog=list_json_help("disks", {"id": "str", "provider": "str", "location": "str", "price_per_gb_month": "str"}))
@@ -123,6 +123,6 @@ def disks(
              "price_per_gb_month": f"${d.spec.price_per_unit:.4f}" if d.spec.price_per_unit is not None else "N/A",
              "min_gb": d.spec.min_count, "max_gb": d.spec.max_count, "is_multinode": d.is_multinode} for d in offers]  # fmt: skip
     emit(output, {"disks": rows, "total_count": len(rows), "filters": {"regions": regions, "data_center_id": data_center_id}}, "Available Disks",
-         [("ID", "cyan"), "Provider", "Data center", ("Location", "green"), ("Stock", "yellow"), ("Price/GB", "magenta"), "Min GB", "Max GB", "Multi-node"],
+         [("ID", "cyan"), "Provider", "Data center", ("Location", "green"), ("Stock", "yellow"), ("Price/GB", "magenta"), "Min Size (GB)", "Max Size (GB)", "Multi-node"],
          [[r["id"], r["provider"], r["data_center"], r["location"], r["stock_status"], r["price_per_gb_month"], r["min_gb"], r["max_gb"],
            r["is_multinode"]] for r in rows], "\n[bold blue]Create one:[/bold blue] [green]prime disks create --id <ID> --size <GB>[/green]")  # fmt: skip

@@ -570,3 +570,17 @@ def run_eval_cmd(
         console.print()
         return follow_logs(client, eval_ids[0], poll_interval)
     console.print(f"\n[dim]Follow progress with: prime eval logs {eval_ids[0]} -f[/dim]")
+
+
+# the reference's private spellings of the helpers above — its white-box tests and a few downstream scripts import them by name
+def _create_hosted_evaluations(config: HostedEvalConfig, environment_ids: list[str] | None = None) -> dict[str, Any]:
+    return create_hosted(APIClient(), config, environment_ids)
+
+
+_has_eval_files = has_eval_files
+_validate_eval_path = validate_eval_path
+_load_eval_directory = load_eval_directory
+_push_single_eval = push_single_eval
+_load_hosted_eval_configs = load_hosted_eval_configs
+_print_eval_status = print_eval_status
+_build_hosted_evaluation_payload = hosted_payload

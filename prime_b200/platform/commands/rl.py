@@ -232,8 +232,8 @@ max_tokens = 2048
 
 # [buffer]
 # online_difficulty_filtering = true
-# easy_threshold = 0.9
-# hard_threshold = 0.1
+# easy_threshold = 1.0
+# hard_threshold = 0.0
 
 # [wandb]                       # needs WANDB_API_KEY via -e/--env-file
 # project = "my-project"

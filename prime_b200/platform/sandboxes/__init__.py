@@ -1,6 +1,7 @@
 """Remote code-execution sandbox SDK (sync + async)."""
 
-from ..core.client import APIClient, APIError, APITimeoutError, AsyncAPIClient, PaymentRequiredError, UnauthorizedError  # noqa: F401
+from ..core.client import APIError, APITimeoutError, PaymentRequiredError, UnauthorizedError  # noqa: F401
+from .client import APIClient, AsyncAPIClient  # noqa: F401  (the shared clients with the SDK's retry default)
 from ..core.config import Config  # noqa: F401
 from .exceptions import (  # noqa: F401
     CommandTimeoutError,

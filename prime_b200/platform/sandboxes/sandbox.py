@@ -16,6 +16,7 @@ functions; the sync and async classes only differ in how they perform the reques
 from __future__ import annotations
 
 import asyncio
+import functools
 import json
 import os
 import re
@@ -70,6 +71,20 @@ _ENV_KEY = re.compile(r"[A-Za-z_][A-Za-z0-9_]*\Z")
 NOT_FOUND_HINT = "Sandbox is no longer present on the runtime node. Please create a new sandbox."
 
 
+def __getattr__(name: str):
+    """``sandbox.ConnectClientSync`` / ``sandbox.ConnectClient``: the connectrpc client classes, imported on first use (only VM sandboxes pay
+    for connectrpc + protobuf) yet still module attributes — code that substitutes a fake transport there keeps working."""
+    if name in ("ConnectClientSync", "ConnectClient"):
+        import connectrpc.client
+
+        return getattr(connectrpc.client, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def _rpc_class(name: str):
+    return globals().get(name) or __getattr__(name)
+
+
 def sandboxes_user_agent() -> str:
     return user_agent("prime-b200-sandboxes")
 
@@ -96,6 +111,35 @@ def retryable(exc: BaseException, idempotent: bool) -> bool:
 
 def backoff(attempt: int, lo: float = 1.0, hi: float = 30.0) -> float:
     return max(lo, min(hi, float(2**attempt)))
+
+
+def gateway_retry(idempotent: bool, sleep=None):
+    """Decorator form of the gateway policy: up to ``GATEWAY_ATTEMPTS`` calls, 1 → 30 s exponential back-off between them, retrying only what
+    ``retryable(exc, idempotent)`` allows; the last failure propagates unchanged.  ``sleep`` defaults to ``time.sleep`` looked up at call time."""
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*a, **kw):
+            for attempt in range(GATEWAY_ATTEMPTS):
+                try:
+                    return fn(*a, **kw)
+                except Exception as e:
+                    if attempt + 1 < GATEWAY_ATTEMPTS and retryable(e, idempotent):
+                        (sleep or time.sleep)(backoff(attempt))
+                        continue
+                    raise
+            raise AssertionError("unreachable")
+
+        return wrapper
+
+    return deco
+
+
+# the reference module's names for the two policies and their inputs (prime_sandboxes/sandbox.py:66-109)
+GATEWAY_RETRYABLE_EXCEPTIONS = CONNECT_ERRORS
+RETRYABLE_5XX_STATUSES = RETRYABLE_5XX
+_gateway_retry = gateway_retry(idempotent=True)
+_gateway_post_retry = gateway_retry(idempotent=False)
 
 
 def validate_env_key(key: str) -> str:
@@ -415,18 +459,14 @@ class SandboxClient:
 
     # ---- gateway I/O with the idempotency-aware retry split
     def _gateway(self, method: str, url: str, *, idempotent: bool, headers: dict, timeout: float, **kw) -> httpx.Response:
-        for attempt in range(GATEWAY_ATTEMPTS):
-            try:
-                resp = self._pool().request(method, url, headers=headers, timeout=timeout, **kw)
-                if idempotent and resp.status_code in RETRYABLE_5XX:
-                    resp.raise_for_status()
-                return resp
-            except Exception as e:
-                if attempt + 1 < GATEWAY_ATTEMPTS and retryable(e, idempotent):
-                    self._sleep(backoff(attempt))
-                    continue
-                raise
-        raise AssertionError("unreachable")
+        @gateway_retry(idempotent, sleep=self._sleep)
+        def once() -> httpx.Response:
+            resp = self._pool().request(method, url, headers=headers, timeout=timeout, **kw)
+            if idempotent and resp.status_code in RETRYABLE_5XX:
+                resp.raise_for_status()
+            return resp
+
+        return once()
 
     def _gateway_post(self, url: str, headers: dict, timeout: float, **kw) -> httpx.Response:
         return self._gateway("POST", url, idempotent=False, headers=headers, timeout=timeout, **kw)
@@ -502,14 +542,13 @@ class SandboxClient:
 
     def _execute_command_connect_rpc(self, sandbox_id: str, command: str, auth: dict, working_dir: str | None = None,
                                      env: dict[str, str] | None = None, timeout: int | None = None) -> CommandResponse:  # fmt: skip
-        from connectrpc.client import ConnectClientSync
         from connectrpc.code import Code
         from connectrpc.errors import ConnectError
 
         from .rpc_command_session import START_METHOD, OutputCollector, build_start_request  # protobuf: only VM sandboxes pay for the import
 
         limit = timeout if timeout is not None else DEFAULT_COMMAND_TIMEOUT
-        rpc = ConnectClientSync(gateway_url(auth))
+        rpc = _rpc_class("ConnectClientSync")(gateway_url(auth))
         out = OutputCollector()
         try:
             for ev in rpc.execute_server_stream(request=build_start_request(command, working_dir, env), method=START_METHOD,
@@ -859,14 +898,13 @@ class AsyncSandboxClient:
 
     async def _execute_command_connect_rpc(self, sandbox_id: str, command: str, auth: dict, working_dir: str | None = None,
                                            env: dict[str, str] | None = None, timeout: int | None = None) -> CommandResponse:  # fmt: skip
-        from connectrpc.client import ConnectClient
         from connectrpc.code import Code
         from connectrpc.errors import ConnectError
 
         from .rpc_command_session import START_METHOD, OutputCollector, build_start_request
 
         limit = timeout if timeout is not None else DEFAULT_COMMAND_TIMEOUT
-        rpc = ConnectClient(gateway_url(auth))
+        rpc = _rpc_class("ConnectClient")(gateway_url(auth))
         out = OutputCollector()
         try:
             async for ev in rpc.execute_server_stream(request=build_start_request(command, working_dir, env), method=START_METHOD,
@@ -1097,7 +1135,7 @@ class TemplateClient:
     """Registry credentials + docker image accessibility checks."""
 
     def __init__(self, api_client: APIClient | None = None):
-        self.client = api_client or APIClient(user_agent=sandboxes_user_agent())
+        self.client = api_client or APIClient(user_agent=sandboxes_user_agent(), retry=TRANSPORT_RETRY)
 
     def list_registry_credentials(self) -> list[RegistryCredentialSummary]:
         resp = self.client.request("GET", "/template/registry-credentials")
@@ -1112,7 +1150,7 @@ class TemplateClient:
 
 class AsyncTemplateClient:
     def __init__(self, api_client: AsyncAPIClient | None = None):
-        self.client = api_client or AsyncAPIClient(user_agent=sandboxes_user_agent())
+        self.client = api_client or AsyncAPIClient(user_agent=sandboxes_user_agent(), retry=TRANSPORT_RETRY)
 
     async def aclose(self) -> None:
         await self.client.aclose()

@@ -558,3 +558,6 @@ def run_gepa_passthrough(environment_or_config: str, passthrough_args: list[str]
     else:
         target = prepare_environment(plugin, environment_or_config, env_dir).env_name
     run_command(plugin.build_module_command(plugin.gepa_module, [target, *args]), env=env)
+
+
+_sanitize_help_text = sanitize_help_text  # the reference's private spelling (imported by its tests)
