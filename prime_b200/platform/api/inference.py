@@ -50,7 +50,7 @@ class InferenceClient:
     def __init__(self, api_key: str | None = None, team_id: str | None = None, inference_url: str | None = None,
                  timeout: float | httpx.Timeout | None = None, transport: httpx.BaseTransport | None = None,
                  config: Config | None = None) -> None:  # fmt: skip
-        self.config = config or Config(writable=False)
+        self.config = config or Config()
         self.api_key = api_key or self.config.api_key
         if not self.api_key:
             raise InferenceAPIError("No API key. Run `prime config set-api-key` or set PRIME_API_KEY.")
@@ -86,17 +86,20 @@ class InferenceClient:
 
     def chat_completion(self, payload: dict[str, Any], stream: bool = False, headers: dict[str, str] | None = None):
         url = f"{self.inference_url}/chat/completions"
+        extra = {"headers": headers} if headers else {}
         if not stream:
-            r = self._client.post(url, json=payload, headers=headers)
+            r = self._client.post(url, json=payload, **extra)
             if r.is_error:
                 self._fail("POST", url, r)
             return r.json()
 
         def gen() -> Iterator[dict[str, Any]]:
-            with self._client.stream("POST", url, json=payload, headers=headers) as r:
-                if r.is_error:
-                    r.read()
-                    self._fail("POST", url, r)
+            with self._client.stream("POST", url, json=payload, **extra) as r:
+                try:
+                    r.raise_for_status()
+                except httpx.HTTPStatusError as e:
+                    e.response.read()  # a streamed body is not loaded yet: read it BEFORE the message is formatted from it
+                    self._fail("POST", url, e.response)
                 yield from parse_sse_lines(r.iter_lines())
 
         return gen()

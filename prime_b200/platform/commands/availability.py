@@ -123,6 +123,6 @@ def disks(
              "price_per_gb_month": f"${d.spec.price_per_unit:.4f}" if d.spec.price_per_unit is not None else "N/A",
              "min_gb": d.spec.min_count, "max_gb": d.spec.max_count, "is_multinode": d.is_multinode} for d in offers]  # fmt: skip
     emit(output, {"disks": rows, "total_count": len(rows), "filters": {"regions": regions, "data_center_id": data_center_id}}, "Available Disks",
-         [("ID", "cyan"), "Provider", "Data center", ("Location", "green"), ("Stock", "yellow"), ("Price/GB", "magenta"), "Min Size (GB)", "Max Size (GB)", "Multi-node"],
+         [("ID", "cyan"), "Provider", "Data center", ("Location", "green"), ("Stock", "yellow"), ("Price/GB", "magenta"), "Min Size (GB)", "Max Size (GB)", "Is Multinode"],
          [[r["id"], r["provider"], r["data_center"], r["location"], r["stock_status"], r["price_per_gb_month"], r["min_gb"], r["max_gb"],
-           r["is_multinode"]] for r in rows], "\n[bold blue]Create one:[/bold blue] [green]prime disks create --id <ID> --size <GB>[/green]")  # fmt: skip
+           r["is_multinode"]] for r in rows], "\n[bold blue]To create a disk with one of these configurations:[/bold blue]\n  [green]prime disks create --id <ID> --size <GB>[/green]")  # fmt: skip

@@ -44,7 +44,7 @@ app = make_app("Run and manage evaluations", default_cmd="run")
 
 LOGS_TAIL, LOGS_POLL_S, RUN_POLL_S = 1000, 5.0, 10.0
 DEFAULT_NUM_EXAMPLES, DEFAULT_ROLLOUTS = 5, 3
-RATE_LIMIT_AFTER, RATE_LIMIT_WAIT_S, RETRY_WAIT_S, STATUS_EVERY_POLLS = 3, 30, 10, 6
+RATE_LIMIT_AFTER, RATE_LIMIT_WAIT_S, RETRY_WAIT_S, HOSTED_LOGS_STATUS_UPDATE_EVERY_POLLS = 3, 30, 10, 6
 EXAMPLE = "prime eval run gsm8k -n 10"
 HOSTED_ALLOWED = {"env_id", "env_args", "env_dir_path", "endpoints_path", "endpoint_id", "model", "num_examples", "rollouts_per_example",
                   "timeout_minutes", "allow_sandbox_access", "allow_instances_access", "sampling_args", "api_base_url", "api_key_var", "eval_name"}  # fmt: skip
@@ -229,14 +229,25 @@ def print_eval_status(data: dict[str, Any]) -> None:
         console.print(f"[dim]View: {where}[/dim]")
 
 
-def follow_logs(client: APIClient, eval_id: str, poll_interval: float, sleep=time.sleep) -> None:
-    """Poll logs (diffing the sliding tail window) until the evaluation reaches a terminal status."""
-    console.print(f"[dim]Following logs for {eval_id} (Ctrl+C to stop)...[/dim]\n")
-    shown, errors, polls = "", 0, 0
+def _fetch_eval_status(client: APIClient, eval_id: str) -> dict[str, Any]:
+    return client.get(f"/evaluations/{eval_id}")
+
+
+def _fetch_logs(client: APIClient, eval_id: str) -> str:
+    return client.get(f"/hosted-evaluations/{eval_id}/logs").get("logs") or ""
+
+
+def follow_logs(client: APIClient, eval_id: str, poll_interval: float, sleep=None) -> None:
+    """Poll status + logs (diffing the sliding tail window) until the evaluation reaches a terminal status; every
+    ``HOSTED_LOGS_STATUS_UPDATE_EVERY_POLLS`` polls without a new line, say what the status is so a quiet run does not look hung
+    (reference: commands/evals.py:483-527).  ``sleep`` defaults to ``time.sleep`` looked up at call time."""
+    console.print(f"[dim]Watching logs for evaluation {eval_id}... (Ctrl+C to stop)[/dim]\n")
+    shown, errors, quiet = "", 0, 0
     while True:
+        nap = sleep or time.sleep
         try:
-            data = client.get(f"/evaluations/{eval_id}")
-            logs = clean_logs(client.get(f"/hosted-evaluations/{eval_id}/logs").get("logs") or "")
+            data = _fetch_eval_status(client, eval_id)
+            logs = clean_logs(_fetch_logs(client, eval_id) or "")
             errors = 0
         except APIError as e:
             errors += 1
@@ -244,16 +255,18 @@ def follow_logs(client: APIClient, eval_id: str, poll_interval: float, sleep=tim
                 wait = RATE_LIMIT_WAIT_S if errors >= RATE_LIMIT_AFTER else RETRY_WAIT_S
                 if errors >= RATE_LIMIT_AFTER:
                     console.print(f"[yellow]Rate limited. Waiting {wait}s...[/yellow]")
-                sleep(wait)
+                nap(wait)
                 continue
             if errors >= RATE_LIMIT_AFTER:
                 raise
-            sleep(RETRY_WAIT_S)
+            nap(RETRY_WAIT_S)
             continue
         if logs and logs != shown:
             for ln in get_new_log_lines(shown, logs):
                 console.print(ln, markup=False, highlight=False)
-            shown = logs
+            shown, quiet = logs, 0
+        else:
+            quiet += 1
         raw, st = parse_status(data)
         if st is not None and st.is_terminal:
             console.print()
@@ -261,10 +274,9 @@ def follow_logs(client: APIClient, eval_id: str, poll_interval: float, sleep=tim
             if st is not EvalStatus.COMPLETED:
                 raise typer.Exit(1)
             return
-        polls += 1
-        if not logs and polls % STATUS_EVERY_POLLS == 0:
-            console.print(f"[dim]Status: {raw} (waiting for logs...)[/dim]")
-        sleep(poll_interval)
+        if quiet and quiet % HOSTED_LOGS_STATUS_UPDATE_EVERY_POLLS == 0:
+            console.print(f"[dim]Evaluation status: {raw} (waiting for logs...)[/dim]")
+        nap(poll_interval)
 
 
 # ------------------------------------------------------------------------------------------------- list / get / samples
@@ -284,7 +296,7 @@ def list_evals(output: str = typer.Option("table", "--output", "-o", help="table
     """List evaluations of the active account."""
     if page < 1 or num < 1:
         raise fail("--page and --num must be >= 1")
-    data = EvalsClient(api()).list_evaluations(env_name=env, skip=(page - 1) * num, limit=num, team_id=Config(writable=False).team_id)
+    data = EvalsClient(_client()).list_evaluations(env_name=env, skip=(page - 1) * num, limit=num, team_id=Config().team_id)
     evs = data.get("evaluations", [])
     emit(output, data, f"Evaluations (Total: {data.get('total', len(evs))})",
          [("ID", "cyan"), ("Name", "blue"), ("Model", "green"), "Type", "Status", "Samples", ("Created", "magenta")],
@@ -436,12 +448,21 @@ def tui_cmd(env_dir: Optional[str] = typer.Option(None, "--env-dir", "-e", help=
 def logs_cmd(eval_id: str = typer.Argument(...), tail: int = typer.Option(LOGS_TAIL, "--tail", "-n"), follow: bool = typer.Option(False, "--follow", "-f"),
              poll_interval: float = typer.Option(LOGS_POLL_S, "--poll-interval", help="Seconds between polls with --follow")) -> None:  # fmt: skip
     """Logs of a hosted evaluation."""
-    c = api()
+    _display_logs(eval_id, tail, follow, poll_interval)
+
+
+def _display_logs(eval_id: str, tail: int, follow: bool, poll_interval: float = LOGS_POLL_S) -> None:
+    """What ``eval logs`` and ``eval run --hosted --follow`` both end in (same name and signature as the reference's seam)."""
+    c = _client()
     if follow:
-        return follow_logs(c, eval_id, poll_interval)
+        try:
+            return follow_logs(c, eval_id, poll_interval)
+        except KeyboardInterrupt:  # not a failure: the run goes on server-side
+            console.print("\n[dim]Stopped watching logs. Evaluation continues running.[/dim]")
+            return None
     # status first, then the whole log (the endpoint takes no tail parameter: the last `tail` lines are cut here), then the status line
-    status = c.get(f"/evaluations/{eval_id}")
-    text = clean_logs(c.get(f"/hosted-evaluations/{eval_id}/logs").get("logs") or "")
+    status = _fetch_eval_status(c, eval_id)
+    text = clean_logs(_fetch_logs(c, eval_id) or "")
     if text:
         console.print("\n".join(text.splitlines()[-tail:]), markup=False, highlight=False)
     else:
@@ -541,40 +562,58 @@ def run_eval_cmd(
                         "eval_name": eval_name or t.get("eval_name")})  # fmt: skip
     if follow and len(targets) > 1:
         raise fail("`--follow` is only supported for a single hosted evaluation")
-    client = api()
-    slugs: list[str] = []
-    eval_ids: list[str] = []
+    _shared_client.append(api())
     try:
-        # resolve EVERY environment before anything is submitted: an unknown slug in the last [[eval]] table must not leave the earlier
-        # groups running (the reference resolves in file order first, then submits group by group)
-        resolved_by_target = {id(t): resolve_hosted_environment(client, t["env_id"], t["env_dir_path"], env_path) for t in targets}
-        for group in group_targets(targets):
-            resolved = [resolved_by_target[id(t)] for t in group]
-            t = group[0]
-            cfg = HostedEvalConfig(environment_id=resolved[0][1], inference_model=t["model"], num_examples=t["num_examples"],
-                                   rollouts_per_example=t["rollouts_per_example"], env_args=t.get("env_args"), name=t.get("eval_name"),
-                                   timeout_minutes=t.get("timeout_minutes"), allow_sandbox_access=t["allow_sandbox_access"],
-                                   allow_instances_access=t["allow_instances_access"], custom_secrets=t.get("custom_secrets"),
-                                   sampling_args=t.get("sampling_args"), api_base_url=t.get("api_base_url"), api_key_var=t.get("api_key_var"))  # fmt: skip
-            created = create_hosted(client, cfg, environment_ids=[e for _, e in resolved])
-            slugs += [s for s, _ in resolved]
-            eval_ids += created.get("evaluation_ids") or [created["evaluation_id"]]
-    except APIError as e:
-        console.print(f"[red]Hosted evaluation failed:[/red] {e}")
-        raise typer.Exit(1)
-    console.print("[green]✓ Hosted evaluation started[/green]")
-    for s, e in zip(slugs, eval_ids):
-        url = get_eval_viewer_url(e)
-        console.print(f"[cyan]Environment:[/cyan] {s}  [cyan]Evaluation ID:[/cyan] {e}\n  [link={url}]{url}[/link]")
-    if follow:
-        console.print()
-        return follow_logs(client, eval_ids[0], poll_interval)
-    console.print(f"\n[dim]Follow progress with: prime eval logs {eval_ids[0]} -f[/dim]")
+        slugs: list[str] = []
+        eval_ids: list[str] = []
+        try:
+            # resolve EVERY environment before anything is submitted: an unknown slug in the last [[eval]] table must not leave the earlier
+            # groups running (the reference resolves in file order first, then submits group by group)
+            resolved_by_target = {id(t): _resolve_hosted_environment(t["env_id"], env_dir_path=t["env_dir_path"], env_path=env_path) for t in targets}
+            for group in group_targets(targets):
+                resolved = [resolved_by_target[id(t)] for t in group]
+                t = group[0]
+                cfg = HostedEvalConfig(environment_id=resolved[0][1], inference_model=t["model"], num_examples=t["num_examples"],
+                                       rollouts_per_example=t["rollouts_per_example"], env_args=t.get("env_args"), name=t.get("eval_name"),
+                                       timeout_minutes=t.get("timeout_minutes"), allow_sandbox_access=t["allow_sandbox_access"],
+                                       allow_instances_access=t["allow_instances_access"], custom_secrets=t.get("custom_secrets"),
+                                       sampling_args=t.get("sampling_args"), api_base_url=t.get("api_base_url"), api_key_var=t.get("api_key_var"))  # fmt: skip
+                created = _create_hosted_evaluations(cfg, environment_ids=[e for _, e in resolved])
+                slugs += [s for s, _ in resolved]
+                eval_ids += created.get("evaluation_ids") or [created["evaluation_id"]]
+        except APIError as e:
+            console.print(f"[red]Hosted evaluation failed:[/red] {e}")
+            raise typer.Exit(1)
+        console.print("[green]✓ Hosted evaluation started[/green]")
+        for s, e in zip(slugs, eval_ids):
+            url = get_eval_viewer_url(e)
+            console.print(f"[cyan]Environment:[/cyan] {s}  [cyan]Evaluation ID:[/cyan] {e}\n  [link={url}]{url}[/link]")
+        if len(eval_ids) > 1:  # one greppable line with all of them, in submission order
+            console.print(f"[cyan]Evaluation IDs:[/cyan] {', '.join(eval_ids)}")
+        if follow:
+            console.print()
+            return _display_logs(eval_ids[0], LOGS_TAIL, True, poll_interval)
+        console.print(f"\n[dim]Follow progress with: prime eval logs {eval_ids[0]} -f[/dim]")
+    finally:
+        _shared_client.pop()
 
 
-# the reference's private spellings of the helpers above — its white-box tests and a few downstream scripts import them by name
+# ---- seams: the steps of a hosted run as module-level callables with the reference's names and signatures, looked up at call time, so that
+# a harness (the reference's own tests; a dry-run wrapper) can replace one step.  They share the command's client while it runs.
+_shared_client: list[APIClient] = []
+
+
+def _client() -> APIClient:
+    return _shared_client[-1] if _shared_client else api()
+
+
+def _resolve_hosted_environment(environment: str, env_dir_path: str | None = None, env_path: str | None = None) -> tuple[str, str]:
+    return resolve_hosted_environment(_client(), environment, env_dir_path, env_path)
+
+
 def _create_hosted_evaluations(config: HostedEvalConfig, environment_ids: list[str] | None = None) -> dict[str, Any]:
-    return create_hosted(APIClient(), config, environment_ids)
+    return create_hosted(_client(), config, environment_ids)
+
 
 
 _has_eval_files = has_eval_files

@@ -12,7 +12,7 @@ import click
 import httpx
 import typer
 
-from ..core import APIError, Config, UnauthorizedError
+from ..core import APIClient, APIError, Config, UnauthorizedError  # noqa: F401  (APIClient: the injection point `api()` honours)
 from ..utils.display import colorize
 from ..utils.json_help import list_json_help
 from ._common import OUTPUT_OPT, api, console, emit, fail, handle_errors, make_app

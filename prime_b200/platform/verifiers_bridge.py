@@ -440,22 +440,29 @@ def with_inference_defaults(passthrough: list[str], config: Config) -> tuple[lis
     return args, env, model, base
 
 
-def preflight(model: str, base_url: str, configured_base_url: str, make_client=InferenceClient) -> None:
-    """Against our own inference service only: check the model exists, then one tiny completion to surface 402s early."""
+def preflight(model: str, base_url: str, configured_base_url: str, make_client=None) -> None:
+    """Against our own inference service only, two independent checks, each with its own client and its own time-out handling
+    (reference: verifiers_bridge.py — model validation, then the billing probe): (1) the model exists; (2) one tiny completion, so a
+    402 surfaces now and not after the environment was installed.  A time-out in either is a warning — slow-warming models still run —
+    and does not skip the other.  ``make_client`` defaults to this module's ``InferenceClient`` looked up at call time."""
     if base_url != configured_base_url:
         return
-    client = make_client(timeout=EVAL_PREFLIGHT_TIMEOUT)
-    try:
-        client.retrieve_model(model)
-        client.chat_completion({"model": model, "messages": [{"role": "user", "content": "Reply with OK."}]})
-    except httpx.TimeoutException:
-        console.print(f"[yellow]Timed out during the inference pre-flight for '{model}'.[/yellow] Continuing: some thinking models warm up slowly.")
-    except InferencePaymentRequiredError as e:
-        console.print(f"[red]{e}[/red]")
-        raise typer.Exit(1) from e
-    except InferenceAPIError as e:
-        console.print(f"[red]Invalid model:[/red] {e} \n\n[b]Use 'prime inference models' to see available models.[/b]")
-        raise typer.Exit(1) from e
+    make = make_client or InferenceClient
+
+    def step(what: str, call) -> None:
+        try:
+            call(make(timeout=EVAL_PREFLIGHT_TIMEOUT))
+        except httpx.TimeoutException:
+            console.print(f"[yellow]Timed out during {what} for '{model}'.[/yellow] Continuing: some thinking models warm up slowly.")
+        except InferencePaymentRequiredError as e:
+            console.print(f"[red]{e}[/red]")
+            raise typer.Exit(1) from e
+        except InferenceAPIError as e:
+            console.print(f"[red]Invalid model:[/red] {e} \n\n[b]Use 'prime inference models' to see available models.[/b]")
+            raise typer.Exit(1) from e
+
+    step("model validation", lambda c: c.retrieve_model(model))
+    step("the billing pre-flight", lambda c: c.chat_completion({"model": model, "messages": [{"role": "user", "content": "Reply with OK."}]}))
 
 
 def format_push_command(r: ResolvedEnvironment) -> str:
@@ -488,7 +495,7 @@ def run_eval_tui(env_dir: str | None, outputs_dir: str | None) -> None:
 
 
 def run_eval_passthrough(environment: str, passthrough_args: list[str], *, skip_upload: bool, env_path: str | None) -> None:
-    plugin, config = load_verifiers_prime_plugin(console=console), Config(writable=False)
+    plugin, config = load_verifiers_prime_plugin(console=console), Config()
     _require_key(config)
     args, env, model, base_url = with_inference_defaults(passthrough_args, config)
     preflight(model, base_url, (config.inference_url or "").strip().rstrip("/"))
@@ -499,7 +506,7 @@ def run_eval_passthrough(environment: str, passthrough_args: list[str], *, skip_
         for ref, d in collect_eval_config_envs(Path(environment), env_dir):
             prepare_environment(plugin, ref, d)
     else:
-        resolved = prepare_environment(plugin, environment, env_dir)
+        resolved = _prepare_single_environment(plugin, environment, env_dir)
         target = resolved.env_name
         if resolved.env_display_id:
             args += ["--header", f"{INTERNAL_ENV_DISPLAY_HEADER}: {resolved.env_display_id}"]
@@ -546,7 +553,7 @@ def run_eval_passthrough(environment: str, passthrough_args: list[str], *, skip_
 
 
 def run_gepa_passthrough(environment_or_config: str, passthrough_args: list[str]) -> None:
-    plugin, config = load_verifiers_prime_plugin(console=console), Config(writable=False)
+    plugin, config = load_verifiers_prime_plugin(console=console), Config()
     _require_key(config)
     args, env, _model, _base = with_inference_defaults(passthrough_args, config)
     env_dir = parse_value_option(args, "--env-dir-path", "-p") or DEFAULT_ENV_DIR_PATH
@@ -560,4 +567,6 @@ def run_gepa_passthrough(environment_or_config: str, passthrough_args: list[str]
     run_command(plugin.build_module_command(plugin.gepa_module, [target, *args]), env=env)
 
 
-_sanitize_help_text = sanitize_help_text  # the reference's private spelling (imported by its tests)
+# the reference's private spellings: its tests import the first and replace the second to stop a run after the pre-flight
+_sanitize_help_text = sanitize_help_text
+_prepare_single_environment = prepare_environment

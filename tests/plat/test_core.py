@@ -316,6 +316,30 @@ def test_cli_commands_behave_like_the_reference_cli(capsys):
     assert rc == 0 and out["commands"] >= 20 and out["identical"] == out["commands"] and out["differences"] == [], [d["command"] for d in out["differences"]]
 
 
+@pytest.mark.slow
+def test_the_references_own_test_files_pass_against_this_package(tmp_path):
+    """tools/reference_tests.py: the reference's unmodified test files, collected through the compat aliases, against the same files run
+    on the reference itself.  Quick pass: the tunnel + evals SDK suites (the CLI, sandboxes and MCP suites — 334 more tests — under PRIME_B200_FULL_DIFF;
+    the whole five-package run is profiles/reference_tests.json).  No test the reference passes may fail here."""
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[2]
+    if not Path("/root/reference/packages").is_dir():
+        pytest.skip("reference tree not mounted")
+    sys.path.insert(0, str(root))
+    from tools import reference_tests
+
+    pkgs = list(reference_tests.PACKAGES) if os.environ.get("PRIME_B200_FULL_DIFF") else ["prime-tunnel", "prime-evals"]
+    out = tmp_path / "report.json"
+    assert reference_tests.main(["--packages", *pkgs, "--out", str(out)]) == 0
+    report = json.loads(out.read_text())
+    assert report["total_gaps"] == 0, {p: e["reference_passes_ours_does_not"] for p, e in report["packages"].items()}
+    assert report["total_passed"]["ours"] == report["total_passed"]["reference"] >= 21
+    for p in pkgs:
+        assert report["packages"][p]["ours"]["counts"] == report["packages"][p]["reference"]["counts"]
+
+
 def test_plain_mode_tables_carry_no_markup():
     """`--plain` is the mode for scripts and agents: a coloured status cell must come out as the bare word."""
     from prime_b200.platform.utils.display import build_table, colorize
