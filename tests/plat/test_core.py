@@ -340,6 +340,31 @@ def test_the_references_own_test_files_pass_against_this_package(tmp_path):
         assert report["packages"][p]["ours"]["counts"] == report["packages"][p]["reference"]["counts"]
 
 
+@pytest.mark.slow
+def test_the_references_example_programs_run_unchanged_on_this_package(tmp_path):
+    """tools/run_reference_examples.py: /root/reference/examples/*.py, unmodified, with `prime_sandboxes` resolving to this package, against
+    a local sandbox service that really runs the commands — next to the same script on the reference.  Quick pass: the two short demos
+    (all six, including the 50-sandbox high-volume one, under PRIME_B200_FULL_DIFF; the whole run is profiles/reference_examples.json)."""
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[2]
+    if not Path("/root/reference/examples").is_dir():
+        pytest.skip("reference tree not mounted")
+    sys.path.insert(0, str(root))
+    from tools import run_reference_examples as rre
+
+    only = [] if os.environ.get("PRIME_B200_FULL_DIFF") else ["--only", "sandbox_demo", "sandbox_file_operations"]
+    out = tmp_path / "examples.json"
+    assert rre.main([*only, "--out", str(out)]) == 0
+    report = json.loads(out.read_text())
+    assert report["all_ok"] and len(report["examples"]) >= 2
+    for name, e in report["examples"].items():
+        assert e["same_exit"] and e["ours"]["exit"] == 0, (name, e)
+        assert e["same_route_multiset"] and e["ours"]["requests"] == e["reference"]["requests"], (name, e)
+        assert e["ours"]["sandboxes_left_running"] == 0, (name, e)
+
+
 def test_plain_mode_tables_carry_no_markup():
     """`--plain` is the mode for scripts and agents: a coloured status cell must come out as the bare word."""
     from prime_b200.platform.utils.display import build_table, colorize
