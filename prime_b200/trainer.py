@@ -50,6 +50,7 @@ class Trainer:
         dtype = torch.bfloat16 if cuda else torch.float32
         overrides = dict(model_overrides or {})
         overrides.setdefault("max_seq_len", max(cfg.data.seq_length, 128))
+        self.memory_plan = self._plan_memory(cfg, mesh, overrides) if cuda else None  # refuse what cannot fit BEFORE allocating
         # identical init on every rank (same seed) — workers start from the same θ₀
         self.model: Transformer = build_model(cfg.name_model, cfg.type_model, device=self.device, dtype=dtype, seed=cfg.seed, **overrides)
         if cfg.train.init_weights:
@@ -214,6 +215,27 @@ class Trainer:
             did_outer = True
         tokens = self.tokens_per_step * (self.global_workers if self.cfg.mesh.elastic else 1)
         return StepResult(self._loss_acc / self.accum, lr, eng.last_grad_norm, tokens, did_outer)
+
+    # ------------------------------------------------------------------ memory budget
+    @staticmethod
+    def _plan_memory(cfg: Config, mesh: Mesh, overrides: dict, capacity: int | None = None):
+        """Per-GPU HBM budget of this configuration (``utils/memory_plan.py``). Raises ``MemoryPlanError`` when model + optimizer state
+        alone exceed the device — every rank computes the same numbers, so all of them refuse together instead of one dying in
+        ``cudaMalloc`` while its peers wait in the heap handle exchange. Anything else that goes wrong in here is logged, not fatal."""
+        from .utils import memory_plan as mp
+        from .utils.logging import get_logger
+
+        log = get_logger(mesh.worker_id, mesh.world.rank)
+        try:
+            if capacity is None:
+                capacity = int(torch.cuda.get_device_properties(mesh.device).total_memory)
+            plan = mp.plan_from_config(cfg, mesh.world.world_size, capacity=capacity, fsdp_size=mesh.fsdp_size,
+                                       model_overrides={k: v for k, v in overrides.items() if k != "max_seq_len"})  # fmt: skip
+        except Exception as e:  # noqa: BLE001 — the plan is advice; never let a bug in it stop a run that would have fitted
+            log.warning("memory plan skipped: %s", e)
+            return None
+        mp.check(plan, log)
+        return plan
 
     # ------------------------------------------------------------------ validation
     @torch.no_grad()
