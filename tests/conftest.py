@@ -9,6 +9,9 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 os.environ.setdefault("PRIME_DISABLE_VERSION_CHECK", "1")
+# rich reads COLUMNS / LINES when a Console is CONSTRUCTED (the package's consoles are module-level), so a narrow terminal exported by
+# the caller (or by pytest-xdist: 80 × 24) would wrap the tables the CLI tests read. Pin the size before anything imports the package.
+os.environ["COLUMNS"], os.environ["LINES"] = "200", "50"
 
 
 def pytest_configure(config):
