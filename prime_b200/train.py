@@ -221,7 +221,9 @@ def train(cfg: Config, *, max_steps: int | None = None) -> dict[str, Any]:
                     jsonl.write({"time": time.time(), **last})
                     prom.write(last)
             if cfg.train.eval_interval and step % cfg.train.eval_interval == 0:
-                val = trainer.evaluate()
+                t_eval = time.perf_counter()
+                val = trainer.evaluate()  # ends in a device→host read, so the wall time below covers the whole pass
+                timer.exclude(time.perf_counter() - t_eval)  # tokens/s and MFU of the next log line are training only
                 last["val_loss"] = round(val, 5)
                 if leader:
                     log.info("step %d validation loss %.4f (%d batches per rank)", step, val, cfg.train.eval_batches)

@@ -104,3 +104,7 @@ class StepTimer:
         now = time.perf_counter()
         dt, self.t = now - self.t, now
         return dt
+
+    def exclude(self, seconds: float) -> None:
+        """Take ``seconds`` of non-training work (a validation pass) out of the lap in progress."""
+        self.t += max(0.0, seconds)

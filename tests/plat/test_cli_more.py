@@ -170,3 +170,19 @@ def test_eval_hosted_config_expansion(tmp_path):
     for bad in ("[1]", "{nope"):
         with pytest.raises(Exception):
             evals_mod.parse_json_object_option(bad, "--x")
+
+
+def test_shipped_eval_results_sample_is_a_pushable_directory():
+    """examples/eval_results_sample/ (this repo's counterpart of the reference's examples/verifiers_example/): the loader takes it as is,
+    its metadata agrees with its rows, and the hub payload keeps every row."""
+    from pathlib import Path
+
+    from prime_b200.platform.utils import eval_push as ep
+
+    d = Path(__file__).resolve().parents[2] / "examples" / "eval_results_sample"
+    assert evals_mod.has_eval_files(d) and evals_mod.validate_eval_path(str(d)) == d
+    meta = json.loads((d / "metadata.json").read_text())
+    rows = ep.load_results_jsonl(d / "results.jsonl")
+    assert len(rows) == meta["num_examples"] * meta["rollouts_per_example"]
+    assert abs(sum(r["reward"] for r in rows) / len(rows) - meta["avg_reward"]) < 1e-3
+    assert len(ep.to_hub_samples(rows)) == len(rows)

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -99,6 +100,7 @@ COMMANDS: list[list[str]] = [
     ["rl", "run", "rl.toml"], ["rl", "run", "rl.toml", "-e", "WANDB_MODE=offline", "-o", "json"], ["rl", "init", "template.toml"],
     ["sandbox", "upload", "s1", "a.txt", "/tmp/a.txt"], ["sandbox", "download", "s1", "/tmp/a.txt", "got.txt"],
     ["eval", "push", "outputs/evals/gsm8k--org--m/run1", "--env", "owner/env"], ["eval", "push", "--env", "owner/env", "-o", "json"],
+    ["eval", "push", "verifiers_example", "--env", "owner/env"], ["eval", "push", "verifiers_example", "-o", "json"],
 ]  # fmt: skip
 
 
@@ -131,6 +133,9 @@ def prepare_files(home: Path) -> None:
     (home / "ctx" / "app.py").write_text("print(1)\n")
     (home / "evals.toml").write_text('model = "org/m"\nnum_examples = 5\nrollouts_per_example = 2\n\n[[eval]]\nenv_id = "owner/env"\n\n[[eval]]\nenv_id = "owner/env2"\nnum_examples = 7\n')
     make_env_project(home / "myenv")
+    sample = Path(os.environ.get("PRIME_REFERENCE_ROOT", "/root/reference")) / "examples" / "verifiers_example"
+    if sample.is_dir():  # the reference's own verifiers-format sample, pushed as it ships
+        shutil.copytree(sample, home / "verifiers_example")
     run = home / "outputs" / "evals" / "gsm8k--org--m" / "run1"
     run.mkdir(parents=True)
     (run / "metadata.json").write_text(json.dumps({"env_id": "gsm8k", "env": "gsm8k", "model": "org/m", "num_examples": 2, "rollouts_per_example": 1,
