@@ -724,6 +724,8 @@ class SandboxClient:
             except httpx.HTTPStatusError as e:
                 if e.response.status_code == 409 and self._should_retry_409(sandbox_id, e, attempt):
                     continue
+                if e.response.status_code == 404:  # same message as any other failed download, but a class callers can tell apart
+                    raise SandboxFileNotFoundError(f"Download failed: {http_detail(e)}") from e
                 raise APIError(f"Download failed: {http_detail(e)}") from e
             except httpx.RequestError as e:
                 raise APIError(f"Download failed: {request_detail(e)}") from e
@@ -1084,6 +1086,8 @@ class AsyncSandboxClient:
             except httpx.HTTPStatusError as e:
                 if e.response.status_code == 409 and await self._should_retry_409(sandbox_id, e, attempt):
                     continue
+                if e.response.status_code == 404:  # same message as any other failed download, but a class callers can tell apart
+                    raise SandboxFileNotFoundError(f"Download failed: {http_detail(e)}") from e
                 raise APIError(f"Download failed: {http_detail(e)}") from e
             except httpx.RequestError as e:
                 raise APIError(f"Download failed: {request_detail(e)}") from e

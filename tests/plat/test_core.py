@@ -300,7 +300,7 @@ def test_wire_requests_are_identical_to_the_reference(capsys):
 
 @pytest.mark.slow
 def test_cli_commands_behave_like_the_reference_cli(capsys):
-    """tools/cli_diff.py: ``prime …`` command lines (every sixth of the 195 in the quick pass) through both CLIs against the recording server — same exit codes, same HTTP
+    """tools/cli_diff.py: ``prime …`` command lines (every sixth of the 197 in the quick pass) through both CLIs against the recording server — same exit codes, same HTTP
     requests, and every key / value of the reference's ``--output json`` present in ours."""
     import sys
     from pathlib import Path
@@ -311,7 +311,7 @@ def test_cli_commands_behave_like_the_reference_cli(capsys):
     sys.path.insert(0, str(root))
     from tools import cli_diff
 
-    rc = cli_diff.main(stride=1 if os.environ.get("PRIME_B200_FULL_DIFF") else 6)  # the full 195-command run is profiles/cli_diff.json
+    rc = cli_diff.main(stride=1 if os.environ.get("PRIME_B200_FULL_DIFF") else 6)  # the full 197-command run is profiles/cli_diff.json
     out = json.loads(capsys.readouterr().out)
     assert rc == 0 and out["commands"] >= 20 and out["identical"] == out["commands"] and out["differences"] == [], [d["command"] for d in out["differences"]]
 

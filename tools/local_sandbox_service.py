@@ -99,7 +99,9 @@ class Sandbox:
         if not cwd.is_dir():
             return 200, {"stdout": "", "stderr": f"bash: cd: {working_dir}: No such file or directory\n", "exit_code": 1}
         full_env = {**os.environ, "HOME": str(self.root / "sandbox-workspace"), "SANDBOX_ID": self.id, "SANDBOX_NAME": str(self.body.get("name", "")),
-                    **{k: str(v) for k, v in (self.body.get("environment_vars") or {}).items()}, **{k: str(v) for k, v in (env or {}).items()}}  # fmt: skip
+                    **{k: str(v) for k, v in (self.body.get("environment_vars") or {}).items()},
+                    **{k: str(v) for k, v in (self.body.get("secrets") or {}).items()},  # injected like variables, never echoed in the record
+                    **{k: str(v) for k, v in (env or {}).items()}}  # fmt: skip
         for k in [k for k in full_env if k.startswith("PRIME_")]:
             del full_env[k]
         self.log.append(f"[{now()}] exec: {command[:200]}")
