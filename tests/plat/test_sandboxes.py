@@ -260,6 +260,46 @@ def test_read_file_404(isolated_home):
         c.read_file("s1", "/nope")
 
 
+def test_download_of_a_missing_file_is_a_file_not_found_error_with_the_download_message(isolated_home, tmp_path):
+    """404 on download: the reference raises a bare APIError("Download failed: …"); here the same message on SandboxFileNotFoundError (an
+    APIError subclass — `except APIError` keeps working), so a caller can tell a missing file from a broken gateway. 500 stays APIError."""
+    c, _ = make_client(isolated_home, gateway=lambda *a, **k: resp(404, {"detail": "file not found: /nope"}, method="GET"))
+    with pytest.raises(SandboxFileNotFoundError, match="Download failed: HTTP 404") as e:
+        c.download_file("s1", "/nope", str(tmp_path / "x"))
+    assert isinstance(e.value, APIError) and not (tmp_path / "x").exists()
+    c, _ = make_client(isolated_home, gateway=lambda *a, **k: resp(500, {}, method="GET"))
+    with pytest.raises(APIError) as e:
+        c.download_file("s1", "/nope", str(tmp_path / "x"))
+    assert not isinstance(e.value, SandboxFileNotFoundError)
+
+
+@pytest.mark.anyio
+async def test_async_download_of_a_missing_file(isolated_home, tmp_path):
+    from prime_b200.platform.sandboxes import AsyncSandboxClient
+
+    class FakeAsyncAPI:
+        def __init__(self):
+            from prime_b200.platform.core import Config
+
+            self.config = Config(writable=False)
+
+        async def request(self, method, endpoint, params=None, json=None, timeout=None):
+            return dict(AUTH)
+
+        async def aclose(self):
+            pass
+
+    c = AsyncSandboxClient(api_client=FakeAsyncAPI())
+
+    async def gw(method, url, *, idempotent, headers, timeout, **kw):
+        return resp(404, {"detail": "file not found"}, method="GET")
+
+    c._gateway = gw
+    with pytest.raises(SandboxFileNotFoundError, match="Download failed"):
+        await c.download_file("s1", "/nope", str(tmp_path / "x"))
+    await c.aclose()
+
+
 def test_wait_for_creation_failure_classification(isolated_home):
     sbx = {"id": "s1", "name": "n", "dockerImage": "i", "cpuCores": 1, "memoryGB": 1, "diskSizeGB": 1, "diskMountPath": "/", "gpuCount": 0,
            "status": "ERROR", "timeoutMinutes": 1, "createdAt": FUTURE, "updatedAt": FUTURE, "errorType": "IMAGE_PULL_FAILED",
