@@ -263,9 +263,16 @@ class CheckpointManager:
         if failed:  # every rank raises together: nobody is left waiting in a barrier
             cause = h.error[0] if h.error else None
             raise RuntimeError(f"checkpoint step {h.step} failed on {'this rank' if h.error else 'another rank'}") from cause
+        publish_error: BaseException | None = None
         if self.rank == 0:
-            self._publish(h.step, self._pending_meta)
-        self._barrier()
+            try:
+                self._publish(h.step, self._pending_meta)
+            except BaseException as e:  # disk full, directory removed under us, …: tell the others instead of leaving them in a barrier
+                publish_error = e
+        # doubles as the barrier that used to follow the publish: nobody returns before rank 0 has renamed the directory (or failed to)
+        _, failed = self._status(True, publish_error is not None)
+        if failed:
+            raise RuntimeError(f"checkpoint step {h.step}: every shard was written but rank 0 could not publish the directory") from publish_error
 
     def poll(self) -> bool:
         """Call once per training step on every rank: publishes the asynchronously written checkpoint as soon as ALL shards are on
