@@ -223,6 +223,19 @@ def main() -> None:
     e2e_ms, e2e_host_s, _ = run_region(K, read_loss=True)
     clocks = sampler.finish() if rank == 0 else {}
     trainer.check_health()
+    memory = None
+    try:  # the start-up memory plan next to what torch's allocator actually peaked at (before the B0 arm allocates anything); never fatal
+        plan = getattr(trainer, "memory_plan", None)
+        if plan is not None:
+            gb = 1e9
+            memory = {"planned_total_gb": round(plan.total_bytes / gb, 2), "planned_state_gb": round(plan.state_bytes / gb, 2),
+                      "planned_heap_gb": round(plan.heap_bytes / gb, 2),
+                      "planned_torch_gb": round(sum(r.nbytes for r in plan.rows if r.where == "torch") / gb, 2),
+                      "torch_peak_gb": round(torch.cuda.max_memory_allocated() / gb, 2),
+                      "heap_gb": round(getattr(trainer.heap, "nbytes", 0) / gb, 2) if trainer.heap is not None else 0.0,
+                      "capacity_gb": round(plan.capacity / gb, 1)}  # fmt: skip
+    except Exception:  # noqa: BLE001
+        memory = None
 
     tokens = trainer.tokens_per_step * K
     value = tokens / (dev_ms / 1e3)
@@ -315,6 +328,7 @@ def main() -> None:
             },
             "gpu_launches": launches,
             "nvlink": NvlinkCounters.delta(nvl0, nvl1, K),
+            "memory": memory,
             "losses_e2e_region": losses,
             "outer_allreduce": outer_info,
             "outer_allreduce_GBps": outer_info["GBps"] if outer_info else None,
