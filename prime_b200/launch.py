@@ -449,6 +449,24 @@ def create_run(train_args: list[str], *, name: str | None, gpus: int, workers: i
     return Run(path)
 
 
+def preflight_memory(train_args: list[str], ranks_per_worker: int) -> None:
+    """``run --gpus N``: the per-GPU memory plan of the configuration (``utils/memory_plan.py``) before the supervisor and N ranks are
+    started. A plan whose exact part exceeds the device ends the command with the table; a configuration the planner cannot read is
+    left to the workers (they print the real validation error); ``PB_SKIP_MEMORY_CHECK=1`` skips the refusal."""
+    from .utils import memory_plan as mp
+
+    try:
+        from .config import load_config
+
+        plan = mp.plan_from_config(load_config(train_args), ranks_per_worker)
+    except BaseException:  # noqa: BLE001 — SystemExit from the config loader included: not this function's error to report
+        return
+    try:
+        mp.check(plan)
+    except mp.MemoryPlanError as e:
+        raise SystemExit(str(e)) from None
+
+
 def stop_run(run: Run, *, force: bool = False, wait_s: float = 120.0) -> dict[str, Any]:
     st = run.status()
     if st["state"] not in ACTIVE:
@@ -569,6 +587,8 @@ def main(argv: Sequence[str] | None = None) -> int:
         bad = [e for e in a.env if "=" not in e]
         if bad:
             raise SystemExit(f"--env wants KEY=VALUE, got {bad[0]!r}")
+        if a.gpus > 0:
+            preflight_memory(targs, a.gpus)  # refuse what cannot fit a GPU before any process is started
         run = create_run(targs, name=a.name, gpus=a.gpus, workers=a.workers, elastic=a.elastic, respawn=a.respawn, grace_s=a.grace,
                          env=dict(e.split("=", 1) for e in a.env))  # fmt: skip
         spawn_supervisor(run, resume=False)

@@ -59,6 +59,19 @@ def test_worker_command_injects_paths_once(runs):
     assert launch.worker_command(solo.spec, solo, "w0", 1, resume=False)[1:3] == ["-m", "prime_b200.train"]
 
 
+def test_run_refuses_a_configuration_that_cannot_fit_before_starting_anything(runs, monkeypatch):
+    """`run --gpus 8` with llama2/70B: model + optimizer state alone exceed a 180 GB part → the command ends with the memory table and
+    no run directory, no supervisor, no ranks. A configuration the planner cannot read is not this check's business."""
+    with pytest.raises(SystemExit) as e:
+        launch.main(["run", "--gpus", "8", "--detach", "--", "--name_model", "70B", "--data.seq_length", "4096", "--train.micro_bs", "1"])
+    assert "cannot fit a 180 GB GPU" in str(e.value) and "fp32 main_grad" in str(e.value)
+    assert list(launch.iter_runs()) == []
+    launch.preflight_memory(["--name_model", "7B", "--data.seq_length", "4096", "--train.micro_bs", "1"], 8)  # fits: no exception
+    launch.preflight_memory(["--no_such_key", "1"], 8)  # unreadable: left to the workers
+    monkeypatch.setenv("PB_SKIP_MEMORY_CHECK", "1")
+    launch.preflight_memory(["--name_model", "70B"], 8)  # explicit override: no refusal
+
+
 def test_run_then_inspect(runs, capsys):
     assert launch.main(["run", "--detach", "--name", "quick", CFG, "--optim.total_steps", "6"]) == 0
     rid = json.loads(capsys.readouterr().out)["run"]
